@@ -1,0 +1,178 @@
+/*
+ * mcb200.h — C-ABI of libmcb200.so: the B200 (sm_100a) hot path of
+ * AnishDelft/ModelCompression (pruned YOLOv2-VOC forward, pruning masks, region decode + NMS).
+ *
+ * The reference has no FFI layer: its hot path is PyTorch/NumPy library calls made from Python
+ * (SURVEY.md §8b).  Each entry point below names the reference call site it replaces
+ * (paths under the reference repo root).  The Python package `modelcompression_b200` binds these
+ * with ctypes and re-exposes the reference's own function/class names.
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller; h_* is a HOST pointer.
+ *   - the library never allocates or frees device memory; scratch is passed as (d_ws, ws_bytes)
+ *     and sized by the matching mc_workspace_bytes_* function.
+ *   - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on it.
+ *   - return 0 on success; <0 on error: -1 bad argument, -2 unsupported shape,
+ *     -3 workspace too small, -(1000+cudaError_t) CUDA failure.
+ *     mc_last_error_string() gives the thread-local message for the last failure.
+ *   - sm_100a only.  There is no CPU fallback.
+ */
+#ifndef MCB200_H_
+#define MCB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCB200_VERSION 100
+#define MC_MAX_SEGMENTS 64 /* max tensors per multi-tensor launch (YOLOv2-VOC has 23 conv weights) */
+
+int mc_version(void);
+const char* mc_last_error_string(void);
+/* 1 if the current device is compute capability 10.x, else 0 (or <0 on CUDA error). */
+int mc_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Magnitude (weight) pruner — replaces src/pruning/weightPruning/methods.py:9-26 (weight_prune):
+ *   all_weights = concat(|p| for p in params if p.dim()!=1); thr = np.percentile(all_weights, perc)
+ *   mask = (|p| > thr).float()
+ * and the apply half of MaskedConv2d.set_mask (src/pruning/weightPruning/layers.py:41-47).
+ * -------------------------------------------------------------------------------------------- */
+
+/* Exact order statistics of |w| over `nseg` fp32 tensors (n = sum of h_sizes):
+ *   a = sorted(|w|)[k], b = sorted(|w|)[min(k+1, n-1)]
+ *   d_out[0] = thr = NumPy's _lerp(a, b, gamma) in float32 (gamma==0 -> a); d_out[1] = a; d_out[2] = b.
+ * k and gamma are the data-independent "virtual index" pieces of np.percentile, computed by the host
+ * (modelcompression_b200/pruning/weightPruning/methods.py).  Radix select on the fp32 bit pattern of |w|
+ * (monotone as uint32), so the result is bit-exact.                                                    */
+int mc_kth_abs_select(const float* const* h_seg_ptrs, const int64_t* h_seg_sizes, int nseg,
+                      int64_t k, float gamma, float* d_out3,
+                      void* d_ws, size_t ws_bytes, void* stream);
+size_t mc_workspace_bytes_kth_abs_select(int64_t n_total);
+
+/* mask[i] = (|w[i]| > *d_thr) ? 1.f : 0.f for every segment; if apply!=0 also w[i] *= mask[i]
+ * (set_mask).  h_mask_ptrs may be NULL when apply!=0 (apply only).                                  */
+int mc_mask_apply_gt(float* const* h_w_ptrs, float* const* h_mask_ptrs, const int64_t* h_seg_sizes,
+                     int nseg, const float* d_thr, int apply, void* stream);
+
+/* w[i] *= mask[i] for every segment — MaskedConv2d.set_mask, layers.py:46.                          */
+int mc_apply_masks(float* const* h_w_ptrs, const float* const* h_mask_ptrs,
+                   const int64_t* h_seg_sizes, int nseg, void* stream);
+
+/* Counts exact zeros per segment into d_counts[nseg] (int64) — prune_rate, utils.py:59-93.          */
+int mc_count_zeros(const float* const* h_w_ptrs, const int64_t* h_seg_sizes, int nseg,
+                   int64_t* d_counts, void* stream);
+
+/* d_out[s] = sum_i w[i] * |mask[i] - 1| per segment, fp64 accumulation — are_masks_consistent,
+ * utils.py:122-133 (the reference only tests the total against 0).                                  */
+int mc_masked_residual(const float* const* h_w_ptrs, const float* const* h_mask_ptrs,
+                       const int64_t* h_seg_sizes, int nseg, double* d_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Filter pruner — replaces methods.py:28-78 (quick_filter_prune).
+ * Layer l has weight [O_l, C_l, kh_l, kw_l] fp32, contiguous.
+ * -------------------------------------------------------------------------------------------- */
+
+/* Step 1 (methods.py:43-44 / 64-65): d_values[off_l + o] = (sum_{c,h,w} w^2) / (C*kh*kw) in float32, with
+ * NumPy's exact summation order (sequential over c, then h, then w for kh*kw>1; pairwise over c for 1x1).
+ * Step 2 (methods.py:46-51): v /= sqrt(pairwise_sum(v^2)); v /= max(v), per layer, float32.
+ * off_l = sum of O of the previous layers.                                                           */
+int mc_filter_values(const float* const* h_w_ptrs, const int* h_O, const int* h_C, const int* h_kh,
+                     const int* h_kw, int nlayers, float* d_values, void* stream);
+
+/* Step 3 (methods.py:55): float64 np.percentile(values, perc), method 'linear':
+ *   *d_thr = _lerp(sorted[k], sorted[min(k+1,n-1)], gamma) in float64.  n <= 65536.                 */
+int mc_filter_threshold(const float* d_values, int n, int64_t k, double gamma, double* d_thr,
+                        void* d_ws, size_t ws_bytes, void* stream);
+size_t mc_workspace_bytes_filter_threshold(int n);
+
+/* Step 4 (methods.py:75): d_keep[off_l+o] = !( (double)v < *d_thr ); full-shape masks (fp32 1/0 per weight)
+ * are written when h_mask_ptrs != NULL.                                                              */
+int mc_filter_masks(const float* d_values, const double* d_thr, const int* h_O, const int* h_per_filter,
+                    int nlayers, float* const* h_mask_ptrs, uint8_t* d_keep, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Region decode + NMS — replaces src/nets2_utils.py:141-234 (get_region_boxes) and :236-259 (nms),
+ * :63-98 (bbox_iou, centre format).
+ * -------------------------------------------------------------------------------------------- */
+
+/* d_head: [B, A*(5+nc), H, W] fp32 (raw Darknet.forward output).  For every image, candidates are
+ * emitted in the reference's list order (cy, cx, anchor) into
+ *   d_boxes  [B, H*W*A, 8] : x/W, y/H, w/W, h/H, conf, cls_max_conf, (float)cls_max_id, (float)src_pos
+ *   d_cls    [B, H*W*A, nc]: softmax class probabilities of each candidate (may be NULL)
+ *   d_counts [B]           : number of candidates per image
+ * Candidate iff conf > thresh (only_objectness) or conf*cls_max_conf > thresh.                       */
+int mc_decode_region(const float* d_head, int B, int H, int W, int A, int nc, const float* h_anchors,
+                     float conf_thresh, int only_objectness,
+                     float* d_boxes, float* d_cls, int* d_counts, void* stream);
+
+/* Greedy class-agnostic NMS per image on centre-format boxes (stride 8 floats as above, `cap` boxes per
+ * image, counts[b] valid).  Sort key 1-conf ascending, ties by ascending candidate index (the
+ * reference's torch.sort is unstable; SURVEY.md §8c shim 3 pins the stable order).
+ * d_keep[b, 0..d_keep_counts[b]) = candidate indices of the kept boxes in sorted order.
+ * Boxes suppressed get conf (element 4) set to 0 in d_boxes, as the reference mutates its input.     */
+int mc_nms_batched(float* d_boxes, const int* d_counts, int B, int cap, float nms_thresh,
+                   int* d_keep, int* d_keep_counts, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Darknet-19 forward — replaces the F.conv2d + BatchNorm2d + LeakyReLU + MaxPool2d + Reorg + cat
+ * call sites of src/nets.py:720-774 / src/pruning/weightPruning/layers.py:53-64.
+ *
+ * Activation layout ("PNHWC"): bf16, row-major [rows, C] with rows = B*(H+1)*(W+1); pixel (b,y,x) is row
+ * b*(H+1)*(W+1) + y*(W+1) + x; column x==W of every line and line y==H of every image are zero, so a
+ * 3x3 tap is a constant row offset dy*(W+1)+dx and the implicit GEMM needs no bounds logic.
+ * -------------------------------------------------------------------------------------------- */
+
+enum { MC_EPI_PNHWC = 0,      /* bf16 PNHWC at the same resolution, channel offset ch_off, row pitch ldc   */
+       MC_EPI_REORG2 = 1,     /* bf16 PNHWC at (H/2,W/2): channel ((y&1)*2+(x&1))*N + n + ch_off (Reorg)   */
+       MC_EPI_NCHW_F32 = 2,   /* fp32 NCHW [B,N,H,W] (network head)                                        */
+       MC_EPI_POOL2 = 3 };    /* bf16 PNHWC at (H/2,W/2) after 2x2/2 max-pool                              */
+
+typedef struct mc_conv_desc {
+  const void* d_in;      /* bf16 PNHWC [B*(H+1)*(W+1), Cin_ld]                                           */
+  const void* d_wpack;   /* bf16 [Npad, ntaps*Kc] K-major, Kc = round_up(Cin,64); from mc_pack_conv_weights */
+  const float* d_scale;  /* [Npad] per-output-channel multiplier (folded BN gamma/sqrt(var+eps), or 1)     */
+  const float* d_shift;  /* [Npad] per-output-channel addend (folded BN beta - mean*scale, or conv bias)   */
+  void* d_out;
+  int B, H, W;           /* input (= conv output) resolution                                              */
+  int Cin, Cin_ld;       /* channels read, row pitch (elements) of d_in; both multiples of 8              */
+  int N, Npad;           /* output channels, padded to a multiple of 16                                   */
+  int ksize;             /* 1 or 3 (stride 1, 'same' padding)                                             */
+  int leaky;             /* 1: y = max(y, 0.1y)                                                           */
+  int epi_mode;          /* MC_EPI_*                                                                      */
+  int ldc, ch_off;       /* output row pitch (elements) and channel offset (bf16 modes)                   */
+  int block_n;           /* 0 = auto; else 16..256 multiple of 16                                         */
+  int stages;            /* 0 = auto                                                                      */
+} mc_conv_desc;
+
+int mc_conv_fwd(const mc_conv_desc* desc, void* stream);
+
+/* First layer: fp32 NCHW [B,3,H,W] image -> conv3x3(3->N) + scale/shift + leaky + 2x2 max-pool,
+ * bf16 PNHWC [(B*(H/2+1)*(W/2+1)), ldc].  d_w: fp32 [N,3,3,3] (already masked).                        */
+int mc_conv1_fwd(const float* d_img, const float* d_w, const float* d_scale, const float* d_shift,
+                 void* d_out, int B, int H, int W, int N, int ldc, int pool, void* stream);
+
+/* fp32 [O,C,kh,kw] (optionally * mask, optionally gathered by h_oidx/h_cidx surviving-index lists)
+ * -> bf16 [Npad, kh*kw*Kc] with column (tap*Kc + c).  d_oidx/d_cidx are device int32 arrays or NULL. */
+int mc_pack_conv_weights(const float* d_w, const float* d_mask, int O, int C, int ksize,
+                         const int* d_oidx, int n_o, const int* d_cidx, int n_c,
+                         void* d_wpack, int Npad, int Kc, void* stream);
+
+/* 2x2/2 max-pool on PNHWC bf16: in [B,(H+1),(W+1),C] -> out [B,(H/2+1),(W/2+1),C].                   */
+int mc_maxpool2x2(const void* d_in, void* d_out, int B, int H, int W, int C, int ld_in, int ld_out,
+                  void* stream);
+
+/* PNHWC bf16 -> NCHW fp32 [B,C,H,W] (debug / per-block parity checks). */
+int mc_unpack_pnhwc(const void* d_in, float* d_out, int B, int H, int W, int C, int ld_in, int ch_off,
+                    void* stream);
+
+/* NCHW fp32 [B,C,H,W] -> PNHWC bf16 (channels >= C up to ld zeroed; pad rows/cols zeroed). */
+int mc_pack_pnhwc(const float* d_in, void* d_out, int B, int H, int W, int C, int ld_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCB200_H_ */

@@ -1,0 +1,396 @@
+// conv_tcgen05.cu — Darknet-19 conv + folded-BN + leaky-ReLU as an implicit GEMM on tcgen05/TMEM, fed by TMA.
+//
+// Replaces: MaskedConv2d.forward -> F.conv2d (src/pruning/weightPruning/layers.py:53-64) followed by
+// nn.BatchNorm2d (eval) and nn.LeakyReLU(0.1) (src/nets.py:802,809), the Reorg module (src/nets.py:648-667)
+// and the route concat (src/nets.py:735-746), which are folded into the store addressing of the epilogue.
+//
+// Formulation.  Activations live in "PNHWC" (see include/mcb200.h): a 2-D bf16 matrix [rows, C] in which a
+// 3x3 tap (dy,dx) is the constant row offset dy*(W+1)+dx and out-of-image reads hit zero rows/columns (or TMA
+// out-of-bounds zero fill at the ends of the buffer).  So
+//     Y[p, n] = sum_{tap} sum_{c} X[p + off(tap), c] * Wt[n, tap*Kc + c]
+// is a plain GEMM whose A-tile row coordinate is shifted per k-block: no im2col buffer, no bounds logic.
+// M tile = 128 rows (UMMA M=128, cta_group::1), N tile = block_n (16..256), K block = 64 bf16 = one
+// 128-byte swizzle row.  Warp roles: warp0 = TMA producer, warp1 = TMEM owner + MMA issuer (one thread),
+// warps 2..5 = epilogue (TMEM -> regs -> scale/shift/leaky -> bf16/fp32 global stores).
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+#include <string>
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+constexpr int MAX_STAGES = 8;
+constexpr int NUM_THREADS = 192;
+
+struct ConvKParams {
+  int M_rows;      // B*(H+1)*(W+1)
+  int N;           // valid output channels
+  int Npad;        // length of scale/shift arrays
+  int num_kb;      // ntaps * kb_per_tap
+  int kb_per_tap;  // Kc / 64
+  int ksize;       // 1 or 3
+  int Wp, Hp, W, H;  // Wp = W+1, Hp = H+1
+  int block_n, stages, tmem_cols;
+  uint32_t idesc;
+  const float* scale;
+  const float* shift;
+  void* out;
+  int ldc, ch_off, epi_mode, leaky;
+};
+
+__device__ __forceinline__ float leaky01(float v) { return v > 0.f ? v : 0.1f * v; }
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const ConvKParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve-up: [stages x (A 16KB | B block_n*128)] | barriers | tmem ptr | scale/shift staging
+  const uint32_t b_tile_bytes = (uint32_t)p.block_n * 128u;
+  const uint32_t stage_bytes = A_TILE_BYTES + b_tile_bytes;
+  uint8_t* smem = smem_raw;
+  // dynamic smem base is only guaranteed 16B aligned by the ABI: align up to 1024 (host adds 1 KB of slack)
+  {
+    uint32_t a = ptx::smem_u32(smem);
+    uint32_t pad = (1024u - (a & 1023u)) & 1023u;
+    smem += pad;
+  }
+  uint8_t* tiles = smem;
+  uint8_t* aux = tiles + (size_t)p.stages * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* s_scale = reinterpret_cast<float*>(aux + 256);
+  float* s_shift = s_scale + 256;
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * p.block_n;
+  const int m0 = blockIdx.y * BLOCK_M;
+
+  if (warp_idx == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_a);
+    ptx::prefetch_tensormap(&tmap_b);
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp_idx == 1) {
+    ptx::tmem_alloc(tmem_ptr_smem, (uint32_t)p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer (one thread) =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int tap = kb / p.kb_per_tap;
+        const int cb = kb - tap * p.kb_per_tap;
+        int row_off = 0;
+        if (p.ksize == 3) row_off = (tap / 3 - 1) * p.Wp + (tap % 3 - 1);
+        ptx::mbar_wait(&empty_bar[s], phase ^ 1u);
+        uint8_t* a_dst = tiles + (size_t)s * stage_bytes;
+        uint8_t* b_dst = a_dst + A_TILE_BYTES;
+        ptx::mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+        ptx::tma_load_2d(a_dst, &tmap_a, &full_bar[s], cb * BLOCK_K, m0 + row_off);
+        ptx::tma_load_2d(b_dst, &tmap_b, &full_bar[s], kb * BLOCK_K, n0);
+        if (++s == p.stages) { s = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        ptx::mbar_wait(&full_bar[s], phase);
+        ptx::tc_fence_after();
+        const uint32_t a_addr = ptx::smem_u32(tiles + (size_t)s * stage_bytes);
+        const uint64_t adesc = ptx::make_sw128_kmajor_desc(a_addr);
+        const uint64_t bdesc = ptx::make_sw128_kmajor_desc(a_addr + A_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 16; ++k) {
+          // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr>>4) field
+          ptx::umma_bf16_ss(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
+                            (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        ptx::umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+        if (++s == p.stages) { s = 0; phase ^= 1u; }
+      }
+      ptx::umma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ===================== epilogue: warps 2..5 =====================
+    const int et = threadIdx.x - 64;  // 0..127
+    for (int i = et; i < p.block_n; i += 128) {
+      const bool ok = (n0 + i) < p.Npad;
+      s_scale[i] = ok ? p.scale[n0 + i] : 0.f;
+      s_shift[i] = ok ? p.shift[n0 + i] : 0.f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+
+    const int quarter = warp_idx & 3;  // TMEM lane quarter this warp may access
+    const int row = m0 + quarter * 32 + lane;
+    const int x = row % p.Wp;
+    const int t = row / p.Wp;
+    const int y = t % p.Hp;
+    const int b = t / p.Hp;
+    const bool in_buf = row < p.M_rows;
+    const bool interior = in_buf && (x < p.W) && (y < p.H);
+
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tc_fence_after();
+    const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+
+    __nv_bfloat16* out_bf = reinterpret_cast<__nv_bfloat16*>(p.out);
+    float* out_f = reinterpret_cast<float*>(p.out);
+    long long out_row_base = 0;
+    bool do_store = false;
+    if (p.epi_mode == MC_EPI_PNHWC) {
+      out_row_base = (long long)row * p.ldc + p.ch_off;
+      do_store = in_buf;  // pad rows are written as zeros to keep the layout invariant
+    } else if (p.epi_mode == MC_EPI_REORG2) {
+      const int Wo = p.W / 2 + 1, Ho = p.H / 2 + 1;
+      const long long orow = ((long long)b * Ho + (y >> 1)) * Wo + (x >> 1);
+      out_row_base = orow * p.ldc + p.ch_off + ((y & 1) * 2 + (x & 1)) * p.N;
+      do_store = interior;
+    } else {  // MC_EPI_NCHW_F32
+      out_row_base = ((long long)b * p.N * p.H + y) * p.W + x;  // + n*H*W
+      do_store = interior;
+    }
+    const bool vec_ok = ((p.ldc | p.ch_off) & 7) == 0 && (p.epi_mode != MC_EPI_REORG2 || (p.N & 7) == 0);
+
+    for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+      uint32_t r[16];
+      ptx::tmem_ld_32x32b_x16(taddr_row + (uint32_t)c0, r);
+      ptx::tmem_ld_wait();
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float a = __uint_as_float(r[j]) * s_scale[c0 + j] + s_shift[c0 + j];
+        if (p.leaky) a = leaky01(a);
+        v[j] = interior ? a : 0.f;
+      }
+      if (!do_store) continue;
+      const int nbase = n0 + c0;
+      if (p.epi_mode == MC_EPI_NCHW_F32) {
+        const long long hw = (long long)p.H * p.W;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (nbase + j < p.N) out_f[out_row_base + (long long)(nbase + j) * hw] = v[j];
+      } else {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const int n = nbase + g * 8;
+          if (vec_ok && n + 8 <= p.N) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[g * 8 + 0], v[g * 8 + 1]);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(v[g * 8 + 2], v[g * 8 + 3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[g * 8 + 4], v[g * 8 + 5]);
+            __nv_bfloat162 h3 = __floats2bfloat162_rn(v[g * 8 + 6], v[g * 8 + 7]);
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&h0);
+            pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            pk.z = *reinterpret_cast<uint32_t*>(&h2);
+            pk.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(out_bf + out_row_base + n) = pk;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (n + j < p.N) out_bf[out_row_base + n + j] = __float2bfloat16_rn(v[g * 8 + j]);
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Host side: tensor-map construction (driver entry point fetched at run time: no link-time libcuda dependency)
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] with row pitch ld (elements), box = [box_rows, 64 cols], 128B swizzle.
+int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return mc_set_error(MC_ERR_ARG, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return mc_set_error(MC_ERR_ARG, "cuTensorMapEncodeTiled failed (CUresult %d) rows=%llu cols=%llu ld=%llu box_rows=%u",
+                        (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
+  return 0;
+}
+
+struct TmapKey {
+  const void* base;
+  uint64_t rows, cols, ld;
+  uint32_t box_rows;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = std::hash<const void*>()(k.base);
+    h ^= std::hash<uint64_t>()(k.rows * 1315423911ull + k.cols * 2654435761ull + k.ld * 97ull + k.box_rows);
+    return h;
+  }
+};
+
+int cached_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey key{base, rows, cols, ld, box_rows};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return 0;
+  }
+  CUtensorMap tm;
+  int rc = make_tmap_2d(&tm, base, rows, cols, ld, box_rows);
+  if (rc) return rc;
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, tm);
+  *out = tm;
+  return 0;
+}
+
+// Tile-width heuristic.  One 64-wide k-block of a 128 x bn tile costs max(2*bn, 128+bn) SM cycles: 2*bn is the
+// tcgen05 issue floor (128*bn*64 MACs at 4096 MAC/clk), 128+bn is the shared-memory read of the A (16 KB) and
+// B (bn*128 B) tiles at 128 B/clk.  Cost = waves over the SMs x (k-blocks x that + a fixed prologue/epilogue).
+int pick_block_n(int Npad, int m_tiles, int num_kb, int num_sms) {
+  static const int cands[] = {16, 32, 48, 64, 96, 128, 160, 192, 224, 256};
+  int best = 16;
+  double best_cost = 1e30;
+  for (int bn : cands) {
+    const int n_tiles = (Npad + bn - 1) / bn;
+    const long long tiles = (long long)n_tiles * m_tiles;
+    const long long waves = (tiles + num_sms - 1) / num_sms;
+    const double per_kb = (double)((2 * bn > 128 + bn) ? 2 * bn : 128 + bn);
+    const double cost = (double)waves * (per_kb * num_kb + 2500.0 + 12.0 * bn);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+}  // namespace
+
+extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MC_CHECK_ARG(d != nullptr, "mc_conv_fwd: null descriptor");
+  MC_CHECK_ARG(d->d_in && d->d_wpack && d->d_scale && d->d_shift && d->d_out, "mc_conv_fwd: null pointer");
+  MC_CHECK_ARG(d->ksize == 1 || d->ksize == 3, "mc_conv_fwd: ksize must be 1 or 3 (got %d)", d->ksize);
+  MC_CHECK_ARG(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->N > 0, "mc_conv_fwd: bad dims");
+  MC_CHECK_ARG((d->Cin_ld % 8) == 0 && d->Cin <= d->Cin_ld, "mc_conv_fwd: Cin_ld must be a multiple of 8 >= Cin");
+  MC_CHECK_ARG((d->Npad % 16) == 0 && d->Npad >= d->N, "mc_conv_fwd: Npad must be a multiple of 16 >= N");
+  MC_CHECK_ARG(((uintptr_t)d->d_in & 15) == 0 && ((uintptr_t)d->d_wpack & 15) == 0 && ((uintptr_t)d->d_out & 15) == 0,
+               "mc_conv_fwd: pointers must be 16-byte aligned");
+  MC_CHECK_ARG(d->epi_mode == MC_EPI_PNHWC || d->epi_mode == MC_EPI_REORG2 || d->epi_mode == MC_EPI_NCHW_F32,
+               "mc_conv_fwd: unsupported epilogue mode %d", d->epi_mode);
+  if (d->epi_mode == MC_EPI_REORG2) MC_CHECK_ARG((d->H % 2) == 0 && (d->W % 2) == 0, "mc_conv_fwd: reorg needs even H,W");
+
+  const int ntaps = d->ksize * d->ksize;
+  const int Kc = ((d->Cin + BLOCK_K - 1) / BLOCK_K) * BLOCK_K;
+  const long long M_rows = (long long)d->B * (d->H + 1) * (d->W + 1);
+  MC_CHECK_ARG(M_rows < (1ll << 31), "mc_conv_fwd: too many rows");
+  const int m_tiles = (int)((M_rows + BLOCK_M - 1) / BLOCK_M);
+
+  int block_n = d->block_n;
+  if (block_n <= 0) block_n = pick_block_n(d->Npad, m_tiles, ntaps * (Kc / BLOCK_K), mc_num_sms());
+  MC_CHECK_ARG(block_n >= 16 && block_n <= 256 && (block_n % 16) == 0, "mc_conv_fwd: block_n %d invalid", block_n);
+  const int n_tiles = (d->Npad + block_n - 1) / block_n;
+
+  const int stage_bytes = A_TILE_BYTES + block_n * 128;
+  int stages = d->stages;
+  if (stages <= 0) {
+    stages = (200 * 1024) / stage_bytes;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+  }
+  MC_CHECK_ARG(stages >= 1 && stages <= MAX_STAGES, "mc_conv_fwd: stages %d invalid", stages);
+  const size_t smem_bytes = (size_t)stages * stage_bytes + 256 + 2 * 256 * sizeof(float) + 1024;
+  MC_CHECK_ARG(smem_bytes <= 227 * 1024, "mc_conv_fwd: smem %zu too large", smem_bytes);
+
+  CUtensorMap tm_a, tm_b;
+  int rc = cached_tmap(&tm_a, d->d_in, (uint64_t)M_rows, (uint64_t)d->Cin, (uint64_t)d->Cin_ld, BLOCK_M);
+  if (rc) return rc;
+  // weights: [n_tiles*block_n >= Npad rows (OOB rows zero-filled), ntaps*Kc]
+  rc = cached_tmap(&tm_b, d->d_wpack, (uint64_t)d->Npad, (uint64_t)ntaps * Kc, (uint64_t)ntaps * Kc, (uint32_t)block_n);
+  if (rc) return rc;
+
+  ConvKParams p;
+  p.M_rows = (int)M_rows;
+  p.N = d->N;
+  p.Npad = d->Npad;
+  p.kb_per_tap = Kc / BLOCK_K;
+  p.num_kb = ntaps * p.kb_per_tap;
+  p.ksize = d->ksize;
+  p.W = d->W;
+  p.H = d->H;
+  p.Wp = d->W + 1;
+  p.Hp = d->H + 1;
+  p.block_n = block_n;
+  p.stages = stages;
+  int tc = 32;
+  while (tc < block_n) tc <<= 1;
+  p.tmem_cols = tc;
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+  p.scale = d->d_scale;
+  p.shift = d->d_shift;
+  p.out = d->d_out;
+  p.ldc = d->ldc;
+  p.ch_off = d->ch_off;
+  p.epi_mode = d->epi_mode;
+  p.leaky = d->leaky;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    MC_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)n_tiles, (unsigned)m_tiles, 1);
+  conv_gemm_tcgen05_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tm_a, tm_b, p);
+  MC_LAUNCH_CHECK("conv_gemm_tcgen05_kernel");
+  return 0;
+}

@@ -1,0 +1,352 @@
+// prune_filter.cu — global filter pruner ("scaled L2 norm" of each filter) on the GPU.
+//
+// Replaces quick_filter_prune (src/pruning/weightPruning/methods.py:28-78).  The reference computes, per conv
+// weight p[O,C,kh,kw] (float32, NumPy):
+//     v = np.square(p).sum(axis=1).sum(axis=1).sum(axis=1) / (C*kh*kw)          methods.py:43-44
+//     v = v / np.sqrt(np.square(v).sum());  v /= np.max(v)                      methods.py:46-51
+//     thr = np.percentile(concat(v of all layers) as float64, perc)             methods.py:53-55
+//     mask[o] = 0 where v[o] < thr                                              methods.py:75
+// Bit-exactness needs NumPy's float32 summation ORDER:
+//   kh*kw > 1 : s[h,w] = sum over c, sequential in c; then sequential over h; then sequential over w.
+//   kh*kw == 1: NumPy pairwise summation over the contiguous C axis (numpy/_core/src/umath/loops_utils.h.src:
+//               n<8 sequential; n<=128: 8 strided accumulators, ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), tail;
+//               else split at n/2 rounded down to a multiple of 8).  sum(v^2) over O uses the same rule.
+// All products/sums use *_rn intrinsics so nvcc cannot contract them into FMAs.
+#include "common.cuh"
+
+namespace {
+
+constexpr int MAX_LAYERS = MC_MAX_SEGMENTS;
+
+struct LayerTable {
+  const float* w[MAX_LAYERS];
+  float* mask[MAX_LAYERS];
+  int O[MAX_LAYERS], C[MAX_LAYERS], taps[MAX_LAYERS];
+  int voff[MAX_LAYERS + 1];        // prefix of O
+  long long woff[MAX_LAYERS + 1];  // prefix of O*C*taps
+  int toff[MAX_LAYERS + 1];        // prefix of threads used by sumsq kernel
+  int nlayers;
+};
+
+// NumPy pairwise sum of f(a[i]) for i in [0,n), a contiguous.  SQUARE: element is a[i]*a[i] rounded to fp32 first.
+template <bool SQUARE>
+__device__ float np_pairwise(const float* __restrict__ a, int n) {
+  auto el = [&](int i) -> float {
+    const float x = a[i];
+    return SQUARE ? __fmul_rn(x, x) : x;
+  };
+  if (n < 8) {
+    float res = 0.f;
+    for (int i = 0; i < n; ++i) res = __fadd_rn(res, el(i));
+    return res;
+  } else if (n <= 128) {
+    float r0 = el(0), r1 = el(1), r2 = el(2), r3 = el(3), r4 = el(4), r5 = el(5), r6 = el(6), r7 = el(7);
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+      r0 = __fadd_rn(r0, el(i + 0));
+      r1 = __fadd_rn(r1, el(i + 1));
+      r2 = __fadd_rn(r2, el(i + 2));
+      r3 = __fadd_rn(r3, el(i + 3));
+      r4 = __fadd_rn(r4, el(i + 4));
+      r5 = __fadd_rn(r5, el(i + 5));
+      r6 = __fadd_rn(r6, el(i + 6));
+      r7 = __fadd_rn(r7, el(i + 7));
+    }
+    float res = __fadd_rn(__fadd_rn(__fadd_rn(r0, r1), __fadd_rn(r2, r3)),
+                          __fadd_rn(__fadd_rn(r4, r5), __fadd_rn(r6, r7)));
+    for (; i < n; ++i) res = __fadd_rn(res, el(i));
+    return res;
+  } else {
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return __fadd_rn(np_pairwise<SQUARE>(a, n2), np_pairwise<SQUARE>(a + n2, n - n2));
+  }
+}
+
+// Raw per-filter sums.  taps>1: one thread per (filter, tap) runs the sequential-in-c chain; the taps of a filter
+// sit in adjacent lanes and are combined in NumPy's (h then w) order through shared memory.  taps==1: one thread
+// per filter runs the pairwise recursion.
+constexpr int SS_THREADS = 288;  // multiple of 9 and of 32
+
+__global__ void __launch_bounds__(SS_THREADS) filter_sumsq_kernel(const LayerTable lt, float* __restrict__ values) {
+  __shared__ float s_tap[SS_THREADS];
+  const int gt = blockIdx.x * SS_THREADS + threadIdx.x;  // global thread slot (blocks never straddle layers)
+  int l = 0;
+  while (l + 1 < lt.nlayers && gt >= lt.toff[l + 1]) ++l;
+  const int local = gt - lt.toff[l];
+  const int taps = lt.taps[l], C = lt.C[l], O = lt.O[l];
+  const float* __restrict__ w = lt.w[l];
+  if (taps == 1) {
+    if (local < O) {
+      const float s = np_pairwise<true>(w + (long long)local * C, C);
+      values[lt.voff[l] + local] = __fdiv_rn(s, (float)C);
+    }
+    return;
+  }
+  // blocks hold whole filters: fpb filters x taps threads, the remaining threads of the block idle
+  const int fpb = SS_THREADS / taps;
+  const int blk = local / SS_THREADS, tl = local - blk * SS_THREADS;
+  const int fl = tl / taps, j = tl - fl * taps;
+  const int o = (fl < fpb) ? blk * fpb + fl : O;  // O = out of range -> idle
+  float acc = 0.f;
+  if (o < O) {
+    const float* p = w + (long long)o * C * taps + j;
+    int c = 0;
+    for (; c + 8 <= C; c += 8) {
+      float x[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) x[u] = p[(long long)(c + u) * taps];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc = __fadd_rn(acc, __fmul_rn(x[u], x[u]));
+    }
+    for (; c < C; ++c) {
+      const float x = p[(long long)c * taps];
+      acc = __fadd_rn(acc, __fmul_rn(x, x));
+    }
+  }
+  s_tap[threadIdx.x] = acc;
+  __syncthreads();
+  if (o < O && j == 0) {
+    // taps = kh*kw with kh == kw (square kernels): s[h][w] at s_tap[base + h*k + w]
+    int k = 1;
+    while (k * k < taps) ++k;
+    const float* s = &s_tap[threadIdx.x];
+    float tot = 0.f;
+    for (int ww = 0; ww < k; ++ww) {
+      float col = 0.f;
+      for (int hh = 0; hh < k; ++hh) col = __fadd_rn(col, s[hh * k + ww]);  // .sum(axis=1) over h, sequential
+      tot = __fadd_rn(tot, col);                                            // final .sum(axis=1) over w (n<8)
+    }
+    values[lt.voff[l] + o] = __fdiv_rn(tot, (float)(C * taps));
+  }
+}
+
+// One block per layer: v /= sqrt(pairwise(v^2)); v /= max(v).
+__global__ void __launch_bounds__(256) filter_norm_kernel(const LayerTable lt, float* __restrict__ values) {
+  __shared__ float s_norm;
+  __shared__ float s_red[256];
+  const int l = blockIdx.x;
+  const int O = lt.O[l];
+  float* v = values + lt.voff[l];
+  if (threadIdx.x == 0) s_norm = __fsqrt_rn(np_pairwise<true>(v, O));
+  __syncthreads();
+  const float nrm = s_norm;
+  float mx = -INFINITY;
+  for (int o = threadIdx.x; o < O; o += 256) {
+    const float x = __fdiv_rn(v[o], nrm);
+    v[o] = x;
+    mx = fmaxf(mx, x);
+  }
+  s_red[threadIdx.x] = mx;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) s_red[threadIdx.x] = fmaxf(s_red[threadIdx.x], s_red[threadIdx.x + s]);
+    __syncthreads();
+  }
+  mx = s_red[0];
+  for (int o = threadIdx.x; o < O; o += 256) v[o] = __fdiv_rn(v[o], mx);
+}
+
+// Single-block radix select of two ranks over n non-negative floats, then NumPy's float64 _lerp.
+__device__ unsigned int block_select(const float* __restrict__ v, int n, unsigned int rank, unsigned int* s_hist,
+                                     unsigned int* s_pick) {
+  unsigned int prefix = 0, mask = 0;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned int key = __float_as_uint(v[i]);
+      if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int cum = 0, b = 0;
+      for (; b < 255; ++b) {
+        if (cum + s_hist[b] > rank) break;
+        cum += s_hist[b];
+      }
+      s_pick[0] = b;
+      s_pick[1] = rank - cum;
+    }
+    __syncthreads();
+    prefix |= s_pick[0] << shift;
+    mask |= 255u << shift;
+    rank = s_pick[1];
+    __syncthreads();
+  }
+  return prefix;
+}
+
+__global__ void __launch_bounds__(1024) filter_threshold_kernel(const float* __restrict__ v, int n, long long k,
+                                                                double gamma, double* __restrict__ thr) {
+  __shared__ unsigned int s_hist[256];
+  __shared__ unsigned int s_pick[2];
+  __shared__ int s_nan;
+  if (threadIdx.x == 0) s_nan = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    if (v[i] != v[i]) s_nan = 1;  // np.percentile returns nan if any value is nan (an all-zero layer gives 0/0)
+  __syncthreads();
+  if (s_nan) {
+    if (threadIdx.x == 0) *thr = __longlong_as_double(0x7ff8000000000000LL);
+    return;
+  }
+  const unsigned int ka = block_select(v, n, (unsigned int)k, s_hist, s_pick);
+  const long long k1 = (k + 1 < n) ? k + 1 : (long long)n - 1;
+  const unsigned int kb = block_select(v, n, (unsigned int)k1, s_hist, s_pick);
+  if (threadIdx.x == 0) {
+    const double a = (double)__uint_as_float(ka);
+    const double b = (double)__uint_as_float(kb);
+    const double diff = __dsub_rn(b, a);
+    double r = __dadd_rn(a, __dmul_rn(diff, gamma));
+    if (gamma >= 0.5) r = __dsub_rn(b, __dmul_rn(diff, __dsub_rn(1.0, gamma)));
+    *thr = r;
+  }
+}
+
+__global__ void filter_keep_kernel(const float* __restrict__ v, int n, const double* __restrict__ thr,
+                                   uint8_t* __restrict__ keep) {
+  const double t = *thr;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    keep[i] = ((double)v[i] < t) ? 0 : 1;
+}
+
+__global__ void __launch_bounds__(256) filter_mask_fill_kernel(const LayerTable lt, const float* __restrict__ v,
+                                                               const double* __restrict__ thr) {
+  const double t = *thr;
+  const long long total4 = lt.woff[lt.nlayers];
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < total4;
+       i += (long long)gridDim.x * blockDim.x * 4) {
+    int l = 0;
+    while (l + 1 < lt.nlayers && i >= lt.woff[l + 1]) ++l;
+    const long long li = i - lt.woff[l];
+    const long long lsize = lt.woff[l + 1] - lt.woff[l];
+    const int per = lt.C[l] * lt.taps[l];
+    float* m = lt.mask[l];
+    float r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long e = li + j;
+      r[j] = 0.f;
+      if (e < lsize) r[j] = ((double)v[lt.voff[l] + (int)(e / per)] < t) ? 0.f : 1.f;
+    }
+    if (li + 4 <= lsize && (reinterpret_cast<uintptr_t>(m) & 15) == 0) {
+      st_stream_f4(reinterpret_cast<float4*>(m + li), make_float4(r[0], r[1], r[2], r[3]));
+    } else {
+      for (int j = 0; j < 4; ++j)
+        if (li + j < lsize) m[li + j] = r[j];
+    }
+  }
+}
+
+int build_layers(LayerTable* lt, const float* const* w, float* const* masks, const int* O, const int* C,
+                 const int* taps, int nlayers, const char* who) {
+  if (nlayers <= 0 || nlayers > MAX_LAYERS) return mc_set_error(MC_ERR_ARG, "%s: nlayers %d out of range", who, nlayers);
+  lt->nlayers = nlayers;
+  lt->voff[0] = 0;
+  lt->woff[0] = 0;
+  lt->toff[0] = 0;
+  for (int l = 0; l < nlayers; ++l) {
+    if (O[l] <= 0 || C[l] <= 0 || taps[l] <= 0) return mc_set_error(MC_ERR_ARG, "%s: layer %d has bad dims", who, l);
+    lt->w[l] = w ? w[l] : nullptr;
+    lt->mask[l] = masks ? masks[l] : nullptr;
+    lt->O[l] = O[l];
+    lt->C[l] = C[l];
+    lt->taps[l] = taps[l];
+    lt->voff[l + 1] = lt->voff[l] + O[l];
+    // element offsets are rounded up to 4 so the vectorised mask fill never straddles two layers
+    const long long sz = (long long)O[l] * C[l] * taps[l];
+    lt->woff[l + 1] = lt->woff[l] + ((sz + 3) / 4) * 4;
+    const long long thr = (taps[l] == 1) ? O[l] : (long long)O[l] * taps[l];
+    // per-layer thread slots rounded up to whole blocks; for taps>1 a block must hold whole filters
+    long long slots;
+    if (taps[l] == 1) slots = ((thr + SS_THREADS - 1) / SS_THREADS) * SS_THREADS;
+    else {
+      const int fpb = SS_THREADS / taps[l];  // filters per block
+      slots = (long long)((O[l] + fpb - 1) / fpb) * SS_THREADS;
+    }
+    lt->toff[l + 1] = lt->toff[l] + (int)slots;
+  }
+  for (int l = nlayers; l < MAX_LAYERS; ++l) {
+    lt->w[l] = nullptr;
+    lt->mask[l] = nullptr;
+    lt->O[l] = lt->C[l] = lt->taps[l] = 0;
+    lt->voff[l + 1] = lt->voff[nlayers];
+    lt->woff[l + 1] = lt->woff[nlayers];
+    lt->toff[l + 1] = lt->toff[nlayers];
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int mc_filter_values(const float* const* h_w_ptrs, const int* h_O, const int* h_C, const int* h_kh,
+                                const int* h_kw, int nlayers, float* d_values, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MC_CHECK_ARG(h_w_ptrs && h_O && h_C && h_kh && h_kw && d_values, "mc_filter_values: null pointer");
+  MC_CHECK_ARG(nlayers > 0 && nlayers <= MAX_LAYERS, "mc_filter_values: nlayers out of range");
+  int taps[MAX_LAYERS];
+  for (int l = 0; l < nlayers; ++l) {
+    MC_CHECK_ARG(h_kh[l] == h_kw[l] && h_kh[l] >= 1 && h_kh[l] * h_kw[l] <= 49,
+                 "mc_filter_values: layer %d kernel %dx%d unsupported (square, <=7x7)", l, h_kh[l], h_kw[l]);
+    MC_CHECK_ARG(h_w_ptrs[l] != nullptr, "mc_filter_values: layer %d null weight", l);
+    taps[l] = h_kh[l] * h_kw[l];
+  }
+  LayerTable lt;
+  int rc = build_layers(&lt, h_w_ptrs, nullptr, h_O, h_C, taps, nlayers, "mc_filter_values");
+  if (rc) return rc;
+  // with taps>1 the in-block position of a filter is local/taps: filters-per-block packing needs local indices that
+  // restart per block -> remap: thread slot -> (block-local filter, tap)
+  const int nblocks = lt.toff[nlayers] / SS_THREADS;
+  filter_sumsq_kernel<<<nblocks, SS_THREADS, 0, stream>>>(lt, d_values);
+  MC_LAUNCH_CHECK("filter_sumsq_kernel");
+  filter_norm_kernel<<<nlayers, 256, 0, stream>>>(lt, d_values);
+  MC_LAUNCH_CHECK("filter_norm_kernel");
+  return 0;
+}
+
+extern "C" size_t mc_workspace_bytes_filter_threshold(int n) {
+  (void)n;
+  return 0;
+}
+
+extern "C" int mc_filter_threshold(const float* d_values, int n, int64_t k, double gamma, double* d_thr, void* d_ws,
+                                   size_t ws_bytes, void* stream_) {
+  (void)d_ws;
+  (void)ws_bytes;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MC_CHECK_ARG(d_values && d_thr && n > 0, "mc_filter_threshold: bad argument");
+  MC_CHECK_ARG(k >= 0 && k < n, "mc_filter_threshold: rank out of range");
+  MC_CHECK_ARG(gamma >= 0.0 && gamma < 1.0, "mc_filter_threshold: gamma must be in [0,1)");
+  filter_threshold_kernel<<<1, 1024, 0, stream>>>(d_values, n, (long long)k, gamma, d_thr);
+  MC_LAUNCH_CHECK("filter_threshold_kernel");
+  return 0;
+}
+
+extern "C" int mc_filter_masks(const float* d_values, const double* d_thr, const int* h_O, const int* h_per_filter,
+                               int nlayers, float* const* h_mask_ptrs, uint8_t* d_keep, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MC_CHECK_ARG(d_values && d_thr && h_O && h_per_filter, "mc_filter_masks: null pointer");
+  MC_CHECK_ARG(h_mask_ptrs || d_keep, "mc_filter_masks: nothing to do");
+  int ones[MAX_LAYERS];
+  for (int l = 0; l < nlayers && l < MAX_LAYERS; ++l) ones[l] = 1;
+  LayerTable lt;
+  // per-filter element count goes into C, taps = 1
+  int rc = build_layers(&lt, nullptr, h_mask_ptrs, h_O, h_per_filter, ones, nlayers, "mc_filter_masks");
+  if (rc) return rc;
+  const int n = lt.voff[nlayers];
+  if (d_keep) {
+    filter_keep_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_values, n, d_thr, d_keep);
+    MC_LAUNCH_CHECK("filter_keep_kernel");
+  }
+  if (h_mask_ptrs) {
+    for (int l = 0; l < nlayers; ++l) MC_CHECK_ARG(h_mask_ptrs[l] != nullptr, "mc_filter_masks: null mask %d", l);
+    const long long total4 = lt.woff[nlayers] / 4;
+    long long blocks = (total4 + 255) / 256;
+    const long long cap = (long long)mc_num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    filter_mask_fill_kernel<<<(int)blocks, 256, 0, stream>>>(lt, d_values, d_thr);
+    MC_LAUNCH_CHECK("filter_mask_fill_kernel");
+  }
+  return 0;
+}

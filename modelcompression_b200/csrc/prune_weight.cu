@@ -1,0 +1,521 @@
+// prune_weight.cu — global magnitude pruner on the GPU.
+//
+// Replaces weight_prune (src/pruning/weightPruning/methods.py:9-26): np.percentile over |w| of every
+// parameter with dim != 1, then mask = (|w| > thr).float(); and the weight.data *= mask half of
+// MaskedConv2d.set_mask (src/pruning/weightPruning/layers.py:41-47); plus the full-tensor scans of
+// prune_rate / are_masks_consistent (src/pruning/weightPruning/utils.py:59-93,122-133).
+//
+// Selection is exact: |w| >= 0, so its fp32 bit pattern is monotone as uint32 and the k-th smallest value is
+// found by a 12+12+7-bit radix select.  Pass 0 histograms the top 12 bits of every element (one read of W),
+// pass 1 compacts the elements of the selected bin into the workspace, passes 2..3 histogram the remaining
+// bits on the (small) candidate list.  HBM traffic: 2 reads of W for the select + read W / write mask.
+#include "common.cuh"
+
+namespace {
+
+constexpr int THREADS = 256;
+constexpr int CHUNK = THREADS * 8;  // elements per block-iteration (two float4 per thread)
+constexpr int BINS0 = 4096;         // bits [30:19]
+constexpr int BINS1 = 4096;         // bits [18:7]
+constexpr int BINS2 = 128;          // bits [6:0]
+
+// device-side state of one selection (lives at the head of the workspace)
+struct SelState {
+  unsigned int hist0[BINS0];
+  unsigned int hist1[BINS1];
+  unsigned int hist2[BINS2];
+  unsigned long long k;         // requested rank (0-based)
+  unsigned long long rem1;      // rank inside bin0
+  unsigned long long rem2;      // rank inside bin1
+  unsigned int bin0, bin1;
+  unsigned int cand_count;      // number of compacted candidates
+  unsigned int key_a;           // bit pattern of sorted[k]
+  unsigned long long cnt_le;    // #elements with key <= key_a (only when b is needed)
+  unsigned int min_gt;          // min key > key_a
+  unsigned int has_nan;         // any NaN input: np.percentile returns nan
+};
+
+struct Chunks {
+  long long cstart[MC_MAX_SEGMENTS + 1];  // prefix of per-segment chunk counts
+};
+
+__device__ __forceinline__ unsigned int absbits(float v) { return __float_as_uint(v) & 0x7fffffffu; }
+
+// locate segment of a global chunk id (nseg <= 64: linear scan over a kernel-parameter table)
+__device__ __forceinline__ int find_seg(const Chunks& ch, int nseg, long long cid) {
+  int s = 0;
+  while (s + 1 < nseg && cid >= ch.cstart[s + 1]) ++s;
+  return s;
+}
+
+// Visit every element of every segment: f(value, seg, index).  Vectorised when the segment base is 16B aligned.
+template <typename F>
+__device__ __forceinline__ void for_each_element(const SegTable& st, const Chunks& ch, F f) {
+  const long long nchunks = ch.cstart[st.nseg];
+  for (long long cid = blockIdx.x; cid < nchunks; cid += gridDim.x) {
+    const int s = find_seg(ch, st.nseg, cid);
+    const long long size = st.start[s + 1] - st.start[s];
+    const long long base = (cid - ch.cstart[s]) * CHUNK;
+    const float* p = st.ptr[s];
+    const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const long long i = base + ((long long)it * THREADS + threadIdx.x) * 4;
+      if (aligned && i + 4 <= size) {
+        const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(p + i));
+        f(v.x, s, i);
+        f(v.y, s, i + 1);
+        f(v.z, s, i + 2);
+        f(v.w, s, i + 3);
+      } else {
+        for (int j = 0; j < 4; ++j)
+          if (i + j < size) f(p[i + j], s, i + j);
+      }
+    }
+  }
+}
+
+__global__ void set_rank_kernel(SelState* state, unsigned long long k) { state->k = k; }
+
+__global__ void __launch_bounds__(THREADS) hist0_kernel(const SegTable st, const Chunks ch, SelState* state) {
+  __shared__ unsigned int sh[BINS0];
+  for (int i = threadIdx.x; i < BINS0; i += THREADS) sh[i] = 0;
+  __syncthreads();
+  bool saw_nan = false;
+  for_each_element(st, ch, [&](float v, int, long long) {
+    const unsigned int key = absbits(v);
+    saw_nan |= key > 0x7f800000u;
+    atomicAdd(&sh[key >> 19], 1u);
+  });
+  if (saw_nan) atomicOr(&state->has_nan, 1u);
+  __syncthreads();
+  for (int i = threadIdx.x; i < BINS0; i += THREADS)
+    if (sh[i]) atomicAdd(&state->hist0[i], sh[i]);
+}
+
+// Block-wide: find the bin holding rank `k` in hist[nbins]; returns bin, and the rank inside that bin.
+// Executed redundantly by every block that needs it (nbins <= 4096: 16 bins per thread).
+template <int NBINS>
+__device__ void block_find_bin(const unsigned int* __restrict__ hist, unsigned long long k, unsigned int* s_bin,
+                               unsigned long long* s_rem) {
+  __shared__ unsigned long long s_part[THREADS];
+  constexpr int PER = (NBINS + THREADS - 1) / THREADS;
+  unsigned long long local = 0;
+  const int b0 = threadIdx.x * PER;
+  for (int j = 0; j < PER; ++j)
+    if (b0 + j < NBINS) local += hist[b0 + j];
+  s_part[threadIdx.x] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long cum = 0;
+    int t = 0;
+    for (; t < THREADS; ++t) {
+      if (cum + s_part[t] > k) break;
+      cum += s_part[t];
+    }
+    if (t == THREADS) t = THREADS - 1;  // k beyond total: clamp (caller validates k < n)
+    int bin = t * PER;
+    const int bend = (t * PER + PER < NBINS) ? t * PER + PER : NBINS;
+    for (; bin < bend - 1; ++bin) {
+      if (cum + hist[bin] > k) break;
+      cum += hist[bin];
+    }
+    *s_bin = (unsigned int)bin;
+    *s_rem = k - cum;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(THREADS) compact_kernel(const SegTable st, const Chunks ch, SelState* state,
+                                                          unsigned int* __restrict__ cand,
+                                                          unsigned long long cand_cap) {
+  __shared__ unsigned int s_bin;
+  __shared__ unsigned long long s_rem;
+  block_find_bin<BINS0>(state->hist0, state->k, &s_bin, &s_rem);
+  const unsigned int bin = s_bin;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    state->bin0 = bin;
+    state->rem1 = s_rem;
+  }
+  for_each_element(st, ch, [&](float v, int, long long) {
+    const unsigned int key = absbits(v);
+    const bool hit = (key >> 19) == bin;
+    // warp-aggregated append
+    const unsigned int m = __ballot_sync(__activemask(), hit);
+    if (hit) {
+      const int lane = threadIdx.x & 31;
+      const int leader = __ffs(m) - 1;
+      unsigned int basepos = 0;
+      if (lane == leader) basepos = atomicAdd(&state->cand_count, (unsigned int)__popc(m));
+      basepos = __shfl_sync(m, basepos, leader);
+      const unsigned int pos = basepos + __popc(m & ((1u << lane) - 1));
+      if (pos < cand_cap) cand[pos] = key;
+    }
+  });
+}
+
+__global__ void __launch_bounds__(THREADS) hist1_kernel(SelState* state, const unsigned int* __restrict__ cand) {
+  __shared__ unsigned int sh[BINS1];
+  for (int i = threadIdx.x; i < BINS1; i += THREADS) sh[i] = 0;
+  __syncthreads();
+  const unsigned int m = state->cand_count;
+  for (unsigned int i = blockIdx.x * THREADS + threadIdx.x; i < m; i += gridDim.x * THREADS)
+    atomicAdd(&sh[(cand[i] >> 7) & (BINS1 - 1)], 1u);
+  __syncthreads();
+  for (int i = threadIdx.x; i < BINS1; i += THREADS)
+    if (sh[i]) atomicAdd(&state->hist1[i], sh[i]);
+}
+
+__global__ void __launch_bounds__(THREADS) hist2_kernel(SelState* state, const unsigned int* __restrict__ cand) {
+  __shared__ unsigned int s_bin;
+  __shared__ unsigned long long s_rem;
+  __shared__ unsigned int sh[BINS2];
+  block_find_bin<BINS1>(state->hist1, state->rem1, &s_bin, &s_rem);
+  const unsigned int bin1 = s_bin;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    state->bin1 = bin1;
+    state->rem2 = s_rem;
+  }
+  if (threadIdx.x < BINS2) sh[threadIdx.x] = 0;
+  __syncthreads();
+  const unsigned int m = state->cand_count;
+  for (unsigned int i = blockIdx.x * THREADS + threadIdx.x; i < m; i += gridDim.x * THREADS) {
+    const unsigned int key = cand[i];
+    if (((key >> 7) & (BINS1 - 1)) == bin1) atomicAdd(&sh[key & (BINS2 - 1)], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < BINS2 && sh[threadIdx.x]) atomicAdd(&state->hist2[threadIdx.x], sh[threadIdx.x]);
+}
+
+// single block: resolve the last 7 bits -> key_a; if the (k+1)-th value is not needed, also emit the result.
+__global__ void __launch_bounds__(THREADS) final_kernel(SelState* state, float* out3, int need_b) {
+  __shared__ unsigned int s_bin;
+  __shared__ unsigned long long s_rem;
+  block_find_bin<BINS2>(state->hist2, state->rem2, &s_bin, &s_rem);
+  if (threadIdx.x == 0) {
+    const unsigned int key = (state->bin0 << 19) | (state->bin1 << 7) | s_bin;
+    state->key_a = key;
+    state->cnt_le = 0;
+    state->min_gt = 0xffffffffu;
+    if (!need_b) {
+      const float a = state->has_nan ? __uint_as_float(0x7fc00000u) : __uint_as_float(key);
+      out3[0] = a;
+      out3[1] = a;
+      out3[2] = a;
+    }
+  }
+}
+
+// count(key <= key_a) and min(key > key_a) over the ORIGINAL data: decides sorted[k+1].
+__global__ void __launch_bounds__(THREADS) succ_kernel(const SegTable st, const Chunks ch, SelState* state) {
+  const unsigned int key_a = state->key_a;
+  unsigned long long cnt = 0;
+  unsigned int mn = 0xffffffffu;
+  for_each_element(st, ch, [&](float v, int, long long) {
+    const unsigned int key = absbits(v);
+    if (key <= key_a) ++cnt;
+    else if (key < mn) mn = key;
+  });
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    const unsigned int other = __shfl_xor_sync(0xffffffffu, mn, o);
+    mn = other < mn ? other : mn;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (cnt) atomicAdd(&state->cnt_le, cnt);
+    if (mn != 0xffffffffu) atomicMin(&state->min_gt, mn);
+  }
+}
+
+// NumPy's _lerp (numpy/lib/_function_base_impl.py) in float32, no FMA contraction:
+//   lerp = a + (b-a)*t ; where t >= 0.5: lerp = b - (b-a)*(1-t)
+__global__ void lerp_kernel(SelState* state, float gamma, float* out3) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float a = __uint_as_float(state->key_a);
+  float b = a;
+  if (state->cnt_le <= state->k + 1ull && state->min_gt != 0xffffffffu) b = __uint_as_float(state->min_gt);
+  const float diff = __fsub_rn(b, a);
+  float r = __fadd_rn(a, __fmul_rn(diff, gamma));
+  if (gamma >= 0.5f) r = __fsub_rn(b, __fmul_rn(diff, __fsub_rn(1.0f, gamma)));
+  if (state->has_nan) r = __uint_as_float(0x7fc00000u);
+  out3[0] = r;
+  out3[1] = a;
+  out3[2] = b;
+}
+
+// ---- mask / apply ----------------------------------------------------------------------------------------
+template <bool WRITE_MASK, bool APPLY>
+__global__ void __launch_bounds__(THREADS) mask_kernel(const SegTable st, const Chunks ch, const float* __restrict__ thr_p) {
+  const float thr = *thr_p;
+  const long long nchunks = ch.cstart[st.nseg];
+  for (long long cid = blockIdx.x; cid < nchunks; cid += gridDim.x) {
+    const int s = find_seg(ch, st.nseg, cid);
+    const long long size = st.start[s + 1] - st.start[s];
+    const long long base = (cid - ch.cstart[s]) * CHUNK;
+    float* w = const_cast<float*>(st.ptr[s]);
+    float* m = st.out[s];
+    const bool aligned = ((reinterpret_cast<uintptr_t>(w) | (WRITE_MASK ? reinterpret_cast<uintptr_t>(m) : 0)) & 15) == 0;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const long long i = base + ((long long)it * THREADS + threadIdx.x) * 4;
+      if (aligned && i + 4 <= size) {
+        const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(w + i));
+        float4 mk;
+        mk.x = fabsf(v.x) > thr ? 1.f : 0.f;
+        mk.y = fabsf(v.y) > thr ? 1.f : 0.f;
+        mk.z = fabsf(v.z) > thr ? 1.f : 0.f;
+        mk.w = fabsf(v.w) > thr ? 1.f : 0.f;
+        if (WRITE_MASK) st_stream_f4(reinterpret_cast<float4*>(m + i), mk);
+        if (APPLY) {
+          float4 o;
+          o.x = __fmul_rn(v.x, mk.x);
+          o.y = __fmul_rn(v.y, mk.y);
+          o.z = __fmul_rn(v.z, mk.z);
+          o.w = __fmul_rn(v.w, mk.w);
+          st_stream_f4(reinterpret_cast<float4*>(w + i), o);
+        }
+      } else {
+        for (int j = 0; j < 4; ++j)
+          if (i + j < size) {
+            const float v = w[i + j];
+            const float mk = fabsf(v) > thr ? 1.f : 0.f;
+            if (WRITE_MASK) m[i + j] = mk;
+            if (APPLY) w[i + j] = __fmul_rn(v, mk);
+          }
+      }
+    }
+  }
+}
+
+// w *= mask (out[] of the table holds the mask pointers)
+__global__ void __launch_bounds__(THREADS) apply_masks_kernel(const SegTable st, const Chunks ch) {
+  const long long nchunks = ch.cstart[st.nseg];
+  for (long long cid = blockIdx.x; cid < nchunks; cid += gridDim.x) {
+    const int s = find_seg(ch, st.nseg, cid);
+    const long long size = st.start[s + 1] - st.start[s];
+    const long long base = (cid - ch.cstart[s]) * CHUNK;
+    float* w = const_cast<float*>(st.ptr[s]);
+    const float* m = st.out[s];
+    const bool aligned = ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(m)) & 15) == 0;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const long long i = base + ((long long)it * THREADS + threadIdx.x) * 4;
+      if (aligned && i + 4 <= size) {
+        const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(w + i));
+        const float4 k = ld_stream_f4(reinterpret_cast<const float4*>(m + i));
+        float4 o;
+        o.x = __fmul_rn(v.x, k.x);
+        o.y = __fmul_rn(v.y, k.y);
+        o.z = __fmul_rn(v.z, k.z);
+        o.w = __fmul_rn(v.w, k.w);
+        st_stream_f4(reinterpret_cast<float4*>(w + i), o);
+      } else {
+        for (int j = 0; j < 4; ++j)
+          if (i + j < size) w[i + j] = __fmul_rn(w[i + j], m[i + j]);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(THREADS) count_zeros_kernel(const SegTable st, const Chunks ch,
+                                                              unsigned long long* __restrict__ counts) {
+  __shared__ unsigned int s_cnt[MC_MAX_SEGMENTS];
+  if (threadIdx.x < MC_MAX_SEGMENTS) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const long long nchunks = ch.cstart[st.nseg];
+  for (long long cid = blockIdx.x; cid < nchunks; cid += gridDim.x) {
+    const int s = find_seg(ch, st.nseg, cid);
+    const long long size = st.start[s + 1] - st.start[s];
+    const long long base = (cid - ch.cstart[s]) * CHUNK;
+    const float* p = st.ptr[s];
+    const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+    unsigned int c = 0;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const long long i = base + ((long long)it * THREADS + threadIdx.x) * 4;
+      if (aligned && i + 4 <= size) {
+        const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(p + i));
+        c += (v.x == 0.f) + (v.y == 0.f) + (v.z == 0.f) + (v.w == 0.f);
+      } else {
+        for (int j = 0; j < 4; ++j)
+          if (i + j < size) c += (p[i + j] == 0.f);
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt[s], c);
+  }
+  __syncthreads();
+  if (threadIdx.x < st.nseg && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(THREADS) masked_residual_kernel(const SegTable st, const Chunks ch,
+                                                                  double* __restrict__ out) {
+  const long long nchunks = ch.cstart[st.nseg];
+  for (long long cid = blockIdx.x; cid < nchunks; cid += gridDim.x) {
+    const int s = find_seg(ch, st.nseg, cid);
+    const long long size = st.start[s + 1] - st.start[s];
+    const long long base = (cid - ch.cstart[s]) * CHUNK;
+    const float* w = st.ptr[s];
+    const float* m = st.out[s];
+    double acc = 0.0;
+    for (int it = 0; it < 2; ++it) {
+      const long long i = base + ((long long)it * THREADS + threadIdx.x) * 4;
+      for (int j = 0; j < 4; ++j)
+        if (i + j < size) acc += (double)(w[i + j] * fabsf(m[i + j] - 1.f));
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc != 0.0) atomicAdd(&out[s], acc);
+  }
+}
+
+int build_tables(SegTable* st, Chunks* ch, const float* const* ptrs, float* const* outs, const int64_t* sizes,
+                 int nseg, const char* who) {
+  if (nseg <= 0 || nseg > MC_MAX_SEGMENTS) return mc_set_error(MC_ERR_ARG, "%s: nseg %d out of range 1..%d", who, nseg, MC_MAX_SEGMENTS);
+  if (!ptrs || !sizes) return mc_set_error(MC_ERR_ARG, "%s: null table", who);
+  st->nseg = nseg;
+  st->start[0] = 0;
+  ch->cstart[0] = 0;
+  for (int s = 0; s < nseg; ++s) {
+    if (sizes[s] < 0 || (sizes[s] > 0 && !ptrs[s])) return mc_set_error(MC_ERR_ARG, "%s: segment %d invalid", who, s);
+    st->ptr[s] = ptrs[s];
+    st->out[s] = outs ? outs[s] : nullptr;
+    st->start[s + 1] = st->start[s] + sizes[s];
+    ch->cstart[s + 1] = ch->cstart[s] + (sizes[s] + CHUNK - 1) / CHUNK;
+  }
+  for (int s = nseg; s < MC_MAX_SEGMENTS; ++s) {
+    st->ptr[s] = nullptr;
+    st->out[s] = nullptr;
+    st->start[s + 1] = st->start[nseg];
+    ch->cstart[s + 1] = ch->cstart[nseg];
+  }
+  return 0;
+}
+
+int stream_grid(long long nchunks) {
+  long long g = (long long)mc_num_sms() * 8;
+  if (g > nchunks) g = nchunks;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+extern "C" size_t mc_workspace_bytes_kth_abs_select(int64_t n_total) {
+  if (n_total < 0) n_total = 0;
+  // state + worst-case candidate list (every element in one 12-bit bin, e.g. an already-pruned model)
+  return ((sizeof(SelState) + 255) / 256) * 256 + (size_t)n_total * sizeof(unsigned int) + 256;
+}
+
+extern "C" int mc_kth_abs_select(const float* const* h_seg_ptrs, const int64_t* h_seg_sizes, int nseg, int64_t k,
+                                 float gamma, float* d_out3, void* d_ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  SegTable st;
+  Chunks ch;
+  int rc = build_tables(&st, &ch, h_seg_ptrs, nullptr, h_seg_sizes, nseg, "mc_kth_abs_select");
+  if (rc) return rc;
+  const long long n = st.start[nseg];
+  MC_CHECK_ARG(n > 0, "mc_kth_abs_select: empty input");
+  MC_CHECK_ARG(k >= 0 && k < n, "mc_kth_abs_select: rank %lld out of range [0,%lld)", (long long)k, n);
+  MC_CHECK_ARG(d_out3 && d_ws, "mc_kth_abs_select: null output/workspace");
+  MC_CHECK_ARG(gamma >= 0.f && gamma < 1.f, "mc_kth_abs_select: gamma must be in [0,1)");
+  if (ws_bytes < mc_workspace_bytes_kth_abs_select(n))
+    return mc_set_error(MC_ERR_WS, "mc_kth_abs_select: workspace %zu < required %zu", ws_bytes,
+                        mc_workspace_bytes_kth_abs_select(n));
+  SelState* state = reinterpret_cast<SelState*>(d_ws);
+  const size_t state_bytes = ((sizeof(SelState) + 255) / 256) * 256;
+  unsigned int* cand = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(d_ws) + state_bytes);
+
+  MC_CUDA(cudaMemsetAsync(state, 0, sizeof(SelState), stream));
+  set_rank_kernel<<<1, 1, 0, stream>>>(state, (unsigned long long)k);
+  MC_LAUNCH_CHECK("set_rank_kernel");
+  const int grid = stream_grid(ch.cstart[nseg]);
+  hist0_kernel<<<grid, THREADS, 0, stream>>>(st, ch, state);
+  MC_LAUNCH_CHECK("hist0_kernel");
+  compact_kernel<<<grid, THREADS, 0, stream>>>(st, ch, state, cand, (unsigned long long)n);
+  MC_LAUNCH_CHECK("compact_kernel");
+  const int cgrid = mc_num_sms() * 2;
+  hist1_kernel<<<cgrid, THREADS, 0, stream>>>(state, cand);
+  MC_LAUNCH_CHECK("hist1_kernel");
+  hist2_kernel<<<cgrid, THREADS, 0, stream>>>(state, cand);
+  MC_LAUNCH_CHECK("hist2_kernel");
+  const int need_b = (gamma != 0.f && k + 1 < n) ? 1 : 0;
+  final_kernel<<<1, THREADS, 0, stream>>>(state, d_out3, need_b);
+  MC_LAUNCH_CHECK("final_kernel");
+  if (need_b) {
+    succ_kernel<<<grid, THREADS, 0, stream>>>(st, ch, state);
+    MC_LAUNCH_CHECK("succ_kernel");
+    lerp_kernel<<<1, 32, 0, stream>>>(state, gamma, d_out3);
+    MC_LAUNCH_CHECK("lerp_kernel");
+  }
+  return 0;
+}
+
+extern "C" int mc_mask_apply_gt(float* const* h_w_ptrs, float* const* h_mask_ptrs, const int64_t* h_seg_sizes,
+                                int nseg, const float* d_thr, int apply, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MC_CHECK_ARG(d_thr != nullptr, "mc_mask_apply_gt: null threshold pointer");
+  MC_CHECK_ARG(h_mask_ptrs != nullptr || apply, "mc_mask_apply_gt: nothing to do (no masks, no apply)");
+  SegTable st;
+  Chunks ch;
+  int rc = build_tables(&st, &ch, const_cast<const float* const*>(h_w_ptrs), h_mask_ptrs, h_seg_sizes, nseg,
+                        "mc_mask_apply_gt");
+  if (rc) return rc;
+  if (h_mask_ptrs)
+    for (int s = 0; s < nseg; ++s) MC_CHECK_ARG(h_mask_ptrs[s] || h_seg_sizes[s] == 0, "mc_mask_apply_gt: null mask %d", s);
+  if (ch.cstart[nseg] == 0) return 0;
+  const int grid = stream_grid(ch.cstart[nseg]);
+  if (h_mask_ptrs && apply) mask_kernel<true, true><<<grid, THREADS, 0, stream>>>(st, ch, d_thr);
+  else if (h_mask_ptrs) mask_kernel<true, false><<<grid, THREADS, 0, stream>>>(st, ch, d_thr);
+  else mask_kernel<false, true><<<grid, THREADS, 0, stream>>>(st, ch, d_thr);
+  MC_LAUNCH_CHECK("mask_kernel");
+  return 0;
+}
+
+extern "C" int mc_apply_masks(float* const* h_w_ptrs, const float* const* h_mask_ptrs, const int64_t* h_seg_sizes,
+                              int nseg, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MC_CHECK_ARG(h_mask_ptrs != nullptr, "mc_apply_masks: null mask table");
+  SegTable st;
+  Chunks ch;
+  int rc = build_tables(&st, &ch, const_cast<const float* const*>(h_w_ptrs),
+                        const_cast<float* const*>(reinterpret_cast<const float* const*>(h_mask_ptrs)), h_seg_sizes,
+                        nseg, "mc_apply_masks");
+  if (rc) return rc;
+  for (int s = 0; s < nseg; ++s) MC_CHECK_ARG(h_mask_ptrs[s] || h_seg_sizes[s] == 0, "mc_apply_masks: null mask %d", s);
+  if (ch.cstart[nseg] == 0) return 0;
+  apply_masks_kernel<<<stream_grid(ch.cstart[nseg]), THREADS, 0, stream>>>(st, ch);
+  MC_LAUNCH_CHECK("apply_masks_kernel");
+  return 0;
+}
+
+extern "C" int mc_count_zeros(const float* const* h_w_ptrs, const int64_t* h_seg_sizes, int nseg, int64_t* d_counts,
+                              void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MC_CHECK_ARG(d_counts != nullptr, "mc_count_zeros: null output");
+  SegTable st;
+  Chunks ch;
+  int rc = build_tables(&st, &ch, h_w_ptrs, nullptr, h_seg_sizes, nseg, "mc_count_zeros");
+  if (rc) return rc;
+  MC_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int64_t) * nseg, stream));
+  if (ch.cstart[nseg] == 0) return 0;
+  count_zeros_kernel<<<stream_grid(ch.cstart[nseg]), THREADS, 0, stream>>>(st, ch,
+                                                                           reinterpret_cast<unsigned long long*>(d_counts));
+  MC_LAUNCH_CHECK("count_zeros_kernel");
+  return 0;
+}
+
+extern "C" int mc_masked_residual(const float* const* h_w_ptrs, const float* const* h_mask_ptrs,
+                                  const int64_t* h_seg_sizes, int nseg, double* d_out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MC_CHECK_ARG(d_out != nullptr && h_mask_ptrs != nullptr, "mc_masked_residual: null pointer");
+  SegTable st;
+  Chunks ch;
+  int rc = build_tables(&st, &ch, h_w_ptrs, const_cast<float* const*>(reinterpret_cast<const float* const*>(h_mask_ptrs)),
+                        h_seg_sizes, nseg, "mc_masked_residual");
+  if (rc) return rc;
+  MC_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * nseg, stream));
+  if (ch.cstart[nseg] == 0) return 0;
+  masked_residual_kernel<<<stream_grid(ch.cstart[nseg]), THREADS, 0, stream>>>(st, ch, d_out);
+  MC_LAUNCH_CHECK("masked_residual_kernel");
+  return 0;
+}

@@ -1,0 +1,499 @@
+"""B200 forward engine behind ``Darknet.forward`` (reference: src/nets.py:720-774 walks nn.Modules; here the graph is
+compiled once into a list of libmcb200 kernel launches).
+
+Compile step (host, once per weight/mask version):
+  * BatchNorm (eval) is folded into a per-channel fp32 (scale, shift) applied in the conv epilogue
+    (nn.BatchNorm2d eps=1e-5, src/nets.py:802); leaky-ReLU(0.1) (:809) is fused in the same epilogue.
+  * conv weights (already multiplied by their mask — MaskedConv2d.forward, layers.py:59) are packed to bf16
+    [Npad, taps*Kc] K-major for the TMA/tcgen05 implicit GEMM.
+  * route/concat (:735-746) and Reorg (:648-667) become store addressing: conv20 and conv21 write disjoint channel
+    slices of one buffer; conv21's epilogue performs the space-to-depth shuffle.
+  * "physical shrink": a filter whose masked weights are all zero is removed from its layer and from every consumer's
+    input channels.  Its output is the constant leaky(shift[o]); when that constant is non-zero it is folded into the
+    consumers through ONE extra "ones" channel (value 1 inside the image, 0 in the padding, so border taps are
+    handled exactly).  With the reference's default BN statistics the constant is 0 and nothing is added.
+
+Activation layout between layers is PNHWC bf16 (include/mcb200.h).  There is no PyTorch/CPU fallback: a missing
+library, a CPU tensor or an unsupported cfg raises.
+"""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class _TensorRef(object):
+    """A logical activation: where it lives and how its physical channels map to the original channel space."""
+
+    def __init__(self, buf_id, H, W, c_orig, colsrc, const, ch_off=0):
+        self.buf_id = buf_id      # index into the buffer table
+        self.H, self.W = H, W
+        self.c_orig = c_orig      # channel count of the un-shrunk tensor
+        self.colsrc = colsrc      # list[int], len = physical channels: orig channel, -1 unused, -2 the ones channel
+        self.const = const        # float32 cpu tensor [c_orig]: value of removed channels (0 where kept)
+        self.ch_off = ch_off      # channel offset inside the buffer
+
+    @property
+    def c_phys(self):
+        return len(self.colsrc)
+
+
+class _Buf(object):
+    def __init__(self, H, W, ld, zero_init=False, fp32_nchw_channels=0):
+        self.H, self.W, self.ld = H, W, ld
+        self.zero_init = zero_init
+        self.fp32_nchw_channels = fp32_nchw_channels  # >0: this is the fp32 NCHW network output
+
+
+class CompiledDarknet(object):
+    def __init__(self, model, shrink=True):
+        self.lib = _lib.load()
+        params = list(model.parameters())
+        if not params:
+            raise RuntimeError("Darknet has no parameters")
+        self.device = params[0].device
+        _lib.require_cuda(params[0], "Darknet.forward")
+        with torch.cuda.device(self.device):
+            if self.lib.mc_device_ok() != 1:
+                raise RuntimeError("Darknet.forward: " + self.lib.mc_last_error_string().decode())
+        self.shrink = bool(shrink)
+        self.bufs = []       # list[_Buf] (shapes depend on input H, W: compiled for the cfg's width/height lazily)
+        self.ops = []        # list of dict
+        self.block_out = {}  # models index -> _TensorRef
+        self.flops_per_image = 0  # algorithmic (unpadded) conv FLOPs of the compiled (possibly shrunk) network
+        self._alloc = {}     # (B, H, W) -> list of tensors
+        self.in_hw = None
+        self._compile(model)
+
+    # ------------------------------------------------------------------------------------------------ compile
+    def _new_buf(self, H, W, ld, **kw):
+        self.bufs.append(_Buf(H, W, ld, **kw))
+        return len(self.bufs) - 1
+
+    def _compile(self, model):
+        blocks = model.blocks
+        H, W = model.height, model.width
+        if H % 32 or W % 32:
+            raise NotImplementedError("input size must be a multiple of 32 (cfg has %dx%d)" % (W, H))
+        self.in_hw = (H, W)
+        # which block outputs feed a 2-input route (concat)?  producer index -> (route index, slot)
+        cat_of = {}
+        ind = -2
+        for block in blocks:
+            ind += 1
+            if block['type'] == 'route':
+                layers = [int(i) if int(i) > 0 else int(i) + ind for i in block['layers'].split(',')]
+                if len(layers) == 2:
+                    cat_of[layers[0]] = (ind, 0)
+                    cat_of[layers[1]] = (ind, 1)
+                elif len(layers) != 1:
+                    raise NotImplementedError("route with %d inputs" % len(layers))
+        n_models = len(model.models)
+        last_conv = max(i for i, b in enumerate(blocks[1:]) if b['type'] == 'convolutional')
+
+        cur = None  # _TensorRef of the running activation; None = the fp32 NCHW input image
+        cur_hw = (H, W)
+        cat_state = {}  # route index -> dict(buf_id, parts)
+        ind = -2
+        skip_next_pool = False
+        for bi, block in enumerate(blocks):
+            ind += 1
+            btype = block['type']
+            if btype == 'net':
+                in_ch = int(block['channels'])
+                continue
+            if btype == 'convolutional':
+                seq = model.models[ind]
+                conv = seq[0]
+                bn = seq[1] if int(block['batch_normalize']) else None
+                act = block['activation']
+                if act not in ('leaky', 'linear'):
+                    raise NotImplementedError("activation '%s'" % act)
+                k = conv.kernel_size[0]
+                if conv.kernel_size != (k, k) or k not in (1, 3) or conv.stride != (1, 1) or \
+                        conv.padding != ((k - 1) // 2, (k - 1) // 2) or conv.groups != 1 or conv.dilation != (1, 1):
+                    raise NotImplementedError("conv %s is outside the B200 path (need k in {1,3}, stride 1, 'same' "
+                                              "padding)" % (conv,))
+                is_head = (ind == last_conv)
+                nxt = blocks[bi + 1] if bi + 1 < len(blocks) else None
+                nxt_is_pool = nxt is not None and nxt['type'] == 'maxpool' and int(nxt['size']) == 2 and \
+                    int(nxt['stride']) == 2
+                nxt_is_reorg = nxt is not None and nxt['type'] == 'reorg' and int(nxt['stride']) == 2
+                cur, fused = self._compile_conv(conv, bn, act == 'leaky', cur, cur_hw, in_ch, is_head, ind, cat_of,
+                                                cat_state, nxt_is_pool, nxt_is_reorg)
+                self.block_out[ind] = cur
+                if fused == 'pool':
+                    skip_next_pool = True
+                    cur_hw = (cur.H, cur.W)
+                elif fused == 'reorg':
+                    skip_next_pool = True  # the reorg block is already applied
+                    cur_hw = (cur.H, cur.W)
+            elif btype == 'maxpool':
+                if skip_next_pool:
+                    skip_next_pool = False
+                    self.block_out[ind] = cur
+                    continue
+                if int(block['size']) != 2 or int(block['stride']) != 2:
+                    raise NotImplementedError("maxpool size=%s stride=%s" % (block['size'], block['stride']))
+                src = cur
+                Ho, Wo = src.H // 2, src.W // 2
+                ld = _round_up(src.c_phys, 8)
+                bid = self._new_buf(Ho, Wo, ld)
+                self.ops.append(dict(kind='pool', src=src, dst_buf=bid, C=src.c_phys, name='pool@%d' % ind))
+                cur = _TensorRef(bid, Ho, Wo, src.c_orig, list(src.colsrc), src.const)
+                cur_hw = (Ho, Wo)
+                self.block_out[ind] = cur
+            elif btype == 'reorg':
+                if skip_next_pool:
+                    skip_next_pool = False
+                    self.block_out[ind] = cur
+                    continue
+                raise NotImplementedError("reorg that does not directly follow a convolution")
+            elif btype == 'route':
+                layers = [int(i) if int(i) > 0 else int(i) + ind for i in block['layers'].split(',')]
+                if len(layers) == 1:
+                    cur = self.block_out[layers[0]]
+                else:
+                    st = cat_state.get(ind)
+                    if st is None or len(st['parts']) != 2:
+                        raise NotImplementedError("concat inputs must both be produced by convolutions (cfg block %d)" % bi)
+                    p0, p1 = st['parts'][0], st['parts'][1]
+                    colsrc = list(p0.colsrc)
+                    have_ones = -2 in colsrc
+                    for c in p1.colsrc:
+                        if c >= 0:
+                            colsrc.append(c + p0.c_orig)
+                        elif c == -2 and not have_ones:
+                            colsrc.append(-2)
+                            have_ones = True
+                        else:
+                            colsrc.append(-1)
+                    cur = _TensorRef(st['buf_id'], p0.H, p0.W, p0.c_orig + p1.c_orig, colsrc,
+                                     torch.cat([p0.const, p1.const]))
+                cur_hw = (cur.H, cur.W)
+                self.block_out[ind] = cur
+            elif btype == 'region':
+                continue
+            else:
+                raise NotImplementedError("cfg block type '%s'" % btype)
+        self.out_ref = cur
+        del n_models
+
+    def _compile_conv(self, conv, bn, leaky, src, src_hw, in_ch, is_head, ind, cat_of, cat_state, nxt_is_pool,
+                      nxt_is_reorg):
+        dev = self.device
+        H, W = src_hw
+        w = conv.weight.data.float()
+        if getattr(conv, 'mask_flag', False):
+            w = w * conv.mask.to(dev)
+        O, Corig = w.shape[0], w.shape[1]
+        k = w.shape[2]
+        taps = k * k
+        # folded BN / bias
+        if bn is not None:
+            scale = bn.weight.data.float() / torch.sqrt(bn.running_var.float() + bn.eps)
+            shift = bn.bias.data.float() - bn.running_mean.float() * scale
+        else:
+            scale = torch.ones(O, device=dev)
+            shift = conv.bias.data.float() if conv.bias is not None else torch.zeros(O, device=dev)
+        # ---- input channel map
+        if src is None:
+            in_colsrc, in_const, c_in_orig = list(range(in_ch)), torch.zeros(in_ch), in_ch
+        else:
+            in_colsrc, in_const, c_in_orig = src.colsrc, src.const, src.c_orig
+        if c_in_orig != Corig:
+            raise RuntimeError("conv at block %d expects %d input channels, graph provides %d" % (ind, Corig, c_in_orig))
+        # ---- output channel set
+        if self.shrink and not is_head:
+            alive = (w.abs().amax(dim=(1, 2, 3)) > 0)
+            if not bool(alive.any()):
+                alive[0] = True  # keep the layer non-empty
+            keep = torch.nonzero(alive).flatten()
+        else:
+            keep = torch.arange(O, device=dev)
+        n_keep = int(keep.numel())
+        const_out = torch.zeros(O)
+        need_ones_out = False
+        if n_keep < O:
+            dead = torch.ones(O, dtype=torch.bool, device=dev)
+            dead[keep] = False
+            cval = shift.clone()
+            if leaky:
+                cval = torch.where(cval > 0, cval, 0.1 * cval)
+            cval = torch.where(dead, cval, torch.zeros_like(cval))
+            const_out = cval.cpu()
+            need_ones_out = bool((const_out != 0).any())
+        # a ones channel is also forwarded when the input has one and downstream may need it? No: each producer
+        # decides from its own removed filters only.
+        out_colsrc = [int(i) for i in keep.tolist()] + ([-2] if need_ones_out else [])
+        n_phys = len(out_colsrc)
+        # ---- packed weights in the PHYSICAL input-channel order
+        in_has_const = bool((in_const != 0).any())
+        w_aug = w
+        if in_has_const:
+            if -2 not in in_colsrc:
+                raise RuntimeError("internal: constant input channels without a ones channel")
+            w1 = torch.einsum('ocrs,c->ors', w, in_const.to(dev))  # combined weight of all removed channels
+            w_aug = torch.cat([w, w1[:, None]], dim=1)
+        cidx = [(c if c >= 0 else (Corig if (c == -2 and in_has_const) else -1)) for c in in_colsrc]
+        c_phys_in = len(cidx)
+        self.flops_per_image += 2 * H * W * n_keep * sum(1 for c in in_colsrc if c >= 0) * taps
+        o_list = [int(i) for i in keep.tolist()] + ([-1] if need_ones_out else [])
+        sc = torch.cat([scale[keep], torch.zeros(1, device=dev)]) if need_ones_out else scale[keep]
+        sh = torch.cat([shift[keep], torch.ones(1, device=dev)]) if need_ones_out else shift[keep]
+        Npad = _round_up(n_phys, 16)
+        scale_p = torch.zeros(Npad, device=dev)
+        shift_p = torch.zeros(Npad, device=dev)
+        scale_p[:n_phys] = sc
+        shift_p[:n_phys] = sh
+
+        # ---- first layer: direct kernel on the fp32 image, pool fused
+        if src is None:
+            if k == 3 and Corig == 3 and nxt_is_pool and n_phys <= 32:
+                w1st = torch.zeros(n_phys, 27, device=dev)
+                w1st[:n_keep] = w[keep].reshape(n_keep, 27)
+                Ho, Wo = H // 2, W // 2
+                ld = _round_up(n_phys, 8)
+                bid = self._new_buf(Ho, Wo, ld)
+                self.ops.append(dict(kind='conv1', w=w1st.contiguous(), scale=scale_p, shift=shift_p, dst_buf=bid,
+                                     N=n_phys, H=H, W=W, ld=ld, pool=1, name='conv1+pool@%d' % ind))
+                return _TensorRef(bid, Ho, Wo, O, out_colsrc, const_out), 'pool'
+            # generic: pack the image to PNHWC (C=3 -> pitch 8) and run the tensor-core kernel
+            bid_in = self._new_buf(H, W, 8)
+            self.ops.append(dict(kind='pack_input', dst_buf=bid_in, C=in_ch, H=H, W=W, name='pack_input'))
+            src = _TensorRef(bid_in, H, W, in_ch, list(range(in_ch)), torch.zeros(in_ch))
+
+        Kc = _round_up(c_phys_in, 64)
+        wpack = torch.empty(Npad, taps * Kc, dtype=torch.bfloat16, device=dev)
+        oidx_t = torch.tensor(o_list, dtype=torch.int32, device=dev)
+        cidx_t = torch.tensor(cidx, dtype=torch.int32, device=dev)
+        w_src = w_aug.contiguous()
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.mc_pack_conv_weights(w_src.data_ptr(), None, w_src.shape[0], w_src.shape[1], k,
+                                                     oidx_t.data_ptr(), n_phys, cidx_t.data_ptr(), c_phys_in,
+                                                     wpack.data_ptr(), Npad, Kc, _lib.stream_ptr()),
+                       "mc_pack_conv_weights")
+        op = dict(kind='conv', src=src, wpack=wpack, scale=scale_p, shift=shift_p, N=n_phys, Npad=Npad, ksize=k,
+                  leaky=int(leaky), Cin=c_phys_in, name='conv@%d' % ind, H=H, W=W)
+        fused = None
+        if is_head:
+            bid = self._new_buf(H, W, 0, fp32_nchw_channels=n_phys)
+            op.update(epi=_lib.MC_EPI_NCHW_F32, dst_buf=bid, ldc=0, ch_off=0)
+            out = _TensorRef(bid, H, W, O, out_colsrc, const_out)
+        elif nxt_is_reorg and (ind + 1) in cat_of:
+            route, slot = cat_of[ind + 1]
+            Ho, Wo = H // 2, W // 2
+            st = cat_state.setdefault(route, dict(buf_id=None, parts={}, pending=[]))
+            colsrc4 = []
+            for q in range(4):
+                for c in out_colsrc:
+                    colsrc4.append(c + q * O if c >= 0 else (c if (c == -2 and q == 0) else -1))
+            out = _TensorRef(None, Ho, Wo, 4 * O, colsrc4, const_out.repeat(4))
+            op.update(epi=_lib.MC_EPI_REORG2)
+            st['parts'][slot] = out
+            st['pending'].append((op, slot))
+            fused = 'reorg'
+        elif ind in cat_of:
+            route, slot = cat_of[ind]
+            st = cat_state.setdefault(route, dict(buf_id=None, parts={}, pending=[]))
+            out = _TensorRef(None, H, W, O, out_colsrc, const_out)
+            op.update(epi=_lib.MC_EPI_PNHWC)
+            st['parts'][slot] = out
+            st['pending'].append((op, slot))
+        else:
+            ld = _round_up(n_phys, 8)
+            bid = self._new_buf(H, W, ld)
+            op.update(epi=_lib.MC_EPI_PNHWC, dst_buf=bid, ldc=ld, ch_off=0)
+            out = _TensorRef(bid, H, W, O, out_colsrc, const_out)
+        self.ops.append(op)
+        # resolve a concat once both producers are known
+        for route, st in cat_state.items():
+            if st['buf_id'] is None and len(st['parts']) == 2:
+                p0, p1 = st['parts'][0], st['parts'][1]
+                if (p0.H, p0.W) != (p1.H, p1.W):
+                    raise NotImplementedError("concat of different resolutions")
+                ld = _round_up(p0.c_phys + p1.c_phys, 8)
+                st['buf_id'] = self._new_buf(p0.H, p0.W, ld, zero_init=True)
+                for pop, slot in st['pending']:
+                    pop.update(dst_buf=st['buf_id'], ldc=ld, ch_off=0 if slot == 0 else p0.c_phys)
+                p0.buf_id = p1.buf_id = st['buf_id']
+                p1.ch_off = p0.c_phys
+        return out, fused
+
+    # ------------------------------------------------------------------------------------------------ run
+    def _buffers(self, B, H, W):
+        key = (B, H, W)
+        got = self._alloc.get(key)
+        if got is not None:
+            return got
+        if (H, W) != self.in_hw:
+            raise NotImplementedError("this plan was compiled for %dx%d inputs (cfg width/height); got %dx%d" %
+                                      (self.in_hw[1], self.in_hw[0], W, H))
+        tensors = []
+        for b in self.bufs:
+            if b.fp32_nchw_channels:
+                tensors.append(None)  # allocated per call (returned to the caller)
+            else:
+                rows = B * (b.H + 1) * (b.W + 1)
+                f = torch.zeros if b.zero_init else torch.empty
+                tensors.append(f(rows, b.ld, dtype=torch.bfloat16, device=self.device))
+        self._alloc[key] = tensors
+        return tensors
+
+    def run(self, x):
+        if x.dim() != 4:
+            raise ValueError("expected [B,3,H,W] input")
+        _lib.require_cuda(x, "Darknet.forward")
+        if x.device != self.device:
+            raise RuntimeError("input on %s, model on %s" % (x.device, self.device))
+        x = x.detach()
+        if x.dtype != torch.float32:
+            x = x.float()
+        x = x.contiguous()
+        B, _, H, W = x.shape
+        lib = self.lib
+        with torch.cuda.device(self.device):
+            bufs = list(self._buffers(B, H, W))
+            stream = _lib.stream_ptr()
+            out = None
+            for op in self.ops:
+                kind = op['kind']
+                if kind == 'conv1':
+                    _lib.check(lib.mc_conv1_fwd(x.data_ptr(), op['w'].data_ptr(), op['scale'].data_ptr(),
+                                                op['shift'].data_ptr(), bufs[op['dst_buf']].data_ptr(), B, op['H'],
+                                                op['W'], op['N'], op['ld'], op['pool'], stream), op['name'])
+                elif kind == 'pack_input':
+                    _lib.check(lib.mc_pack_pnhwc(x.data_ptr(), bufs[op['dst_buf']].data_ptr(), B, op['H'], op['W'],
+                                                 op['C'], 8, stream), op['name'])
+                elif kind == 'pool':
+                    s = op['src']
+                    sb = self.bufs[s.buf_id]
+                    if s.ch_off != 0:
+                        raise NotImplementedError("maxpool on a channel slice")
+                    _lib.check(lib.mc_maxpool2x2(bufs[s.buf_id].data_ptr(), bufs[op['dst_buf']].data_ptr(), B, s.H, s.W,
+                                                 op['C'], sb.ld, self.bufs[op['dst_buf']].ld, stream), op['name'])
+                elif kind == 'conv':
+                    s = op['src']
+                    d = _lib.mc_conv_desc()
+                    sb = self.bufs[s.buf_id]
+                    d.d_in = bufs[s.buf_id].data_ptr() + 2 * s.ch_off
+                    d.d_wpack = op['wpack'].data_ptr()
+                    d.d_scale = op['scale'].data_ptr()
+                    d.d_shift = op['shift'].data_ptr()
+                    if op['epi'] == _lib.MC_EPI_NCHW_F32:
+                        out = torch.empty(B, op['N'], op['H'], op['W'], dtype=torch.float32, device=self.device)
+                        bufs[op['dst_buf']] = out
+                    d.d_out = bufs[op['dst_buf']].data_ptr()
+                    d.B, d.H, d.W = B, op['H'], op['W']
+                    d.Cin, d.Cin_ld = op['Cin'], sb.ld
+                    d.N, d.Npad = op['N'], op['Npad']
+                    d.ksize, d.leaky, d.epi_mode = op['ksize'], op['leaky'], op['epi']
+                    d.ldc, d.ch_off = op['ldc'], op['ch_off']
+                    d.block_n = op.get('block_n', 0)
+                    d.stages = op.get('stages', 0)
+                    _lib.check(lib.mc_conv_fwd(ctypes.byref(d), stream), op['name'])
+                else:
+                    raise RuntimeError("unknown op " + kind)
+            self._last_bufs = bufs
+        return out
+
+    @property
+    def num_launches(self):
+        """kernel launches per forward (conv1 = 2: pad clear + conv)."""
+        return sum(2 if op['kind'] == 'conv1' else 1 for op in self.ops)
+
+    def block_activation(self, ind):
+        """fp32 NCHW view (in the ORIGINAL channel space) of the output of models[ind] from the last run — for the
+        per-block parity tests.  Removed channels are filled with their folded constant."""
+        ref = self.block_out[ind]
+        bufs = self._last_bufs
+        t = bufs[ref.buf_id]
+        if t.dtype == torch.float32:
+            return t
+        B = t.shape[0] // ((ref.H + 1) * (ref.W + 1))
+        phys = torch.empty(B, ref.c_phys, ref.H, ref.W, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mc_unpack_pnhwc(t.data_ptr(), phys.data_ptr(), B, ref.H, ref.W, ref.c_phys,
+                                                self.bufs[ref.buf_id].ld, ref.ch_off, _lib.stream_ptr()),
+                       "mc_unpack_pnhwc")
+        full = ref.const.to(self.device).view(1, -1, 1, 1).expand(B, ref.c_orig, ref.H, ref.W).clone()
+        for p, c in enumerate(ref.colsrc):
+            if c >= 0:
+                full[:, c] = phys[:, p]
+        return full
+
+
+def _plan_key(model):
+    vers = []
+    for p in model.parameters():
+        vers.append(p._version)
+        vers.append(p.data_ptr())
+    for b in model.buffers():
+        vers.append(b._version)
+        vers.append(b.data_ptr())
+    for m in model.modules():
+        e = getattr(m, '_mask_epoch', None)
+        if e is not None:
+            vers.append(e)
+    return (bool(getattr(model, 'b200_shrink', True)), tuple(vers))
+
+
+def compile_darknet(model, force=False):
+    key = _plan_key(model)
+    if force or model._b200_plan is None or model._b200_plan_key != key:
+        model._b200_plan = CompiledDarknet(model, shrink=key[0])
+        model._b200_plan_key = key
+    return model._b200_plan
+
+
+def darknet_forward(model, x):
+    if model.training:
+        raise NotImplementedError(
+            "Darknet.forward in training mode (batch-statistics BatchNorm + backward, src/train.py:221-235) is not "
+            "built yet; call model.eval() for the inference/eval path (SURVEY.md §8a-12 is tracked in DESIGN.md).")
+    return compile_darknet(model).run(x)
+
+
+def single_conv_forward(conv, x):
+    """Stand-alone MaskedConv2d.forward (layers.py:53-64) through the same tcgen05 kernel: fp32 NCHW in/out."""
+    lib = _lib.load()
+    _lib.require_cuda(x, "MaskedConv2d.forward")
+    k = conv.kernel_size[0]
+    if conv.kernel_size != (k, k) or k not in (1, 3) or conv.stride != (1, 1) or \
+            conv.padding != ((k - 1) // 2, (k - 1) // 2) or conv.groups != 1 or conv.dilation != (1, 1):
+        raise NotImplementedError("MaskedConv2d on the B200 path needs k in {1,3}, stride 1, 'same' padding")
+    dev = x.device
+    x = x.detach().float().contiguous()
+    B, C, H, W = x.shape
+    w = conv.weight.data.float().contiguous()
+    mask = conv.mask.to(dev).contiguous() if getattr(conv, 'mask_flag', False) else None
+    O = w.shape[0]
+    ld_in, Kc, Npad, ld_out = _round_up(C, 8), _round_up(C, 64), _round_up(O, 16), _round_up(O, 8)
+    xin = torch.empty(B * (H + 1) * (W + 1), ld_in, dtype=torch.bfloat16, device=dev)
+    wpack = torch.empty(Npad, k * k * Kc, dtype=torch.bfloat16, device=dev)
+    scale = torch.zeros(Npad, device=dev)
+    shift = torch.zeros(Npad, device=dev)
+    scale[:O] = 1
+    if conv.bias is not None:
+        shift[:O] = conv.bias.data.float()
+    yb = torch.empty(B * (H + 1) * (W + 1), ld_out, dtype=torch.bfloat16, device=dev)
+    y = torch.empty(B, O, H, W, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        s = _lib.stream_ptr()
+        _lib.check(lib.mc_pack_pnhwc(x.data_ptr(), xin.data_ptr(), B, H, W, C, ld_in, s), "mc_pack_pnhwc")
+        _lib.check(lib.mc_pack_conv_weights(w.data_ptr(), None if mask is None else mask.data_ptr(), O, C, k, None, O,
+                                            None, C, wpack.data_ptr(), Npad, Kc, s), "mc_pack_conv_weights")
+        d = _lib.mc_conv_desc()
+        d.d_in, d.d_wpack, d.d_scale, d.d_shift, d.d_out = (xin.data_ptr(), wpack.data_ptr(), scale.data_ptr(),
+                                                            shift.data_ptr(), yb.data_ptr())
+        d.B, d.H, d.W, d.Cin, d.Cin_ld, d.N, d.Npad = B, H, W, C, ld_in, O, Npad
+        d.ksize, d.leaky, d.epi_mode, d.ldc, d.ch_off, d.block_n, d.stages = k, 0, _lib.MC_EPI_PNHWC, ld_out, 0, 0, 0
+        _lib.check(lib.mc_conv_fwd(ctypes.byref(d), s), "mc_conv_fwd")
+        _lib.check(lib.mc_unpack_pnhwc(yb.data_ptr(), y.data_ptr(), B, H, W, O, ld_out, 0, s), "mc_unpack_pnhwc")
+    return y

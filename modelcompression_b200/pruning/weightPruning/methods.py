@@ -1,0 +1,150 @@
+"""Drop-in for src/pruning/weightPruning/methods.py of the reference: weight_prune (:9-26) and
+quick_filter_prune (:28-78), computed on the GPU by libmcb200 (no device->host copy of the weights).
+
+Host-side logic kept here is the data-independent part of ``np.percentile``: the rank ``k`` and interpolation
+weight ``gamma`` of the 'linear' method, evaluated in the SAME dtype NumPy 2.x uses (float32 for the float32
+magnitude array of weight_prune, float64 for the float64 value array of quick_filter_prune).
+``prune_one_filter`` / ``filter_prune`` (methods.py:81-142) are not on the hot path.
+"""
+import numpy as np
+import torch
+
+from ... import _lib
+
+
+def percentile_rank(n, pruning_perc, dtype):
+    """(k, gamma) such that np.percentile(a, pruning_perc) == _lerp(sorted(a)[k], sorted(a)[k+1], gamma) for an
+    array ``a`` of ``n`` elements of ``dtype`` (NumPy >= 2.0, method='linear').
+
+    Follows numpy/lib/_function_base_impl.py: percentile() divides by ``a.dtype.type(100)`` so a Python-float
+    percentage takes the data dtype; _quantile(): virtual_index = (n-1)*q in that dtype; _get_indexes():
+    previous = floor(virtual_index), clipped when virtual_index >= n-1; _get_gamma(): fractional part."""
+    dtype = np.dtype(dtype)
+    q = np.true_divide(pruning_perc, dtype.type(100) if dtype.kind == "f" else 100)
+    if not (0 <= q <= 1):
+        raise ValueError("Percentiles must be in the range [0, 100]")
+    virtual_index = np.asanyarray((n - 1) * q)
+    if virtual_index >= n - 1:
+        return n - 1, 0.0
+    if virtual_index < 0:
+        return 0, 0.0
+    previous = np.floor(virtual_index).astype(np.intp)
+    gamma = np.asanyarray(virtual_index - previous).astype(virtual_index.dtype)
+    return int(previous), float(gamma)
+
+
+def _prunable(model, conv_only):
+    params = []
+    for p in model.parameters():
+        nd = p.dim()
+        if (nd == 4) if conv_only else (nd != 1):
+            _lib.require_cuda(p, "weight_prune / quick_filter_prune")
+            if p.dtype != torch.float32:
+                raise TypeError("pruners expect float32 parameters, got %s" % p.dtype)
+            params.append(p.data if p.data.is_contiguous() else p.data.contiguous())
+    return params
+
+
+def weight_threshold(params, pruning_perc):
+    """Device tensor [3] = (thr, sorted|w|[k], sorted|w|[k+1]) for the global magnitude percentile."""
+    lib = _lib.load()
+    n = sum(p.numel() for p in params)
+    k, gamma = percentile_rank(n, pruning_perc, np.float32)
+    dev = params[0].device
+    segs = params
+    if len(segs) > _lib.MC_MAX_SEGMENTS:  # rare: more tensors than one launch takes -> select on a flat copy
+        segs = [torch.cat([p.reshape(-1) for p in params])]
+    ws_bytes = lib.mc_workspace_bytes_kth_abs_select(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    out3 = torch.empty(3, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.mc_kth_abs_select(_lib.ptr_array(segs), _lib.int64_array([t.numel() for t in segs]), len(segs),
+                                         k, gamma, out3.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr()),
+                   "mc_kth_abs_select")
+    return out3
+
+
+def weight_prune(model, pruning_perc):
+    '''
+    Prune pruning_perc% weights globally (not layer-wise)
+    arXiv: 1606.09274
+
+    methods.py:9-26.  Returns one float32 {0,1} mask per parameter with dim != 1, in model.parameters() order, on
+    the parameter's device: mask = |w| > np.percentile(|all w|, pruning_perc) (strict; ties are pruned).
+    '''
+    lib = _lib.load()
+    params = _prunable(model, conv_only=False)
+    if not params:
+        return []
+    out3 = weight_threshold(params, pruning_perc)
+    masks = [torch.empty_like(p) for p in params]
+    dev = params[0].device
+    with torch.cuda.device(dev):
+        for lo in range(0, len(params), _lib.MC_MAX_SEGMENTS):
+            grp, mgrp = params[lo:lo + _lib.MC_MAX_SEGMENTS], masks[lo:lo + _lib.MC_MAX_SEGMENTS]
+            _lib.check(lib.mc_mask_apply_gt(_lib.ptr_array(grp), _lib.ptr_array(mgrp),
+                                            _lib.int64_array([t.numel() for t in grp]), len(grp), out3.data_ptr(), 0,
+                                            _lib.stream_ptr()), "mc_mask_apply_gt")
+    return masks
+
+
+def filter_values(params):
+    """Normalised per-filter values of every conv weight, concatenated (device float32 [sum O])."""
+    lib = _lib.load()
+    if len(params) > _lib.MC_MAX_SEGMENTS:
+        raise NotImplementedError("quick_filter_prune: more than %d conv layers" % _lib.MC_MAX_SEGMENTS)
+    dev = params[0].device
+    O = [p.shape[0] for p in params]
+    values = torch.empty(sum(O), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.mc_filter_values(_lib.ptr_array(params), _lib.int_array(O),
+                                        _lib.int_array([p.shape[1] for p in params]),
+                                        _lib.int_array([p.shape[2] for p in params]),
+                                        _lib.int_array([p.shape[3] for p in params]), len(params),
+                                        values.data_ptr(), _lib.stream_ptr()), "mc_filter_values")
+    return values
+
+
+def quick_filter_prune(model, pruning_perc, return_keep=False):
+    '''
+    Prune pruning_perc% filters globally
+
+    methods.py:28-78.  Per conv weight: v = mean(w^2) per filter (float32, NumPy summation order), v /= ||v||_2,
+    v /= max(v); thr = float64 np.percentile over all layers; mask[o] = 0 where v[o] < thr.  Returns full-shape
+    float32 masks in parameter order.  (The reference returns CPU tensors built from NumPy, methods.py:77, and
+    set_mask moves them to the GPU; here they are created on the parameters' device.)
+    With return_keep=True also returns the per-layer surviving-filter index tensors (int64, ascending).
+    '''
+    lib = _lib.load()
+    params = _prunable(model, conv_only=True)
+    if not params:
+        return ([], []) if return_keep else []
+    dev = params[0].device
+    values = filter_values(params)
+    n = values.numel()
+    k, gamma = percentile_rank(n, pruning_perc, np.float64)
+    thr = torch.empty(1, dtype=torch.float64, device=dev)
+    masks = [torch.empty_like(p) for p in params]
+    keep = torch.empty(n, dtype=torch.uint8, device=dev)
+    O = [p.shape[0] for p in params]
+    per = [p.numel() // p.shape[0] for p in params]
+    with torch.cuda.device(dev):
+        _lib.check(lib.mc_filter_threshold(values.data_ptr(), n, k, gamma, thr.data_ptr(), None, 0,
+                                           _lib.stream_ptr()), "mc_filter_threshold")
+        _lib.check(lib.mc_filter_masks(values.data_ptr(), thr.data_ptr(), _lib.int_array(O), _lib.int_array(per),
+                                       len(params), _lib.ptr_array(masks), keep.data_ptr(), _lib.stream_ptr()),
+                   "mc_filter_masks")
+    if not return_keep:
+        return masks
+    keep_idx = [torch.nonzero(kp, as_tuple=False).flatten() for kp in torch.split(keep, O)]
+    return masks, keep_idx
+
+
+def prune_one_filter(model, masks):
+    raise NotImplementedError("prune_one_filter (methods.py:81-126) is not on the B200 hot path: the reference's "
+                              "train path calls weight_prune / quick_filter_prune only (src/train.py:168-171)")
+
+
+def filter_prune(model, pruning_perc):
+    raise NotImplementedError("filter_prune (methods.py:129-142) is not on the B200 hot path: the reference's "
+                              "train path calls weight_prune / quick_filter_prune only (src/train.py:168-171)")

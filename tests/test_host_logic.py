@@ -1,0 +1,130 @@
+"""CPU: host-side logic that mirrors the reference interface (cfg parsing, module tree, percentile rank arithmetic,
+weights IO, sharding helpers)."""
+import numpy as np
+import pytest
+import torch
+
+import modelcompression_b200 as mc
+from modelcompression_b200.eval import compact_detections, shard_range
+from modelcompression_b200.pruning.weightPruning.methods import percentile_rank
+from modelcompression_b200.pruning.weightPruning.utils import arg_nonzero_min
+
+
+def _lerp(a, b, t):
+    d = b - a
+    r = a + d * t
+    if t >= 0.5:
+        r = b - d * (1 - t)
+    return r
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_percentile_rank_matches_numpy(dtype):
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 3, 17, 1000, 10461, 65537):
+        a = np.abs(rng.standard_normal(n)).astype(dtype)
+        s = np.sort(a)
+        for perc in (0., 0.01, 5., 20., 33.3, 40., 50., 60., 70., 75., 80., 90., 99.99, 100.):
+            k, g = percentile_rank(n, perc, dtype)
+            got = _lerp(s[k], s[min(k + 1, n - 1)], dtype(g))
+            assert got == np.percentile(a, perc), (n, perc)
+
+
+def test_percentile_rank_darknet_float32_virtual_index():
+    # n = 50,634,592 float32 magnitudes -> the virtual index is evaluated in float32
+    n = 50634592
+    assert percentile_rank(n, 70., np.float32) == (35444212, 0.0)
+    assert percentile_rank(n, 75., np.float32) == (37975944, 0.0)
+    assert percentile_rank(n, 80., np.float32) == (40507676, 0.0)
+    assert percentile_rank(n, 90., np.float32) == (45571132, 0.0)
+    # 10,461 filters, float64: integer ranks at 20/40/60/80 %
+    assert [percentile_rank(10461, p, np.float64)[0] for p in (20., 40., 60., 80.)] == [2092, 4184, 6276, 8368]
+    with pytest.raises(ValueError):
+        percentile_rank(10, 101., np.float32)
+
+
+def test_parse_cfg_and_module_tree(cfg_path):
+    blocks = mc.parse_cfg(cfg_path)
+    assert blocks[0]['type'] == 'net' and blocks[-1]['type'] == 'region'
+    assert sum(b['type'] == 'convolutional' for b in blocks) == 23
+    assert sum(b['type'] == 'maxpool' for b in blocks) == 5
+    assert blocks[-2]['batch_normalize'] == 0  # default for [convolutional] without the key
+    model = mc.Darknet(cfg_path)
+    assert len(model.models) == 32
+    assert sum(p.numel() for p in model.parameters()) == 50655389  # README.md:34 of the reference
+    assert sum(p.numel() for p in model.parameters() if p.dim() != 1) == 50634592
+    assert (model.width, model.height, model.num_anchors, model.num_classes) == (416, 416, 5, 20)
+    assert model.anchor_step == 2.0 and len(model.anchors) == 10
+    keys = list(model.state_dict().keys())
+    assert keys[0] == 'models.0.conv1.weight' and 'models.30.conv23.bias' in keys
+    assert 'models.29.bn22.running_var' in keys and 'models.0.bn1.num_batches_tracked' in keys
+    convs = model.masked_convs()
+    assert len(convs) == 23 and all(c.name == 'MaskedConv2d' and c.mask_flag is False for c in convs)
+    # 1x1 convs get padding 0 although the cfg says pad=1 (nets.py:796)
+    assert model.models[5][0].padding == (0, 0) and model.models[4][0].padding == (1, 1)
+    with pytest.raises(ValueError):
+        model.set_masks([])
+
+
+def test_parse_cfg_type_key(tmp_path):
+    p = tmp_path / 'x.cfg'
+    p.write_text("[net]\nwidth=32\nheight=32\nchannels=3\n# comment\n\n[cost]\ntype=sse\n")
+    blocks = mc.parse_cfg(str(p))
+    assert blocks[1] == {'type': 'cost', '_type': 'sse'}
+
+
+def test_weights_file_roundtrip(cfg_path, tmp_path):
+    torch.manual_seed(5)
+    a = mc.Darknet(cfg_path)
+    for m in a.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_()
+            m.running_var.uniform_(0.5, 1.5)
+    a.seen = 12345
+    path = str(tmp_path / 'w.weights')
+    a.save_weights(path)
+    # header = 4 x int32 (0,0,0,seen) + 50,655,389 + 20,672 running stats floats
+    n_float = sum(p.numel() for p in a.parameters()) + sum(m.num_features * 2 for m in a.modules()
+                                                         if isinstance(m, torch.nn.BatchNorm2d))
+    import os
+    assert os.path.getsize(path) == 16 + 4 * n_float
+    b = mc.Darknet(cfg_path)
+    b.load_weights(path)
+    assert b.seen == 12345
+    sa, sb = a.state_dict(), b.state_dict()
+    for k in sa:
+        if not k.endswith('num_batches_tracked'):
+            assert torch.equal(sa[k], sb[k]), k
+
+
+def test_arg_nonzero_min_reference_quirks():
+    assert arg_nonzero_min([0.0, 3.0, 2.0, 5.0]) == (2.0, 2)
+    assert arg_nonzero_min([]) is None
+    assert arg_nonzero_min([4.0, 0.0]) == (np.inf, np.inf)  # only nonzero at index 0 -> "all zero" (reference quirk)
+
+
+def test_bbox_iou_host():
+    a = [0.5, 0.5, 0.2, 0.2]
+    assert mc.bbox_iou(a, a, x1y1x2y2=False) == pytest.approx(1.0)
+    assert mc.bbox_iou(a, [0.9, 0.9, 0.1, 0.1], x1y1x2y2=False) == 0.0
+    assert mc.bbox_iou([0, 0, 2, 2], [1, 1, 3, 3]) == pytest.approx(1.0 / 7.0)
+
+
+def test_shard_range_covers_everything():
+    for n in (0, 1, 7, 64, 4952):
+        for world in (1, 2, 4, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (a, b), (c, d) in zip(spans, spans[1:]):
+                assert b == c and a <= b and c <= d
+    assert shard_range(4952, 7, 8) == (4333, 4952) and shard_range(4952, 0, 8) == (0, 619)
+
+
+def test_compact_detections_order():
+    boxes = torch.arange(2 * 4 * 8, dtype=torch.float32).view(2, 4, 8)
+    keep = torch.tensor([[2, 0, 0, 0], [3, 1, 2, 0]], dtype=torch.int32)
+    kc = torch.tensor([2, 3], dtype=torch.int32)
+    det = compact_detections(boxes, keep, kc, first_image_index=10)
+    assert det.shape == (5, 8)
+    assert det[:, 0].tolist() == [10, 10, 11, 11, 11]
+    assert torch.equal(det[0, 1:], boxes[0, 2, :7]) and torch.equal(det[4, 1:], boxes[1, 2, :7])
