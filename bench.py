@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path (BASELINE.json: "YOLOv2-416 pruned-fwd images/sec ...; prune-mask ms vs
+HBM roofline").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): YOLOv2-VOC, seed-0 default init, 40 % global filter pruning
+(quick_filter_prune) with the pruned filters PHYSICALLY removed, bf16 forward, batch 64 per GPU, 416x416 synthetic
+images.  One step = one forward over one batch.  Under torchrun each rank runs the same per-GPU batch on its own
+images (weak scaling, weights replicated, no data-path collective); the timed region is bracketed by
+barrier + synchronize and the elapsed time is the max over ranks.
+
+`--impl reference` times the CPU path (oracle port of the reference's PyTorch forward: same F.conv2d / batch_norm /
+leaky_relu / max_pool2d calls, same masked weights) on the host cores, on a bounded sample per step.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BATCH = 64
+IMG = 416
+PRUNE_PERC = 40.0
+METRIC = "yolov2_416_pruned_fwd_images_per_sec"
+CPU_SAMPLE_BATCH = 4
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p.get('hbm_gbs', 6650.0), bf16=p.get('bf16_tflops', 1590.0),
+                    bf16_sustained=p.get('bf16_tflops_sustained', 1400.0), source='measured')
+    return dict(hbm_gbs=6650.0, bf16=1590.0, bf16_sustained=1400.0, source='fallback')
+
+
+class ClockSampler(object):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {'hw_slowdown': 0x8, 'sw_power_cap': 0x4, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20,
+                 'hw_power_brake': 0x80, 'sync_boost': 0x10}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.01)
+
+    def start(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def build_pruned_model(device):
+    """seed-0 default-init Darknet, 40 % filter pruning applied with set_masks (reference flow: src/train.py:167-174)."""
+    import torch
+    import modelcompression_b200 as mc
+    torch.manual_seed(0)
+    model = mc.Darknet(mc.write_yolov2_voc_cfg()).to(device).eval()
+    masks, keep = mc.quick_filter_prune(model, PRUNE_PERC, return_keep=True)
+    model.set_masks(masks)
+    model.b200_shrink = True
+    return model, masks, keep
+
+
+def cpu_forward_sample(state, blocks, batch, steps, warmup=1):
+    """Oracle port of the reference forward on the host cores.  Returns (images/s, seconds per step)."""
+    import torch
+    from oracle import forward_oracle
+    torch.manual_seed(1)
+    x = torch.rand(batch, 3, IMG, IMG)
+    with torch.no_grad():
+        for _ in range(warmup):
+            forward_oracle.darknet_forward_fp32(blocks, state, x)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            forward_oracle.darknet_forward_fp32(blocks, state, x)
+        dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps
+
+
+def run_reference_arm(args, rank):
+    """CPU implementation of the path (oracle port; the reference itself is Python and cannot travel to the box)."""
+    if rank != 0:
+        return
+    import torch
+    import modelcompression_b200 as mc
+    from oracle import prune_oracle
+    torch.manual_seed(0)
+    model = mc.Darknet(mc.write_yolov2_voc_cfg()).eval()
+    cw = [p.data.numpy() for p in model.parameters() if p.dim() == 4]
+    _, _, _, masks = prune_oracle.quick_filter_prune_np(cw, PRUNE_PERC)
+    state = dict(model.state_dict())
+    for (name, p), m in zip([(n, p) for n, p in model.named_parameters() if p.dim() == 4], masks):
+        state[name] = p.data * torch.from_numpy(m)  # set_mask: weight.data *= mask (layers.py:46)
+    cores = torch.get_num_threads()
+    ips, sps = cpu_forward_sample(state, model.blocks, CPU_SAMPLE_BATCH, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "yolov2-voc-416 40% filter-pruned (masked) forward, CPU oracle port of the reference "
+                               "PyTorch path", "batch_per_step": CPU_SAMPLE_BATCH, "prune": "quick_filter_prune 40%"},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": "%d steps of batch %d (each step is a bounded sample of the batch-64 workload)" %
+                                   (args.steps, CPU_SAMPLE_BATCH)},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def time_masks(model_dense, peaks):
+    """prune-mask ms vs the HBM roofline: weight_prune = 12n bytes, quick_filter_prune = 8n bytes."""
+    import torch
+    import modelcompression_b200 as mc
+    n = sum(p.numel() for p in model_dense.parameters() if p.dim() != 1)
+    out = {}
+    for name, fn, nbytes in (("weight_prune_70", lambda: mc.weight_prune(model_dense, 70.), 12 * n),
+                             ("quick_filter_prune_40", lambda: mc.quick_filter_prune(model_dense, 40.), 8 * n)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = statistics.median(ts)
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out[name] = {"ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peaks['hbm_gbs']}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=BATCH)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--dense', action='store_true', help='extra: also time the un-pruned dense network')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else max(args.warmup, 1)
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+
+    if args.impl == 'reference':
+        run_reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import modelcompression_b200 as mc
+    from modelcompression_b200.engine import compile_darknet
+
+    assert torch.cuda.is_available(), "bench.py (b200 arm) needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=device)
+    peaks = measured_peaks()
+    B = args.batch
+
+    model, masks, keep = build_pruned_model(device)
+    plan = compile_darknet(model)
+    flops_img = plan.flops_per_image
+
+    # inputs resident in HBM: 3 rotating batches (133 MB each at B=64 > 126 MB L2)
+    gen = torch.Generator(device=device).manual_seed(1 + rank)
+    xs = [torch.rand(B, 3, IMG, IMG, device=device, generator=gen) for _ in range(3)]
+
+    def step(i):
+        return model(xs[i % len(xs)])
+
+    with torch.no_grad():
+        for i in range(args.warmup):
+            step(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            y = step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+        elapsed_ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([elapsed_ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            elapsed_ms = float(t.item())
+        value = B * args.steps * world / (elapsed_ms * 1e-3)
+
+        # ---- per-kernel timing (CUDA events around every launch, same stream), K steps
+        conv_ms, conv_flops, other_ms = 0.0, 0.0, 0.0
+        per_layer = {}
+        ksteps = min(args.steps, 20)
+        for i in range(ksteps):
+            events = []
+            plan.run(xs[i % len(xs)], events=events)
+            torch.cuda.synchronize()
+            for op, a, b in events:
+                ms = a.elapsed_time(b)
+                if op['kind'] == 'conv':
+                    conv_ms += ms
+                    per_layer.setdefault(op['name'], []).append(ms)
+                else:
+                    other_ms += ms
+                    per_layer.setdefault(op['name'], []).append(ms)
+        conv_flops_step = 0.0
+        conv_launches = 0
+        for op in plan.ops:
+            if op['kind'] == 'conv':
+                conv_launches += 1
+                conv_flops_step += float(op['flops_per_image']) * B
+        conv_ms_per_launch = conv_ms / (ksteps * max(conv_launches, 1))
+        achieved_tflops = conv_flops_step * ksteps / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+
+        # ---- end to end through the public API with HOST buffers (H2D of the batch + D2H of the head every step),
+        #      double-buffered on a copy stream so the transfer of step i+1 overlaps the forward of step i
+        host_in = [torch.rand(B, 3, IMG, IMG).pin_memory() for _ in range(2)]
+        host_out = [torch.empty(B, y.shape[1], y.shape[2], y.shape[3]).pin_memory() for _ in range(2)]
+        dev_in = [torch.empty(B, 3, IMG, IMG, device=device) for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=device)
+        main_stream = torch.cuda.current_stream()
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+
+        def e2e_loop(nsteps):
+            with torch.cuda.stream(copy_stream):
+                dev_in[0].copy_(host_in[0], non_blocking=True)
+                ready[0].record(copy_stream)
+            for i in range(nsteps):
+                cur, nxt = i % 2, (i + 1) % 2
+                if i + 1 < nsteps:
+                    with torch.cuda.stream(copy_stream):
+                        if i >= 1:
+                            copy_stream.wait_event(consumed[nxt])
+                        dev_in[nxt].copy_(host_in[nxt], non_blocking=True)
+                        ready[nxt].record(copy_stream)
+                main_stream.wait_event(ready[cur])
+                out = model(dev_in[cur])
+                consumed[cur].record(main_stream)
+                host_out[cur].copy_(out, non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_loop(3)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e2e_loop(args.steps)
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e_value = B * args.steps * world / e2e_s
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "yolov2-voc-416 (seed-0 default init) 40% filter-pruned, filters physically removed, "
+                               "forward", "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
+                   "prune": "quick_filter_prune 40%% -> %d/%d filters kept" % (sum(int(k.numel()) for k in keep),
+                                                                            sum(m.shape[0] for m in masks)),
+                   "algorithmic_gflop_per_image": flops_img / 1e9,
+                   "l2": "inputs larger than L2: %d rotating %.0f MB batches" % (len(xs), B * 3 * IMG * IMG * 4 / 1e6)},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * IMG * IMG * 4,
+                "d2h_bytes_per_step": int(y.numel() * 4)},
+        "gpu_launches": plan.num_launches * args.steps,
+        "roofline": {"bound": "tensor", "kernel": "conv_gemm_tcgen05_kernel", "achieved": achieved_tflops,
+                     "peak": peaks['bf16_sustained'], "unit": "TFLOP/s",
+                     "frac": achieved_tflops / peaks['bf16_sustained'] if peaks['bf16_sustained'] else None,
+                     "traffic": None, "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peaks['source'],
+                     "avg_launch_ms": conv_ms_per_launch, "launches_per_step": conv_launches,
+                     "algorithmic_gflop_per_step": conv_flops_step / 1e9,
+                     "kernel_share_of_step": conv_ms / max(conv_ms + other_ms, 1e-9)},
+        "whole_net_tflops": flops_img * value / world / 1e12,
+    }
+    if rank == 0:
+        line["per_op_ms"] = {k: round(statistics.median(v), 4) for k, v in per_layer.items()}
+        if world == 1:
+            torch.manual_seed(0)
+            dense = mc.Darknet(mc.write_yolov2_voc_cfg()).to(device).eval()
+            line["mask"] = time_masks(dense, peaks)
+            if args.dense:
+                with torch.no_grad():
+                    for i in range(3):
+                        dense(xs[i % 3])
+                    torch.cuda.synchronize()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    for i in range(20):
+                        dense(xs[i % 3])
+                    b.record()
+                    torch.cuda.synchronize()
+                    ms = a.elapsed_time(b) / 20
+                line["dense"] = {"images_per_s": B / (ms * 1e-3), "tflops": 29.36e9 * B / (ms * 1e-3) / 1e12}
+            del dense
+            if not args.no_cpu_baseline:
+                state = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+                ips, sps = cpu_forward_sample(state, model.blocks, CPU_SAMPLE_BATCH, 6, 1)
+                line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": torch.get_num_threads(),
+                                        "kind": "port", "sample": "6 forwards of batch %d of the same pruned network "
+                                        "(oracle port of the reference PyTorch CPU path)" % CPU_SAMPLE_BATCH}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

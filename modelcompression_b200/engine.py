@@ -243,7 +243,8 @@ class CompiledDarknet(object):
             w_aug = torch.cat([w, w1[:, None]], dim=1)
         cidx = [(c if c >= 0 else (Corig if (c == -2 and in_has_const) else -1)) for c in in_colsrc]
         c_phys_in = len(cidx)
-        self.flops_per_image += 2 * H * W * n_keep * sum(1 for c in in_colsrc if c >= 0) * taps
+        op_flops = 2 * H * W * n_keep * sum(1 for c in in_colsrc if c >= 0) * taps  # algorithmic, unpadded
+        self.flops_per_image += op_flops
         o_list = [int(i) for i in keep.tolist()] + ([-1] if need_ones_out else [])
         sc = torch.cat([scale[keep], torch.zeros(1, device=dev)]) if need_ones_out else scale[keep]
         sh = torch.cat([shift[keep], torch.ones(1, device=dev)]) if need_ones_out else shift[keep]
@@ -262,7 +263,8 @@ class CompiledDarknet(object):
                 ld = _round_up(n_phys, 8)
                 bid = self._new_buf(Ho, Wo, ld)
                 self.ops.append(dict(kind='conv1', w=w1st.contiguous(), scale=scale_p, shift=shift_p, dst_buf=bid,
-                                     N=n_phys, H=H, W=W, ld=ld, pool=1, name='conv1+pool@%d' % ind))
+                                     N=n_phys, H=H, W=W, ld=ld, pool=1, name='conv1+pool@%d' % ind,
+                                     flops_per_image=op_flops))
                 return _TensorRef(bid, Ho, Wo, O, out_colsrc, const_out), 'pool'
             # generic: pack the image to PNHWC (C=3 -> pitch 8) and run the tensor-core kernel
             bid_in = self._new_buf(H, W, 8)
@@ -280,7 +282,7 @@ class CompiledDarknet(object):
                                                      wpack.data_ptr(), Npad, Kc, _lib.stream_ptr()),
                        "mc_pack_conv_weights")
         op = dict(kind='conv', src=src, wpack=wpack, scale=scale_p, shift=shift_p, N=n_phys, Npad=Npad, ksize=k,
-                  leaky=int(leaky), Cin=c_phys_in, name='conv@%d' % ind, H=H, W=W)
+                  leaky=int(leaky), Cin=c_phys_in, name='conv@%d' % ind, H=H, W=W, flops_per_image=op_flops)
         fused = None
         if is_head:
             bid = self._new_buf(H, W, 0, fp32_nchw_channels=n_phys)
@@ -346,7 +348,8 @@ class CompiledDarknet(object):
         self._alloc[key] = tensors
         return tensors
 
-    def run(self, x):
+    def run(self, x, events=None):
+        """events: optional list; when given, (op, start_event, end_event) is appended per op (bench/profiling)."""
         if x.dim() != 4:
             raise ValueError("expected [B,3,H,W] input")
         _lib.require_cuda(x, "Darknet.forward")
@@ -364,6 +367,9 @@ class CompiledDarknet(object):
             out = None
             for op in self.ops:
                 kind = op['kind']
+                if events is not None:
+                    ev0 = torch.cuda.Event(enable_timing=True)
+                    ev0.record()
                 if kind == 'conv1':
                     _lib.check(lib.mc_conv1_fwd(x.data_ptr(), op['w'].data_ptr(), op['scale'].data_ptr(),
                                                 op['shift'].data_ptr(), bufs[op['dst_buf']].data_ptr(), B, op['H'],
@@ -400,6 +406,10 @@ class CompiledDarknet(object):
                     _lib.check(lib.mc_conv_fwd(ctypes.byref(d), stream), op['name'])
                 else:
                     raise RuntimeError("unknown op " + kind)
+                if events is not None:
+                    ev1 = torch.cuda.Event(enable_timing=True)
+                    ev1.record()
+                    events.append((op, ev0, ev1))
             self._last_bufs = bufs
         return out
 
