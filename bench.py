@@ -350,7 +350,17 @@ def main():
                     b.record()
                     torch.cuda.synchronize()
                     ms = a.elapsed_time(b) / 20
-                line["dense"] = {"images_per_s": B / (ms * 1e-3), "tflops": 29.36e9 * B / (ms * 1e-3) / 1e12}
+                    dplan = compile_darknet(dense)
+                    dper = {}
+                    for i in range(5):
+                        evs = []
+                        dplan.run(xs[i % 3], events=evs)
+                        torch.cuda.synchronize()
+                        for op, e0_, e1_ in evs:
+                            dper.setdefault(op['name'], []).append(e0_.elapsed_time(e1_))
+                line["dense"] = {"images_per_s": B / (ms * 1e-3), "tflops": 29.36e9 * B / (ms * 1e-3) / 1e12,
+                                 "ms_per_step": ms,
+                                 "per_op_ms": {k: round(statistics.median(v), 4) for k, v in dper.items()}}
             del dense
             if not args.no_cpu_baseline:
                 state = {k: v.detach().cpu() for k, v in model.state_dict().items()}

@@ -150,10 +150,15 @@ typedef struct mc_conv_desc {
 
 int mc_conv_fwd(const mc_conv_desc* desc, void* stream);
 
-/* First layer: fp32 NCHW [B,3,H,W] image -> conv3x3(3->N) + scale/shift + leaky + 2x2 max-pool,
- * bf16 PNHWC [(B*(H/2+1)*(W/2+1)), ldc].  d_w: fp32 [N,3,3,3] (already masked).                        */
-int mc_conv1_fwd(const float* d_img, const float* d_w, const float* d_scale, const float* d_shift,
-                 void* d_out, int B, int H, int W, int N, int ldc, int pool, void* stream);
+/* Small-channel direct convolution on CUDA cores, for layers too thin for a 128xNx64 tensor-core tile: the 3-channel
+ * first layer (in_is_nchw_f32=1: d_in is the fp32 NCHW image [B,Cin,H,W]) and the first blocks of a filter-pruned
+ * network (d_in PNHWC bf16, pitch Cin_ld).  d_w: fp32 [N,Cin,k,k] (already masked / gathered).  Fused scale/shift,
+ * leaky and optional 2x2/2 max-pool; writes channels [0,N) of the interior rows of a PNHWC bf16 buffer at (H,W) or
+ * (H/2,W/2) — the destination's pad line/column must already be zero.  Limits: mc_conv_direct_supported().        */
+int mc_conv_direct_supported(int Cin, int N, int ksize);
+int mc_conv_direct_fwd(const void* d_in, int in_is_nchw_f32, const float* d_w, const float* d_scale,
+                       const float* d_shift, void* d_out, int B, int H, int W, int Cin, int Cin_ld, int N, int ldc,
+                       int ksize, int leaky, int pool, void* stream);
 
 /* fp32 [O,C,kh,kw] (optionally * mask, optionally gathered by h_oidx/h_cidx surviving-index lists)
  * -> bf16 [Npad, kh*kw*Kc] with column (tap*Kc + c).  d_oidx/d_cidx are device int32 arrays or NULL. */

@@ -54,8 +54,9 @@ _SIGNATURES = {
                                  c_void_p, c_void_p, c_void_p, c_void_p]),
     "mc_nms_batched": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "mc_conv_fwd": (c_int, [POINTER(mc_conv_desc), c_void_p]),
-    "mc_conv1_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                             c_int, c_void_p]),
+    "mc_conv_direct_supported": (c_int, [c_int, c_int, c_int]),
+    "mc_conv_direct_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                   c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mc_pack_conv_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int,
                                      c_void_p, c_int, c_int, c_void_p]),
     "mc_maxpool2x2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

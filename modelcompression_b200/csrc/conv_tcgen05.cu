@@ -35,7 +35,8 @@ struct ConvKParams {
   int kb_per_tap;  // Kc / 64
   int ksize;       // 1 or 3
   int Wp, Hp, W, H;  // Wp = W+1, Hp = H+1
-  int block_n, stages, tmem_cols;
+  int block_n, stages, tmem_cols, acc_stride;  // acc_stride: TMEM columns between the two accumulator stages
+  int m_tiles, n_tiles;
   uint32_t idesc;
   const float* scale;
   const float* shift;
@@ -45,33 +46,31 @@ struct ConvKParams {
 
 __device__ __forceinline__ float leaky01(float v) { return v > 0.f ? v : 0.1f * v; }
 
+// Persistent: grid = min(#tiles, #SMs); CTA c works on tiles c, c+grid, ...  The smem ring runs across tiles, and the
+// accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const ConvKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve-up: [stages x (A 16KB | B block_n*128)] | barriers | tmem ptr | scale/shift staging
+  // carve-up: [stages x (A 16KB | B block_n*128)] | barriers | tmem ptr
   const uint32_t b_tile_bytes = (uint32_t)p.block_n * 128u;
   const uint32_t stage_bytes = A_TILE_BYTES + b_tile_bytes;
   uint8_t* smem = smem_raw;
-  // dynamic smem base is only guaranteed 16B aligned by the ABI: align up to 1024 (host adds 1 KB of slack)
-  {
+  {  // dynamic smem base is only guaranteed 16B aligned: align up to 1024 (host adds 1 KB of slack)
     uint32_t a = ptx::smem_u32(smem);
-    uint32_t pad = (1024u - (a & 1023u)) & 1023u;
-    smem += pad;
+    smem += (1024u - (a & 1023u)) & 1023u;
   }
   uint8_t* tiles = smem;
   uint8_t* aux = tiles + (size_t)p.stages * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
-  uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float* s_scale = reinterpret_cast<float*>(aux + 256);
-  float* s_shift = s_scale + 256;
+  uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * p.block_n;
-  const int m0 = blockIdx.y * BLOCK_M;
+  const int total_tiles = p.m_tiles * p.n_tiles;
 
   if (warp_idx == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_a);
@@ -80,7 +79,10 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    ptx::mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);
+      ptx::mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
+    }
     ptx::fence_barrier_init();
   }
   if (warp_idx == 1) {
@@ -97,18 +99,22 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (lane == 0) {
       int s = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int tap = kb / p.kb_per_tap;
-        const int cb = kb - tap * p.kb_per_tap;
-        int row_off = 0;
-        if (p.ksize == 3) row_off = (tap / 3 - 1) * p.Wp + (tap % 3 - 1);
-        ptx::mbar_wait(&empty_bar[s], phase ^ 1u);
-        uint8_t* a_dst = tiles + (size_t)s * stage_bytes;
-        uint8_t* b_dst = a_dst + A_TILE_BYTES;
-        ptx::mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
-        ptx::tma_load_2d(a_dst, &tmap_a, &full_bar[s], cb * BLOCK_K, m0 + row_off);
-        ptx::tma_load_2d(b_dst, &tmap_b, &full_bar[s], kb * BLOCK_K, n0);
-        if (++s == p.stages) { s = 0; phase ^= 1u; }
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.n_tiles) * p.block_n;
+        const int m0 = (tile / p.n_tiles) * BLOCK_M;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          const int tap = kb / p.kb_per_tap;
+          const int cb = kb - tap * p.kb_per_tap;
+          int row_off = 0;
+          if (p.ksize == 3) row_off = (tap / 3 - 1) * p.Wp + (tap % 3 - 1);
+          ptx::mbar_wait(&empty_bar[s], phase ^ 1u);
+          uint8_t* a_dst = tiles + (size_t)s * stage_bytes;
+          uint8_t* b_dst = a_dst + A_TILE_BYTES;
+          ptx::mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+          ptx::tma_load_2d(a_dst, &tmap_a, &full_bar[s], cb * BLOCK_K, m0 + row_off);
+          ptx::tma_load_2d(b_dst, &tmap_b, &full_bar[s], kb * BLOCK_K, n0);
+          if (++s == p.stages) { s = 0; phase ^= 1u; }
+        }
       }
     }
   } else if (warp_idx == 1) {
@@ -116,104 +122,117 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (lane == 0) {
       int s = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        ptx::mbar_wait(&full_bar[s], phase);
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1u);  // epilogue has drained this accumulator stage
         ptx::tc_fence_after();
-        const uint32_t a_addr = ptx::smem_u32(tiles + (size_t)s * stage_bytes);
-        const uint64_t adesc = ptx::make_sw128_kmajor_desc(a_addr);
-        const uint64_t bdesc = ptx::make_sw128_kmajor_desc(a_addr + A_TILE_BYTES);
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(as * p.acc_stride);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[s], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(tiles + (size_t)s * stage_bytes);
+          const uint64_t adesc = ptx::make_sw128_kmajor_desc(a_addr);
+          const uint64_t bdesc = ptx::make_sw128_kmajor_desc(a_addr + A_TILE_BYTES);
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / 16; ++k) {
-          // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr>>4) field
-          ptx::umma_bf16_ss(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
-                            (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr>>4) field
+            ptx::umma_bf16_ss(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
+                              (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+          if (++s == p.stages) { s = 0; phase ^= 1u; }
         }
-        ptx::umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
-        if (++s == p.stages) { s = 0; phase ^= 1u; }
+        ptx::umma_commit(&tmem_full_bar[as]);  // accumulator complete
+        if (++as == 2) { as = 0; aphase ^= 1u; }
       }
-      ptx::umma_commit(tmem_full_bar);  // accumulator complete
     }
   } else {
     // ===================== epilogue: warps 2..5 =====================
-    const int et = threadIdx.x - 64;  // 0..127
-    for (int i = et; i < p.block_n; i += 128) {
-      const bool ok = (n0 + i) < p.Npad;
-      s_scale[i] = ok ? p.scale[n0 + i] : 0.f;
-      s_shift[i] = ok ? p.shift[n0 + i] : 0.f;
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-
     const int quarter = warp_idx & 3;  // TMEM lane quarter this warp may access
-    const int row = m0 + quarter * 32 + lane;
-    const int x = row % p.Wp;
-    const int t = row / p.Wp;
-    const int y = t % p.Hp;
-    const int b = t / p.Hp;
-    const bool in_buf = row < p.M_rows;
-    const bool interior = in_buf && (x < p.W) && (y < p.H);
-
-    ptx::mbar_wait(tmem_full_bar, 0);
-    ptx::tc_fence_after();
-    const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
-
     __nv_bfloat16* out_bf = reinterpret_cast<__nv_bfloat16*>(p.out);
     float* out_f = reinterpret_cast<float*>(p.out);
-    long long out_row_base = 0;
-    bool do_store = false;
-    if (p.epi_mode == MC_EPI_PNHWC) {
-      out_row_base = (long long)row * p.ldc + p.ch_off;
-      do_store = in_buf;  // pad rows are written as zeros to keep the layout invariant
-    } else if (p.epi_mode == MC_EPI_REORG2) {
-      const int Wo = p.W / 2 + 1, Ho = p.H / 2 + 1;
-      const long long orow = ((long long)b * Ho + (y >> 1)) * Wo + (x >> 1);
-      out_row_base = orow * p.ldc + p.ch_off + ((y & 1) * 2 + (x & 1)) * p.N;
-      do_store = interior;
-    } else {  // MC_EPI_NCHW_F32
-      out_row_base = ((long long)b * p.N * p.H + y) * p.W + x;  // + n*H*W
-      do_store = interior;
-    }
     const bool vec_ok = ((p.ldc | p.ch_off) & 7) == 0 && (p.epi_mode != MC_EPI_REORG2 || (p.N & 7) == 0);
-
-    for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-      uint32_t r[16];
-      ptx::tmem_ld_32x32b_x16(taddr_row + (uint32_t)c0, r);
-      ptx::tmem_ld_wait();
-      float v[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float a = __uint_as_float(r[j]) * s_scale[c0 + j] + s_shift[c0 + j];
-        if (p.leaky) a = leaky01(a);
-        v[j] = interior ? a : 0.f;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n0 = (tile % p.n_tiles) * p.block_n;
+      const int m0 = (tile / p.n_tiles) * BLOCK_M;
+      const int row = m0 + quarter * 32 + lane;
+      const int x = row % p.Wp;
+      const int t = row / p.Wp;
+      const int y = t % p.Hp;
+      const int b = t / p.Hp;
+      const bool in_buf = row < p.M_rows;
+      const bool interior = in_buf && (x < p.W) && (y < p.H);
+      long long out_row_base = 0;
+      bool do_store = false;
+      if (p.epi_mode == MC_EPI_PNHWC) {
+        out_row_base = (long long)row * p.ldc + p.ch_off;
+        do_store = in_buf;  // pad rows are written as zeros to keep the layout invariant
+      } else if (p.epi_mode == MC_EPI_REORG2) {
+        const int Wo = p.W / 2 + 1, Ho = p.H / 2 + 1;
+        const long long orow = ((long long)b * Ho + (y >> 1)) * Wo + (x >> 1);
+        out_row_base = orow * p.ldc + p.ch_off + ((y & 1) * 2 + (x & 1)) * p.N;
+        do_store = interior;
+      } else {  // MC_EPI_NCHW_F32
+        out_row_base = ((long long)b * p.N * p.H + y) * p.W + x;  // + n*H*W
+        do_store = interior;
       }
-      if (!do_store) continue;
-      const int nbase = n0 + c0;
-      if (p.epi_mode == MC_EPI_NCHW_F32) {
-        const long long hw = (long long)p.H * p.W;
+
+      ptx::mbar_wait(&tmem_full_bar[as], aphase);
+      ptx::tc_fence_after();
+      const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.acc_stride);
+
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        uint32_t r[16];
+        ptx::tmem_ld_32x32b_x16(taddr_row + (uint32_t)c0, r);
+        ptx::tmem_ld_wait();
+        if (!do_store) continue;
+        const int nbase = n0 + c0;
+        float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (nbase + j < p.N) out_f[out_row_base + (long long)(nbase + j) * hw] = v[j];
-      } else {
+        for (int j = 0; j < 16; ++j) {
+          const int n = nbase + j;
+          const float sc = (n < p.Npad) ? __ldg(p.scale + n) : 0.f;
+          const float sh = (n < p.Npad) ? __ldg(p.shift + n) : 0.f;
+          float a = __uint_as_float(r[j]) * sc + sh;
+          if (p.leaky) a = leaky01(a);
+          v[j] = interior ? a : 0.f;
+        }
+        if (p.epi_mode == MC_EPI_NCHW_F32) {
+          const long long hw = (long long)p.H * p.W;
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const int n = nbase + g * 8;
-          if (vec_ok && n + 8 <= p.N) {
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[g * 8 + 0], v[g * 8 + 1]);
-            __nv_bfloat162 h1 = __floats2bfloat162_rn(v[g * 8 + 2], v[g * 8 + 3]);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[g * 8 + 4], v[g * 8 + 5]);
-            __nv_bfloat162 h3 = __floats2bfloat162_rn(v[g * 8 + 6], v[g * 8 + 7]);
-            uint4 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&h0);
-            pk.y = *reinterpret_cast<uint32_t*>(&h1);
-            pk.z = *reinterpret_cast<uint32_t*>(&h2);
-            pk.w = *reinterpret_cast<uint32_t*>(&h3);
-            *reinterpret_cast<uint4*>(out_bf + out_row_base + n) = pk;
-          } else {
+          for (int j = 0; j < 16; ++j)
+            if (nbase + j < p.N) out_f[out_row_base + (long long)(nbase + j) * hw] = v[j];
+        } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (n + j < p.N) out_bf[out_row_base + n + j] = __float2bfloat16_rn(v[g * 8 + j]);
+          for (int g = 0; g < 2; ++g) {
+            const int n = nbase + g * 8;
+            if (vec_ok && n + 8 <= p.N) {
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[g * 8 + 0], v[g * 8 + 1]);
+              __nv_bfloat162 h1 = __floats2bfloat162_rn(v[g * 8 + 2], v[g * 8 + 3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[g * 8 + 4], v[g * 8 + 5]);
+              __nv_bfloat162 h3 = __floats2bfloat162_rn(v[g * 8 + 6], v[g * 8 + 7]);
+              uint4 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&h0);
+              pk.y = *reinterpret_cast<uint32_t*>(&h1);
+              pk.z = *reinterpret_cast<uint32_t*>(&h2);
+              pk.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(out_bf + out_row_base + n) = pk;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (n + j < p.N) out_bf[out_row_base + n + j] = __float2bfloat16_rn(v[g * 8 + j]);
+            }
           }
         }
       }
+      // this warp has finished reading the accumulator stage: hand it back to the MMA issuer
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+      if (++as == 2) { as = 0; aphase ^= 1u; }
     }
   }
 
@@ -345,11 +364,11 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   const int stage_bytes = A_TILE_BYTES + block_n * 128;
   int stages = d->stages;
   if (stages <= 0) {
-    stages = (200 * 1024) / stage_bytes;
+    stages = (208 * 1024) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
   }
   MC_CHECK_ARG(stages >= 1 && stages <= MAX_STAGES, "mc_conv_fwd: stages %d invalid", stages);
-  const size_t smem_bytes = (size_t)stages * stage_bytes + 256 + 2 * 256 * sizeof(float) + 1024;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + 256 + 1024;
   MC_CHECK_ARG(smem_bytes <= 227 * 1024, "mc_conv_fwd: smem %zu too large", smem_bytes);
 
   CUtensorMap tm_a, tm_b;
@@ -372,9 +391,12 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   p.Hp = d->H + 1;
   p.block_n = block_n;
   p.stages = stages;
+  p.acc_stride = ((block_n + 31) / 32) * 32;
   int tc = 32;
-  while (tc < block_n) tc <<= 1;
-  p.tmem_cols = tc;
+  while (tc < 2 * p.acc_stride) tc <<= 1;
+  p.tmem_cols = tc;  // two accumulator stages
+  p.m_tiles = m_tiles;
+  p.n_tiles = n_tiles;
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
   p.scale = d->d_scale;
   p.shift = d->d_shift;
@@ -389,7 +411,8 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
     MC_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  dim3 grid((unsigned)n_tiles, (unsigned)m_tiles, 1);
+  long long total_tiles = (long long)n_tiles * m_tiles;
+  int grid = (int)(total_tiles < mc_num_sms() ? total_tiles : mc_num_sms());
   conv_gemm_tcgen05_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tm_a, tm_b, p);
   MC_LAUNCH_CHECK("conv_gemm_tcgen05_kernel");
   return 0;

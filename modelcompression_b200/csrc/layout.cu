@@ -116,17 +116,27 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ w, const floa
   }
 }
 
-// ---- conv1: fp32 NCHW image, 3 input channels, 3x3, N<=32 filters, fused scale/shift + leaky + 2x2 pool ---------
-// One block = 16x16 conv outputs (8x8 pooled); thread t owns conv pixel (2*wy+dy, 2*wx+dx) with
-// window = t/4, (dy,dx) = t%4, so a pool window is 4 adjacent lanes and pooling is two shuffles.
-constexpr int C1_MAXN = 32;
+// ---- small-channel direct conv (CUDA cores) ------------------------------------------------------------------
+// For layers whose channel counts are too small to feed a 128 x N x 64 tensor-core tile (the 3-channel first layer,
+// and the first blocks of a filter-pruned network: e.g. 3->4, 4->1, 1->17 channels), the op is bound by reading
+// the input once, not by math.  One block = 16x16 output pixels; the (16+2)^2 x Cin input patch is staged in shared
+// memory as bf16 (the same rounding the tensor-core layers apply to activations); thread t owns pixel
+// (2*wy+dy, 2*wx+dx) with window = t/4, (dy,dx) = t%4, so a 2x2 pool window is 4 adjacent lanes (two shuffles).
+// FIRST: input is the fp32 NCHW image; else PNHWC bf16.  Output PNHWC bf16 (interior rows only: the destination's
+// pad line/column are zero-initialised once by the engine and never written).
+constexpr int SD_MAX_CIN = 32;
+constexpr int SD_MAX_WELEMS = 9 * 512;  // taps * Cin * NT floats of shared memory (18 KB)
+
+template <int NT, bool FIRST>
 __global__ void __launch_bounds__(256)
-conv1_direct_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ scale,
-                    const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, int B, int H, int W, int N,
-                    int ldc, int pool) {
-  __shared__ float s_in[3][18][19];
-  __shared__ float s_w[27][C1_MAXN];
-  __shared__ float s_sc[C1_MAXN], s_sh[C1_MAXN];
+conv_direct_kernel(const void* __restrict__ in_, const float* __restrict__ w, const float* __restrict__ scale,
+                   const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, int B, int H, int W, int Cin,
+                   int Cin_ld, int N, int ldc, int ksize, int leaky, int pool) {
+  __shared__ __nv_bfloat16 s_in[18 * 18 * SD_MAX_CIN];  // [r][s][c], c fastest
+  __shared__ __align__(16) float s_w[SD_MAX_WELEMS];     // [tap][c][n]
+  __shared__ float s_sc[NT], s_sh[NT];
+  const int taps = ksize * ksize;
+  const int halo = ksize / 2;
   const int tiles_x = (W + 15) / 16;
   const int tiles_y = (H + 15) / 16;
   const int tile = blockIdx.x;
@@ -134,22 +144,38 @@ conv1_direct_kernel(const float* __restrict__ img, const float* __restrict__ w, 
   const int ty = (tile / tiles_x) % tiles_y;
   const int tx = tile % tiles_x;
   const int y0 = ty * 16, x0 = tx * 16;
+  const int P = 16 + 2 * halo;
 
-  for (int i = threadIdx.x; i < 27 * C1_MAXN; i += 256) {
-    const int k = i / C1_MAXN, n = i % C1_MAXN;  // k = c*9 + r*3 + s  (weight layout [N,3,3,3])
-    s_w[k][n] = (n < N) ? w[n * 27 + k] : 0.f;
+  // weights: global [N][Cin][taps] fp32 -> shared [tap][c][n]
+  for (int i = threadIdx.x; i < taps * Cin * NT; i += 256) {
+    const int n = i % NT;
+    const int c = (i / NT) % Cin;
+    const int tp = i / (NT * Cin);
+    s_w[i] = (n < N) ? w[((long long)n * Cin + c) * taps + tp] : 0.f;
   }
-  if (threadIdx.x < C1_MAXN) {
+  if (threadIdx.x < NT) {
     s_sc[threadIdx.x] = threadIdx.x < N ? scale[threadIdx.x] : 0.f;
     s_sh[threadIdx.x] = threadIdx.x < N ? shift[threadIdx.x] : 0.f;
   }
-  for (int i = threadIdx.x; i < 3 * 18 * 18; i += 256) {
-    const int c = i / 324, r = (i / 18) % 18, s = i % 18;
-    const int yy = y0 + r - 1, xx = x0 + s - 1;
-    float v = 0.f;
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = img[(((long long)b * 3 + c) * H + yy) * W + xx];
-    // the tensor-core layers consume bf16 activations; round the image the same way for a uniform contract
-    s_in[c][r][s] = __bfloat162float(__float2bfloat16_rn(v));
+  if (FIRST) {
+    const float* img = reinterpret_cast<const float*>(in_);
+    for (int i = threadIdx.x; i < Cin * P * P; i += 256) {
+      const int c = i / (P * P), r = (i / P) % P, sx = i % P;
+      const int yy = y0 + r - halo, xx = x0 + sx - halo;
+      float v = 0.f;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = img[(((long long)b * Cin + c) * H + yy) * W + xx];
+      s_in[(r * P + sx) * Cin + c] = __float2bfloat16_rn(v);
+    }
+  } else {
+    const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(in_);
+    for (int i = threadIdx.x; i < P * P * Cin; i += 256) {
+      const int c = i % Cin, sx = (i / Cin) % P, r = i / (Cin * P);
+      const int yy = y0 + r - halo, xx = x0 + sx - halo;
+      __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+        v = x[(((long long)b * (H + 1) + yy) * (W + 1) + xx) * Cin_ld + c];
+      s_in[(r * P + sx) * Cin + c] = v;
+    }
   }
   __syncthreads();
 
@@ -157,58 +183,61 @@ conv1_direct_kernel(const float* __restrict__ img, const float* __restrict__ w, 
   const int win = t >> 2, sub = t & 3;
   const int ly = 2 * (win >> 3) + (sub >> 1);
   const int lx = 2 * (win & 7) + (sub & 1);
-  float acc[C1_MAXN];
+  float acc[NT];
 #pragma unroll
-  for (int n = 0; n < C1_MAXN; ++n) acc[n] = 0.f;
+  for (int n = 0; n < NT; ++n) acc[n] = 0.f;
+  for (int tp = 0; tp < taps; ++tp) {
+    const int r = tp / ksize, sx = tp - r * ksize;
+    const __nv_bfloat16* ip = &s_in[((ly + r) * P + (lx + sx)) * Cin];
+    const float* wp = &s_w[tp * Cin * NT];
+    for (int c = 0; c < Cin; ++c) {
+      const float a = __bfloat162float(ip[c]);
 #pragma unroll
-  for (int c = 0; c < 3; ++c)
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const float a = s_in[c][ly + r][lx + s];
-        const int k = c * 9 + r * 3 + s;
-#pragma unroll
-        for (int n = 0; n < C1_MAXN; ++n) acc[n] = fmaf(a, s_w[k][n], acc[n]);
-      }
+      for (int n = 0; n < NT; ++n) acc[n] = fmaf(a, wp[c * NT + n], acc[n]);
+    }
+  }
   const int gy = y0 + ly, gx = x0 + lx;
 #pragma unroll
-  for (int n = 0; n < C1_MAXN; ++n) {
-    float v = leaky01(acc[n] * s_sc[n] + s_sh[n]);
+  for (int n = 0; n < NT; ++n) {
+    float v = acc[n] * s_sc[n] + s_sh[n];
+    if (leaky) v = leaky01(v);
     if (pool) {
       v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
       v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
     }
     acc[n] = v;
   }
+  long long row;
+  bool store;
   if (pool) {
-    if (sub == 0 && gy < H && gx < W) {
-      const int Ho = H / 2, Wo = W / 2;
-      const long long row = ((long long)b * (Ho + 1) + (gy >> 1)) * (Wo + 1) + (gx >> 1);
-      for (int n = 0; n < N; ++n) out[row * ldc + n] = __float2bfloat16_rn(acc[n]);
-    }
+    const int Ho = H / 2, Wo = W / 2;
+    row = ((long long)b * (Ho + 1) + (gy >> 1)) * (Wo + 1) + (gx >> 1);
+    store = (sub == 0) && gy < H && gx < W;
   } else {
-    if (gy < H && gx < W) {
-      const long long row = ((long long)b * (H + 1) + gy) * (W + 1) + gx;
-      for (int n = 0; n < N; ++n) out[row * ldc + n] = __float2bfloat16_rn(acc[n]);
-    }
+    row = ((long long)b * (H + 1) + gy) * (W + 1) + gx;
+    store = gy < H && gx < W;
   }
-}
-
-// zero the pad column / pad line of a PNHWC buffer (channels [0, ld)).
-__global__ void zero_pads_kernel(__nv_bfloat16* __restrict__ out, int B, int H, int W, int ld8) {
-  const long long npad_rows = (long long)B * ((H + 1) + W);  // per image: pad column (H+1 rows) + pad line (W more)
-  const long long total = npad_rows * ld8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long pr = i / ld8;
-    const int g = (int)(i - pr * ld8);
-    const int b = (int)(pr / (H + 1 + W));
-    const int q = (int)(pr % (H + 1 + W));
-    int y, x;
-    if (q <= H) { y = q; x = W; } else { y = H; x = q - (H + 1); }
-    const long long row = ((long long)b * (H + 1) + y) * (W + 1) + x;
-    *reinterpret_cast<uint4*>(out + (row * ld8 + g) * 8) = make_uint4(0, 0, 0, 0);
+  if (store) {
+    __nv_bfloat16* dst = out + row * ldc;
+    if ((NT % 8) == 0 && (ldc % 8) == 0) {
+#pragma unroll
+      for (int g = 0; g < NT / 8; ++g) {
+        if (g * 8 + 8 <= N) {
+          __align__(16) __nv_bfloat16 v8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v8[j] = __float2bfloat16_rn(acc[g * 8 + j]);
+          *reinterpret_cast<uint4*>(dst + g * 8) = *reinterpret_cast<const uint4*>(v8);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (g * 8 + j < N) dst[g * 8 + j] = __float2bfloat16_rn(acc[g * 8 + j]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int n = 0; n < NT; ++n)
+        if (n < N) dst[n] = __float2bfloat16_rn(acc[n]);
+    }
   }
 }
 
@@ -274,24 +303,42 @@ extern "C" int mc_pack_conv_weights(const float* d_w, const float* d_mask, int O
   return 0;
 }
 
-extern "C" int mc_conv1_fwd(const float* d_img, const float* d_w, const float* d_scale, const float* d_shift,
-                            void* d_out, int B, int H, int W, int N, int ldc, int pool, void* stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  MC_CHECK_ARG(d_img && d_w && d_scale && d_shift && d_out, "mc_conv1_fwd: null pointer");
-  MC_CHECK_ARG(B > 0 && H > 0 && W > 0 && N > 0 && N <= C1_MAXN, "mc_conv1_fwd: N must be in 1..%d (got %d)", C1_MAXN, N);
-  MC_CHECK_ARG(ldc % 8 == 0 && ldc >= N, "mc_conv1_fwd: ldc must be a multiple of 8 >= N");
-  if (pool) MC_CHECK_ARG((H % 2) == 0 && (W % 2) == 0, "mc_conv1_fwd: pooling needs even H,W");
-  const int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
-  // pad line/column of the destination (and channels >= N) must be zero: clear the pads, the kernel
-  // writes channels [0,N) of interior rows; channels [N,ldc) are never read (TMA extent = Cin).
-  {
-    const long long total = (long long)B * ((Ho + 1) + Wo) * (ldc / 8);
-    zero_pads_kernel<<<grid_for(total, 256), 256, 0, stream>>>((__nv_bfloat16*)d_out, B, Ho, Wo, ldc / 8);
-    MC_LAUNCH_CHECK("zero_pads_kernel");
-  }
+template <bool FIRST>
+static int launch_direct(const void* d_in, const float* d_w, const float* d_scale, const float* d_shift, void* d_out,
+                         int B, int H, int W, int Cin, int Cin_ld, int N, int ldc, int ksize, int leaky, int pool,
+                         cudaStream_t stream) {
   const int tiles = B * ((H + 15) / 16) * ((W + 15) / 16);
-  conv1_direct_kernel<<<tiles, 256, 0, stream>>>(d_img, d_w, d_scale, d_shift, (__nv_bfloat16*)d_out, B, H, W, N, ldc,
-                                                 pool);
-  MC_LAUNCH_CHECK("conv1_direct_kernel");
+  __nv_bfloat16* out = (__nv_bfloat16*)d_out;
+#define MC_LAUNCH_DIRECT(NT_)                                                                                  \
+  conv_direct_kernel<NT_, FIRST><<<tiles, 256, 0, stream>>>(d_in, d_w, d_scale, d_shift, out, B, H, W, Cin, Cin_ld, N, \
+                                                           ldc, ksize, leaky, pool)
+  if (N <= 4) MC_LAUNCH_DIRECT(4);
+  else if (N <= 8) MC_LAUNCH_DIRECT(8);
+  else if (N <= 16) MC_LAUNCH_DIRECT(16);
+  else MC_LAUNCH_DIRECT(32);
+#undef MC_LAUNCH_DIRECT
+  MC_LAUNCH_CHECK("conv_direct_kernel");
   return 0;
+}
+
+static int direct_nt(int N) { return N <= 4 ? 4 : N <= 8 ? 8 : N <= 16 ? 16 : 32; }
+
+extern "C" int mc_conv_direct_supported(int Cin, int N, int ksize) {
+  if (!(ksize == 1 || ksize == 3) || Cin < 1 || N < 1 || Cin > SD_MAX_CIN || N > 32) return 0;
+  return (ksize * ksize * Cin * direct_nt(N) <= SD_MAX_WELEMS) ? 1 : 0;
+}
+
+extern "C" int mc_conv_direct_fwd(const void* d_in, int in_is_nchw_f32, const float* d_w, const float* d_scale,
+                                  const float* d_shift, void* d_out, int B, int H, int W, int Cin, int Cin_ld, int N,
+                                  int ldc, int ksize, int leaky, int pool, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MC_CHECK_ARG(d_in && d_w && d_scale && d_shift && d_out, "mc_conv_direct_fwd: null pointer");
+  MC_CHECK_ARG(B > 0 && H > 0 && W > 0, "mc_conv_direct_fwd: bad dims");
+  MC_CHECK_ARG(mc_conv_direct_supported(Cin, N, ksize), "mc_conv_direct_fwd: Cin=%d N=%d k=%d outside the direct path", Cin, N, ksize);
+  MC_CHECK_ARG(ldc >= N, "mc_conv_direct_fwd: ldc < N");
+  if (!in_is_nchw_f32) MC_CHECK_ARG(Cin_ld >= Cin, "mc_conv_direct_fwd: Cin_ld < Cin");
+  if (pool) MC_CHECK_ARG((H % 2) == 0 && (W % 2) == 0, "mc_conv_direct_fwd: pooling needs even H,W");
+  if (in_is_nchw_f32)
+    return launch_direct<true>(d_in, d_w, d_scale, d_shift, d_out, B, H, W, Cin, Cin_ld, N, ldc, ksize, leaky, pool, stream);
+  return launch_direct<false>(d_in, d_w, d_scale, d_shift, d_out, B, H, W, Cin, Cin_ld, N, ldc, ksize, leaky, pool, stream);
 }

@@ -63,13 +63,65 @@ __device__ float np_pairwise(const float* __restrict__ a, int n) {
   }
 }
 
-// Raw per-filter sums.  taps>1: one thread per (filter, tap) runs the sequential-in-c chain; the taps of a filter
-// sit in adjacent lanes and are combined in NumPy's (h then w) order through shared memory.  taps==1: one thread
-// per filter runs the pairwise recursion.
+// ---- exact lane-parallel version of NumPy's pairwise sum -----------------------------------------------------
+// The recursion splits [0,n) into leaves of <= 128 elements (in order); a leaf is summed with 8 strided accumulators
+// (or sequentially when shorter than 8).  Leaves are independent, so lane L of a warp sums leaf L (L+32, ...), and
+// lane 0 then combines the leaf sums by replaying the recursion.  Same operations, same order per value => bit-exact.
+template <bool SQUARE>
+__device__ __forceinline__ float np_leaf_sum(const float* __restrict__ a, int n) {  // n <= 128
+  return np_pairwise<SQUARE>(a, n);
+}
+
+// walk the recursion; call f(leaf_index, start, len) for every leaf, in order.  Returns the number of leaves.
+template <typename F>
+__device__ __forceinline__ int np_for_each_leaf(int n, F f) {
+  int stack_start[24], stack_len[24];
+  int sp = 0, leaf = 0;
+  stack_start[0] = 0;
+  stack_len[0] = n;
+  sp = 1;
+  while (sp > 0) {
+    --sp;
+    const int st = stack_start[sp], ln = stack_len[sp];
+    if (ln <= 128) {
+      f(leaf, st, ln);
+      ++leaf;
+    } else {
+      int n2 = ln / 2;
+      n2 -= n2 % 8;
+      // push right first so the left half is visited first (in-order)
+      stack_start[sp] = st + n2;
+      stack_len[sp] = ln - n2;
+      ++sp;
+      stack_start[sp] = st;
+      stack_len[sp] = n2;
+      ++sp;
+    }
+  }
+  return leaf;
+}
+
+// combine leaf sums in recursion order (replays the split; leaves are consumed in order)
+__device__ float np_combine_leaves(const float* __restrict__ leaf_sums, int n, int* next_leaf) {
+  if (n <= 128) return leaf_sums[(*next_leaf)++];
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  const float l = np_combine_leaves(leaf_sums, n2, next_leaf);
+  const float r = np_combine_leaves(leaf_sums, n - n2, next_leaf);
+  return __fadd_rn(l, r);
+}
+
+constexpr int MAX_LEAVES = 128;  // warp path handles C <= 4096 (leaves are >= 57 long once n > 128)
+
+// Raw per-filter sums.  taps>1: one thread per (filter, tap) runs the sequential-in-c chain (loads are issued 32 deep
+// so the chain is not exposed to memory latency); the taps of a filter sit in adjacent lanes and are combined in
+// NumPy's (h then w) order through shared memory.  taps==1: one WARP per filter runs the lane-parallel pairwise sum.
 constexpr int SS_THREADS = 288;  // multiple of 9 and of 32
+constexpr int SS_WARPS = SS_THREADS / 32;
 
 __global__ void __launch_bounds__(SS_THREADS) filter_sumsq_kernel(const LayerTable lt, float* __restrict__ values) {
   __shared__ float s_tap[SS_THREADS];
+  __shared__ float s_leaf[SS_WARPS][MAX_LEAVES];
   const int gt = blockIdx.x * SS_THREADS + threadIdx.x;  // global thread slot (blocks never straddle layers)
   int l = 0;
   while (l + 1 < lt.nlayers && gt >= lt.toff[l + 1]) ++l;
@@ -77,9 +129,22 @@ __global__ void __launch_bounds__(SS_THREADS) filter_sumsq_kernel(const LayerTab
   const int taps = lt.taps[l], C = lt.C[l], O = lt.O[l];
   const float* __restrict__ w = lt.w[l];
   if (taps == 1) {
-    if (local < O) {
-      const float s = np_pairwise<true>(w + (long long)local * C, C);
-      values[lt.voff[l] + local] = __fdiv_rn(s, (float)C);
+    const int o = local >> 5, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (o >= O) return;  // whole warp
+    const float* a = w + (long long)o * C;
+    float* ls = s_leaf[wib];
+    if (C <= 4096) {
+      np_for_each_leaf(C, [&](int leaf, int st, int ln) {
+        if ((leaf & 31) == lane) ls[leaf] = np_leaf_sum<true>(a + st, ln);
+      });
+      __syncwarp();
+      if (lane == 0) {
+        int next = 0;
+        const float s = np_combine_leaves(ls, C, &next);
+        values[lt.voff[l] + o] = __fdiv_rn(s, (float)C);
+      }
+    } else if (lane == 0) {
+      values[lt.voff[l] + o] = __fdiv_rn(np_pairwise<true>(a, C), (float)C);
     }
     return;
   }
@@ -92,12 +157,12 @@ __global__ void __launch_bounds__(SS_THREADS) filter_sumsq_kernel(const LayerTab
   if (o < O) {
     const float* p = w + (long long)o * C * taps + j;
     int c = 0;
-    for (; c + 8 <= C; c += 8) {
-      float x[8];
+    for (; c + 32 <= C; c += 32) {
+      float x[32];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) x[u] = p[(long long)(c + u) * taps];
+      for (int u = 0; u < 32; ++u) x[u] = p[(long long)(c + u) * taps];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) acc = __fadd_rn(acc, __fmul_rn(x[u], x[u]));
+      for (int u = 0; u < 32; ++u) acc = __fadd_rn(acc, __fmul_rn(x[u], x[u]));
     }
     for (; c < C; ++c) {
       const float x = p[(long long)c * taps];
@@ -121,20 +186,27 @@ __global__ void __launch_bounds__(SS_THREADS) filter_sumsq_kernel(const LayerTab
   }
 }
 
-// One block per layer: v /= sqrt(pairwise(v^2)); v /= max(v).
+// One block per layer: v /= sqrt(pairwise(v^2)); v /= max(v).  v is staged in shared memory so the serial pairwise
+// recursion of thread 0 runs at shared-memory latency.
+constexpr int NORM_SMEM = 8192;
 __global__ void __launch_bounds__(256) filter_norm_kernel(const LayerTable lt, float* __restrict__ values) {
+  __shared__ float s_v[NORM_SMEM];
   __shared__ float s_norm;
   __shared__ float s_red[256];
   const int l = blockIdx.x;
   const int O = lt.O[l];
   float* v = values + lt.voff[l];
-  if (threadIdx.x == 0) s_norm = __fsqrt_rn(np_pairwise<true>(v, O));
+  const bool staged = O <= NORM_SMEM;
+  if (staged)
+    for (int o = threadIdx.x; o < O; o += 256) s_v[o] = v[o];
+  __syncthreads();
+  if (threadIdx.x == 0) s_norm = __fsqrt_rn(np_pairwise<true>(staged ? s_v : v, O));
   __syncthreads();
   const float nrm = s_norm;
   float mx = -INFINITY;
   for (int o = threadIdx.x; o < O; o += 256) {
-    const float x = __fdiv_rn(v[o], nrm);
-    v[o] = x;
+    const float x = __fdiv_rn(staged ? s_v[o] : v[o], nrm);
+    if (staged) s_v[o] = x; else v[o] = x;
     mx = fmaxf(mx, x);
   }
   s_red[threadIdx.x] = mx;
@@ -144,43 +216,43 @@ __global__ void __launch_bounds__(256) filter_norm_kernel(const LayerTable lt, f
     __syncthreads();
   }
   mx = s_red[0];
-  for (int o = threadIdx.x; o < O; o += 256) v[o] = __fdiv_rn(v[o], mx);
+  for (int o = threadIdx.x; o < O; o += 256) v[o] = __fdiv_rn(staged ? s_v[o] : v[o], mx);
 }
 
-// Single-block radix select of two ranks over n non-negative floats, then NumPy's float64 _lerp.
-__device__ unsigned int block_select(const float* __restrict__ v, int n, unsigned int rank, unsigned int* s_hist,
-                                     unsigned int* s_pick) {
-  unsigned int prefix = 0, mask = 0;
-  for (int shift = 24; shift >= 0; shift -= 8) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const unsigned int key = __float_as_uint(v[i]);
-      if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned int cum = 0, b = 0;
-      for (; b < 255; ++b) {
-        if (cum + s_hist[b] > rank) break;
-        cum += s_hist[b];
-      }
-      s_pick[0] = b;
-      s_pick[1] = rank - cum;
-    }
-    __syncthreads();
-    prefix |= s_pick[0] << shift;
-    mask |= 255u << shift;
-    rank = s_pick[1];
-    __syncthreads();
+// Single-block radix select of TWO ranks at once over n non-negative floats (8 bits per pass, 4 passes), then NumPy's
+// float64 _lerp.  Each pass keeps one 256-bin histogram per rank (elements matching that rank's prefix); warp 0 / warp 1
+// locate the bins with shuffle prefix sums.
+__device__ __forceinline__ void warp_find_bin(const unsigned int* hist, unsigned int rank, unsigned int* out_bin,
+                                              unsigned int* out_rem) {
+  const int lane = threadIdx.x & 31;
+  unsigned int c[8], tot = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { c[j] = hist[lane * 8 + j]; tot += c[j]; }
+  unsigned int incl = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
   }
-  return prefix;
+  const unsigned int excl = incl - tot;
+  const bool mine = (rank >= excl) && (rank < incl);
+  const unsigned int who = __ballot_sync(0xffffffffu, mine);
+  const int src = who ? (__ffs(who) - 1) : 31;  // rank beyond the total: clamp (caller validates)
+  if (lane == src) {
+    unsigned int cum = excl, b = 0;
+    for (; b < 7; ++b) {
+      if (cum + c[b] > rank) break;
+      cum += c[b];
+    }
+    *out_bin = lane * 8 + b;
+    *out_rem = rank - cum;
+  }
 }
 
 __global__ void __launch_bounds__(1024) filter_threshold_kernel(const float* __restrict__ v, int n, long long k,
                                                                 double gamma, double* __restrict__ thr) {
-  __shared__ unsigned int s_hist[256];
-  __shared__ unsigned int s_pick[2];
+  __shared__ unsigned int s_hist[2][256];
+  __shared__ unsigned int s_bin[2], s_rem[2];
   __shared__ int s_nan;
   if (threadIdx.x == 0) s_nan = 0;
   __syncthreads();
@@ -191,12 +263,32 @@ __global__ void __launch_bounds__(1024) filter_threshold_kernel(const float* __r
     if (threadIdx.x == 0) *thr = __longlong_as_double(0x7ff8000000000000LL);
     return;
   }
-  const unsigned int ka = block_select(v, n, (unsigned int)k, s_hist, s_pick);
   const long long k1 = (k + 1 < n) ? k + 1 : (long long)n - 1;
-  const unsigned int kb = block_select(v, n, (unsigned int)k1, s_hist, s_pick);
+  unsigned int rank[2] = {(unsigned int)k, (unsigned int)k1};
+  unsigned int prefix[2] = {0, 0}, mask = 0;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned int key = __float_as_uint(v[i]);
+      const unsigned int d = (key >> shift) & 255u;
+      if ((key & mask) == prefix[0]) atomicAdd(&s_hist[0][d], 1u);
+      if ((key & mask) == prefix[1]) atomicAdd(&s_hist[1][d], 1u);
+    }
+    __syncthreads();
+    const int wid = threadIdx.x >> 5;
+    if (wid < 2) warp_find_bin(s_hist[wid], rank[wid], &s_bin[wid], &s_rem[wid]);
+    __syncthreads();
+    prefix[0] |= s_bin[0] << shift;
+    prefix[1] |= s_bin[1] << shift;
+    rank[0] = s_rem[0];
+    rank[1] = s_rem[1];
+    mask |= 255u << shift;
+    __syncthreads();
+  }
   if (threadIdx.x == 0) {
-    const double a = (double)__uint_as_float(ka);
-    const double b = (double)__uint_as_float(kb);
+    const double a = (double)__uint_as_float(prefix[0]);
+    const double b = (double)__uint_as_float(prefix[1]);
     const double diff = __dsub_rn(b, a);
     double r = __dadd_rn(a, __dmul_rn(diff, gamma));
     if (gamma >= 0.5) r = __dsub_rn(b, __dmul_rn(diff, __dsub_rn(1.0, gamma)));
@@ -211,31 +303,28 @@ __global__ void filter_keep_kernel(const float* __restrict__ v, int n, const dou
     keep[i] = ((double)v[i] < t) ? 0 : 1;
 }
 
+// one block per filter (grid-stride): constant fill of `per` floats, 128-bit stores on the aligned body
 __global__ void __launch_bounds__(256) filter_mask_fill_kernel(const LayerTable lt, const float* __restrict__ v,
                                                                const double* __restrict__ thr) {
   const double t = *thr;
-  const long long total4 = lt.woff[lt.nlayers];
-  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < total4;
-       i += (long long)gridDim.x * blockDim.x * 4) {
+  const int nfilters = lt.voff[lt.nlayers];
+  for (int f = blockIdx.x; f < nfilters; f += gridDim.x) {
     int l = 0;
-    while (l + 1 < lt.nlayers && i >= lt.woff[l + 1]) ++l;
-    const long long li = i - lt.woff[l];
-    const long long lsize = lt.woff[l + 1] - lt.woff[l];
+    while (l + 1 < lt.nlayers && f >= lt.voff[l + 1]) ++l;
+    const int o = f - lt.voff[l];
     const int per = lt.C[l] * lt.taps[l];
-    float* m = lt.mask[l];
-    float r[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const long long e = li + j;
-      r[j] = 0.f;
-      if (e < lsize) r[j] = ((double)v[lt.voff[l] + (int)(e / per)] < t) ? 0.f : 1.f;
-    }
-    if (li + 4 <= lsize && (reinterpret_cast<uintptr_t>(m) & 15) == 0) {
-      st_stream_f4(reinterpret_cast<float4*>(m + li), make_float4(r[0], r[1], r[2], r[3]));
-    } else {
-      for (int j = 0; j < 4; ++j)
-        if (li + j < lsize) m[li + j] = r[j];
-    }
+    const float val = ((double)v[f] < t) ? 0.f : 1.f;
+    float* m = lt.mask[l] + (long long)o * per;
+    // scalar head up to 16-byte alignment
+    int head = (int)(((16 - (reinterpret_cast<uintptr_t>(m) & 15)) & 15) >> 2);
+    if (head > per) head = per;
+    if ((int)threadIdx.x < head) m[threadIdx.x] = val;
+    const int body4 = (per - head) >> 2;
+    float4* m4 = reinterpret_cast<float4*>(m + head);
+    const float4 v4 = make_float4(val, val, val, val);
+    for (int i = threadIdx.x; i < body4; i += 256) st_stream_f4(m4 + i, v4);
+    const int tail0 = head + body4 * 4;
+    if ((int)threadIdx.x < per - tail0) m[tail0 + threadIdx.x] = val;
   }
 }
 
@@ -260,7 +349,7 @@ int build_layers(LayerTable* lt, const float* const* w, float* const* masks, con
     const long long thr = (taps[l] == 1) ? O[l] : (long long)O[l] * taps[l];
     // per-layer thread slots rounded up to whole blocks; for taps>1 a block must hold whole filters
     long long slots;
-    if (taps[l] == 1) slots = ((thr + SS_THREADS - 1) / SS_THREADS) * SS_THREADS;
+    if (taps[l] == 1) slots = ((thr * 32 + SS_THREADS - 1) / SS_THREADS) * SS_THREADS;  // one warp per filter
     else {
       const int fpb = SS_THREADS / taps[l];  // filters per block
       slots = (long long)((O[l] + fpb - 1) / fpb) * SS_THREADS;
@@ -341,11 +430,10 @@ extern "C" int mc_filter_masks(const float* d_values, const double* d_thr, const
   }
   if (h_mask_ptrs) {
     for (int l = 0; l < nlayers; ++l) MC_CHECK_ARG(h_mask_ptrs[l] != nullptr, "mc_filter_masks: null mask %d", l);
-    const long long total4 = lt.woff[nlayers] / 4;
-    long long blocks = (total4 + 255) / 256;
-    const long long cap = (long long)mc_num_sms() * 16;
+    int blocks = lt.voff[nlayers];
+    const int cap = mc_num_sms() * 16;
     if (blocks > cap) blocks = cap;
-    filter_mask_fill_kernel<<<(int)blocks, 256, 0, stream>>>(lt, d_values, d_thr);
+    filter_mask_fill_kernel<<<blocks, 256, 0, stream>>>(lt, d_values, d_thr);
     MC_LAUNCH_CHECK("filter_mask_fill_kernel");
   }
   return 0;

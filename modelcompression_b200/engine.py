@@ -164,7 +164,7 @@ class CompiledDarknet(object):
                     if st is None or len(st['parts']) != 2:
                         raise NotImplementedError("concat inputs must both be produced by convolutions (cfg block %d)" % bi)
                     p0, p1 = st['parts'][0], st['parts'][1]
-                    colsrc = list(p0.colsrc)
+                    colsrc = list(p0.colsrc) + [-1] * (p1.ch_off - p0.c_phys)  # alignment gap: zero, never written
                     have_ones = -2 in colsrc
                     for c in p1.colsrc:
                         if c >= 0:
@@ -254,19 +254,27 @@ class CompiledDarknet(object):
         scale_p[:n_phys] = sc
         shift_p[:n_phys] = sh
 
-        # ---- first layer: direct kernel on the fp32 image, pool fused
+        # ---- thin layers: direct CUDA-core kernel (first layer on the fp32 image; tiny shrunk layers), pool fused
+        plain_dst = (ind not in cat_of) and not (nxt_is_reorg and (ind + 1) in cat_of) and not is_head
+        nt = 4 if n_phys <= 4 else 8 if n_phys <= 8 else 16 if n_phys <= 16 else 32
+        direct_ok = plain_dst and self.lib.mc_conv_direct_supported(c_phys_in, n_phys, k) == 1 and \
+            (src is None or taps * c_phys_in * nt <= 1024)
+        if direct_ok:
+            rows = torch.tensor([o if o >= 0 else 0 for o in o_list], dtype=torch.long, device=dev)
+            cols = torch.tensor([c if c >= 0 else 0 for c in cidx], dtype=torch.long, device=dev)
+            wd = w_aug[rows][:, cols].reshape(n_phys, c_phys_in, taps).clone()
+            wd[torch.tensor([o < 0 for o in o_list], device=dev)] = 0
+            wd[:, torch.tensor([c < 0 for c in cidx], device=dev)] = 0
+            pool = 1 if nxt_is_pool else 0
+            Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+            ld = _round_up(n_phys, 8)
+            bid = self._new_buf(Ho, Wo, ld, zero_init=True)  # pad line/column stay zero: the kernel never writes them
+            self.ops.append(dict(kind='direct', src=src, w=wd.contiguous(), scale=scale_p, shift=shift_p, dst_buf=bid,
+                                 N=n_phys, Cin=c_phys_in, H=H, W=W, ld=ld, pool=pool, ksize=k, leaky=int(leaky),
+                                 name='direct%s@%d' % ('+pool' if pool else '', ind), flops_per_image=op_flops))
+            return _TensorRef(bid, Ho, Wo, O, out_colsrc, const_out), ('pool' if pool else None)
         if src is None:
-            if k == 3 and Corig == 3 and nxt_is_pool and n_phys <= 32:
-                w1st = torch.zeros(n_phys, 27, device=dev)
-                w1st[:n_keep] = w[keep].reshape(n_keep, 27)
-                Ho, Wo = H // 2, W // 2
-                ld = _round_up(n_phys, 8)
-                bid = self._new_buf(Ho, Wo, ld)
-                self.ops.append(dict(kind='conv1', w=w1st.contiguous(), scale=scale_p, shift=shift_p, dst_buf=bid,
-                                     N=n_phys, H=H, W=W, ld=ld, pool=1, name='conv1+pool@%d' % ind,
-                                     flops_per_image=op_flops))
-                return _TensorRef(bid, Ho, Wo, O, out_colsrc, const_out), 'pool'
-            # generic: pack the image to PNHWC (C=3 -> pitch 8) and run the tensor-core kernel
+            # generic first layer: pack the image to PNHWC (C=3 -> pitch 8) and run the tensor-core kernel
             bid_in = self._new_buf(H, W, 8)
             self.ops.append(dict(kind='pack_input', dst_buf=bid_in, C=in_ch, H=H, W=W, name='pack_input'))
             src = _TensorRef(bid_in, H, W, in_ch, list(range(in_ch)), torch.zeros(in_ch))
@@ -320,12 +328,13 @@ class CompiledDarknet(object):
                 p0, p1 = st['parts'][0], st['parts'][1]
                 if (p0.H, p0.W) != (p1.H, p1.W):
                     raise NotImplementedError("concat of different resolutions")
-                ld = _round_up(p0.c_phys + p1.c_phys, 8)
+                off1 = _round_up(p0.c_phys, 8)  # 16-byte aligned slice start -> vector stores in the epilogue
+                ld = _round_up(off1 + p1.c_phys, 8)
                 st['buf_id'] = self._new_buf(p0.H, p0.W, ld, zero_init=True)
                 for pop, slot in st['pending']:
-                    pop.update(dst_buf=st['buf_id'], ldc=ld, ch_off=0 if slot == 0 else p0.c_phys)
+                    pop.update(dst_buf=st['buf_id'], ldc=ld, ch_off=0 if slot == 0 else off1)
                 p0.buf_id = p1.buf_id = st['buf_id']
-                p1.ch_off = p0.c_phys
+                p1.ch_off = off1
         return out, fused
 
     # ------------------------------------------------------------------------------------------------ run
@@ -370,10 +379,16 @@ class CompiledDarknet(object):
                 if events is not None:
                     ev0 = torch.cuda.Event(enable_timing=True)
                     ev0.record()
-                if kind == 'conv1':
-                    _lib.check(lib.mc_conv1_fwd(x.data_ptr(), op['w'].data_ptr(), op['scale'].data_ptr(),
-                                                op['shift'].data_ptr(), bufs[op['dst_buf']].data_ptr(), B, op['H'],
-                                                op['W'], op['N'], op['ld'], op['pool'], stream), op['name'])
+                if kind == 'direct':
+                    s = op['src']
+                    if s is None:
+                        in_ptr, nchw, cin_ld = x.data_ptr(), 1, op['Cin']
+                    else:
+                        in_ptr, nchw, cin_ld = bufs[s.buf_id].data_ptr() + 2 * s.ch_off, 0, self.bufs[s.buf_id].ld
+                    _lib.check(lib.mc_conv_direct_fwd(in_ptr, nchw, op['w'].data_ptr(), op['scale'].data_ptr(),
+                                                      op['shift'].data_ptr(), bufs[op['dst_buf']].data_ptr(), B,
+                                                      op['H'], op['W'], op['Cin'], cin_ld, op['N'], op['ld'],
+                                                      op['ksize'], op['leaky'], op['pool'], stream), op['name'])
                 elif kind == 'pack_input':
                     _lib.check(lib.mc_pack_pnhwc(x.data_ptr(), bufs[op['dst_buf']].data_ptr(), B, op['H'], op['W'],
                                                  op['C'], 8, stream), op['name'])
@@ -415,8 +430,8 @@ class CompiledDarknet(object):
 
     @property
     def num_launches(self):
-        """kernel launches per forward (conv1 = 2: pad clear + conv)."""
-        return sum(2 if op['kind'] == 'conv1' else 1 for op in self.ops)
+        """kernel launches per forward."""
+        return len(self.ops)
 
     def block_activation(self, ind):
         """fp32 NCHW view (in the ORIGINAL channel space) of the output of models[ind] from the last run — for the

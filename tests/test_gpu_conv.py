@@ -144,7 +144,7 @@ def test_filter_pruned_network_physically_shrunk(cfg_path):
     model.b200_shrink = True
     y_s, y_ref = _check_blocks(model, x1, 'f40-shrunk')
     plan = compile_darknet(model)
-    convs = [op for op in plan.ops if op['kind'] in ('conv', 'conv1')]
+    convs = [op for op in plan.ops if op['kind'] in ('conv', 'direct')]
     kept = [int(k.numel()) for k in keep]
     # every non-head layer lost filters physically (+1 for the ones channel where constants are non-zero)
     assert all(op['N'] <= n + 1 for op, n in zip(convs[:-1], kept[:-1]))
