@@ -160,6 +160,19 @@ int mc_conv_direct_fwd(const void* d_in, int in_is_nchw_f32, const float* d_w, c
                        const float* d_shift, void* d_out, int B, int H, int W, int Cin, int Cin_ld, int N, int ldc,
                        int ksize, int leaky, int pool, void* stream);
 
+/* Thin 3x3 layers on the tensor cores with the im2col tile built in shared memory (csrc/conv_im2col_tc.cu): the
+ * 3-channel first layer (in_is_nchw_f32=1, Cin<=4) or a PNHWC bf16 input with pitch == CL (8 for Cin<=8, 16 for
+ * Cin<=16).  pool=1 fuses the 2x2/2 max-pool ("pool-window GEMM").  d_wexp is the expanded bf16 weight matrix
+ * [nb_pad, kpad] described by mc_conv_im2col_geometry():
+ *   pool=0: row n,            column (r*3+s)*CL + c         = w[n,c,r,s]
+ *   pool=1: row pos*npos + n, column (py*4+px)*CL + c       = w[n,c,py-dy,px-dx]  (pos = dy*2+dx; 0 outside the 3x3)
+ * Writes channels [0,N) of the interior rows of a PNHWC bf16 buffer whose pad line/column are already zero.       */
+int mc_conv_im2col_supported(int Cin, int in_is_nchw_f32, int N, int pool);
+int mc_conv_im2col_geometry(int Cin, int in_is_nchw_f32, int N, int pool, int* cl, int* npos, int* nb, int* kpad);
+int mc_conv_im2col_fwd(const void* d_in, int in_is_nchw_f32, const void* d_wexp, const float* d_scale,
+                       const float* d_shift, void* d_out, int B, int H, int W, int Cin, int Cin_ld, int N, int ldc,
+                       int leaky, int pool, void* stream);
+
 /* fp32 [O,C,kh,kw] (optionally * mask, optionally gathered by h_oidx/h_cidx surviving-index lists)
  * -> bf16 [Npad, kh*kw*Kc] with column (tap*Kc + c).  d_oidx/d_cidx are device int32 arrays or NULL. */
 int mc_pack_conv_weights(const float* d_w, const float* d_mask, int O, int C, int ksize,

@@ -336,6 +336,12 @@ int pick_block_n(int Npad, int m_tiles, int num_kb, int num_sms) {
 
 }  // namespace
 
+// shared with conv_im2col_tc.cu
+int mc_make_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                         uint32_t box_rows) {
+  return cached_tmap(tm, base, rows, cols, ld, box_rows);
+}
+
 extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MC_CHECK_ARG(d != nullptr, "mc_conv_fwd: null descriptor");

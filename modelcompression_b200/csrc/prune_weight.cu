@@ -126,32 +126,75 @@ __device__ void block_find_bin(const unsigned int* __restrict__ hist, unsigned l
   __syncthreads();
 }
 
+// Compaction of the selected bin: one global atomic per block-iteration (block-wide exclusive scan of the per-thread
+// hit counts), not one per warp — a single counter address serialises in L2 otherwise.
 __global__ void __launch_bounds__(THREADS) compact_kernel(const SegTable st, const Chunks ch, SelState* state,
                                                           unsigned int* __restrict__ cand,
                                                           unsigned long long cand_cap) {
   __shared__ unsigned int s_bin;
   __shared__ unsigned long long s_rem;
+  __shared__ unsigned int s_wsum[THREADS / 32];
+  __shared__ unsigned int s_base;
   block_find_bin<BINS0>(state->hist0, state->k, &s_bin, &s_rem);
   const unsigned int bin = s_bin;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     state->bin0 = bin;
     state->rem1 = s_rem;
   }
-  for_each_element(st, ch, [&](float v, int, long long) {
-    const unsigned int key = absbits(v);
-    const bool hit = (key >> 19) == bin;
-    // warp-aggregated append
-    const unsigned int m = __ballot_sync(__activemask(), hit);
-    if (hit) {
-      const int lane = threadIdx.x & 31;
-      const int leader = __ffs(m) - 1;
-      unsigned int basepos = 0;
-      if (lane == leader) basepos = atomicAdd(&state->cand_count, (unsigned int)__popc(m));
-      basepos = __shfl_sync(m, basepos, leader);
-      const unsigned int pos = basepos + __popc(m & ((1u << lane) - 1));
-      if (pos < cand_cap) cand[pos] = key;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long nchunks = ch.cstart[st.nseg];
+  for (long long cid = blockIdx.x; cid < nchunks; cid += gridDim.x) {
+    const int s = find_seg(ch, st.nseg, cid);
+    const long long size = st.start[s + 1] - st.start[s];
+    const long long base = (cid - ch.cstart[s]) * CHUNK;
+    const float* p = st.ptr[s];
+    const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+    unsigned int keys[8];
+    unsigned int hits = 0;  // bit j set: keys[j] belongs to the bin
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const long long i = base + ((long long)it * THREADS + threadIdx.x) * 4;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      int nvalid = 0;
+      if (aligned && i + 4 <= size) {
+        const float4 q = ld_stream_f4(reinterpret_cast<const float4*>(p + i));
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        nvalid = 4;
+      } else {
+        for (int j = 0; j < 4; ++j)
+          if (i + j < size) { v[j] = p[i + j]; nvalid = j + 1; }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const unsigned int key = absbits(v[j]);
+        keys[it * 4 + j] = key;
+        if (j < nvalid && (key >> 19) == bin) hits |= 1u << (it * 4 + j);
+      }
     }
-  });
+    const unsigned int cnt = __popc(hits);
+    unsigned int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_wsum[wid] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int tot = 0;
+      for (int w = 0; w < THREADS / 32; ++w) { const unsigned int c = s_wsum[w]; s_wsum[w] = tot; tot += c; }
+      s_base = tot ? atomicAdd(&state->cand_count, tot) : 0u;
+    }
+    __syncthreads();
+    unsigned int pos = s_base + s_wsum[wid] + (incl - cnt);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (hits & (1u << j)) {
+        if (pos < cand_cap) cand[pos] = keys[j];
+        ++pos;
+      }
+    __syncthreads();  // s_wsum / s_base are reused by the next iteration
+  }
 }
 
 __global__ void __launch_bounds__(THREADS) hist1_kernel(SelState* state, const unsigned int* __restrict__ cand) {
@@ -433,7 +476,7 @@ extern "C" int mc_kth_abs_select(const float* const* h_seg_ptrs, const int64_t* 
   MC_LAUNCH_CHECK("hist0_kernel");
   compact_kernel<<<grid, THREADS, 0, stream>>>(st, ch, state, cand, (unsigned long long)n);
   MC_LAUNCH_CHECK("compact_kernel");
-  const int cgrid = mc_num_sms() * 2;
+  const int cgrid = mc_num_sms();
   hist1_kernel<<<cgrid, THREADS, 0, stream>>>(state, cand);
   MC_LAUNCH_CHECK("hist1_kernel");
   hist2_kernel<<<cgrid, THREADS, 0, stream>>>(state, cand);

@@ -254,21 +254,60 @@ class CompiledDarknet(object):
         scale_p[:n_phys] = sc
         shift_p[:n_phys] = sh
 
-        # ---- thin layers: direct CUDA-core kernel (first layer on the fp32 image; tiny shrunk layers), pool fused
+        # ---- thin layers.  3x3 with <= 16 input channels (or the fp32 image): tensor cores with the im2col tile built
+        #      in shared memory, pool fused (csrc/conv_im2col_tc.cu).  Other first layers: direct CUDA-core kernel.
         plain_dst = (ind not in cat_of) and not (nxt_is_reorg and (ind + 1) in cat_of) and not is_head
-        nt = 4 if n_phys <= 4 else 8 if n_phys <= 8 else 16 if n_phys <= 16 else 32
-        direct_ok = plain_dst and self.lib.mc_conv_direct_supported(c_phys_in, n_phys, k) == 1 and \
-            (src is None or taps * c_phys_in * nt <= 1024)
-        if direct_ok:
+        first = src is None
+        pool = 1 if nxt_is_pool else 0
+
+        def gathered_fp32():
             rows = torch.tensor([o if o >= 0 else 0 for o in o_list], dtype=torch.long, device=dev)
             cols = torch.tensor([c if c >= 0 else 0 for c in cidx], dtype=torch.long, device=dev)
-            wd = w_aug[rows][:, cols].reshape(n_phys, c_phys_in, taps).clone()
+            wd = w_aug[rows][:, cols].clone()  # [n_phys, c_phys_in, k, k]
             wd[torch.tensor([o < 0 for o in o_list], device=dev)] = 0
             wd[:, torch.tensor([c < 0 for c in cidx], device=dev)] = 0
-            pool = 1 if nxt_is_pool else 0
+            return wd
+
+        src_ok = first or (src.ch_off == 0 and self.bufs[src.buf_id].ld == (8 if c_phys_in <= 8 else 16))
+        if plain_dst and k == 3 and src_ok and (H % 2 == 0 and W % 2 == 0 or not pool) and \
+                self.lib.mc_conv_im2col_supported(c_phys_in, 1 if first else 0, n_phys, pool) == 1:
+            cl, npos, nb, kpad = (ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int())
+            _lib.check(self.lib.mc_conv_im2col_geometry(c_phys_in, 1 if first else 0, n_phys, pool, ctypes.byref(cl),
+                                                        ctypes.byref(npos), ctypes.byref(nb), ctypes.byref(kpad)),
+                       "mc_conv_im2col_geometry")
+            cl, npos, nb, kpad = cl.value, npos.value, nb.value, kpad.value
+            wd = gathered_fp32().permute(0, 2, 3, 1)  # [n, r, s, c]
+            nb_pad = _round_up(nb, 16)
+            if pool:
+                wexp = torch.zeros(nb_pad, 4, 4, cl, device=dev)
+                for dy in range(2):
+                    for dx in range(2):
+                        r0 = (dy * 2 + dx) * npos
+                        wexp[r0:r0 + n_phys, dy:dy + 3, dx:dx + 3, :c_phys_in] = wd
+                wexp = wexp.reshape(nb_pad, 16 * cl)
+            else:
+                wexp = torch.zeros(nb_pad, 3, 3, cl, device=dev)
+                wexp[:n_phys, :, :, :c_phys_in] = wd
+                wexp = wexp.reshape(nb_pad, 9 * cl)
+            wfull = torch.zeros(nb_pad, kpad, device=dev)
+            wfull[:, :wexp.shape[1]] = wexp
             Ho, Wo = (H // 2, W // 2) if pool else (H, W)
             ld = _round_up(n_phys, 8)
             bid = self._new_buf(Ho, Wo, ld, zero_init=True)  # pad line/column stay zero: the kernel never writes them
+            n_sc = max(_round_up(npos, 16), 16)
+            sc2 = torch.zeros(n_sc, device=dev)
+            sh2 = torch.zeros(n_sc, device=dev)
+            sc2[:n_phys] = sc
+            sh2[:n_phys] = sh
+            self.ops.append(dict(kind='im2col', src=src, w=wfull.to(torch.bfloat16).contiguous(), scale=sc2, shift=sh2,
+                                 dst_buf=bid, N=n_phys, Cin=c_phys_in, H=H, W=W, ld=ld, pool=pool, leaky=int(leaky),
+                                 name='im2col%s@%d' % ('+pool' if pool else '', ind), flops_per_image=op_flops))
+            return _TensorRef(bid, Ho, Wo, O, out_colsrc, const_out), ('pool' if pool else None)
+        if first and plain_dst and self.lib.mc_conv_direct_supported(c_phys_in, n_phys, k) == 1:
+            wd = gathered_fp32().reshape(n_phys, c_phys_in, taps)
+            Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+            ld = _round_up(n_phys, 8)
+            bid = self._new_buf(Ho, Wo, ld, zero_init=True)
             self.ops.append(dict(kind='direct', src=src, w=wd.contiguous(), scale=scale_p, shift=shift_p, dst_buf=bid,
                                  N=n_phys, Cin=c_phys_in, H=H, W=W, ld=ld, pool=pool, ksize=k, leaky=int(leaky),
                                  name='direct%s@%d' % ('+pool' if pool else '', ind), flops_per_image=op_flops))
@@ -379,7 +418,17 @@ class CompiledDarknet(object):
                 if events is not None:
                     ev0 = torch.cuda.Event(enable_timing=True)
                     ev0.record()
-                if kind == 'direct':
+                if kind == 'im2col':
+                    s = op['src']
+                    if s is None:
+                        in_ptr, nchw, cin_ld = x.data_ptr(), 1, op['Cin']
+                    else:
+                        in_ptr, nchw, cin_ld = bufs[s.buf_id].data_ptr(), 0, self.bufs[s.buf_id].ld
+                    _lib.check(lib.mc_conv_im2col_fwd(in_ptr, nchw, op['w'].data_ptr(), op['scale'].data_ptr(),
+                                                      op['shift'].data_ptr(), bufs[op['dst_buf']].data_ptr(), B,
+                                                      op['H'], op['W'], op['Cin'], cin_ld, op['N'], op['ld'],
+                                                      op['leaky'], op['pool'], stream), op['name'])
+                elif kind == 'direct':
                     s = op['src']
                     if s is None:
                         in_ptr, nchw, cin_ld = x.data_ptr(), 1, op['Cin']

@@ -74,11 +74,16 @@ def _check_blocks(model, x, tag, tol_block=3e-2, tol_head_l2=2e-2):
     plan = compile_darknet(model)
     report = []
     for ind in sorted(plan.block_out):
-        if ind not in outs or ind == 0 or ind == 26:  # 0 and 26 are fused with the following pool / reorg block
+        if ind not in outs:
             continue
         got = plan.block_activation(ind)
         want = outs[ind]
-        assert got.shape == want.shape, (tag, ind, got.shape, want.shape)
+        if got.shape != want.shape:
+            # a conv fused with the following maxpool / reorg block only materialises the fused result, which is
+            # checked under the following block's index
+            assert model.blocks[ind + 2]['type'] in ('maxpool', 'reorg'), (tag, ind, got.shape, want.shape)
+            assert plan.block_out[ind + 1] is plan.block_out[ind]
+            continue
         report.append((ind, _rel(got, want), _rel_l2(got, want)))
     worst = max(report, key=lambda r: r[1])
     print("[%s] worst block %d: max-rel %.3g, l2-rel %.3g; head max-rel %.3g l2-rel %.3g" %
@@ -144,7 +149,7 @@ def test_filter_pruned_network_physically_shrunk(cfg_path):
     model.b200_shrink = True
     y_s, y_ref = _check_blocks(model, x1, 'f40-shrunk')
     plan = compile_darknet(model)
-    convs = [op for op in plan.ops if op['kind'] in ('conv', 'direct')]
+    convs = [op for op in plan.ops if op['kind'] in ('conv', 'direct', 'im2col')]
     kept = [int(k.numel()) for k in keep]
     # every non-head layer lost filters physically (+1 for the ones channel where constants are non-zero)
     assert all(op['N'] <= n + 1 for op, n in zip(convs[:-1], kept[:-1]))
