@@ -65,7 +65,7 @@ __device__ __forceinline__ void store_group(__nv_bfloat16* dst, int n0, const fl
 }
 
 template <int CL, bool POOL, bool FIRST>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const Im2colParams p) {
   constexpr int PR = POOL ? 2 * TY + 2 : TY + 2;   // patch rows / cols (conv pixels incl. halo)
   constexpr int PC = POOL ? 2 * TX + 2 : TX + 2;
@@ -113,48 +113,70 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const Im2colPa
   uint32_t mma_phase = 0;
   bool b_ready = false;
 
+  // Patch staging goes through registers so that the global loads of tile i+1 are in flight while tile i is built,
+  // multiplied and stored (one DRAM round trip per tile would otherwise sit on the critical path).
+  constexpr int PV = FIRST ? 1 : CL / 8;                       // 16-byte vectors per patch pixel (FIRST: one pixel)
+  constexpr int NLOAD = (PR * PC * PV + 127) / 128;
+  float pf[FIRST ? NLOAD * 4 : 1];
+  uint4 pq[FIRST ? 1 : NLOAD];
+  auto load_patch = [&](int tile) {
+    const int tx = tile % p.tiles_x;
+    const int ty = (tile / p.tiles_x) % p.tiles_y;
+    const int b = tile / (p.tiles_x * p.tiles_y);
+    const int iy0 = (POOL ? 2 * ty * TY : ty * TY) - 1, ix0 = (POOL ? 2 * tx * TX : tx * TX) - 1;
+#pragma unroll
+    for (int u = 0; u < NLOAD; ++u) {
+      const int i = t + u * 128;
+      const int pix = i / PV, v = i - pix * PV;
+      const int r = pix / PC, sx = pix - r * PC;
+      const int yy = iy0 + r, xx = ix0 + sx;
+      const bool ok = (i < PR * PC * PV) && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+      if constexpr (FIRST) {
+        const float* img = reinterpret_cast<const float*>(p.in);
+        const long long o = ((long long)b * p.Cin * p.H + yy) * p.W + xx;
+        const long long plane = (long long)p.H * p.W;
+        pf[u * 4 + 0] = ok ? img[o] : 0.f;
+        pf[u * 4 + 1] = (ok && p.Cin > 1) ? img[o + plane] : 0.f;
+        pf[u * 4 + 2] = (ok && p.Cin > 2) ? img[o + 2 * plane] : 0.f;
+        pf[u * 4 + 3] = (ok && p.Cin > 3) ? img[o + 3 * plane] : 0.f;
+      } else {
+        const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.in);
+        pq[u] = ok ? *reinterpret_cast<const uint4*>(
+                         x + (((long long)b * (p.H + 1) + yy) * (p.W + 1) + xx) * p.Cin_ld + v * 8)
+                   : make_uint4(0, 0, 0, 0);
+      }
+    }
+  };
+  auto store_patch = [&]() {
+#pragma unroll
+    for (int u = 0; u < NLOAD; ++u) {
+      const int i = t + u * 128;
+      if (i < PR * PC * PV) {
+        if constexpr (FIRST) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(pf[u * 4 + 0], pf[u * 4 + 1]);
+          __nv_bfloat162 hi = __floats2bfloat162_rn(pf[u * 4 + 2], pf[u * 4 + 3]);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(patch + (size_t)i * CL) = pk;  // CL == 4 for FIRST
+        } else {
+          *reinterpret_cast<uint4*>(patch + (size_t)i * 8) = pq[u];  // pixel-major, PV vectors per pixel
+        }
+      }
+    }
+  };
+
+  if ((int)blockIdx.x < p.total_tiles) load_patch(blockIdx.x);
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
     const int tx = tile % p.tiles_x;
     const int ty = (tile / p.tiles_x) % p.tiles_y;
     const int b = tile / (p.tiles_x * p.tiles_y);
-    const int oy0 = ty * TY, ox0 = tx * TX;                       // first output row/col of the tile
-    const int iy0 = (POOL ? 2 * oy0 : oy0) - 1, ix0 = (POOL ? 2 * ox0 : ox0) - 1;  // patch origin (conv coords)
+    const int oy0 = ty * TY, ox0 = tx * TX;  // first output row/col of the tile
 
-    // ---- 1. stage the input patch as bf16 [PR][PC][CL]
-    if constexpr (FIRST) {
-      const float* img = reinterpret_cast<const float*>(p.in);
-      for (int i = t; i < PR * PC; i += 128) {
-        const int r = i / PC, s = i - r * PC;
-        const int yy = iy0 + r, xx = ix0 + s;
-        float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
-        if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
-          const long long o = ((long long)b * p.Cin * p.H + yy) * p.W + xx;
-          const long long plane = (long long)p.H * p.W;
-          c0 = img[o];
-          if (p.Cin > 1) c1 = img[o + plane];
-          if (p.Cin > 2) c2 = img[o + 2 * plane];
-          if (p.Cin > 3) c3 = img[o + 3 * plane];
-        }
-        __nv_bfloat162 lo = __floats2bfloat162_rn(c0, c1), hi = __floats2bfloat162_rn(c2, c3);
-        uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&lo);
-        pk.y = *reinterpret_cast<uint32_t*>(&hi);
-        *reinterpret_cast<uint2*>(patch + (size_t)i * CL) = pk;  // CL == 4 for FIRST
-      }
-    } else {
-      const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.in);
-      constexpr int V = CL / 8;  // 16-byte vectors per pixel
-      for (int i = t; i < PR * PC * V; i += 128) {
-        const int pix = i / V, v = i - pix * V;
-        const int r = pix / PC, s = pix - r * PC;
-        const int yy = iy0 + r, xx = ix0 + s;
-        uint4 q = make_uint4(0, 0, 0, 0);
-        if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
-          q = *reinterpret_cast<const uint4*>(x + (((long long)b * (p.H + 1) + yy) * (p.W + 1) + xx) * p.Cin_ld + v * 8);
-        *reinterpret_cast<uint4*>(patch + (size_t)pix * CL + v * 8) = q;
-      }
-    }
+    // ---- 1. patch registers -> shared memory (bf16 [PR][PC][CL]); then prefetch the next tile's patch
+    store_patch();
     __syncthreads();
+    if (tile + (int)gridDim.x < p.total_tiles) load_patch(tile + gridDim.x);
 
     // ---- 2. build GEMM row t: NPIX patch pixels x CL channels, pixel-major, zero padded to NKB*64 elements
     {
@@ -295,7 +317,11 @@ int launch_im2col(const CUtensorMap& tm_b, const Im2colParams& p, cudaStream_t s
   const size_t smem = (size_t)NKB * 128 * 128 + (size_t)NKB * nb_pad * 128 + ((PR * PC * CL * 2 + 15) & ~15) + 64 + 1024;
   if (smem > 227 * 1024) return mc_set_error(MC_ERR_SHAPE, "mc_conv_im2col_fwd: %zu B of shared memory", smem);
   auto kern = conv_im2col_tc_kernel<CL, POOL, FIRST>;
-  MC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static size_t attr_smem = 0;  // per template instantiation
+  if (smem > attr_smem) {
+    MC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
   int per_sm = (int)((200 * 1024) / smem);
   const int tmem_lim = 512 / p.tmem_cols;
   if (per_sm > tmem_lim) per_sm = tmem_lim;

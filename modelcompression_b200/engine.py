@@ -68,6 +68,9 @@ class CompiledDarknet(object):
         self.block_out = {}  # models index -> _TensorRef
         self.flops_per_image = 0  # algorithmic (unpadded) conv FLOPs of the compiled (possibly shrunk) network
         self._alloc = {}     # (B, H, W) -> list of tensors
+        self._graphs = {}    # (shape, input address, stream) -> (CUDAGraph, static output, input)
+        self._graph_seen = {}
+        self.use_graph = True
         self.in_hw = None
         self._compile(model)
 
@@ -390,14 +393,42 @@ class CompiledDarknet(object):
             if b.fp32_nchw_channels:
                 tensors.append(None)  # allocated per call (returned to the caller)
             else:
+                # zero-initialised: pad rows/columns that no kernel writes, and the channels between a layer's physical
+                # channel count and the 8-aligned pitch, must be finite zeros (0-weight x NaN garbage would poison
+                # consumers that read whole 16-byte pixels)
                 rows = B * (b.H + 1) * (b.W + 1)
-                f = torch.zeros if b.zero_init else torch.empty
-                tensors.append(f(rows, b.ld, dtype=torch.bfloat16, device=self.device))
+                tensors.append(torch.zeros(rows, b.ld, dtype=torch.bfloat16, device=self.device))
         self._alloc[key] = tensors
         return tensors
 
     def run(self, x, events=None):
-        """events: optional list; when given, (op, start_event, end_event) is appended per op (bench/profiling)."""
+        """Forward.  The launch sequence is captured into a CUDA graph the second time an input buffer (same
+        device address and shape) is seen and replayed afterwards: ~25 launches per step otherwise cost more host time
+        than the GPU needs for the small layers.  events: optional list; when given the eager path is used and
+        (op, start_event, end_event) is appended per op (bench/profiling)."""
+        if events is not None or not self.use_graph or not x.is_cuda or x.dtype != torch.float32 or \
+                not x.is_contiguous() or x.requires_grad:
+            return self._run_eager(x, events)
+        key = (tuple(x.shape), x.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream)
+        entry = self._graphs.get(key)
+        if entry is None:
+            seen = self._graph_seen.get(key, 0)
+            self._graph_seen[key] = seen + 1
+            if seen < 1:
+                return self._run_eager(x, None)
+            if len(self._graphs) >= 8:
+                self._graphs.pop(next(iter(self._graphs)))
+            with torch.cuda.device(self.device):
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    out = self._run_eager(x, None)
+            entry = (graph, out, x)  # keep the input tensor alive: the graph reads its address
+            self._graphs[key] = entry
+        entry[0].replay()
+        return entry[1].clone()
+
+    def _run_eager(self, x, events=None):
         if x.dim() != 4:
             raise ValueError("expected [B,3,H,W] input")
         _lib.require_cuda(x, "Darknet.forward")
@@ -504,18 +535,18 @@ class CompiledDarknet(object):
 
 
 def _plan_key(model):
-    vers = []
-    for p in model.parameters():
-        vers.append(p._version)
-        vers.append(p.data_ptr())
-    for b in model.buffers():
-        vers.append(b._version)
-        vers.append(b.data_ptr())
-    for m in model.modules():
-        e = getattr(m, '_mask_epoch', None)
-        if e is not None:
-            vers.append(e)
-    return (bool(getattr(model, 'b200_shrink', True)), tuple(vers))
+    """Cheap change detector (~20 us): autograd version counters of every parameter/buffer (optimizer steps,
+    load_state_dict, in-place edits), storage addresses of the conv weights (.data reassignment, .to()), and the
+    set_mask epochs (libmcb200 writes weight.data behind autograd's back)."""
+    watch = getattr(model, '_b200_watch', None)
+    if watch is None:
+        tensors = list(model.parameters()) + list(model.buffers())
+        convs = [m for m in model.modules() if getattr(m, 'name', None) == 'MaskedConv2d']
+        watch = model._b200_watch = (tensors, convs, len(tensors))
+    tensors, convs, _ = watch
+    return (bool(getattr(model, 'b200_shrink', True)), tuple(t._version for t in tensors),
+            tuple(c.weight.data_ptr() for c in convs),
+            tuple((getattr(c, '_mask_epoch', 0), c.mask.data_ptr() if c.mask_flag else 0) for c in convs))
 
 
 def compile_darknet(model, force=False):

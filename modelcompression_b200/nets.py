@@ -124,6 +124,7 @@ class Darknet(nn.Module):
         # B200 engine state (not part of state_dict)
         self._b200_plan = None
         self._b200_plan_key = None
+        self._b200_watch = None
         self.b200_shrink = True      # physically drop filters whose (masked) weights are all zero
         self.b200_keep_blocks = False  # keep every block's activation buffer alive for per-block parity checks
 
@@ -236,6 +237,7 @@ class Darknet(nn.Module):
         for conv, mask in zip(convs, masks):
             conv.set_mask(mask)
         self._b200_plan = None
+        self._b200_watch = None  # new mask buffers: rebuild the change-detector's tensor list
 
     # ------------------------------------------------------------------ darknet .weights IO
     def _conv_blocks(self, cutoff=None):
