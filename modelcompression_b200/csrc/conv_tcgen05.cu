@@ -44,7 +44,132 @@ struct ConvKParams {
   int ldc, ch_off, epi_mode, leaky;
 };
 
-__device__ __forceinline__ float leaky01(float v) { return v > 0.f ? v : 0.1f * v; }
+// 16 accumulator columns of one row: y = acc*scale + shift (-> leaky) ; rows outside the image become 0.
+template <bool LEAKY>
+__device__ __forceinline__ void scale_act16(const uint32_t (&r)[16], const float* __restrict__ sc,
+                                            const float* __restrict__ sh, bool interior, float (&v)[16]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 a = *reinterpret_cast<const float4*>(sc + 4 * q);  // same address in every lane: smem broadcast
+    const float4 b = *reinterpret_cast<const float4*>(sh + 4 * q);
+    v[4 * q + 0] = fmaf(__uint_as_float(r[4 * q + 0]), a.x, b.x);
+    v[4 * q + 1] = fmaf(__uint_as_float(r[4 * q + 1]), a.y, b.y);
+    v[4 * q + 2] = fmaf(__uint_as_float(r[4 * q + 2]), a.z, b.z);
+    v[4 * q + 3] = fmaf(__uint_as_float(r[4 * q + 3]), a.w, b.w);
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (LEAKY) v[j] = fmaxf(v[j], 0.1f * v[j]);
+    v[j] = interior ? v[j] : 0.f;
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void store16(const ConvKParams& p, const float (&v)[16], int nbase, long long out_row_base,
+                                        bool vec_ok) {
+  if (MODE == MC_EPI_NCHW_F32) {
+    float* out_f = reinterpret_cast<float*>(p.out);
+    const long long hw = (long long)p.H * p.W;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (nbase + j < p.N) out_f[out_row_base + (long long)(nbase + j) * hw] = v[j];
+  } else {
+    __nv_bfloat16* out_bf = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row_base;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int n = nbase + g * 8;
+      if (vec_ok && n + 8 <= p.N) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[g * 8 + 0], v[g * 8 + 1]);
+        __nv_bfloat162 h1 = __floats2bfloat162_rn(v[g * 8 + 2], v[g * 8 + 3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[g * 8 + 4], v[g * 8 + 5]);
+        __nv_bfloat162 h3 = __floats2bfloat162_rn(v[g * 8 + 6], v[g * 8 + 7]);
+        uint4 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&h0);
+        pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        pk.z = *reinterpret_cast<uint32_t*>(&h2);
+        pk.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(out_bf + n) = pk;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (n + j < p.N) out_bf[n + j] = __float2bfloat16_rn(v[g * 8 + j]);
+      }
+    }
+  }
+}
+
+// Epilogue warps (threads 64..191): per tile, stage the tile's scale/shift in shared memory (double-buffered with
+// the accumulator stage, one named barrier per tile), then drain the accumulator 32 columns at a time.
+template <int MODE, bool LEAKY>
+__device__ __forceinline__ void epilogue_loop(const ConvKParams& p, uint32_t tmem_base, uint64_t* tmem_full_bar,
+                                              uint64_t* tmem_empty_bar, float* s_ss) {
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int et = threadIdx.x - 64;   // 0..127
+  const int quarter = warp_idx & 3;  // TMEM lane quarter this warp may access
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const bool vec_ok = ((p.ldc | p.ch_off) & 7) == 0 && (MODE != MC_EPI_REORG2 || (p.N & 7) == 0);
+  int as = 0;
+  uint32_t aphase = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int n0 = (tile % p.n_tiles) * p.block_n;
+    const int m0 = (tile / p.n_tiles) * BLOCK_M;
+    float* sc = s_ss + as * 512;
+    float* sh = sc + 256;
+    for (int i = et; i < p.block_n; i += 128) {
+      const bool ok = (n0 + i) < p.Npad;
+      sc[i] = ok ? __ldg(p.scale + n0 + i) : 0.f;
+      sh[i] = ok ? __ldg(p.shift + n0 + i) : 0.f;
+    }
+    const int row = m0 + quarter * 32 + lane;
+    const int x = row % p.Wp;
+    const int t = row / p.Wp;
+    const int y = t % p.Hp;
+    const int b = t / p.Hp;
+    const bool in_buf = row < p.M_rows;
+    const bool interior = in_buf && (x < p.W) && (y < p.H);
+    long long out_row_base = 0;
+    bool do_store = false;
+    if (MODE == MC_EPI_PNHWC) {
+      out_row_base = (long long)row * p.ldc + p.ch_off;
+      do_store = in_buf;  // pad rows are written as zeros to keep the layout invariant
+    } else if (MODE == MC_EPI_REORG2) {
+      const int Wo = p.W / 2 + 1, Ho = p.H / 2 + 1;
+      const long long orow = ((long long)b * Ho + (y >> 1)) * Wo + (x >> 1);
+      out_row_base = orow * p.ldc + p.ch_off + ((y & 1) * 2 + (x & 1)) * p.N;
+      do_store = interior;
+    } else {  // MC_EPI_NCHW_F32
+      out_row_base = ((long long)b * p.N * p.H + y) * p.W + x;  // + n*H*W
+      do_store = interior;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // scale/shift of this tile visible to the 4 epilogue warps
+
+    ptx::mbar_wait(&tmem_full_bar[as], aphase);
+    ptx::tc_fence_after();
+    const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.acc_stride);
+
+    for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+      uint32_t r0[16], r1[16];
+      const bool two = c0 + 16 < p.block_n;
+      ptx::tmem_ld_32x32b_x16(taddr_row + (uint32_t)c0, r0);
+      if (two) ptx::tmem_ld_32x32b_x16(taddr_row + (uint32_t)(c0 + 16), r1);
+      ptx::tmem_ld_wait();
+      if (!do_store) continue;
+      float v[16];
+      scale_act16<LEAKY>(r0, sc + c0, sh + c0, interior, v);
+      store16<MODE>(p, v, n0 + c0, out_row_base, vec_ok);
+      if (two) {
+        scale_act16<LEAKY>(r1, sc + c0 + 16, sh + c0 + 16, interior, v);
+        store16<MODE>(p, v, n0 + c0 + 16, out_row_base, vec_ok);
+      }
+    }
+    // this warp has finished reading the accumulator stage: hand it back to the MMA issuer
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+    if (++as == 2) { as = 0; aphase ^= 1u; }
+  }
+}
 
 // Persistent: grid = min(#tiles, #SMs); CTA c works on tiles c, c+grid, ...  The smem ring runs across tiles, and the
 // accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
@@ -52,7 +177,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const ConvKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve-up: [stages x (A 16KB | B block_n*128)] | barriers | tmem ptr
+  // carve-up: [stages x (A 16KB | B block_n*128)] | barriers | tmem ptr | scale/shift staging (4 KB)
   const uint32_t b_tile_bytes = (uint32_t)p.block_n * 128u;
   const uint32_t stage_bytes = A_TILE_BYTES + b_tile_bytes;
   uint8_t* smem = smem_raw;
@@ -67,6 +192,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* s_ss = reinterpret_cast<float*>(aux + 256);  // [2 acc stages][scale|shift][256]
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -149,90 +275,15 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
   } else {
     // ===================== epilogue: warps 2..5 =====================
-    const int quarter = warp_idx & 3;  // TMEM lane quarter this warp may access
-    __nv_bfloat16* out_bf = reinterpret_cast<__nv_bfloat16*>(p.out);
-    float* out_f = reinterpret_cast<float*>(p.out);
-    const bool vec_ok = ((p.ldc | p.ch_off) & 7) == 0 && (p.epi_mode != MC_EPI_REORG2 || (p.N & 7) == 0);
-    int as = 0;
-    uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n0 = (tile % p.n_tiles) * p.block_n;
-      const int m0 = (tile / p.n_tiles) * BLOCK_M;
-      const int row = m0 + quarter * 32 + lane;
-      const int x = row % p.Wp;
-      const int t = row / p.Wp;
-      const int y = t % p.Hp;
-      const int b = t / p.Hp;
-      const bool in_buf = row < p.M_rows;
-      const bool interior = in_buf && (x < p.W) && (y < p.H);
-      long long out_row_base = 0;
-      bool do_store = false;
-      if (p.epi_mode == MC_EPI_PNHWC) {
-        out_row_base = (long long)row * p.ldc + p.ch_off;
-        do_store = in_buf;  // pad rows are written as zeros to keep the layout invariant
-      } else if (p.epi_mode == MC_EPI_REORG2) {
-        const int Wo = p.W / 2 + 1, Ho = p.H / 2 + 1;
-        const long long orow = ((long long)b * Ho + (y >> 1)) * Wo + (x >> 1);
-        out_row_base = orow * p.ldc + p.ch_off + ((y & 1) * 2 + (x & 1)) * p.N;
-        do_store = interior;
-      } else {  // MC_EPI_NCHW_F32
-        out_row_base = ((long long)b * p.N * p.H + y) * p.W + x;  // + n*H*W
-        do_store = interior;
-      }
-
-      ptx::mbar_wait(&tmem_full_bar[as], aphase);
-      ptx::tc_fence_after();
-      const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.acc_stride);
-
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-        uint32_t r[16];
-        ptx::tmem_ld_32x32b_x16(taddr_row + (uint32_t)c0, r);
-        ptx::tmem_ld_wait();
-        if (!do_store) continue;
-        const int nbase = n0 + c0;
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int n = nbase + j;
-          const float sc = (n < p.Npad) ? __ldg(p.scale + n) : 0.f;
-          const float sh = (n < p.Npad) ? __ldg(p.shift + n) : 0.f;
-          float a = __uint_as_float(r[j]) * sc + sh;
-          if (p.leaky) a = leaky01(a);
-          v[j] = interior ? a : 0.f;
-        }
-        if (p.epi_mode == MC_EPI_NCHW_F32) {
-          const long long hw = (long long)p.H * p.W;
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (nbase + j < p.N) out_f[out_row_base + (long long)(nbase + j) * hw] = v[j];
-        } else {
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            const int n = nbase + g * 8;
-            if (vec_ok && n + 8 <= p.N) {
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[g * 8 + 0], v[g * 8 + 1]);
-              __nv_bfloat162 h1 = __floats2bfloat162_rn(v[g * 8 + 2], v[g * 8 + 3]);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[g * 8 + 4], v[g * 8 + 5]);
-              __nv_bfloat162 h3 = __floats2bfloat162_rn(v[g * 8 + 6], v[g * 8 + 7]);
-              uint4 pk;
-              pk.x = *reinterpret_cast<uint32_t*>(&h0);
-              pk.y = *reinterpret_cast<uint32_t*>(&h1);
-              pk.z = *reinterpret_cast<uint32_t*>(&h2);
-              pk.w = *reinterpret_cast<uint32_t*>(&h3);
-              *reinterpret_cast<uint4*>(out_bf + out_row_base + n) = pk;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                if (n + j < p.N) out_bf[out_row_base + n + j] = __float2bfloat16_rn(v[g * 8 + j]);
-            }
-          }
-        }
-      }
-      // this warp has finished reading the accumulator stage: hand it back to the MMA issuer
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
-      if (++as == 2) { as = 0; aphase ^= 1u; }
+    if (p.epi_mode == MC_EPI_PNHWC) {
+      if (p.leaky) epilogue_loop<MC_EPI_PNHWC, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss);
+      else epilogue_loop<MC_EPI_PNHWC, false>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss);
+    } else if (p.epi_mode == MC_EPI_REORG2) {
+      if (p.leaky) epilogue_loop<MC_EPI_REORG2, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss);
+      else epilogue_loop<MC_EPI_REORG2, false>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss);
+    } else {
+      if (p.leaky) epilogue_loop<MC_EPI_NCHW_F32, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss);
+      else epilogue_loop<MC_EPI_NCHW_F32, false>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss);
     }
   }
 
@@ -370,11 +421,11 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   const int stage_bytes = A_TILE_BYTES + block_n * 128;
   int stages = d->stages;
   if (stages <= 0) {
-    stages = (208 * 1024) / stage_bytes;
+    stages = (204 * 1024) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
   }
   MC_CHECK_ARG(stages >= 1 && stages <= MAX_STAGES, "mc_conv_fwd: stages %d invalid", stages);
-  const size_t smem_bytes = (size_t)stages * stage_bytes + 256 + 1024;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + 256 + 4096 + 1024;
   MC_CHECK_ARG(smem_bytes <= 227 * 1024, "mc_conv_fwd: smem %zu too large", smem_bytes);
 
   CUtensorMap tm_a, tm_b;
