@@ -218,7 +218,9 @@ def main():
         return model(xs[i % len(xs)])
 
     with torch.no_grad():
-        for i in range(args.warmup):
+        # warm-up: at least W steps and at least two passes over every input buffer (the engine captures its CUDA
+        # graph the second time it sees a buffer; captures must not land in the timed region)
+        for i in range(max(args.warmup, 2 * len(xs))):
             step(i)
         torch.cuda.synchronize()
         if world > 1:
@@ -296,7 +298,7 @@ def main():
                 host_out[cur].copy_(out, non_blocking=True)
             torch.cuda.synchronize()
 
-        e2e_loop(3)
+        e2e_loop(4)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -340,7 +342,7 @@ def main():
             line["mask"] = time_masks(dense, peaks)
             if args.dense:
                 with torch.no_grad():
-                    for i in range(3):
+                    for i in range(6):
                         dense(xs[i % 3])
                     torch.cuda.synchronize()
                     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
