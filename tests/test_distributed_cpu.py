@@ -1,0 +1,56 @@
+"""CPU, gloo, world size 2: the host-side logic of the batch-sharded evaluation (shard ranges + the two-collective
+detection gather).  The per-shard compute is CUDA-only and is covered by test_gpu_eval.py."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from modelcompression_b200.eval import DET_COLS, gather_detections, shard_range
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _fake_detections(lo, hi):
+    """Deterministic ragged detections for images [lo, hi): image i has (i % 4) rows (so some images have none)."""
+    rows = []
+    for i in range(lo, hi):
+        for j in range(i % 4):
+            rows.append([float(i)] + [float(i * 10 + j + c) for c in range(DET_COLS - 1)])
+    return torch.tensor(rows, dtype=torch.float32).view(-1, DET_COLS)
+
+
+def _worker(rank, world, port, n_images, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        lo, hi = shard_range(n_images, rank, world)
+        local = _fake_detections(lo, hi)
+        got = gather_detections(local)
+        want = _fake_detections(0, n_images)
+        assert got.shape == want.shape, (got.shape, want.shape)
+        assert torch.equal(got, want), "rank-major gather must equal the single-process result"
+        torch.save(got, os.path.join(out_dir, 'rank%d.pt' % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_images", [7, 1, 0, 64])
+def test_gather_detections_world2(tmp_path, n_images):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, n_images, str(tmp_path)), nprocs=2, join=True)
+    a = torch.load(os.path.join(str(tmp_path), 'rank0.pt'))
+    b = torch.load(os.path.join(str(tmp_path), 'rank1.pt'))
+    assert torch.equal(a, b)  # every rank ends with the same, image-ordered table
+
+
+def test_gather_is_identity_without_process_group():
+    x = _fake_detections(0, 5)
+    assert gather_detections(x) is x
