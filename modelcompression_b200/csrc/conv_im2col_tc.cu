@@ -18,8 +18,7 @@
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 
-int mc_make_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
-                         uint32_t box_rows);
+#include "tmap.cuh"
 
 namespace {
 
@@ -66,7 +65,8 @@ __device__ __forceinline__ void store_group(__nv_bfloat16* dst, int n0, const fl
 
 template <int CL, bool POOL, bool FIRST>
 __global__ void __launch_bounds__(128, 4)
-conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const Im2colParams p) {
+conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_in,
+                      const Im2colParams p) {
   constexpr int PR = POOL ? 2 * TY + 2 : TY + 2;   // patch rows / cols (conv pixels incl. halo)
   constexpr int PC = POOL ? 2 * TX + 2 : TX + 2;
   constexpr int NPIX = POOL ? 16 : 9;              // patch pixels per GEMM row
@@ -80,17 +80,26 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const Im2colPa
   uint8_t* a_tile = smem;                                   // [NKB][128 rows][128 B], 128B swizzle
   uint8_t* b_tile = a_tile + A_BYTES;                       // [NKB][nb_pad rows][128 B]
   const int nb_pad = (p.nb + 15) & ~15;
-  __nv_bfloat16* patch = reinterpret_cast<__nv_bfloat16*>(b_tile + (size_t)NKB * nb_pad * 128);  // [PR][PC][CL]
-  uint64_t* b_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(patch) + ((PR * PC * CL * 2 + 15) & ~15));
+  // input patch, double-buffered, filled by TMA (out-of-image elements arrive as zeros):
+  //   FIRST: fp32 [Cin][PR][PCF] (PCF = PC rounded up to a 16-byte multiple); else bf16 [PR][PC][CL]
+  constexpr int PCF = (PC + 3) & ~3;
+  const uint32_t patch_bytes = FIRST ? (uint32_t)(p.Cin * PR * PCF * 4) : (uint32_t)(PR * PC * CL * 2);
+  const uint32_t patch_stride = (patch_bytes + 127u) & ~127u;
+  uint8_t* patch0 = b_tile + (size_t)NKB * nb_pad * 128;  // 1024-aligned
+  uint64_t* b_bar = reinterpret_cast<uint64_t*>(patch0 + 2 * patch_stride);
   uint64_t* mma_bar = b_bar + 1;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(mma_bar + 1);
+  uint64_t* patch_bar = mma_bar + 1;  // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(patch_bar + 2);
 
   const int t = threadIdx.x;
   const int warp_idx = t >> 5;
   if (t == 0) {
     ptx::prefetch_tensormap(&tmap_b);
+    ptx::prefetch_tensormap(&tmap_in);
     ptx::mbar_init(b_bar, 1);
     ptx::mbar_init(mma_bar, 1);
+    ptx::mbar_init(&patch_bar[0], 1);
+    ptx::mbar_init(&patch_bar[1], 1);
     ptx::fence_barrier_init();
   }
   if (warp_idx == 0) {
@@ -113,70 +122,31 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const Im2colPa
   uint32_t mma_phase = 0;
   bool b_ready = false;
 
-  // Patch staging goes through registers so that the global loads of tile i+1 are in flight while tile i is built,
-  // multiplied and stored (one DRAM round trip per tile would otherwise sit on the critical path).
-  constexpr int PV = FIRST ? 1 : CL / 8;                       // 16-byte vectors per patch pixel (FIRST: one pixel)
-  constexpr int NLOAD = (PR * PC * PV + 127) / 128;
-  float pf[FIRST ? NLOAD * 4 : 1];
-  uint4 pq[FIRST ? 1 : NLOAD];
-  auto load_patch = [&](int tile) {
+  // one thread asks TMA for the patch of `tile` into buffer `buf`
+  auto issue_patch = [&](int tile, int buf) {
     const int tx = tile % p.tiles_x;
     const int ty = (tile / p.tiles_x) % p.tiles_y;
     const int b = tile / (p.tiles_x * p.tiles_y);
     const int iy0 = (POOL ? 2 * ty * TY : ty * TY) - 1, ix0 = (POOL ? 2 * tx * TX : tx * TX) - 1;
-#pragma unroll
-    for (int u = 0; u < NLOAD; ++u) {
-      const int i = t + u * 128;
-      const int pix = i / PV, v = i - pix * PV;
-      const int r = pix / PC, sx = pix - r * PC;
-      const int yy = iy0 + r, xx = ix0 + sx;
-      const bool ok = (i < PR * PC * PV) && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
-      if constexpr (FIRST) {
-        const float* img = reinterpret_cast<const float*>(p.in);
-        const long long o = ((long long)b * p.Cin * p.H + yy) * p.W + xx;
-        const long long plane = (long long)p.H * p.W;
-        pf[u * 4 + 0] = ok ? img[o] : 0.f;
-        pf[u * 4 + 1] = (ok && p.Cin > 1) ? img[o + plane] : 0.f;
-        pf[u * 4 + 2] = (ok && p.Cin > 2) ? img[o + 2 * plane] : 0.f;
-        pf[u * 4 + 3] = (ok && p.Cin > 3) ? img[o + 3 * plane] : 0.f;
-      } else {
-        const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.in);
-        pq[u] = ok ? *reinterpret_cast<const uint4*>(
-                         x + (((long long)b * (p.H + 1) + yy) * (p.W + 1) + xx) * p.Cin_ld + v * 8)
-                   : make_uint4(0, 0, 0, 0);
-      }
-    }
-  };
-  auto store_patch = [&]() {
-#pragma unroll
-    for (int u = 0; u < NLOAD; ++u) {
-      const int i = t + u * 128;
-      if (i < PR * PC * PV) {
-        if constexpr (FIRST) {
-          __nv_bfloat162 lo = __floats2bfloat162_rn(pf[u * 4 + 0], pf[u * 4 + 1]);
-          __nv_bfloat162 hi = __floats2bfloat162_rn(pf[u * 4 + 2], pf[u * 4 + 3]);
-          uint2 pk;
-          pk.x = *reinterpret_cast<uint32_t*>(&lo);
-          pk.y = *reinterpret_cast<uint32_t*>(&hi);
-          *reinterpret_cast<uint2*>(patch + (size_t)i * CL) = pk;  // CL == 4 for FIRST
-        } else {
-          *reinterpret_cast<uint4*>(patch + (size_t)i * 8) = pq[u];  // pixel-major, PV vectors per pixel
-        }
-      }
-    }
+    ptx::mbar_arrive_expect_tx(&patch_bar[buf], patch_bytes);
+    if constexpr (FIRST) ptx::tma_load_4d(patch0 + buf * patch_stride, &tmap_in, &patch_bar[buf], ix0, iy0, 0, b);
+    else ptx::tma_load_3d(patch0 + buf * patch_stride, &tmap_in, &patch_bar[buf], 0, ix0, b * (p.H + 1) + iy0);
   };
 
-  if ((int)blockIdx.x < p.total_tiles) load_patch(blockIdx.x);
-  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+  if (t == 0 && (int)blockIdx.x < p.total_tiles) issue_patch(blockIdx.x, 0);
+  int it = 0;
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
     const int tx = tile % p.tiles_x;
     const int ty = (tile / p.tiles_x) % p.tiles_y;
     const int b = tile / (p.tiles_x * p.tiles_y);
     const int oy0 = ty * TY, ox0 = tx * TX;  // first output row/col of the tile
+    const int buf = it & 1;
 
-    // ---- 1. patch registers -> shared memory (bf16 [PR][PC][CL]); then prefetch the next tile's patch
-    store_patch();
-    __syncthreads();
-    if (tile + (int)gridDim.x < p.total_tiles) load_patch(tile + gridDim.x);
+    // ---- 1. prefetch the next tile's patch (its buffer was last read two tiles ago, behind a __syncthreads), then
+    //         wait for this tile's patch
+    if (t == 0 && tile + (int)gridDim.x < p.total_tiles) issue_patch(tile + gridDim.x, buf ^ 1);
+    ptx::mbar_wait(&patch_bar[buf], (uint32_t)((it >> 1) & 1));
+    const uint8_t* patch_raw = patch0 + buf * patch_stride;
 
     // ---- 2. build GEMM row t: NPIX patch pixels x CL channels, pixel-major, zero padded to NKB*64 elements
     {
@@ -185,23 +155,40 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const Im2colPa
       for (int q = 0; q < NKB * 8; ++q) {  // 16-byte chunk q holds K elements [8q, 8q+8)
         uint4 val = make_uint4(0, 0, 0, 0);
         if (q * 8 < KELEMS) {
-          if constexpr (CL == 4) {
-            const int pa = 2 * q, pb = 2 * q + 1;  // two pixels per chunk
-            uint2 lo = make_uint2(0, 0), hi = make_uint2(0, 0);
-            {
-              const int r = POOL ? pa / 4 : pa / 3, s = POOL ? pa % 4 : pa % 3;
-              lo = *reinterpret_cast<const uint2*>(patch + ((by + r) * PC + bx + s) * CL);
+          if constexpr (FIRST) {
+            // two pixels per chunk, 4 bf16 each (c0,c1,c2,c3; absent channels 0); patch is fp32 [c][PR][PCF]
+            const float* pf = reinterpret_cast<const float*>(patch_raw);
+            const int pa = 2 * q, pb = 2 * q + 1;
+            float va[4] = {0.f, 0.f, 0.f, 0.f}, vb[4] = {0.f, 0.f, 0.f, 0.f};
+            if constexpr (POOL) {  // pa, pb are x-neighbours (px even): one 8-byte load per channel
+              const int r = pa / 4, sx = pa % 4;
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                if (c < p.Cin) {
+                  const float2 f = *reinterpret_cast<const float2*>(pf + (c * PR + by + r) * PCF + bx + sx);
+                  va[c] = f.x;
+                  vb[c] = f.y;
+                }
+            } else {
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                if (c < p.Cin) {
+                  va[c] = pf[(c * PR + by + pa / 3) * PCF + bx + pa % 3];
+                  if (pb < NPIX) vb[c] = pf[(c * PR + by + pb / 3) * PCF + bx + pb % 3];
+                }
             }
-            if (pb < NPIX) {
-              const int r = POOL ? pb / 4 : pb / 3, s = POOL ? pb % 4 : pb % 3;
-              hi = *reinterpret_cast<const uint2*>(patch + ((by + r) * PC + bx + s) * CL);
-            }
-            val = make_uint4(lo.x, lo.y, hi.x, hi.y);
+            __nv_bfloat162 a0 = __floats2bfloat162_rn(va[0], va[1]), a1 = __floats2bfloat162_rn(va[2], va[3]);
+            __nv_bfloat162 b0 = __floats2bfloat162_rn(vb[0], vb[1]), b1 = __floats2bfloat162_rn(vb[2], vb[3]);
+            val.x = *reinterpret_cast<uint32_t*>(&a0);
+            val.y = *reinterpret_cast<uint32_t*>(&a1);
+            val.z = *reinterpret_cast<uint32_t*>(&b0);
+            val.w = *reinterpret_cast<uint32_t*>(&b1);
           } else {
+            const __nv_bfloat16* patch = reinterpret_cast<const __nv_bfloat16*>(patch_raw);
             constexpr int V = CL / 8;
             const int pix = q / V, v = q % V;
-            const int r = POOL ? pix / 4 : pix / 3, s = POOL ? pix % 4 : pix % 3;
-            val = *reinterpret_cast<const uint4*>(patch + ((by + r) * PC + bx + s) * CL + v * 8);
+            const int r = POOL ? pix / 4 : pix / 3, sx = POOL ? pix % 4 : pix % 3;
+            val = *reinterpret_cast<const uint4*>(patch + ((by + r) * PC + bx + sx) * CL + v * 8);
           }
         }
         const int kb = q >> 3, j = q & 7;
@@ -311,11 +298,32 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const Im2colPa
 template <int CL, bool POOL, bool FIRST>
 int launch_im2col(const CUtensorMap& tm_b, const Im2colParams& p, cudaStream_t stream) {
   constexpr int PR = POOL ? 2 * TY + 2 : TY + 2, PC = POOL ? 2 * TX + 2 : TX + 2;
+  constexpr int PCF = (PC + 3) & ~3;
   constexpr int NPIX = POOL ? 16 : 9;
   constexpr int NKB = (NPIX * CL + 63) / 64;
   const int nb_pad = (p.nb + 15) & ~15;
-  const size_t smem = (size_t)NKB * 128 * 128 + (size_t)NKB * nb_pad * 128 + ((PR * PC * CL * 2 + 15) & ~15) + 64 + 1024;
+  const size_t patch_bytes = FIRST ? (size_t)p.Cin * PR * PCF * 4 : (size_t)PR * PC * CL * 2;
+  const size_t patch_stride = (patch_bytes + 127) & ~(size_t)127;
+  const size_t smem = (size_t)NKB * 128 * 128 + (size_t)NKB * nb_pad * 128 + 2 * patch_stride + 64 + 1024;
   if (smem > 227 * 1024) return mc_set_error(MC_ERR_SHAPE, "mc_conv_im2col_fwd: %zu B of shared memory", smem);
+
+  // input patch tensor map
+  CUtensorMap tm_in;
+  int rc;
+  if (FIRST) {  // fp32 NCHW [B][Cin][H][W], box [1][Cin][PR][PCF]
+    const uint64_t dims[4] = {(uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.Cin, (uint64_t)p.B};
+    const uint64_t strides[3] = {(uint64_t)p.W * 4, (uint64_t)p.W * p.H * 4, (uint64_t)p.W * p.H * p.Cin * 4};
+    const uint32_t box[4] = {(uint32_t)PCF, (uint32_t)PR, (uint32_t)p.Cin, 1};
+    if ((p.W * 4) % 16 != 0) return mc_set_error(MC_ERR_SHAPE, "mc_conv_im2col_fwd: image width must be a multiple of 4");
+    rc = mc_make_tmap(&tm_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+  } else {      // bf16 PNHWC viewed as [B*(H+1)][W+1][CL], box [PR][PC][CL]
+    const uint64_t dims[3] = {(uint64_t)CL, (uint64_t)(p.W + 1), (uint64_t)p.B * (p.H + 1)};
+    const uint64_t strides[2] = {(uint64_t)CL * 2, (uint64_t)(p.W + 1) * CL * 2};
+    const uint32_t box[3] = {(uint32_t)CL, (uint32_t)PC, (uint32_t)PR};
+    rc = mc_make_tmap(&tm_in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, p.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+  }
+  if (rc) return rc;
+
   auto kern = conv_im2col_tc_kernel<CL, POOL, FIRST>;
   static size_t attr_smem = 0;  // per template instantiation
   if (smem > attr_smem) {
@@ -329,7 +337,7 @@ int launch_im2col(const CUtensorMap& tm_b, const Im2colParams& p, cudaStream_t s
   if (per_sm < 1) per_sm = 1;
   long long grid = (long long)mc_num_sms() * per_sm;
   if (grid > p.total_tiles) grid = p.total_tiles;
-  kern<<<(int)grid, 128, smem, stream>>>(tm_b, p);
+  kern<<<(int)grid, 128, smem, stream>>>(tm_b, tm_in, p);
   MC_LAUNCH_CHECK("conv_im2col_tc_kernel");
   return 0;
 }

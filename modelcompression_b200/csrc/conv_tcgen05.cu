@@ -13,11 +13,9 @@
 // 128-byte swizzle row.  Warp roles: warp0 = TMA producer, warp1 = TMEM owner + MMA issuer (one thread),
 // warps 2..5 = epilogue (TMEM -> regs -> scale/shift/leaky -> bf16/fp32 global stores).
 #include <cuda.h>
-#include <mutex>
-#include <unordered_map>
-#include <string>
 #include "common.cuh"
 #include "ptx_sm100.cuh"
+#include "tmap.cuh"
 
 namespace {
 
@@ -292,78 +290,6 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp_idx == 1) ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Host side: tensor-map construction (driver entry point fetched at run time: no link-time libcuda dependency)
-// ---------------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  });
-  return fn;
-}
-
-// 2-D bf16 row-major [rows, cols] with row pitch ld (elements), box = [box_rows, 64 cols], 128B swizzle.
-int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) return mc_set_error(MC_ERR_ARG, "cuTensorMapEncodeTiled entry point unavailable");
-  cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS)
-    return mc_set_error(MC_ERR_ARG, "cuTensorMapEncodeTiled failed (CUresult %d) rows=%llu cols=%llu ld=%llu box_rows=%u",
-                        (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
-  return 0;
-}
-
-struct TmapKey {
-  const void* base;
-  uint64_t rows, cols, ld;
-  uint32_t box_rows;
-  bool operator==(const TmapKey& o) const {
-    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
-  }
-};
-struct TmapKeyHash {
-  size_t operator()(const TmapKey& k) const {
-    size_t h = std::hash<const void*>()(k.base);
-    h ^= std::hash<uint64_t>()(k.rows * 1315423911ull + k.cols * 2654435761ull + k.ld * 97ull + k.box_rows);
-    return h;
-  }
-};
-
-int cached_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
-  static std::mutex mu;
-  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
-  TmapKey key{base, rows, cols, ld, box_rows};
-  std::lock_guard<std::mutex> lock(mu);
-  auto it = cache.find(key);
-  if (it != cache.end()) {
-    *out = it->second;
-    return 0;
-  }
-  CUtensorMap tm;
-  int rc = make_tmap_2d(&tm, base, rows, cols, ld, box_rows);
-  if (rc) return rc;
-  if (cache.size() > 4096) cache.clear();
-  cache.emplace(key, tm);
-  *out = tm;
-  return 0;
-}
-
 // Tile-width heuristic.  One 64-wide k-block of a 128 x bn tile costs max(2*bn, 128+bn) SM cycles: 2*bn is the
 // tcgen05 issue floor (128*bn*64 MACs at 4096 MAC/clk), 128+bn is the shared-memory read of the A (16 KB) and
 // B (bn*128 B) tiles at 128 B/clk.  Cost = waves over the SMs x (k-blocks x that + a fixed prologue/epilogue).
@@ -386,12 +312,6 @@ int pick_block_n(int Npad, int m_tiles, int num_kb, int num_sms) {
 }
 
 }  // namespace
-
-// shared with conv_im2col_tc.cu
-int mc_make_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
-                         uint32_t box_rows) {
-  return cached_tmap(tm, base, rows, cols, ld, box_rows);
-}
 
 extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -429,10 +349,10 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   MC_CHECK_ARG(smem_bytes <= 227 * 1024, "mc_conv_fwd: smem %zu too large", smem_bytes);
 
   CUtensorMap tm_a, tm_b;
-  int rc = cached_tmap(&tm_a, d->d_in, (uint64_t)M_rows, (uint64_t)d->Cin, (uint64_t)d->Cin_ld, BLOCK_M);
+  int rc = mc_make_tmap_2d_bf16(&tm_a, d->d_in, (uint64_t)M_rows, (uint64_t)d->Cin, (uint64_t)d->Cin_ld, BLOCK_M);
   if (rc) return rc;
   // weights: [n_tiles*block_n >= Npad rows (OOB rows zero-filled), ntaps*Kc]
-  rc = cached_tmap(&tm_b, d->d_wpack, (uint64_t)d->Npad, (uint64_t)ntaps * Kc, (uint64_t)ntaps * Kc, (uint32_t)block_n);
+  rc = mc_make_tmap_2d_bf16(&tm_b, d->d_wpack, (uint64_t)d->Npad, (uint64_t)ntaps * Kc, (uint64_t)ntaps * Kc, (uint32_t)block_n);
   if (rc) return rc;
 
   ConvKParams p;
