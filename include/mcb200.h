@@ -173,6 +173,9 @@ int mc_conv_im2col_fwd(const void* d_in, int in_is_nchw_f32, const void* d_wexp,
                        const float* d_shift, void* d_out, int B, int H, int W, int Cin, int Cin_ld, int N, int ldc,
                        int leaky, int pool, void* stream);
 
+/* Debug aid: code of the first mbarrier wait that timed out inside mc_conv_im2col_fwd kernels (0 = none). */
+int mc_debug_im2col_timeout(void);
+
 /* fp32 [O,C,kh,kw] (optionally * mask, optionally gathered by h_oidx/h_cidx surviving-index lists)
  * -> bf16 [Npad, kh*kw*Kc] with column (tap*Kc + c).  d_oidx/d_cidx are device int32 arrays or NULL. */
 int mc_pack_conv_weights(const float* d_w, const float* d_mask, int O, int C, int ksize,

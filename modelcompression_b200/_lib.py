@@ -62,6 +62,7 @@ _SIGNATURES = {
                                         POINTER(c_int)]),
     "mc_conv_im2col_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                    c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mc_debug_im2col_timeout": (c_int, []),
     "mc_pack_conv_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int,
                                      c_void_p, c_int, c_int, c_void_p]),
     "mc_maxpool2x2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -22,6 +22,8 @@
 
 namespace {
 
+__device__ unsigned int g_im2col_dbg = 0;  // first mbarrier wait that timed out (0 = none)
+
 constexpr int TY = 8, TX = 16;  // tile of GEMM rows
 
 struct Im2colParams {
@@ -81,8 +83,10 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
   uint8_t* b_tile = a_tile + A_BYTES;                       // [NKB][nb_pad rows][128 B]
   const int nb_pad = (p.nb + 15) & ~15;
   // input patch, double-buffered, filled by TMA (out-of-image elements arrive as zeros):
-  //   FIRST: fp32 [Cin][PR][PCF] (PCF = PC rounded up to a 16-byte multiple); else bf16 [PR][PC][CL]
-  constexpr int PCF = (PC + 3) & ~3;
+  //   FIRST: fp32 [Cin][PR][PCF]; TMA needs a 16-byte aligned innermost start, so the box begins XS = 3 columns left
+  //   of the halo column (x0-4 instead of x0-1) and PCF = round_up(PC + 3, 4); else bf16 [PR][PC][CL]
+  constexpr int XS = 3;
+  constexpr int PCF = (PC + XS + 3) & ~3;
   const uint32_t patch_bytes = FIRST ? (uint32_t)(p.Cin * PR * PCF * 4) : (uint32_t)(PR * PC * CL * 2);
   const uint32_t patch_stride = (patch_bytes + 127u) & ~127u;
   uint8_t* patch0 = b_tile + (size_t)NKB * nb_pad * 128;  // 1024-aligned
@@ -129,7 +133,7 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
     const int b = tile / (p.tiles_x * p.tiles_y);
     const int iy0 = (POOL ? 2 * ty * TY : ty * TY) - 1, ix0 = (POOL ? 2 * tx * TX : tx * TX) - 1;
     ptx::mbar_arrive_expect_tx(&patch_bar[buf], patch_bytes);
-    if constexpr (FIRST) ptx::tma_load_4d(patch0 + buf * patch_stride, &tmap_in, &patch_bar[buf], ix0, iy0, 0, b);
+    if constexpr (FIRST) ptx::tma_load_4d(patch0 + buf * patch_stride, &tmap_in, &patch_bar[buf], ix0 - XS, iy0, 0, b);
     else ptx::tma_load_3d(patch0 + buf * patch_stride, &tmap_in, &patch_bar[buf], 0, ix0, b * (p.H + 1) + iy0);
   };
 
@@ -145,7 +149,7 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
     // ---- 1. prefetch the next tile's patch (its buffer was last read two tiles ago, behind a __syncthreads), then
     //         wait for this tile's patch
     if (t == 0 && tile + (int)gridDim.x < p.total_tiles) issue_patch(tile + gridDim.x, buf ^ 1);
-    ptx::mbar_wait(&patch_bar[buf], (uint32_t)((it >> 1) & 1));
+    ptx::mbar_wait(&patch_bar[buf], (uint32_t)((it >> 1) & 1), &g_im2col_dbg, 0x100u + (unsigned)it);
     const uint8_t* patch_raw = patch0 + buf * patch_stride;
 
     // ---- 2. build GEMM row t: NPIX patch pixels x CL channels, pixel-major, zero padded to NKB*64 elements
@@ -160,21 +164,21 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
             const float* pf = reinterpret_cast<const float*>(patch_raw);
             const int pa = 2 * q, pb = 2 * q + 1;
             float va[4] = {0.f, 0.f, 0.f, 0.f}, vb[4] = {0.f, 0.f, 0.f, 0.f};
-            if constexpr (POOL) {  // pa, pb are x-neighbours (px even): one 8-byte load per channel
+            if constexpr (POOL) {  // pa, pb are x-neighbours
               const int r = pa / 4, sx = pa % 4;
 #pragma unroll
               for (int c = 0; c < 4; ++c)
                 if (c < p.Cin) {
-                  const float2 f = *reinterpret_cast<const float2*>(pf + (c * PR + by + r) * PCF + bx + sx);
-                  va[c] = f.x;
-                  vb[c] = f.y;
+                  const float* src = pf + (c * PR + by + r) * PCF + bx + sx + XS;
+                  va[c] = src[0];
+                  vb[c] = src[1];
                 }
             } else {
 #pragma unroll
               for (int c = 0; c < 4; ++c)
                 if (c < p.Cin) {
-                  va[c] = pf[(c * PR + by + pa / 3) * PCF + bx + pa % 3];
-                  if (pb < NPIX) vb[c] = pf[(c * PR + by + pb / 3) * PCF + bx + pb % 3];
+                  va[c] = pf[(c * PR + by + pa / 3) * PCF + bx + pa % 3 + XS];
+                  if (pb < NPIX) vb[c] = pf[(c * PR + by + pb / 3) * PCF + bx + pb % 3 + XS];
                 }
             }
             __nv_bfloat162 a0 = __floats2bfloat162_rn(va[0], va[1]), a1 = __floats2bfloat162_rn(va[2], va[3]);
@@ -201,7 +205,7 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
 
     // ---- 3. MMA (one thread)
     if (t == 0) {
-      if (!b_ready) ptx::mbar_wait(b_bar, 0);
+      if (!b_ready) ptx::mbar_wait(b_bar, 0, &g_im2col_dbg, 0x200u);
       ptx::tc_fence_after();
       const uint32_t a_addr = ptx::smem_u32(a_tile), b_addr = ptx::smem_u32(b_tile);
       for (int ks = 0; ks < p.ksteps; ++ks) {
@@ -215,7 +219,7 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
     b_ready = true;
 
     // ---- 4. epilogue: TMEM lane t -> scale/shift (-> max over the 4 window positions) -> leaky -> bf16 store
-    ptx::mbar_wait(mma_bar, mma_phase);
+    ptx::mbar_wait(mma_bar, mma_phase, &g_im2col_dbg, 0x300u + (unsigned)it);
     mma_phase ^= 1u;
     ptx::tc_fence_after();
     const int oy = oy0 + wy, ox = ox0 + wx;
@@ -298,7 +302,7 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
 template <int CL, bool POOL, bool FIRST>
 int launch_im2col(const CUtensorMap& tm_b, const Im2colParams& p, cudaStream_t stream) {
   constexpr int PR = POOL ? 2 * TY + 2 : TY + 2, PC = POOL ? 2 * TX + 2 : TX + 2;
-  constexpr int PCF = (PC + 3) & ~3;
+  constexpr int PCF = (PC + 3 + 3) & ~3;  // see XS in the kernel
   constexpr int NPIX = POOL ? 16 : 9;
   constexpr int NKB = (NPIX * CL + 63) / 64;
   const int nb_pad = (p.nb + 15) & ~15;
@@ -343,6 +347,15 @@ int launch_im2col(const CUtensorMap& tm_b, const Im2colParams& p, cudaStream_t s
 }
 
 }  // namespace
+
+// Debug: code of the first mbarrier wait that timed out in conv_im2col_tc_kernel since the last call (0 = none):
+// 0x100+it patch TMA, 0x200 weight TMA, 0x300+it MMA commit.
+extern "C" int mc_debug_im2col_timeout(void) {
+  unsigned int v = 0, zero = 0;
+  if (cudaMemcpyFromSymbol(&v, g_im2col_dbg, sizeof(v)) != cudaSuccess) return -1;
+  cudaMemcpyToSymbol(g_im2col_dbg, &zero, sizeof(zero));
+  return (int)v;
+}
 
 // K elements per GEMM row (before padding to a multiple of 64) and UMMA-N of the expanded weight matrix.
 extern "C" int mc_conv_im2col_supported(int Cin, int in_is_nchw_f32, int N, int pool) {

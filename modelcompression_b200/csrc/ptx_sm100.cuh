@@ -51,11 +51,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a broken pipeline traps (launch error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Bounded wait: a broken pipeline traps (launch error) instead of hanging the GPU.  With a debug flag the timeout is
+// recorded (first code wins) and execution continues, so the host can report WHICH wait starved.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned int* dbg_flag = nullptr,
+                                          unsigned int dbg_code = 0) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if (++spins > (1u << 22)) {
+      if (dbg_flag != nullptr) {
+        atomicCAS(dbg_flag, 0u, dbg_code);
+        return;
+      }
+      if (spins > (1u << 26)) __trap();
+    }
   }
 }
 
