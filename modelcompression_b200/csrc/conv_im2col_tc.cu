@@ -35,13 +35,12 @@ struct Im2colParams {
   int Cin, Cin_ld;      // valid input channels, input pitch (PNHWC) — FIRST: Cin planes of the NCHW image
   int N, npos, nb;      // valid outputs; per-position column stride; UMMA N (pool: 4*npos, else npos)
   int ldc, leaky;
+  int nsc;              // entries of scale/shift that may be read
   int nkb, ksteps;      // k-blocks of 64, total UMMA K steps (16 elements each)
   int tiles_x, tiles_y, total_tiles;
   int tmem_cols;
   uint32_t idesc;
 };
-
-__device__ __forceinline__ float leaky01(float v) { return v > 0.f ? v : 0.1f * v; }
 
 __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
@@ -94,6 +93,8 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
   uint64_t* mma_bar = b_bar + 1;
   uint64_t* patch_bar = mma_bar + 1;  // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(patch_bar + 2);
+  float* s_sc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(b_bar) + 64);  // [256] scale, [256] shift
+  float* s_sh = s_sc + 256;
 
   const int t = threadIdx.x;
   const int warp_idx = t >> 5;
@@ -109,6 +110,11 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
   if (warp_idx == 0) {
     ptx::tmem_alloc(tmem_ptr_smem, (uint32_t)p.tmem_cols);
     ptx::tmem_relinquish();
+  }
+  for (int i = t; i < 256; i += 128) {  // per-channel scale/shift (arrays are padded to >= 16 entries by the host)
+    const bool ok = i < p.nsc;
+    s_sc[i] = ok ? __ldg(p.scale + i) : 0.f;
+    s_sh[i] = ok ? __ldg(p.shift + i) : 0.f;
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -234,15 +240,15 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
           float m[16], v[16];
           tmem_ld_x16(trow + n0, m);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) m[j] = m[j] * __ldg(p.scale + n0 + j) + __ldg(p.shift + n0 + j);
+          for (int j = 0; j < 16; ++j) m[j] = fmaf(m[j], s_sc[n0 + j], s_sh[n0 + j]);
           for (int pos = 1; pos < 4; ++pos) {
             tmem_ld_x16(trow + pos * np + n0, v);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) m[j] = fmaxf(m[j], v[j] * __ldg(p.scale + n0 + j) + __ldg(p.shift + n0 + j));
+            for (int j = 0; j < 16; ++j) m[j] = fmaxf(m[j], fmaf(v[j], s_sc[n0 + j], s_sh[n0 + j]));
           }
           if (p.leaky) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) m[j] = leaky01(m[j]);
+            for (int j = 0; j < 16; ++j) m[j] = fmaxf(m[j], 0.1f * m[j]);
           }
           if (valid) {
             store_group(dst, n0, m, p.N, vec_store);
@@ -267,11 +273,11 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
         for (int n = 0; n < 8; ++n) {
           m[n] = 0.f;
           if (n < np) {
-            const float sc = __ldg(p.scale + n), sh = __ldg(p.shift + n);
-            float r = v[n] * sc + sh;
+            const float sc = s_sc[n], sh = s_sh[n];
+            float r = fmaf(v[n], sc, sh);
 #pragma unroll
-            for (int pos = 1; pos < 4; ++pos) r = fmaxf(r, v[pos * np + n] * sc + sh);
-            m[n] = p.leaky ? leaky01(r) : r;
+            for (int pos = 1; pos < 4; ++pos) r = fmaxf(r, fmaf(v[pos * np + n], sc, sh));
+            m[n] = p.leaky ? fmaxf(r, 0.1f * r) : r;
           }
         }
         if (valid) store_group(dst, 0, m, p.N, vec_store);
@@ -282,8 +288,8 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
         tmem_ld_x16(trow + n0, v);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float a = v[j] * __ldg(p.scale + n0 + j) + __ldg(p.shift + n0 + j);
-          v[j] = p.leaky ? leaky01(a) : a;
+          const float a = fmaf(v[j], s_sc[n0 + j], s_sh[n0 + j]);
+          v[j] = p.leaky ? fmaxf(a, 0.1f * a) : a;
         }
         if (valid) {
           store_group(dst, n0, v, p.N, vec_store);
@@ -308,7 +314,7 @@ int launch_im2col(const CUtensorMap& tm_b, const Im2colParams& p, cudaStream_t s
   const int nb_pad = (p.nb + 15) & ~15;
   const size_t patch_bytes = FIRST ? (size_t)p.Cin * PR * PCF * 4 : (size_t)PR * PC * CL * 2;
   const size_t patch_stride = (patch_bytes + 127) & ~(size_t)127;
-  const size_t smem = (size_t)NKB * 128 * 128 + (size_t)NKB * nb_pad * 128 + 2 * patch_stride + 64 + 1024;
+  const size_t smem = (size_t)NKB * 128 * 128 + (size_t)NKB * nb_pad * 128 + 2 * patch_stride + 64 + 2048 + 1024;
   if (smem > 227 * 1024) return mc_set_error(MC_ERR_SHAPE, "mc_conv_im2col_fwd: %zu B of shared memory", smem);
 
   // input patch tensor map
@@ -406,6 +412,7 @@ extern "C" int mc_conv_im2col_fwd(const void* d_in, int in_is_nchw_f32, const vo
   p.Cin = Cin; p.Cin_ld = Cin_ld;
   p.N = N; p.npos = npos; p.nb = nb;
   p.ldc = ldc; p.leaky = leaky;
+  p.nsc = ((pool ? npos : ((N + 15) & ~15)) + 15) & ~15;  // the engine pads scale/shift to max(round_up(npos,16),16)
   p.nkb = kpad / 64;
   const int kelems = (pool ? 16 : 9) * CL;
   p.ksteps = (kelems + 15) / 16;
