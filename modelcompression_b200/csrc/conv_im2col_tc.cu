@@ -161,48 +161,67 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
     // ---- 2. build GEMM row t: NPIX patch pixels x CL channels, pixel-major, zero padded to NKB*64 elements
     {
       const int by = POOL ? 2 * wy : wy, bx = POOL ? 2 * wx : wx;
+      uint8_t* arow = a_tile + t * 128;
+      const uint32_t swz = (uint32_t)(t & 7) << 4;
+      if (FIRST && POOL && p.Cin == 3) {
+        // RGB fast path: everything at compile-time offsets from one base pointer.  Row r of the 4x4 window gives
+        // chunks 2r (pixels px 0,1) and 2r+1 (pixels px 2,3), each pixel = (c0,c1,c2,0) in bf16.
+        const float* base = reinterpret_cast<const float*>(patch_raw) + by * PCF + bx + XS;
 #pragma unroll
-      for (int q = 0; q < NKB * 8; ++q) {  // 16-byte chunk q holds K elements [8q, 8q+8)
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (q * 8 < KELEMS) {
-          if constexpr (FIRST) {
-            // two pixels per chunk, 4 bf16 each (c0,c1,c2,c3; absent channels 0); patch is fp32 [c][PR][PCF]
-            const float* pf = reinterpret_cast<const float*>(patch_raw);
-            const int pa = 2 * q, pb = 2 * q + 1;
-            float va[4] = {0.f, 0.f, 0.f, 0.f}, vb[4] = {0.f, 0.f, 0.f, 0.f};
-            if constexpr (POOL) {  // pa, pb are x-neighbours
-              const int r = pa / 4, sx = pa % 4;
+        for (int r = 0; r < 4; ++r) {
+          float v[3][4];
 #pragma unroll
-              for (int c = 0; c < 4; ++c)
-                if (c < p.Cin) {
-                  const float* src = pf + (c * PR + by + r) * PCF + bx + sx + XS;
-                  va[c] = src[0];
-                  vb[c] = src[1];
-                }
-            } else {
+          for (int c = 0; c < 3; ++c)
 #pragma unroll
-              for (int c = 0; c < 4; ++c)
-                if (c < p.Cin) {
-                  va[c] = pf[(c * PR + by + pa / 3) * PCF + bx + pa % 3 + XS];
-                  if (pb < NPIX) vb[c] = pf[(c * PR + by + pb / 3) * PCF + bx + pb % 3 + XS];
-                }
-            }
-            __nv_bfloat162 a0 = __floats2bfloat162_rn(va[0], va[1]), a1 = __floats2bfloat162_rn(va[2], va[3]);
-            __nv_bfloat162 b0 = __floats2bfloat162_rn(vb[0], vb[1]), b1 = __floats2bfloat162_rn(vb[2], vb[3]);
+            for (int sx = 0; sx < 4; ++sx) v[c][sx] = base[(c * PR + r) * PCF + sx];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            __nv_bfloat162 a0 = __floats2bfloat162_rn(v[0][2 * h], v[1][2 * h]);
+            __nv_bfloat162 a1 = __floats2bfloat162_rn(v[2][2 * h], 0.f);
+            __nv_bfloat162 b0 = __floats2bfloat162_rn(v[0][2 * h + 1], v[1][2 * h + 1]);
+            __nv_bfloat162 b1 = __floats2bfloat162_rn(v[2][2 * h + 1], 0.f);
+            uint4 val;
             val.x = *reinterpret_cast<uint32_t*>(&a0);
             val.y = *reinterpret_cast<uint32_t*>(&a1);
             val.z = *reinterpret_cast<uint32_t*>(&b0);
             val.w = *reinterpret_cast<uint32_t*>(&b1);
-          } else {
-            const __nv_bfloat16* patch = reinterpret_cast<const __nv_bfloat16*>(patch_raw);
-            constexpr int V = CL / 8;
-            const int pix = q / V, v = q % V;
-            const int r = POOL ? pix / 4 : pix / 3, sx = POOL ? pix % 4 : pix % 3;
-            val = *reinterpret_cast<const uint4*>(patch + ((by + r) * PC + bx + sx) * CL + v * 8);
+            *reinterpret_cast<uint4*>(arow + ((uint32_t)((2 * r + h) << 4) ^ swz)) = val;
           }
         }
-        const int kb = q >> 3, j = q & 7;
-        *reinterpret_cast<uint4*>(a_tile + (size_t)kb * (128 * 128) + t * 128 + ((j ^ (t & 7)) << 4)) = val;
+      } else {
+#pragma unroll
+        for (int q = 0; q < NKB * 8; ++q) {  // 16-byte chunk q holds K elements [8q, 8q+8)
+          uint4 val = make_uint4(0, 0, 0, 0);
+          if (q * 8 < KELEMS) {
+            if constexpr (FIRST) {
+              // two pixels per chunk, 4 bf16 each (c0,c1,c2,c3; absent channels 0); patch is fp32 [c][PR][PCF]
+              const float* pf = reinterpret_cast<const float*>(patch_raw);
+              const int pa = 2 * q, pb = 2 * q + 1;
+              float va[4] = {0.f, 0.f, 0.f, 0.f}, vb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                if (c < p.Cin) {
+                  va[c] = pf[(c * PR + by + (POOL ? pa / 4 : pa / 3)) * PCF + bx + (POOL ? pa % 4 : pa % 3) + XS];
+                  if (pb < NPIX)
+                    vb[c] = pf[(c * PR + by + (POOL ? pb / 4 : pb / 3)) * PCF + bx + (POOL ? pb % 4 : pb % 3) + XS];
+                }
+              __nv_bfloat162 a0 = __floats2bfloat162_rn(va[0], va[1]), a1 = __floats2bfloat162_rn(va[2], va[3]);
+              __nv_bfloat162 b0 = __floats2bfloat162_rn(vb[0], vb[1]), b1 = __floats2bfloat162_rn(vb[2], vb[3]);
+              val.x = *reinterpret_cast<uint32_t*>(&a0);
+              val.y = *reinterpret_cast<uint32_t*>(&a1);
+              val.z = *reinterpret_cast<uint32_t*>(&b0);
+              val.w = *reinterpret_cast<uint32_t*>(&b1);
+            } else {
+              const __nv_bfloat16* patch = reinterpret_cast<const __nv_bfloat16*>(patch_raw);
+              constexpr int V = CL / 8;
+              const int pix = q / V, v = q % V;
+              const int r = POOL ? pix / 4 : pix / 3, sx = POOL ? pix % 4 : pix % 3;
+              val = *reinterpret_cast<const uint4*>(patch + ((by + r) * PC + bx + sx) * CL + v * 8);
+            }
+          }
+          const int kb = q >> 3, j = q & 7;
+          *reinterpret_cast<uint4*>(arow + (size_t)kb * (128 * 128) + ((uint32_t)(j << 4) ^ swz)) = val;
+        }
       }
     }
     ptx::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)

@@ -40,14 +40,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+  // suspend-time hint (ns): the thread sleeps in hardware until the phase completes or the hint expires, instead of
+  // burning issue slots in a polling loop
   asm volatile(
       "{\n\t"
       ".reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, P;\n\t"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(10000u)
       : "memory");
   return ok != 0;
 }
@@ -57,12 +59,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsign
                                           unsigned int dbg_code = 0) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) {
+    if (++spins > (1u << 16)) {
       if (dbg_flag != nullptr) {
         atomicCAS(dbg_flag, 0u, dbg_code);
         return;
       }
-      if (spins > (1u << 26)) __trap();
+      if (spins > (1u << 18)) __trap();
     }
   }
 }
