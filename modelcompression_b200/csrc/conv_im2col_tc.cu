@@ -64,8 +64,46 @@ __device__ __forceinline__ void store_group(__nv_bfloat16* dst, int n0, const fl
   }
 }
 
+// ---- epilogue helpers -------------------------------------------------------------------------------------------
+// pooled, NP (per-position column stride) = 4 or 8: all four window positions sit in one or two 16-column loads
+template <int NP>
+__device__ __forceinline__ void epilogue_pool_small(uint32_t trow, const float* s_sc, const float* s_sh, int leaky,
+                                                    bool valid, __nv_bfloat16* dst, int N, bool vec_store) {
+  float v[4 * NP];
+  {
+    float a[16];
+    tmem_ld_x16(trow, a);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = a[j];
+    if (NP == 8) {
+      tmem_ld_x16(trow + 16, a);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[(16 + j) % (4 * NP)] = a[j];
+    }
+  }
+  float m[8];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    m[n] = 0.f;
+    if (n < NP) {
+      const float sc = s_sc[n], sh = s_sh[n];
+      float r = fmaf(v[n], sc, sh);
+#pragma unroll
+      for (int pos = 1; pos < 4; ++pos) r = fmaxf(r, fmaf(v[pos * NP + n], sc, sh));
+      m[n] = leaky ? fmaxf(r, 0.1f * r) : r;
+    }
+  }
+  if (valid) store_group(dst, 0, m, N, vec_store);
+}
+
+// CTA = 256 threads.  Warps 0-3 ("builders"): thread t builds GEMM row t of the im2col tile from the TMA-staged input
+// patch, thread 0 additionally issues the patch TMA and the MMAs.  Warps 4-7: epilogue (TMEM lane quarter = warp%4).
+// Everything is double-buffered on the tile parity (patch, A tile, TMEM accumulator), so the build of tile i+1
+// overlaps the MMA + epilogue of tile i:
+//   patch_full[2]  TMA -> builders          a_free[2]    tcgen05.commit -> builders (MMA has consumed A[s])
+//   tmem_full[2]   tcgen05.commit -> epilogue   tmem_free[2] epilogue warps (4 arrivals) -> MMA issuer
 template <int CL, bool POOL, bool FIRST>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(256, 2)
 conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_in,
                       const Im2colParams p) {
   constexpr int PR = POOL ? 2 * TY + 2 : TY + 2;   // patch rows / cols (conv pixels incl. halo)
@@ -74,26 +112,28 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
   constexpr int KELEMS = NPIX * CL;
   constexpr int NKB = (KELEMS + 63) / 64;
   constexpr int A_BYTES = NKB * 128 * 128;
+  // FIRST: fp32 patch [Cin][PR][PCF]; TMA needs a 16-byte aligned innermost start, so the box begins XS = 3 columns
+  // left of the halo column (x0-4 instead of x0-1) and PCF = round_up(PC + 3, 4).  Else bf16 patch [PR][PC][CL].
+  constexpr int XS = 3;
+  constexpr int PCF = (PC + XS + 3) & ~3;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   smem += (1024u - (ptx::smem_u32(smem) & 1023u)) & 1023u;
-  uint8_t* a_tile = smem;                                   // [NKB][128 rows][128 B], 128B swizzle
-  uint8_t* b_tile = a_tile + A_BYTES;                       // [NKB][nb_pad rows][128 B]
+  uint8_t* a_tile = smem;                                   // [2][NKB][128 rows][128 B], 128B swizzle
+  uint8_t* b_tile = a_tile + 2 * A_BYTES;                   // [NKB][nb_pad rows][128 B]
   const int nb_pad = (p.nb + 15) & ~15;
-  // input patch, double-buffered, filled by TMA (out-of-image elements arrive as zeros):
-  //   FIRST: fp32 [Cin][PR][PCF]; TMA needs a 16-byte aligned innermost start, so the box begins XS = 3 columns left
-  //   of the halo column (x0-4 instead of x0-1) and PCF = round_up(PC + 3, 4); else bf16 [PR][PC][CL]
-  constexpr int XS = 3;
-  constexpr int PCF = (PC + XS + 3) & ~3;
   const uint32_t patch_bytes = FIRST ? (uint32_t)(p.Cin * PR * PCF * 4) : (uint32_t)(PR * PC * CL * 2);
   const uint32_t patch_stride = (patch_bytes + 127u) & ~127u;
   uint8_t* patch0 = b_tile + (size_t)NKB * nb_pad * 128;  // 1024-aligned
-  uint64_t* b_bar = reinterpret_cast<uint64_t*>(patch0 + 2 * patch_stride);
-  uint64_t* mma_bar = b_bar + 1;
-  uint64_t* patch_bar = mma_bar + 1;  // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(patch_bar + 2);
-  float* s_sc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(b_bar) + 64);  // [256] scale, [256] shift
+  uint64_t* bars = reinterpret_cast<uint64_t*>(patch0 + 2 * patch_stride);
+  uint64_t* b_bar = bars;            // weights landed
+  uint64_t* patch_full = bars + 1;   // [2]
+  uint64_t* a_free = bars + 3;       // [2]
+  uint64_t* tmem_full = bars + 5;    // [2]
+  uint64_t* tmem_free = bars + 7;    // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 9);
+  float* s_sc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);  // [256] scale, [256] shift
   float* s_sh = s_sc + 256;
 
   const int t = threadIdx.x;
@@ -102,16 +142,19 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
     ptx::prefetch_tensormap(&tmap_b);
     ptx::prefetch_tensormap(&tmap_in);
     ptx::mbar_init(b_bar, 1);
-    ptx::mbar_init(mma_bar, 1);
-    ptx::mbar_init(&patch_bar[0], 1);
-    ptx::mbar_init(&patch_bar[1], 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&patch_full[i], 1);
+      ptx::mbar_init(&a_free[i], 1);
+      ptx::mbar_init(&tmem_full[i], 1);
+      ptx::mbar_init(&tmem_free[i], 4);
+    }
     ptx::fence_barrier_init();
   }
   if (warp_idx == 0) {
     ptx::tmem_alloc(tmem_ptr_smem, (uint32_t)p.tmem_cols);
     ptx::tmem_relinquish();
   }
-  for (int i = t; i < 256; i += 128) {  // per-channel scale/shift (arrays are padded to >= 16 entries by the host)
+  for (int i = t; i < 256; i += 256) {  // per-channel scale/shift (arrays are padded to >= 16 entries by the host)
     const bool ok = i < p.nsc;
     s_sc[i] = ok ? __ldg(p.scale + i) : 0.f;
     s_sh[i] = ok ? __ldg(p.shift + i) : 0.f;
@@ -120,52 +163,44 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-
-  if (t == 0) {  // expanded weights: loaded once per CTA
-    ptx::mbar_arrive_expect_tx(b_bar, (uint32_t)(NKB * nb_pad * 128));
-    for (int kb = 0; kb < NKB; ++kb) ptx::tma_load_2d(b_tile + (size_t)kb * nb_pad * 128, &tmap_b, b_bar, kb * 64, 0);
-  }
-
-  const int wy = t / TX, wx = t % TX;
+  const uint32_t acc_stride = (uint32_t)((nb_pad + 31) & ~31);  // TMEM columns between the two accumulator stages
+  const unsigned int tiles_xy = (unsigned)(p.tiles_x * p.tiles_y);
   const int Hout = POOL ? p.H / 2 : p.H, Wout = POOL ? p.W / 2 : p.W;
-  const bool vec_store = (p.ldc & 7) == 0;
-  uint32_t mma_phase = 0;
-  bool b_ready = false;
 
-  // one thread asks TMA for the patch of `tile` into buffer `buf`
-  auto issue_patch = [&](int tile, int buf) {
-    const int tx = tile % p.tiles_x;
-    const int ty = (tile / p.tiles_x) % p.tiles_y;
-    const int b = tile / (p.tiles_x * p.tiles_y);
-    const int iy0 = (POOL ? 2 * ty * TY : ty * TY) - 1, ix0 = (POOL ? 2 * tx * TX : tx * TX) - 1;
-    ptx::mbar_arrive_expect_tx(&patch_bar[buf], patch_bytes);
-    if constexpr (FIRST) ptx::tma_load_4d(patch0 + buf * patch_stride, &tmap_in, &patch_bar[buf], ix0 - XS, iy0, 0, b);
-    else ptx::tma_load_3d(patch0 + buf * patch_stride, &tmap_in, &patch_bar[buf], 0, ix0, b * (p.H + 1) + iy0);
-  };
-
-  if (t == 0 && (int)blockIdx.x < p.total_tiles) issue_patch(blockIdx.x, 0);
-  int it = 0;
-  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-    const int tx = tile % p.tiles_x;
-    const int ty = (tile / p.tiles_x) % p.tiles_y;
-    const int b = tile / (p.tiles_x * p.tiles_y);
-    const int oy0 = ty * TY, ox0 = tx * TX;  // first output row/col of the tile
-    const int buf = it & 1;
-
-    // ---- 1. prefetch the next tile's patch (its buffer was last read two tiles ago, behind a __syncthreads), then
-    //         wait for this tile's patch
-    if (t == 0 && tile + (int)gridDim.x < p.total_tiles) issue_patch(tile + gridDim.x, buf ^ 1);
-    ptx::mbar_wait(&patch_bar[buf], (uint32_t)((it >> 1) & 1), &g_im2col_dbg, 0x100u + (unsigned)it);
-    const uint8_t* patch_raw = patch0 + buf * patch_stride;
-
-    // ---- 2. build GEMM row t: NPIX patch pixels x CL channels, pixel-major, zero padded to NKB*64 elements
-    {
-      const int by = POOL ? 2 * wy : wy, bx = POOL ? 2 * wx : wx;
-      uint8_t* arow = a_tile + t * 128;
-      const uint32_t swz = (uint32_t)(t & 7) << 4;
+  if (warp_idx < 4) {
+    // ============================== builders (+ TMA / MMA issue by thread 0) ==============================
+    auto issue_patch = [&](unsigned int tile, int buf) {
+      const unsigned int b = tile / tiles_xy, rem = tile - b * tiles_xy;
+      const unsigned int ty = rem / (unsigned)p.tiles_x, tx = rem - ty * (unsigned)p.tiles_x;
+      const int iy0 = (int)(POOL ? 2 * ty * TY : ty * TY) - 1, ix0 = (int)(POOL ? 2 * tx * TX : tx * TX) - 1;
+      ptx::mbar_arrive_expect_tx(&patch_full[buf], patch_bytes);
+      if constexpr (FIRST)
+        ptx::tma_load_4d(patch0 + buf * patch_stride, &tmap_in, &patch_full[buf], ix0 - XS, iy0, 0, (int)b);
+      else
+        ptx::tma_load_3d(patch0 + buf * patch_stride, &tmap_in, &patch_full[buf], 0, ix0, (int)b * (p.H + 1) + iy0);
+    };
+    if (t == 0) {
+      ptx::mbar_arrive_expect_tx(b_bar, (uint32_t)(NKB * nb_pad * 128));  // expanded weights: once per CTA
+      for (int kb = 0; kb < NKB; ++kb)
+        ptx::tma_load_2d(b_tile + (size_t)kb * nb_pad * 128, &tmap_b, b_bar, kb * 64, 0);
+      unsigned int tl = blockIdx.x;
+      for (int i = 0; i < 2 && tl < (unsigned)p.total_tiles; ++i, tl += gridDim.x) issue_patch(tl, i);
+    }
+    const int wy = t / TX, wx = t % TX;
+    const int by = POOL ? 2 * wy : wy, bx = POOL ? 2 * wx : wx;
+    const uint32_t swz = (uint32_t)(t & 7) << 4;
+    bool b_ready = false;
+    int it = 0;
+    for (unsigned int tile = blockIdx.x; tile < (unsigned)p.total_tiles; tile += gridDim.x, ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (uint32_t)((it >> 1) & 1);
+      ptx::mbar_wait(&a_free[s], ph ^ 1u, &g_im2col_dbg, 0x400u + (unsigned)it);   // MMA of tile it-2 has read A[s]
+      ptx::mbar_wait(&patch_full[s], ph, &g_im2col_dbg, 0x100u + (unsigned)it);
+      const uint8_t* patch_raw = patch0 + s * patch_stride;
+      uint8_t* arow = a_tile + (size_t)s * A_BYTES + t * 128;
       if (FIRST && POOL && p.Cin == 3) {
-        // RGB fast path: everything at compile-time offsets from one base pointer.  Row r of the 4x4 window gives
-        // chunks 2r (pixels px 0,1) and 2r+1 (pixels px 2,3), each pixel = (c0,c1,c2,0) in bf16.
+        // RGB fast path: compile-time offsets from one base pointer.  Row r of the 4x4 window gives chunks 2r
+        // (pixels px 0,1) and 2r+1 (pixels px 2,3), each pixel = (c0,c1,c2,0) in bf16.
         const float* base = reinterpret_cast<const float*>(patch_raw) + by * PCF + bx + XS;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
@@ -223,100 +258,95 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
           *reinterpret_cast<uint4*>(arow + (size_t)kb * (128 * 128) + ((uint32_t)(j << 4) ^ swz)) = val;
         }
       }
-    }
-    ptx::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-    ptx::tc_fence_before();
-    __syncthreads();
+      ptx::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // all 128 rows of A[s] written; patch[s] fully consumed
 
-    // ---- 3. MMA (one thread)
-    if (t == 0) {
-      if (!b_ready) ptx::mbar_wait(b_bar, 0, &g_im2col_dbg, 0x200u);
-      ptx::tc_fence_after();
-      const uint32_t a_addr = ptx::smem_u32(a_tile), b_addr = ptx::smem_u32(b_tile);
-      for (int ks = 0; ks < p.ksteps; ++ks) {
-        const int kb = ks >> 2, k = ks & 3;
-        const uint64_t adesc = ptx::make_sw128_kmajor_desc(a_addr + kb * (128 * 128)) + (uint64_t)(2 * k);
-        const uint64_t bdesc = ptx::make_sw128_kmajor_desc(b_addr + kb * (nb_pad * 128)) + (uint64_t)(2 * k);
-        ptx::umma_bf16_ss(tmem_base, adesc, bdesc, p.idesc, ks > 0 ? 1u : 0u);
+      if (t == 0) {
+        // patch[s] is free again: fetch the patch of tile it+2
+        const unsigned int nxt = tile + 2u * gridDim.x;
+        if (nxt < (unsigned)p.total_tiles) issue_patch(nxt, s);
+        if (!b_ready) ptx::mbar_wait(b_bar, 0, &g_im2col_dbg, 0x200u);
+        b_ready = true;
+        ptx::mbar_wait(&tmem_free[s], ph ^ 1u, &g_im2col_dbg, 0x500u + (unsigned)it);  // epilogue drained TMEM[s]
+        ptx::tc_fence_after();
+        const uint32_t a_addr = ptx::smem_u32(a_tile + (size_t)s * A_BYTES), b_addr = ptx::smem_u32(b_tile);
+        const uint32_t tacc = tmem_base + (uint32_t)s * acc_stride;
+        for (int ks = 0; ks < p.ksteps; ++ks) {
+          const int kb = ks >> 2, k = ks & 3;
+          const uint64_t adesc = ptx::make_sw128_kmajor_desc(a_addr + kb * (128 * 128)) + (uint64_t)(2 * k);
+          const uint64_t bdesc = ptx::make_sw128_kmajor_desc(b_addr + kb * (nb_pad * 128)) + (uint64_t)(2 * k);
+          ptx::umma_bf16_ss(tacc, adesc, bdesc, p.idesc, ks > 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&a_free[s]);     // A[s] may be rebuilt once these MMAs retire
+        ptx::umma_commit(&tmem_full[s]);  // accumulator ready for the epilogue warps
       }
-      ptx::umma_commit(mma_bar);
     }
-    b_ready = true;
-
-    // ---- 4. epilogue: TMEM lane t -> scale/shift (-> max over the 4 window positions) -> leaky -> bf16 store
-    ptx::mbar_wait(mma_bar, mma_phase, &g_im2col_dbg, 0x300u + (unsigned)it);
-    mma_phase ^= 1u;
-    ptx::tc_fence_after();
-    const int oy = oy0 + wy, ox = ox0 + wx;
-    const bool valid = oy < Hout && ox < Wout;
-    __nv_bfloat16* dst =
-        reinterpret_cast<__nv_bfloat16*>(p.out) + (((long long)b * (Hout + 1) + oy) * (Wout + 1) + ox) * p.ldc;
-    const uint32_t trow = tmem_base + ((uint32_t)(warp_idx * 32) << 16);
-    if (POOL) {
-      const int np = p.npos;
-      if (np % 16 == 0) {
-        for (int n0 = 0; n0 < np; n0 += 16) {
-          float m[16], v[16];
-          tmem_ld_x16(trow + n0, m);
+  } else {
+    // ============================== epilogue warps 4..7 ==============================
+    const int et = t - 128;                 // TMEM lane == GEMM row
+    const int quarter = warp_idx & 3;
+    const int lane = t & 31;
+    const int wy = et / TX, wx = et % TX;
+    const bool vec_store = (p.ldc & 7) == 0;
+    int it = 0;
+    for (unsigned int tile = blockIdx.x; tile < (unsigned)p.total_tiles; tile += gridDim.x, ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (uint32_t)((it >> 1) & 1);
+      const unsigned int b = tile / tiles_xy, rem = tile - b * tiles_xy;
+      const unsigned int ty = rem / (unsigned)p.tiles_x, tx = rem - ty * (unsigned)p.tiles_x;
+      const int oy = (int)ty * TY + wy, ox = (int)tx * TX + wx;
+      const bool valid = oy < Hout && ox < Wout;
+      __nv_bfloat16* dst =
+          reinterpret_cast<__nv_bfloat16*>(p.out) + (((long long)b * (Hout + 1) + oy) * (Wout + 1) + ox) * p.ldc;
+      ptx::mbar_wait(&tmem_full[s], ph, &g_im2col_dbg, 0x300u + (unsigned)it);
+      ptx::tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)s * acc_stride;
+      if (POOL) {
+        const int np = p.npos;
+        if (np == 4) {
+          epilogue_pool_small<4>(trow, s_sc, s_sh, p.leaky, valid, dst, p.N, vec_store);
+        } else if (np == 8) {
+          epilogue_pool_small<8>(trow, s_sc, s_sh, p.leaky, valid, dst, p.N, vec_store);
+        } else {
+          for (int n0 = 0; n0 < np; n0 += 16) {
+            float m[16], v[16];
+            tmem_ld_x16(trow + n0, m);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) m[j] = fmaf(m[j], s_sc[n0 + j], s_sh[n0 + j]);
-          for (int pos = 1; pos < 4; ++pos) {
-            tmem_ld_x16(trow + pos * np + n0, v);
+            for (int j = 0; j < 16; ++j) m[j] = fmaf(m[j], s_sc[n0 + j], s_sh[n0 + j]);
+            for (int pos = 1; pos < 4; ++pos) {
+              tmem_ld_x16(trow + pos * np + n0, v);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) m[j] = fmaxf(m[j], fmaf(v[j], s_sc[n0 + j], s_sh[n0 + j]));
+              for (int j = 0; j < 16; ++j) m[j] = fmaxf(m[j], fmaf(v[j], s_sc[n0 + j], s_sh[n0 + j]));
+            }
+            if (p.leaky) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) m[j] = fmaxf(m[j], 0.1f * m[j]);
+            }
+            if (valid) {
+              store_group(dst, n0, m, p.N, vec_store);
+              store_group(dst, n0 + 8, m + 8, p.N, vec_store);
+            }
           }
-          if (p.leaky) {
+        }
+      } else {
+        for (int n0 = 0; n0 < p.nb; n0 += 16) {
+          float v[16];
+          tmem_ld_x16(trow + n0, v);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) m[j] = fmaxf(m[j], 0.1f * m[j]);
+          for (int j = 0; j < 16; ++j) {
+            const float a = fmaf(v[j], s_sc[n0 + j], s_sh[n0 + j]);
+            v[j] = p.leaky ? fmaxf(a, 0.1f * a) : a;
           }
           if (valid) {
-            store_group(dst, n0, m, p.N, vec_store);
-            store_group(dst, n0 + 8, m + 8, p.N, vec_store);
+            store_group(dst, n0, v, p.N, vec_store);
+            store_group(dst, n0 + 8, v + 8, p.N, vec_store);
           }
-        }
-      } else {  // np == 4 or 8: the four positions sit in one or two 16-column loads
-        float v[32];
-        {
-          float a[16];
-          tmem_ld_x16(trow, a);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = a[j];
-          if (np == 8) {
-            tmem_ld_x16(trow + 16, a);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[16 + j] = a[j];
-          }
-        }
-        float m[8];
-#pragma unroll
-        for (int n = 0; n < 8; ++n) {
-          m[n] = 0.f;
-          if (n < np) {
-            const float sc = s_sc[n], sh = s_sh[n];
-            float r = fmaf(v[n], sc, sh);
-#pragma unroll
-            for (int pos = 1; pos < 4; ++pos) r = fmaxf(r, fmaf(v[pos * np + n], sc, sh));
-            m[n] = p.leaky ? fmaxf(r, 0.1f * r) : r;
-          }
-        }
-        if (valid) store_group(dst, 0, m, p.N, vec_store);
-      }
-    } else {
-      for (int n0 = 0; n0 < p.nb; n0 += 16) {
-        float v[16];
-        tmem_ld_x16(trow + n0, v);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float a = fmaf(v[j], s_sc[n0 + j], s_sh[n0 + j]);
-          v[j] = p.leaky ? fmaxf(a, 0.1f * a) : a;
-        }
-        if (valid) {
-          store_group(dst, n0, v, p.N, vec_store);
-          store_group(dst, n0 + 8, v + 8, p.N, vec_store);
         }
       }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_free[s]);  // this warp has drained TMEM[s]
     }
-    ptx::tc_fence_before();  // TMEM reads done before the next tile's MMA (ordered by the next __syncthreads)
   }
 
   ptx::tc_fence_before();
@@ -333,7 +363,7 @@ int launch_im2col(const CUtensorMap& tm_b, const Im2colParams& p, cudaStream_t s
   const int nb_pad = (p.nb + 15) & ~15;
   const size_t patch_bytes = FIRST ? (size_t)p.Cin * PR * PCF * 4 : (size_t)PR * PC * CL * 2;
   const size_t patch_stride = (patch_bytes + 127) & ~(size_t)127;
-  const size_t smem = (size_t)NKB * 128 * 128 + (size_t)NKB * nb_pad * 128 + 2 * patch_stride + 64 + 2048 + 1024;
+  const size_t smem = 2 * (size_t)NKB * 128 * 128 + (size_t)NKB * nb_pad * 128 + 2 * patch_stride + 128 + 2048 + 1024;
   if (smem > 227 * 1024) return mc_set_error(MC_ERR_SHAPE, "mc_conv_im2col_fwd: %zu B of shared memory", smem);
 
   // input patch tensor map
@@ -362,13 +392,24 @@ int launch_im2col(const CUtensorMap& tm_b, const Im2colParams& p, cudaStream_t s
   int per_sm = (int)((200 * 1024) / smem);
   const int tmem_lim = 512 / p.tmem_cols;
   if (per_sm > tmem_lim) per_sm = tmem_lim;
-  if (per_sm > 8) per_sm = 8;
+  if (per_sm > 4) per_sm = 4;
   if (per_sm < 1) per_sm = 1;
   long long grid = (long long)mc_num_sms() * per_sm;
   if (grid > p.total_tiles) grid = p.total_tiles;
-  kern<<<(int)grid, 128, smem, stream>>>(tm_b, tm_in, p);
+  kern<<<(int)grid, 256, smem, stream>>>(tm_b, tm_in, p);
   MC_LAUNCH_CHECK("conv_im2col_tc_kernel");
   return 0;
+}
+
+
+// shared-memory bytes conv_im2col_tc_kernel needs for a geometry (mirrors the kernel's carve-up)
+static size_t im2col_smem_bytes(int CL, int pool, int first, int nb_pad, int Cin) {
+  const int PR = pool ? 2 * TY + 2 : TY + 2, PC = pool ? 2 * TX + 2 : TX + 2;
+  const int PCF = (PC + 3 + 3) & ~3;
+  const int NKB = ((pool ? 16 : 9) * CL + 63) / 64;
+  const size_t patch_bytes = first ? (size_t)Cin * PR * PCF * 4 : (size_t)PR * PC * CL * 2;
+  const size_t patch_stride = (patch_bytes + 127) & ~(size_t)127;
+  return 2 * (size_t)NKB * 128 * 128 + (size_t)NKB * nb_pad * 128 + 2 * patch_stride + 128 + 2048 + 1024;
 }
 
 }  // namespace
@@ -392,7 +433,9 @@ extern "C" int mc_conv_im2col_supported(int Cin, int in_is_nchw_f32, int N, int 
   }
   const int npos = pool ? ((N <= 4) ? 4 : (N <= 8) ? 8 : ((N + 15) & ~15)) : ((N + 15) & ~15);
   const int nb = pool ? 4 * npos : npos;
-  return nb <= 256 ? 1 : 0;
+  if (nb > 256) return 0;
+  const int CL = in_is_nchw_f32 ? 4 : (Cin <= 8 ? 8 : 16);
+  return im2col_smem_bytes(CL, pool, in_is_nchw_f32, (nb + 15) & ~15, Cin) <= 200 * 1024 ? 1 : 0;
 }
 
 extern "C" int mc_conv_im2col_geometry(int Cin, int in_is_nchw_f32, int N, int pool, int* cl, int* npos, int* nb,
@@ -439,10 +482,10 @@ extern "C" int mc_conv_im2col_fwd(const void* d_in, int in_is_nchw_f32, const vo
   p.tiles_x = (Wout + TX - 1) / TX;
   p.tiles_y = (Hout + TY - 1) / TY;
   p.total_tiles = B * p.tiles_x * p.tiles_y;
-  int tc = 32;
-  while (tc < nb) tc <<= 1;
-  p.tmem_cols = tc;
   const int nb_pad = (nb + 15) & ~15;
+  int tc = 32;
+  while (tc < 2 * ((nb_pad + 31) & ~31)) tc <<= 1;
+  p.tmem_cols = tc;  // two accumulator stages
   p.nb = nb_pad;  // UMMA N must be a multiple of 16; padded columns are zero rows of d_wexp
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nb_pad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
