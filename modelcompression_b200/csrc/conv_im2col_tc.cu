@@ -50,12 +50,15 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float (&v)[16]) {
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
 }
 
-// store `cnt` (<=8) bf16 values starting at channel n0 of dst row
-__device__ __forceinline__ void store_group(__nv_bfloat16* dst, int n0, const float* v, int N, bool vec) {
-  if (vec && n0 + 8 <= N) {
+// store 8 bf16 values at channels [n0, n0+8) of a destination row.  Channels >= N are the row's zero padding: when the
+// 8-group fits inside the pitch it is written as ONE 16-byte store with zeros there (whole-sector, coalesced writes);
+// scalar stores only when the pitch is not a multiple of 8.
+__device__ __forceinline__ void store_group(__nv_bfloat16* dst, int n0, const float* v, int N, int ldc, bool vec) {
+  if (n0 >= N) return;
+  if (vec && n0 + 8 <= ldc) {
     __align__(16) __nv_bfloat16 h[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) h[j] = __float2bfloat16_rn(v[j]);
+    for (int j = 0; j < 8; ++j) h[j] = __float2bfloat16_rn(n0 + j < N ? v[j] : 0.f);
     *reinterpret_cast<uint4*>(dst + n0) = *reinterpret_cast<const uint4*>(h);
   } else {
 #pragma unroll
@@ -68,7 +71,7 @@ __device__ __forceinline__ void store_group(__nv_bfloat16* dst, int n0, const fl
 // pooled, NP (per-position column stride) = 4 or 8: all four window positions sit in one or two 16-column loads
 template <int NP>
 __device__ __forceinline__ void epilogue_pool_small(uint32_t trow, const float* s_sc, const float* s_sh, int leaky,
-                                                    bool valid, __nv_bfloat16* dst, int N, bool vec_store) {
+                                                    bool valid, __nv_bfloat16* dst, int N, int ldc, bool vec_store) {
   float v[4 * NP];
   {
     float a[16];
@@ -93,7 +96,7 @@ __device__ __forceinline__ void epilogue_pool_small(uint32_t trow, const float* 
       m[n] = leaky ? fmaxf(r, 0.1f * r) : r;
     }
   }
-  if (valid) store_group(dst, 0, m, N, vec_store);
+  if (valid) store_group(dst, 0, m, N, ldc, vec_store);
 }
 
 // CTA = 256 threads.  Warps 0-3 ("builders"): thread t builds GEMM row t of the im2col tile from the TMA-staged input
@@ -304,9 +307,9 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
       if (POOL) {
         const int np = p.npos;
         if (np == 4) {
-          epilogue_pool_small<4>(trow, s_sc, s_sh, p.leaky, valid, dst, p.N, vec_store);
+          epilogue_pool_small<4>(trow, s_sc, s_sh, p.leaky, valid, dst, p.N, p.ldc, vec_store);
         } else if (np == 8) {
-          epilogue_pool_small<8>(trow, s_sc, s_sh, p.leaky, valid, dst, p.N, vec_store);
+          epilogue_pool_small<8>(trow, s_sc, s_sh, p.leaky, valid, dst, p.N, p.ldc, vec_store);
         } else {
           for (int n0 = 0; n0 < np; n0 += 16) {
             float m[16], v[16];
@@ -323,8 +326,8 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
               for (int j = 0; j < 16; ++j) m[j] = fmaxf(m[j], 0.1f * m[j]);
             }
             if (valid) {
-              store_group(dst, n0, m, p.N, vec_store);
-              store_group(dst, n0 + 8, m + 8, p.N, vec_store);
+              store_group(dst, n0, m, p.N, p.ldc, vec_store);
+              store_group(dst, n0 + 8, m + 8, p.N, p.ldc, vec_store);
             }
           }
         }
@@ -338,8 +341,8 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
             v[j] = p.leaky ? fmaxf(a, 0.1f * a) : a;
           }
           if (valid) {
-            store_group(dst, n0, v, p.N, vec_store);
-            store_group(dst, n0 + 8, v + 8, p.N, vec_store);
+            store_group(dst, n0, v, p.N, p.ldc, vec_store);
+            store_group(dst, n0 + 8, v + 8, p.N, p.ldc, vec_store);
           }
         }
       }

@@ -76,11 +76,18 @@ __device__ __forceinline__ void store16(const ConvKParams& p, const float (&v)[1
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
       const int n = nbase + g * 8;
-      if (vec_ok && n + 8 <= p.N) {
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[g * 8 + 0], v[g * 8 + 1]);
-        __nv_bfloat162 h1 = __floats2bfloat162_rn(v[g * 8 + 2], v[g * 8 + 3]);
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[g * 8 + 4], v[g * 8 + 5]);
-        __nv_bfloat162 h3 = __floats2bfloat162_rn(v[g * 8 + 6], v[g * 8 + 7]);
+      if (n >= p.N) continue;
+      // channels >= N of a PNHWC row are zero padding up to the pitch: a partial 8-group is still written as one
+      // 16-byte store (zeros there) when it fits inside the pitch
+      const bool full = n + 8 <= p.N;
+      if (vec_ok && (full || (MODE == MC_EPI_PNHWC && p.ch_off + n + 8 <= p.ldc))) {
+        float w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = (full || n + j < p.N) ? v[g * 8 + j] : 0.f;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(w[0], w[1]);
+        __nv_bfloat162 h1 = __floats2bfloat162_rn(w[2], w[3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(w[4], w[5]);
+        __nv_bfloat162 h3 = __floats2bfloat162_rn(w[6], w[7]);
         uint4 pk;
         pk.x = *reinterpret_cast<uint32_t*>(&h0);
         pk.y = *reinterpret_cast<uint32_t*>(&h1);
