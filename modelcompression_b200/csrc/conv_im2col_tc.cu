@@ -377,12 +377,15 @@ int launch_im2col(const CUtensorMap& tm_b, const Im2colParams& p, cudaStream_t s
     const uint64_t strides[3] = {(uint64_t)p.W * 4, (uint64_t)p.W * p.H * 4, (uint64_t)p.W * p.H * p.Cin * 4};
     const uint32_t box[4] = {(uint32_t)PCF, (uint32_t)PR, (uint32_t)p.Cin, 1};
     if ((p.W * 4) % 16 != 0) return mc_set_error(MC_ERR_SHAPE, "mc_conv_im2col_fwd: image width must be a multiple of 4");
-    rc = mc_make_tmap(&tm_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    // short (160-byte) misaligned rows: 128 B promotion halves the L2->SM over-fetch of the default 256 B
+    rc = mc_make_tmap(&tm_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
   } else {      // bf16 PNHWC viewed as [B*(H+1)][W+1][CL], box [PR][PC][CL]
     const uint64_t dims[3] = {(uint64_t)CL, (uint64_t)(p.W + 1), (uint64_t)p.B * (p.H + 1)};
     const uint64_t strides[2] = {(uint64_t)CL * 2, (uint64_t)(p.W + 1) * CL * 2};
     const uint32_t box[3] = {(uint32_t)CL, (uint32_t)PC, (uint32_t)PR};
-    rc = mc_make_tmap(&tm_in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, p.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    rc = mc_make_tmap(&tm_in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, p.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
   }
   if (rc) return rc;
 

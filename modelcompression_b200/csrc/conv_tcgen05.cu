@@ -301,15 +301,17 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 // tcgen05 issue floor (128*bn*64 MACs at 4096 MAC/clk), 128+bn is the shared-memory read of the A (16 KB) and
 // B (bn*128 B) tiles at 128 B/clk.  Cost = waves over the SMs x (k-blocks x that + a fixed prologue/epilogue).
 int pick_block_n(int Npad, int m_tiles, int num_kb, int num_sms) {
-  static const int cands[] = {16, 32, 48, 64, 96, 128, 160, 192, 224, 256};
   int best = 16;
   double best_cost = 1e30;
-  for (int bn : cands) {
+  for (int bn = 16; bn <= 256; bn += 16) {  // every legal UMMA N for M=128
     const int n_tiles = (Npad + bn - 1) / bn;
     const long long tiles = (long long)n_tiles * m_tiles;
-    const long long waves = (tiles + num_sms - 1) / num_sms;
+    const long long rounds = (tiles + num_sms - 1) / num_sms;  // persistent CTAs: tiles per CTA
     const double per_kb = (double)((2 * bn > 128 + bn) ? 2 * bn : 128 + bn);
-    const double cost = (double)waves * (per_kb * num_kb + 2500.0 + 12.0 * bn);
+    // one epilogue (~12 cycles per column) is exposed at the end; the others overlap the next tile's MMAs unless
+    // they are longer than the mainloop
+    const double main = per_kb * num_kb, epi = 12.0 * bn + 400.0;
+    const double cost = (double)rounds * (main > epi ? main : epi) + epi + 2500.0;
     if (cost < best_cost - 1e-9) {
       best_cost = cost;
       best = bn;

@@ -39,14 +39,15 @@ struct KeyHash {
 }  // namespace
 
 int mc_make_tmap(CUtensorMap* tm, CUtensorMapDataType dtype, int rank, const void* base, const uint64_t* dims,
-                 const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
+                 const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle,
+                 CUtensorMapL2promotion promo) {
   if (rank < 1 || rank > 4) return mc_set_error(MC_ERR_ARG, "mc_make_tmap: rank %d", rank);
   static std::mutex mu;
   static std::unordered_map<Key, CUtensorMap, KeyHash> cache;
   Key key;
   memset(&key, 0, sizeof(key));
   key.v[0] = (uint64_t)(uintptr_t)base;
-  key.v[1] = ((uint64_t)dtype << 32) | ((uint64_t)rank << 8) | (uint64_t)swizzle;
+  key.v[1] = ((uint64_t)dtype << 32) | ((uint64_t)promo << 16) | ((uint64_t)rank << 8) | (uint64_t)swizzle;
   for (int i = 0; i < rank; ++i) {
     key.v[2 + i] = dims[i];
     key.v[6 + i] = (i + 1 < rank) ? strides_bytes[i] : 0;
@@ -71,7 +72,7 @@ int mc_make_tmap(CUtensorMap* tm, CUtensorMapDataType dtype, int rank, const voi
   }
   CUtensorMap out;
   CUresult r = fn(&out, dtype, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, promo,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return mc_set_error(MC_ERR_ARG, "cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims %llu,%llu,%llu,%llu box %u,%u,%u,%u",
