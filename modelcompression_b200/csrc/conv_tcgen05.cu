@@ -307,7 +307,13 @@ int pick_block_n(int Npad, int m_tiles, int num_kb, int num_sms) {
     const int n_tiles = (Npad + bn - 1) / bn;
     const long long tiles = (long long)n_tiles * m_tiles;
     const long long rounds = (tiles + num_sms - 1) / num_sms;  // persistent CTAs: tiles per CTA
-    const double per_kb = (double)((2 * bn > 128 + bn) ? 2 * bn : 128 + bn);
+    // per 64-wide k-block: tcgen05 issue floor 2*bn cycles; smem operand read (16 KB + bn*128 B at 128 B/clk);
+    // operand FEED from L2 through TMA, measured on B200 at ~13.3 cycles per KB per SM when all SMs stream
+    // (128x256 tiles run at ~80% tensor-active = 640 cycles per k-block for 48 KB)
+    double per_kb = 2.0 * bn;
+    if (128.0 + bn > per_kb) per_kb = 128.0 + bn;
+    const double feed = 13.3 * (16.0 + bn / 8.0);
+    if (feed > per_kb) per_kb = feed;
     // one epilogue (~12 cycles per column) is exposed at the end; the others overlap the next tile's MMAs unless
     // they are longer than the mainloop
     const double main = per_kb * num_kb, epi = 12.0 * bn + 400.0;
