@@ -33,6 +33,11 @@ struct SelState {
   unsigned long long cnt_le;    // #elements with key <= key_a (only when b is needed)
   unsigned int min_gt;          // min key > key_a
   unsigned int has_nan;         // any NaN input: np.percentile returns nan
+  // sample-pivot fast path
+  unsigned int lo_key, hi_key;  // pivots from the sample: sorted[k] lies in [lo_key, hi_key] unless the sample lied
+  unsigned long long below;     // #elements with key < lo_key
+  unsigned int done;            // 1: the fast path produced key_a (the exact radix path is skipped)
+  unsigned int pad2;
 };
 
 struct Chunks {
@@ -75,24 +80,6 @@ __device__ __forceinline__ void for_each_element(const SegTable& st, const Chunk
   }
 }
 
-__global__ void set_rank_kernel(SelState* state, unsigned long long k) { state->k = k; }
-
-__global__ void __launch_bounds__(THREADS) hist0_kernel(const SegTable st, const Chunks ch, SelState* state) {
-  __shared__ unsigned int sh[BINS0];
-  for (int i = threadIdx.x; i < BINS0; i += THREADS) sh[i] = 0;
-  __syncthreads();
-  bool saw_nan = false;
-  for_each_element(st, ch, [&](float v, int, long long) {
-    const unsigned int key = absbits(v);
-    saw_nan |= key > 0x7f800000u;
-    atomicAdd(&sh[key >> 19], 1u);
-  });
-  if (saw_nan) atomicOr(&state->has_nan, 1u);
-  __syncthreads();
-  for (int i = threadIdx.x; i < BINS0; i += THREADS)
-    if (sh[i]) atomicAdd(&state->hist0[i], sh[i]);
-}
-
 // Block-wide: find the bin holding rank `k` in hist[nbins]; returns bin, and the rank inside that bin.
 // Executed redundantly by every block that needs it (nbins <= 4096: 16 bins per thread).
 template <int NBINS>
@@ -126,6 +113,280 @@ __device__ void block_find_bin(const unsigned int* __restrict__ hist, unsigned l
   __syncthreads();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fast path.  A strided sample of S = 16384 elements gives two pivots lo <= hi that bracket the rank-k element with
+// overwhelming probability (+-6 sigma of the sample rank); ONE pass over the data then counts the elements below lo
+// and compacts those in [lo, hi] (~5 % of n); the exact rank is resolved on that small list.  If the bracket turns out
+// wrong (k not inside), `done` stays 0 and the exact radix path below runs instead — the result is always exact.
+constexpr int SAMPLE = 16384;
+
+__device__ __forceinline__ unsigned int load_key_at(const SegTable& st, long long g) {
+  int lo = 0, hi = st.nseg - 1;
+  while (lo < hi) {  // last segment with start <= g
+    const int mid = (lo + hi + 1) >> 1;
+    if (st.start[mid] <= g) lo = mid; else hi = mid - 1;
+  }
+  return absbits(st.ptr[lo][g - st.start[lo]]);
+}
+
+// block-wide radix select of two ranks over `n` uint keys in shared memory (8 bits per pass)
+__device__ void smem_select2(const unsigned int* keys, int n, unsigned int rank0, unsigned int rank1,
+                             unsigned int* s_hist /*[2][256]*/, unsigned int* s_pick /*[4]*/, unsigned int* out0,
+                             unsigned int* out1) {
+  unsigned int prefix0 = 0, prefix1 = 0, mask = 0, r0 = rank0, r1 = rank1;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned int key = keys[i], d = (key >> shift) & 255u;
+      if ((key & mask) == prefix0) atomicAdd(&s_hist[d], 1u);
+      if ((key & mask) == prefix1) atomicAdd(&s_hist[256 + d], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      const unsigned int* h = s_hist + threadIdx.x * 256;
+      const unsigned int rank = threadIdx.x ? r1 : r0;
+      unsigned int cum = 0, b = 0;
+      for (; b < 255; ++b) {
+        if (cum + h[b] > rank) break;
+        cum += h[b];
+      }
+      s_pick[threadIdx.x * 2] = b;
+      s_pick[threadIdx.x * 2 + 1] = rank - cum;
+    }
+    __syncthreads();
+    prefix0 |= s_pick[0] << shift;
+    r0 = s_pick[1];
+    prefix1 |= s_pick[2] << shift;
+    r1 = s_pick[3];
+    mask |= 255u << shift;
+    __syncthreads();
+  }
+  *out0 = prefix0;
+  *out1 = prefix1;
+}
+
+__global__ void __launch_bounds__(1024) sample_pivot_kernel(const SegTable st, SelState* state, long long n,
+                                                            unsigned long long k) {
+  extern __shared__ unsigned int s_keys[];  // [SAMPLE]
+  __shared__ unsigned int s_hist[512];
+  __shared__ unsigned int s_pick[4];
+  const int S = (n < SAMPLE) ? (int)n : SAMPLE;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    // stratified: one element from each of S equal slices, position inside the slice hashed
+    // S == SAMPLE == 2^14 whenever n >= SAMPLE (i*n < 2^14 * 2^40 fits 64 bits); otherwise every element is sampled
+    const long long lo = (S == SAMPLE) ? (((long long)i * n) >> 14) : (long long)i;
+    const long long hi = (S == SAMPLE) ? (((long long)(i + 1) * n) >> 14) : (long long)i + 1;
+    unsigned int h = (unsigned int)i * 2654435761u;
+    h ^= h >> 15;
+    const long long g = lo + (long long)(h % (unsigned int)((hi - lo) > 0 ? (hi - lo) : 1));
+    s_keys[i] = load_key_at(st, g);
+  }
+  __syncthreads();
+  // sample ranks bracketing k: m = k*S/n, +- (6 sigma + 8), sigma = sqrt(S q (1-q))
+  const double q = (double)k / (double)n;
+  const double m = q * S;
+  const double sig = sqrt((double)S * q * (1.0 - q));
+  const double d = 6.0 * sig + 8.0;
+  long long rlo = (long long)floor(m - d), rhi = (long long)ceil(m + d);
+  const bool open_lo = rlo <= 0, open_hi = rhi >= S - 1;
+  if (rlo < 0) rlo = 0;
+  if (rhi > S - 1) rhi = S - 1;
+  unsigned int klo, khi;
+  smem_select2(s_keys, S, (unsigned int)rlo, (unsigned int)rhi, s_hist, s_pick, &klo, &khi);
+  if (threadIdx.x == 0) {
+    state->lo_key = open_lo ? 0u : klo;
+    state->hi_key = open_hi ? 0xffffffffu : khi;
+  }
+}
+
+// one pass over the data: count keys < lo, compact keys in [lo, hi]
+__global__ void __launch_bounds__(THREADS) count_compact_kernel(const SegTable st, const Chunks ch, SelState* state,
+                                                                unsigned int* __restrict__ cand,
+                                                                unsigned long long cand_cap) {
+  __shared__ unsigned int s_wsum[THREADS / 32];
+  __shared__ unsigned int s_base;
+  __shared__ unsigned long long s_below[THREADS / 32];
+  const unsigned int lo = state->lo_key, hi = state->hi_key;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned long long below = 0;
+  bool saw_nan = false;
+  const long long nchunks = ch.cstart[st.nseg];
+  for (long long cid = blockIdx.x; cid < nchunks; cid += gridDim.x) {
+    const int s = find_seg(ch, st.nseg, cid);
+    const long long size = st.start[s + 1] - st.start[s];
+    const long long base = (cid - ch.cstart[s]) * CHUNK;
+    const float* p = st.ptr[s];
+    const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+    unsigned int keys[8];
+    unsigned int hits = 0;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const long long i = base + ((long long)it * THREADS + threadIdx.x) * 4;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      int nvalid = 0;
+      if (aligned && i + 4 <= size) {
+        const float4 q = ld_stream_f4(reinterpret_cast<const float4*>(p + i));
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        nvalid = 4;
+      } else {
+        for (int j = 0; j < 4; ++j)
+          if (i + j < size) { v[j] = p[i + j]; nvalid = j + 1; }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const unsigned int key = absbits(v[j]);
+        keys[it * 4 + j] = key;
+        if (j < nvalid) {
+          saw_nan |= key > 0x7f800000u;
+          if (key < lo) ++below;
+          else if (key <= hi) hits |= 1u << (it * 4 + j);
+        }
+      }
+    }
+    const unsigned int cnt = __popc(hits);
+    unsigned int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_wsum[wid] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int tot = 0;
+      for (int w = 0; w < THREADS / 32; ++w) { const unsigned int c = s_wsum[w]; s_wsum[w] = tot; tot += c; }
+      s_base = tot ? atomicAdd(&state->cand_count, tot) : 0u;
+    }
+    __syncthreads();
+    unsigned int pos = s_base + s_wsum[wid] + (incl - cnt);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (hits & (1u << j)) {
+        if (pos < cand_cap) cand[pos] = keys[j];
+        ++pos;
+      }
+    __syncthreads();
+  }
+  for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+  if (lane == 0) s_below[wid] = below;
+  if (saw_nan) atomicOr(&state->has_nan, 1u);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long tot = 0;
+    for (int w = 0; w < THREADS / 32; ++w) tot += s_below[w];
+    if (tot) atomicAdd(&state->below, tot);
+  }
+}
+
+// candidate-list histograms of the fast path: level A = bits [30:19] of every candidate
+__global__ void __launch_bounds__(THREADS) histA_kernel(SelState* state, const unsigned int* __restrict__ cand) {
+  __shared__ unsigned int sh[BINS0];
+  for (int i = threadIdx.x; i < BINS0; i += THREADS) sh[i] = 0;
+  __syncthreads();
+  const unsigned int m = state->cand_count;
+  for (unsigned int i = blockIdx.x * THREADS + threadIdx.x; i < m; i += gridDim.x * THREADS)
+    atomicAdd(&sh[cand[i] >> 19], 1u);
+  __syncthreads();
+  for (int i = threadIdx.x; i < BINS0; i += THREADS)
+    if (sh[i]) atomicAdd(&state->hist0[i], sh[i]);
+}
+
+// level B: bits [18:7] of the candidates inside bin0 (bin0 located from hist0 with the rank k - below)
+__global__ void __launch_bounds__(THREADS) histB_kernel(SelState* state, const unsigned int* __restrict__ cand) {
+  __shared__ unsigned int s_bin;
+  __shared__ unsigned long long s_rem;
+  __shared__ unsigned int sh[BINS1];
+  const unsigned long long below = state->below;
+  const unsigned int m = state->cand_count;
+  if (state->k < below || state->k - below >= (unsigned long long)m) return;  // bracket missed: exact path takes over
+  block_find_bin<BINS0>(state->hist0, state->k - below, &s_bin, &s_rem);
+  const unsigned int bin0 = s_bin;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    state->bin0 = bin0;
+    state->rem1 = s_rem;
+  }
+  for (int i = threadIdx.x; i < BINS1; i += THREADS) sh[i] = 0;
+  __syncthreads();
+  for (unsigned int i = blockIdx.x * THREADS + threadIdx.x; i < m; i += gridDim.x * THREADS) {
+    const unsigned int key = cand[i];
+    if ((key >> 19) == bin0) atomicAdd(&sh[(key >> 7) & (BINS1 - 1)], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < BINS1; i += THREADS)
+    if (sh[i]) atomicAdd(&state->hist1[i], sh[i]);
+}
+
+// level C: bits [6:0] of the candidates inside (bin0, bin1)
+__global__ void __launch_bounds__(THREADS) histC_kernel(SelState* state, const unsigned int* __restrict__ cand) {
+  __shared__ unsigned int s_bin;
+  __shared__ unsigned long long s_rem;
+  __shared__ unsigned int sh[BINS2];
+  const unsigned long long below = state->below;
+  const unsigned int m = state->cand_count;
+  if (state->k < below || state->k - below >= (unsigned long long)m) return;
+  block_find_bin<BINS1>(state->hist1, state->rem1, &s_bin, &s_rem);
+  const unsigned int bin1 = s_bin, bin0 = state->bin0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    state->bin1 = bin1;
+    state->rem2 = s_rem;
+  }
+  if (threadIdx.x < BINS2) sh[threadIdx.x] = 0;
+  __syncthreads();
+  for (unsigned int i = blockIdx.x * THREADS + threadIdx.x; i < m; i += gridDim.x * THREADS) {
+    const unsigned int key = cand[i];
+    if ((key >> 19) == bin0 && ((key >> 7) & (BINS1 - 1)) == bin1) atomicAdd(&sh[key & (BINS2 - 1)], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < BINS2 && sh[threadIdx.x]) atomicAdd(&state->hist2[threadIdx.x], sh[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(THREADS) finalF_kernel(SelState* state, SelState* exact, float* out3, int need_b) {
+  __shared__ unsigned int s_bin;
+  __shared__ unsigned long long s_rem;
+  const unsigned long long below = state->below;
+  if (state->k < below || state->k - below >= (unsigned long long)state->cand_count) return;  // done stays 0
+  block_find_bin<BINS2>(state->hist2, state->rem2, &s_bin, &s_rem);
+  if (threadIdx.x == 0) {
+    const unsigned int key = (state->bin0 << 19) | (state->bin1 << 7) | s_bin;
+    // the succ/lerp kernels read the EXACT-path state: publish the result there
+    exact->key_a = key;
+    exact->cnt_le = 0;
+    exact->min_gt = 0xffffffffu;
+    exact->has_nan = state->has_nan;
+    exact->done = 1;
+    state->done = 1;
+    if (!need_b) {
+      const float a = state->has_nan ? __uint_as_float(0x7fc00000u) : __uint_as_float(key);
+      out3[0] = a;
+      out3[1] = a;
+      out3[2] = a;
+    }
+  }
+}
+
+__global__ void set_rank_kernel(SelState* state, SelState* fast, unsigned long long k) {
+  state->k = k;
+  fast->k = k;
+}
+
+__global__ void __launch_bounds__(THREADS) hist0_kernel(const SegTable st, const Chunks ch, SelState* state) {
+  __shared__ unsigned int sh[BINS0];
+  if (state->done) return;  // the sample-pivot fast path already produced the answer
+  for (int i = threadIdx.x; i < BINS0; i += THREADS) sh[i] = 0;
+  __syncthreads();
+  bool saw_nan = false;
+  for_each_element(st, ch, [&](float v, int, long long) {
+    const unsigned int key = absbits(v);
+    saw_nan |= key > 0x7f800000u;
+    atomicAdd(&sh[key >> 19], 1u);
+  });
+  if (saw_nan) atomicOr(&state->has_nan, 1u);
+  __syncthreads();
+  for (int i = threadIdx.x; i < BINS0; i += THREADS)
+    if (sh[i]) atomicAdd(&state->hist0[i], sh[i]);
+}
+
 // Compaction of the selected bin: one global atomic per block-iteration (block-wide exclusive scan of the per-thread
 // hit counts), not one per warp — a single counter address serialises in L2 otherwise.
 __global__ void __launch_bounds__(THREADS) compact_kernel(const SegTable st, const Chunks ch, SelState* state,
@@ -135,6 +396,7 @@ __global__ void __launch_bounds__(THREADS) compact_kernel(const SegTable st, con
   __shared__ unsigned long long s_rem;
   __shared__ unsigned int s_wsum[THREADS / 32];
   __shared__ unsigned int s_base;
+  if (state->done) return;
   block_find_bin<BINS0>(state->hist0, state->k, &s_bin, &s_rem);
   const unsigned int bin = s_bin;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -199,6 +461,7 @@ __global__ void __launch_bounds__(THREADS) compact_kernel(const SegTable st, con
 
 __global__ void __launch_bounds__(THREADS) hist1_kernel(SelState* state, const unsigned int* __restrict__ cand) {
   __shared__ unsigned int sh[BINS1];
+  if (state->done) return;
   for (int i = threadIdx.x; i < BINS1; i += THREADS) sh[i] = 0;
   __syncthreads();
   const unsigned int m = state->cand_count;
@@ -213,6 +476,7 @@ __global__ void __launch_bounds__(THREADS) hist2_kernel(SelState* state, const u
   __shared__ unsigned int s_bin;
   __shared__ unsigned long long s_rem;
   __shared__ unsigned int sh[BINS2];
+  if (state->done) return;
   block_find_bin<BINS1>(state->hist1, state->rem1, &s_bin, &s_rem);
   const unsigned int bin1 = s_bin;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -234,6 +498,7 @@ __global__ void __launch_bounds__(THREADS) hist2_kernel(SelState* state, const u
 __global__ void __launch_bounds__(THREADS) final_kernel(SelState* state, float* out3, int need_b) {
   __shared__ unsigned int s_bin;
   __shared__ unsigned long long s_rem;
+  if (state->done) return;
   block_find_bin<BINS2>(state->hist2, state->rem2, &s_bin, &s_rem);
   if (threadIdx.x == 0) {
     const unsigned int key = (state->bin0 << 19) | (state->bin1 << 7) | s_bin;
@@ -446,7 +711,7 @@ int stream_grid(long long nchunks) {
 extern "C" size_t mc_workspace_bytes_kth_abs_select(int64_t n_total) {
   if (n_total < 0) n_total = 0;
   // state + worst-case candidate list (every element in one 12-bit bin, e.g. an already-pruned model)
-  return ((sizeof(SelState) + 255) / 256) * 256 + (size_t)n_total * sizeof(unsigned int) + 256;
+  return 2 * (((sizeof(SelState) + 255) / 256) * 256) + (size_t)n_total * sizeof(unsigned int) + 256;
 }
 
 extern "C" int mc_kth_abs_select(const float* const* h_seg_ptrs, const int64_t* h_seg_sizes, int nseg, int64_t k,
@@ -464,24 +729,46 @@ extern "C" int mc_kth_abs_select(const float* const* h_seg_ptrs, const int64_t* 
   if (ws_bytes < mc_workspace_bytes_kth_abs_select(n))
     return mc_set_error(MC_ERR_WS, "mc_kth_abs_select: workspace %zu < required %zu", ws_bytes,
                         mc_workspace_bytes_kth_abs_select(n));
-  SelState* state = reinterpret_cast<SelState*>(d_ws);
   const size_t state_bytes = ((sizeof(SelState) + 255) / 256) * 256;
-  unsigned int* cand = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(d_ws) + state_bytes);
+  SelState* state = reinterpret_cast<SelState*>(d_ws);                                          // exact radix path
+  SelState* fast = reinterpret_cast<SelState*>(reinterpret_cast<char*>(d_ws) + state_bytes);    // sample-pivot path
+  unsigned int* cand = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(d_ws) + 2 * state_bytes);
 
-  MC_CUDA(cudaMemsetAsync(state, 0, sizeof(SelState), stream));
-  set_rank_kernel<<<1, 1, 0, stream>>>(state, (unsigned long long)k);
+  MC_CUDA(cudaMemsetAsync(d_ws, 0, 2 * state_bytes, stream));
+  set_rank_kernel<<<1, 1, 0, stream>>>(state, fast, (unsigned long long)k);
   MC_LAUNCH_CHECK("set_rank_kernel");
   const int grid = stream_grid(ch.cstart[nseg]);
+  const int cgrid = mc_num_sms();
+  const int need_b = (gamma != 0.f && k + 1 < n) ? 1 : 0;
+  if (n >= 4 * SAMPLE) {
+    // fast path: pivots from a sample, one pass over W (count + compact), exact rank on the ~5 % candidates
+    static bool attr_set = false;
+    if (!attr_set) {
+      MC_CUDA(cudaFuncSetAttribute(sample_pivot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SAMPLE * 4));
+      attr_set = true;
+    }
+    sample_pivot_kernel<<<1, 1024, SAMPLE * 4, stream>>>(st, fast, n, (unsigned long long)k);
+    MC_LAUNCH_CHECK("sample_pivot_kernel");
+    count_compact_kernel<<<grid, THREADS, 0, stream>>>(st, ch, fast, cand, (unsigned long long)n);
+    MC_LAUNCH_CHECK("count_compact_kernel");
+    histA_kernel<<<cgrid, THREADS, 0, stream>>>(fast, cand);
+    MC_LAUNCH_CHECK("histA_kernel");
+    histB_kernel<<<cgrid, THREADS, 0, stream>>>(fast, cand);
+    MC_LAUNCH_CHECK("histB_kernel");
+    histC_kernel<<<cgrid, THREADS, 0, stream>>>(fast, cand);
+    MC_LAUNCH_CHECK("histC_kernel");
+    finalF_kernel<<<1, THREADS, 0, stream>>>(fast, state, d_out3, need_b);
+    MC_LAUNCH_CHECK("finalF_kernel");
+  }
+  // exact radix path: every kernel returns immediately when the fast path has set `done`
   hist0_kernel<<<grid, THREADS, 0, stream>>>(st, ch, state);
   MC_LAUNCH_CHECK("hist0_kernel");
   compact_kernel<<<grid, THREADS, 0, stream>>>(st, ch, state, cand, (unsigned long long)n);
   MC_LAUNCH_CHECK("compact_kernel");
-  const int cgrid = mc_num_sms();
   hist1_kernel<<<cgrid, THREADS, 0, stream>>>(state, cand);
   MC_LAUNCH_CHECK("hist1_kernel");
   hist2_kernel<<<cgrid, THREADS, 0, stream>>>(state, cand);
   MC_LAUNCH_CHECK("hist2_kernel");
-  const int need_b = (gamma != 0.f && k + 1 < n) ? 1 : 0;
   final_kernel<<<1, THREADS, 0, stream>>>(state, d_out3, need_b);
   MC_LAUNCH_CHECK("final_kernel");
   if (need_b) {
