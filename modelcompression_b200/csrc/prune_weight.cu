@@ -9,6 +9,7 @@
 // found by a 12+12+7-bit radix select.  Pass 0 histograms the top 12 bits of every element (one read of W),
 // pass 1 compacts the elements of the selected bin into the workspace, passes 2..3 histogram the remaining
 // bits on the (small) candidate list.  HBM traffic: 2 reads of W for the select + read W / write mask.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -200,17 +201,34 @@ __global__ void __launch_bounds__(1024) sample_pivot_kernel(const SegTable st, S
   }
 }
 
-// one pass over the data: count keys < lo, compact keys in [lo, hi]
+// one pass over the data: count keys < lo, compact keys in [lo, hi].  Hits are appended to a shared-memory staging
+// buffer with one warp-aggregated shared atomic per warp and iteration; the buffer is flushed to the global candidate
+// list (one global atomic per flush) only when it could overflow, so no iteration waits on an L2 round trip.
+constexpr int STAGE_CAP = 6144;  // keys; a block-iteration appends at most CHUNK = 2048
 __global__ void __launch_bounds__(THREADS) count_compact_kernel(const SegTable st, const Chunks ch, SelState* state,
                                                                 unsigned int* __restrict__ cand,
                                                                 unsigned long long cand_cap) {
-  __shared__ unsigned int s_wsum[THREADS / 32];
-  __shared__ unsigned int s_base;
+  __shared__ unsigned int s_buf[STAGE_CAP];
+  __shared__ unsigned int s_cnt, s_base;
   __shared__ unsigned long long s_below[THREADS / 32];
   const unsigned int lo = state->lo_key, hi = state->hi_key;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
   unsigned long long below = 0;
   bool saw_nan = false;
+  auto flush = [&]() {  // block-wide; caller guarantees every thread calls it
+    __syncthreads();
+    const unsigned int cnt = s_cnt;
+    if (threadIdx.x == 0) s_base = cnt ? atomicAdd(&state->cand_count, cnt) : 0u;
+    __syncthreads();
+    const unsigned int base = s_base;
+    for (unsigned int i = threadIdx.x; i < cnt; i += THREADS)
+      if ((unsigned long long)base + i < cand_cap) cand[base + i] = s_buf[i];
+    __syncthreads();
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+  };
   const long long nchunks = ch.cstart[st.nseg];
   for (long long cid = blockIdx.x; cid < nchunks; cid += gridDim.x) {
     const int s = find_seg(ch, st.nseg, cid);
@@ -244,6 +262,8 @@ __global__ void __launch_bounds__(THREADS) count_compact_kernel(const SegTable s
         }
       }
     }
+    // block-uniform decision (s_cnt is only modified between barriers): make room for this iteration's hits
+    if (s_cnt > STAGE_CAP - CHUNK) flush();
     const unsigned int cnt = __popc(hits);
     unsigned int incl = cnt;
 #pragma unroll
@@ -251,23 +271,16 @@ __global__ void __launch_bounds__(THREADS) count_compact_kernel(const SegTable s
       const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += t;
     }
-    if (lane == 31) s_wsum[wid] = incl;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned int tot = 0;
-      for (int w = 0; w < THREADS / 32; ++w) { const unsigned int c = s_wsum[w]; s_wsum[w] = tot; tot += c; }
-      s_base = tot ? atomicAdd(&state->cand_count, tot) : 0u;
-    }
-    __syncthreads();
-    unsigned int pos = s_base + s_wsum[wid] + (incl - cnt);
+    unsigned int wbase = 0;
+    if (lane == 31 && incl) wbase = atomicAdd(&s_cnt, incl);
+    wbase = __shfl_sync(0xffffffffu, wbase, 31);
+    unsigned int pos = wbase + (incl - cnt);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      if (hits & (1u << j)) {
-        if (pos < cand_cap) cand[pos] = keys[j];
-        ++pos;
-      }
-    __syncthreads();
+      if (hits & (1u << j)) s_buf[pos++] = keys[j];
+    __syncthreads();  // s_cnt stable before the next iteration's overflow test
   }
+  flush();
   for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
   if (lane == 0) s_below[wid] = below;
   if (saw_nan) atomicOr(&state->has_nan, 1u);
@@ -279,20 +292,39 @@ __global__ void __launch_bounds__(THREADS) count_compact_kernel(const SegTable s
   }
 }
 
-// candidate-list histograms of the fast path: level A = bits [30:19] of every candidate
+// Candidate-list histograms of the fast path.  Candidates all lie in [lo, hi], so bins are taken on d = key - lo:
+// level A = d >> sA with sA chosen so that (hi-lo) >> sA < 4096 (candidates spread over the bins instead of piling
+// into the two or three bins their common high bits select), level B = the next min(12, sA) bits, level C the rest.
+__device__ __forceinline__ void fast_shifts(const SelState* st, unsigned int* lo, int* sA, int* sB) {
+  const unsigned int l = st->lo_key;
+  const unsigned int h = st->hi_key > 0x7fffffffu ? 0x7fffffffu : st->hi_key;
+  unsigned int width = (h >= l) ? (h - l) : 0u;
+  int a = 0;
+  while ((width >> a) >= (unsigned int)BINS0) ++a;
+  *lo = l;
+  *sA = a;
+  *sB = a > 12 ? a - 12 : 0;
+}
+__device__ __forceinline__ unsigned int fast_rel(unsigned int key, unsigned int lo) {
+  const unsigned int k = key > 0x7fffffffu ? 0x7fffffffu : key;
+  return k - lo;
+}
+
 __global__ void __launch_bounds__(THREADS) histA_kernel(SelState* state, const unsigned int* __restrict__ cand) {
   __shared__ unsigned int sh[BINS0];
+  unsigned int lo;
+  int sA, sB;
+  fast_shifts(state, &lo, &sA, &sB);
   for (int i = threadIdx.x; i < BINS0; i += THREADS) sh[i] = 0;
   __syncthreads();
   const unsigned int m = state->cand_count;
   for (unsigned int i = blockIdx.x * THREADS + threadIdx.x; i < m; i += gridDim.x * THREADS)
-    atomicAdd(&sh[cand[i] >> 19], 1u);
+    atomicAdd(&sh[fast_rel(cand[i], lo) >> sA], 1u);
   __syncthreads();
   for (int i = threadIdx.x; i < BINS0; i += THREADS)
     if (sh[i]) atomicAdd(&state->hist0[i], sh[i]);
 }
 
-// level B: bits [18:7] of the candidates inside bin0 (bin0 located from hist0 with the rank k - below)
 __global__ void __launch_bounds__(THREADS) histB_kernel(SelState* state, const unsigned int* __restrict__ cand) {
   __shared__ unsigned int s_bin;
   __shared__ unsigned long long s_rem;
@@ -300,6 +332,9 @@ __global__ void __launch_bounds__(THREADS) histB_kernel(SelState* state, const u
   const unsigned long long below = state->below;
   const unsigned int m = state->cand_count;
   if (state->k < below || state->k - below >= (unsigned long long)m) return;  // bracket missed: exact path takes over
+  unsigned int lo;
+  int sA, sB;
+  fast_shifts(state, &lo, &sA, &sB);
   block_find_bin<BINS0>(state->hist0, state->k - below, &s_bin, &s_rem);
   const unsigned int bin0 = s_bin;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -309,15 +344,14 @@ __global__ void __launch_bounds__(THREADS) histB_kernel(SelState* state, const u
   for (int i = threadIdx.x; i < BINS1; i += THREADS) sh[i] = 0;
   __syncthreads();
   for (unsigned int i = blockIdx.x * THREADS + threadIdx.x; i < m; i += gridDim.x * THREADS) {
-    const unsigned int key = cand[i];
-    if ((key >> 19) == bin0) atomicAdd(&sh[(key >> 7) & (BINS1 - 1)], 1u);
+    const unsigned int d = fast_rel(cand[i], lo);
+    if ((d >> sA) == bin0) atomicAdd(&sh[(d >> sB) & (BINS1 - 1) & ((1u << (sA - sB)) - 1u)], 1u);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < BINS1; i += THREADS)
     if (sh[i]) atomicAdd(&state->hist1[i], sh[i]);
 }
 
-// level C: bits [6:0] of the candidates inside (bin0, bin1)
 __global__ void __launch_bounds__(THREADS) histC_kernel(SelState* state, const unsigned int* __restrict__ cand) {
   __shared__ unsigned int s_bin;
   __shared__ unsigned long long s_rem;
@@ -325,6 +359,9 @@ __global__ void __launch_bounds__(THREADS) histC_kernel(SelState* state, const u
   const unsigned long long below = state->below;
   const unsigned int m = state->cand_count;
   if (state->k < below || state->k - below >= (unsigned long long)m) return;
+  unsigned int lo;
+  int sA, sB;
+  fast_shifts(state, &lo, &sA, &sB);
   block_find_bin<BINS1>(state->hist1, state->rem1, &s_bin, &s_rem);
   const unsigned int bin1 = s_bin, bin0 = state->bin0;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -333,12 +370,15 @@ __global__ void __launch_bounds__(THREADS) histC_kernel(SelState* state, const u
   }
   if (threadIdx.x < BINS2) sh[threadIdx.x] = 0;
   __syncthreads();
-  for (unsigned int i = blockIdx.x * THREADS + threadIdx.x; i < m; i += gridDim.x * THREADS) {
-    const unsigned int key = cand[i];
-    if ((key >> 19) == bin0 && ((key >> 7) & (BINS1 - 1)) == bin1) atomicAdd(&sh[key & (BINS2 - 1)], 1u);
+  if (sB > 0) {  // sB <= 7 (d < 2^31, sA <= 19): at most 128 bins
+    const unsigned int maskB = (1u << (sA - sB)) - 1u;
+    for (unsigned int i = blockIdx.x * THREADS + threadIdx.x; i < m; i += gridDim.x * THREADS) {
+      const unsigned int d = fast_rel(cand[i], lo);
+      if ((d >> sA) == bin0 && ((d >> sB) & maskB) == bin1) atomicAdd(&sh[d & ((1u << sB) - 1u)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < BINS2 && sh[threadIdx.x]) atomicAdd(&state->hist2[threadIdx.x], sh[threadIdx.x]);
   }
-  __syncthreads();
-  if (threadIdx.x < BINS2 && sh[threadIdx.x]) atomicAdd(&state->hist2[threadIdx.x], sh[threadIdx.x]);
 }
 
 __global__ void __launch_bounds__(THREADS) finalF_kernel(SelState* state, SelState* exact, float* out3, int need_b) {
@@ -346,9 +386,14 @@ __global__ void __launch_bounds__(THREADS) finalF_kernel(SelState* state, SelSta
   __shared__ unsigned long long s_rem;
   const unsigned long long below = state->below;
   if (state->k < below || state->k - below >= (unsigned long long)state->cand_count) return;  // done stays 0
-  block_find_bin<BINS2>(state->hist2, state->rem2, &s_bin, &s_rem);
+  unsigned int lo;
+  int sA, sB;
+  fast_shifts(state, &lo, &sA, &sB);
+  if (sB > 0) block_find_bin<BINS2>(state->hist2, state->rem2, &s_bin, &s_rem);
+  else if (threadIdx.x == 0) s_bin = 0;
+  __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned int key = (state->bin0 << 19) | (state->bin1 << 7) | s_bin;
+    const unsigned int key = lo + ((state->bin0 << sA) | (state->bin1 << sB) | s_bin);
     // the succ/lerp kernels read the EXACT-path state: publish the result there
     exact->key_a = key;
     exact->cnt_le = 0;
@@ -740,7 +785,9 @@ extern "C" int mc_kth_abs_select(const float* const* h_seg_ptrs, const int64_t* 
   const int grid = stream_grid(ch.cstart[nseg]);
   const int cgrid = mc_num_sms();
   const int need_b = (gamma != 0.f && k + 1 < n) ? 1 : 0;
-  if (n >= 4 * SAMPLE) {
+  // MCB200_SELECT_EXACT=1 forces the radix path (used by the tests to cover the fallback on large inputs)
+  const char* force_exact = getenv("MCB200_SELECT_EXACT");
+  if (n >= 4 * SAMPLE && !(force_exact && force_exact[0] == '1')) {
     // fast path: pivots from a sample, one pass over W (count + compact), exact rank on the ~5 % candidates
     static bool attr_set = false;
     if (!attr_set) {

@@ -63,6 +63,15 @@ def test_weight_prune_darknet_bit_exact(darknet, idx):
         assert m.shape == p.shape and m.device == p.device
 
 
+def test_weight_prune_exact_radix_fallback(darknet, monkeypatch):
+    # the sample-pivot fast path falls back to the full radix select on the device when its bracket misses; force
+    # that path on the full model and check it gives the same (bit-exact) masks
+    g = load_golden('weight_prune_darknet.npz')
+    monkeypatch.setenv('MCB200_SELECT_EXACT', '1')
+    masks = mc.weight_prune(darknet, 80.)
+    assert [_sha(_bits(m.cpu().numpy())) for m in masks] == g['sha_2'].tolist()
+
+
 def test_weight_prune_vs_oracle_other_percentiles(darknet):
     ws = [p.detach().cpu().numpy() for p in darknet.parameters() if p.dim() != 1]
     for perc in (1.0, 50.0, 99.9):
