@@ -15,7 +15,8 @@
 namespace {
 
 constexpr int THREADS = 256;
-constexpr int CHUNK = THREADS * 8;  // elements per block-iteration (two float4 per thread)
+constexpr int ITERS = 4;                  // float4 loads per thread and block-iteration (all issued before use)
+constexpr int CHUNK = THREADS * 4 * ITERS;  // elements per block-iteration
 constexpr int BINS0 = 4096;         // bits [30:19]
 constexpr int BINS1 = 4096;         // bits [18:7]
 constexpr int BINS2 = 128;          // bits [6:0]
@@ -65,7 +66,7 @@ __device__ __forceinline__ void for_each_element(const SegTable& st, const Chunk
     const float* p = st.ptr[s];
     const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
+    for (int it = 0; it < ITERS; ++it) {
       const long long i = base + ((long long)it * THREADS + threadIdx.x) * 4;
       if (aligned && i + 4 <= size) {
         const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(p + i));
@@ -201,33 +202,30 @@ __global__ void __launch_bounds__(1024) sample_pivot_kernel(const SegTable st, S
   }
 }
 
-// one pass over the data: count keys < lo, compact keys in [lo, hi].  Hits are appended to a shared-memory staging
-// buffer with one warp-aggregated shared atomic per warp and iteration; the buffer is flushed to the global candidate
-// list (one global atomic per flush) only when it could overflow, so no iteration waits on an L2 round trip.
-constexpr int STAGE_CAP = 6144;  // keys; a block-iteration appends at most CHUNK = 2048
+// one pass over the data: count keys < lo, compact keys in [lo, hi].  Each WARP stages its hits in its own slice of
+// shared memory (no block barrier in the loop) and flushes the slice to the global candidate list with one global
+// atomic when it could overflow, so no iteration waits on an L2 round trip or on the other warps.
+constexpr int WSTAGE = 1024;               // keys per warp slice; one warp-iteration appends at most 32*4*ITERS = 512
 __global__ void __launch_bounds__(THREADS) count_compact_kernel(const SegTable st, const Chunks ch, SelState* state,
                                                                 unsigned int* __restrict__ cand,
                                                                 unsigned long long cand_cap) {
-  __shared__ unsigned int s_buf[STAGE_CAP];
-  __shared__ unsigned int s_cnt, s_base;
+  __shared__ unsigned int s_buf[(THREADS / 32) * WSTAGE];
   __shared__ unsigned long long s_below[THREADS / 32];
   const unsigned int lo = state->lo_key, hi = state->hi_key;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_cnt = 0;
-  __syncthreads();
+  unsigned int* wbuf = s_buf + wid * WSTAGE;
+  unsigned int wcnt = 0;  // warp-uniform
   unsigned long long below = 0;
   bool saw_nan = false;
-  auto flush = [&]() {  // block-wide; caller guarantees every thread calls it
-    __syncthreads();
-    const unsigned int cnt = s_cnt;
-    if (threadIdx.x == 0) s_base = cnt ? atomicAdd(&state->cand_count, cnt) : 0u;
-    __syncthreads();
-    const unsigned int base = s_base;
-    for (unsigned int i = threadIdx.x; i < cnt; i += THREADS)
-      if ((unsigned long long)base + i < cand_cap) cand[base + i] = s_buf[i];
-    __syncthreads();
-    if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
+  auto flush = [&]() {  // warp-wide
+    unsigned int base = 0;
+    if (lane == 0 && wcnt) base = atomicAdd(&state->cand_count, wcnt);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    __syncwarp();
+    for (unsigned int i = lane; i < wcnt; i += 32)
+      if ((unsigned long long)base + i < cand_cap) cand[base + i] = wbuf[i];
+    __syncwarp();
+    wcnt = 0;
   };
   const long long nchunks = ch.cstart[st.nseg];
   for (long long cid = blockIdx.x; cid < nchunks; cid += gridDim.x) {
@@ -236,34 +234,40 @@ __global__ void __launch_bounds__(THREADS) count_compact_kernel(const SegTable s
     const long long base = (cid - ch.cstart[s]) * CHUNK;
     const float* p = st.ptr[s];
     const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
-    unsigned int keys[8];
+    float4 q[ITERS];
+    int nvalid[ITERS];
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {  // all loads in flight before the first use
+      const long long i = base + ((long long)it * THREADS + threadIdx.x) * 4;
+      q[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      nvalid[it] = 0;
+      if (aligned && i + 4 <= size) {
+        q[it] = ld_stream_f4(reinterpret_cast<const float4*>(p + i));
+        nvalid[it] = 4;
+      } else if (i < size) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < 4; ++j)
+          if (i + j < size) { v[j] = p[i + j]; nvalid[it] = j + 1; }
+        q[it] = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    }
+    unsigned int keys[4 * ITERS];
     unsigned int hits = 0;
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
-      const long long i = base + ((long long)it * THREADS + threadIdx.x) * 4;
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      int nvalid = 0;
-      if (aligned && i + 4 <= size) {
-        const float4 q = ld_stream_f4(reinterpret_cast<const float4*>(p + i));
-        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-        nvalid = 4;
-      } else {
-        for (int j = 0; j < 4; ++j)
-          if (i + j < size) { v[j] = p[i + j]; nvalid = j + 1; }
-      }
+    for (int it = 0; it < ITERS; ++it) {
+      const float v[4] = {q[it].x, q[it].y, q[it].z, q[it].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const unsigned int key = absbits(v[j]);
         keys[it * 4 + j] = key;
-        if (j < nvalid) {
+        if (j < nvalid[it]) {
           saw_nan |= key > 0x7f800000u;
           if (key < lo) ++below;
           else if (key <= hi) hits |= 1u << (it * 4 + j);
         }
       }
     }
-    // block-uniform decision (s_cnt is only modified between barriers): make room for this iteration's hits
-    if (s_cnt > STAGE_CAP - CHUNK) flush();
+    if (wcnt > WSTAGE - 32 * 4 * ITERS) flush();
     const unsigned int cnt = __popc(hits);
     unsigned int incl = cnt;
 #pragma unroll
@@ -271,14 +275,11 @@ __global__ void __launch_bounds__(THREADS) count_compact_kernel(const SegTable s
       const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += t;
     }
-    unsigned int wbase = 0;
-    if (lane == 31 && incl) wbase = atomicAdd(&s_cnt, incl);
-    wbase = __shfl_sync(0xffffffffu, wbase, 31);
-    unsigned int pos = wbase + (incl - cnt);
+    unsigned int pos = wcnt + (incl - cnt);
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (hits & (1u << j)) s_buf[pos++] = keys[j];
-    __syncthreads();  // s_cnt stable before the next iteration's overflow test
+    for (int j = 0; j < 4 * ITERS; ++j)
+      if (hits & (1u << j)) wbuf[pos++] = keys[j];
+    wcnt += __shfl_sync(0xffffffffu, incl, 31);
   }
   flush();
   for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
@@ -456,10 +457,10 @@ __global__ void __launch_bounds__(THREADS) compact_kernel(const SegTable st, con
     const long long base = (cid - ch.cstart[s]) * CHUNK;
     const float* p = st.ptr[s];
     const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
-    unsigned int keys[8];
+    unsigned int keys[4 * ITERS];
     unsigned int hits = 0;  // bit j set: keys[j] belongs to the bin
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
+    for (int it = 0; it < ITERS; ++it) {
       const long long i = base + ((long long)it * THREADS + threadIdx.x) * 4;
       float v[4] = {0.f, 0.f, 0.f, 0.f};
       int nvalid = 0;
@@ -495,7 +496,7 @@ __global__ void __launch_bounds__(THREADS) compact_kernel(const SegTable st, con
     __syncthreads();
     unsigned int pos = s_base + s_wsum[wid] + (incl - cnt);
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int j = 0; j < 4 * ITERS; ++j)
       if (hits & (1u << j)) {
         if (pos < cand_cap) cand[pos] = keys[j];
         ++pos;
@@ -609,7 +610,7 @@ __global__ void __launch_bounds__(THREADS) mask_kernel(const SegTable st, const 
     float* m = st.out[s];
     const bool aligned = ((reinterpret_cast<uintptr_t>(w) | (WRITE_MASK ? reinterpret_cast<uintptr_t>(m) : 0)) & 15) == 0;
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
+    for (int it = 0; it < ITERS; ++it) {
       const long long i = base + ((long long)it * THREADS + threadIdx.x) * 4;
       if (aligned && i + 4 <= size) {
         const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(w + i));
@@ -651,7 +652,7 @@ __global__ void __launch_bounds__(THREADS) apply_masks_kernel(const SegTable st,
     const float* m = st.out[s];
     const bool aligned = ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(m)) & 15) == 0;
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
+    for (int it = 0; it < ITERS; ++it) {
       const long long i = base + ((long long)it * THREADS + threadIdx.x) * 4;
       if (aligned && i + 4 <= size) {
         const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(w + i));
@@ -684,7 +685,7 @@ __global__ void __launch_bounds__(THREADS) count_zeros_kernel(const SegTable st,
     const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
     unsigned int c = 0;
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
+    for (int it = 0; it < ITERS; ++it) {
       const long long i = base + ((long long)it * THREADS + threadIdx.x) * 4;
       if (aligned && i + 4 <= size) {
         const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(p + i));
@@ -711,7 +712,7 @@ __global__ void __launch_bounds__(THREADS) masked_residual_kernel(const SegTable
     const float* w = st.ptr[s];
     const float* m = st.out[s];
     double acc = 0.0;
-    for (int it = 0; it < 2; ++it) {
+    for (int it = 0; it < ITERS; ++it) {
       const long long i = base + ((long long)it * THREADS + threadIdx.x) * 4;
       for (int j = 0; j < 4; ++j)
         if (i + j < size) acc += (double)(w[i + j] * fabsf(m[i + j] - 1.f));
@@ -783,7 +784,7 @@ extern "C" int mc_kth_abs_select(const float* const* h_seg_ptrs, const int64_t* 
   set_rank_kernel<<<1, 1, 0, stream>>>(state, fast, (unsigned long long)k);
   MC_LAUNCH_CHECK("set_rank_kernel");
   const int grid = stream_grid(ch.cstart[nseg]);
-  const int cgrid = mc_num_sms();
+  const int cgrid = 32;  // candidate-list kernels: every block flushes up to 4096 bins with global atomics
   const int need_b = (gamma != 0.f && k + 1 < n) ? 1 : 0;
   // MCB200_SELECT_EXACT=1 forces the radix path (used by the tests to cover the fallback on large inputs)
   const char* force_exact = getenv("MCB200_SELECT_EXACT");
