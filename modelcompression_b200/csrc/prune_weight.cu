@@ -293,6 +293,22 @@ __global__ void __launch_bounds__(THREADS) count_compact_kernel(const SegTable s
   }
 }
 
+// grid-stride visit of the candidate list with 8 independent loads in flight per thread (the plain loop is bound by
+// one L2 round trip per element)
+template <typename F>
+__device__ __forceinline__ void for_each_cand(const unsigned int* __restrict__ cand, unsigned int m, F f) {
+  const unsigned int stride = gridDim.x * THREADS;
+  unsigned int i = blockIdx.x * THREADS + threadIdx.x;
+  for (; i + 7 * stride < m; i += 8 * stride) {
+    unsigned int k[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) k[u] = cand[i + u * stride];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) f(k[u]);
+  }
+  for (; i < m; i += stride) f(cand[i]);
+}
+
 // Candidate-list histograms of the fast path.  Candidates all lie in [lo, hi], so bins are taken on d = key - lo:
 // level A = d >> sA with sA chosen so that (hi-lo) >> sA < 4096 (candidates spread over the bins instead of piling
 // into the two or three bins their common high bits select), level B = the next min(12, sA) bits, level C the rest.
@@ -319,8 +335,7 @@ __global__ void __launch_bounds__(THREADS) histA_kernel(SelState* state, const u
   for (int i = threadIdx.x; i < BINS0; i += THREADS) sh[i] = 0;
   __syncthreads();
   const unsigned int m = state->cand_count;
-  for (unsigned int i = blockIdx.x * THREADS + threadIdx.x; i < m; i += gridDim.x * THREADS)
-    atomicAdd(&sh[fast_rel(cand[i], lo) >> sA], 1u);
+  for_each_cand(cand, m, [&](unsigned int key) { atomicAdd(&sh[fast_rel(key, lo) >> sA], 1u); });
   __syncthreads();
   for (int i = threadIdx.x; i < BINS0; i += THREADS)
     if (sh[i]) atomicAdd(&state->hist0[i], sh[i]);
@@ -344,10 +359,10 @@ __global__ void __launch_bounds__(THREADS) histB_kernel(SelState* state, const u
   }
   for (int i = threadIdx.x; i < BINS1; i += THREADS) sh[i] = 0;
   __syncthreads();
-  for (unsigned int i = blockIdx.x * THREADS + threadIdx.x; i < m; i += gridDim.x * THREADS) {
-    const unsigned int d = fast_rel(cand[i], lo);
+  for_each_cand(cand, m, [&](unsigned int key) {
+    const unsigned int d = fast_rel(key, lo);
     if ((d >> sA) == bin0) atomicAdd(&sh[(d >> sB) & (BINS1 - 1) & ((1u << (sA - sB)) - 1u)], 1u);
-  }
+  });
   __syncthreads();
   for (int i = threadIdx.x; i < BINS1; i += THREADS)
     if (sh[i]) atomicAdd(&state->hist1[i], sh[i]);
@@ -373,10 +388,10 @@ __global__ void __launch_bounds__(THREADS) histC_kernel(SelState* state, const u
   __syncthreads();
   if (sB > 0) {  // sB <= 7 (d < 2^31, sA <= 19): at most 128 bins
     const unsigned int maskB = (1u << (sA - sB)) - 1u;
-    for (unsigned int i = blockIdx.x * THREADS + threadIdx.x; i < m; i += gridDim.x * THREADS) {
-      const unsigned int d = fast_rel(cand[i], lo);
+    for_each_cand(cand, m, [&](unsigned int key) {
+      const unsigned int d = fast_rel(key, lo);
       if ((d >> sA) == bin0 && ((d >> sB) & maskB) == bin1) atomicAdd(&sh[d & ((1u << sB) - 1u)], 1u);
-    }
+    });
     __syncthreads();
     if (threadIdx.x < BINS2 && sh[threadIdx.x]) atomicAdd(&state->hist2[threadIdx.x], sh[threadIdx.x]);
   }
@@ -784,7 +799,7 @@ extern "C" int mc_kth_abs_select(const float* const* h_seg_ptrs, const int64_t* 
   set_rank_kernel<<<1, 1, 0, stream>>>(state, fast, (unsigned long long)k);
   MC_LAUNCH_CHECK("set_rank_kernel");
   const int grid = stream_grid(ch.cstart[nseg]);
-  const int cgrid = 32;  // candidate-list kernels: every block flushes up to 4096 bins with global atomics
+  const int cgrid = mc_num_sms();
   const int need_b = (gamma != 0.f && k + 1 < n) ? 1 : 0;
   // MCB200_SELECT_EXACT=1 forces the radix path (used by the tests to cover the fallback on large inputs)
   const char* force_exact = getenv("MCB200_SELECT_EXACT");
