@@ -145,16 +145,33 @@ __device__ void smem_select2(const unsigned int* keys, int n, unsigned int rank0
       if ((key & mask) == prefix1) atomicAdd(&s_hist[256 + d], 1u);
     }
     __syncthreads();
-    if (threadIdx.x < 2) {
-      const unsigned int* h = s_hist + threadIdx.x * 256;
-      const unsigned int rank = threadIdx.x ? r1 : r0;
-      unsigned int cum = 0, b = 0;
-      for (; b < 255; ++b) {
-        if (cum + h[b] > rank) break;
-        cum += h[b];
+    {  // warps 0 and 1 locate the bins of the two ranks with a shuffle prefix sum (8 bins per lane)
+      const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      if (wid < 2) {
+        const unsigned int* h = s_hist + wid * 256;
+        const unsigned int rank = wid ? r1 : r0;
+        unsigned int c[8], tot = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { c[j] = h[lane * 8 + j]; tot += c[j]; }
+        unsigned int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const unsigned int excl = incl - tot;
+        const unsigned int who = __ballot_sync(0xffffffffu, rank >= excl && rank < incl);
+        const int src = who ? (__ffs(who) - 1) : 31;
+        if (lane == src) {
+          unsigned int cum = excl, b = 0;
+          for (; b < 7; ++b) {
+            if (cum + c[b] > rank) break;
+            cum += c[b];
+          }
+          s_pick[wid * 2] = lane * 8 + b;
+          s_pick[wid * 2 + 1] = rank - cum;
+        }
       }
-      s_pick[threadIdx.x * 2] = b;
-      s_pick[threadIdx.x * 2 + 1] = rank - cum;
     }
     __syncthreads();
     prefix0 |= s_pick[0] << shift;
@@ -174,6 +191,7 @@ __global__ void __launch_bounds__(1024) sample_pivot_kernel(const SegTable st, S
   __shared__ unsigned int s_hist[512];
   __shared__ unsigned int s_pick[4];
   const int S = (n < SAMPLE) ? (int)n : SAMPLE;
+#pragma unroll 8
   for (int i = threadIdx.x; i < S; i += blockDim.x) {
     // stratified: one element from each of S equal slices, position inside the slice hashed
     // S == SAMPLE == 2^14 whenever n >= SAMPLE (i*n < 2^14 * 2^40 fits 64 bits); otherwise every element is sampled

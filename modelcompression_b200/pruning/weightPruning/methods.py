@@ -33,6 +33,30 @@ def percentile_rank(n, pruning_perc, dtype):
     return int(previous), float(gamma)
 
 
+_WS = {}
+
+
+def _workspace(dev, nbytes):
+    """Scratch buffer kept between calls (the select needs up to 4n bytes; allocating 200 MB per call costs more
+    than the kernels)."""
+    key = (dev.type, dev.index)
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = _WS[key] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    return ws
+
+
+def _empty_like_all(params):
+    """One allocation for all masks, returned as per-parameter views (23 allocator calls -> 1)."""
+    sizes = [((p.numel() + 3) // 4) * 4 for p in params]  # keep every view 16-byte aligned
+    flat = torch.empty(sum(sizes), dtype=torch.float32, device=params[0].device)
+    out, off = [], 0
+    for p, sz in zip(params, sizes):
+        out.append(flat[off:off + p.numel()].view(p.shape))
+        off += sz
+    return out
+
+
 def _prunable(model, conv_only):
     params = []
     for p in model.parameters():
@@ -55,7 +79,7 @@ def weight_threshold(params, pruning_perc):
     if len(segs) > _lib.MC_MAX_SEGMENTS:  # rare: more tensors than one launch takes -> select on a flat copy
         segs = [torch.cat([p.reshape(-1) for p in params])]
     ws_bytes = lib.mc_workspace_bytes_kth_abs_select(n)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    ws = _workspace(dev, ws_bytes)
     out3 = torch.empty(3, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         _lib.check(lib.mc_kth_abs_select(_lib.ptr_array(segs), _lib.int64_array([t.numel() for t in segs]), len(segs),
@@ -77,7 +101,7 @@ def weight_prune(model, pruning_perc):
     if not params:
         return []
     out3 = weight_threshold(params, pruning_perc)
-    masks = [torch.empty_like(p) for p in params]
+    masks = _empty_like_all(params)
     dev = params[0].device
     with torch.cuda.device(dev):
         for lo in range(0, len(params), _lib.MC_MAX_SEGMENTS):
@@ -124,7 +148,7 @@ def quick_filter_prune(model, pruning_perc, return_keep=False):
     n = values.numel()
     k, gamma = percentile_rank(n, pruning_perc, np.float64)
     thr = torch.empty(1, dtype=torch.float64, device=dev)
-    masks = [torch.empty_like(p) for p in params]
+    masks = _empty_like_all(params)
     keep = torch.empty(n, dtype=torch.uint8, device=dev)
     O = [p.shape[0] for p in params]
     per = [p.numel() // p.shape[0] for p in params]
