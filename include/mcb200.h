@@ -53,6 +53,20 @@ int mc_kth_abs_select(const float* const* h_seg_ptrs, const int64_t* h_seg_sizes
                       void* d_ws, size_t ws_bytes, void* stream);
 size_t mc_workspace_bytes_kth_abs_select(int64_t n_total);
 
+/* The whole of weight_prune in ONE cooperative launch: the order statistics as above (same d_out3) AND
+ * mask[i] = (|w[i]| > thr) ? 1.f : 0.f for every segment.  Fast path: pivots from a sample bracket the rank-k key,
+ * one pass over W writes provisional masks and collects the bracketed ~5 % as candidates, the exact rank is resolved
+ * on the candidates and only their masks are fixed up (HBM traffic 8n bytes: read W once, write masks once).  A missed
+ * bracket falls back, inside the same launch, to an exact 12+10+9-bit radix select and a full mask pass.
+ * Workspace: mc_workspace_bytes_kth_abs_select(n).                                                    */
+int mc_weight_prune_masks(const float* const* h_w_ptrs, float* const* h_mask_ptrs, const int64_t* h_seg_sizes,
+                          int nseg, int64_t k, float gamma, float* d_out3, void* d_ws, size_t ws_bytes,
+                          void* stream);
+/* Diagnostics (synchronises the stream): 1 if the last select on this workspace took the sample-pivot fast path. */
+int mc_debug_select_used_fast(const void* d_ws, void* stream);
+/* Diagnostics (synchronises): globaltimer (ns) of block 0 at the phase boundaries of the last launch, 12 values. */
+int mc_debug_select_tstamps(const void* d_ws, unsigned long long* h_out12, void* stream);
+
 /* mask[i] = (|w[i]| > *d_thr) ? 1.f : 0.f for every segment; if apply!=0 also w[i] *= mask[i]
  * (set_mask).  h_mask_ptrs may be NULL when apply!=0 (apply only).                                  */
 int mc_mask_apply_gt(float* const* h_w_ptrs, float* const* h_mask_ptrs, const int64_t* h_seg_sizes,

@@ -38,6 +38,10 @@ _SIGNATURES = {
     "mc_kth_abs_select": (c_int, [POINTER(c_void_p), POINTER(c_int64), c_int, c_int64, c_float, c_void_p,
                                   c_void_p, c_size_t, c_void_p]),
     "mc_workspace_bytes_kth_abs_select": (c_size_t, [c_int64]),
+    "mc_weight_prune_masks": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64), c_int, c_int64, c_float,
+                                      c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mc_debug_select_used_fast": (c_int, [c_void_p, c_void_p]),
+    "mc_debug_select_tstamps": (c_int, [c_void_p, c_void_p, c_void_p]),
     "mc_mask_apply_gt": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64), c_int, c_void_p, c_int,
                                  c_void_p]),
     "mc_apply_masks": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64), c_int, c_void_p]),

@@ -5,11 +5,10 @@
 // MaskedConv2d.set_mask (src/pruning/weightPruning/layers.py:41-47); plus the full-tensor scans of
 // prune_rate / are_masks_consistent (src/pruning/weightPruning/utils.py:59-93,122-133).
 //
-// Selection is exact: |w| >= 0, so its fp32 bit pattern is monotone as uint32 and the k-th smallest value is
-// found by a 12+12+7-bit radix select.  Pass 0 histograms the top 12 bits of every element (one read of W),
-// pass 1 compacts the elements of the selected bin into the workspace, passes 2..3 histogram the remaining
-// bits on the (small) candidate list.  HBM traffic: 2 reads of W for the select + read W / write mask.
+// Selection is exact: |w| >= 0, so its fp32 bit pattern is monotone as uint32 and order statistics can be found by
+// integer radix/histogram selection on the bit patterns (weight_prune_kernel below: one cooperative launch).
 #include <stdlib.h>
+#include <cooperative_groups.h>
 #include "common.cuh"
 
 namespace {
@@ -18,29 +17,6 @@ constexpr int THREADS = 256;
 constexpr int ITERS = 4;                  // float4 loads per thread and block-iteration (all issued before use)
 constexpr int CHUNK = THREADS * 4 * ITERS;  // elements per block-iteration
 constexpr int BINS0 = 4096;         // bits [30:19]
-constexpr int BINS1 = 4096;         // bits [18:7]
-constexpr int BINS2 = 128;          // bits [6:0]
-
-// device-side state of one selection (lives at the head of the workspace)
-struct SelState {
-  unsigned int hist0[BINS0];
-  unsigned int hist1[BINS1];
-  unsigned int hist2[BINS2];
-  unsigned long long k;         // requested rank (0-based)
-  unsigned long long rem1;      // rank inside bin0
-  unsigned long long rem2;      // rank inside bin1
-  unsigned int bin0, bin1;
-  unsigned int cand_count;      // number of compacted candidates
-  unsigned int key_a;           // bit pattern of sorted[k]
-  unsigned long long cnt_le;    // #elements with key <= key_a (only when b is needed)
-  unsigned int min_gt;          // min key > key_a
-  unsigned int has_nan;         // any NaN input: np.percentile returns nan
-  // sample-pivot fast path
-  unsigned int lo_key, hi_key;  // pivots from the sample: sorted[k] lies in [lo_key, hi_key] unless the sample lied
-  unsigned long long below;     // #elements with key < lo_key
-  unsigned int done;            // 1: the fast path produced key_a (the exact radix path is skipped)
-  unsigned int pad2;
-};
 
 struct Chunks {
   long long cstart[MC_MAX_SEGMENTS + 1];  // prefix of per-segment chunk counts
@@ -82,166 +58,479 @@ __device__ __forceinline__ void for_each_element(const SegTable& st, const Chunk
   }
 }
 
-// Block-wide: find the bin holding rank `k` in hist[nbins]; returns bin, and the rank inside that bin.
-// Executed redundantly by every block that needs it (nbins <= 4096: 16 bins per thread).
-template <int NBINS>
-__device__ void block_find_bin(const unsigned int* __restrict__ hist, unsigned long long k, unsigned int* s_bin,
-                               unsigned long long* s_rem) {
-  __shared__ unsigned long long s_part[THREADS];
-  constexpr int PER = (NBINS + THREADS - 1) / THREADS;
-  unsigned long long local = 0;
-  const int b0 = threadIdx.x * PER;
-  for (int j = 0; j < PER; ++j)
-    if (b0 + j < NBINS) local += hist[b0 + j];
-  s_part[threadIdx.x] = local;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned long long cum = 0;
-    int t = 0;
-    for (; t < THREADS; ++t) {
-      if (cum + s_part[t] > k) break;
-      cum += s_part[t];
-    }
-    if (t == THREADS) t = THREADS - 1;  // k beyond total: clamp (caller validates k < n)
-    int bin = t * PER;
-    const int bend = (t * PER + PER < NBINS) ? t * PER + PER : NBINS;
-    for (; bin < bend - 1; ++bin) {
-      if (cum + hist[bin] > k) break;
-      cum += hist[bin];
-    }
-    *s_bin = (unsigned int)bin;
-    *s_rem = k - cum;
+// ---------------------------------------------------------------------------------------------------------------
+// ONE cooperative kernel does the whole of weight_prune (select + masks), with grid-wide barriers between phases:
+//
+//   S  a stratified sample of SAMPLE keys is ranked by counting (whole grid) to get three pivots
+//      lo <= mid <= hi: [lo, hi] brackets the rank-k key with high probability (+-4.5 sigma of the sample rank), mid
+//      is the sample's estimate of it.
+//   P  ONE pass over W: count keys < lo, append (key, element index) of the keys in [lo, hi] (~5 % of n) to the
+//      candidate list (and bin them for the first histogram level), and write the PROVISIONAL mask |w| > mid —
+//      final for everything outside the bracket.
+//   R  exact rank inside the candidates: 10-bit histogram levels on (key - lo), all from L2.
+//   F  fix-up: the candidates on which (|w| > mid) and (|w| > thr) disagree (~0.5 % of n) are rewritten.
+//
+// HBM traffic on this path: read W once + write the masks once = 8n bytes (SURVEY.md §8d charges 12n).
+// If the bracket missed (k outside, non-finite values present, candidate list overflow) the same kernel falls through
+// to the EXACT path: 12-bit histogram of all keys -> compact the selected bin -> 10-bit levels -> full mask pass.  The
+// result is always the exact order statistic; only the time differs.
+constexpr int SAMPLE = 4096;
+constexpr int SAMPLE_LOG2 = 12;
+constexpr int LVL_BITS = 10;
+constexpr int LVL_BINS = 1 << LVL_BITS;
+constexpr int MAX_LVLS = 4;     // keys are < 2^31: 10+10+10+1
+constexpr int NWARPS = THREADS / 32;
+constexpr int STG = 256;        // staged candidates per warp in the fast pass
+constexpr int STG_X = 640;      // ... in the exact-path compaction (a warp-iteration appends at most 32*4*ITERS = 512)
+constexpr int SMEM_WORDS = 2 * NWARPS * STG_X;  // 40 KB, carved differently per phase
+constexpr int MAXB = 2048;      // max blocks of the cooperative grid (148 SMs x <= 8 resident blocks, with headroom)
+
+// Global atomics are avoided on purpose: atomics to one 128-byte line serialise in L2 at ~5 ns each (measured: 600 K
+// histogram flushes to 32 lines cost 110 us).  Every block therefore owns a private slice of the candidate list and
+// publishes its counts / first-level histogram with plain stores; sums are taken after the grid barrier.
+struct SelState {
+  unsigned int lvl_hist[2][MAX_LVLS][LVL_BINS];  // [0] fast attempt, [1] exact attempt
+  unsigned int hist0[BINS0];                     // exact path: top 12 bits of every key
+  unsigned int sample[SAMPLE];
+  unsigned int rank_lt[SAMPLE], rank_le[SAMPLE];  // #sample keys < / <= sample[i]
+  unsigned int blk_cnt[2][MAXB];       // candidates held by each block ([0] fast, [1] exact)
+  unsigned long long blk_below[MAXB];  // fast: #keys < lo seen by each block
+  unsigned long long cnt_le[2];  // #keys <= key_a (fast: among candidates; exact: all)
+  unsigned int min_gt[2];        // ~(min key > key_a), 0 = none (atomicMax)
+  unsigned int lo_key, mid_key, hi_key;
+  unsigned int overflow;         // a block's candidate slice overflowed (fast path gives up)
+  unsigned int has_nan;          // a NaN/Inf was seen (fast pass: maybe; exact pass: NaN for sure)
+  unsigned int used_fast;        // diagnostics: 1 when the fast path produced the result
+  unsigned long long tstamp[12]; // diagnostics: globaltimer of block 0 at the phase boundaries
+};
+
+__device__ __forceinline__ void stamp(SelState* st, int i) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    st->tstamp[i] = t;
   }
+}
+
+namespace cg = cooperative_groups;
+
+// Block-wide: bin of hist[NBINS] holding rank `rank`, and the rank inside it.  hist was produced by atomics of other
+// SMs before a grid barrier: read through L2 (__ldcg).  Every block computes this redundantly.
+template <int NBINS>
+__device__ void find_bin(const unsigned int* hist, unsigned long long rank, unsigned int* bin_out,
+                         unsigned long long* rem_out) {
+  __shared__ unsigned long long s_w[NWARPS];
+  __shared__ unsigned int s_bin;
+  __shared__ unsigned long long s_rem;
+  constexpr int PER = NBINS / THREADS;
+  static_assert(NBINS % THREADS == 0, "bins per thread");
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned int c[PER];
+  unsigned long long tot = 0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) { c[j] = __ldcg(hist + threadIdx.x * PER + j); tot += c[j]; }
+  unsigned long long incl = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_w[wid] = incl;
+  if (threadIdx.x == 0) { s_bin = NBINS - 1; s_rem = 0; }  // rank beyond the total: clamp
+  __syncthreads();
+  unsigned long long off = 0;
+  for (int w = 0; w < wid; ++w) off += s_w[w];
+  unsigned long long cum = off + incl - tot;
+  if (rank >= cum && rank < cum + tot) {
+    int j = 0;
+    for (; j < PER - 1; ++j) {
+      if (cum + c[j] > rank) break;
+      cum += c[j];
+    }
+    s_bin = threadIdx.x * PER + j;
+    s_rem = rank - cum;
+  }
+  __syncthreads();
+  *bin_out = s_bin;
+  *rem_out = s_rem;
   __syncthreads();
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Fast path.  A strided sample of S = 16384 elements gives two pivots lo <= hi that bracket the rank-k element with
-// overwhelming probability (+-6 sigma of the sample rank); ONE pass over the data then counts the elements below lo
-// and compacts those in [lo, hi] (~5 % of n); the exact rank is resolved on that small list.  If the bracket turns out
-// wrong (k not inside), `done` stays 0 and the exact radix path below runs instead — the result is always exact.
-constexpr int SAMPLE = 16384;
-
-__device__ __forceinline__ unsigned int load_key_at(const SegTable& st, long long g) {
+// segment holding global element index g (last segment with start <= g)
+__device__ __forceinline__ int seg_of(const SegTable& st, long long g) {
   int lo = 0, hi = st.nseg - 1;
-  while (lo < hi) {  // last segment with start <= g
+  while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
     if (st.start[mid] <= g) lo = mid; else hi = mid - 1;
   }
-  return absbits(st.ptr[lo][g - st.start[lo]]);
+  return lo;
 }
 
-// block-wide radix select of two ranks over `n` uint keys in shared memory (8 bits per pass)
-__device__ void smem_select2(const unsigned int* keys, int n, unsigned int rank0, unsigned int rank1,
-                             unsigned int* s_hist /*[2][256]*/, unsigned int* s_pick /*[4]*/, unsigned int* out0,
-                             unsigned int* out1) {
-  unsigned int prefix0 = 0, prefix1 = 0, mask = 0, r0 = rank0, r1 = rank1;
-  for (int shift = 24; shift >= 0; shift -= 8) {
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_hist[i] = 0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const unsigned int key = keys[i], d = (key >> shift) & 255u;
-      if ((key & mask) == prefix0) atomicAdd(&s_hist[d], 1u);
-      if ((key & mask) == prefix1) atomicAdd(&s_hist[256 + d], 1u);
-    }
-    __syncthreads();
-    {  // warps 0 and 1 locate the bins of the two ranks with a shuffle prefix sum (8 bins per lane)
-      const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-      if (wid < 2) {
-        const unsigned int* h = s_hist + wid * 256;
-        const unsigned int rank = wid ? r1 : r0;
-        unsigned int c[8], tot = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { c[j] = h[lane * 8 + j]; tot += c[j]; }
-        unsigned int incl = tot;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += t;
-        }
-        const unsigned int excl = incl - tot;
-        const unsigned int who = __ballot_sync(0xffffffffu, rank >= excl && rank < incl);
-        const int src = who ? (__ffs(who) - 1) : 31;
-        if (lane == src) {
-          unsigned int cum = excl, b = 0;
-          for (; b < 7; ++b) {
-            if (cum + c[b] > rank) break;
-            cum += c[b];
-          }
-          s_pick[wid * 2] = lane * 8 + b;
-          s_pick[wid * 2 + 1] = rank - cum;
+// ---- S: pivots by rank counting ------------------------------------------------------------------------------
+// stratified sample: element i is taken from the i-th of SAMPLE equal slices of the data, position hashed
+__device__ __forceinline__ unsigned int sample_key(const SegTable& st, long long n, int i) {
+  const long long a = ((long long)i * n) >> SAMPLE_LOG2, b = ((long long)(i + 1) * n) >> SAMPLE_LOG2;
+  unsigned int h = (unsigned int)i * 2654435761u;
+  h ^= h >> 15;
+  const long long g = a + (long long)(h % (unsigned int)((b - a) > 0 ? (b - a) : 1));
+  const int s = seg_of(st, g);
+  return absbits(st.ptr[s][g - st.start[s]]);
+}
+
+// The whole grid ranks the sample by counting (S^2 = 16.7 M compares, ~100 per thread): block b compares its 256 keys
+// (key group b % 16) against slice b / 16 of the sample and adds the counts with global atomics.  A radix select in
+// one block (8 warps, dependent shuffle/atomic chains) costs 30-50 us; this costs ~5.
+__device__ void sample_rank_count(const SegTable& st, long long n, SelState* state, unsigned int* s_slice) {
+  constexpr int GROUPS = SAMPLE / THREADS;  // 16
+  const int nslices = (int)gridDim.x / GROUPS;
+  if (nslices == 0) {  // tiny grid: every block handles whole key groups against the full sample
+    for (int grp = blockIdx.x; grp < GROUPS; grp += gridDim.x) {
+      const int i = grp * THREADS + threadIdx.x;
+      const unsigned int ki = sample_key(st, n, i);
+      state->sample[i] = ki;
+      unsigned int lt = 0, le = 0;
+      for (int j0 = 0; j0 < SAMPLE; j0 += THREADS) {
+        __syncthreads();
+        s_slice[threadIdx.x] = sample_key(st, n, j0 + threadIdx.x);
+        __syncthreads();
+        for (int j = 0; j < THREADS; ++j) {
+          const unsigned int kj = s_slice[j];
+          lt += kj < ki;
+          le += kj <= ki;
         }
       }
+      state->rank_lt[i] = lt;
+      state->rank_le[i] = le;
     }
-    __syncthreads();
-    prefix0 |= s_pick[0] << shift;
-    r0 = s_pick[1];
-    prefix1 |= s_pick[2] << shift;
-    r1 = s_pick[3];
-    mask |= 255u << shift;
-    __syncthreads();
+    return;
   }
-  *out0 = prefix0;
-  *out1 = prefix1;
+  const int grp = blockIdx.x % GROUPS, slice = blockIdx.x / GROUPS;
+  if (slice >= nslices) return;
+  const int len = (SAMPLE + nslices - 1) / nslices;  // <= THREADS because nslices >= 1 ... guarded below
+  const int j0 = slice * len;
+  const int jn = (j0 + len < SAMPLE ? j0 + len : SAMPLE) - j0;
+  const int i = grp * THREADS + threadIdx.x;
+  const unsigned int ki = sample_key(st, n, i);
+  for (int j = threadIdx.x; j < jn; j += THREADS) s_slice[j] = sample_key(st, n, j0 + j);
+  if (slice == 0) state->sample[i] = ki;
+  __syncthreads();
+  unsigned int lt = 0, le = 0;
+  int j = 0;
+  for (; j + 4 <= jn; j += 4) {
+    const uint4 kq = *reinterpret_cast<const uint4*>(s_slice + j);
+    lt += (kq.x < ki) + (kq.y < ki) + (kq.z < ki) + (kq.w < ki);
+    le += (kq.x <= ki) + (kq.y <= ki) + (kq.z <= ki) + (kq.w <= ki);
+  }
+  for (; j < jn; ++j) {
+    const unsigned int kj = s_slice[j];
+    lt += kj < ki;
+    le += kj <= ki;
+  }
+  if (lt) atomicAdd(&state->rank_lt[i], lt);
+  if (le) atomicAdd(&state->rank_le[i], le);
 }
 
-__global__ void __launch_bounds__(1024) sample_pivot_kernel(const SegTable st, SelState* state, long long n,
-                                                            unsigned long long k) {
-  extern __shared__ unsigned int s_keys[];  // [SAMPLE]
-  __shared__ unsigned int s_hist[512];
-  __shared__ unsigned int s_pick[4];
-  const int S = (n < SAMPLE) ? (int)n : SAMPLE;
-#pragma unroll 8
-  for (int i = threadIdx.x; i < S; i += blockDim.x) {
-    // stratified: one element from each of S equal slices, position inside the slice hashed
-    // S == SAMPLE == 2^14 whenever n >= SAMPLE (i*n < 2^14 * 2^40 fits 64 bits); otherwise every element is sampled
-    const long long lo = (S == SAMPLE) ? (((long long)i * n) >> 14) : (long long)i;
-    const long long hi = (S == SAMPLE) ? (((long long)(i + 1) * n) >> 14) : (long long)i + 1;
-    unsigned int h = (unsigned int)i * 2654435761u;
-    h ^= h >> 15;
-    const long long g = lo + (long long)(h % (unsigned int)((hi - lo) > 0 ? (hi - lo) : 1));
-    s_keys[i] = load_key_at(st, g);
+// after the grid barrier: every block finds the sample keys holding three ranks (rank_lt <= r < rank_le)
+__device__ void sample_pick(const SelState* state, const unsigned int (&ranks)[3], unsigned int (&piv)[3]) {
+  __shared__ unsigned int s_piv[3];
+  if (threadIdx.x < 3) s_piv[threadIdx.x] = 0;
+  __syncthreads();
+  for (int i0 = threadIdx.x * 4; i0 < SAMPLE; i0 += THREADS * 4) {
+    const uint4 lt = __ldcg(reinterpret_cast<const uint4*>(state->rank_lt + i0));
+    const uint4 le = __ldcg(reinterpret_cast<const uint4*>(state->rank_le + i0));
+    const unsigned int l[4] = {lt.x, lt.y, lt.z, lt.w}, e[4] = {le.x, le.y, le.z, le.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        if (l[u] <= ranks[q] && ranks[q] < e[u]) s_piv[q] = __ldcg(state->sample + i0 + u);  // equal keys: same value
   }
   __syncthreads();
-  // sample ranks bracketing k: m = k*S/n, +- (6 sigma + 8), sigma = sqrt(S q (1-q))
-  const double q = (double)k / (double)n;
-  const double m = q * S;
-  const double sig = sqrt((double)S * q * (1.0 - q));
-  const double d = 6.0 * sig + 8.0;
-  long long rlo = (long long)floor(m - d), rhi = (long long)ceil(m + d);
-  const bool open_lo = rlo <= 0, open_hi = rhi >= S - 1;
-  if (rlo < 0) rlo = 0;
-  if (rhi > S - 1) rhi = S - 1;
-  unsigned int klo, khi;
-  smem_select2(s_keys, S, (unsigned int)rlo, (unsigned int)rhi, s_hist, s_pick, &klo, &khi);
-  if (threadIdx.x == 0) {
-    state->lo_key = open_lo ? 0u : klo;
-    state->hi_key = open_hi ? 0xffffffffu : khi;
-  }
+  piv[0] = s_piv[0];
+  piv[1] = s_piv[1];
+  piv[2] = s_piv[2];
+  __syncthreads();
 }
 
-// one pass over the data: count keys < lo, compact keys in [lo, hi].  Each WARP stages its hits in its own slice of
-// shared memory (no block barrier in the loop) and flushes the slice to the global candidate list with one global
-// atomic when it could overflow, so no iteration waits on an L2 round trip or on the other warps.
-constexpr int WSTAGE = 1024;               // keys per warp slice; one warp-iteration appends at most 32*4*ITERS = 512
-__global__ void __launch_bounds__(THREADS) count_compact_kernel(const SegTable st, const Chunks ch, SelState* state,
-                                                                unsigned int* __restrict__ cand,
-                                                                unsigned long long cand_cap) {
-  __shared__ unsigned int s_buf[(THREADS / 32) * WSTAGE];
-  __shared__ unsigned long long s_below[THREADS / 32];
-  const unsigned int lo = state->lo_key, hi = state->hi_key;
+// visit the block's own candidate slice, 8 independent loads in flight per thread
+template <typename F>
+__device__ __forceinline__ void for_each_own(const unsigned int* __restrict__ seg, unsigned int cnt, F f) {
+  unsigned int i = threadIdx.x;
+  for (; i + 7u * THREADS < cnt; i += 8 * THREADS) {
+    unsigned int k[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) k[u] = __ldcg(seg + i + u * THREADS);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) f(k[u], i + u * THREADS);
+  }
+  for (; i < cnt; i += THREADS) f(__ldcg(seg + i), i);
+}
+
+// first-level geometry of the candidate histogram: keys rel = key - lo in [0, width]
+__device__ __forceinline__ int level0_shift(unsigned int width) {
+  const int nb = 32 - __clz((int)width);
+  return nb - (nb < LVL_BITS ? nb : LVL_BITS);
+}
+
+// sum over the blocks of a per-block value published before the last grid barrier
+template <typename T>
+__device__ unsigned long long grid_total(const T* per_block) {
+  __shared__ unsigned long long s_part[NWARPS];
+  __shared__ unsigned long long s_tot;
+  unsigned long long v = 0;
+  for (unsigned int b = threadIdx.x; b < gridDim.x; b += THREADS) v += (unsigned long long)__ldcg(per_block + b);
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < NWARPS; ++w) t += s_part[w];
+    s_tot = t;
+  }
+  __syncthreads();
+  const unsigned long long r = s_tot;
+  __syncthreads();
+  return r;
+}
+
+// Exact rank `rank` among the candidate keys held in the blocks' private slices (this block: seg[0..cnt)), all known
+// to lie in [lo, lo+width]: 10-bit histogram levels on rel = key - lo, most significant first.  Collective over the
+// grid (one barrier per level); returns the key.  Per-block histograms are merged with global atomics on the non-zero
+// bins (measured on B200: 740 blocks x 1024 atomics to the same 4 KB complete in ~6 us).
+// lvl0_ready: ghist level 0 was already accumulated before the last grid barrier (binned during the fast pass).
+__device__ unsigned int resolve_rank(cg::grid_group& grid, unsigned int* ghist /*[MAX_LVLS][LVL_BINS], zeroed*/,
+                                     const unsigned int* seg, unsigned int cnt, unsigned int lo, unsigned int width,
+                                     unsigned long long rank, unsigned int* s_hist /*[LVL_BINS]*/, bool lvl0_ready) {
+  int shift = 32 - __clz((int)width);  // width < 2^31; width == 0 -> no level needed
+  unsigned int prefix = 0;
+  for (int lvl = 0; shift > 0; ++lvl) {
+    const int bits = shift < LVL_BITS ? shift : LVL_BITS;
+    const int hi_shift = shift;  // rel >> hi_shift must equal the bits chosen so far
+    shift -= bits;
+    if (!(lvl == 0 && lvl0_ready)) {
+      for (int i = threadIdx.x; i < LVL_BINS; i += THREADS) s_hist[i] = 0;
+      __syncthreads();
+      const unsigned int bmask = (1u << bits) - 1u;
+      for_each_own(seg, cnt, [&](unsigned int key, unsigned int) {
+        const unsigned int rel = key - lo;
+        if ((rel >> hi_shift) == prefix) atomicAdd(&s_hist[(rel >> shift) & bmask], 1u);
+      });
+      __syncthreads();
+      for (int i = threadIdx.x; i < LVL_BINS; i += THREADS)
+        if (s_hist[i]) atomicAdd(&ghist[lvl * LVL_BINS + i], s_hist[i]);
+      grid.sync();
+    }
+    unsigned int bin;
+    unsigned long long rem;
+    find_bin<LVL_BINS>(ghist + lvl * LVL_BINS, rank, &bin, &rem);
+    prefix = (prefix << bits) | bin;
+    rank = rem;
+  }
+  return lo + prefix;
+}
+
+// ---- P: the one pass of the fast path.  ~12 instructions per element: the per-element work is three float compares
+// (|w| against the pivots), the mask select and two predicated bit-sets; candidate keys are recovered afterwards
+// from a per-lane copy of the 16 values in shared memory, only for the ~5 % that are candidates.
+template <bool WRITE_MASK>
+__device__ __forceinline__ void fast_pass(const SegTable& st, const Chunks& ch, SelState* state, unsigned int lo,
+                                          unsigned int mid, unsigned int hi, unsigned int* __restrict__ cand_key,
+                                          unsigned int* __restrict__ cand_idx, unsigned int cap, unsigned int* s_mem) {
+  __shared__ unsigned int s_cnt;         // candidates appended by this block
+  __shared__ unsigned int s_below[NWARPS];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  unsigned int* wbuf = s_buf + wid * WSTAGE;
+  // smem: [NWARPS][ITERS][32] float4 value copies | [NWARPS][STG] keys | [NWARPS][STG] indices | [LVL_BINS] level-0 bins
+  float4* vals = reinterpret_cast<float4*>(s_mem) + wid * (ITERS * 32);
+  unsigned int* wkeys = s_mem + NWARPS * ITERS * 32 * 4 + wid * STG;
+  unsigned int* widx = wkeys + NWARPS * STG;
+  unsigned int* s_lvl = s_mem + NWARPS * ITERS * 32 * 4 + 2 * NWARPS * STG;
+  static_assert(NWARPS * ITERS * 32 * 4 + 2 * NWARPS * STG + LVL_BINS <= SMEM_WORDS, "fast_pass smem carve-up");
+  const float lo_f = __uint_as_float(lo), mid_f = __uint_as_float(mid), hi_f = __uint_as_float(hi);
+  const int shiftA = level0_shift(hi - lo);
+  for (int i = threadIdx.x; i < LVL_BINS; i += THREADS) s_lvl[i] = 0;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
   unsigned int wcnt = 0;  // warp-uniform
-  unsigned long long below = 0;
-  bool saw_nan = false;
+  unsigned int below = 0;
+  float nanacc = 0.f;  // becomes NaN iff a NaN or Inf was seen (x*0)
   auto flush = [&]() {  // warp-wide
     unsigned int base = 0;
-    if (lane == 0 && wcnt) base = atomicAdd(&state->cand_count, wcnt);
+    if (lane == 0 && wcnt) base = atomicAdd(&s_cnt, wcnt);
     base = __shfl_sync(0xffffffffu, base, 0);
     __syncwarp();
     for (unsigned int i = lane; i < wcnt; i += 32)
-      if ((unsigned long long)base + i < cand_cap) cand[base + i] = wbuf[i];
+      if (base + i < cap) {
+        cand_key[base + i] = wkeys[i];
+        cand_idx[base + i] = widx[i];
+      }
+    __syncwarp();
+    wcnt = 0;
+  };
+  const long long nchunks = ch.cstart[st.nseg];
+  // software pipeline: the loads of chunk i+1 are issued before chunk i is processed, so every warp keeps 2 KB in
+  // flight while it computes (without this the pass is latency-bound at ~40 % of the HBM rate)
+  struct Where {
+    const float* p;
+    float* mk;
+    long long base, size, gstart;
+    bool full;
+  };
+  auto locate = [&](long long cid) {
+    Where w;
+    const int s = find_seg(ch, st.nseg, cid);
+    w.size = st.start[s + 1] - st.start[s];
+    w.gstart = st.start[s];
+    w.base = (cid - ch.cstart[s]) * CHUNK;
+    w.p = st.ptr[s];
+    w.mk = st.out[s];
+    const bool aligned = ((reinterpret_cast<uintptr_t>(w.p) | (WRITE_MASK ? reinterpret_cast<uintptr_t>(w.mk) : 0)) & 15) == 0;
+    w.full = aligned && w.base + CHUNK <= w.size;
+    return w;
+  };
+  float4 qn[ITERS];
+  Where nxt;
+  long long cid = blockIdx.x;
+  if (cid < nchunks) {
+    nxt = locate(cid);
+    if (nxt.full) {
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it)
+        qn[it] = ld_stream_f4(reinterpret_cast<const float4*>(nxt.p + nxt.base + ((long long)it * THREADS + threadIdx.x) * 4));
+    }
+  }
+  for (; cid < nchunks; cid += gridDim.x) {
+    const Where cur = nxt;
+    float4 q[ITERS];
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) q[it] = qn[it];
+    if (cid + gridDim.x < nchunks) {
+      nxt = locate(cid + gridDim.x);
+      if (nxt.full) {
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it)
+          qn[it] = ld_stream_f4(reinterpret_cast<const float4*>(nxt.p + nxt.base + ((long long)it * THREADS + threadIdx.x) * 4));
+      }
+    }
+    const long long size = cur.size, base = cur.base;
+    const float* p = cur.p;
+    float* mk = cur.mk;
+    if (!cur.full) {
+      // ragged chunk (segment tail / unaligned tensor): scalar, candidates appended one by one
+      for (long long i = base + threadIdx.x; i < size && i < base + CHUNK; i += THREADS) {
+        const float v = p[i];
+        const float a = fabsf(v);
+        nanacc = fmaf(v, 0.f, nanacc);
+        if (WRITE_MASK) mk[i] = a > mid_f ? 1.f : 0.f;
+        if (a < lo_f) ++below;
+        else if (a <= hi_f) {
+          const unsigned int key = __float_as_uint(a);
+          const unsigned int pos = atomicAdd(&s_cnt, 1u);
+          if (pos < cap) {
+            cand_key[pos] = key;
+            cand_idx[pos] = (unsigned int)(cur.gstart + i);
+          }
+          atomicAdd(&s_lvl[(key - lo) >> shiftA], 1u);
+        }
+      }
+      continue;
+    }
+    unsigned int hits = 0, ge = 0;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const float v[4] = {q[it].x, q[it].y, q[it].z, q[it].w};
+      float m4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = fabsf(v[j]);
+        nanacc = fmaf(v[j], 0.f, nanacc);
+        m4[j] = a > mid_f ? 1.f : 0.f;
+        const bool p1 = a >= lo_f;
+        if (p1) ge |= 1u << (it * 4 + j);
+        if (p1 && a <= hi_f) hits |= 1u << (it * 4 + j);
+      }
+      if (WRITE_MASK)
+        st_stream_f4(reinterpret_cast<float4*>(mk + base + ((long long)it * THREADS + threadIdx.x) * 4),
+                     make_float4(m4[0], m4[1], m4[2], m4[3]));
+      vals[it * 32 + lane] = q[it];
+    }
+    below += 4 * ITERS - __popc(ge);
+    const unsigned int cnt = __popc(hits);
+    unsigned int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const unsigned int tot = __shfl_sync(0xffffffffu, incl, 31);
+    if (tot == 0) continue;  // warp-uniform
+    if (wcnt + tot > STG) flush();
+    const bool direct = tot > STG;  // burst (e.g. thousands of equal keys): straight to the global list
+    unsigned int gbase = 0;
+    if (direct) {
+      if (lane == 0) gbase = atomicAdd(&s_cnt, tot);
+      gbase = __shfl_sync(0xffffffffu, gbase, 0);
+    }
+    unsigned int pos = (direct ? gbase : wcnt) + (incl - cnt);
+    const unsigned int idx0 = (unsigned int)(cur.gstart + base) + threadIdx.x * 4;
+    const float* myvals = reinterpret_cast<const float*>(vals);
+    while (hits) {
+      const int j = __ffs(hits) - 1;
+      hits &= hits - 1;
+      const unsigned int key = absbits(myvals[((j >> 2) * 32 + lane) * 4 + (j & 3)]);
+      const unsigned int idx = idx0 + (unsigned int)(j >> 2) * (THREADS * 4) + (unsigned int)(j & 3);
+      if (direct) {
+        if (pos < cap) {
+          cand_key[pos] = key;
+          cand_idx[pos] = idx;
+        }
+      } else {
+        wkeys[pos] = key;
+        widx[pos] = idx;
+      }
+      ++pos;
+      atomicAdd(&s_lvl[(key - lo) >> shiftA], 1u);
+    }
+    if (!direct) wcnt += tot;
+  }
+  flush();
+  for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+  if (lane == 0) s_below[wid] = below;
+  if (nanacc != nanacc) state->has_nan = 1u;  // rare; every writer stores the same value
+  __syncthreads();
+  // publish this block's results (read by everyone after the grid barrier)
+  for (int i = threadIdx.x; i < LVL_BINS; i += THREADS)
+    if (s_lvl[i]) atomicAdd(&state->lvl_hist[0][0][i], s_lvl[i]);
+  if (threadIdx.x == 0) {
+    unsigned long long tot = 0;
+    for (int w = 0; w < NWARPS; ++w) tot += s_below[w];
+    state->blk_below[blockIdx.x] = tot;
+    const unsigned int c = s_cnt;
+    state->blk_cnt[0][blockIdx.x] = c < cap ? c : cap;
+    if (c > cap) state->overflow = 1u;
+  }
+}
+
+// Streaming passes of the exact path.
+//   MODE 1: stage the keys in [lo, hi] (one 12-bit bin) and append them to the candidate list
+//   MODE 2: 4096-bin histogram of key >> 19 into s_mem (flushed by the caller); records NaNs
+template <int MODE>
+__device__ __forceinline__ void exact_pass(const SegTable& st, const Chunks& ch, SelState* state, unsigned int lo,
+                                           unsigned int hi, unsigned int* __restrict__ cand_key, unsigned int cand_cap,
+                                           unsigned int* s_mem) {
+  __shared__ unsigned int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned int* wkeys = s_mem + wid * STG_X;
+  unsigned int wcnt = 0;  // warp-uniform
+  bool saw_nan = false;
+  auto flush = [&]() {  // warp-wide
+    unsigned int base = 0;
+    if (lane == 0 && wcnt) base = atomicAdd(&s_cnt, wcnt);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    __syncwarp();
+    for (unsigned int i = lane; i < wcnt; i += 32)
+      if (base + i < cand_cap) cand_key[base + i] = wkeys[i];
     __syncwarp();
     wcnt = 0;
   };
@@ -279,13 +568,17 @@ __global__ void __launch_bounds__(THREADS) count_compact_kernel(const SegTable s
         const unsigned int key = absbits(v[j]);
         keys[it * 4 + j] = key;
         if (j < nvalid[it]) {
-          saw_nan |= key > 0x7f800000u;
-          if (key < lo) ++below;
-          else if (key <= hi) hits |= 1u << (it * 4 + j);
+          if (MODE == 2) {
+            saw_nan |= key > 0x7f800000u;
+            atomicAdd(&s_mem[key >> 19], 1u);
+          } else if (key >= lo && key <= hi) {
+            hits |= 1u << (it * 4 + j);
+          }
         }
       }
     }
-    if (wcnt > WSTAGE - 32 * 4 * ITERS) flush();
+    if (MODE == 2) continue;
+    if (wcnt > STG_X - 32 * 4 * ITERS) flush();
     const unsigned int cnt = __popc(hits);
     unsigned int incl = cnt;
 #pragma unroll
@@ -296,338 +589,187 @@ __global__ void __launch_bounds__(THREADS) count_compact_kernel(const SegTable s
     unsigned int pos = wcnt + (incl - cnt);
 #pragma unroll
     for (int j = 0; j < 4 * ITERS; ++j)
-      if (hits & (1u << j)) wbuf[pos++] = keys[j];
+      if (hits & (1u << j)) wkeys[pos++] = keys[j];
     wcnt += __shfl_sync(0xffffffffu, incl, 31);
   }
-  flush();
-  for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
-  if (lane == 0) s_below[wid] = below;
-  if (saw_nan) atomicOr(&state->has_nan, 1u);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned long long tot = 0;
-    for (int w = 0; w < THREADS / 32; ++w) tot += s_below[w];
-    if (tot) atomicAdd(&state->below, tot);
-  }
-}
-
-// grid-stride visit of the candidate list with 8 independent loads in flight per thread (the plain loop is bound by
-// one L2 round trip per element)
-template <typename F>
-__device__ __forceinline__ void for_each_cand(const unsigned int* __restrict__ cand, unsigned int m, F f) {
-  const unsigned int stride = gridDim.x * THREADS;
-  unsigned int i = blockIdx.x * THREADS + threadIdx.x;
-  for (; i + 7 * stride < m; i += 8 * stride) {
-    unsigned int k[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) k[u] = cand[i + u * stride];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) f(k[u]);
-  }
-  for (; i < m; i += stride) f(cand[i]);
-}
-
-// Candidate-list histograms of the fast path.  Candidates all lie in [lo, hi], so bins are taken on d = key - lo:
-// level A = d >> sA with sA chosen so that (hi-lo) >> sA < 4096 (candidates spread over the bins instead of piling
-// into the two or three bins their common high bits select), level B = the next min(12, sA) bits, level C the rest.
-__device__ __forceinline__ void fast_shifts(const SelState* st, unsigned int* lo, int* sA, int* sB) {
-  const unsigned int l = st->lo_key;
-  const unsigned int h = st->hi_key > 0x7fffffffu ? 0x7fffffffu : st->hi_key;
-  unsigned int width = (h >= l) ? (h - l) : 0u;
-  int a = 0;
-  while ((width >> a) >= (unsigned int)BINS0) ++a;
-  *lo = l;
-  *sA = a;
-  *sB = a > 12 ? a - 12 : 0;
-}
-__device__ __forceinline__ unsigned int fast_rel(unsigned int key, unsigned int lo) {
-  const unsigned int k = key > 0x7fffffffu ? 0x7fffffffu : key;
-  return k - lo;
-}
-
-__global__ void __launch_bounds__(THREADS) histA_kernel(SelState* state, const unsigned int* __restrict__ cand) {
-  __shared__ unsigned int sh[BINS0];
-  unsigned int lo;
-  int sA, sB;
-  fast_shifts(state, &lo, &sA, &sB);
-  for (int i = threadIdx.x; i < BINS0; i += THREADS) sh[i] = 0;
-  __syncthreads();
-  const unsigned int m = state->cand_count;
-  for_each_cand(cand, m, [&](unsigned int key) { atomicAdd(&sh[fast_rel(key, lo) >> sA], 1u); });
-  __syncthreads();
-  for (int i = threadIdx.x; i < BINS0; i += THREADS)
-    if (sh[i]) atomicAdd(&state->hist0[i], sh[i]);
-}
-
-__global__ void __launch_bounds__(THREADS) histB_kernel(SelState* state, const unsigned int* __restrict__ cand) {
-  __shared__ unsigned int s_bin;
-  __shared__ unsigned long long s_rem;
-  __shared__ unsigned int sh[BINS1];
-  const unsigned long long below = state->below;
-  const unsigned int m = state->cand_count;
-  if (state->k < below || state->k - below >= (unsigned long long)m) return;  // bracket missed: exact path takes over
-  unsigned int lo;
-  int sA, sB;
-  fast_shifts(state, &lo, &sA, &sB);
-  block_find_bin<BINS0>(state->hist0, state->k - below, &s_bin, &s_rem);
-  const unsigned int bin0 = s_bin;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    state->bin0 = bin0;
-    state->rem1 = s_rem;
-  }
-  for (int i = threadIdx.x; i < BINS1; i += THREADS) sh[i] = 0;
-  __syncthreads();
-  for_each_cand(cand, m, [&](unsigned int key) {
-    const unsigned int d = fast_rel(key, lo);
-    if ((d >> sA) == bin0) atomicAdd(&sh[(d >> sB) & (BINS1 - 1) & ((1u << (sA - sB)) - 1u)], 1u);
-  });
-  __syncthreads();
-  for (int i = threadIdx.x; i < BINS1; i += THREADS)
-    if (sh[i]) atomicAdd(&state->hist1[i], sh[i]);
-}
-
-__global__ void __launch_bounds__(THREADS) histC_kernel(SelState* state, const unsigned int* __restrict__ cand) {
-  __shared__ unsigned int s_bin;
-  __shared__ unsigned long long s_rem;
-  __shared__ unsigned int sh[BINS2];
-  const unsigned long long below = state->below;
-  const unsigned int m = state->cand_count;
-  if (state->k < below || state->k - below >= (unsigned long long)m) return;
-  unsigned int lo;
-  int sA, sB;
-  fast_shifts(state, &lo, &sA, &sB);
-  block_find_bin<BINS1>(state->hist1, state->rem1, &s_bin, &s_rem);
-  const unsigned int bin1 = s_bin, bin0 = state->bin0;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    state->bin1 = bin1;
-    state->rem2 = s_rem;
-  }
-  if (threadIdx.x < BINS2) sh[threadIdx.x] = 0;
-  __syncthreads();
-  if (sB > 0) {  // sB <= 7 (d < 2^31, sA <= 19): at most 128 bins
-    const unsigned int maskB = (1u << (sA - sB)) - 1u;
-    for_each_cand(cand, m, [&](unsigned int key) {
-      const unsigned int d = fast_rel(key, lo);
-      if ((d >> sA) == bin0 && ((d >> sB) & maskB) == bin1) atomicAdd(&sh[d & ((1u << sB) - 1u)], 1u);
-    });
+  if (MODE == 1) {
+    flush();
     __syncthreads();
-    if (threadIdx.x < BINS2 && sh[threadIdx.x]) atomicAdd(&state->hist2[threadIdx.x], sh[threadIdx.x]);
+    if (threadIdx.x == 0) state->blk_cnt[1][blockIdx.x] = s_cnt < cand_cap ? s_cnt : cand_cap;  // cannot overflow
   }
-}
-
-__global__ void __launch_bounds__(THREADS) finalF_kernel(SelState* state, SelState* exact, float* out3, int need_b) {
-  __shared__ unsigned int s_bin;
-  __shared__ unsigned long long s_rem;
-  const unsigned long long below = state->below;
-  if (state->k < below || state->k - below >= (unsigned long long)state->cand_count) return;  // done stays 0
-  unsigned int lo;
-  int sA, sB;
-  fast_shifts(state, &lo, &sA, &sB);
-  if (sB > 0) block_find_bin<BINS2>(state->hist2, state->rem2, &s_bin, &s_rem);
-  else if (threadIdx.x == 0) s_bin = 0;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int key = lo + ((state->bin0 << sA) | (state->bin1 << sB) | s_bin);
-    // the succ/lerp kernels read the EXACT-path state: publish the result there
-    exact->key_a = key;
-    exact->cnt_le = 0;
-    exact->min_gt = 0xffffffffu;
-    exact->has_nan = state->has_nan;
-    exact->done = 1;
-    state->done = 1;
-    if (!need_b) {
-      const float a = state->has_nan ? __uint_as_float(0x7fc00000u) : __uint_as_float(key);
-      out3[0] = a;
-      out3[1] = a;
-      out3[2] = a;
-    }
-  }
-}
-
-__global__ void set_rank_kernel(SelState* state, SelState* fast, unsigned long long k) {
-  state->k = k;
-  fast->k = k;
-}
-
-__global__ void __launch_bounds__(THREADS) hist0_kernel(const SegTable st, const Chunks ch, SelState* state) {
-  __shared__ unsigned int sh[BINS0];
-  if (state->done) return;  // the sample-pivot fast path already produced the answer
-  for (int i = threadIdx.x; i < BINS0; i += THREADS) sh[i] = 0;
-  __syncthreads();
-  bool saw_nan = false;
-  for_each_element(st, ch, [&](float v, int, long long) {
-    const unsigned int key = absbits(v);
-    saw_nan |= key > 0x7f800000u;
-    atomicAdd(&sh[key >> 19], 1u);
-  });
-  if (saw_nan) atomicOr(&state->has_nan, 1u);
-  __syncthreads();
-  for (int i = threadIdx.x; i < BINS0; i += THREADS)
-    if (sh[i]) atomicAdd(&state->hist0[i], sh[i]);
-}
-
-// Compaction of the selected bin: one global atomic per block-iteration (block-wide exclusive scan of the per-thread
-// hit counts), not one per warp — a single counter address serialises in L2 otherwise.
-__global__ void __launch_bounds__(THREADS) compact_kernel(const SegTable st, const Chunks ch, SelState* state,
-                                                          unsigned int* __restrict__ cand,
-                                                          unsigned long long cand_cap) {
-  __shared__ unsigned int s_bin;
-  __shared__ unsigned long long s_rem;
-  __shared__ unsigned int s_wsum[THREADS / 32];
-  __shared__ unsigned int s_base;
-  if (state->done) return;
-  block_find_bin<BINS0>(state->hist0, state->k, &s_bin, &s_rem);
-  const unsigned int bin = s_bin;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    state->bin0 = bin;
-    state->rem1 = s_rem;
-  }
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const long long nchunks = ch.cstart[st.nseg];
-  for (long long cid = blockIdx.x; cid < nchunks; cid += gridDim.x) {
-    const int s = find_seg(ch, st.nseg, cid);
-    const long long size = st.start[s + 1] - st.start[s];
-    const long long base = (cid - ch.cstart[s]) * CHUNK;
-    const float* p = st.ptr[s];
-    const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
-    unsigned int keys[4 * ITERS];
-    unsigned int hits = 0;  // bit j set: keys[j] belongs to the bin
-#pragma unroll
-    for (int it = 0; it < ITERS; ++it) {
-      const long long i = base + ((long long)it * THREADS + threadIdx.x) * 4;
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      int nvalid = 0;
-      if (aligned && i + 4 <= size) {
-        const float4 q = ld_stream_f4(reinterpret_cast<const float4*>(p + i));
-        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-        nvalid = 4;
-      } else {
-        for (int j = 0; j < 4; ++j)
-          if (i + j < size) { v[j] = p[i + j]; nvalid = j + 1; }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const unsigned int key = absbits(v[j]);
-        keys[it * 4 + j] = key;
-        if (j < nvalid && (key >> 19) == bin) hits |= 1u << (it * 4 + j);
-      }
-    }
-    const unsigned int cnt = __popc(hits);
-    unsigned int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (lane == 31) s_wsum[wid] = incl;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned int tot = 0;
-      for (int w = 0; w < THREADS / 32; ++w) { const unsigned int c = s_wsum[w]; s_wsum[w] = tot; tot += c; }
-      s_base = tot ? atomicAdd(&state->cand_count, tot) : 0u;
-    }
-    __syncthreads();
-    unsigned int pos = s_base + s_wsum[wid] + (incl - cnt);
-#pragma unroll
-    for (int j = 0; j < 4 * ITERS; ++j)
-      if (hits & (1u << j)) {
-        if (pos < cand_cap) cand[pos] = keys[j];
-        ++pos;
-      }
-    __syncthreads();  // s_wsum / s_base are reused by the next iteration
-  }
-}
-
-__global__ void __launch_bounds__(THREADS) hist1_kernel(SelState* state, const unsigned int* __restrict__ cand) {
-  __shared__ unsigned int sh[BINS1];
-  if (state->done) return;
-  for (int i = threadIdx.x; i < BINS1; i += THREADS) sh[i] = 0;
-  __syncthreads();
-  const unsigned int m = state->cand_count;
-  for (unsigned int i = blockIdx.x * THREADS + threadIdx.x; i < m; i += gridDim.x * THREADS)
-    atomicAdd(&sh[(cand[i] >> 7) & (BINS1 - 1)], 1u);
-  __syncthreads();
-  for (int i = threadIdx.x; i < BINS1; i += THREADS)
-    if (sh[i]) atomicAdd(&state->hist1[i], sh[i]);
-}
-
-__global__ void __launch_bounds__(THREADS) hist2_kernel(SelState* state, const unsigned int* __restrict__ cand) {
-  __shared__ unsigned int s_bin;
-  __shared__ unsigned long long s_rem;
-  __shared__ unsigned int sh[BINS2];
-  if (state->done) return;
-  block_find_bin<BINS1>(state->hist1, state->rem1, &s_bin, &s_rem);
-  const unsigned int bin1 = s_bin;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    state->bin1 = bin1;
-    state->rem2 = s_rem;
-  }
-  if (threadIdx.x < BINS2) sh[threadIdx.x] = 0;
-  __syncthreads();
-  const unsigned int m = state->cand_count;
-  for (unsigned int i = blockIdx.x * THREADS + threadIdx.x; i < m; i += gridDim.x * THREADS) {
-    const unsigned int key = cand[i];
-    if (((key >> 7) & (BINS1 - 1)) == bin1) atomicAdd(&sh[key & (BINS2 - 1)], 1u);
-  }
-  __syncthreads();
-  if (threadIdx.x < BINS2 && sh[threadIdx.x]) atomicAdd(&state->hist2[threadIdx.x], sh[threadIdx.x]);
-}
-
-// single block: resolve the last 7 bits -> key_a; if the (k+1)-th value is not needed, also emit the result.
-__global__ void __launch_bounds__(THREADS) final_kernel(SelState* state, float* out3, int need_b) {
-  __shared__ unsigned int s_bin;
-  __shared__ unsigned long long s_rem;
-  if (state->done) return;
-  block_find_bin<BINS2>(state->hist2, state->rem2, &s_bin, &s_rem);
-  if (threadIdx.x == 0) {
-    const unsigned int key = (state->bin0 << 19) | (state->bin1 << 7) | s_bin;
-    state->key_a = key;
-    state->cnt_le = 0;
-    state->min_gt = 0xffffffffu;
-    if (!need_b) {
-      const float a = state->has_nan ? __uint_as_float(0x7fc00000u) : __uint_as_float(key);
-      out3[0] = a;
-      out3[1] = a;
-      out3[2] = a;
-    }
-  }
-}
-
-// count(key <= key_a) and min(key > key_a) over the ORIGINAL data: decides sorted[k+1].
-__global__ void __launch_bounds__(THREADS) succ_kernel(const SegTable st, const Chunks ch, SelState* state) {
-  const unsigned int key_a = state->key_a;
-  unsigned long long cnt = 0;
-  unsigned int mn = 0xffffffffu;
-  for_each_element(st, ch, [&](float v, int, long long) {
-    const unsigned int key = absbits(v);
-    if (key <= key_a) ++cnt;
-    else if (key < mn) mn = key;
-  });
-  for (int o = 16; o > 0; o >>= 1) {
-    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    const unsigned int other = __shfl_xor_sync(0xffffffffu, mn, o);
-    mn = other < mn ? other : mn;
-  }
-  if ((threadIdx.x & 31) == 0) {
-    if (cnt) atomicAdd(&state->cnt_le, cnt);
-    if (mn != 0xffffffffu) atomicMin(&state->min_gt, mn);
+  if (MODE == 2) {
+    // has_nan may hold a "maybe" from the fast pass (Inf also trips it): the exact pass decides
+    if (saw_nan) atomicOr(&state->has_nan, 2u);
   }
 }
 
 // NumPy's _lerp (numpy/lib/_function_base_impl.py) in float32, no FMA contraction:
 //   lerp = a + (b-a)*t ; where t >= 0.5: lerp = b - (b-a)*(1-t)
-__global__ void lerp_kernel(SelState* state, float gamma, float* out3) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const float a = __uint_as_float(state->key_a);
-  float b = a;
-  if (state->cnt_le <= state->k + 1ull && state->min_gt != 0xffffffffu) b = __uint_as_float(state->min_gt);
+__device__ __forceinline__ float np_lerp_f32(float a, float b, float gamma) {
   const float diff = __fsub_rn(b, a);
   float r = __fadd_rn(a, __fmul_rn(diff, gamma));
   if (gamma >= 0.5f) r = __fsub_rn(b, __fmul_rn(diff, __fsub_rn(1.0f, gamma)));
-  if (state->has_nan) r = __uint_as_float(0x7fc00000u);
-  out3[0] = r;
-  out3[1] = a;
-  out3[2] = b;
+  return r;
+}
+
+// count(key <= key_a) and max(~key) over keys > key_a, warp-reduced and accumulated into the state
+__device__ __forceinline__ void succ_accumulate(SelState* state, int slot, unsigned long long cnt, unsigned int mx) {
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    const unsigned int other = __shfl_xor_sync(0xffffffffu, mx, o);
+    mx = other > mx ? other : mx;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (cnt) atomicAdd(&state->cnt_le[slot], cnt);
+    if (mx) atomicMax(&state->min_gt[slot], mx);
+  }
+}
+
+template <bool WRITE_MASK>
+__global__ void __launch_bounds__(THREADS, 4) weight_prune_kernel(const SegTable st, const Chunks ch, SelState* state,
+                                                               unsigned int* cand, unsigned long long region_words,
+                                                               unsigned long long k, float gamma, int use_fast,
+                                                               float* out3) {
+  __shared__ __align__(16) unsigned int s_mem[SMEM_WORDS];  // 40 KB: staging | sample keys | histograms
+  static_assert(SMEM_WORDS >= SAMPLE && SMEM_WORDS >= BINS0, "shared scratch too small");
+  cg::grid_group grid = cg::this_grid();
+  const long long n = st.start[st.nseg];
+  // this block's private slice of the candidate area: region_words >= the number of elements the block visits
+  unsigned int* region = cand + (size_t)blockIdx.x * region_words;
+  unsigned int* my_keys = region;
+  const unsigned int fast_cap = (unsigned int)(region_words / 2);
+  unsigned int* my_idx = region + fast_cap;
+  const int need_b = (gamma != 0.f && (long long)k + 1 < n) ? 1 : 0;
+  unsigned int key_a = 0, key_b = 0;
+  stamp(state, 0);
+
+  if (use_fast) {
+    // ---- S ----
+    sample_rank_count(st, n, state, s_mem);
+    grid.sync();
+    stamp(state, 1);
+    unsigned int lo, mid, hi;
+    {
+      // sample ranks: m = k*S/n estimates the pivot, +- (4.5 sigma + 8) brackets it, sigma = sqrt(S q (1-q))
+      const double q = (double)k / (double)n;
+      const double m = q * SAMPLE;
+      const double sig = sqrt((double)SAMPLE * q * (1.0 - q));
+      const double d = 4.5 * sig + 8.0;
+      long long rlo = (long long)floor(m - d), rhi = (long long)ceil(m + d) + need_b, rmid = (long long)floor(m);
+      const bool open_lo = rlo <= 0, open_hi = rhi >= SAMPLE - 1;
+      if (rlo < 0) rlo = 0;
+      if (rhi > SAMPLE - 1) rhi = SAMPLE - 1;
+      if (rmid < rlo) rmid = rlo;
+      if (rmid > rhi) rmid = rhi;
+      const unsigned int ranks[3] = {(unsigned int)rlo, (unsigned int)rmid, (unsigned int)rhi};
+      unsigned int piv[3];
+      sample_pick(state, ranks, piv);
+      lo = open_lo ? 0u : piv[0];
+      mid = piv[1];
+      hi = open_hi ? 0x7fffffffu : piv[2];
+      if (blockIdx.x == 0 && threadIdx.x == 0) {
+        state->lo_key = lo;
+        state->mid_key = mid;
+        state->hi_key = hi;
+      }
+    }
+    stamp(state, 2);
+    // ---- P ----
+    fast_pass<WRITE_MASK>(st, ch, state, lo, mid, hi, my_keys, my_idx, fast_cap, s_mem);
+    stamp(state, 3);
+    grid.sync();
+    stamp(state, 4);
+    const unsigned long long below = grid_total(state->blk_below);
+    const unsigned long long m = grid_total(state->blk_cnt[0]);
+    const unsigned int my_cnt = __ldcg(&state->blk_cnt[0][blockIdx.x]);
+    const bool ok = !__ldcg(&state->has_nan) && !__ldcg(&state->overflow) && k >= below &&
+                    (k + (unsigned long long)need_b - below) < m;
+    if (ok) {  // grid-uniform
+      // ---- R: exact rank among the candidates (level 0 was binned during the pass) ----
+      key_a = resolve_rank(grid, &state->lvl_hist[0][0][0], my_keys, my_cnt, lo, hi - lo, k - below, s_mem, true);
+      stamp(state, 5);
+      key_b = key_a;
+      if (need_b) {
+        unsigned long long cnt = 0;
+        unsigned int mx = 0;  // max of ~key over keys > key_a  ==  ~(min key > key_a)
+        for_each_own(my_keys, my_cnt, [&](unsigned int key, unsigned int) {
+          if (key <= key_a) ++cnt;
+          else if (~key > mx) mx = ~key;
+        });
+        succ_accumulate(state, 0, cnt, mx);
+        grid.sync();
+        const unsigned long long cnt_le = below + __ldcg(&state->cnt_le[0]);
+        const unsigned int mg = __ldcg(&state->min_gt[0]);
+        if (cnt_le <= k + 1ull && mg) key_b = ~mg;
+      }
+      const float thr = np_lerp_f32(__uint_as_float(key_a), __uint_as_float(key_b), gamma);
+      // ---- F: candidates whose provisional mask (|w| > mid) differs from the final one (|w| > thr) ----
+      if (WRITE_MASK) {
+        const float mid_f = __uint_as_float(mid);
+        for_each_own(my_keys, my_cnt, [&](unsigned int key, unsigned int i) {
+          const float a = __uint_as_float(key);
+          const bool fin = a > thr;
+          if (fin != (a > mid_f)) {
+            const long long g = (long long)__ldcg(my_idx + i);
+            const int s = seg_of(st, g);
+            st.out[s][g - st.start[s]] = fin ? 1.f : 0.f;
+          }
+        });
+      }
+      if (blockIdx.x == 0 && threadIdx.x == 0) {
+        out3[0] = thr;
+        out3[1] = __uint_as_float(key_a);
+        out3[2] = __uint_as_float(key_b);
+        state->used_fast = 1;
+      }
+      stamp(state, 6);
+      return;
+    }
+  }
+
+  // ---- exact path ----
+  for (int i = threadIdx.x; i < BINS0; i += THREADS) s_mem[i] = 0;
+  __syncthreads();
+  exact_pass<2>(st, ch, state, 0u, 0u, nullptr, 0u, s_mem);
+  __syncthreads();
+  for (int i = threadIdx.x; i < BINS0; i += THREADS)
+    if (s_mem[i]) atomicAdd(&state->hist0[i], s_mem[i]);
+  grid.sync();
+  unsigned int bin0;
+  unsigned long long rem1;
+  find_bin<BINS0>(state->hist0, k, &bin0, &rem1);
+  const unsigned int lo = bin0 << 19, hi = lo + ((1u << 19) - 1u);
+  exact_pass<1>(st, ch, state, lo, hi, my_keys, (unsigned int)region_words, s_mem);
+  grid.sync();
+  const unsigned int my_cnt = __ldcg(&state->blk_cnt[1][blockIdx.x]);
+  key_a = resolve_rank(grid, &state->lvl_hist[1][0][0], my_keys, my_cnt, lo, hi - lo, rem1, s_mem, false);
+  key_b = key_a;
+  if (need_b) {
+    // count(key <= key_a) and min(key > key_a) over the ORIGINAL data decide sorted[k+1]
+    unsigned long long cnt = 0;
+    unsigned int mx = 0;
+    for_each_element(st, ch, [&](float v, int, long long) {
+      const unsigned int key = absbits(v);
+      if (key <= key_a) ++cnt;
+      else if (~key > mx) mx = ~key;
+    });
+    succ_accumulate(state, 1, cnt, mx);
+    grid.sync();
+    const unsigned long long cnt_le = __ldcg(&state->cnt_le[1]);
+    const unsigned int mg = __ldcg(&state->min_gt[1]);
+    if (cnt_le <= k + 1ull && mg) key_b = ~mg;
+  }
+  float thr = np_lerp_f32(__uint_as_float(key_a), __uint_as_float(key_b), gamma);
+  float fa = __uint_as_float(key_a), fb = __uint_as_float(key_b);
+  if (__ldcg(&state->has_nan) & 2u) thr = fa = fb = __uint_as_float(0x7fc00000u);  // np.percentile of data with NaN
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    out3[0] = thr;
+    out3[1] = fa;
+    out3[2] = fb;
+  }
+  if (WRITE_MASK) {
+    for_each_element(st, ch, [&](float v, int s, long long i) { st.out[s][i] = fabsf(v) > thr ? 1.f : 0.f; });
+  }
 }
 
 // ---- mask / apply ----------------------------------------------------------------------------------------
@@ -789,76 +931,94 @@ int stream_grid(long long nchunks) {
 
 extern "C" size_t mc_workspace_bytes_kth_abs_select(int64_t n_total) {
   if (n_total < 0) n_total = 0;
-  // state + worst-case candidate list (every element in one 12-bit bin, e.g. an already-pruned model)
-  return 2 * (((sizeof(SelState) + 255) / 256) * 256) + (size_t)n_total * sizeof(unsigned int) + 256;
+  // state + per-block candidate slices (worst case of the exact path: every element a candidate, e.g. an
+  // already-pruned model; each block's slice is rounded up to whole chunks)
+  return ((sizeof(SelState) + 255) / 256) * 256 +
+         ((size_t)n_total + (size_t)MAXB * CHUNK) * sizeof(unsigned int) + 256;
 }
+
+namespace {
+
+int launch_weight_prune(const float* const* h_w_ptrs, float* const* h_mask_ptrs, const int64_t* h_seg_sizes, int nseg,
+                        int64_t k, float gamma, float* d_out3, void* d_ws, size_t ws_bytes, cudaStream_t stream,
+                        const char* who) {
+  SegTable st;
+  Chunks ch;
+  int rc = build_tables(&st, &ch, h_w_ptrs, h_mask_ptrs, h_seg_sizes, nseg, who);
+  if (rc) return rc;
+  const long long n = st.start[nseg];
+  MC_CHECK_ARG(n > 0, "%s: empty input", who);
+  MC_CHECK_ARG(k >= 0 && k < n, "%s: rank %lld out of range [0,%lld)", who, (long long)k, n);
+  MC_CHECK_ARG(d_out3 && d_ws, "%s: null output/workspace", who);
+  MC_CHECK_ARG(gamma >= 0.f && gamma < 1.f, "%s: gamma must be in [0,1)", who);
+  if (h_mask_ptrs)
+    for (int s = 0; s < nseg; ++s) MC_CHECK_ARG(h_mask_ptrs[s] || h_seg_sizes[s] == 0, "%s: null mask %d", who, s);
+  if (ws_bytes < mc_workspace_bytes_kth_abs_select(n))
+    return mc_set_error(MC_ERR_WS, "%s: workspace %zu < required %zu", who, ws_bytes, mc_workspace_bytes_kth_abs_select(n));
+  const size_t state_bytes = ((sizeof(SelState) + 255) / 256) * 256;
+  SelState* state = reinterpret_cast<SelState*>(d_ws);
+  unsigned int* cand = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(d_ws) + state_bytes);
+
+  // MCB200_SELECT_EXACT=1 forces the exact radix path (used by the tests to cover the fallback on large inputs)
+  const char* force_exact = getenv("MCB200_SELECT_EXACT");
+  // the fast path indexes elements with 32 bits and needs a sample much smaller than the data
+  int use_fast = (n >= 8 * SAMPLE && n < (1ll << 32) && !(force_exact && force_exact[0] == '1')) ? 1 : 0;
+
+  static int blocks_per_sm[2] = {0, 0};
+  const int which = h_mask_ptrs ? 1 : 0;
+  if (blocks_per_sm[which] == 0) {
+    int nb = 0;
+    if (which) MC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, weight_prune_kernel<true>, THREADS, 0));
+    else MC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, weight_prune_kernel<false>, THREADS, 0));
+    if (nb < 1) return mc_set_error(MC_ERR_SHAPE, "%s: kernel does not fit an SM", who);
+    blocks_per_sm[which] = nb;
+  }
+  long long grid = (long long)mc_num_sms() * blocks_per_sm[which];
+  if (grid > ch.cstart[nseg]) grid = ch.cstart[nseg];
+  if (grid > MAXB) grid = MAXB;
+  if (grid < 1) grid = 1;
+  // a block visits at most ceil(nchunks / grid) chunks: its candidate slice holds that many elements
+  unsigned long long region_words = (unsigned long long)((ch.cstart[nseg] + grid - 1) / grid) * CHUNK;
+
+  MC_CUDA(cudaMemsetAsync(d_ws, 0, state_bytes, stream));
+  unsigned long long kk = (unsigned long long)k;
+  void* args[] = {&st, &ch, &state, &cand, &region_words, &kk, &gamma, &use_fast, &d_out3};
+  const void* fn = which ? (const void*)weight_prune_kernel<true> : (const void*)weight_prune_kernel<false>;
+  MC_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(THREADS), args, 0, stream));
+  return 0;
+}
+
+}  // namespace
 
 extern "C" int mc_kth_abs_select(const float* const* h_seg_ptrs, const int64_t* h_seg_sizes, int nseg, int64_t k,
                                  float gamma, float* d_out3, void* d_ws, size_t ws_bytes, void* stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  SegTable st;
-  Chunks ch;
-  int rc = build_tables(&st, &ch, h_seg_ptrs, nullptr, h_seg_sizes, nseg, "mc_kth_abs_select");
-  if (rc) return rc;
-  const long long n = st.start[nseg];
-  MC_CHECK_ARG(n > 0, "mc_kth_abs_select: empty input");
-  MC_CHECK_ARG(k >= 0 && k < n, "mc_kth_abs_select: rank %lld out of range [0,%lld)", (long long)k, n);
-  MC_CHECK_ARG(d_out3 && d_ws, "mc_kth_abs_select: null output/workspace");
-  MC_CHECK_ARG(gamma >= 0.f && gamma < 1.f, "mc_kth_abs_select: gamma must be in [0,1)");
-  if (ws_bytes < mc_workspace_bytes_kth_abs_select(n))
-    return mc_set_error(MC_ERR_WS, "mc_kth_abs_select: workspace %zu < required %zu", ws_bytes,
-                        mc_workspace_bytes_kth_abs_select(n));
-  const size_t state_bytes = ((sizeof(SelState) + 255) / 256) * 256;
-  SelState* state = reinterpret_cast<SelState*>(d_ws);                                          // exact radix path
-  SelState* fast = reinterpret_cast<SelState*>(reinterpret_cast<char*>(d_ws) + state_bytes);    // sample-pivot path
-  unsigned int* cand = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(d_ws) + 2 * state_bytes);
+  return launch_weight_prune(h_seg_ptrs, nullptr, h_seg_sizes, nseg, k, gamma, d_out3, d_ws, ws_bytes,
+                             reinterpret_cast<cudaStream_t>(stream_), "mc_kth_abs_select");
+}
 
-  MC_CUDA(cudaMemsetAsync(d_ws, 0, 2 * state_bytes, stream));
-  set_rank_kernel<<<1, 1, 0, stream>>>(state, fast, (unsigned long long)k);
-  MC_LAUNCH_CHECK("set_rank_kernel");
-  const int grid = stream_grid(ch.cstart[nseg]);
-  const int cgrid = mc_num_sms();
-  const int need_b = (gamma != 0.f && k + 1 < n) ? 1 : 0;
-  // MCB200_SELECT_EXACT=1 forces the radix path (used by the tests to cover the fallback on large inputs)
-  const char* force_exact = getenv("MCB200_SELECT_EXACT");
-  if (n >= 4 * SAMPLE && !(force_exact && force_exact[0] == '1')) {
-    // fast path: pivots from a sample, one pass over W (count + compact), exact rank on the ~5 % candidates
-    static bool attr_set = false;
-    if (!attr_set) {
-      MC_CUDA(cudaFuncSetAttribute(sample_pivot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SAMPLE * 4));
-      attr_set = true;
-    }
-    sample_pivot_kernel<<<1, 1024, SAMPLE * 4, stream>>>(st, fast, n, (unsigned long long)k);
-    MC_LAUNCH_CHECK("sample_pivot_kernel");
-    count_compact_kernel<<<grid, THREADS, 0, stream>>>(st, ch, fast, cand, (unsigned long long)n);
-    MC_LAUNCH_CHECK("count_compact_kernel");
-    histA_kernel<<<cgrid, THREADS, 0, stream>>>(fast, cand);
-    MC_LAUNCH_CHECK("histA_kernel");
-    histB_kernel<<<cgrid, THREADS, 0, stream>>>(fast, cand);
-    MC_LAUNCH_CHECK("histB_kernel");
-    histC_kernel<<<cgrid, THREADS, 0, stream>>>(fast, cand);
-    MC_LAUNCH_CHECK("histC_kernel");
-    finalF_kernel<<<1, THREADS, 0, stream>>>(fast, state, d_out3, need_b);
-    MC_LAUNCH_CHECK("finalF_kernel");
-  }
-  // exact radix path: every kernel returns immediately when the fast path has set `done`
-  hist0_kernel<<<grid, THREADS, 0, stream>>>(st, ch, state);
-  MC_LAUNCH_CHECK("hist0_kernel");
-  compact_kernel<<<grid, THREADS, 0, stream>>>(st, ch, state, cand, (unsigned long long)n);
-  MC_LAUNCH_CHECK("compact_kernel");
-  hist1_kernel<<<cgrid, THREADS, 0, stream>>>(state, cand);
-  MC_LAUNCH_CHECK("hist1_kernel");
-  hist2_kernel<<<cgrid, THREADS, 0, stream>>>(state, cand);
-  MC_LAUNCH_CHECK("hist2_kernel");
-  final_kernel<<<1, THREADS, 0, stream>>>(state, d_out3, need_b);
-  MC_LAUNCH_CHECK("final_kernel");
-  if (need_b) {
-    succ_kernel<<<grid, THREADS, 0, stream>>>(st, ch, state);
-    MC_LAUNCH_CHECK("succ_kernel");
-    lerp_kernel<<<1, 32, 0, stream>>>(state, gamma, d_out3);
-    MC_LAUNCH_CHECK("lerp_kernel");
-  }
+extern "C" int mc_weight_prune_masks(const float* const* h_w_ptrs, float* const* h_mask_ptrs, const int64_t* h_seg_sizes,
+                                     int nseg, int64_t k, float gamma, float* d_out3, void* d_ws, size_t ws_bytes,
+                                     void* stream_) {
+  MC_CHECK_ARG(h_mask_ptrs != nullptr, "mc_weight_prune_masks: null mask table");
+  return launch_weight_prune(h_w_ptrs, h_mask_ptrs, h_seg_sizes, nseg, k, gamma, d_out3, d_ws, ws_bytes,
+                             reinterpret_cast<cudaStream_t>(stream_), "mc_weight_prune_masks");
+}
+
+extern "C" int mc_debug_select_tstamps(const void* d_ws, unsigned long long* h_out12, void* stream_) {
+  const SelState* state = reinterpret_cast<const SelState*>(d_ws);
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MC_CUDA(cudaMemcpyAsync(h_out12, state->tstamp, sizeof(state->tstamp), cudaMemcpyDeviceToHost, stream));
+  MC_CUDA(cudaStreamSynchronize(stream));
   return 0;
+}
+
+extern "C" int mc_debug_select_used_fast(const void* d_ws, void* stream_) {
+  unsigned int v = 0;
+  const SelState* state = reinterpret_cast<const SelState*>(d_ws);
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MC_CUDA(cudaMemcpyAsync(&v, &state->used_fast, sizeof(v), cudaMemcpyDeviceToHost, stream));
+  MC_CUDA(cudaStreamSynchronize(stream));
+  return (int)v;
 }
 
 extern "C" int mc_mask_apply_gt(float* const* h_w_ptrs, float* const* h_mask_ptrs, const int64_t* h_seg_sizes,

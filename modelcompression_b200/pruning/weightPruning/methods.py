@@ -6,6 +6,8 @@ weight ``gamma`` of the 'linear' method, evaluated in the SAME dtype NumPy 2.x u
 magnitude array of weight_prune, float64 for the float64 value array of quick_filter_prune).
 ``prune_one_filter`` / ``filter_prune`` (methods.py:81-142) are not on the hot path.
 """
+from itertools import chain as _chain
+
 import numpy as np
 import torch
 
@@ -46,26 +48,86 @@ def _workspace(dev, nbytes):
     return ws
 
 
+def _flat_like_all(params):
+    """One allocation for all masks (23 allocator calls -> 1).  Returns (flat, element offsets); every offset is a
+    multiple of 4 so each mask starts 16-byte aligned."""
+    offs, off = [], 0
+    for p in params:
+        offs.append(off)
+        off += ((p.numel() + 3) // 4) * 4
+    return torch.empty(off, dtype=torch.float32, device=params[0].device), offs
+
+
+def _views(flat, offs, params):
+    return [flat[o:o + p.numel()].view(p.shape) for o, p in zip(offs, params)]
+
+
 def _empty_like_all(params):
-    """One allocation for all masks, returned as per-parameter views (23 allocator calls -> 1)."""
-    sizes = [((p.numel() + 3) // 4) * 4 for p in params]  # keep every view 16-byte aligned
-    flat = torch.empty(sum(sizes), dtype=torch.float32, device=params[0].device)
-    out, off = [], 0
-    for p, sz in zip(params, sizes):
-        out.append(flat[off:off + p.numel()].view(p.shape))
-        off += sz
-    return out
+    flat, offs = _flat_like_all(params)
+    return _views(flat, offs, params)
+
+
+class _ParamIndex(object):
+    """model.parameters() without walking the module tree on every call (the nn.Module generator walk costs ~200 us on
+    the 75-module Darknet, twice the pruning kernel).  The tree is walked once; afterwards the per-module
+    ``_parameters`` / ``_modules`` dicts are re-read at C speed and compared by identity with what the walk saw, so a
+    replaced Parameter, a replaced/added/removed sub-module or a new parameter all invalidate the index."""
+
+    def __init__(self, model):
+        mods, seen = [], set()
+
+        def walk(m):
+            if id(m) in seen:
+                return
+            seen.add(id(m))
+            mods.append(m)
+            for c in m._modules.values():
+                if c is not None:
+                    walk(c)
+        walk(model)
+        self.pdicts = [m._parameters for m in mods]
+        self.mdicts = [m._modules for m in mods]
+        flat = self._flat(self.pdicts)
+        self.pids = tuple(map(id, flat))
+        self.mids = tuple(map(id, self._flat(self.mdicts)))
+        uniq, seen_p = [], set()
+        for i, p in enumerate(flat):  # parameters() order: first occurrence of every non-None parameter
+            if p is not None and id(p) not in seen_p:
+                seen_p.add(id(p))
+                uniq.append(i)
+        self.uniq = uniq
+
+    @staticmethod
+    def _flat(dicts):
+        return list(_chain.from_iterable(map(dict.values, dicts)))
+
+    def parameters(self):
+        """Current parameter list, or None when the module tree changed since the walk."""
+        flat = self._flat(self.pdicts)
+        if tuple(map(id, flat)) != self.pids or tuple(map(id, self._flat(self.mdicts))) != self.mids:
+            return None
+        return [flat[i] for i in self.uniq]
+
+
+def _all_parameters(model):
+    idx = model.__dict__.get('_b200_param_index')
+    params = idx.parameters() if idx is not None else None
+    if params is None:
+        idx = model.__dict__['_b200_param_index'] = _ParamIndex(model)
+        params = idx.parameters()
+    return params
 
 
 def _prunable(model, conv_only):
     params = []
-    for p in model.parameters():
+    for p in _all_parameters(model):
         nd = p.dim()
         if (nd == 4) if conv_only else (nd != 1):
-            _lib.require_cuda(p, "weight_prune / quick_filter_prune")
+            if not p.is_cuda:
+                _lib.require_cuda(p, "weight_prune / quick_filter_prune")
             if p.dtype != torch.float32:
                 raise TypeError("pruners expect float32 parameters, got %s" % p.dtype)
-            params.append(p.data if p.data.is_contiguous() else p.data.contiguous())
+            params.append(p.data if p.is_contiguous() else p.data.contiguous())
     return params
 
 
@@ -73,7 +135,7 @@ def weight_threshold(params, pruning_perc):
     """Device tensor [3] = (thr, sorted|w|[k], sorted|w|[k+1]) for the global magnitude percentile."""
     lib = _lib.load()
     n = sum(p.numel() for p in params)
-    k, gamma = percentile_rank(n, pruning_perc, np.float32)
+    k, gamma = _rank_cached(n, pruning_perc, np.float32)
     dev = params[0].device
     segs = params
     if len(segs) > _lib.MC_MAX_SEGMENTS:  # rare: more tensors than one launch takes -> select on a flat copy
@@ -88,6 +150,19 @@ def weight_threshold(params, pruning_perc):
     return out3
 
 
+_RANK_CACHE = {}
+
+
+def _rank_cached(n, pruning_perc, dtype):
+    key = (n, float(pruning_perc), dtype)
+    got = _RANK_CACHE.get(key)
+    if got is None:
+        if len(_RANK_CACHE) > 256:
+            _RANK_CACHE.clear()
+        got = _RANK_CACHE[key] = percentile_rank(n, pruning_perc, dtype)
+    return got
+
+
 def weight_prune(model, pruning_perc):
     '''
     Prune pruning_perc% weights globally (not layer-wise)
@@ -95,11 +170,32 @@ def weight_prune(model, pruning_perc):
 
     methods.py:9-26.  Returns one float32 {0,1} mask per parameter with dim != 1, in model.parameters() order, on
     the parameter's device: mask = |w| > np.percentile(|all w|, pruning_perc) (strict; ties are pruned).
+    One cooperative kernel launch (mc_weight_prune_masks): W is read once and the masks are written once.
     '''
     lib = _lib.load()
     params = _prunable(model, conv_only=False)
     if not params:
         return []
+    if len(params) > _lib.MC_MAX_SEGMENTS:  # more tensors than one launch takes: threshold first, then mask in groups
+        return _weight_prune_grouped(lib, params, pruning_perc)
+    n = sum(p.numel() for p in params)
+    k, gamma = _rank_cached(n, pruning_perc, np.float32)
+    dev = params[0].device
+    flat, offs = _flat_like_all(params)
+    base = flat.data_ptr()
+    mask_ptrs = (_lib.c_void_p * len(params))(*[base + 4 * o for o in offs])
+    ws_bytes = lib.mc_workspace_bytes_kth_abs_select(n)
+    ws = _workspace(dev, ws_bytes)
+    out3 = torch.empty(3, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.mc_weight_prune_masks(_lib.ptr_array(params), mask_ptrs,
+                                             _lib.int64_array([t.numel() for t in params]), len(params), k, gamma,
+                                             out3.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr()),
+                   "mc_weight_prune_masks")
+    return _views(flat, offs, params)  # the per-parameter views are created while the kernel runs
+
+
+def _weight_prune_grouped(lib, params, pruning_perc):
     out3 = weight_threshold(params, pruning_perc)
     masks = _empty_like_all(params)
     dev = params[0].device

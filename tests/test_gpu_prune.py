@@ -63,6 +63,48 @@ def test_weight_prune_darknet_bit_exact(darknet, idx):
         assert m.shape == p.shape and m.device == p.device
 
 
+def test_weight_prune_uses_fast_path(darknet):
+    # on the 50.6 M-weight model the sample-pivot bracket holds: one pass over W (the exact path is the fallback)
+    from modelcompression_b200 import _lib
+    from modelcompression_b200.pruning.weightPruning import methods
+    mc.weight_prune(darknet, 70.)
+    ws = methods._WS[('cuda', 0)]
+    with torch.cuda.device(0):
+        assert _lib.load().mc_debug_select_used_fast(ws.data_ptr(), _lib.stream_ptr()) == 1
+
+
+class _ParamBag(torch.nn.Module):
+    def __init__(self, tensors):
+        super().__init__()
+        self.ps = torch.nn.ParameterList([torch.nn.Parameter(t) for t in tensors])
+
+
+@pytest.mark.parametrize("sizes", [(70001,), (300000, 17, 700003), (1 << 20, 5)])
+def test_weight_prune_midsize_interpolated(sizes):
+    # n < 2^24 so float32 np.percentile interpolates (gamma != 0) and n >= 8*SAMPLE so the fast path runs: the
+    # (k+1)-th order statistic is resolved among the bracketed candidates
+    from modelcompression_b200 import _lib
+    from modelcompression_b200.pruning.weightPruning import methods
+    gen = torch.Generator().manual_seed(5)
+    ts = [torch.randn(sz, 3, generator=gen) for sz in sizes]
+    bag = _ParamBag(ts).to(DEV)
+    ws = [t.numpy() for t in ts]
+    for perc in (0.0, 0.01, 12.5, 33.3, 70.0, 99.99, 100.0):
+        thr_o, masks_o = prune_oracle.weight_prune_np(ws, perc)
+        masks = mc.weight_prune(bag, perc)
+        for a, b in zip(masks, masks_o):
+            assert np.array_equal(a.cpu().numpy(), b), "perc %s" % perc
+        out3 = methods.weight_threshold([p.data for p in bag.parameters()], perc).cpu().numpy()
+        assert out3[0] == np.float32(thr_o), "perc %s" % perc
+    # heavy ties: quantised weights (the k-th value is shared by thousands of elements)
+    tq = [torch.round(t * 4) / 4 for t in ts]
+    bagq = _ParamBag(tq).to(DEV)
+    for perc in (20.0, 61.7):
+        _, masks_o = prune_oracle.weight_prune_np([t.numpy() for t in tq], perc)
+        for a, b in zip(mc.weight_prune(bagq, perc), masks_o):
+            assert np.array_equal(a.cpu().numpy(), b), "perc %s" % perc
+
+
 def test_weight_prune_exact_radix_fallback(darknet, monkeypatch):
     # the sample-pivot fast path falls back to the full radix select on the device when its bracket misses; force
     # that path on the full model and check it gives the same (bit-exact) masks

@@ -128,3 +128,24 @@ def test_compact_detections_order():
     assert det.shape == (5, 8)
     assert det[:, 0].tolist() == [10, 10, 11, 11, 11]
     assert torch.equal(det[0, 1:], boxes[0, 2, :7]) and torch.equal(det[4, 1:], boxes[1, 2, :7])
+
+
+def test_param_index_tracks_module_tree(cfg_path):
+    """The pruners' cached parameter index must equal model.parameters() after any edit of the module tree."""
+    import torch
+    from modelcompression_b200.pruning.weightPruning import methods
+    model = mc.Darknet(cfg_path)
+
+    def same():
+        return [id(p) for p in methods._all_parameters(model)] == [id(p) for p in model.parameters()]
+    assert same() and same()
+    model.models[0][0].weight = torch.nn.Parameter(model.models[0][0].weight.data.clone())  # replaced Parameter
+    assert same()
+    model.models[2] = torch.nn.Sequential(torch.nn.Conv2d(32, 64, 3))                       # replaced sub-module
+    assert same()
+    model.extra = torch.nn.Linear(3, 3)                                                      # added sub-module
+    assert same()
+    del model.extra                                                                          # removed sub-module
+    assert same()
+    model.models[4][0].weight = model.models[5][0].weight                                    # shared Parameter
+    assert same()
