@@ -108,6 +108,15 @@ size_t mc_workspace_bytes_filter_threshold(int n);
 int mc_filter_masks(const float* d_values, const double* d_thr, const int* h_O, const int* h_per_filter,
                     int nlayers, float* const* h_mask_ptrs, uint8_t* d_keep, void* stream);
 
+/* The whole of quick_filter_prune (steps 1-4 above) in one call: d_values [sum O] float32, *d_thr float64,
+ * d_keep [sum O] (may be NULL), full-shape masks (h_mask_ptrs may be NULL).  Three launches: per-filter sums (3x3
+ * layers tiled through shared memory with 128-bit loads), per-layer normalisation + float64 percentile (bitwise
+ * binary search on the bit patterns) + keep flags, mask fill.  d_ws: mc_workspace_bytes_filter_prune() bytes.      */
+int mc_filter_prune(const float* const* h_w_ptrs, const int* h_O, const int* h_C, const int* h_kh, const int* h_kw,
+                    int nlayers, int64_t k, double gamma, float* d_values, double* d_thr,
+                    float* const* h_mask_ptrs, uint8_t* d_keep, void* d_ws, size_t ws_bytes, void* stream);
+size_t mc_workspace_bytes_filter_prune(void);
+
 /* ------------------------------------------------------------------------------------------
  * Region decode + NMS — replaces src/nets2_utils.py:141-234 (get_region_boxes) and :236-259 (nms),
  * :63-98 (bbox_iou, centre format).

@@ -12,6 +12,7 @@
 //               n<8 sequential; n<=128: 8 strided accumulators, ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), tail;
 //               else split at n/2 rounded down to a multiple of 8).  sum(v^2) over O uses the same rule.
 // All products/sums use *_rn intrinsics so nvcc cannot contract them into FMAs.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -24,8 +25,12 @@ struct LayerTable {
   int O[MAX_LAYERS], C[MAX_LAYERS], taps[MAX_LAYERS];
   int voff[MAX_LAYERS + 1];        // prefix of O
   long long woff[MAX_LAYERS + 1];  // prefix of O*C*taps
-  int toff[MAX_LAYERS + 1];        // prefix of threads used by sumsq kernel
+  int toff[MAX_LAYERS + 1];        // prefix of threads used by the generic sumsq path (tiled layers take none)
   int nlayers;
+  // tiled path (3x3, C % 32 == 0, O % 32 == 0): work items = groups of 32 filters, layers ordered by descending C
+  int torder[MAX_LAYERS];          // layer index of the i-th tiled layer
+  int tblk[MAX_LAYERS + 1];        // prefix of work items over torder
+  int ntiled;
 };
 
 // NumPy pairwise sum of f(a[i]) for i in [0,n), a contiguous.  SQUARE: element is a[i]*a[i] rounded to fp32 first.
@@ -111,37 +116,85 @@ __device__ float np_combine_leaves(const float* __restrict__ leaf_sums, int n, i
   return __fadd_rn(l, r);
 }
 
-constexpr int MAX_LEAVES = 128;  // warp path handles C <= 4096 (leaves are >= 57 long once n > 128)
+constexpr int MAX_LEAVES = 128;  // leaves are >= 57 long once n > 128
+constexpr int ROW_MAX = 2048;     // 1x1 rows up to this many channels are staged in shared memory (warp path)
 
 // Raw per-filter sums.  taps>1: one thread per (filter, tap) runs the sequential-in-c chain (loads are issued 32 deep
 // so the chain is not exposed to memory latency); the taps of a filter sit in adjacent lanes and are combined in
 // NumPy's (h then w) order through shared memory.  taps==1: one WARP per filter runs the lane-parallel pairwise sum.
 constexpr int SS_THREADS = 288;  // multiple of 9 and of 32
-constexpr int SS_WARPS = SS_THREADS / 32;
 
-__global__ void __launch_bounds__(SS_THREADS) filter_sumsq_kernel(const LayerTable lt, float* __restrict__ values) {
-  __shared__ float s_tap[SS_THREADS];
-  __shared__ float s_leaf[SS_WARPS][MAX_LEAVES];
-  const int gt = blockIdx.x * SS_THREADS + threadIdx.x;  // global thread slot (blocks never straddle layers)
+__device__ void sumsq_generic_block(const LayerTable& lt, int gblk, float* __restrict__ values, float* s_tap,
+                                    float (*s_leaf)[MAX_LEAVES]) {
+  const int gt = gblk * SS_THREADS + threadIdx.x;  // global thread slot (blocks never straddle layers)
   int l = 0;
   while (l + 1 < lt.nlayers && gt >= lt.toff[l + 1]) ++l;
   const int local = gt - lt.toff[l];
   const int taps = lt.taps[l], C = lt.C[l], O = lt.O[l];
   const float* __restrict__ w = lt.w[l];
   if (taps == 1) {
+    // one WARP per filter.  The row (C floats, contiguous) is staged in shared memory with ONE round of coalesced
+    // loads; the leaves of NumPy's pairwise recursion are then summed four at a time, lane = (leaf, accumulator):
+    // a leaf of n >= 8 elements is 8 strided chains r[j] += a[i+j], combined ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) —
+    // the xor-butterfly does exactly these additions (fp add is commutative) — plus a sequential tail.
     const int o = local >> 5, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     if (o >= O) return;  // whole warp
     const float* a = w + (long long)o * C;
-    float* ls = s_leaf[wib];
-    if (C <= 4096) {
-      np_for_each_leaf(C, [&](int leaf, int st, int ln) {
-        if ((leaf & 31) == lane) ls[leaf] = np_leaf_sum<true>(a + st, ln);
-      });
+    float* ls = s_leaf[wib];                                    // [MAX_LEAVES] leaf sums
+    int* linfo = reinterpret_cast<int*>(s_leaf[SS_THREADS / 32]) + wib * 2 * MAX_LEAVES;  // (start, len) per leaf
+    float* srow = reinterpret_cast<float*>(s_leaf[SS_THREADS / 32]) + (SS_THREADS / 32) * 2 * MAX_LEAVES + wib * ROW_MAX;
+    if (C <= ROW_MAX) {
+      if ((C & 3) == 0) {
+        const float4* a4 = reinterpret_cast<const float4*>(a);
+        for (int i = lane; i < C / 4; i += 32) reinterpret_cast<float4*>(srow)[i] = ld_stream_f4(a4 + i);
+      } else {
+        for (int i = lane; i < C; i += 32) srow[i] = a[i];
+      }
+      int nleaves = 0;
+      if (lane == 0) {
+        nleaves = np_for_each_leaf(C, [&](int leaf, int st, int ln) {
+          linfo[2 * leaf] = st;
+          linfo[2 * leaf + 1] = ln;
+        });
+      }
+      nleaves = __shfl_sync(0xffffffffu, nleaves, 0);
+      __syncwarp();
+      const int lq = lane >> 3, j = lane & 7;
+      for (int g0 = 0; g0 < nleaves; g0 += 4) {
+        const int leaf = g0 + lq;
+        const bool have = leaf < nleaves;
+        const int st = have ? linfo[2 * leaf] : 0, ln = have ? linfo[2 * leaf + 1] : 0;
+        float res = 0.f;
+        if (ln >= 8) {
+          float x = srow[st + j];
+          float r = __fmul_rn(x, x);
+          const int body = ln - (ln % 8);
+          for (int i = 8; i < body; i += 8) {
+            x = srow[st + i + j];
+            r = __fadd_rn(r, __fmul_rn(x, x));
+          }
+          res = r;
+        }
+        // all 32 lanes take part in the butterfly (leaves shorter than 8 ignore its result)
+        float t = __fadd_rn(res, __shfl_xor_sync(0xffffffffu, res, 1));
+        t = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, 2));
+        t = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, 4));
+        if (have && j == 0) {
+          float sum;
+          int i;
+          if (ln >= 8) { sum = t; i = ln - (ln % 8); } else { sum = 0.f; i = 0; }
+          for (; i < ln; ++i) {
+            const float x = srow[st + i];
+            sum = __fadd_rn(sum, __fmul_rn(x, x));
+          }
+          ls[leaf] = sum;
+        }
+      }
       __syncwarp();
       if (lane == 0) {
         int next = 0;
-        const float s = np_combine_leaves(ls, C, &next);
-        values[lt.voff[l] + o] = __fdiv_rn(s, (float)C);
+        const float sres = np_combine_leaves(ls, C, &next);
+        values[lt.voff[l] + o] = __fdiv_rn(sres, (float)C);
       }
     } else if (lane == 0) {
       values[lt.voff[l] + o] = __fdiv_rn(np_pairwise<true>(a, C), (float)C);
@@ -185,6 +238,100 @@ __global__ void __launch_bounds__(SS_THREADS) filter_sumsq_kernel(const LayerTab
     values[lt.voff[l] + o] = __fdiv_rn(tot, (float)(C * taps));
   }
 }
+
+// ---- tiled path for the 3x3 layers (97 % of the weights) ------------------------------------------------------
+// A block owns 32 filters and walks their C axis in chunks of 32 channels: the 32 x 288 floats of a chunk are
+// contiguous per filter (1152 B) and are copied with 16-byte cp.async into a 3-stage shared-memory ring (two chunks
+// = 72 KB in flight per block, no registers involved); thread (f, tap) runs its 32 sequential square-adds on the
+// oldest stage meanwhile.  The summation order per (filter, tap) is the same sequential-in-c chain as above.  What
+// bounds a block is the LENGTH of that chain (C/32 ring steps), so a step must cost the compute, not a DRAM latency.
+constexpr int TL_F = 32;               // filters per block
+constexpr int TL_C = 32;               // channels per chunk
+constexpr int TL_ROW4 = 74;            // float4 per tile row: 72 data + 2 pad (bank = 8f + tap: 2-way conflicts at most)
+constexpr int TL_TILE4 = TL_F * TL_ROW4;
+constexpr int TL_STAGES = 3;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ void sumsq_tiled_block(const LayerTable& lt, int item, float* __restrict__ values,
+                                  float4* s_tile /*[TL_STAGES][TL_TILE4]*/, float* s_tap /*[SS_THREADS]*/) {
+  int ti = 0;
+  while (ti + 1 < lt.ntiled && item >= lt.tblk[ti + 1]) ++ti;
+  const int l = lt.torder[ti];
+  const int C = lt.C[l];
+  const int o0 = (item - lt.tblk[ti]) * TL_F;
+  const int t = threadIdx.x;
+  const int f = t / 9, j = t - f * 9;
+  const int nchunks = C / TL_C;
+  // o0*C*9*4 bytes is a multiple of 16 because C % 32 == 0
+  const float4* __restrict__ w4 = reinterpret_cast<const float4*>(lt.w[l] + (long long)o0 * C * 9);
+  // this thread's 8 float4 of a chunk: q = u*288 + t -> (row = q / 72, col4 = q % 72)
+  int grow[8], scol[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int q = u * SS_THREADS + t;
+    const int row = q / 72, col4 = q - row * 72;
+    grow[u] = row * (C * 9 / 4) + col4;  // float4 index inside the block's filters
+    scol[u] = row * TL_ROW4 + col4;
+  }
+  auto issue = [&](int cc) {
+    if (cc < nchunks) {
+      float4* tile = s_tile + (cc % TL_STAGES) * TL_TILE4;
+      const float4* src = w4 + (long long)cc * (TL_C * 9 / 4);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) cp_async16(tile + scol[u], src + grow[u]);
+    }
+    cp_async_commit();  // an empty group keeps the wait_group arithmetic uniform at the tail
+  };
+#pragma unroll
+  for (int p = 0; p < TL_STAGES - 1; ++p) issue(p);
+  float acc = 0.f;
+  for (int cc = 0; cc < nchunks; ++cc) {
+    cp_async_wait<TL_STAGES - 2>();  // this thread's copies of chunk cc have landed
+    __syncthreads();                 // ... and everyone's; all threads are also done with the stage refilled next
+    issue(cc + TL_STAGES - 1);
+    const float* row = reinterpret_cast<const float*>(s_tile + (cc % TL_STAGES) * TL_TILE4 + f * TL_ROW4) + j;
+#pragma unroll
+    for (int c = 0; c < TL_C; ++c) {
+      const float x = row[c * 9];
+      acc = __fadd_rn(acc, __fmul_rn(x, x));
+    }
+  }
+  s_tap[t] = acc;
+  __syncthreads();
+  if (j == 0) {
+    const float* s = &s_tap[t];
+    float tot = 0.f;
+    for (int ww = 0; ww < 3; ++ww) {
+      float col = 0.f;
+      for (int hh = 0; hh < 3; ++hh) col = __fadd_rn(col, s[hh * 3 + ww]);  // .sum(axis=1) over h, sequential
+      tot = __fadd_rn(tot, col);                                            // final .sum(axis=1) over w (n<8)
+    }
+    values[lt.voff[l] + o0 + f] = __fdiv_rn(tot, (float)(C * 9));
+  }
+}
+
+// blocks [0, n_tiled): tiled work items; the first `first_wave` items (largest C first) land one per SM, the remaining
+// items are taken smallest-first so that an SM's second block complements its first.  Blocks beyond: generic path.
+__global__ void __launch_bounds__(SS_THREADS) filter_sumsq_kernel(const LayerTable lt, float* __restrict__ values,
+                                                                  int n_tiled, int first_wave) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  __shared__ float s_tap[SS_THREADS];
+  if ((int)blockIdx.x < n_tiled) {
+    int item = blockIdx.x;
+    if (item >= first_wave) item = first_wave + (n_tiled - 1 - item);
+    sumsq_tiled_block(lt, item, values, reinterpret_cast<float4*>(dsm), s_tap);
+  } else {
+    sumsq_generic_block(lt, (int)blockIdx.x - n_tiled, values, s_tap, reinterpret_cast<float(*)[MAX_LEAVES]>(dsm));
+  }
+}
+constexpr size_t SUMSQ_SMEM = TL_STAGES * TL_TILE4 * sizeof(float4);  // 113,664 B (the generic path needs 4.6 KB of it)
 
 // One block per layer: v /= sqrt(pairwise(v^2)); v /= max(v).  v is staged in shared memory so the serial pairwise
 // recursion of thread 0 runs at shared-memory latency.
@@ -296,6 +443,186 @@ __global__ void __launch_bounds__(1024) filter_threshold_kernel(const float* __r
   }
 }
 
+// ---- finish: per-layer normalisation, then (last block to arrive) the float64 percentile and the keep flags -------
+// Order statistics by bitwise binary search on the fp32 bit pattern (values are >= 0, so the pattern is monotone):
+// 31 rounds of "count keys below prefix|bit", both ranks at once, keys in shared memory — ~4 us for 10,461 values,
+// where a shared-memory radix histogram serialises on the few distinct high digits of values that all lie in (0,1].
+constexpr int FIN_THREADS = 1024;
+
+__device__ void block_count2(unsigned int c0, unsigned int c1, unsigned int* s_red /*[64]*/, unsigned int* out0,
+                             unsigned int* out1) {
+  for (int o = 16; o > 0; o >>= 1) {
+    c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+    c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { s_red[wid] = c0; s_red[32 + wid] = c1; }
+  __syncthreads();
+  if (wid == 0) {
+    unsigned int a = s_red[lane], b = s_red[32 + lane];  // FIN_THREADS / 32 == 32 warps
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) { s_red[0] = a; s_red[32] = b; }
+  }
+  __syncthreads();
+  *out0 = s_red[0];
+  *out1 = s_red[32];
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(FIN_THREADS) filter_finish_kernel(const LayerTable lt, float* __restrict__ values,
+                                                                    long long k, double gamma, double* __restrict__ thr,
+                                                                    uint8_t* __restrict__ keep,
+                                                                    unsigned int* __restrict__ ticket) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  float* s_v = reinterpret_cast<float*>(dsm);  // max(O_l, n) floats
+  __shared__ float s_norm;
+  __shared__ float s_leaf[MAX_LEAVES];
+  __shared__ unsigned int s_red[64];
+  __shared__ unsigned int s_last;
+  const int l = blockIdx.x;
+  const int O = lt.O[l];
+  float* v = values + lt.voff[l];
+  unsigned long long* dbg = reinterpret_cast<unsigned long long*>(ticket) + 1;  // diagnostics: phase stamps of the last block
+  auto stamp = [&](int i) {
+    if (threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[i] = t; }
+  };
+  unsigned long long t_begin = 0;
+  if (threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_begin));
+  // ---- v /= sqrt(pairwise(v^2)); v /= max(v)   (methods.py:46-51)
+  for (int o = threadIdx.x; o < O; o += FIN_THREADS) s_v[o] = v[o];
+  __syncthreads();
+  if (O <= 128 * MAX_LEAVES) {
+    if (threadIdx.x < 32) {  // lane-parallel replay of NumPy's pairwise recursion (leaves are independent)
+      const int lane = threadIdx.x;
+      np_for_each_leaf(O, [&](int leaf, int st, int ln) {
+        if ((leaf & 31) == lane && leaf < MAX_LEAVES) s_leaf[leaf] = np_leaf_sum<true>(s_v + st, ln);
+      });
+      __syncwarp();
+      if (lane == 0) {
+        int next = 0;
+        s_norm = __fsqrt_rn(np_combine_leaves(s_leaf, O, &next));
+      }
+    }
+  } else if (threadIdx.x == 0) {
+    s_norm = __fsqrt_rn(np_pairwise<true>(s_v, O));
+  }
+  __syncthreads();
+  const float nrm = s_norm;
+  float mx = -INFINITY;
+  for (int o = threadIdx.x; o < O; o += FIN_THREADS) {
+    const float x = __fdiv_rn(s_v[o], nrm);
+    s_v[o] = x;
+    mx = fmaxf(mx, x);
+  }
+  {
+    unsigned int a, b;  // max of non-negative floats == max of their bit patterns; NaN (0/0) handled below
+    block_count2(0u, 0u, s_red, &a, &b);  // barrier only
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = __float_as_uint(mx);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float m2 = -INFINITY;
+      for (int w2 = 0; w2 < FIN_THREADS / 32; ++w2) m2 = fmaxf(m2, __uint_as_float(s_red[w2]));
+      s_norm = m2;
+    }
+    __syncthreads();
+  }
+  mx = s_norm;
+  for (int o = threadIdx.x; o < O; o += FIN_THREADS) v[o] = __fdiv_rn(s_v[o], mx);
+  // ---- last block to finish computes the threshold over all layers
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) dbg[0] = t_begin;
+  stamp(1);
+  const int n = lt.voff[lt.nlayers];
+  unsigned int* s_k = reinterpret_cast<unsigned int*>(dsm);
+  unsigned int nan = 0;
+  for (int i = threadIdx.x; i < n; i += FIN_THREADS) {
+    const float x = __ldcg(values + i);
+    s_k[i] = __float_as_uint(x);
+    nan |= (x != x);
+  }
+  __syncthreads();
+  unsigned int nn, dummy;
+  block_count2(nan, 0u, s_red, &nn, &dummy);
+  if (nn) {  // np.percentile returns nan if any value is nan (an all-zero layer gives 0/0): nothing is < nan
+    if (threadIdx.x == 0) *thr = __longlong_as_double(0x7ff8000000000000LL);
+    if (keep)
+      for (int i = threadIdx.x; i < n; i += FIN_THREADS) keep[i] = 1;
+    return;
+  }
+  stamp(2);
+  const unsigned int r0 = (unsigned int)k, r1 = (unsigned int)((k + 1 < n) ? k + 1 : (long long)n - 1);
+  unsigned int p0 = 0, p1 = 0;
+  // The rounds run on ONE SM, so what they cost is warp-instructions issued (4 per clock), not latency: only the
+  // first SEL_THREADS threads take part (the others leave), keys sit in registers (n <= KPT*SEL_THREADS, else shared
+  // memory), the two ranks share one compare while their prefixes coincide, and the cross-warp sum is: redux -> one
+  // slot per warp -> ONE named barrier -> every warp adds the slots itself (slots alternate by round parity).
+  constexpr int SEL_THREADS = 512, SEL_WARPS = SEL_THREADS / 32, KPT = 24;
+  __shared__ unsigned int s_part[2][2][SEL_WARPS];
+  __syncthreads();  // s_k complete, NaN decision taken by everyone
+  if (threadIdx.x >= SEL_THREADS) return;
+  const bool in_regs = n <= KPT * SEL_THREADS;
+  unsigned int kreg[KPT];
+#pragma unroll
+  for (int u = 0; u < KPT; ++u) {
+    const int i = u * SEL_THREADS + threadIdx.x;
+    kreg[u] = (in_regs && i < n) ? s_k[i] : 0xffffffffu;  // padding never counts as "below"
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int bit = 30, r = 0; bit >= 0; --bit, ++r) {  // keys < 2^31
+    const unsigned int c0 = p0 | (1u << bit), c1 = p1 | (1u << bit);
+    const bool split = p0 != p1;  // block-uniform
+    unsigned int n0 = 0, n1 = 0;
+    if (in_regs) {
+#pragma unroll
+      for (int u = 0; u < KPT; ++u) n0 += kreg[u] < c0;
+      if (split) {
+#pragma unroll
+        for (int u = 0; u < KPT; ++u) n1 += kreg[u] < c1;
+      }
+    } else {
+      for (int i = threadIdx.x; i < n; i += SEL_THREADS) {
+        const unsigned int key = s_k[i];
+        n0 += key < c0;
+        n1 += key < c1;
+      }
+    }
+    n0 = __reduce_add_sync(0xffffffffu, n0);
+    if (split || !in_regs) n1 = __reduce_add_sync(0xffffffffu, n1);
+    if (lane == 0) {
+      s_part[r & 1][0][wid] = n0;
+      s_part[r & 1][1][wid] = n1;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(SEL_THREADS) : "memory");
+    const unsigned int t0 = __reduce_add_sync(0xffffffffu, lane < SEL_WARPS ? s_part[r & 1][0][lane] : 0u);
+    unsigned int t1 = t0;
+    if (split || !in_regs) t1 = __reduce_add_sync(0xffffffffu, lane < SEL_WARPS ? s_part[r & 1][1][lane] : 0u);
+    if (t0 <= r0) p0 = c0;  // at most r0 keys below the candidate: the r0-th smallest is >= candidate
+    if (t1 <= r1) p1 = c1;
+  }
+  double t;
+  {
+    const double a = (double)__uint_as_float(p0);
+    const double b = (double)__uint_as_float(p1);
+    const double diff = __dsub_rn(b, a);
+    t = __dadd_rn(a, __dmul_rn(diff, gamma));
+    if (gamma >= 0.5) t = __dsub_rn(b, __dmul_rn(diff, __dsub_rn(1.0, gamma)));
+  }
+  stamp(3);
+  if (threadIdx.x == 0) *thr = t;
+  if (keep)
+    for (int i = threadIdx.x; i < n; i += SEL_THREADS) keep[i] = ((double)__uint_as_float(s_k[i]) < t) ? 0 : 1;
+  stamp(4);
+}
+
 __global__ void filter_keep_kernel(const float* __restrict__ v, int n, const double* __restrict__ thr,
                                    uint8_t* __restrict__ keep) {
   const double t = *thr;
@@ -349,12 +676,30 @@ int build_layers(LayerTable* lt, const float* const* w, float* const* masks, con
     const long long thr = (taps[l] == 1) ? O[l] : (long long)O[l] * taps[l];
     // per-layer thread slots rounded up to whole blocks; for taps>1 a block must hold whole filters
     long long slots;
-    if (taps[l] == 1) slots = ((thr * 32 + SS_THREADS - 1) / SS_THREADS) * SS_THREADS;  // one warp per filter
+    if (w && taps[l] == 9 && (C[l] % TL_C) == 0 && (O[l] % TL_F) == 0) slots = 0;  // tiled path
+    else if (taps[l] == 1) slots = ((thr * 32 + SS_THREADS - 1) / SS_THREADS) * SS_THREADS;  // one warp per filter
     else {
       const int fpb = SS_THREADS / taps[l];  // filters per block
       slots = (long long)((O[l] + fpb - 1) / fpb) * SS_THREADS;
     }
     lt->toff[l + 1] = lt->toff[l] + (int)slots;
+  }
+  // tiled layers, largest C first (insertion sort; nlayers <= 64)
+  lt->ntiled = 0;
+  for (int l = 0; l < nlayers; ++l) {
+    if (!(w && taps[l] == 9 && (C[l] % TL_C) == 0 && (O[l] % TL_F) == 0)) continue;
+    int pos = lt->ntiled++;
+    while (pos > 0 && C[lt->torder[pos - 1]] < C[l]) {
+      lt->torder[pos] = lt->torder[pos - 1];
+      --pos;
+    }
+    lt->torder[pos] = l;
+  }
+  lt->tblk[0] = 0;
+  for (int i = 0; i < lt->ntiled; ++i) lt->tblk[i + 1] = lt->tblk[i] + O[lt->torder[i]] / TL_F;
+  for (int i = lt->ntiled; i < MAX_LAYERS; ++i) {
+    lt->torder[i] = 0;
+    lt->tblk[i + 1] = lt->tblk[lt->ntiled];
   }
   for (int l = nlayers; l < MAX_LAYERS; ++l) {
     lt->w[l] = nullptr;
@@ -367,6 +712,32 @@ int build_layers(LayerTable* lt, const float* const* w, float* const* masks, con
   return 0;
 }
 
+}  // namespace
+
+namespace {
+int launch_sumsq(const LayerTable& lt, float* d_values, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    MC_CUDA(cudaFuncSetAttribute(filter_sumsq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SUMSQ_SMEM));
+    attr_set = true;
+  }
+  const int n_tiled = lt.tblk[lt.ntiled];
+  const int n_generic = lt.toff[lt.nlayers] / SS_THREADS;
+  const int first_wave = n_tiled < mc_num_sms() ? n_tiled : mc_num_sms();
+  if (n_tiled + n_generic == 0) return 0;
+  const char* dbg = getenv("MCB200_SUMSQ_ONLY");  // timing experiments only (results are incomplete)
+  if (dbg && dbg[0] == 't') {
+    filter_sumsq_kernel<<<n_tiled, SS_THREADS, SUMSQ_SMEM, stream>>>(lt, d_values, n_tiled, first_wave);
+    return 0;
+  }
+  if (dbg && dbg[0] == 'g') {
+    filter_sumsq_kernel<<<n_generic, SS_THREADS, SUMSQ_SMEM, stream>>>(lt, d_values, 0, 0);
+    return 0;
+  }
+  filter_sumsq_kernel<<<n_tiled + n_generic, SS_THREADS, SUMSQ_SMEM, stream>>>(lt, d_values, n_tiled, first_wave);
+  MC_LAUNCH_CHECK("filter_sumsq_kernel");
+  return 0;
+}
 }  // namespace
 
 extern "C" int mc_filter_values(const float* const* h_w_ptrs, const int* h_O, const int* h_C, const int* h_kh,
@@ -384,11 +755,8 @@ extern "C" int mc_filter_values(const float* const* h_w_ptrs, const int* h_O, co
   LayerTable lt;
   int rc = build_layers(&lt, h_w_ptrs, nullptr, h_O, h_C, taps, nlayers, "mc_filter_values");
   if (rc) return rc;
-  // with taps>1 the in-block position of a filter is local/taps: filters-per-block packing needs local indices that
-  // restart per block -> remap: thread slot -> (block-local filter, tap)
-  const int nblocks = lt.toff[nlayers] / SS_THREADS;
-  filter_sumsq_kernel<<<nblocks, SS_THREADS, 0, stream>>>(lt, d_values);
-  MC_LAUNCH_CHECK("filter_sumsq_kernel");
+  rc = launch_sumsq(lt, d_values, stream);
+  if (rc) return rc;
   filter_norm_kernel<<<nlayers, 256, 0, stream>>>(lt, d_values);
   MC_LAUNCH_CHECK("filter_norm_kernel");
   return 0;
@@ -431,6 +799,57 @@ extern "C" int mc_filter_masks(const float* d_values, const double* d_thr, const
   if (h_mask_ptrs) {
     for (int l = 0; l < nlayers; ++l) MC_CHECK_ARG(h_mask_ptrs[l] != nullptr, "mc_filter_masks: null mask %d", l);
     int blocks = lt.voff[nlayers];
+    const int cap = mc_num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    filter_mask_fill_kernel<<<blocks, 256, 0, stream>>>(lt, d_values, d_thr);
+    MC_LAUNCH_CHECK("filter_mask_fill_kernel");
+  }
+  return 0;
+}
+
+/* The whole of quick_filter_prune in one call (3 launches: per-filter sums, normalise + percentile + keep flags, mask
+ * fill).  See include/mcb200.h. */
+extern "C" size_t mc_workspace_bytes_filter_prune(void) { return 256; }
+
+extern "C" int mc_filter_prune(const float* const* h_w_ptrs, const int* h_O, const int* h_C, const int* h_kh,
+                               const int* h_kw, int nlayers, int64_t k, double gamma, float* d_values, double* d_thr,
+                               float* const* h_mask_ptrs, uint8_t* d_keep, void* d_ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MC_CHECK_ARG(h_w_ptrs && h_O && h_C && h_kh && h_kw && d_values && d_thr && d_ws, "mc_filter_prune: null pointer");
+  MC_CHECK_ARG(nlayers > 0 && nlayers <= MAX_LAYERS, "mc_filter_prune: nlayers out of range");
+  if (ws_bytes < mc_workspace_bytes_filter_prune()) return mc_set_error(MC_ERR_WS, "mc_filter_prune: workspace too small");
+  int taps[MAX_LAYERS];
+  int max_o = 0;
+  for (int l = 0; l < nlayers; ++l) {
+    MC_CHECK_ARG(h_kh[l] == h_kw[l] && h_kh[l] >= 1 && h_kh[l] * h_kw[l] <= 49,
+                 "mc_filter_prune: layer %d kernel %dx%d unsupported (square, <=7x7)", l, h_kh[l], h_kw[l]);
+    MC_CHECK_ARG(h_w_ptrs[l] != nullptr, "mc_filter_prune: layer %d null weight", l);
+    MC_CHECK_ARG(!h_mask_ptrs || h_mask_ptrs[l] != nullptr, "mc_filter_prune: null mask %d", l);
+    taps[l] = h_kh[l] * h_kw[l];
+    if (h_O[l] > max_o) max_o = h_O[l];
+  }
+  LayerTable lt;
+  int rc = build_layers(&lt, h_w_ptrs, h_mask_ptrs, h_O, h_C, taps, nlayers, "mc_filter_prune");
+  if (rc) return rc;
+  const int n = lt.voff[nlayers];
+  MC_CHECK_ARG(k >= 0 && k < n, "mc_filter_prune: rank out of range");
+  MC_CHECK_ARG(gamma >= 0.0 && gamma < 1.0, "mc_filter_prune: gamma must be in [0,1)");
+  const size_t fin_smem = (size_t)(n > max_o ? n : max_o) * sizeof(float);
+  if (fin_smem > 200 * 1024) return mc_set_error(MC_ERR_SHAPE, "mc_filter_prune: %d filters exceed the single-block select", n);
+  static size_t fin_attr = 0;
+  if (fin_smem > fin_attr) {
+    MC_CUDA(cudaFuncSetAttribute(filter_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+    fin_attr = fin_smem;
+  }
+  MC_CUDA(cudaMemsetAsync(d_ws, 0, 8, stream));
+  rc = launch_sumsq(lt, d_values, stream);
+  if (rc) return rc;
+  filter_finish_kernel<<<nlayers, FIN_THREADS, fin_smem, stream>>>(lt, d_values, (long long)k, gamma, d_thr, d_keep,
+                                                                   reinterpret_cast<unsigned int*>(d_ws));
+  MC_LAUNCH_CHECK("filter_finish_kernel");
+  if (h_mask_ptrs) {
+    // the fill kernel addresses layer l's filter o at mask[l] + o*per: per-filter element count in C, taps = 1
+    int blocks = n;
     const int cap = mc_num_sms() * 16;
     if (blocks > cap) blocks = cap;
     filter_mask_fill_kernel<<<blocks, 256, 0, stream>>>(lt, d_values, d_thr);

@@ -88,47 +88,106 @@ class _ParamIndex(object):
         self.pdicts = [m._parameters for m in mods]
         self.mdicts = [m._modules for m in mods]
         flat = self._flat(self.pdicts)
-        self.pids = tuple(map(id, flat))
-        self.mids = tuple(map(id, self._flat(self.mdicts)))
+        self.ids = tuple(map(id, flat)) + tuple(map(id, self._flat(self.mdicts)))
         uniq, seen_p = [], set()
         for i, p in enumerate(flat):  # parameters() order: first occurrence of every non-None parameter
             if p is not None and id(p) not in seen_p:
                 seen_p.add(id(p))
                 uniq.append(i)
         self.uniq = uniq
+        self.plans = {}  # conv_only -> _PrunePlan
 
     @staticmethod
     def _flat(dicts):
         return list(_chain.from_iterable(map(dict.values, dicts)))
 
-    def parameters(self):
-        """Current parameter list, or None when the module tree changed since the walk."""
+    def flat_parameters(self):
+        """Current values of every module's _parameters dict (with None / duplicates), or None when the module
+        tree changed since the walk."""
         flat = self._flat(self.pdicts)
-        if tuple(map(id, flat)) != self.pids or tuple(map(id, self._flat(self.mdicts))) != self.mids:
+        if tuple(map(id, _chain(flat, _chain.from_iterable(map(dict.values, self.mdicts))))) != self.ids:
             return None
-        return [flat[i] for i in self.uniq]
+        return flat
+
+    def parameters(self):
+        flat = self.flat_parameters()
+        return None if flat is None else [flat[i] for i in self.uniq]
+
+
+def _index(model):
+    """(index, flat parameter slots) for the model, rebuilding the index when the module tree changed."""
+    idx = model.__dict__.get('_b200_param_index')
+    flat = idx.flat_parameters() if idx is not None else None
+    if flat is None:
+        idx = model.__dict__['_b200_param_index'] = _ParamIndex(model)
+        flat = idx.flat_parameters()
+    return idx, flat
 
 
 def _all_parameters(model):
-    idx = model.__dict__.get('_b200_param_index')
-    params = idx.parameters() if idx is not None else None
-    if params is None:
-        idx = model.__dict__['_b200_param_index'] = _ParamIndex(model)
-        params = idx.parameters()
-    return params
+    idx, flat = _index(model)
+    return [flat[i] for i in idx.uniq]
+
+
+class _PrunePlan(object):
+    """Everything about the prunable tensors that only depends on their shapes: which parameter slots, the ctypes size
+    tables for the C-ABI, the layout of the flat mask buffer."""
+
+    def __init__(self, idx, flat, conv_only):
+        self.slots, self.shapes = [], []
+        for i in idx.uniq:
+            p = flat[i]
+            nd = p.dim()
+            if (nd == 4) if conv_only else (nd != 1):
+                self.slots.append(i)
+                self.shapes.append(p.shape)
+        self.numels = [int(np.prod(sh)) if len(sh) else 1 for sh in self.shapes]
+        self.n = sum(self.numels)
+        self.sizes64 = _lib.int64_array(self.numels)
+        self.offs, off = [], 0
+        for ne in self.numels:  # every mask starts 16-byte aligned inside the flat buffer
+            self.offs.append(off)
+            off += (ne + 3) // 4 * 4
+        self.flat_len = off
+        if conv_only:
+            self.O = [sh[0] for sh in self.shapes]
+            self.tables = tuple(_lib.int_array([sh[d] for sh in self.shapes]) for d in range(4))
+        self.ok_ptrs = None  # data pointers of the last call that passed the device/dtype/contiguity checks
+
+
+def _plan_and_tensors(model, conv_only):
+    """(plan, tensors): the prunable parameter data tensors in parameters() order, validated (CUDA, float32,
+    contiguous).  The per-tensor checks are skipped when the storage pointers are the ones already checked."""
+    idx, flat = _index(model)
+    plan = idx.plans.get(conv_only)
+    if plan is not None:
+        for i, sh in zip(plan.slots, plan.shapes):
+            if flat[i].shape != sh:  # .data was re-assigned with another shape
+                plan = None
+                break
+    if plan is None:
+        plan = idx.plans[conv_only] = _PrunePlan(idx, flat, conv_only)
+    tensors = [flat[i] for i in plan.slots]
+    ptrs = [t.data_ptr() for t in tensors]
+    if ptrs != plan.ok_ptrs:
+        checked = []
+        all_contig = True
+        for t in tensors:
+            if not t.is_cuda:
+                _lib.require_cuda(t, "weight_prune / quick_filter_prune")
+            if t.dtype != torch.float32:
+                raise TypeError("pruners expect float32 parameters, got %s" % t.dtype)
+            if not t.is_contiguous():
+                all_contig = False
+                t = t.data.contiguous()
+            checked.append(t)
+        tensors = checked
+        plan.ok_ptrs = ptrs if all_contig else None
+    return plan, tensors
 
 
 def _prunable(model, conv_only):
-    params = []
-    for p in _all_parameters(model):
-        nd = p.dim()
-        if (nd == 4) if conv_only else (nd != 1):
-            if not p.is_cuda:
-                _lib.require_cuda(p, "weight_prune / quick_filter_prune")
-            if p.dtype != torch.float32:
-                raise TypeError("pruners expect float32 parameters, got %s" % p.dtype)
-            params.append(p.data if p.is_contiguous() else p.data.contiguous())
-    return params
+    return [t.data for t in _plan_and_tensors(model, conv_only)[1]]
 
 
 def weight_threshold(params, pruning_perc):
@@ -173,26 +232,28 @@ def weight_prune(model, pruning_perc):
     One cooperative kernel launch (mc_weight_prune_masks): W is read once and the masks are written once.
     '''
     lib = _lib.load()
-    params = _prunable(model, conv_only=False)
+    plan, params = _plan_and_tensors(model, conv_only=False)
     if not params:
         return []
     if len(params) > _lib.MC_MAX_SEGMENTS:  # more tensors than one launch takes: threshold first, then mask in groups
-        return _weight_prune_grouped(lib, params, pruning_perc)
-    n = sum(p.numel() for p in params)
+        return _weight_prune_grouped(lib, [t.data for t in params], pruning_perc)
+    n = plan.n
     k, gamma = _rank_cached(n, pruning_perc, np.float32)
     dev = params[0].device
-    flat, offs = _flat_like_all(params)
-    base = flat.data_ptr()
-    mask_ptrs = (_lib.c_void_p * len(params))(*[base + 4 * o for o in offs])
     ws_bytes = lib.mc_workspace_bytes_kth_abs_select(n)
+    # one allocation: the masks (flat, every mask 16-byte aligned) followed by the 3 result floats
+    flat = torch.empty(plan.flat_len + 4, dtype=torch.float32, device=dev)
+    base = flat.data_ptr()
+    mask_ptrs = (_lib.c_void_p * len(params))(*[base + 4 * o for o in plan.offs])
     ws = _workspace(dev, ws_bytes)
-    out3 = torch.empty(3, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.mc_weight_prune_masks(_lib.ptr_array(params), mask_ptrs,
-                                             _lib.int64_array([t.numel() for t in params]), len(params), k, gamma,
-                                             out3.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr()),
+        _lib.check(lib.mc_weight_prune_masks(_lib.ptr_array(params), mask_ptrs, plan.sizes64, len(params), k, gamma,
+                                             base + 4 * plan.flat_len, ws.data_ptr(), ws_bytes, _lib.stream_ptr()),
                    "mc_weight_prune_masks")
-    return _views(flat, offs, params)  # the per-parameter views are created while the kernel runs
+    # the per-parameter views are created while the kernel runs
+    return [v.view(sh) for v, sh in zip(torch.split(flat[:plan.flat_len], [(ne + 3) // 4 * 4 for ne in plan.numels]),
+                                        plan.shapes)] if all(ne % 4 == 0 for ne in plan.numels) else \
+        [flat[o:o + ne].view(sh) for o, ne, sh in zip(plan.offs, plan.numels, plan.shapes)]
 
 
 def _weight_prune_grouped(lib, params, pruning_perc):
@@ -236,26 +297,30 @@ def quick_filter_prune(model, pruning_perc, return_keep=False):
     With return_keep=True also returns the per-layer surviving-filter index tensors (int64, ascending).
     '''
     lib = _lib.load()
-    params = _prunable(model, conv_only=True)
+    plan, params = _plan_and_tensors(model, conv_only=True)
     if not params:
         return ([], []) if return_keep else []
+    if len(params) > _lib.MC_MAX_SEGMENTS:
+        raise NotImplementedError("quick_filter_prune: more than %d conv layers" % _lib.MC_MAX_SEGMENTS)
     dev = params[0].device
-    values = filter_values(params)
-    n = values.numel()
-    k, gamma = percentile_rank(n, pruning_perc, np.float64)
-    thr = torch.empty(1, dtype=torch.float64, device=dev)
-    masks = _empty_like_all(params)
-    keep = torch.empty(n, dtype=torch.uint8, device=dev)
-    O = [p.shape[0] for p in params]
-    per = [p.numel() // p.shape[0] for p in params]
+    O = plan.O
+    n = sum(O)
+    k, gamma = _rank_cached(n, pruning_perc, np.float64)
+    # one allocation: masks (flat, 16-byte aligned each) | values [n] f32 | thr f64 | ticket + diagnostics | keep [n] u8
+    n4 = (n + 1) // 2 * 2
+    flat = torch.empty(plan.flat_len + n4 + 2 + 64 + (n + 3) // 4, dtype=torch.float32, device=dev)
+    mbase = flat.data_ptr()
+    vbase = mbase + 4 * plan.flat_len
+    mask_ptrs = (_lib.c_void_p * len(params))(*[mbase + 4 * o for o in plan.offs])
     with torch.cuda.device(dev):
-        _lib.check(lib.mc_filter_threshold(values.data_ptr(), n, k, gamma, thr.data_ptr(), None, 0,
-                                           _lib.stream_ptr()), "mc_filter_threshold")
-        _lib.check(lib.mc_filter_masks(values.data_ptr(), thr.data_ptr(), _lib.int_array(O), _lib.int_array(per),
-                                       len(params), _lib.ptr_array(masks), keep.data_ptr(), _lib.stream_ptr()),
-                   "mc_filter_masks")
+        _lib.check(lib.mc_filter_prune(_lib.ptr_array(params), plan.tables[0], plan.tables[1], plan.tables[2],
+                                       plan.tables[3], len(params), k, gamma, vbase, vbase + 4 * n4, mask_ptrs,
+                                       vbase + 4 * n4 + 8 + 256, vbase + 4 * n4 + 8, 256, _lib.stream_ptr()),
+                   "mc_filter_prune")
+    masks = [flat[o:o + ne].view(sh) for o, ne, sh in zip(plan.offs, plan.numels, plan.shapes)]  # while the kernels run
     if not return_keep:
         return masks
+    keep = flat[plan.flat_len + n4 + 2 + 64:].view(torch.uint8)[:n]
     keep_idx = [torch.nonzero(kp, as_tuple=False).flatten() for kp in torch.split(keep, O)]
     return masks, keep_idx
 

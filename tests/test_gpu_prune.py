@@ -201,6 +201,43 @@ def test_filter_prune_odd_shapes():
             assert a.cpu().tolist() == np.nonzero(b)[0].tolist()
 
 
+def test_filter_prune_tiled_and_generic_mix():
+    # 3x3 layers with C % 32 == 0 and O % 32 == 0 take the tiled shared-memory path, the others the generic one; an
+    # all-zero layer gives 0/0 -> NaN values -> NaN percentile -> nothing is pruned (NumPy semantics)
+    torch.manual_seed(9)
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = torch.nn.Conv2d(32, 32, 3)      # tiled, one chunk
+            self.b = torch.nn.Conv2d(96, 160, 3)     # tiled, 3 chunks, 5 groups
+            self.c = torch.nn.Conv2d(64, 48, 3)      # generic (O % 32 != 0)
+            self.d = torch.nn.Conv2d(40, 64, 3)      # generic (C % 32 != 0)
+            self.e = torch.nn.Conv2d(320, 32, 3)     # tiled, 10 chunks
+            self.f = torch.nn.Conv2d(64, 37, 1)      # 1x1
+
+    net = Net().to(DEV)
+    cw = [p.detach().cpu().numpy() for p in net.parameters() if p.dim() == 4]
+    for perc in (0., 25., 61.8, 100.):
+        masks, keep = mc.quick_filter_prune(net, perc, return_keep=True)
+        _, _, keep_o, masks_o = prune_oracle.quick_filter_prune_np(cw, perc)
+        for a, b in zip(masks, masks_o):
+            assert np.array_equal(a.cpu().numpy(), b), "perc %s" % perc
+        for a, b in zip(keep, keep_o):
+            assert a.cpu().tolist() == np.nonzero(b)[0].tolist()
+    with torch.no_grad():
+        net.c.weight.zero_()
+    cw = [p.detach().cpu().numpy() for p in net.parameters() if p.dim() == 4]
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _, thr_o, keep_o, _ = prune_oracle.quick_filter_prune_np(cw, 50.)
+    assert np.isnan(thr_o)
+    _, keep = mc.quick_filter_prune(net, 50., return_keep=True)
+    for a, b in zip(keep, keep_o):
+        assert a.cpu().tolist() == np.nonzero(b)[0].tolist()
+
+
 def test_count_zeros_and_unaligned_segments():
     from modelcompression_b200.pruning.weightPruning.utils import count_zeros
     torch.manual_seed(0)
