@@ -216,6 +216,54 @@ int mc_unpack_pnhwc(const void* d_in, float* d_out, int B, int H, int W, int C, 
 /* NCHW fp32 [B,C,H,W] -> PNHWC bf16 (channels >= C up to ld zeroed; pad rows/cols zeroed). */
 int mc_pack_pnhwc(const float* d_in, void* d_out, int B, int H, int W, int C, int ld_out, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------
+ * Masked retrain step — replaces, for model.train(), the autograd graph of src/train.py:221-235 over the Darknet of
+ * src/nets.py:779-822: F.conv2d(x, weight*mask) forward/dgrad/wgrad (layers.py:53-64), nn.BatchNorm2d in training mode
+ * (batch statistics, eps 1e-5, running stats momentum 0.1; nets.py:802), nn.LeakyReLU(0.1) (:809), nn.MaxPool2d(2,2)
+ * (:821) and their backward.  Convolutions (forward and data gradient) reuse mc_conv_fwd; the weight gradient is
+ * mc_conv_wgrad.  All activations / gradients are PNHWC bf16, per-channel statistics and weight gradients fp32.
+ * -------------------------------------------------------------------------------------------- */
+
+/* d_sum[c] = sum over rows of z[row, ch_off+c]; d_sumsq[c] likewise of z^2 (may be NULL).  Pad rows are zero.       */
+int mc_col_stats(const void* d_z, int64_t rows, int C, int ld, int ch_off, float* d_sum, float* d_sumsq, void* stream);
+
+/* Batch statistics -> per-channel (scale, shift) of y = z*scale + shift, mean, invstd; running stats updated in place
+ * (running = (1-momentum)*running + momentum*batch, unbiased variance) when the pointers are not NULL.              */
+int mc_bn_finalize(const float* d_sum, const float* d_sumsq, int C, double count, const float* d_gamma,
+                   const float* d_beta, float eps, float momentum, float* d_running_mean, float* d_running_var,
+                   float* d_scale, float* d_shift, float* d_mean, float* d_invstd, void* stream);
+
+/* out = act(z*scale + shift) at interior pixels, 0 at pads.  reorg=0: out[row, ch_off + c]; reorg=1: the Reorg(2)
+ * shuffle into a (H/2, W/2) buffer, channel ((y&1)*2+(x&1))*C + c + ch_off (interior rows only).                   */
+int mc_bn_apply(const void* d_z, int ld_z, int B, int H, int W, int C, const float* d_scale, const float* d_shift,
+                int leaky, void* d_out, int ld_out, int ch_off, int reorg, void* stream);
+
+/* BatchNorm(training) + leaky backward: g = da * leaky'(.), dbeta = sum g, dgamma = sum g*xhat,
+ * dz = gamma*invstd*(g - dbeta/N - xhat*dgamma/N) (0 at pads).  da is read through (ld_da, ch_off, reorg) so a concat
+ * slice / reorg'd gradient needs no un-shuffling copy.                                                              */
+int mc_bn_backward(const void* d_z, int ld_z, const void* d_da, int ld_da, int ch_off, int reorg, int B, int H, int W,
+                   int C, const float* d_mean, const float* d_invstd, const float* d_gamma, const float* d_beta,
+                   int leaky, float* d_dbeta, float* d_dgamma, void* d_dz, int ld_dz, void* stream);
+
+/* d_full[b,y,x,c] (+)= d_pooled[b,y/2,x/2,c] where a_full[b,y,x,c] is the first maximum of its 2x2 window.          */
+int mc_maxpool2x2_backward(const void* d_a_full, int ld_a, const void* d_dpooled, int ld_dp, int B, int H, int W, int C,
+                           void* d_dfull, int ld_df, int accumulate, void* stream);
+
+/* dgrad weights for mc_conv_fwd: bf16 [Cpad, taps*Ko], row c, column tap'*Ko + o = (w*mask)[o, c, taps-1-tap'].      */
+int mc_pack_conv_weights_dgrad(const float* d_w, const float* d_mask, int O, int C, int ksize, void* d_wpack, int Cpad,
+                               int Ko, void* stream);
+
+/* dW[O,C,k,k] (fp32, PyTorch layout) = mask * sum_p dZ[p, o] * A[p + off(tap), c]  on tcgen05 (both operands
+ * MN-major from TMA); split over the pixel rows, partials in the workspace.  accumulate!=0 adds to d_dw.          */
+int mc_conv_wgrad(const void* d_a, int lda, int C, const void* d_dz, int ld_dz, int O, int B, int H, int W, int ksize,
+                  const float* d_mask, float* d_dw, int accumulate, void* d_ws, size_t ws_bytes, void* stream);
+size_t mc_workspace_bytes_conv_wgrad(int B, int H, int W, int C, int O, int ksize);
+
+/* Weight gradient of the first layer: x is the fp32 NCHW image [B,C<=4,H,W], 3x3, O <= 32 (CUDA cores).           */
+int mc_conv_wgrad_first(const float* d_x, const void* d_dz, int ld_dz, int B, int H, int W, int C, int O,
+                        const float* d_mask, float* d_dw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

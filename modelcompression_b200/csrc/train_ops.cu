@@ -1,0 +1,444 @@
+// train_ops.cu — batch-statistics BatchNorm, leaky-ReLU and max-pool pieces of the masked retrain step.
+//
+// Replaces, for the training-mode forward/backward of src/train.py:221-235 on the Darknet of src/nets.py:779-822:
+// nn.BatchNorm2d in training mode (batch mean / biased variance, eps 1e-5, running stats momentum 0.1),
+// nn.LeakyReLU(0.1), nn.MaxPool2d(2,2) and their autograd backward.  Convolutions (forward, dgrad, wgrad) are the
+// tensor-core kernels in conv_tcgen05.cu / conv_wgrad.cu; these kernels are the HBM-bound glue between them.
+//
+// All activations/gradients are PNHWC bf16 ([rows, ld]; pad rows/columns hold zeros), per-channel statistics fp32.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TB = 256;
+
+__device__ __forceinline__ bool interior_row(long long row, int H, int W, int* b, int* y, int* x) {
+  const int xx = (int)(row % (W + 1));
+  const long long t = row / (W + 1);
+  const int yy = (int)(t % (H + 1));
+  *b = (int)(t / (H + 1));
+  *y = yy;
+  *x = xx;
+  return xx < W && yy < H;
+}
+
+// ---- column sums: sum[c] += z[row,c], sumsq[c] += z[row,c]^2 over all rows (pad rows are zero) -----------------------
+// block = 256 threads = 32 channel-octets x 8 row lanes; grid.x strides rows, grid.y strides channel groups of 256.
+__global__ void __launch_bounds__(TB) col_stats_kernel(const __nv_bfloat16* __restrict__ z, long long rows, int C, int ld,
+                                                       int ch_off, float* __restrict__ sum, float* __restrict__ sumsq) {
+  __shared__ float s_a[8][256], s_b[8][256];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c0 = blockIdx.y * 256 + cg * 8;
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
+  if (c0 < C) {
+    for (long long r = (long long)blockIdx.x * 8 + rl; r < rows; r += (long long)gridDim.x * 8) {
+      const uint4 q = *reinterpret_cast<const uint4*>(z + r * ld + ch_off + c0);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h[j]);
+        a[2 * j] += f.x; b[2 * j] += f.x * f.x;
+        a[2 * j + 1] += f.y; b[2 * j + 1] += f.y * f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s_a[rl][cg * 8 + j] = a[j]; s_b[rl][cg * 8 + j] = b[j]; }
+  __syncthreads();
+  const int c = blockIdx.y * 256 + threadIdx.x;
+  if (c < C) {
+    float ta = 0.f, tb = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { ta += s_a[k][threadIdx.x]; tb += s_b[k][threadIdx.x]; }
+    atomicAdd(&sum[c], ta);
+    if (sumsq) atomicAdd(&sumsq[c], tb);
+  }
+}
+
+// ---- BN finalize: batch mean / biased var -> (scale, shift, mean, invstd); running stats update --------------------
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, int C, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ invstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = (double)sum[c] / count;
+  double var = (double)sumsq[c] / count - m * m;
+  if (var < 0.0) var = 0.0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - (float)m * sc;
+  mean_out[c] = (float)m;
+  invstd_out[c] = invstd;
+  if (running_mean) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// ---- BN apply (+leaky): out = act(z*scale+shift), pads zero; optional reorg / channel-slice store ------------------
+__global__ void __launch_bounds__(TB) bn_apply_kernel(const __nv_bfloat16* __restrict__ z, int ld_z, int B, int H, int W,
+                                                      int C, const float* __restrict__ scale,
+                                                      const float* __restrict__ shift, int leaky,
+                                                      __nv_bfloat16* __restrict__ out, int ld_out, int ch_off, int reorg) {
+  const int C8 = (C + 7) / 8;
+  const long long rows = (long long)B * (H + 1) * (W + 1);
+  const long long total = rows * C8;
+  for (long long i = blockIdx.x * (long long)TB + threadIdx.x; i < total; i += (long long)gridDim.x * TB) {
+    const long long row = i / C8;
+    const int c0 = (int)(i - row * C8) * 8;
+    int b, y, x;
+    const bool in = interior_row(row, H, W, &b, &y, &x);
+    __align__(16) __nv_bfloat16 o[8];
+    if (in) {
+      const uint4 q = *reinterpret_cast<const uint4*>(z + row * ld_z + c0);
+      const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&q);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = 0.f;
+        if (c0 + j < C) {
+          v = fmaf(__bfloat162float(h[j]), scale[c0 + j], shift[c0 + j]);
+          if (leaky) v = fmaxf(v, 0.1f * v);
+        }
+        o[j] = __float2bfloat16_rn(v);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(0.f);
+    }
+    if (!reorg) {
+      __nv_bfloat16* dst = out + row * ld_out + ch_off + c0;
+      if (c0 + 8 <= C && ((ld_out | ch_off) & 7) == 0) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(o);
+      else
+        for (int j = 0; j < 8 && c0 + j < C; ++j) dst[j] = o[j];
+    } else if (in) {
+      const int Wo = W / 2 + 1, Ho = H / 2 + 1;
+      const long long orow = ((long long)b * Ho + (y >> 1)) * Wo + (x >> 1);
+      __nv_bfloat16* dst = out + orow * ld_out + ch_off + ((y & 1) * 2 + (x & 1)) * C + c0;
+      for (int j = 0; j < 8 && c0 + j < C; ++j) dst[j] = o[j];
+    }
+  }
+}
+
+// ---- BN + leaky backward -----------------------------------------------------------------------------------------
+// da is read through (ld_da, ch_off, reorg) so a concat slice / reorg'd tensor needs no un-shuffling copy.
+__device__ __forceinline__ const __nv_bfloat16* da_ptr(const __nv_bfloat16* da, long long row, int b, int y, int x, int H,
+                                                       int W, int C, int ld_da, int ch_off, int reorg) {
+  if (!reorg) return da + row * ld_da + ch_off;
+  const int Wo = W / 2 + 1, Ho = H / 2 + 1;
+  const long long orow = ((long long)b * Ho + (y >> 1)) * Wo + (x >> 1);
+  return da + orow * ld_da + ch_off + ((y & 1) * 2 + (x & 1)) * C;
+}
+
+// pass 1: dbeta[c] = sum g, dgamma[c] = sum g*xhat with g = da * leaky'(zhat), xhat = (z-mean)*invstd
+__global__ void __launch_bounds__(TB) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ z, int ld_z,
+                                                           const __nv_bfloat16* __restrict__ da, int ld_da, int ch_off,
+                                                           int reorg, int B, int H, int W, int C,
+                                                           const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           int leaky, float* __restrict__ dbeta, float* __restrict__ dgamma) {
+  __shared__ float s_a[TB], s_b[TB];
+  // block handles channel c = blockIdx.y*32 + (tid&31) over a strided set of rows; 8 row lanes per block
+  const int c = blockIdx.y * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
+  const long long rows = (long long)B * (H + 1) * (W + 1);
+  float sa = 0.f, sb = 0.f;
+  if (c < C) {
+    const float m = mean[c], is = invstd[c], g0 = gamma ? gamma[c] : 1.f, b0 = beta ? beta[c] : 0.f;
+    for (long long r = (long long)blockIdx.x * 8 + rl; r < rows; r += (long long)gridDim.x * 8) {
+      int b, y, x;
+      if (!interior_row(r, H, W, &b, &y, &x)) continue;
+      const float xh = (__bfloat162float(z[r * ld_z + c]) - m) * is;
+      float g = __bfloat162float(da_ptr(da, r, b, y, x, H, W, C, ld_da, ch_off, reorg)[c]);
+      if (leaky && (g0 * xh + b0) <= 0.f) g *= 0.1f;
+      sa += g;
+      sb += g * xh;
+    }
+  }
+  s_a[threadIdx.x] = sa;
+  s_b[threadIdx.x] = sb;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+    for (int k = 1; k < 8; ++k) { sa += s_a[k * 32 + threadIdx.x]; sb += s_b[k * 32 + threadIdx.x]; }
+    atomicAdd(&dbeta[c], sa);
+    atomicAdd(&dgamma[c], sb);
+  }
+}
+
+// pass 2: dz = gamma*invstd*(g - dbeta/N - xhat*dgamma/N) at interior pixels, 0 at pads.  With bn == 0 (no BatchNorm:
+// the head) dz = g.
+__global__ void __launch_bounds__(TB) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ z, int ld_z,
+                                                          const __nv_bfloat16* __restrict__ da, int ld_da, int ch_off,
+                                                          int reorg, int B, int H, int W, int C,
+                                                          const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          int leaky, const float* __restrict__ dbeta,
+                                                          const float* __restrict__ dgamma, float inv_count,
+                                                          __nv_bfloat16* __restrict__ dz, int ld_dz) {
+  const long long rows = (long long)B * (H + 1) * (W + 1);
+  const long long total = rows * C;
+  for (long long i = blockIdx.x * (long long)TB + threadIdx.x; i < total; i += (long long)gridDim.x * TB) {
+    const long long row = i / C;
+    const int c = (int)(i - row * C);
+    int b, y, x;
+    float v = 0.f;
+    if (interior_row(row, H, W, &b, &y, &x)) {
+      const float xh = (__bfloat162float(z[row * ld_z + c]) - mean[c]) * invstd[c];
+      float g = __bfloat162float(da_ptr(da, row, b, y, x, H, W, C, ld_da, ch_off, reorg)[c]);
+      if (leaky && (gamma[c] * xh + beta[c]) <= 0.f) g *= 0.1f;
+      v = gamma[c] * invstd[c] * (g - dbeta[c] * inv_count - xh * dgamma[c] * inv_count);
+    }
+    dz[row * ld_dz + c] = __float2bfloat16_rn(v);
+  }
+}
+
+// ---- max-pool 2x2/2 backward: gradient goes to the first maximum of each window (PyTorch scan order) ---------------
+__global__ void __launch_bounds__(TB) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ a_full, int ld_a,
+                                                         const __nv_bfloat16* __restrict__ d_pooled, int ld_dp, int B,
+                                                         int H, int W, int C, __nv_bfloat16* __restrict__ d_full,
+                                                         int ld_df, int accumulate) {
+  const long long rows = (long long)B * (H + 1) * (W + 1);
+  const long long total = rows * C;
+  const int Ho = H / 2, Wo = W / 2;
+  for (long long i = blockIdx.x * (long long)TB + threadIdx.x; i < total; i += (long long)gridDim.x * TB) {
+    const long long row = i / C;
+    const int c = (int)(i - row * C);
+    int b, y, x;
+    float v = 0.f;
+    if (interior_row(row, H, W, &b, &y, &x)) {
+      const int wy = y >> 1, wx = x >> 1;
+      const long long r00 = ((long long)b * (H + 1) + 2 * wy) * (W + 1) + 2 * wx;
+      const float v00 = __bfloat162float(a_full[r00 * ld_a + c]);
+      const float v01 = __bfloat162float(a_full[(r00 + 1) * ld_a + c]);
+      const float v10 = __bfloat162float(a_full[(r00 + W + 1) * ld_a + c]);
+      const float v11 = __bfloat162float(a_full[(r00 + W + 2) * ld_a + c]);
+      int arg = 0;
+      float best = v00;
+      if (v01 > best) { best = v01; arg = 1; }
+      if (v10 > best) { best = v10; arg = 2; }
+      if (v11 > best) { best = v11; arg = 3; }
+      if (arg == ((y & 1) * 2 + (x & 1))) {
+        const long long prow = ((long long)b * (Ho + 1) + wy) * (Wo + 1) + wx;
+        v = __bfloat162float(d_pooled[prow * ld_dp + c]);
+      }
+    }
+    __nv_bfloat16* dst = d_full + row * ld_df + c;
+    if (accumulate) v += __bfloat162float(*dst);
+    *dst = __float2bfloat16_rn(v);
+  }
+}
+
+inline int grid_for(long long total, int threads) {
+  long long blocks = (total + threads - 1) / threads;
+  const long long cap = (long long)mc_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace
+
+extern "C" int mc_col_stats(const void* d_z, int64_t rows, int C, int ld, int ch_off, float* d_sum, float* d_sumsq,
+                            void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MC_CHECK_ARG(d_z && d_sum && rows > 0 && C > 0, "mc_col_stats: bad argument");
+  MC_CHECK_ARG((ld % 8) == 0 && (ch_off % 8) == 0 && ch_off + ((C + 7) / 8) * 8 <= ld,
+               "mc_col_stats: ld/ch_off must be multiples of 8 and cover round_up(C,8) channels");
+  MC_CUDA(cudaMemsetAsync(d_sum, 0, sizeof(float) * C, stream));
+  if (d_sumsq) MC_CUDA(cudaMemsetAsync(d_sumsq, 0, sizeof(float) * C, stream));
+  long long gx = (rows + 8 * 64 - 1) / (8 * 64);
+  const long long cap = (long long)mc_num_sms() * 4;
+  if (gx > cap) gx = cap;
+  dim3 grid((unsigned)gx, (unsigned)((C + 255) / 256), 1);
+  col_stats_kernel<<<grid, TB, 0, stream>>>((const __nv_bfloat16*)d_z, rows, C, ld, ch_off, d_sum, d_sumsq);
+  MC_LAUNCH_CHECK("col_stats_kernel");
+  return 0;
+}
+
+extern "C" int mc_bn_finalize(const float* d_sum, const float* d_sumsq, int C, double count, const float* d_gamma,
+                              const float* d_beta, float eps, float momentum, float* d_running_mean,
+                              float* d_running_var, float* d_scale, float* d_shift, float* d_mean, float* d_invstd,
+                              void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MC_CHECK_ARG(d_sum && d_sumsq && d_gamma && d_beta && d_scale && d_shift && d_mean && d_invstd && C > 0 && count > 0,
+               "mc_bn_finalize: bad argument");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(d_sum, d_sumsq, C, count, d_gamma, d_beta, eps, momentum,
+                                                          d_running_mean, d_running_var, d_scale, d_shift, d_mean,
+                                                          d_invstd);
+  MC_LAUNCH_CHECK("bn_finalize_kernel");
+  return 0;
+}
+
+extern "C" int mc_bn_apply(const void* d_z, int ld_z, int B, int H, int W, int C, const float* d_scale,
+                           const float* d_shift, int leaky, void* d_out, int ld_out, int ch_off, int reorg,
+                           void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MC_CHECK_ARG(d_z && d_scale && d_shift && d_out && B > 0 && H > 0 && W > 0 && C > 0, "mc_bn_apply: bad argument");
+  MC_CHECK_ARG((ld_z % 8) == 0 && ld_z >= ((C + 7) / 8) * 8, "mc_bn_apply: ld_z must be a multiple of 8 covering C");
+  if (reorg) MC_CHECK_ARG((H % 2) == 0 && (W % 2) == 0, "mc_bn_apply: reorg needs even H,W");
+  const long long total = (long long)B * (H + 1) * (W + 1) * ((C + 7) / 8);
+  bn_apply_kernel<<<grid_for(total, TB), TB, 0, stream>>>((const __nv_bfloat16*)d_z, ld_z, B, H, W, C, d_scale, d_shift,
+                                                          leaky, (__nv_bfloat16*)d_out, ld_out, ch_off, reorg);
+  MC_LAUNCH_CHECK("bn_apply_kernel");
+  return 0;
+}
+
+extern "C" int mc_bn_backward(const void* d_z, int ld_z, const void* d_da, int ld_da, int ch_off, int reorg, int B, int H,
+                              int W, int C, const float* d_mean, const float* d_invstd, const float* d_gamma,
+                              const float* d_beta, int leaky, float* d_dbeta, float* d_dgamma, void* d_dz, int ld_dz,
+                              void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MC_CHECK_ARG(d_z && d_da && d_mean && d_invstd && d_gamma && d_beta && d_dbeta && d_dgamma && d_dz,
+               "mc_bn_backward: null pointer");
+  MC_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0, "mc_bn_backward: bad dims");
+  MC_CUDA(cudaMemsetAsync(d_dbeta, 0, sizeof(float) * C, stream));
+  MC_CUDA(cudaMemsetAsync(d_dgamma, 0, sizeof(float) * C, stream));
+  const long long rows = (long long)B * (H + 1) * (W + 1);
+  long long gx = (rows + 8 * 32 - 1) / (8 * 32);
+  const long long cap = (long long)mc_num_sms() * 8;
+  if (gx > cap) gx = cap;
+  dim3 grid((unsigned)gx, (unsigned)((C + 31) / 32), 1);
+  bn_bwd_reduce_kernel<<<grid, TB, 0, stream>>>((const __nv_bfloat16*)d_z, ld_z, (const __nv_bfloat16*)d_da, ld_da, ch_off,
+                                                reorg, B, H, W, C, d_mean, d_invstd, d_gamma, d_beta, leaky, d_dbeta,
+                                                d_dgamma);
+  MC_LAUNCH_CHECK("bn_bwd_reduce_kernel");
+  const float inv_count = 1.0f / (float)((double)B * H * W);
+  bn_bwd_apply_kernel<<<grid_for(rows * C, TB), TB, 0, stream>>>((const __nv_bfloat16*)d_z, ld_z, (const __nv_bfloat16*)d_da,
+                                                                 ld_da, ch_off, reorg, B, H, W, C, d_mean, d_invstd,
+                                                                 d_gamma, d_beta, leaky, d_dbeta, d_dgamma, inv_count,
+                                                                 (__nv_bfloat16*)d_dz, ld_dz);
+  MC_LAUNCH_CHECK("bn_bwd_apply_kernel");
+  return 0;
+}
+
+extern "C" int mc_maxpool2x2_backward(const void* d_a_full, int ld_a, const void* d_dpooled, int ld_dp, int B, int H,
+                                      int W, int C, void* d_dfull, int ld_df, int accumulate, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MC_CHECK_ARG(d_a_full && d_dpooled && d_dfull && B > 0 && H > 0 && W > 0 && C > 0, "mc_maxpool2x2_backward: bad argument");
+  MC_CHECK_ARG((H % 2) == 0 && (W % 2) == 0, "mc_maxpool2x2_backward: H, W must be even");
+  const long long total = (long long)B * (H + 1) * (W + 1) * C;
+  maxpool_bwd_kernel<<<grid_for(total, TB), TB, 0, stream>>>((const __nv_bfloat16*)d_a_full, ld_a,
+                                                             (const __nv_bfloat16*)d_dpooled, ld_dp, B, H, W, C,
+                                                             (__nv_bfloat16*)d_dfull, ld_df, accumulate);
+  MC_LAUNCH_CHECK("maxpool_bwd_kernel");
+  return 0;
+}
+
+// ---- dgrad weights: the data gradient of a 'same' 3x3 / 1x1 convolution is itself a 'same' convolution of dZ with the
+// spatially flipped, channel-transposed filter:  dA[p, c] = sum_{tap', o} dZ[p + off(tap'), o] * W[o, c, taps-1-tap'].
+// So dgrad reuses the forward tcgen05 kernel (mc_conv_fwd) on this packing: bf16 [Cpad, taps*Ko] K-major, row c,
+// column tap'*Ko + o  (Ko = round_up(O, 64)), masked like the forward weights (layers.py:59).
+namespace {
+__global__ void pack_dgrad_weights_kernel(const float* __restrict__ w, const float* __restrict__ mask, int O, int C,
+                                          int taps, __nv_bfloat16* __restrict__ out, int Cpad, int Ko) {
+  const long long total = (long long)Cpad * taps * Ko;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(i % Ko);
+    long long t = i / Ko;
+    const int tapp = (int)(t % taps);
+    const int c = (int)(t / taps);
+    float v = 0.f;
+    if (o < O && c < C) {
+      const long long src = ((long long)o * C + c) * taps + (taps - 1 - tapp);
+      v = w[src];
+      if (mask) v *= mask[src];
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// ---- weight gradient of the FIRST layer (3-channel fp32 NCHW image): too thin for a tensor-core tile (N = 3), so
+// CUDA cores: thread = (4 output channels, input channel, pixel slice) keeps 4 x 9 accumulators in registers over a
+// grid-stride sweep of the image lines; one shared-memory reduction and 9*C*O atomics per block at the end.
+constexpr int WF_THREADS = 256;
+__global__ void __launch_bounds__(WF_THREADS) wgrad_first_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dz,
+                                                                 int ld_dz, int B, int H, int W, int C, int O,
+                                                                 float* __restrict__ dw) {
+  __shared__ float s_acc[32 * 4 * 9];  // [o][c][tap] partial of this block (O <= 32, C <= 4)
+  for (int i = threadIdx.x; i < 32 * 4 * 9; i += WF_THREADS) s_acc[i] = 0.f;
+  __syncthreads();
+  const int og = threadIdx.x & 7, c = (threadIdx.x >> 3) & 3, slice = threadIdx.x >> 5;
+  float acc[4][9];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[a][t] = 0.f;
+  const bool active = c < C && og * 4 < O;
+  const long long lines = (long long)B * H;
+  for (long long ln = blockIdx.x; ln < lines; ln += gridDim.x) {
+    const int b = (int)(ln / H), y = (int)(ln - (long long)b * H);
+    if (!active) continue;
+    const __nv_bfloat16* dzl = dz + (((long long)b * (H + 1) + y) * (W + 1)) * ld_dz + og * 4;
+    const float* xc = x + ((long long)b * C + c) * H * W;
+    for (int px = slice; px < W; px += WF_THREADS / 32) {
+      const uint2 q = *reinterpret_cast<const uint2*>(dzl + (long long)px * ld_dz);
+      const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&q.x);
+      const __nv_bfloat162 h1 = *reinterpret_cast<const __nv_bfloat162*>(&q.y);
+      const float g[4] = {__low2float(h0), __high2float(h0), __low2float(h1), __high2float(h1)};
+      float xv[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int yy = y + t / 3 - 1, xx = px + t % 3 - 1;
+        xv[t] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(xc + (long long)yy * W + xx) : 0.f;
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[a][t] = fmaf(g[a], xv[t], acc[a][t]);
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) atomicAdd(&s_acc[((og * 4 + a) * 4 + c) * 9 + t], acc[a][t]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * 4 * 9; i += WF_THREADS) {
+    const int t = i % 9, cc = (i / 9) % 4, o = i / 36;
+    if (o < O && cc < C && s_acc[i] != 0.f) atomicAdd(&dw[((long long)o * C + cc) * 9 + t], s_acc[i]);
+  }
+}
+
+__global__ void mul_inplace_kernel(float* __restrict__ a, const float* __restrict__ m, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    a[i] *= m[i];
+}
+}  // namespace
+
+extern "C" int mc_pack_conv_weights_dgrad(const float* d_w, const float* d_mask, int O, int C, int ksize, void* d_wpack,
+                                          int Cpad, int Ko, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MC_CHECK_ARG(d_w && d_wpack && O > 0 && C > 0 && (ksize == 1 || ksize == 3), "mc_pack_conv_weights_dgrad: bad argument");
+  MC_CHECK_ARG(Cpad >= C && (Cpad % 16) == 0 && Ko >= O && (Ko % 64) == 0, "mc_pack_conv_weights_dgrad: bad packed dims");
+  const int taps = ksize * ksize;
+  const long long total = (long long)Cpad * taps * Ko;
+  pack_dgrad_weights_kernel<<<grid_for(total, 256), 256, 0, stream>>>(d_w, d_mask, O, C, taps, (__nv_bfloat16*)d_wpack,
+                                                                      Cpad, Ko);
+  MC_LAUNCH_CHECK("pack_dgrad_weights_kernel");
+  return 0;
+}
+
+extern "C" int mc_conv_wgrad_first(const float* d_x, const void* d_dz, int ld_dz, int B, int H, int W, int C, int O,
+                                   const float* d_mask, float* d_dw, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MC_CHECK_ARG(d_x && d_dz && d_dw && B > 0 && H > 0 && W > 0, "mc_conv_wgrad_first: bad argument");
+  MC_CHECK_ARG(C >= 1 && C <= 4 && O >= 1 && O <= 32 && (O % 4) == 0 && (ld_dz % 4) == 0 && ld_dz >= O,
+               "mc_conv_wgrad_first: needs C <= 4, O <= 32 (multiple of 4), 3x3 (got C=%d O=%d)", C, O);
+  MC_CUDA(cudaMemsetAsync(d_dw, 0, sizeof(float) * (size_t)O * C * 9, stream));
+  long long lines = (long long)B * H;
+  int grid = mc_num_sms() * 4;
+  if (grid > lines) grid = (int)lines;
+  wgrad_first_kernel<<<grid, WF_THREADS, 0, stream>>>(d_x, (const __nv_bfloat16*)d_dz, ld_dz, B, H, W, C, O, d_dw);
+  MC_LAUNCH_CHECK("wgrad_first_kernel");
+  if (d_mask) {
+    mul_inplace_kernel<<<4, 256, 0, stream>>>(d_dw, d_mask, (long long)O * C * 9);
+    MC_LAUNCH_CHECK("mul_inplace_kernel");
+  }
+  return 0;
+}

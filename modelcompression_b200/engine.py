@@ -559,9 +559,9 @@ def compile_darknet(model, force=False):
 
 def darknet_forward(model, x):
     if model.training:
-        raise NotImplementedError(
-            "Darknet.forward in training mode (batch-statistics BatchNorm + backward, src/train.py:221-235) is not "
-            "built yet; call model.eval() for the inference/eval path (SURVEY.md §8a-12 is tracked in DESIGN.md).")
+        # batch-statistics BatchNorm + autograd-visible output: the retrain step (src/train.py:221-235)
+        from .engine_train import darknet_train_forward
+        return darknet_train_forward(model, x)
     return compile_darknet(model).run(x)
 
 

