@@ -233,6 +233,197 @@ __global__ void __launch_bounds__(TB) maxpool_bwd_kernel(const __nv_bfloat16* __
   }
 }
 
+// ---- vectorised versions (8 channels = one 16-byte access per thread) -----------------------------------------
+// Work item i = row * O8 + octet (O8 = C/8 octets per row).  The launch uses a thread count that is a multiple of O8,
+// so a thread meets the same octet on every grid-stride step: its per-channel constants / accumulators live in
+// registers, and consecutive threads touch consecutive 16-byte pieces of a row.
+__device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 v = __bfloat1622float2(h[j]);
+    f[2 * j] = v.x;
+    f[2 * j + 1] = v.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 q;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+  return q;
+}
+// row -> (b, y, x) with 32-bit arithmetic; returns interior flag
+__device__ __forceinline__ bool row_coords(unsigned int row, unsigned int Wp, unsigned int Hp, int H, int W, int* b,
+                                           int* y, int* x) {
+  const unsigned int t = row / Wp;
+  const unsigned int xx = row - t * Wp;
+  const unsigned int bb = t / Hp;
+  const unsigned int yy = t - bb * Hp;
+  *b = (int)bb;
+  *y = (int)yy;
+  *x = (int)xx;
+  return (int)xx < W && (int)yy < H;
+}
+__device__ __forceinline__ const uint4* da_vec(const __nv_bfloat16* da, unsigned int row, int b, int y, int x, int H,
+                                               int W, int C, int ld_da, int ch_off, int reorg, int c0) {
+  if (!reorg) return reinterpret_cast<const uint4*>(da + (long long)row * ld_da + ch_off + c0);
+  const int Wo = W / 2 + 1, Ho = H / 2 + 1;
+  const long long orow = ((long long)b * Ho + (y >> 1)) * Wo + (x >> 1);
+  return reinterpret_cast<const uint4*>(da + orow * ld_da + ch_off + ((y & 1) * 2 + (x & 1)) * C + c0);
+}
+
+__global__ void __launch_bounds__(TB) bn_bwd_reduce_vec_kernel(const __nv_bfloat16* __restrict__ z, int ld_z,
+                                                               const __nv_bfloat16* __restrict__ da, int ld_da, int ch_off,
+                                                               int reorg, int B, int H, int W, int C, int O8,
+                                                               const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               int leaky, float* __restrict__ dbeta, float* __restrict__ dgamma) {
+  __shared__ float s_a[TB][9], s_b[TB][9];  // padded rows: conflict-free column sums
+  const unsigned int rows = (unsigned int)B * (H + 1) * (W + 1);
+  const unsigned int total = rows * (unsigned int)O8;  // host guarantees < 2^32
+  const unsigned int nthreads = gridDim.x * TB;        // multiple of O8
+  unsigned int i = blockIdx.x * TB + threadIdx.x;
+  const int oc = (int)(i % (unsigned int)O8), c0 = oc * 8;
+  float m[8], is[8], g0[8], b0[8], sa[8], sb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    m[j] = mean[c0 + j]; is[j] = invstd[c0 + j]; g0[j] = gamma[c0 + j]; b0[j] = beta[c0 + j];
+    sa[j] = sb[j] = 0.f;
+  }
+  for (; i < total; i += nthreads) {
+    const unsigned int row = i / (unsigned int)O8;
+    int b, y, x;
+    if (!row_coords(row, W + 1, H + 1, H, W, &b, &y, &x)) continue;
+    const uint4 qz = *reinterpret_cast<const uint4*>(z + (long long)row * ld_z + c0);
+    const uint4 qa = *da_vec(da, row, b, y, x, H, W, C, ld_da, ch_off, reorg, c0);
+    float fz[8], fa[8];
+    unpack8(qz, fz);
+    unpack8(qa, fa);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (fz[j] - m[j]) * is[j];
+      float g = fa[j];
+      if (leaky && (g0[j] * xh + b0[j]) <= 0.f) g *= 0.1f;
+      sa[j] += g;
+      sb[j] += g * xh;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s_a[threadIdx.x][j] = sa[j]; s_b[threadIdx.x][j] = sb[j]; }
+  __syncthreads();
+  // threads with the same octet are O8 apart inside the block (TB % O8 == 0)
+  for (int w = threadIdx.x; w < O8 * 8; w += TB) {
+    const int o2 = w >> 3, j = w & 7;
+    float ta = 0.f, tb = 0.f;
+    const int first = (int)(((unsigned int)O8 + o2 - (blockIdx.x * TB) % (unsigned int)O8) % (unsigned int)O8);
+    for (int t = first; t < TB; t += O8) { ta += s_a[t][j]; tb += s_b[t][j]; }
+    atomicAdd(&dbeta[o2 * 8 + j], ta);
+    atomicAdd(&dgamma[o2 * 8 + j], tb);
+  }
+}
+
+__global__ void __launch_bounds__(TB) bn_bwd_apply_vec_kernel(const __nv_bfloat16* __restrict__ z, int ld_z,
+                                                              const __nv_bfloat16* __restrict__ da, int ld_da, int ch_off,
+                                                              int reorg, int B, int H, int W, int C, int O8,
+                                                              const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              int leaky, const float* __restrict__ dbeta,
+                                                              const float* __restrict__ dgamma, float inv_count,
+                                                              __nv_bfloat16* __restrict__ dz, int ld_dz) {
+  const unsigned int rows = (unsigned int)B * (H + 1) * (W + 1);
+  const unsigned int total = rows * (unsigned int)O8;
+  const unsigned int nthreads = gridDim.x * TB;
+  unsigned int i = blockIdx.x * TB + threadIdx.x;
+  const int oc = (int)(i % (unsigned int)O8), c0 = oc * 8;
+  float m[8], is[8], g0[8], b0[8], k1[8], kb[8], kg[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    m[j] = mean[c0 + j]; is[j] = invstd[c0 + j]; g0[j] = gamma[c0 + j]; b0[j] = beta[c0 + j];
+    k1[j] = g0[j] * is[j];
+    kb[j] = dbeta[c0 + j] * inv_count;
+    kg[j] = dgamma[c0 + j] * inv_count;
+  }
+  for (; i < total; i += nthreads) {
+    const unsigned int row = i / (unsigned int)O8;
+    int b, y, x;
+    float out[8];
+    if (row_coords(row, W + 1, H + 1, H, W, &b, &y, &x)) {
+      const uint4 qz = *reinterpret_cast<const uint4*>(z + (long long)row * ld_z + c0);
+      const uint4 qa = *da_vec(da, row, b, y, x, H, W, C, ld_da, ch_off, reorg, c0);
+      float fz[8], fa[8];
+      unpack8(qz, fz);
+      unpack8(qa, fa);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (fz[j] - m[j]) * is[j];
+        float g = fa[j];
+        if (leaky && (g0[j] * xh + b0[j]) <= 0.f) g *= 0.1f;
+        out[j] = k1[j] * (g - kb[j] - xh * kg[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) out[j] = 0.f;
+    }
+    *reinterpret_cast<uint4*>(dz + (long long)row * ld_dz + c0) = pack8(out);
+  }
+}
+
+// one thread = one pooled pixel x 8 channels: the 2x2 window is read once, the four gradients written once.  Pad
+// rows/columns of d_full are not touched (they are zero and stay zero).
+__global__ void __launch_bounds__(TB) maxpool_bwd_vec_kernel(const __nv_bfloat16* __restrict__ a_full, int ld_a,
+                                                             const __nv_bfloat16* __restrict__ d_pooled, int ld_dp, int B,
+                                                             int H, int W, int O8, __nv_bfloat16* __restrict__ d_full,
+                                                             int ld_df, int accumulate) {
+  const int Ho = H / 2, Wo = W / 2;
+  const unsigned int total = (unsigned int)B * Ho * Wo * O8;
+  for (unsigned int i = blockIdx.x * TB + threadIdx.x; i < total; i += gridDim.x * TB) {
+    const unsigned int pix = i / (unsigned int)O8;
+    const int c0 = (int)(i - pix * (unsigned int)O8) * 8;
+    const unsigned int t = pix / (unsigned int)Wo;
+    const int wx = (int)(pix - t * (unsigned int)Wo);
+    const int b = (int)(t / (unsigned int)Ho), wy = (int)(t - (t / (unsigned int)Ho) * (unsigned int)Ho);
+    const long long r00 = ((long long)b * (H + 1) + 2 * wy) * (W + 1) + 2 * wx;
+    const long long roff[4] = {r00, r00 + 1, r00 + W + 1, r00 + W + 2};
+    float v[4][8], g[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) unpack8(*reinterpret_cast<const uint4*>(a_full + roff[q] * ld_a + c0), v[q]);
+    const long long prow = ((long long)b * (Ho + 1) + wy) * (Wo + 1) + wx;
+    unpack8(*reinterpret_cast<const uint4*>(d_pooled + prow * ld_dp + c0), g);
+    float o[4][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int arg = 0;
+      float best = v[0][j];
+      if (v[1][j] > best) { best = v[1][j]; arg = 1; }
+      if (v[2][j] > best) { best = v[2][j]; arg = 2; }
+      if (v[3][j] > best) { best = v[3][j]; arg = 3; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q][j] = (q == arg) ? g[j] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4* dst = reinterpret_cast<uint4*>(d_full + roff[q] * ld_df + c0);
+      if (accumulate) {
+        float old[8];
+        unpack8(*dst, old);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[q][j] += old[j];
+      }
+      *dst = pack8(o[q]);
+    }
+  }
+}
+
+// thread count that is a multiple of O8 (O8 must divide TB * k): returns blocks, or 0 if the vector path does not apply
+inline int vec_blocks(long long total, int O8) {
+  if (O8 <= 0 || (TB % O8) != 0 || total >= (1ll << 32)) return 0;
+  long long blocks = (total + TB - 1) / TB;
+  const long long cap = (long long)mc_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
 inline int grid_for(long long total, int threads) {
   long long blocks = (total + threads - 1) / threads;
   const long long cap = (long long)mc_num_sms() * 16;
@@ -299,6 +490,22 @@ extern "C" int mc_bn_backward(const void* d_z, int ld_z, const void* d_da, int l
   MC_CUDA(cudaMemsetAsync(d_dbeta, 0, sizeof(float) * C, stream));
   MC_CUDA(cudaMemsetAsync(d_dgamma, 0, sizeof(float) * C, stream));
   const long long rows = (long long)B * (H + 1) * (W + 1);
+  const float inv_count = 1.0f / (float)((double)B * H * W);
+  // vector path: whole octets of channels, 16-byte aligned pieces everywhere
+  const bool vec_ok = (C % 8) == 0 && (ld_z % 8) == 0 && (ld_da % 8) == 0 && (ld_dz % 8) == 0 && (ch_off % 8) == 0 &&
+                      (((uintptr_t)d_z | (uintptr_t)d_da | (uintptr_t)d_dz) & 15) == 0;
+  const int vb = vec_ok ? vec_blocks(rows * (C / 8), C / 8) : 0;
+  if (vb > 0) {
+    bn_bwd_reduce_vec_kernel<<<vb, TB, 0, stream>>>((const __nv_bfloat16*)d_z, ld_z, (const __nv_bfloat16*)d_da, ld_da,
+                                                    ch_off, reorg, B, H, W, C, C / 8, d_mean, d_invstd, d_gamma, d_beta,
+                                                    leaky, d_dbeta, d_dgamma);
+    MC_LAUNCH_CHECK("bn_bwd_reduce_vec_kernel");
+    bn_bwd_apply_vec_kernel<<<vb, TB, 0, stream>>>((const __nv_bfloat16*)d_z, ld_z, (const __nv_bfloat16*)d_da, ld_da,
+                                                   ch_off, reorg, B, H, W, C, C / 8, d_mean, d_invstd, d_gamma, d_beta,
+                                                   leaky, d_dbeta, d_dgamma, inv_count, (__nv_bfloat16*)d_dz, ld_dz);
+    MC_LAUNCH_CHECK("bn_bwd_apply_vec_kernel");
+    return 0;
+  }
   long long gx = (rows + 8 * 32 - 1) / (8 * 32);
   const long long cap = (long long)mc_num_sms() * 8;
   if (gx > cap) gx = cap;
@@ -307,7 +514,6 @@ extern "C" int mc_bn_backward(const void* d_z, int ld_z, const void* d_da, int l
                                                 reorg, B, H, W, C, d_mean, d_invstd, d_gamma, d_beta, leaky, d_dbeta,
                                                 d_dgamma);
   MC_LAUNCH_CHECK("bn_bwd_reduce_kernel");
-  const float inv_count = 1.0f / (float)((double)B * H * W);
   bn_bwd_apply_kernel<<<grid_for(rows * C, TB), TB, 0, stream>>>((const __nv_bfloat16*)d_z, ld_z, (const __nv_bfloat16*)d_da,
                                                                  ld_da, ch_off, reorg, B, H, W, C, d_mean, d_invstd,
                                                                  d_gamma, d_beta, leaky, d_dbeta, d_dgamma, inv_count,
@@ -321,6 +527,16 @@ extern "C" int mc_maxpool2x2_backward(const void* d_a_full, int ld_a, const void
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MC_CHECK_ARG(d_a_full && d_dpooled && d_dfull && B > 0 && H > 0 && W > 0 && C > 0, "mc_maxpool2x2_backward: bad argument");
   MC_CHECK_ARG((H % 2) == 0 && (W % 2) == 0, "mc_maxpool2x2_backward: H, W must be even");
+  if ((C % 8) == 0 && (ld_a % 8) == 0 && (ld_dp % 8) == 0 && (ld_df % 8) == 0 &&
+      (((uintptr_t)d_a_full | (uintptr_t)d_dpooled | (uintptr_t)d_dfull) & 15) == 0 &&
+      (long long)B * (H / 2) * (W / 2) * (C / 8) < (1ll << 32)) {
+    const long long tv = (long long)B * (H / 2) * (W / 2) * (C / 8);
+    maxpool_bwd_vec_kernel<<<grid_for(tv, TB), TB, 0, stream>>>((const __nv_bfloat16*)d_a_full, ld_a,
+                                                               (const __nv_bfloat16*)d_dpooled, ld_dp, B, H, W, C / 8,
+                                                               (__nv_bfloat16*)d_dfull, ld_df, accumulate);
+    MC_LAUNCH_CHECK("maxpool_bwd_vec_kernel");
+    return 0;
+  }
   const long long total = (long long)B * (H + 1) * (W + 1) * C;
   maxpool_bwd_kernel<<<grid_for(total, TB), TB, 0, stream>>>((const __nv_bfloat16*)d_a_full, ld_a,
                                                              (const __nv_bfloat16*)d_dpooled, ld_dp, B, H, W, C,
