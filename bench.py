@@ -172,6 +172,46 @@ def time_masks(model_dense, peaks):
     return out
 
 
+def time_retrain(device, peaks, B, steps=5):
+    """BASELINE.json configs[2]: 90 % weight pruning, masked forward + backward + SGD step at batch B on one B200
+    (src/train.py:214-235 with the synthetic loss of SURVEY.md §8d: loss = (y*g).sum())."""
+    import torch
+    import modelcompression_b200 as mc
+    torch.manual_seed(0)
+    model = mc.Darknet(mc.write_yolov2_voc_cfg()).to(device)
+    model.set_masks(mc.weight_prune(model, 90.))
+    model.train()
+    opt = torch.optim.SGD(model.parameters(), lr=1e-5, momentum=0.9, weight_decay=5e-4 * B)
+    gen = torch.Generator(device=device).manual_seed(1)
+    xs = [torch.rand(B, 3, IMG, IMG, device=device, generator=gen) for _ in range(2)]
+    g = torch.randn(B, 125, 13, 13, device=device, generator=gen)
+    tf, tb, ts = [], [], []
+    for it in range(steps + 2):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        opt.zero_grad(set_to_none=True)
+        ev[0].record()
+        loss = (model(xs[it % 2]) * g).sum()
+        ev[1].record()
+        loss.backward()
+        ev[2].record()
+        opt.step()
+        ev[3].record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            tf.append(ev[0].elapsed_time(ev[1]))
+            tb.append(ev[1].elapsed_time(ev[2]))
+            ts.append(ev[2].elapsed_time(ev[3]))
+    f, b, s = statistics.median(tf), statistics.median(tb), statistics.median(ts)
+    gflop_img = 3 * 29.360 - 0.299  # fwd + dgrad + wgrad, no dgrad for conv1 (SURVEY.md §8d)
+    ok = bool(mc.are_masks_consistent(model, [c.mask for c in model.masked_convs()]))
+    tfl = gflop_img * B / (f + b + s)
+    return {"workload": "yolov2-voc-416 90%% weight-pruned, masked forward+backward+SGD step, batch %d" % B,
+            "forward_ms": f, "backward_ms": b, "sgd_ms": s, "ms_per_step": f + b + s,
+            "images_per_s": B / (f + b + s) * 1e3, "algorithmic_gflop_per_image": gflop_img, "tflops": tfl,
+            "frac_of_bf16_sustained": tfl / peaks['bf16_sustained'], "masks_consistent_after_steps": ok,
+            "optimizer": "torch.optim.SGD(lr 1e-5, momentum 0.9, wd 5e-4*B) as src/train.py:144-147"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -180,7 +220,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--dense', action='store_true', help='extra: also time the un-pruned dense network')
+    ap.add_argument('--no-dense', action='store_true', help='skip the extra un-pruned dense-network timing')
+    ap.add_argument('--no-retrain', action='store_true', help='skip the extra retrain-step timing (configs[2])')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else max(args.warmup, 1)
 
@@ -272,9 +313,11 @@ def main():
 
         # ---- end to end through the public API with HOST buffers (H2D of the batch + D2H of the head every step),
         #      double-buffered on a copy stream so the transfer of step i+1 overlaps the forward of step i
-        host_in = [torch.rand(B, 3, IMG, IMG).pin_memory() for _ in range(2)]
+        # host images are uint8 NCHW, what the reference's do_detect receives from PIL/cv2 before its CPU-side
+        # float().div(255) (src/nets2_utils.py:346-352); Darknet.forward scales them inside the first-layer kernel
+        host_in = [torch.randint(0, 256, (B, 3, IMG, IMG), dtype=torch.uint8).pin_memory() for _ in range(2)]
         host_out = [torch.empty(B, y.shape[1], y.shape[2], y.shape[3]).pin_memory() for _ in range(2)]
-        dev_in = [torch.empty(B, 3, IMG, IMG, device=device) for _ in range(2)]
+        dev_in = [torch.empty(B, 3, IMG, IMG, dtype=torch.uint8, device=device) for _ in range(2)]
         copy_stream = torch.cuda.Stream(device=device)
         main_stream = torch.cuda.current_stream()
         ready = [torch.cuda.Event() for _ in range(2)]
@@ -322,8 +365,9 @@ def main():
                    "algorithmic_gflop_per_image": flops_img / 1e9,
                    "l2": "inputs larger than L2: %d rotating %.0f MB batches" % (len(xs), B * 3 * IMG * IMG * 4 / 1e6)},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * IMG * IMG * 4,
-                "d2h_bytes_per_step": int(y.numel() * 4)},
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * IMG * IMG,
+                "d2h_bytes_per_step": int(y.numel() * 4),
+                "input": "uint8 NCHW images in pinned host memory (do_detect's input type), x/255 on the device"},
         "gpu_launches": plan.num_launches * args.steps,
         "roofline": {"bound": "tensor", "kernel": "conv_gemm_tcgen05_kernel", "achieved": achieved_tflops,
                      "peak": peaks['bf16_sustained'], "unit": "TFLOP/s",
@@ -340,7 +384,7 @@ def main():
             torch.manual_seed(0)
             dense = mc.Darknet(mc.write_yolov2_voc_cfg()).to(device).eval()
             line["mask"] = time_masks(dense, peaks)
-            if args.dense:
+            if not args.no_dense:
                 with torch.no_grad():
                     for i in range(6):
                         dense(xs[i % 3])
@@ -364,6 +408,9 @@ def main():
                                  "ms_per_step": ms,
                                  "per_op_ms": {k: round(statistics.median(v), 4) for k, v in dper.items()}}
             del dense
+            if not args.no_retrain:
+                torch.cuda.empty_cache()
+                line["retrain"] = time_retrain(device, peaks, B)
             if not args.no_cpu_baseline:
                 state = {k: v.detach().cpu() for k, v in model.state_dict().items()}
                 ips, sps = cpu_forward_sample(state, model.blocks, CPU_SAMPLE_BATCH, 6, 1)

@@ -105,7 +105,7 @@ __device__ __forceinline__ void epilogue_pool_small(uint32_t trow, const float* 
 // overlaps the MMA + epilogue of tile i:
 //   patch_full[2]  TMA -> builders          a_free[2]    tcgen05.commit -> builders (MMA has consumed A[s])
 //   tmem_full[2]   tcgen05.commit -> epilogue   tmem_free[2] epilogue warps (4 arrivals) -> MMA issuer
-template <int CL, bool POOL, bool FIRST>
+template <int CL, bool POOL, int FIRST>  // FIRST: 0 = PNHWC bf16 input, 1 = fp32 NCHW image, 2 = uint8 NCHW image (x/255)
 __global__ void __launch_bounds__(256, 2)
 conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_in,
                       const Im2colParams p) {
@@ -117,8 +117,16 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
   constexpr int A_BYTES = NKB * 128 * 128;
   // FIRST: fp32 patch [Cin][PR][PCF]; TMA needs a 16-byte aligned innermost start, so the box begins XS = 3 columns
   // left of the halo column (x0-4 instead of x0-1) and PCF = round_up(PC + 3, 4).  Else bf16 patch [PR][PC][CL].
-  constexpr int XS = 3;
-  constexpr int PCF = (PC + XS + 3) & ~3;
+  // uint8 image: same with 16-byte = 16-pixel granularity (XS = 15, PCF = round_up(PC + 15, 16)).
+  constexpr int XS = FIRST == 2 ? 15 : 3;
+  constexpr int PCF = FIRST == 2 ? ((PC + XS + 15) & ~15) : ((PC + XS + 3) & ~3);
+  constexpr int PEL = FIRST == 2 ? 1 : 4;  // bytes per patch element
+  // patch element -> float: the uint8 image is scaled like ToTensor / do_detect (img.float().div(255.0),
+  // src/nets2_utils.py:346-352) before the bf16 rounding every GEMM operand gets
+  auto pel = [](const uint8_t* patch, int idx) -> float {
+    if constexpr (FIRST == 2) return __fdiv_rn((float)patch[idx], 255.0f);
+    else return reinterpret_cast<const float*>(patch)[idx];
+  };
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -126,7 +134,7 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
   uint8_t* a_tile = smem;                                   // [2][NKB][128 rows][128 B], 128B swizzle
   uint8_t* b_tile = a_tile + 2 * A_BYTES;                   // [NKB][nb_pad rows][128 B]
   const int nb_pad = (p.nb + 15) & ~15;
-  const uint32_t patch_bytes = FIRST ? (uint32_t)(p.Cin * PR * PCF * 4) : (uint32_t)(PR * PC * CL * 2);
+  const uint32_t patch_bytes = FIRST ? (uint32_t)(p.Cin * PR * PCF * PEL) : (uint32_t)(PR * PC * CL * 2);
   const uint32_t patch_stride = (patch_bytes + 127u) & ~127u;
   uint8_t* patch0 = b_tile + (size_t)NKB * nb_pad * 128;  // 1024-aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(patch0 + 2 * patch_stride);
@@ -177,7 +185,7 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
       const unsigned int ty = rem / (unsigned)p.tiles_x, tx = rem - ty * (unsigned)p.tiles_x;
       const int iy0 = (int)(POOL ? 2 * ty * TY : ty * TY) - 1, ix0 = (int)(POOL ? 2 * tx * TX : tx * TX) - 1;
       ptx::mbar_arrive_expect_tx(&patch_full[buf], patch_bytes);
-      if constexpr (FIRST)
+      if constexpr (FIRST != 0)
         ptx::tma_load_4d(patch0 + buf * patch_stride, &tmap_in, &patch_full[buf], ix0 - XS, iy0, 0, (int)b);
       else
         ptx::tma_load_3d(patch0 + buf * patch_stride, &tmap_in, &patch_full[buf], 0, ix0, (int)b * (p.H + 1) + iy0);
@@ -204,14 +212,14 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
       if (FIRST && POOL && p.Cin == 3) {
         // RGB fast path: compile-time offsets from one base pointer.  Row r of the 4x4 window gives chunks 2r
         // (pixels px 0,1) and 2r+1 (pixels px 2,3), each pixel = (c0,c1,c2,0) in bf16.
-        const float* base = reinterpret_cast<const float*>(patch_raw) + by * PCF + bx + XS;
+        const int base = by * PCF + bx + XS;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           float v[3][4];
 #pragma unroll
           for (int c = 0; c < 3; ++c)
 #pragma unroll
-            for (int sx = 0; sx < 4; ++sx) v[c][sx] = base[(c * PR + r) * PCF + sx];
+            for (int sx = 0; sx < 4; ++sx) v[c][sx] = pel(patch_raw, base + (c * PR + r) * PCF + sx);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             __nv_bfloat162 a0 = __floats2bfloat162_rn(v[0][2 * h], v[1][2 * h]);
@@ -231,17 +239,16 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
         for (int q = 0; q < NKB * 8; ++q) {  // 16-byte chunk q holds K elements [8q, 8q+8)
           uint4 val = make_uint4(0, 0, 0, 0);
           if (q * 8 < KELEMS) {
-            if constexpr (FIRST) {
-              // two pixels per chunk, 4 bf16 each (c0,c1,c2,c3; absent channels 0); patch is fp32 [c][PR][PCF]
-              const float* pf = reinterpret_cast<const float*>(patch_raw);
+            if constexpr (FIRST != 0) {
+              // two pixels per chunk, 4 bf16 each (c0,c1,c2,c3; absent channels 0); patch is [c][PR][PCF]
               const int pa = 2 * q, pb = 2 * q + 1;
               float va[4] = {0.f, 0.f, 0.f, 0.f}, vb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
               for (int c = 0; c < 4; ++c)
                 if (c < p.Cin) {
-                  va[c] = pf[(c * PR + by + (POOL ? pa / 4 : pa / 3)) * PCF + bx + (POOL ? pa % 4 : pa % 3) + XS];
+                  va[c] = pel(patch_raw, (c * PR + by + (POOL ? pa / 4 : pa / 3)) * PCF + bx + (POOL ? pa % 4 : pa % 3) + XS);
                   if (pb < NPIX)
-                    vb[c] = pf[(c * PR + by + (POOL ? pb / 4 : pb / 3)) * PCF + bx + (POOL ? pb % 4 : pb % 3) + XS];
+                    vb[c] = pel(patch_raw, (c * PR + by + (POOL ? pb / 4 : pb / 3)) * PCF + bx + (POOL ? pb % 4 : pb % 3) + XS);
                 }
               __nv_bfloat162 a0 = __floats2bfloat162_rn(va[0], va[1]), a1 = __floats2bfloat162_rn(va[2], va[3]);
               __nv_bfloat162 b0 = __floats2bfloat162_rn(vb[0], vb[1]), b1 = __floats2bfloat162_rn(vb[2], vb[3]);
@@ -357,14 +364,15 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
   if (warp_idx == 0) ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
-template <int CL, bool POOL, bool FIRST>
+template <int CL, bool POOL, int FIRST>
 int launch_im2col(const CUtensorMap& tm_b, const Im2colParams& p, cudaStream_t stream) {
   constexpr int PR = POOL ? 2 * TY + 2 : TY + 2, PC = POOL ? 2 * TX + 2 : TX + 2;
-  constexpr int PCF = (PC + 3 + 3) & ~3;  // see XS in the kernel
+  constexpr int PCF = FIRST == 2 ? ((PC + 15 + 15) & ~15) : ((PC + 3 + 3) & ~3);  // see XS in the kernel
+  constexpr int PEL = FIRST == 2 ? 1 : 4;
   constexpr int NPIX = POOL ? 16 : 9;
   constexpr int NKB = (NPIX * CL + 63) / 64;
   const int nb_pad = (p.nb + 15) & ~15;
-  const size_t patch_bytes = FIRST ? (size_t)p.Cin * PR * PCF * 4 : (size_t)PR * PC * CL * 2;
+  const size_t patch_bytes = FIRST ? (size_t)p.Cin * PR * PCF * PEL : (size_t)PR * PC * CL * 2;
   const size_t patch_stride = (patch_bytes + 127) & ~(size_t)127;
   const size_t smem = 2 * (size_t)NKB * 128 * 128 + (size_t)NKB * nb_pad * 128 + 2 * patch_stride + 128 + 2048 + 1024;
   if (smem > 227 * 1024) return mc_set_error(MC_ERR_SHAPE, "mc_conv_im2col_fwd: %zu B of shared memory", smem);
@@ -372,14 +380,15 @@ int launch_im2col(const CUtensorMap& tm_b, const Im2colParams& p, cudaStream_t s
   // input patch tensor map
   CUtensorMap tm_in;
   int rc;
-  if (FIRST) {  // fp32 NCHW [B][Cin][H][W], box [1][Cin][PR][PCF]
+  if (FIRST) {  // fp32 / uint8 NCHW [B][Cin][H][W], box [1][Cin][PR][PCF]
     const uint64_t dims[4] = {(uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.Cin, (uint64_t)p.B};
-    const uint64_t strides[3] = {(uint64_t)p.W * 4, (uint64_t)p.W * p.H * 4, (uint64_t)p.W * p.H * p.Cin * 4};
+    const uint64_t strides[3] = {(uint64_t)p.W * PEL, (uint64_t)p.W * p.H * PEL, (uint64_t)p.W * p.H * p.Cin * PEL};
     const uint32_t box[4] = {(uint32_t)PCF, (uint32_t)PR, (uint32_t)p.Cin, 1};
-    if ((p.W * 4) % 16 != 0) return mc_set_error(MC_ERR_SHAPE, "mc_conv_im2col_fwd: image width must be a multiple of 4");
-    // short (160-byte) misaligned rows: 128 B promotion halves the L2->SM over-fetch of the default 256 B
-    rc = mc_make_tmap(&tm_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE,
-                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    if ((p.W * PEL) % 16 != 0)
+      return mc_set_error(MC_ERR_SHAPE, "mc_conv_im2col_fwd: image rows must be a multiple of 16 bytes (width %d)", p.W);
+    // short misaligned rows: 128 B promotion halves the L2->SM over-fetch of the default 256 B
+    rc = mc_make_tmap(&tm_in, FIRST == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.in, dims,
+                      strides, box, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
   } else {      // bf16 PNHWC viewed as [B*(H+1)][W+1][CL], box [PR][PC][CL]
     const uint64_t dims[3] = {(uint64_t)CL, (uint64_t)(p.W + 1), (uint64_t)p.B * (p.H + 1)};
     const uint64_t strides[2] = {(uint64_t)CL * 2, (uint64_t)(p.W + 1) * CL * 2};
@@ -411,9 +420,9 @@ int launch_im2col(const CUtensorMap& tm_b, const Im2colParams& p, cudaStream_t s
 // shared-memory bytes conv_im2col_tc_kernel needs for a geometry (mirrors the kernel's carve-up)
 static size_t im2col_smem_bytes(int CL, int pool, int first, int nb_pad, int Cin) {
   const int PR = pool ? 2 * TY + 2 : TY + 2, PC = pool ? 2 * TX + 2 : TX + 2;
-  const int PCF = (PC + 3 + 3) & ~3;
+  const int PCF = first == 2 ? ((PC + 15 + 15) & ~15) : ((PC + 3 + 3) & ~3);
   const int NKB = ((pool ? 16 : 9) * CL + 63) / 64;
-  const size_t patch_bytes = first ? (size_t)Cin * PR * PCF * 4 : (size_t)PR * PC * CL * 2;
+  const size_t patch_bytes = first ? (size_t)Cin * PR * PCF * (first == 2 ? 1 : 4) : (size_t)PR * PC * CL * 2;
   const size_t patch_stride = (patch_bytes + 127) & ~(size_t)127;
   return 2 * (size_t)NKB * 128 * 128 + (size_t)NKB * nb_pad * 128 + 2 * patch_stride + 128 + 2048 + 1024;
 }
@@ -499,7 +508,8 @@ extern "C" int mc_conv_im2col_fwd(const void* d_in, int in_is_nchw_f32, const vo
   rc = mc_make_tmap_2d_bf16(&tm_b, d_wexp, (uint64_t)nb_pad, (uint64_t)kpad, (uint64_t)kpad, (uint32_t)nb_pad);
   if (rc) return rc;
 
-  if (in_is_nchw_f32) return pool ? launch_im2col<4, true, true>(tm_b, p, stream) : launch_im2col<4, false, true>(tm_b, p, stream);
-  if (CL == 8) return pool ? launch_im2col<8, true, false>(tm_b, p, stream) : launch_im2col<8, false, false>(tm_b, p, stream);
-  return pool ? launch_im2col<16, true, false>(tm_b, p, stream) : launch_im2col<16, false, false>(tm_b, p, stream);
+  if (in_is_nchw_f32 == 2) return pool ? launch_im2col<4, true, 2>(tm_b, p, stream) : launch_im2col<4, false, 2>(tm_b, p, stream);
+  if (in_is_nchw_f32) return pool ? launch_im2col<4, true, 1>(tm_b, p, stream) : launch_im2col<4, false, 1>(tm_b, p, stream);
+  if (CL == 8) return pool ? launch_im2col<8, true, 0>(tm_b, p, stream) : launch_im2col<8, false, 0>(tm_b, p, stream);
+  return pool ? launch_im2col<16, true, 0>(tm_b, p, stream) : launch_im2col<16, false, 0>(tm_b, p, stream);
 }

@@ -406,7 +406,7 @@ class CompiledDarknet(object):
         device address and shape) is seen and replayed afterwards: ~25 launches per step otherwise cost more host time
         than the GPU needs for the small layers.  events: optional list; when given the eager path is used and
         (op, start_event, end_event) is appended per op (bench/profiling)."""
-        if events is not None or not self.use_graph or not x.is_cuda or x.dtype != torch.float32 or \
+        if events is not None or not self.use_graph or not x.is_cuda or x.dtype not in (torch.float32, torch.uint8) or \
                 not x.is_contiguous() or x.requires_grad:
             return self._run_eager(x, events)
         key = (tuple(x.shape), x.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream)
@@ -435,7 +435,12 @@ class CompiledDarknet(object):
         if x.device != self.device:
             raise RuntimeError("input on %s, model on %s" % (x.device, self.device))
         x = x.detach()
-        if x.dtype != torch.float32:
+        # uint8 images (what PIL / cv2 hand to do_detect, src/nets2_utils.py:346-352) are scaled by 1/255 inside the
+        # first-layer kernel: 4x less host->device traffic than shipping the float tensor the reference builds on the CPU
+        u8 = x.dtype == torch.uint8 and self.ops and self.ops[0]['kind'] == 'im2col' and self.ops[0]['src'] is None
+        if x.dtype == torch.uint8 and not u8:
+            x = x.float().div_(255.0)
+        elif x.dtype not in (torch.float32, torch.uint8):
             x = x.float()
         x = x.contiguous()
         B, _, H, W = x.shape
@@ -452,7 +457,7 @@ class CompiledDarknet(object):
                 if kind == 'im2col':
                     s = op['src']
                     if s is None:
-                        in_ptr, nchw, cin_ld = x.data_ptr(), 1, op['Cin']
+                        in_ptr, nchw, cin_ld = x.data_ptr(), (2 if u8 else 1), op['Cin']
                     else:
                         in_ptr, nchw, cin_ld = bufs[s.buf_id].data_ptr(), 0, self.bufs[s.buf_id].ld
                     _lib.check(lib.mc_conv_im2col_fwd(in_ptr, nchw, op['w'].data_ptr(), op['scale'].data_ptr(),

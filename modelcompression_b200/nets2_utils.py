@@ -162,12 +162,17 @@ def do_detect(model, img, conf_thresh, nms_thresh, use_cuda=1, verbose=0):
     """nets2_utils.py:334-386 — single image: to-tensor -> model -> get_region_boxes(...)[0] -> nms."""
     import numpy as np
     model.eval()
+    # The reference converts to float and divides by 255 on the CPU before .cuda() (nets2_utils.py:346-352).  Here the
+    # uint8 pixels are shipped as they are (4x less host->device traffic) and Darknet.forward applies the same
+    # x/255 inside its first-layer kernel.
     if isinstance(img, np.ndarray):
-        img = torch.from_numpy(img.transpose(2, 0, 1)).float().div(255.0).unsqueeze(0)
+        img = torch.from_numpy(np.ascontiguousarray(img.transpose(2, 0, 1))).unsqueeze(0)
+        if img.dtype != torch.uint8:
+            img = img.float().div(255.0)
     elif hasattr(img, 'tobytes') and hasattr(img, 'width'):  # PIL image
         width, height = img.width, img.height
         buf = torch.frombuffer(bytearray(img.tobytes()), dtype=torch.uint8)
-        img = buf.view(height, width, 3).permute(2, 0, 1).contiguous().view(1, 3, height, width).float().div(255.0)
+        img = buf.view(height, width, 3).permute(2, 0, 1).contiguous().view(1, 3, height, width)
     elif not torch.is_tensor(img):
         raise TypeError("unknown image type")
     img = img.cuda()

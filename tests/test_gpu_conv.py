@@ -179,6 +179,23 @@ def test_plan_invalidation_and_batch_sizes(cfg_path):
         y1b = model(x[1:2].contiguous())
     assert compile_darknet(model) is not plan_a
     assert torch.allclose(y1b, y1 + 1.0, atol=1e-5)
-    with pytest.raises(NotImplementedError):
-        model.train()
-        model(x)
+    model.train()  # training mode is the batch-statistics path of engine_train.py (tests/test_gpu_train.py)
+    yt = model(x)
+    assert yt.requires_grad and yt.shape == y3.shape
+    model.eval()
+
+
+def test_uint8_image_input_matches_float_path(cfg_path):
+    """uint8 NCHW images (do_detect's input, src/nets2_utils.py:346-352) are scaled by 1/255 inside the first-layer
+    kernel: same bf16 operands as feeding img.float().div(255.0), so the head is bit-identical."""
+    for shrink in (True, False):
+        model = make_darknet(cfg_path, seed=0, kn=True, randbn=True, device=DEV)
+        if shrink:
+            model.set_masks(mc.quick_filter_prune(model, 40.))
+        torch.manual_seed(4)
+        xu = torch.randint(0, 256, (3, 3, 416, 416), dtype=torch.uint8, device=DEV)
+        with torch.no_grad():
+            for _ in range(3):  # eager, then graph capture, then replay
+                yu = model(xu)
+            yf = model(xu.float().div(255.0))
+        assert yu.dtype == torch.float32 and torch.equal(yu, yf)
