@@ -319,9 +319,11 @@ def main():
         host_out = [torch.empty(B, y.shape[1], y.shape[2], y.shape[3]).pin_memory() for _ in range(2)]
         dev_in = [torch.empty(B, 3, IMG, IMG, dtype=torch.uint8, device=device) for _ in range(2)]
         copy_stream = torch.cuda.Stream(device=device)
+        out_stream = torch.cuda.Stream(device=device)
         main_stream = torch.cuda.current_stream()
         ready = [torch.cuda.Event() for _ in range(2)]
         consumed = [torch.cuda.Event() for _ in range(2)]
+        produced = [torch.cuda.Event() for _ in range(2)]
 
         def e2e_loop(nsteps):
             with torch.cuda.stream(copy_stream):
@@ -338,7 +340,11 @@ def main():
                 main_stream.wait_event(ready[cur])
                 out = model(dev_in[cur])
                 consumed[cur].record(main_stream)
-                host_out[cur].copy_(out, non_blocking=True)
+                produced[cur].record(main_stream)
+                with torch.cuda.stream(out_stream):  # device->host read of the head, off the compute stream
+                    out_stream.wait_event(produced[cur])
+                    host_out[cur].copy_(out, non_blocking=True)
+                    out.record_stream(out_stream)
             torch.cuda.synchronize()
 
         e2e_loop(4)

@@ -123,8 +123,11 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
   constexpr int PEL = FIRST == 2 ? 1 : 4;  // bytes per patch element
   // patch element -> float: the uint8 image is scaled like ToTensor / do_detect (img.float().div(255.0),
   // src/nets2_utils.py:346-352) before the bf16 rounding every GEMM operand gets
-  auto pel = [](const uint8_t* patch, int idx) -> float {
-    if constexpr (FIRST == 2) return __fdiv_rn((float)patch[idx], 255.0f);
+  // (a 256-entry table in shared memory: one load instead of an IEEE division per element, same values)
+  __shared__ float s_u8lut[FIRST == 2 ? 256 : 1];
+  if constexpr (FIRST == 2) s_u8lut[threadIdx.x & 255] = __fdiv_rn((float)(threadIdx.x & 255), 255.0f);
+  auto pel = [&](const uint8_t* patch, int idx) -> float {
+    if constexpr (FIRST == 2) return s_u8lut[patch[idx]];
     else return reinterpret_cast<const float*>(patch)[idx];
   };
 
