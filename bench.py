@@ -32,6 +32,17 @@ METRIC = "yolov2_416_pruned_fwd_images_per_sec"
 CPU_SAMPLE_BATCH = 4
 
 
+def profiled_traffic():
+    """dram__bytes_read+write per launch of the dominant kernel, from the committed ncu --set full capture of this
+    same workload (profiles/r1_ncu_full_conv_gemm.json, tools/run_ncu_full.sh); None when no capture is committed."""
+    path = os.path.join(ROOT, 'profiles', 'r1_ncu_full_conv_gemm.json')
+    try:
+        with open(path) as f:
+            return float(json.load(f)['dram_bytes_per_launch'])
+    except Exception:
+        return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -378,7 +389,8 @@ def main():
         "roofline": {"bound": "tensor", "kernel": "conv_gemm_tcgen05_kernel", "achieved": achieved_tflops,
                      "peak": peaks['bf16_sustained'], "unit": "TFLOP/s",
                      "frac": achieved_tflops / peaks['bf16_sustained'] if peaks['bf16_sustained'] else None,
-                     "traffic": None, "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peaks['source'],
+                     "traffic": profiled_traffic(), "traffic_unit": "bytes of DRAM traffic per launch (ncu --set full, "
+                     "profiles/r1_ncu_full_conv_gemm.json)", "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peaks['source'],
                      "avg_launch_ms": conv_ms_per_launch, "launches_per_step": conv_launches,
                      "algorithmic_gflop_per_step": conv_flops_step / 1e9,
                      "kernel_share_of_step": conv_ms / max(conv_ms + other_ms, 1e-9)},
