@@ -415,6 +415,88 @@ __global__ void __launch_bounds__(TB) maxpool_bwd_vec_kernel(const __nv_bfloat16
   }
 }
 
+__global__ void __launch_bounds__(TB) col_stats_vec_kernel(const __nv_bfloat16* __restrict__ z, unsigned int rows, int O8,
+                                                           int ld, int ch_off, float* __restrict__ sum,
+                                                           float* __restrict__ sumsq) {
+  __shared__ float s_a[TB][9], s_b[TB][9];
+  const unsigned int total = rows * (unsigned int)O8;
+  const unsigned int nthreads = gridDim.x * TB;  // multiple of O8
+  unsigned int i = blockIdx.x * TB + threadIdx.x;
+  const int c0 = (int)(i % (unsigned int)O8) * 8;
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
+  // 4 independent 16-byte loads in flight per thread
+  for (; i + 3 * nthreads < total; i += 4 * nthreads) {
+    uint4 q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      q[u] = *reinterpret_cast<const uint4*>(z + (long long)((i + u * nthreads) / (unsigned int)O8) * ld + ch_off + c0);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8(q[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a[j] += f[j]; b[j] = fmaf(f[j], f[j], b[j]); }
+    }
+  }
+  for (; i < total; i += nthreads) {
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(z + (long long)(i / (unsigned int)O8) * ld + ch_off + c0), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a[j] += f[j]; b[j] = fmaf(f[j], f[j], b[j]); }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s_a[threadIdx.x][j] = a[j]; s_b[threadIdx.x][j] = b[j]; }
+  __syncthreads();
+  for (int w = threadIdx.x; w < O8 * 8; w += TB) {
+    const int o2 = w >> 3, j = w & 7;
+    float ta = 0.f, tb = 0.f;
+    for (int t = o2; t < TB; t += O8) { ta += s_a[t][j]; tb += s_b[t][j]; }
+    atomicAdd(&sum[o2 * 8 + j], ta);
+    if (sumsq) atomicAdd(&sumsq[o2 * 8 + j], tb);
+  }
+}
+
+__global__ void __launch_bounds__(TB) bn_apply_vec_kernel(const __nv_bfloat16* __restrict__ z, int ld_z, int B, int H, int W,
+                                                          int C, int O8, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, int leaky,
+                                                          __nv_bfloat16* __restrict__ out, int ld_out, int ch_off, int reorg) {
+  const unsigned int rows = (unsigned int)B * (H + 1) * (W + 1);
+  const unsigned int total = rows * (unsigned int)O8;
+  const unsigned int nthreads = gridDim.x * TB;
+  unsigned int i = blockIdx.x * TB + threadIdx.x;
+  const int c0 = (int)(i % (unsigned int)O8) * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; }
+  for (; i < total; i += nthreads) {
+    const unsigned int row = i / (unsigned int)O8;
+    int b, y, x;
+    const bool in = row_coords(row, W + 1, H + 1, H, W, &b, &y, &x);
+    float o[8];
+    if (in) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(z + (long long)row * ld_z + c0), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float v = fmaf(f[j], sc[j], sh[j]);
+        o[j] = leaky ? fmaxf(v, 0.1f * v) : v;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = 0.f;
+    }
+    if (!reorg) {
+      *reinterpret_cast<uint4*>(out + (long long)row * ld_out + ch_off + c0) = pack8(o);
+    } else if (in) {
+      const int Wo = W / 2 + 1, Ho = H / 2 + 1;
+      const long long orow = ((long long)b * Ho + (y >> 1)) * Wo + (x >> 1);
+      *reinterpret_cast<uint4*>(out + orow * ld_out + ch_off + ((y & 1) * 2 + (x & 1)) * C + c0) = pack8(o);
+    }
+  }
+}
+
 // thread count that is a multiple of O8 (O8 must divide TB * k): returns blocks, or 0 if the vector path does not apply
 inline int vec_blocks(long long total, int O8) {
   if (O8 <= 0 || (TB % O8) != 0 || total >= (1ll << 32)) return 0;
@@ -442,6 +524,15 @@ extern "C" int mc_col_stats(const void* d_z, int64_t rows, int C, int ld, int ch
                "mc_col_stats: ld/ch_off must be multiples of 8 and cover round_up(C,8) channels");
   MC_CUDA(cudaMemsetAsync(d_sum, 0, sizeof(float) * C, stream));
   if (d_sumsq) MC_CUDA(cudaMemsetAsync(d_sumsq, 0, sizeof(float) * C, stream));
+  if ((C % 8) == 0 && ((uintptr_t)d_z & 15) == 0) {
+    const int vb = vec_blocks(rows * (C / 8), C / 8);
+    if (vb > 0) {
+      col_stats_vec_kernel<<<vb, TB, 0, stream>>>((const __nv_bfloat16*)d_z, (unsigned int)rows, C / 8, ld, ch_off, d_sum,
+                                                  d_sumsq);
+      MC_LAUNCH_CHECK("col_stats_vec_kernel");
+      return 0;
+    }
+  }
   long long gx = (rows + 8 * 64 - 1) / (8 * 64);
   const long long cap = (long long)mc_num_sms() * 4;
   if (gx > cap) gx = cap;
@@ -473,6 +564,15 @@ extern "C" int mc_bn_apply(const void* d_z, int ld_z, int B, int H, int W, int C
   MC_CHECK_ARG((ld_z % 8) == 0 && ld_z >= ((C + 7) / 8) * 8, "mc_bn_apply: ld_z must be a multiple of 8 covering C");
   if (reorg) MC_CHECK_ARG((H % 2) == 0 && (W % 2) == 0, "mc_bn_apply: reorg needs even H,W");
   const long long total = (long long)B * (H + 1) * (W + 1) * ((C + 7) / 8);
+  if ((C % 8) == 0 && (ld_out % 8) == 0 && (ch_off % 8) == 0 && (((uintptr_t)d_z | (uintptr_t)d_out) & 15) == 0) {
+    const int vb = vec_blocks(total, C / 8);
+    if (vb > 0) {
+      bn_apply_vec_kernel<<<vb, TB, 0, stream>>>((const __nv_bfloat16*)d_z, ld_z, B, H, W, C, C / 8, d_scale, d_shift, leaky,
+                                                 (__nv_bfloat16*)d_out, ld_out, ch_off, reorg);
+      MC_LAUNCH_CHECK("bn_apply_vec_kernel");
+      return 0;
+    }
+  }
   bn_apply_kernel<<<grid_for(total, TB), TB, 0, stream>>>((const __nv_bfloat16*)d_z, ld_z, B, H, W, C, d_scale, d_shift,
                                                           leaky, (__nv_bfloat16*)d_out, ld_out, ch_off, reorg);
   MC_LAUNCH_CHECK("bn_apply_kernel");
@@ -586,26 +686,45 @@ __global__ void __launch_bounds__(WF_THREADS) wgrad_first_kernel(const float* __
     for (int t = 0; t < 9; ++t) acc[a][t] = 0.f;
   const bool active = c < C && og * 4 < O;
   const long long lines = (long long)B * H;
+  // each of the 8 pixel slices of a block walks a CONTIGUOUS run of the line, so the 3x3 window slides through
+  // registers: per pixel 3 new image values + one 8-byte dZ load feed 36 FMAs
+  const int run = (W + WF_THREADS / 32 - 1) / (WF_THREADS / 32);
+  const int px0 = slice * run, px1 = (px0 + run < W) ? px0 + run : W;
   for (long long ln = blockIdx.x; ln < lines; ln += gridDim.x) {
     const int b = (int)(ln / H), y = (int)(ln - (long long)b * H);
-    if (!active) continue;
+    if (!active || px0 >= px1) continue;
     const __nv_bfloat16* dzl = dz + (((long long)b * (H + 1) + y) * (W + 1)) * ld_dz + og * 4;
     const float* xc = x + ((long long)b * C + c) * H * W;
-    for (int px = slice; px < W; px += WF_THREADS / 32) {
+    const float* xr[3];
+    bool rok[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int yy = y + r - 1;
+      rok[r] = yy >= 0 && yy < H;
+      xr[r] = xc + (long long)(rok[r] ? yy : 0) * W;
+    }
+    float xw[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      xw[r][1] = (rok[r] && px0 - 1 >= 0) ? __ldg(xr[r] + px0 - 1) : 0.f;
+      xw[r][2] = rok[r] ? __ldg(xr[r] + px0) : 0.f;
+    }
+#pragma unroll 2
+    for (int px = px0; px < px1; ++px) {
       const uint2 q = *reinterpret_cast<const uint2*>(dzl + (long long)px * ld_dz);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        xw[r][0] = xw[r][1];
+        xw[r][1] = xw[r][2];
+        xw[r][2] = (rok[r] && px + 1 < W) ? __ldg(xr[r] + px + 1) : 0.f;
+      }
       const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&q.x);
       const __nv_bfloat162 h1 = *reinterpret_cast<const __nv_bfloat162*>(&q.y);
       const float g[4] = {__low2float(h0), __high2float(h0), __low2float(h1), __high2float(h1)};
-      float xv[9];
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int yy = y + t / 3 - 1, xx = px + t % 3 - 1;
-        xv[t] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(xc + (long long)yy * W + xx) : 0.f;
-      }
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int t = 0; t < 9; ++t) acc[a][t] = fmaf(g[a], xv[t], acc[a][t]);
+        for (int t = 0; t < 9; ++t) acc[a][t] = fmaf(g[a], xw[t / 3][t % 3], acc[a][t]);
     }
   }
   if (active) {
