@@ -709,22 +709,33 @@ __global__ void __launch_bounds__(WF_THREADS) wgrad_first_kernel(const float* __
       xw[r][1] = (rok[r] && px0 - 1 >= 0) ? __ldg(xr[r] + px0 - 1) : 0.f;
       xw[r][2] = rok[r] ? __ldg(xr[r] + px0) : 0.f;
     }
-#pragma unroll 2
-    for (int px = px0; px < px1; ++px) {
-      const uint2 q = *reinterpret_cast<const uint2*>(dzl + (long long)px * ld_dz);
+    // groups of 4 pixels: the 4 dZ loads (DRAM latency) and the 12 image loads are issued before the 144 FMAs
+    for (int pg = px0; pg < px1; pg += 4) {
+      uint2 q[4];
+      float xn[4][3];
 #pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        xw[r][0] = xw[r][1];
-        xw[r][1] = xw[r][2];
-        xw[r][2] = (rok[r] && px + 1 < W) ? __ldg(xr[r] + px + 1) : 0.f;
+      for (int u = 0; u < 4; ++u) {
+        const int px = pg + u;
+        q[u] = (px < px1) ? *reinterpret_cast<const uint2*>(dzl + (long long)px * ld_dz) : make_uint2(0u, 0u);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) xn[u][r] = (rok[r] && px + 1 < W && px < px1) ? __ldg(xr[r] + px + 1) : 0.f;
       }
-      const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&q.x);
-      const __nv_bfloat162 h1 = *reinterpret_cast<const __nv_bfloat162*>(&q.y);
-      const float g[4] = {__low2float(h0), __high2float(h0), __low2float(h1), __high2float(h1)};
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int u = 0; u < 4; ++u) {
 #pragma unroll
-        for (int t = 0; t < 9; ++t) acc[a][t] = fmaf(g[a], xw[t / 3][t % 3], acc[a][t]);
+        for (int r = 0; r < 3; ++r) {
+          xw[r][0] = xw[r][1];
+          xw[r][1] = xw[r][2];
+          xw[r][2] = xn[u][r];
+        }
+        const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&q[u].x);
+        const __nv_bfloat162 h1 = *reinterpret_cast<const __nv_bfloat162*>(&q[u].y);
+        const float g[4] = {__low2float(h0), __high2float(h0), __low2float(h1), __high2float(h1)};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int t = 0; t < 9; ++t) acc[a][t] = fmaf(g[a], xw[t / 3][t % 3], acc[a][t]);
+      }
     }
   }
   if (active) {

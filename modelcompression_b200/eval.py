@@ -37,6 +37,36 @@ def compact_detections(boxes, keep, keep_counts, first_image_index):
     return out
 
 
+def compact_detections_validation(boxes, keep, keep_counts, cls, conf_thresh, first_image_index):
+    """Validation-mode rows (get_region_boxes(..., only_objectness=0, validation=True), src/nets2_utils.py:223-228, as
+    consumed by src/predict.py:167-172): every kept box yields one row for its arg-max class and one for every other
+    class c with box_conf*cls_conf[c] > conf_thresh.  Rows [img, x, y, w, h, box_conf, cls_conf, cls_id], image-major,
+    NMS order, arg-max class first.  cls [B,P,nc] = softmax probabilities from decode_device(want_cls=True)."""
+    B, P, _ = boxes.shape
+    nc = cls.shape[2]
+    ar = torch.arange(P, device=boxes.device).unsqueeze(0)
+    valid = ar < keep_counts.unsqueeze(1).long()
+    b_idx, slot = torch.nonzero(valid, as_tuple=True)
+    cand = keep[b_idx, slot].long()
+    rows = boxes[b_idx, cand]                       # [K, 8]
+    probs = cls[b_idx, cand]                        # [K, nc]
+    cmax = rows[:, 6].long()
+    thr = torch.tensor(float(conf_thresh), dtype=torch.float32, device=boxes.device)
+    extra = (rows[:, 4:5] * probs) > thr            # float32 product, strict, like the reference
+    extra[torch.arange(rows.shape[0], device=boxes.device), cmax] = False
+    # column 0 = the arg-max pair, columns 1..nc = the other classes in ascending order
+    sel = torch.cat([torch.ones(rows.shape[0], 1, dtype=torch.bool, device=boxes.device), extra], dim=1)
+    k_idx, col = torch.nonzero(sel, as_tuple=True)
+    out = torch.empty(k_idx.shape[0], DET_COLS, dtype=torch.float32, device=boxes.device)
+    out[:, 0] = (b_idx[k_idx] + first_image_index).float()
+    out[:, 1:6] = rows[k_idx, :5]
+    is_max = col == 0
+    cid = torch.where(is_max, cmax[k_idx], col - 1)
+    out[:, 6] = torch.where(is_max, rows[k_idx, 5], probs[k_idx, cid])
+    out[:, 7] = cid.float()
+    return out
+
+
 def gather_detections(local, group=None):
     """All ranks receive the detections of every rank concatenated in rank order.  ``local``: [n, DET_COLS] float32 on
     the backend's device (CUDA for nccl, CPU for gloo).  Two collectives: counts, then rows padded to the max count."""
@@ -57,11 +87,13 @@ def gather_detections(local, group=None):
 
 @torch.no_grad()
 def evaluate_sharded(model, get_batch, n_images, batch_size, conf_thresh=0.005, nms_thresh=0.45, only_objectness=0,
-                     rank=0, world_size=1, group=None, gather=True):
+                     rank=0, world_size=1, group=None, gather=True, validation=False):
     """Run detection over images [0, n_images) split across ranks.
 
     get_batch(lo, hi) -> float32 CUDA tensor [hi-lo, 3, H, W] for global image indices [lo, hi).
-    Returns [n_det, 8] detections (all ranks' when ``gather``), rows ordered by image index then NMS order."""
+    Returns [n_det, 8] detections (all ranks' when ``gather``), rows ordered by image index then NMS order.
+    validation=True (with only_objectness=0) emits the multi-class rows the reference's scorer consumes
+    (compact_detections_validation); feed them to voc_eval.mean_ap."""
     lo, hi = shard_range(n_images, rank, world_size)
     model.eval()
     chunks = []
@@ -69,10 +101,14 @@ def evaluate_sharded(model, get_batch, n_images, batch_size, conf_thresh=0.005, 
         b1 = min(b0 + batch_size, hi)
         x = get_batch(b0, b1)
         head = model(x)
-        boxes, counts, _ = decode_device(head, conf_thresh, model.num_classes, model.anchors, model.num_anchors,
-                                         only_objectness)
+        want_cls = bool(validation) and not only_objectness
+        boxes, counts, cls = decode_device(head, conf_thresh, model.num_classes, model.anchors, model.num_anchors,
+                                           only_objectness, want_cls)
         keep, keep_counts = nms_device(boxes, counts, nms_thresh)
-        chunks.append(compact_detections(boxes, keep, keep_counts, b0))
+        if want_cls:
+            chunks.append(compact_detections_validation(boxes, keep, keep_counts, cls, conf_thresh, b0))
+        else:
+            chunks.append(compact_detections(boxes, keep, keep_counts, b0))
     dev = next(model.parameters()).device
     local = torch.cat(chunks, dim=0) if chunks else torch.zeros(0, DET_COLS, dtype=torch.float32, device=dev)
     return gather_detections(local, group) if gather else local

@@ -54,3 +54,34 @@ def test_do_detect_single_image(cfg_path):
     assert len(boxes) == len(keep)
     got = np.array([[float(v) for v in b[:7]] for b in boxes], dtype=np.float32).reshape(-1, 7)
     np.testing.assert_allclose(got, dec[0]['box'][keep], rtol=2e-5, atol=1e-7)
+
+
+def test_map_scorer_on_device_equals_reference_path():
+    """N1 end to end on the GPU: head logits -> decode (validation mode) -> NMS -> multi-class rows -> mAP, all on the
+    device, against the reference's own route restated by the oracle: get_region_boxes(..., 0, 1) lists -> nms ->
+    per-class '%f' rows -> voc_eval (oracle/map_oracle.py, pinned to src/predict.py).  APs must be equal."""
+    import numpy as np
+    from modelcompression_b200 import voc_eval
+    from modelcompression_b200.eval import compact_detections_validation
+    from modelcompression_b200.nets2_utils import decode_device, nms_device, get_region_boxes, nms
+    from oracle import map_oracle
+    anchors = [1.3221, 1.73145, 3.19275, 4.00944, 5.05587, 8.09892, 9.47112, 4.84053, 11.2364, 10.0071]
+    n_img = 12
+    torch.manual_seed(2)
+    head = (torch.randn(n_img, 125, 13, 13) * 2).to(DEV)
+    gts = map_oracle.synthetic_ground_truth(n_img, seed=4)
+    conf_t, nms_t = 0.05, 0.45
+    # device path
+    boxes, counts, cls = decode_device(head, conf_t, 20, anchors, 5, 0, True)
+    keep, keep_counts = nms_device(boxes, counts, nms_t)
+    dets = compact_detections_validation(boxes, keep, keep_counts, cls, conf_t, 0)
+    gt_rows = torch.tensor([[i, c, x1, y1, x2, y2, d] for i, objs in enumerate(gts) for (c, x1, y1, x2, y2, d) in objs])
+    aps, m = voc_eval.mean_ap(dets, gt_rows.to(DEV), 20, None, 0.5, True)
+    # reference route (legacy list API of this package == reference semantics, then the pinned oracle scorer)
+    lists = get_region_boxes(head, conf_t, 20, anchors, 5, 0, True)
+    kept = [[[float(v) if i < 5 or (i - 5) % 2 == 0 else int(v) for i, v in enumerate(b)] for b in nms(bl, nms_t)] for bl in lists]
+    kept = [[[np.float32(v) if not isinstance(v, int) else v for v in b] for b in bl] for bl in kept]
+    rows = map_oracle.detection_rows(kept, [(416, 416)] * n_img)
+    aps_o, m_o = map_oracle.mean_ap(rows, gts, 20, 0.5, True)
+    assert sum(len(v) for v in rows.values()) == dets.shape[0] > 100
+    assert aps == aps_o and m == m_o

@@ -132,3 +132,28 @@ def test_forward_oracle_against_reference_vectors(cfg_path):
     for i in range(2):
         for j in range(2):
             assert torch.equal(r[:, (i * 2 + j) * 3:(i * 2 + j + 1) * 3], x[:, :, i::2, j::2])
+
+
+def test_voc_scorer_matches_reference_golden():
+    """N1: the tensor scorer (modelcompression_b200/voc_eval.py, device-agnostic torch code, here on CPU tensors) and
+    the NumPy oracle both reproduce the reference's voc_eval APs (tests/golden/voc_map.npz, pinned by
+    oracle/make_golden_map.py): 20 classes, VOC07 11-point and area metrics, ties and 'difficult' boxes included."""
+    import torch
+    from modelcompression_b200 import voc_eval
+    from oracle import map_oracle
+    g = load_golden('voc_map.npz')
+    dets, gts = torch.from_numpy(g['dets']), torch.from_numpy(g['gts'])
+    for m07, key in ((True, 'ap07'), (False, 'ap_area')):
+        aps, m = voc_eval.mean_ap(dets, gts, 20, None, 0.5, m07)
+        assert aps == g[key].tolist()
+        assert m == float(np.mean(g[key]))
+    # the oracle from the flat rows (one (cls_conf, cls_id) pair per row)
+    kept = [[] for _ in range(int(g['n_images']))]
+    for r in g['dets']:
+        kept[int(r[0])].append([np.float32(v) for v in r[1:7]] + [int(r[7])])
+    gt_list = [[] for _ in range(int(g['n_images']))]
+    for r in g['gts']:
+        gt_list[int(r[0])].append(tuple(int(v) for v in r[1:]))
+    rows = map_oracle.detection_rows(kept, [(416, 416)] * len(kept))
+    aps_o, m_o = map_oracle.mean_ap(rows, gt_list, 20, 0.5, True)
+    assert aps_o == g['ap07'].tolist()
