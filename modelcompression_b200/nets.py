@@ -77,8 +77,10 @@ class EmptyModule(nn.Module):
 
 
 class RegionLoss(nn.Module):
-    """Holder of the region-layer hyper-parameters (nets.py:442-460, filled by create_network :873-889).  The loss
-    itself (build_targets + 5 MSE/CE terms, nets.py:322-636) is 'next' row N3 of SURVEY.md §8f."""
+    """nets.py:442-636.  Hyper-parameters as in the reference (filled by create_network :873-889).  ``forward`` is the
+    device-resident, vectorised restatement in region_loss.py: no copy to the CPU, no Python loop
+    over images / boxes / anchors; loss and gradient equal the reference's to float32 round-off
+    (oracle/make_golden_region.py)."""
 
     def __init__(self, num_classes=20, anchor_list=None, anchors_cell=5):
         super(RegionLoss, self).__init__()
@@ -95,7 +97,9 @@ class RegionLoss(nn.Module):
         self.seen = 0
 
     def forward(self, output, target, verbose=0):
-        raise NotImplementedError("RegionLoss is outside the round-1 hot path (SURVEY.md §8f N3)")
+        from .region_loss import region_loss
+        return region_loss(output, target, self.anchors, self.num_anchors, self.num_classes, self.coord_scale,
+                           self.noobject_scale, self.object_scale, self.class_scale, self.thresh)
 
 
 class Darknet(nn.Module):

@@ -334,3 +334,35 @@ def test_training_forward_needs_cuda(cfg_path):
     model = mc.Darknet(cfg_path).train()
     with pytest.raises(RuntimeError):
         model(torch.rand(1, 3, 416, 416))
+
+
+def test_region_loss_on_device_and_full_retrain_step(cfg_path):
+    """N3 on the GPU: the golden reference loss/gradient, then the reference's real retrain step end to end
+    (src/train.py:221-235): model.train() -> model(x) -> model.loss(output, target) -> backward -> SGD step."""
+    from modelcompression_b200.region_loss import region_loss
+    g = load_golden('region_loss.npz')
+    anchors = [1.3221, 1.73145, 3.19275, 4.00944, 5.05587, 8.09892, 9.47112, 4.84053, 11.2364, 10.0071]
+    for name in ('ones', 'cfg', 'mixed'):
+        cs, ns, os_, cl = g['scales_' + name].tolist()
+        out = torch.from_numpy(g['output']).to(DEV).requires_grad_(True)
+        loss = region_loss(out, torch.from_numpy(g['target']).to(DEV), anchors, 5, 20, cs, ns, os_, cl, 0.6)
+        loss.backward()
+        assert abs(float(loss.detach()) - float(g['loss_' + name])) <= 1e-5 * abs(float(g['loss_' + name]))
+        gref = torch.from_numpy(g['grad_' + name]).to(DEV)
+        assert float((out.grad - gref).abs().max()) <= 1e-5 * float(gref.abs().max())
+    model = make_darknet(cfg_path, seed=0, kn=True, device=DEV)
+    model.set_masks(mc.weight_prune(model, 90.))
+    model.train()
+    opt = torch.optim.SGD(model.parameters(), lr=1e-5, momentum=0.9, weight_decay=5e-4 * 4)
+    torch.manual_seed(1)
+    x = torch.rand(4, 3, 416, 416, device=DEV)
+    target = torch.from_numpy(g['target']).to(DEV)
+    losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        loss = model.loss(model(x), target)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert all(np.isfinite(losses)) and all(p.grad is not None for p in model.parameters())
+    assert mc.are_masks_consistent(model, [c.mask for c in model.masked_convs()]) is True

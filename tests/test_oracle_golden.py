@@ -157,3 +157,20 @@ def test_voc_scorer_matches_reference_golden():
     rows = map_oracle.detection_rows(kept, [(416, 416)] * len(kept))
     aps_o, m_o = map_oracle.mean_ap(rows, gt_list, 20, 0.5, True)
     assert aps_o == g['ap07'].tolist()
+
+
+def test_region_loss_matches_reference_golden():
+    """N3: the vectorised region loss equals the reference's RegionLoss + build_targets (loss and gradient stored by
+    oracle/make_golden_region.py) — run here on CPU tensors; the GPU test runs the same check on cuda."""
+    import torch
+    from modelcompression_b200.region_loss import region_loss
+    g = load_golden('region_loss.npz')
+    anchors = [1.3221, 1.73145, 3.19275, 4.00944, 5.05587, 8.09892, 9.47112, 4.84053, 11.2364, 10.0071]
+    for name in ('ones', 'cfg', 'mixed'):
+        cs, ns, os_, cl = g['scales_' + name].tolist()
+        out = torch.from_numpy(g['output']).clone().requires_grad_(True)
+        loss = region_loss(out, torch.from_numpy(g['target']), anchors, 5, 20, cs, ns, os_, cl, 0.6)
+        loss.backward()
+        assert abs(float(loss.detach()) - float(g['loss_' + name])) <= 2e-6 * abs(float(g['loss_' + name]))
+        gref = torch.from_numpy(g['grad_' + name])
+        assert float((out.grad - gref).abs().max()) <= 2e-6 * float(gref.abs().max())
