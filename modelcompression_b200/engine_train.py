@@ -200,6 +200,8 @@ class TrainPlan(object):
             if not L.is_head and L.act is None:
                 raise NotImplementedError("unresolved concat producer at block %d" % L.ind)
         self._bufs = {}  # (B, device) -> dict name -> tensor
+        self.dp_group = None   # set by train_dp.enable(): gradients are all-reduced inside the backward
+        self.dp_world = 1
 
     # ------------------------------------------------------------------------------------------------ parameters
     def parameters(self):
@@ -349,6 +351,15 @@ def _backward(plan, sv, dy, before_bn=None):
     s = _lib.stream_ptr()
     grads = {}
     written = set()  # gradient buffers that already hold a contribution in this backward
+    pending = []     # data-parallel: (work handle, tensor) of the gradient all-reduces in flight
+
+    def reduce_async(t):
+        # the all-reduce of a layer's gradient is issued as soon as the layer's wgrad is queued, so NCCL
+        # (its own stream, NVLink/NVSwitch) overlaps the backward of the layers below
+        if plan.dp_world > 1:
+            import torch.distributed as dist
+            pending.append((dist.all_reduce(t, group=plan.dp_group, async_op=True), t))
+        return t
     head = plan.layers[-1]
     Hh, Wh = head.H, head.W
     ld_h = _round_up(head.O, 8)
@@ -362,7 +373,7 @@ def _backward(plan, sv, dy, before_bn=None):
         if L.is_head:
             dz_ptr, ld_dz = dzh.data_ptr(), ld_h
             # bias gradient = column sums of dY; computed in fp32 from dy itself (tiny)
-            grads[id(conv.bias)] = dy.sum(dim=(0, 2, 3))
+            grads[id(conv.bias)] = reduce_async(dy.sum(dim=(0, 2, 3)))
         else:
             st = sv.stats[L.ind]
             a = L.act
@@ -386,6 +397,7 @@ def _backward(plan, sv, dy, before_bn=None):
                                           int(L.reorg), B, L.H, L.W, O, st[4].data_ptr(), st[5].data_ptr(),
                                           bn.weight.data_ptr(), bn.bias.data_ptr(), L.leaky, dgb[0].data_ptr(),
                                           dgb[1].data_ptr(), dz.data_ptr(), L.z.ld, s), "mc_bn_backward")
+            reduce_async(dgb)
             grads[id(bn.bias)] = dgb[0]
             grads[id(bn.weight)] = dgb[1]
             dz_ptr, ld_dz = dz.data_ptr(), L.z.ld
@@ -400,7 +412,7 @@ def _backward(plan, sv, dy, before_bn=None):
             ws = _workspace(dev, nbytes)
             _lib.check(lib.mc_conv_wgrad(bufs[src.name].data_ptr() + 2 * src.ch_off, src.ld, C, dz_ptr, ld_dz, O, B, L.H,
                                          L.W, k, mask_ptr, dw.data_ptr(), 0, ws.data_ptr(), nbytes, s), "mc_conv_wgrad")
-        grads[id(conv.weight)] = dw
+        grads[id(conv.weight)] = reduce_async(dw)
         # ---- data gradient: the same tcgen05 conv kernel on the flipped / transposed filter
         if L.src is not None:
             src = L.src
@@ -417,6 +429,9 @@ def _backward(plan, sv, dy, before_bn=None):
                            O, ld_dz, C, Cpad, k, 0, _lib.MC_EPI_PNHWC, src.ld, src.ch_off)
             _lib.check(lib.mc_conv_fwd(ctypes.byref(d), s), "dgrad (block %d)" % L.ind)
             written.add(dname)
+    for work, t in pending:  # the current stream waits for NCCL; gradients become the mean over the replicas
+        work.wait()
+        t.div_(plan.dp_world)
     return [grads[id(p)] for p in plan.parameters()]
 
 

@@ -54,3 +54,34 @@ def test_gather_detections_world2(tmp_path, n_images):
 def test_gather_is_identity_without_process_group():
     x = _fake_detections(0, 5)
     assert gather_detections(x) is x
+
+
+def _dp_worker(rank, world, port):
+    """N4 host logic over gloo: bucketed gradient averaging, parameter broadcast, running-statistics averaging."""
+    from modelcompression_b200 import train_dp
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        torch.manual_seed(100 + rank)  # different initial parameters per rank
+        net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.BatchNorm2d(4), torch.nn.Conv2d(4, 2, 1))
+        train_dp.broadcast_parameters(net, src=0)
+        torch.manual_seed(100)
+        ref = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.BatchNorm2d(4), torch.nn.Conv2d(4, 2, 1))
+        for a, b in zip(net.parameters(), ref.parameters()):
+            assert torch.equal(a, b)
+        for i, p in enumerate(net.parameters()):
+            p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+        train_dp.allreduce_gradients(list(net.parameters()))
+        for i, p in enumerate(net.parameters()):
+            assert torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1)))  # mean of (1, 2) * (i+1)
+        net[1].running_mean.fill_(float(rank))
+        train_dp.average_buffers(net)
+        assert torch.allclose(net[1].running_mean, torch.full((4,), 0.5))
+        assert int(net[1].num_batches_tracked) == 0  # integer buffers untouched
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_helpers_world2():
+    mp.spawn(_dp_worker, args=(2, _free_port()), nprocs=2, join=True)
