@@ -106,7 +106,7 @@ __device__ __forceinline__ void epilogue_pool_small(uint32_t trow, const float* 
 //   patch_full[2]  TMA -> builders          a_free[2]    tcgen05.commit -> builders (MMA has consumed A[s])
 //   tmem_full[2]   tcgen05.commit -> epilogue   tmem_free[2] epilogue warps (4 arrivals) -> MMA issuer
 template <int CL, bool POOL, int FIRST>  // FIRST: 0 = PNHWC bf16 input, 1 = fp32 NCHW image, 2 = uint8 NCHW image (x/255)
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 4)
 conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_in,
                       const Im2colParams p) {
   constexpr int PR = POOL ? 2 * TY + 2 : TY + 2;   // patch rows / cols (conv pixels incl. halo)
