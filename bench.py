@@ -183,6 +183,36 @@ def time_masks(model_dense, peaks):
     return out
 
 
+def time_eval_pipeline(model, device, B, rank, world, n_images=4952):
+    """BASELINE.json configs[4]: batch-sharded evaluation of 4952 synthetic VOC2007-test-shaped images — forward,
+    region decode (conf 0.005, validation mode: multi-class rows), per-image NMS (0.45), compaction, one gather of the
+    detections at the end (src/predict.py:116-179 restated in eval.evaluate_sharded).  Images are generated on the
+    device per batch (uint8), so the number is the device pipeline; returns images/s over all ranks."""
+    import torch
+    import torch.distributed as dist
+    from modelcompression_b200.eval import evaluate_sharded
+
+    def get_batch(lo, hi):
+        g = torch.Generator(device=device).manual_seed(lo)
+        return torch.randint(0, 256, (hi - lo, 3, IMG, IMG), dtype=torch.uint8, device=device, generator=g)
+
+    evaluate_sharded(model, get_batch, 4 * B * world, B, 0.005, 0.45, 0, rank, world, validation=True)  # warm-up
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    dets = evaluate_sharded(model, get_batch, n_images, B, 0.005, 0.45, 0, rank, world, validation=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    return {"workload": "%d synthetic 416x416 images, batch %d per GPU: forward + decode (0.005, validation) + NMS (0.45) + "
+                        "detection gather" % (n_images, B), "images_per_s": n_images / dt, "seconds": dt,
+            "detection_rows": int(dets.shape[0]), "includes": "on-device image generation; no host->device copies"}
+
+
 def time_retrain(device, peaks, B, steps=5):
     """BASELINE.json configs[2]: 90 % weight pruning, masked forward + backward + SGD step at batch B on one B200
     (src/train.py:214-235 with the synthetic loss of SURVEY.md §8d: loss = (y*g).sum())."""
@@ -396,6 +426,8 @@ def main():
                      "kernel_share_of_step": conv_ms / max(conv_ms + other_ms, 1e-9)},
         "whole_net_tflops": flops_img * value / world / 1e12,
     }
+    with torch.no_grad():
+        line["eval_pipeline"] = time_eval_pipeline(model, device, B, rank, world)
     if rank == 0:
         line["per_op_ms"] = {k: round(statistics.median(v), 4) for k, v in per_layer.items()}
         if world == 1:
