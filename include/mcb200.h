@@ -156,7 +156,7 @@ enum { MC_EPI_PNHWC = 0,      /* bf16 PNHWC at the same resolution, channel offs
 
 typedef struct mc_conv_desc {
   const void* d_in;      /* bf16 PNHWC [B*(H+1)*(W+1), Cin_ld]                                           */
-  const void* d_wpack;   /* bf16 [Npad, ntaps*Kc] K-major, Kc = round_up(Cin,64); from mc_pack_conv_weights */
+  const void* d_wpack;   /* bf16 [Npad, ntaps*Kc] K-major, Kc = round_up(Cin, block_k); from mc_pack_conv_weights */
   const float* d_scale;  /* [Npad] per-output-channel multiplier (folded BN gamma/sqrt(var+eps), or 1)     */
   const float* d_shift;  /* [Npad] per-output-channel addend (folded BN beta - mean*scale, or conv bias)   */
   void* d_out;
@@ -169,6 +169,8 @@ typedef struct mc_conv_desc {
   int ldc, ch_off;       /* output row pitch (elements) and channel offset (bf16 modes)                   */
   int block_n;           /* 0 = auto; else 16..256 multiple of 16                                         */
   int stages;            /* 0 = auto                                                                      */
+  int block_k;           /* k-block: 0/64 = 64 bf16 (d_wpack Kc = round_up(Cin,64)); 32 = 32 bf16 with 64-byte   */
+                         /* swizzle (Kc = round_up(Cin,32)): less zero padding for Cin like 32, 69, 91             */
 } mc_conv_desc;
 
 int mc_conv_fwd(const mc_conv_desc* desc, void* stream);

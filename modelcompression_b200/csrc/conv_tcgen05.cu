@@ -19,9 +19,7 @@
 
 namespace {
 
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;
-constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+constexpr int BLOCK_M = 128;  // k-block: 64 bf16 (128-byte swizzle rows) or 32 bf16 (64-byte swizzle rows), per launch
 constexpr int MAX_STAGES = 8;
 constexpr int NUM_THREADS = 192;
 
@@ -30,7 +28,8 @@ struct ConvKParams {
   int N;           // valid output channels
   int Npad;        // length of scale/shift arrays
   int num_kb;      // ntaps * kb_per_tap
-  int kb_per_tap;  // Kc / 64
+  int kb_per_tap;  // Kc / block_k
+  int block_k;     // 64 or 32
   int ksize;       // 1 or 3
   int Wp, Hp, W, H;  // Wp = W+1, Hp = H+1
   int block_n, stages, tmem_cols, acc_stride;  // acc_stride: TMEM columns between the two accumulator stages
@@ -183,8 +182,9 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                          const ConvKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve-up: [stages x (A 16KB | B block_n*128)] | barriers | tmem ptr | scale/shift staging (4 KB)
-  const uint32_t b_tile_bytes = (uint32_t)p.block_n * 128u;
-  const uint32_t stage_bytes = A_TILE_BYTES + b_tile_bytes;
+  const uint32_t a_tile_bytes = (uint32_t)(BLOCK_M * p.block_k * 2);
+  const uint32_t b_tile_bytes = (uint32_t)(p.block_n * p.block_k * 2);
+  const uint32_t stage_bytes = a_tile_bytes + b_tile_bytes;
   uint8_t* smem = smem_raw;
   {  // dynamic smem base is only guaranteed 16B aligned: align up to 1024 (host adds 1 KB of slack)
     uint32_t a = ptx::smem_u32(smem);
@@ -240,10 +240,10 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           if (p.ksize == 3) row_off = (tap / 3 - 1) * p.Wp + (tap % 3 - 1);
           ptx::mbar_wait(&empty_bar[s], phase ^ 1u);
           uint8_t* a_dst = tiles + (size_t)s * stage_bytes;
-          uint8_t* b_dst = a_dst + A_TILE_BYTES;
+          uint8_t* b_dst = a_dst + a_tile_bytes;
           ptx::mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
-          ptx::tma_load_2d(a_dst, &tmap_a, &full_bar[s], cb * BLOCK_K, m0 + row_off);
-          ptx::tma_load_2d(b_dst, &tmap_b, &full_bar[s], kb * BLOCK_K, n0);
+          ptx::tma_load_2d(a_dst, &tmap_a, &full_bar[s], cb * p.block_k, m0 + row_off);
+          ptx::tma_load_2d(b_dst, &tmap_b, &full_bar[s], kb * p.block_k, n0);
           if (++s == p.stages) { s = 0; phase ^= 1u; }
         }
       }
@@ -263,11 +263,14 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           ptx::mbar_wait(&full_bar[s], phase);
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(tiles + (size_t)s * stage_bytes);
-          const uint64_t adesc = ptx::make_sw128_kmajor_desc(a_addr);
-          const uint64_t bdesc = ptx::make_sw128_kmajor_desc(a_addr + A_TILE_BYTES);
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr>>4) field
+          const bool k64 = p.block_k == 64;
+          const uint64_t adesc = k64 ? ptx::make_sw128_kmajor_desc(a_addr) : ptx::make_sw64_kmajor_desc(a_addr);
+          const uint64_t bdesc = k64 ? ptx::make_sw128_kmajor_desc(a_addr + a_tile_bytes)
+                                     : ptx::make_sw64_kmajor_desc(a_addr + a_tile_bytes);
+          const int ksteps = p.block_k / 16;
+#pragma unroll 4
+          for (int k = 0; k < ksteps; ++k) {
+            // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr>>4) field
             ptx::umma_bf16_ss(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
                               (kb > 0 || k > 0) ? 1u : 0u);
           }
@@ -343,17 +346,20 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   if (d->epi_mode == MC_EPI_REORG2) MC_CHECK_ARG((d->H % 2) == 0 && (d->W % 2) == 0, "mc_conv_fwd: reorg needs even H,W");
 
   const int ntaps = d->ksize * d->ksize;
+  const int BLOCK_K = d->block_k == 32 ? 32 : 64;
+  MC_CHECK_ARG(d->block_k == 0 || d->block_k == 32 || d->block_k == 64, "mc_conv_fwd: block_k must be 0, 32 or 64");
+  const int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
   const int Kc = ((d->Cin + BLOCK_K - 1) / BLOCK_K) * BLOCK_K;
   const long long M_rows = (long long)d->B * (d->H + 1) * (d->W + 1);
   MC_CHECK_ARG(M_rows < (1ll << 31), "mc_conv_fwd: too many rows");
   const int m_tiles = (int)((M_rows + BLOCK_M - 1) / BLOCK_M);
 
   int block_n = d->block_n;
-  if (block_n <= 0) block_n = pick_block_n(d->Npad, m_tiles, ntaps * (Kc / BLOCK_K), mc_num_sms());
+  if (block_n <= 0) block_n = pick_block_n(d->Npad, m_tiles, (ntaps * Kc + 63) / 64, mc_num_sms());  // 64-wide k-block units
   MC_CHECK_ARG(block_n >= 16 && block_n <= 256 && (block_n % 16) == 0, "mc_conv_fwd: block_n %d invalid", block_n);
   const int n_tiles = (d->Npad + block_n - 1) / block_n;
 
-  const int stage_bytes = A_TILE_BYTES + block_n * 128;
+  const int stage_bytes = A_TILE_BYTES + block_n * BLOCK_K * 2;
   int stages = d->stages;
   if (stages <= 0) {
     stages = (204 * 1024) / stage_bytes;
@@ -364,10 +370,11 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   MC_CHECK_ARG(smem_bytes <= 227 * 1024, "mc_conv_fwd: smem %zu too large", smem_bytes);
 
   CUtensorMap tm_a, tm_b;
-  int rc = mc_make_tmap_2d_bf16(&tm_a, d->d_in, (uint64_t)M_rows, (uint64_t)d->Cin, (uint64_t)d->Cin_ld, BLOCK_M);
+  int rc = mc_make_tmap_2d_bf16_k(&tm_a, d->d_in, (uint64_t)M_rows, (uint64_t)d->Cin, (uint64_t)d->Cin_ld, BLOCK_M, BLOCK_K);
   if (rc) return rc;
   // weights: [n_tiles*block_n >= Npad rows (OOB rows zero-filled), ntaps*Kc]
-  rc = mc_make_tmap_2d_bf16(&tm_b, d->d_wpack, (uint64_t)d->Npad, (uint64_t)ntaps * Kc, (uint64_t)ntaps * Kc, (uint32_t)block_n);
+  rc = mc_make_tmap_2d_bf16_k(&tm_b, d->d_wpack, (uint64_t)d->Npad, (uint64_t)ntaps * Kc, (uint64_t)ntaps * Kc,
+                              (uint32_t)block_n, BLOCK_K);
   if (rc) return rc;
 
   ConvKParams p;
@@ -375,6 +382,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   p.N = d->N;
   p.Npad = d->Npad;
   p.kb_per_tap = Kc / BLOCK_K;
+  p.block_k = BLOCK_K;
   p.num_kb = ntaps * p.kb_per_tap;
   p.ksize = d->ksize;
   p.W = d->W;

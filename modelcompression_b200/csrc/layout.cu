@@ -292,7 +292,7 @@ extern "C" int mc_pack_conv_weights(const float* d_w, const float* d_mask, int O
                                     void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MC_CHECK_ARG(d_w && d_wpack && O > 0 && C > 0 && (ksize == 1 || ksize == 3), "mc_pack_conv_weights: bad argument");
-  MC_CHECK_ARG(n_o > 0 && n_o <= Npad && n_c > 0 && n_c <= Kc && (Kc % 64) == 0 && (Npad % 16) == 0,
+  MC_CHECK_ARG(n_o > 0 && n_o <= Npad && n_c > 0 && n_c <= Kc && (Kc % 32) == 0 && (Npad % 16) == 0,
                "mc_pack_conv_weights: bad packed dims (n_o=%d Npad=%d n_c=%d Kc=%d)", n_o, Npad, n_c, Kc);
   MC_CHECK_ARG((d_oidx || n_o <= O) && (d_cidx || n_c <= C), "mc_pack_conv_weights: counts exceed tensor dims");
   const int taps = ksize * ksize;

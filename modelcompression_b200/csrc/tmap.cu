@@ -85,6 +85,16 @@ int mc_make_tmap(CUtensorMap* tm, CUtensorMapDataType dtype, int rank, const voi
   return 0;
 }
 
+int mc_make_tmap_2d_bf16_k(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                           uint32_t box_rows, uint32_t box_cols) {
+  const uint64_t dims[2] = {cols, rows};
+  const uint64_t strides[1] = {ld * 2};
+  const uint32_t box[2] = {box_cols, box_rows};
+  // the swizzle span equals the box row: 64 bf16 = 128 B, 32 bf16 = 64 B
+  return mc_make_tmap(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box,
+                      box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 int mc_make_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                          uint32_t box_rows) {
   const uint64_t dims[2] = {cols, rows};

@@ -11,3 +11,7 @@ int mc_make_tmap(CUtensorMap* tm, CUtensorMapDataType dtype, int rank, const voi
 // 2-D bf16 row-major [rows, cols], row pitch ld elements, box = [box_rows, 64 cols], 128 B swizzle.
 int mc_make_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                          uint32_t box_rows);
+
+// same with box = [box_rows, box_cols] for box_cols in {32, 64}: 64 B swizzle for the 32-column (64-byte) box.
+int mc_make_tmap_2d_bf16_k(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                           uint32_t box_rows, uint32_t box_cols);

@@ -761,7 +761,7 @@ extern "C" int mc_pack_conv_weights_dgrad(const float* d_w, const float* d_mask,
                                           int Cpad, int Ko, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MC_CHECK_ARG(d_w && d_wpack && O > 0 && C > 0 && (ksize == 1 || ksize == 3), "mc_pack_conv_weights_dgrad: bad argument");
-  MC_CHECK_ARG(Cpad >= C && (Cpad % 16) == 0 && Ko >= O && (Ko % 64) == 0, "mc_pack_conv_weights_dgrad: bad packed dims");
+  MC_CHECK_ARG(Cpad >= C && (Cpad % 16) == 0 && Ko >= O && (Ko % 32) == 0, "mc_pack_conv_weights_dgrad: bad packed dims");
   const int taps = ksize * ksize;
   const long long total = (long long)Cpad * taps * Ko;
   pack_dgrad_weights_kernel<<<grid_for(total, 256), 256, 0, stream>>>(d_w, d_mask, O, C, taps, (__nv_bfloat16*)d_wpack,

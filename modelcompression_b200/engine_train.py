@@ -226,8 +226,14 @@ class TrainPlan(object):
         return got
 
 
-def _conv_desc(in_ptr, wpack, scale, shift, out_ptr, B, H, W, Cin, Cin_ld, N, Npad, k, leaky, epi, ldc, ch_off):
+def _kblk(C):
+    """k-block of the tcgen05 conv: 32 (64-byte swizzle) where it halves the K work, i.e. for <= 32 channels."""
+    return 32 if C <= 32 else 64
+
+
+def _conv_desc(in_ptr, wpack, scale, shift, out_ptr, B, H, W, Cin, Cin_ld, N, Npad, k, leaky, epi, ldc, ch_off, block_k=0):
     d = _lib.mc_conv_desc()
+    d.block_k = block_k
     d.d_in, d.d_wpack, d.d_scale, d.d_shift, d.d_out = in_ptr, wpack, scale, shift, out_ptr
     d.B, d.H, d.W, d.Cin, d.Cin_ld, d.N, d.Npad = B, H, W, Cin, Cin_ld, N, Npad
     d.ksize, d.leaky, d.epi_mode, d.ldc, d.ch_off, d.block_n, d.stages = k, leaky, epi, ldc, ch_off, 0, 0
@@ -286,7 +292,8 @@ def _forward(plan, x, training_stats=True, after_layer=None):
                                               z.data_ptr(), B, L.H, L.W, C, C, O, L.z.ld, 0, 0, s), "conv1 forward")
             sv.keep_alive = (wfull, sc1, sh0)
         else:
-            Kc = _round_up(C, 64)
+            kb = _kblk(C)
+            Kc = _round_up(C, kb)
             wpack = torch.empty(Npad, k * k * Kc, dtype=torch.bfloat16, device=dev)
             _lib.check(lib.mc_pack_conv_weights(w.data_ptr(), mask_ptr, O, C, k, None, O, None, C, wpack.data_ptr(), Npad,
                                                 Kc, s), "mc_pack_conv_weights")
@@ -297,12 +304,12 @@ def _forward(plan, x, training_stats=True, after_layer=None):
                 shift = torch.zeros(Npad, device=dev)
                 shift[:O] = conv.bias.data
                 d = _conv_desc(in_ptr, wpack.data_ptr(), ones.data_ptr(), shift.data_ptr(), y.data_ptr(), B, L.H, L.W, C,
-                               src.ld, O, Npad, k, 0, _lib.MC_EPI_NCHW_F32, 0, 0)
+                               src.ld, O, Npad, k, 0, _lib.MC_EPI_NCHW_F32, 0, 0, kb)
                 _lib.check(lib.mc_conv_fwd(ctypes.byref(d), s), "head forward")
                 continue
             z = bufs[L.z.name]
             d = _conv_desc(in_ptr, wpack.data_ptr(), ones.data_ptr(), zeros.data_ptr(), z.data_ptr(), B, L.H, L.W, C,
-                           src.ld, O, Npad, k, 0, _lib.MC_EPI_PNHWC, L.z.ld, 0)
+                           src.ld, O, Npad, k, 0, _lib.MC_EPI_PNHWC, L.z.ld, 0, kb)
             _lib.check(lib.mc_conv_fwd(ctypes.byref(d), s), "conv forward (block %d)" % L.ind)
         # ---- batch statistics + affine + leaky
         bn = L.bn
@@ -419,14 +426,15 @@ def _backward(plan, sv, dy, before_bn=None):
             dname = 'd' + src.name
             if dname in written:
                 raise NotImplementedError("two convolutions consume the same activation slice (block %d)" % L.ind)
-            Cpad, Ko = _round_up(C, 16), _round_up(O, 64)
+            kb = _kblk(O)
+            Cpad, Ko = _round_up(C, 16), _round_up(O, kb)
             wpack = torch.empty(Cpad, k * k * Ko, dtype=torch.bfloat16, device=dev)
             _lib.check(lib.mc_pack_conv_weights_dgrad(conv.weight.data_ptr(), mask_ptr, O, C, k, wpack.data_ptr(), Cpad, Ko,
                                                       s), "mc_pack_conv_weights_dgrad")
             ones = torch.ones(Cpad, device=dev)
             zeros = torch.zeros(Cpad, device=dev)
             d = _conv_desc(dz_ptr, wpack.data_ptr(), ones.data_ptr(), zeros.data_ptr(), bufs[dname].data_ptr(), B, L.H, L.W,
-                           O, ld_dz, C, Cpad, k, 0, _lib.MC_EPI_PNHWC, src.ld, src.ch_off)
+                           O, ld_dz, C, Cpad, k, 0, _lib.MC_EPI_PNHWC, src.ld, src.ch_off, kb)
             _lib.check(lib.mc_conv_fwd(ctypes.byref(d), s), "dgrad (block %d)" % L.ind)
             written.add(dname)
     for work, t in pending:  # the current stream waits for NCCL; gradients become the mean over the replicas

@@ -199,3 +199,38 @@ def test_uint8_image_input_matches_float_path(cfg_path):
                 yu = model(xu)
             yf = model(xu.float().div(255.0))
         assert yu.dtype == torch.float32 and torch.equal(yu, yf)
+
+
+@pytest.mark.parametrize("C,O,k", [(32, 64, 3), (69, 145, 3), (17, 40, 1), (96, 32, 3)])
+def test_conv_k_block_32(C, O, k):
+    """mc_conv_fwd with block_k = 32 (64-byte swizzle, Kc = round_up(Cin, 32)) equals the 64-wide k-block path."""
+    import ctypes
+    from modelcompression_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(C)
+    B, H, W = 2, 13, 21
+    x = torch.randn(B, C, H, W, device=DEV)
+    w = torch.randn(O, C, k, k, device=DEV) * 0.1
+    ld_in, Npad, ld_out = (C + 7) // 8 * 8, (O + 15) // 16 * 16, (O + 7) // 8 * 8
+    outs = []
+    with torch.cuda.device(0):
+        s = _lib.stream_ptr()
+        xin = torch.empty(B * (H + 1) * (W + 1), ld_in, dtype=torch.bfloat16, device=DEV)
+        _lib.check(lib.mc_pack_pnhwc(x.data_ptr(), xin.data_ptr(), B, H, W, C, ld_in, s), "pack")
+        scale, shift = torch.ones(Npad, device=DEV), torch.zeros(Npad, device=DEV)
+        for kb in (64, 32):
+            Kc = (C + kb - 1) // kb * kb
+            wpack = torch.empty(Npad, k * k * Kc, dtype=torch.bfloat16, device=DEV)
+            _lib.check(lib.mc_pack_conv_weights(w.data_ptr(), None, O, C, k, None, O, None, C, wpack.data_ptr(), Npad, Kc, s), "packw")
+            yb = torch.zeros(B * (H + 1) * (W + 1), ld_out, dtype=torch.bfloat16, device=DEV)
+            d = _lib.mc_conv_desc()
+            d.d_in, d.d_wpack, d.d_scale, d.d_shift, d.d_out = xin.data_ptr(), wpack.data_ptr(), scale.data_ptr(), shift.data_ptr(), yb.data_ptr()
+            d.B, d.H, d.W, d.Cin, d.Cin_ld, d.N, d.Npad = B, H, W, C, ld_in, O, Npad
+            d.ksize, d.leaky, d.epi_mode, d.ldc, d.ch_off, d.block_n, d.stages, d.block_k = k, 1, _lib.MC_EPI_PNHWC, ld_out, 0, 0, 0, kb
+            _lib.check(lib.mc_conv_fwd(ctypes.byref(d), s), "conv")
+            y = torch.empty(B, O, H, W, device=DEV)
+            _lib.check(lib.mc_unpack_pnhwc(yb.data_ptr(), y.data_ptr(), B, H, W, O, ld_out, 0, s), "unpack")
+            outs.append(y)
+    ref = F.leaky_relu(F.conv2d(x.bfloat16().float(), w.bfloat16().float(), padding=(k - 1) // 2), 0.1)
+    assert (outs[0] - ref).abs().max() <= 5e-3 * ref.abs().max() + 2e-3
+    assert (outs[1] - ref).abs().max() <= 5e-3 * ref.abs().max() + 2e-3
