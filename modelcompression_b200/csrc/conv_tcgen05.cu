@@ -13,6 +13,7 @@
 // 128-byte swizzle row.  Warp roles: warp0 = TMA producer, warp1 = TMEM owner + MMA issuer (one thread),
 // warps 2..5 = epilogue (TMEM -> regs -> scale/shift/leaky -> bf16/fp32 global stores).
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 #include "tmap.cuh"
@@ -21,6 +22,10 @@ namespace {
 
 constexpr int BLOCK_M = 128;  // k-block: 64 bf16 (128-byte swizzle rows) or 32 bf16 (64-byte swizzle rows), per launch
 constexpr int MAX_STAGES = 8;
+constexpr int MAX_A_STAGES = 3;
+constexpr int A_BOX_ROWS = BLOCK_M + 8;          // rows m0-1 .. m0+134: the dx = -1, 0, +1 windows of a 128-row tile
+constexpr int A_BOX_BYTES = A_BOX_ROWS * 128;   // 17,408 B landed by TMA
+constexpr int A_BOX_STRIDE = 18 * 1024;         // ring pitch (1024-byte aligned for the 128-byte swizzle)
 constexpr int NUM_THREADS = 192;
 
 struct ConvKParams {
@@ -33,6 +38,7 @@ struct ConvKParams {
   int ksize;       // 1 or 3
   int Wp, Hp, W, H;  // Wp = W+1, Hp = H+1
   int block_n, stages, tmem_cols, acc_stride;  // acc_stride: TMEM columns between the two accumulator stages
+  int share_dx, a_stages;  // 3x3 only: one A box (136 rows) serves the three dx taps of a filter row; separate A / B rings
   int m_tiles, n_tiles;
   uint32_t idesc;
   const float* scale;
@@ -179,7 +185,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvKParams& p, uint32_t tme
 // accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const ConvKParams p) {
+                         const __grid_constant__ CUtensorMap tmap_abox, const ConvKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve-up: [stages x (A 16KB | B block_n*128)] | barriers | tmem ptr | scale/shift staging (4 KB)
   const uint32_t a_tile_bytes = (uint32_t)(BLOCK_M * p.block_k * 2);
@@ -191,12 +197,16 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     smem += (1024u - (a & 1023u)) & 1023u;
   }
   uint8_t* tiles = smem;
-  uint8_t* aux = tiles + (size_t)p.stages * stage_bytes;
+  // share_dx: [a_stages x A box (18 KB pitch)] [stages x B tile]; else [stages x (A | B)]
+  uint8_t* b_ring = tiles + (size_t)p.a_stages * A_BOX_STRIDE;
+  uint8_t* aux = p.share_dx ? b_ring + (size_t)p.stages * b_tile_bytes : tiles + (size_t)p.stages * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* afull_bar = tmem_empty_bar + 2;           // [MAX_A_STAGES]
+  uint64_t* aempty_bar = afull_bar + MAX_A_STAGES;    // [MAX_A_STAGES]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aempty_bar + MAX_A_STAGES);
   float* s_ss = reinterpret_cast<float*>(aux + 256);  // [2 acc stages][scale|shift][256]
 
   const int warp_idx = threadIdx.x >> 5;
@@ -214,6 +224,11 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       ptx::mbar_init(&tmem_full_bar[a], 1);
       ptx::mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
     }
+    for (int a = 0; a < MAX_A_STAGES; ++a) {
+      ptx::mbar_init(&afull_bar[a], 1);
+      ptx::mbar_init(&aempty_bar[a], 1);
+    }
+    ptx::prefetch_tensormap(&tmap_abox);
     ptx::fence_barrier_init();
   }
   if (warp_idx == 1) {
@@ -227,7 +242,31 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   if (warp_idx == 0) {
     // ===================== TMA producer (one thread) =====================
-    if (lane == 0) {
+    if (lane == 0 && p.share_dx) {
+      // A: one 136-row box per (filter row dy, channel block) — the three dx taps read it at row offsets 0, 1, 2, so
+      // the activations cross L2 -> smem 3 times per tile instead of 9.  B: one tile per tap, its own ring.
+      int s = 0, sa = 0;
+      uint32_t phase = 0, pha = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.n_tiles) * p.block_n;
+        const int m0 = (tile / p.n_tiles) * BLOCK_M;
+        for (int g = 0; g < 3 * p.kb_per_tap; ++g) {
+          const int dy = g / p.kb_per_tap, cb = g - dy * p.kb_per_tap;
+          ptx::mbar_wait(&aempty_bar[sa], pha ^ 1u);
+          ptx::mbar_arrive_expect_tx(&afull_bar[sa], A_BOX_BYTES);
+          ptx::tma_load_2d(tiles + (size_t)sa * A_BOX_STRIDE, &tmap_abox, &afull_bar[sa], cb * 64,
+                           m0 + (dy - 1) * p.Wp - 1);
+          if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
+          for (int dx = 0; dx < 3; ++dx) {
+            const int kb = (dy * 3 + dx) * p.kb_per_tap + cb;
+            ptx::mbar_wait(&empty_bar[s], phase ^ 1u);
+            ptx::mbar_arrive_expect_tx(&full_bar[s], b_tile_bytes);
+            ptx::tma_load_2d(b_ring + (size_t)s * b_tile_bytes, &tmap_b, &full_bar[s], kb * 64, n0);
+            if (++s == p.stages) { s = 0; phase ^= 1u; }
+          }
+        }
+      }
+    } else if (lane == 0) {
       int s = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -250,7 +289,39 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    if (lane == 0 && p.share_dx) {
+      int s = 0, sa = 0, as = 0;
+      uint32_t phase = 0, pha = 0, aphase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(as * p.acc_stride);
+        for (int g = 0; g < 3 * p.kb_per_tap; ++g) {
+          ptx::mbar_wait(&afull_bar[sa], pha);
+          const uint32_t a_addr = ptx::smem_u32(tiles + (size_t)sa * A_BOX_STRIDE);
+          for (int dx = 0; dx < 3; ++dx) {
+            ptx::mbar_wait(&full_bar[s], phase);
+            ptx::tc_fence_after();
+            // the window of tap dx starts dx rows (dx * 128 B) into the box.  The start is then not aligned to the
+            // 1024-byte swizzle pattern; measured on B200: the tensor core applies the 128-byte swizzle to the absolute
+            // shared-memory address (as TMA did when it wrote the box), so the descriptor's base-offset field must stay
+            // 0 — setting it to dx (or 8-dx) reads garbage (tools/debug_share.py)
+            const uint64_t adesc = ptx::make_sw128_kmajor_desc(a_addr + (uint32_t)dx * 128u);
+            const uint64_t bdesc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(b_ring + (size_t)s * b_tile_bytes));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_bf16_ss(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
+                                (g > 0 || dx > 0 || k > 0) ? 1u : 0u);
+            ptx::umma_commit(&empty_bar[s]);
+            if (++s == p.stages) { s = 0; phase ^= 1u; }
+          }
+          ptx::umma_commit(&aempty_bar[sa]);  // the box may be refilled once the MMAs of its three taps retire
+          if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
+        }
+        ptx::umma_commit(&tmem_full_bar[as]);
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    } else if (lane == 0) {
       int s = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -360,18 +431,43 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   const int n_tiles = (d->Npad + block_n - 1) / block_n;
 
   const int stage_bytes = A_TILE_BYTES + block_n * BLOCK_K * 2;
-  int stages = d->stages;
-  if (stages <= 0) {
-    stages = (204 * 1024) / stage_bytes;
-    if (stages > MAX_STAGES) stages = MAX_STAGES;
+  // 3x3 with 64-wide k-blocks: share one activation box among the three dx taps (MCB200_SHARE_DX=0 disables)
+  static int share_env = -1;
+  if (share_env < 0) {
+    const char* e = getenv("MCB200_SHARE_DX");
+    share_env = (e && e[0] == '0') ? 0 : 1;
   }
-  MC_CHECK_ARG(stages >= 1 && stages <= MAX_STAGES, "mc_conv_fwd: stages %d invalid", stages);
-  const size_t smem_bytes = (size_t)stages * stage_bytes + 256 + 4096 + 1024;
+  const int share_dx = (d->ksize == 3 && BLOCK_K == 64 && share_env) ? 1 : 0;
+  int stages = d->stages;
+  int a_stages = 0;
+  size_t smem_bytes;
+  if (share_dx) {
+    a_stages = MAX_A_STAGES;
+    const int b_bytes = block_n * 128;
+    if (stages <= 0) {
+      stages = (204 * 1024 - a_stages * A_BOX_STRIDE) / b_bytes;
+      if (stages > MAX_STAGES) stages = MAX_STAGES;
+    }
+    MC_CHECK_ARG(stages >= 2 && stages <= MAX_STAGES, "mc_conv_fwd: stages %d invalid", stages);
+    smem_bytes = (size_t)a_stages * A_BOX_STRIDE + (size_t)stages * b_bytes + 256 + 4096 + 1024;
+  } else {
+    if (stages <= 0) {
+      stages = (204 * 1024) / stage_bytes;
+      if (stages > MAX_STAGES) stages = MAX_STAGES;
+    }
+    MC_CHECK_ARG(stages >= 1 && stages <= MAX_STAGES, "mc_conv_fwd: stages %d invalid", stages);
+    smem_bytes = (size_t)stages * stage_bytes + 256 + 4096 + 1024;
+  }
   MC_CHECK_ARG(smem_bytes <= 227 * 1024, "mc_conv_fwd: smem %zu too large", smem_bytes);
 
-  CUtensorMap tm_a, tm_b;
+  CUtensorMap tm_a, tm_b, tm_abox;
   int rc = mc_make_tmap_2d_bf16_k(&tm_a, d->d_in, (uint64_t)M_rows, (uint64_t)d->Cin, (uint64_t)d->Cin_ld, BLOCK_M, BLOCK_K);
   if (rc) return rc;
+  tm_abox = tm_a;
+  if (share_dx) {
+    rc = mc_make_tmap_2d_bf16_k(&tm_abox, d->d_in, (uint64_t)M_rows, (uint64_t)d->Cin, (uint64_t)d->Cin_ld, A_BOX_ROWS, 64);
+    if (rc) return rc;
+  }
   // weights: [n_tiles*block_n >= Npad rows (OOB rows zero-filled), ntaps*Kc]
   rc = mc_make_tmap_2d_bf16_k(&tm_b, d->d_wpack, (uint64_t)d->Npad, (uint64_t)ntaps * Kc, (uint64_t)ntaps * Kc,
                               (uint32_t)block_n, BLOCK_K);
@@ -391,6 +487,8 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   p.Hp = d->H + 1;
   p.block_n = block_n;
   p.stages = stages;
+  p.share_dx = share_dx;
+  p.a_stages = a_stages;
   p.acc_stride = ((block_n + 31) / 32) * 32;
   int tc = 32;
   while (tc < 2 * p.acc_stride) tc <<= 1;
@@ -413,7 +511,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   }
   long long total_tiles = (long long)n_tiles * m_tiles;
   int grid = (int)(total_tiles < mc_num_sms() ? total_tiles : mc_num_sms());
-  conv_gemm_tcgen05_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tm_a, tm_b, p);
+  conv_gemm_tcgen05_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tm_a, tm_b, tm_abox, p);
   MC_LAUNCH_CHECK("conv_gemm_tcgen05_kernel");
   return 0;
 }
