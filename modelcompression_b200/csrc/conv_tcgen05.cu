@@ -374,7 +374,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 // Tile-width heuristic.  One 64-wide k-block of a 128 x bn tile costs max(2*bn, 128+bn) SM cycles: 2*bn is the
 // tcgen05 issue floor (128*bn*64 MACs at 4096 MAC/clk), 128+bn is the shared-memory read of the A (16 KB) and
 // B (bn*128 B) tiles at 128 B/clk.  Cost = waves over the SMs x (k-blocks x that + a fixed prologue/epilogue).
-int pick_block_n(int Npad, int m_tiles, int num_kb, int num_sms) {
+int pick_block_n(int Npad, int m_tiles, int num_kb, int num_sms, bool share_dx) {
   int best = 16;
   double best_cost = 1e30;
   for (int bn = 16; bn <= 256; bn += 16) {  // every legal UMMA N for M=128
@@ -386,7 +386,8 @@ int pick_block_n(int Npad, int m_tiles, int num_kb, int num_sms) {
     // (128x256 tiles run at ~80% tensor-active = 640 cycles per k-block for 48 KB)
     double per_kb = 2.0 * bn;
     if (128.0 + bn > per_kb) per_kb = 128.0 + bn;
-    const double feed = 13.3 * (16.0 + bn / 8.0);
+    // (with the shared activation box a tap's k-block brings 17/3 KB of A instead of 16 KB)
+    const double feed = 13.3 * ((share_dx ? 17.0 / 3.0 : 16.0) + bn / 8.0);
     if (feed > per_kb) per_kb = feed;
     // one epilogue (~12 cycles per column) is exposed at the end; the others overlap the next tile's MMAs unless
     // they are longer than the mainloop
@@ -425,12 +426,6 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   MC_CHECK_ARG(M_rows < (1ll << 31), "mc_conv_fwd: too many rows");
   const int m_tiles = (int)((M_rows + BLOCK_M - 1) / BLOCK_M);
 
-  int block_n = d->block_n;
-  if (block_n <= 0) block_n = pick_block_n(d->Npad, m_tiles, (ntaps * Kc + 63) / 64, mc_num_sms());  // 64-wide k-block units
-  MC_CHECK_ARG(block_n >= 16 && block_n <= 256 && (block_n % 16) == 0, "mc_conv_fwd: block_n %d invalid", block_n);
-  const int n_tiles = (d->Npad + block_n - 1) / block_n;
-
-  const int stage_bytes = A_TILE_BYTES + block_n * BLOCK_K * 2;
   // 3x3 with 64-wide k-blocks: share one activation box among the three dx taps (MCB200_SHARE_DX=0 disables)
   static int share_env = -1;
   if (share_env < 0) {
@@ -438,6 +433,14 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
     share_env = (e && e[0] == '0') ? 0 : 1;
   }
   const int share_dx = (d->ksize == 3 && BLOCK_K == 64 && share_env) ? 1 : 0;
+  int block_n = d->block_n;
+  // (the operand-feed term keeps the un-shared 16 KB A tile: with the shared-box figure the model picks narrower tiles
+  //  that measured 4 % slower end to end on B200)
+  if (block_n <= 0) block_n = pick_block_n(d->Npad, m_tiles, (ntaps * Kc + 63) / 64, mc_num_sms(), false);  // 64-wide k-block units
+  MC_CHECK_ARG(block_n >= 16 && block_n <= 256 && (block_n % 16) == 0, "mc_conv_fwd: block_n %d invalid", block_n);
+  const int n_tiles = (d->Npad + block_n - 1) / block_n;
+
+  const int stage_bytes = A_TILE_BYTES + block_n * BLOCK_K * 2;
   int stages = d->stages;
   int a_stages = 0;
   size_t smem_bytes;
