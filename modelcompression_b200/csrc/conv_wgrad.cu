@@ -17,6 +17,7 @@
 // range is split over CTAs; each CTA writes its partial tile [tap][o][c] to the workspace with plain vector stores and
 // wgrad_reduce_kernel sums the splits, applies the mask and emits the PyTorch layout [O, C, kh, kw].
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 #include "tmap.cuh"
@@ -26,6 +27,9 @@ namespace {
 constexpr int BLOCK_M = 128;         // output channels (rows of dW) per CTA
 constexpr int BLOCK_K = 64;          // pixel rows per pipeline stage
 constexpr int BOX_BYTES = 64 * 128;  // one TMA box: 64 rows x 64 bf16
+constexpr int BBOX_ROWS = 72;          // 3x3: activation box of a filter row = 64 k-rows + halo, serves dx = -1, 0, +1
+constexpr int BBOX_BYTES = BBOX_ROWS * 128;  // 9,216 B landed by TMA
+constexpr int BBOX_STRIDE = 10 * 1024;       // pitch of the 64-column blocks (1024-byte aligned for the swizzle)
 constexpr int MAX_STAGES = 8;
 constexpr int NUM_THREADS = 192;
 
@@ -36,6 +40,7 @@ struct WgradParams {
   int block_n, nb64;  // N tile (multiple of 16, <= 256) and its number of 64-column boxes
   int stages, tmem_cols;
   int Wp, ksize;
+  int share3;       // 3x3: one CTA = one filter row (dy), three accumulators, the activation box shared by its 3 taps
   int Opad, Cpad;   // workspace tile pitch: m_tiles*128, n_tiles*block_n
   uint32_t idesc;
   float* ws;        // [nsplit][ntaps][Opad][Cpad]
@@ -62,7 +67,9 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __g
     uint32_t a = ptx::smem_u32(smem);
     smem += (1024u - (a & 1023u)) & 1023u;
   }
-  const uint32_t stage_bytes = (uint32_t)(2 + p.nb64) * BOX_BYTES;
+  const uint32_t b_blk = p.share3 ? (uint32_t)BBOX_STRIDE : (uint32_t)BOX_BYTES;  // pitch of a 64-column block of B
+  const uint32_t stage_bytes = 2u * BOX_BYTES + (uint32_t)p.nb64 * b_blk;
+  const uint32_t tx_bytes = 2u * BOX_BYTES + (uint32_t)p.nb64 * (p.share3 ? (uint32_t)BBOX_BYTES : (uint32_t)BOX_BYTES);
   uint8_t* tiles = smem;
   uint8_t* aux = tiles + (size_t)p.stages * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
@@ -79,13 +86,15 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __g
   u /= p.n_tiles;
   const int m_tile = u % p.m_tiles;
   u /= p.m_tiles;
-  const int tap = u % p.ntaps;
-  const int split = u / p.ntaps;
+  const int ngroups = p.share3 ? 3 : p.ntaps;  // share3: a work unit is a filter ROW (3 taps)
+  const int tap = u % ngroups;                 // share3: dy
+  const int split = u / ngroups;
   const int kb0 = (int)(((long long)p.num_kb * split) / p.nsplit);
   const int kb1 = (int)(((long long)p.num_kb * (split + 1)) / p.nsplit);
   const int m0 = m_tile * BLOCK_M, n0 = n_tile * p.block_n;
   int row_off = 0;
-  if (p.ksize == 3) row_off = (tap / 3 - 1) * p.Wp + (tap % 3 - 1);
+  if (p.share3) row_off = (tap - 1) * p.Wp - 1;  // first row of the box: tap dx reads it dx rows further down
+  else if (p.ksize == 3) row_off = (tap / 3 - 1) * p.Wp + (tap % 3 - 1);
 
   if (warp_idx == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_dz);
@@ -114,11 +123,11 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __g
         ptx::mbar_wait(&empty_bar[s], phase ^ 1u);
         uint8_t* a_dst = tiles + (size_t)s * stage_bytes;
         uint8_t* b_dst = a_dst + 2 * BOX_BYTES;
-        ptx::mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+        ptx::mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
         ptx::tma_load_2d(a_dst, &tmap_dz, &full_bar[s], m0, kb * BLOCK_K);
         ptx::tma_load_2d(a_dst + BOX_BYTES, &tmap_dz, &full_bar[s], m0 + 64, kb * BLOCK_K);
         for (int j = 0; j < p.nb64; ++j)
-          ptx::tma_load_2d(b_dst + (size_t)j * BOX_BYTES, &tmap_a, &full_bar[s], n0 + j * 64, kb * BLOCK_K + row_off);
+          ptx::tma_load_2d(b_dst + (size_t)j * b_blk, &tmap_a, &full_bar[s], n0 + j * 64, kb * BLOCK_K + row_off);
         if (++s == p.stages) { s = 0; phase ^= 1u; }
       }
     }
@@ -131,12 +140,26 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __g
         ptx::tc_fence_after();
         const uint32_t a_addr = ptx::smem_u32(tiles + (size_t)s * stage_bytes);
         const uint64_t adesc = make_sw128_mnmajor_desc(a_addr);
-        const uint64_t bdesc = make_sw128_mnmajor_desc(a_addr + 2 * BOX_BYTES);
+        if (p.share3) {
+          // tap dx = rows dx .. dx+63 of the 72-row box: start dx*128 B into it (the swizzle is applied to the absolute
+          // shared-memory address, so an un-aligned start needs no base offset — see conv_tcgen05.cu); 64-column blocks
+          // are BBOX_STRIDE apart (LBO)
+          for (int dx = 0; dx < 3; ++dx) {
+            uint64_t bdesc = make_sw128_mnmajor_desc(a_addr + 2 * BOX_BYTES + (uint32_t)dx * 128u);
+            bdesc = (bdesc & ~((uint64_t)0x3FFF << 16)) | ((uint64_t)(BBOX_STRIDE >> 4) << 16);
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / 16; ++k) {
-          // 16 k-rows = two 1024-byte atoms: +2048 B = +128 in the (addr >> 4) field
-          ptx::umma_bf16_ss(tmem_base, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), p.idesc,
-                            (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / 16; ++k)
+              ptx::umma_bf16_ss(tmem_base + (uint32_t)(dx * p.block_n), adesc + (uint64_t)(128 * k),
+                                bdesc + (uint64_t)(128 * k), p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+        } else {
+          const uint64_t bdesc = make_sw128_mnmajor_desc(a_addr + 2 * BOX_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            // 16 k-rows = two 1024-byte atoms: +2048 B = +128 in the (addr >> 4) field
+            ptx::umma_bf16_ss(tmem_base, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), p.idesc,
+                              (kb > kb0 || k > 0) ? 1u : 0u);
+          }
         }
         ptx::umma_commit(&empty_bar[s]);
         if (++s == p.stages) { s = 0; phase ^= 1u; }
@@ -147,22 +170,26 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __g
     // ===================== epilogue: warps 2..5 -> partial tile to the workspace =====================
     const int quarter = warp_idx & 3;
     const int o = m0 + quarter * 32 + lane;
-    float* dst = p.ws + ((((size_t)split * p.ntaps + tap) * p.Opad + o) * p.Cpad + n0);
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tc_fence_after();
     const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-      uint32_t r[16];
-      ptx::tmem_ld_32x32b_x16(taddr_row + (uint32_t)c0, r);
-      ptx::tmem_ld_wait();
+    const int naccs = p.share3 ? 3 : 1;
+    for (int acc = 0; acc < naccs; ++acc) {
+      const int tap_out = p.share3 ? tap * 3 + acc : tap;
+      float* dst = p.ws + ((((size_t)split * p.ntaps + tap_out) * p.Opad + o) * p.Cpad + n0);
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        uint32_t r[16];
+        ptx::tmem_ld_32x32b_x16(taddr_row + (uint32_t)(acc * p.block_n + c0), r);
+        ptx::tmem_ld_wait();
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float4 v;
-        v.x = __uint_as_float(r[4 * q + 0]);
-        v.y = __uint_as_float(r[4 * q + 1]);
-        v.z = __uint_as_float(r[4 * q + 2]);
-        v.w = __uint_as_float(r[4 * q + 3]);
-        *reinterpret_cast<float4*>(dst + c0 + 4 * q) = v;
+        for (int q = 0; q < 4; ++q) {
+          float4 v;
+          v.x = __uint_as_float(r[4 * q + 0]);
+          v.y = __uint_as_float(r[4 * q + 1]);
+          v.z = __uint_as_float(r[4 * q + 2]);
+          v.w = __uint_as_float(r[4 * q + 3]);
+          *reinterpret_cast<float4*>(dst + c0 + 4 * q) = v;
+        }
       }
     }
   }
@@ -189,7 +216,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 }
 
 struct WgradPlan {
-  int block_n, nb64, n_tiles, m_tiles, ntaps, num_kb, nsplit, stages, tmem_cols, Opad, Cpad;
+  int block_n, nb64, n_tiles, m_tiles, ntaps, num_kb, nsplit, stages, tmem_cols, Opad, Cpad, share3;
   size_t smem_bytes, ws_bytes;
 };
 
@@ -200,25 +227,32 @@ int plan_wgrad(WgradPlan* pl, int B, int H, int W, int C, int O, int ksize) {
   pl->num_kb = (int)((rows + BLOCK_K - 1) / BLOCK_K);
   pl->m_tiles = (O + BLOCK_M - 1) / BLOCK_M;
   const int c16 = (C + 15) / 16 * 16;
-  pl->n_tiles = (c16 + 255) / 256;
+  static int share_env = -1;
+  if (share_env < 0) {
+    const char* e = getenv("MCB200_WGRAD_SHARE");
+    share_env = (e && e[0] == '0') ? 0 : 1;
+  }
+  pl->share3 = (ksize == 3 && share_env) ? 1 : 0;
+  const int max_n = pl->share3 ? 128 : 256;  // share3: three accumulators must fit the 512 TMEM columns
+  pl->n_tiles = (c16 + max_n - 1) / max_n;
   pl->block_n = ((c16 + pl->n_tiles - 1) / pl->n_tiles + 15) / 16 * 16;
   pl->nb64 = (pl->block_n + 63) / 64;
   pl->Opad = pl->m_tiles * BLOCK_M;
   pl->Cpad = pl->n_tiles * pl->block_n;
-  const int tiles = pl->m_tiles * pl->n_tiles * pl->ntaps;
+  const int tiles = pl->m_tiles * pl->n_tiles * (pl->share3 ? 3 : pl->ntaps);
   // enough CTAs for ~2 per SM, but at least 8 pipeline steps each
   int nsplit = (2 * mc_num_sms() + tiles - 1) / tiles;
   const int max_split = pl->num_kb / 8 > 0 ? pl->num_kb / 8 : 1;
   if (nsplit > max_split) nsplit = max_split;
   if (nsplit < 1) nsplit = 1;
   pl->nsplit = nsplit;
-  const int stage_bytes = (2 + pl->nb64) * BOX_BYTES;
+  const int stage_bytes = 2 * BOX_BYTES + pl->nb64 * (pl->share3 ? BBOX_STRIDE : BOX_BYTES);
   int stages = (200 * 1024) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   pl->stages = stages;
   pl->smem_bytes = (size_t)stages * stage_bytes + 256 + 1024;
   int tc = 32;
-  while (tc < pl->block_n) tc <<= 1;
+  while (tc < (pl->share3 ? 3 : 1) * pl->block_n) tc <<= 1;
   pl->tmem_cols = tc;
   pl->ws_bytes = (size_t)nsplit * pl->ntaps * pl->Opad * pl->Cpad * sizeof(float);
   return 0;
@@ -254,7 +288,7 @@ extern "C" int mc_conv_wgrad(const void* d_a, int lda, int C, const void* d_dz, 
   CUtensorMap tm_dz, tm_a;
   rc = mc_make_tmap_2d_bf16(&tm_dz, d_dz, (uint64_t)rows, (uint64_t)O, (uint64_t)ld_dz, BLOCK_K);
   if (rc) return rc;
-  rc = mc_make_tmap_2d_bf16(&tm_a, d_a, (uint64_t)rows, (uint64_t)C, (uint64_t)lda, BLOCK_K);
+  rc = mc_make_tmap_2d_bf16(&tm_a, d_a, (uint64_t)rows, (uint64_t)C, (uint64_t)lda, pl.share3 ? BBOX_ROWS : BLOCK_K);
   if (rc) return rc;
 
   WgradParams p;
@@ -269,6 +303,7 @@ extern "C" int mc_conv_wgrad(const void* d_a, int lda, int C, const void* d_dz, 
   p.tmem_cols = pl.tmem_cols;
   p.Wp = W + 1;
   p.ksize = ksize;
+  p.share3 = pl.share3;
   p.Opad = pl.Opad;
   p.Cpad = pl.Cpad;
   // c=f32, a=b=bf16, both operands MN-major (bits 15/16), N>>3 at [17,23), M>>4 at [24,29)
@@ -281,7 +316,7 @@ extern "C" int mc_conv_wgrad(const void* d_a, int lda, int C, const void* d_dz, 
     MC_CUDA(cudaFuncSetAttribute(conv_wgrad_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const int grid = pl.m_tiles * pl.n_tiles * pl.ntaps * pl.nsplit;
+  const int grid = pl.m_tiles * pl.n_tiles * (pl.share3 ? 3 : pl.ntaps) * pl.nsplit;
   conv_wgrad_tcgen05_kernel<<<grid, NUM_THREADS, pl.smem_bytes, stream>>>(tm_dz, tm_a, p);
   MC_LAUNCH_CHECK("conv_wgrad_tcgen05_kernel");
   long long tot = (long long)O * C;
