@@ -91,28 +91,26 @@ __global__ void maxpool2x2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfl
 
 // ---- weight packing ---------------------------------------------------------------------------------------
 // out[o', tap*Kc + c'] = bf16( w[oidx[o'], cidx[c'], tap] * mask[...] ), zero outside the surviving sets.
+// one thread = one (output row, input channel): the taps of a filter are contiguous in the source (36 B for 3x3), the
+// destination is written tap by tap with consecutive threads on consecutive channels.  Padding rows / columns are
+// zeroed by a memset before the launch.
 __global__ void pack_conv_weights_kernel(const float* __restrict__ w, const float* __restrict__ mask, int O, int C,
                                          int taps, const int* __restrict__ oidx, int n_o,
                                          const int* __restrict__ cidx, int n_c, __nv_bfloat16* __restrict__ out,
                                          int Npad, int Kc) {
-  const long long total = (long long)Npad * taps * Kc;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cp = (int)(i % Kc);
-    long long t = i / Kc;
-    const int tap = (int)(t % taps);
-    const int op = (int)(t / taps);
-    float v = 0.f;
-    if (op < n_o && cp < n_c) {
-      const int o = oidx ? oidx[op] : op;  // negative index = all-zero row / column
-      const int c = cidx ? cidx[cp] : cp;
-      if (o >= 0 && c >= 0) {
-        const long long src = ((long long)o * C + c) * taps + tap;
-        v = w[src];
-        if (mask) v *= mask[src];
-      }
+  const unsigned int total = (unsigned int)n_o * (unsigned int)n_c;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned int op = i / (unsigned int)n_c, cp = i - op * (unsigned int)n_c;
+    const int o = oidx ? oidx[op] : (int)op;  // negative index = all-zero row / column
+    const int c = cidx ? cidx[cp] : (int)cp;
+    if (o < 0 || c < 0) continue;
+    const size_t src = ((size_t)o * C + c) * taps;
+    __nv_bfloat16* dst = out + (size_t)op * taps * Kc + cp;
+    for (int t = 0; t < taps; ++t) {
+      float v = w[src + t];
+      if (mask) v *= mask[src + t];
+      dst[(size_t)t * Kc] = __float2bfloat16_rn(v);
     }
-    out[i] = __float2bfloat16_rn(v);
   }
 }
 
@@ -296,9 +294,11 @@ extern "C" int mc_pack_conv_weights(const float* d_w, const float* d_mask, int O
                "mc_pack_conv_weights: bad packed dims (n_o=%d Npad=%d n_c=%d Kc=%d)", n_o, Npad, n_c, Kc);
   MC_CHECK_ARG((d_oidx || n_o <= O) && (d_cidx || n_c <= C), "mc_pack_conv_weights: counts exceed tensor dims");
   const int taps = ksize * ksize;
-  const long long total = (long long)Npad * taps * Kc;
-  pack_conv_weights_kernel<<<grid_for(total, 256), 256, 0, stream>>>(d_w, d_mask, O, C, taps, d_oidx, n_o, d_cidx, n_c,
-                                                                     (__nv_bfloat16*)d_wpack, Npad, Kc);
+  MC_CHECK_ARG((long long)n_o * n_c < (1ll << 32), "mc_pack_conv_weights: tensor too large");
+  MC_CUDA(cudaMemsetAsync(d_wpack, 0, (size_t)Npad * taps * Kc * sizeof(__nv_bfloat16), stream));
+  pack_conv_weights_kernel<<<grid_for((long long)n_o * n_c, 256), 256, 0, stream>>>(d_w, d_mask, O, C, taps, d_oidx, n_o,
+                                                                                  d_cidx, n_c, (__nv_bfloat16*)d_wpack,
+                                                                                  Npad, Kc);
   MC_LAUNCH_CHECK("pack_conv_weights_kernel");
   return 0;
 }

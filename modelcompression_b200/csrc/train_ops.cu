@@ -291,22 +291,39 @@ __global__ void __launch_bounds__(TB) bn_bwd_reduce_vec_kernel(const __nv_bfloat
     m[j] = mean[c0 + j]; is[j] = invstd[c0 + j]; g0[j] = gamma[c0 + j]; b0[j] = beta[c0 + j];
     sa[j] = sb[j] = 0.f;
   }
-  for (; i < total; i += nthreads) {
-    const unsigned int row = i / (unsigned int)O8;
-    int b, y, x;
-    if (!row_coords(row, W + 1, H + 1, H, W, &b, &y, &x)) continue;
-    const uint4 qz = *reinterpret_cast<const uint4*>(z + (long long)row * ld_z + c0);
-    const uint4 qa = *da_vec(da, row, b, y, x, H, W, C, ld_da, ch_off, reorg, c0);
-    float fz[8], fa[8];
-    unpack8(qz, fz);
-    unpack8(qa, fa);
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  for (; i < total; i += 2 * nthreads) {  // two items per step: four independent 16-byte loads in flight
+    uint4 qz[2], qa[2];
+    bool in[2];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xh = (fz[j] - m[j]) * is[j];
-      float g = fa[j];
-      if (leaky && (g0[j] * xh + b0[j]) <= 0.f) g *= 0.1f;
-      sa[j] += g;
-      sb[j] += g * xh;
+    for (int u = 0; u < 2; ++u) {
+      const unsigned int it = i + u * nthreads;
+      in[u] = false;
+      qz[u] = qa[u] = zero4;
+      if (it < total) {
+        const unsigned int row = it / (unsigned int)O8;
+        int b, y, x;
+        in[u] = row_coords(row, W + 1, H + 1, H, W, &b, &y, &x);
+        if (in[u]) {
+          qz[u] = *reinterpret_cast<const uint4*>(z + (long long)row * ld_z + c0);
+          qa[u] = *da_vec(da, row, b, y, x, H, W, C, ld_da, ch_off, reorg, c0);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!in[u]) continue;
+      float fz[8], fa[8];
+      unpack8(qz[u], fz);
+      unpack8(qa[u], fa);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (fz[j] - m[j]) * is[j];
+        float g = fa[j];
+        if (leaky && (g0[j] * xh + b0[j]) <= 0.f) g *= 0.1f;
+        sa[j] += g;
+        sb[j] += g * xh;
+      }
     }
   }
 #pragma unroll
@@ -344,28 +361,50 @@ __global__ void __launch_bounds__(TB) bn_bwd_apply_vec_kernel(const __nv_bfloat1
     kb[j] = dbeta[c0 + j] * inv_count;
     kg[j] = dgamma[c0 + j] * inv_count;
   }
-  for (; i < total; i += nthreads) {
-    const unsigned int row = i / (unsigned int)O8;
-    int b, y, x;
-    float out[8];
-    if (row_coords(row, W + 1, H + 1, H, W, &b, &y, &x)) {
-      const uint4 qz = *reinterpret_cast<const uint4*>(z + (long long)row * ld_z + c0);
-      const uint4 qa = *da_vec(da, row, b, y, x, H, W, C, ld_da, ch_off, reorg, c0);
-      float fz[8], fa[8];
-      unpack8(qz, fz);
-      unpack8(qa, fa);
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  for (; i < total; i += 2 * nthreads) {  // two items per step: four independent 16-byte loads in flight
+    uint4 qz[2], qa[2];
+    bool in[2], ok[2];
+    unsigned int rows2[2];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = (fz[j] - m[j]) * is[j];
-        float g = fa[j];
-        if (leaky && (g0[j] * xh + b0[j]) <= 0.f) g *= 0.1f;
-        out[j] = k1[j] * (g - kb[j] - xh * kg[j]);
+    for (int u = 0; u < 2; ++u) {
+      const unsigned int it = i + u * nthreads;
+      ok[u] = it < total;
+      in[u] = false;
+      qz[u] = qa[u] = zero4;
+      rows2[u] = 0;
+      if (ok[u]) {
+        const unsigned int row = it / (unsigned int)O8;
+        rows2[u] = row;
+        int b, y, x;
+        in[u] = row_coords(row, W + 1, H + 1, H, W, &b, &y, &x);
+        if (in[u]) {
+          qz[u] = *reinterpret_cast<const uint4*>(z + (long long)row * ld_z + c0);
+          qa[u] = *da_vec(da, row, b, y, x, H, W, C, ld_da, ch_off, reorg, c0);
+        }
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) out[j] = 0.f;
     }
-    *reinterpret_cast<uint4*>(dz + (long long)row * ld_dz + c0) = pack8(out);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!ok[u]) continue;
+      float out[8];
+      if (in[u]) {
+        float fz[8], fa[8];
+        unpack8(qz[u], fz);
+        unpack8(qa[u], fa);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (fz[j] - m[j]) * is[j];
+          float g = fa[j];
+          if (leaky && (g0[j] * xh + b0[j]) <= 0.f) g *= 0.1f;
+          out[j] = k1[j] * (g - kb[j] - xh * kg[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) out[j] = 0.f;
+      }
+      *reinterpret_cast<uint4*>(dz + (long long)rows2[u] * ld_dz + c0) = pack8(out);
+    }
   }
 }
 
@@ -650,21 +689,20 @@ extern "C" int mc_maxpool2x2_backward(const void* d_a_full, int ld_a, const void
 // So dgrad reuses the forward tcgen05 kernel (mc_conv_fwd) on this packing: bf16 [Cpad, taps*Ko] K-major, row c,
 // column tap'*Ko + o  (Ko = round_up(O, 64)), masked like the forward weights (layers.py:59).
 namespace {
+// one thread = one (input channel c, output channel o), o fastest: the taps are read as one contiguous run, each write
+// is coalesced over o.  Padding is zeroed by a memset before the launch.
 __global__ void pack_dgrad_weights_kernel(const float* __restrict__ w, const float* __restrict__ mask, int O, int C,
                                           int taps, __nv_bfloat16* __restrict__ out, int Cpad, int Ko) {
-  const long long total = (long long)Cpad * taps * Ko;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int o = (int)(i % Ko);
-    long long t = i / Ko;
-    const int tapp = (int)(t % taps);
-    const int c = (int)(t / taps);
-    float v = 0.f;
-    if (o < O && c < C) {
-      const long long src = ((long long)o * C + c) * taps + (taps - 1 - tapp);
-      v = w[src];
-      if (mask) v *= mask[src];
+  const unsigned int total = (unsigned int)O * (unsigned int)C;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned int c = i / (unsigned int)O, o = i - c * (unsigned int)O;
+    const size_t src = ((size_t)o * C + c) * taps;
+    __nv_bfloat16* dst = out + (size_t)c * taps * Ko + o;
+    for (int t = 0; t < taps; ++t) {
+      float v = w[src + t];
+      if (mask) v *= mask[src + t];
+      dst[(size_t)(taps - 1 - t) * Ko] = __float2bfloat16_rn(v);
     }
-    out[i] = __float2bfloat16_rn(v);
   }
 }
 
@@ -763,9 +801,10 @@ extern "C" int mc_pack_conv_weights_dgrad(const float* d_w, const float* d_mask,
   MC_CHECK_ARG(d_w && d_wpack && O > 0 && C > 0 && (ksize == 1 || ksize == 3), "mc_pack_conv_weights_dgrad: bad argument");
   MC_CHECK_ARG(Cpad >= C && (Cpad % 16) == 0 && Ko >= O && (Ko % 32) == 0, "mc_pack_conv_weights_dgrad: bad packed dims");
   const int taps = ksize * ksize;
-  const long long total = (long long)Cpad * taps * Ko;
-  pack_dgrad_weights_kernel<<<grid_for(total, 256), 256, 0, stream>>>(d_w, d_mask, O, C, taps, (__nv_bfloat16*)d_wpack,
-                                                                      Cpad, Ko);
+  MC_CHECK_ARG((long long)O * C < (1ll << 32), "mc_pack_conv_weights_dgrad: tensor too large");
+  MC_CUDA(cudaMemsetAsync(d_wpack, 0, (size_t)Cpad * taps * Ko * sizeof(__nv_bfloat16), stream));
+  pack_dgrad_weights_kernel<<<grid_for((long long)O * C, 256), 256, 0, stream>>>(d_w, d_mask, O, C, taps,
+                                                                                (__nv_bfloat16*)d_wpack, Cpad, Ko);
   MC_LAUNCH_CHECK("pack_dgrad_weights_kernel");
   return 0;
 }
