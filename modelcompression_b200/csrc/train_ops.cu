@@ -253,13 +253,30 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
   return q;
 }
+// Division by a run-time constant without the ~30-instruction integer divide (these kernels issue three per 16 bytes
+// and were instruction-bound): q = umulhi(n, mul) >> shr, exact for n < 2^31 and d >= 2 (mul = ceil(2^(31+ceil_log2 d) / d)).
+struct FastDiv {
+  unsigned int d, mul, shr;
+};
+inline FastDiv make_fastdiv(unsigned int d) {
+  FastDiv f;
+  f.d = d;
+  unsigned int l = 0;
+  while ((1u << l) < d) ++l;
+  const unsigned long long p = 31ull + l;
+  f.mul = (unsigned int)((((unsigned long long)1 << p) + d - 1) / d);
+  f.shr = (unsigned int)(p - 32);
+  return f;
+}
+__device__ __forceinline__ unsigned int fdiv(unsigned int n, const FastDiv& f) { return __umulhi(n, f.mul) >> f.shr; }
+
 // row -> (b, y, x) with 32-bit arithmetic; returns interior flag
-__device__ __forceinline__ bool row_coords(unsigned int row, unsigned int Wp, unsigned int Hp, int H, int W, int* b,
+__device__ __forceinline__ bool row_coords(unsigned int row, const FastDiv& Wp, const FastDiv& Hp, int H, int W, int* b,
                                            int* y, int* x) {
-  const unsigned int t = row / Wp;
-  const unsigned int xx = row - t * Wp;
-  const unsigned int bb = t / Hp;
-  const unsigned int yy = t - bb * Hp;
+  const unsigned int t = fdiv(row, Wp);
+  const unsigned int xx = row - t * Wp.d;
+  const unsigned int bb = fdiv(t, Hp);
+  const unsigned int yy = t - bb * Hp.d;
   *b = (int)bb;
   *y = (int)yy;
   *x = (int)xx;
@@ -278,13 +295,14 @@ __global__ void __launch_bounds__(TB) bn_bwd_reduce_vec_kernel(const __nv_bfloat
                                                                int reorg, int B, int H, int W, int C, int O8,
                                                                const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                               int leaky, float* __restrict__ dbeta, float* __restrict__ dgamma) {
+                                                               int leaky, float* __restrict__ dbeta, float* __restrict__ dgamma,
+                                                               int o8_shift, FastDiv fWp, FastDiv fHp) {
   __shared__ float s_a[TB][9], s_b[TB][9];  // padded rows: conflict-free column sums
   const unsigned int rows = (unsigned int)B * (H + 1) * (W + 1);
   const unsigned int total = rows * (unsigned int)O8;  // host guarantees < 2^32
   const unsigned int nthreads = gridDim.x * TB;        // multiple of O8
   unsigned int i = blockIdx.x * TB + threadIdx.x;
-  const int oc = (int)(i % (unsigned int)O8), c0 = oc * 8;
+  const int oc = (int)(i & (unsigned int)(O8 - 1)), c0 = oc * 8;  // O8 is a power of two on this path
   float m[8], is[8], g0[8], b0[8], sa[8], sb[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -301,9 +319,9 @@ __global__ void __launch_bounds__(TB) bn_bwd_reduce_vec_kernel(const __nv_bfloat
       in[u] = false;
       qz[u] = qa[u] = zero4;
       if (it < total) {
-        const unsigned int row = it / (unsigned int)O8;
+        const unsigned int row = it >> o8_shift;
         int b, y, x;
-        in[u] = row_coords(row, W + 1, H + 1, H, W, &b, &y, &x);
+        in[u] = row_coords(row, fWp, fHp, H, W, &b, &y, &x);
         if (in[u]) {
           qz[u] = *reinterpret_cast<const uint4*>(z + (long long)row * ld_z + c0);
           qa[u] = *da_vec(da, row, b, y, x, H, W, C, ld_da, ch_off, reorg, c0);
@@ -347,12 +365,13 @@ __global__ void __launch_bounds__(TB) bn_bwd_apply_vec_kernel(const __nv_bfloat1
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               int leaky, const float* __restrict__ dbeta,
                                                               const float* __restrict__ dgamma, float inv_count,
-                                                              __nv_bfloat16* __restrict__ dz, int ld_dz) {
+                                                              __nv_bfloat16* __restrict__ dz, int ld_dz, int o8_shift,
+                                                              FastDiv fWp, FastDiv fHp) {
   const unsigned int rows = (unsigned int)B * (H + 1) * (W + 1);
   const unsigned int total = rows * (unsigned int)O8;
   const unsigned int nthreads = gridDim.x * TB;
   unsigned int i = blockIdx.x * TB + threadIdx.x;
-  const int oc = (int)(i % (unsigned int)O8), c0 = oc * 8;
+  const int oc = (int)(i & (unsigned int)(O8 - 1)), c0 = oc * 8;  // O8 is a power of two on this path
   float m[8], is[8], g0[8], b0[8], k1[8], kb[8], kg[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -374,10 +393,10 @@ __global__ void __launch_bounds__(TB) bn_bwd_apply_vec_kernel(const __nv_bfloat1
       qz[u] = qa[u] = zero4;
       rows2[u] = 0;
       if (ok[u]) {
-        const unsigned int row = it / (unsigned int)O8;
+        const unsigned int row = it >> o8_shift;
         rows2[u] = row;
         int b, y, x;
-        in[u] = row_coords(row, W + 1, H + 1, H, W, &b, &y, &x);
+        in[u] = row_coords(row, fWp, fHp, H, W, &b, &y, &x);
         if (in[u]) {
           qz[u] = *reinterpret_cast<const uint4*>(z + (long long)row * ld_z + c0);
           qa[u] = *da_vec(da, row, b, y, x, H, W, C, ld_da, ch_off, reorg, c0);
@@ -456,12 +475,12 @@ __global__ void __launch_bounds__(TB) maxpool_bwd_vec_kernel(const __nv_bfloat16
 
 __global__ void __launch_bounds__(TB) col_stats_vec_kernel(const __nv_bfloat16* __restrict__ z, unsigned int rows, int O8,
                                                            int ld, int ch_off, float* __restrict__ sum,
-                                                           float* __restrict__ sumsq) {
+                                                           float* __restrict__ sumsq, int o8_shift) {
   __shared__ float s_a[TB][9], s_b[TB][9];
   const unsigned int total = rows * (unsigned int)O8;
   const unsigned int nthreads = gridDim.x * TB;  // multiple of O8
   unsigned int i = blockIdx.x * TB + threadIdx.x;
-  const int c0 = (int)(i % (unsigned int)O8) * 8;
+  const int c0 = (int)(i & (unsigned int)(O8 - 1)) * 8;  // O8 is a power of two on this path
   float a[8], b[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
@@ -470,7 +489,7 @@ __global__ void __launch_bounds__(TB) col_stats_vec_kernel(const __nv_bfloat16* 
     uint4 q[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-      q[u] = *reinterpret_cast<const uint4*>(z + (long long)((i + u * nthreads) / (unsigned int)O8) * ld + ch_off + c0);
+      q[u] = *reinterpret_cast<const uint4*>(z + (long long)((i + u * nthreads) >> o8_shift) * ld + ch_off + c0);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       float f[8];
@@ -481,7 +500,7 @@ __global__ void __launch_bounds__(TB) col_stats_vec_kernel(const __nv_bfloat16* 
   }
   for (; i < total; i += nthreads) {
     float f[8];
-    unpack8(*reinterpret_cast<const uint4*>(z + (long long)(i / (unsigned int)O8) * ld + ch_off + c0), f);
+    unpack8(*reinterpret_cast<const uint4*>(z + (long long)(i >> o8_shift) * ld + ch_off + c0), f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { a[j] += f[j]; b[j] = fmaf(f[j], f[j], b[j]); }
   }
@@ -500,19 +519,20 @@ __global__ void __launch_bounds__(TB) col_stats_vec_kernel(const __nv_bfloat16* 
 __global__ void __launch_bounds__(TB) bn_apply_vec_kernel(const __nv_bfloat16* __restrict__ z, int ld_z, int B, int H, int W,
                                                           int C, int O8, const float* __restrict__ scale,
                                                           const float* __restrict__ shift, int leaky,
-                                                          __nv_bfloat16* __restrict__ out, int ld_out, int ch_off, int reorg) {
+                                                          __nv_bfloat16* __restrict__ out, int ld_out, int ch_off, int reorg,
+                                                          int o8_shift, FastDiv fWp, FastDiv fHp) {
   const unsigned int rows = (unsigned int)B * (H + 1) * (W + 1);
   const unsigned int total = rows * (unsigned int)O8;
   const unsigned int nthreads = gridDim.x * TB;
   unsigned int i = blockIdx.x * TB + threadIdx.x;
-  const int c0 = (int)(i % (unsigned int)O8) * 8;
+  const int c0 = (int)(i & (unsigned int)(O8 - 1)) * 8;  // O8 is a power of two on this path
   float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; }
   for (; i < total; i += nthreads) {
-    const unsigned int row = i / (unsigned int)O8;
+    const unsigned int row = i >> o8_shift;
     int b, y, x;
-    const bool in = row_coords(row, W + 1, H + 1, H, W, &b, &y, &x);
+    const bool in = row_coords(row, fWp, fHp, H, W, &b, &y, &x);
     float o[8];
     if (in) {
       float f[8];
@@ -537,8 +557,14 @@ __global__ void __launch_bounds__(TB) bn_apply_vec_kernel(const __nv_bfloat16* _
 }
 
 // thread count that is a multiple of O8 (O8 must divide TB * k): returns blocks, or 0 if the vector path does not apply
+inline int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
 inline int vec_blocks(long long total, int O8) {
-  if (O8 <= 0 || (TB % O8) != 0 || total >= (1ll << 32)) return 0;
+  if (O8 <= 0 || (TB % O8) != 0 || (O8 & (O8 - 1)) != 0 || total >= (1ll << 31)) return 0;
   long long blocks = (total + TB - 1) / TB;
   const long long cap = (long long)mc_num_sms() * 8;
   if (blocks > cap) blocks = cap;
@@ -567,7 +593,7 @@ extern "C" int mc_col_stats(const void* d_z, int64_t rows, int C, int ld, int ch
     const int vb = vec_blocks(rows * (C / 8), C / 8);
     if (vb > 0) {
       col_stats_vec_kernel<<<vb, TB, 0, stream>>>((const __nv_bfloat16*)d_z, (unsigned int)rows, C / 8, ld, ch_off, d_sum,
-                                                  d_sumsq);
+                                                  d_sumsq, ilog2(C / 8));
       MC_LAUNCH_CHECK("col_stats_vec_kernel");
       return 0;
     }
@@ -607,7 +633,8 @@ extern "C" int mc_bn_apply(const void* d_z, int ld_z, int B, int H, int W, int C
     const int vb = vec_blocks(total, C / 8);
     if (vb > 0) {
       bn_apply_vec_kernel<<<vb, TB, 0, stream>>>((const __nv_bfloat16*)d_z, ld_z, B, H, W, C, C / 8, d_scale, d_shift, leaky,
-                                                 (__nv_bfloat16*)d_out, ld_out, ch_off, reorg);
+                                                 (__nv_bfloat16*)d_out, ld_out, ch_off, reorg, ilog2(C / 8),
+                                                 make_fastdiv(W + 1), make_fastdiv(H + 1));
       MC_LAUNCH_CHECK("bn_apply_vec_kernel");
       return 0;
     }
@@ -637,11 +664,13 @@ extern "C" int mc_bn_backward(const void* d_z, int ld_z, const void* d_da, int l
   if (vb > 0) {
     bn_bwd_reduce_vec_kernel<<<vb, TB, 0, stream>>>((const __nv_bfloat16*)d_z, ld_z, (const __nv_bfloat16*)d_da, ld_da,
                                                     ch_off, reorg, B, H, W, C, C / 8, d_mean, d_invstd, d_gamma, d_beta,
-                                                    leaky, d_dbeta, d_dgamma);
+                                                    leaky, d_dbeta, d_dgamma, ilog2(C / 8), make_fastdiv(W + 1),
+                                                    make_fastdiv(H + 1));
     MC_LAUNCH_CHECK("bn_bwd_reduce_vec_kernel");
     bn_bwd_apply_vec_kernel<<<vb, TB, 0, stream>>>((const __nv_bfloat16*)d_z, ld_z, (const __nv_bfloat16*)d_da, ld_da,
                                                    ch_off, reorg, B, H, W, C, C / 8, d_mean, d_invstd, d_gamma, d_beta,
-                                                   leaky, d_dbeta, d_dgamma, inv_count, (__nv_bfloat16*)d_dz, ld_dz);
+                                                   leaky, d_dbeta, d_dgamma, inv_count, (__nv_bfloat16*)d_dz, ld_dz,
+                                                   ilog2(C / 8), make_fastdiv(W + 1), make_fastdiv(H + 1));
     MC_LAUNCH_CHECK("bn_bwd_apply_vec_kernel");
     return 0;
   }
