@@ -105,6 +105,49 @@ def test_weight_prune_midsize_interpolated(sizes):
             assert np.array_equal(a.cpu().numpy(), b), "perc %s" % perc
 
 
+def test_weight_prune_unaligned_and_degenerate_inputs():
+    """Ragged edge cases of the one-pass pruner: parameters whose storage is only 4-byte aligned (every chunk takes the
+    scalar path), a tensor of all-equal values (every element is a candidate: the candidate slices overflow and the
+    exact path takes over), NaN / Inf weights (np.percentile semantics), and 1- and 2-element tensors."""
+    gen = torch.Generator().manual_seed(8)
+    base = torch.randn(400003, generator=gen)
+    views = [base[1:150002].view(-1, 1), base[150003:150004].view(1, 1), base[150005:400003].view(-1, 2)]
+    bag = _ParamBag([v.clone() for v in views]).to(DEV)
+    # re-point the parameters at 4-byte-aligned views of one device buffer
+    dbase = base.to(DEV)
+    dviews = [dbase[1:150002].view(-1, 1), dbase[150003:150004].view(1, 1), dbase[150005:400003].view(-1, 2)]
+    for p, v in zip(bag.parameters(), dviews):
+        p.data = v
+        assert p.data_ptr() % 16 != 0 or p.numel() == 1
+    ws = [v.numpy() for v in views]
+    for perc in (5.0, 50.0, 93.7):
+        _, masks_o = prune_oracle.weight_prune_np(ws, perc)
+        for a, b in zip(mc.weight_prune(bag, perc), masks_o):
+            assert np.array_equal(a.cpu().numpy(), b), "perc %s" % perc
+    const = _ParamBag([torch.full((300000, 2), 0.25), torch.full((7, 3), -0.25)]).to(DEV)
+    for perc in (10.0, 99.0):
+        _, masks_o = prune_oracle.weight_prune_np([p.detach().cpu().numpy() for p in const.parameters()], perc)
+        for a, b in zip(mc.weight_prune(const, perc), masks_o):
+            assert np.array_equal(a.cpu().numpy(), b)
+    bad = torch.randn(200000, 2, generator=gen)
+    bad[17, 1] = float('inf')
+    bagi = _ParamBag([bad.clone()]).to(DEV)
+    _, masks_o = prune_oracle.weight_prune_np([bad.numpy()], 60.0)
+    assert np.array_equal(mc.weight_prune(bagi, 60.0)[0].cpu().numpy(), masks_o[0])
+    bad[5, 0] = float('nan')
+    bagn = _ParamBag([bad.clone()]).to(DEV)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _, masks_o = prune_oracle.weight_prune_np([bad.numpy()], 60.0)
+    assert np.array_equal(mc.weight_prune(bagn, 60.0)[0].cpu().numpy(), masks_o[0])  # threshold NaN: nothing survives
+    tiny = _ParamBag([torch.tensor([[3.0]]), torch.tensor([[1.0, -2.0]])]).to(DEV)
+    for perc in (0.0, 50.0, 100.0):
+        _, masks_o = prune_oracle.weight_prune_np([p.detach().cpu().numpy() for p in tiny.parameters()], perc)
+        for a, b in zip(mc.weight_prune(tiny, perc), masks_o):
+            assert np.array_equal(a.cpu().numpy(), b)
+
+
 def test_weight_prune_exact_radix_fallback(darknet, monkeypatch):
     # the sample-pivot fast path falls back to the full radix select on the device when its bracket misses; force
     # that path on the full model and check it gives the same (bit-exact) masks
