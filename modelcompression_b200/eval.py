@@ -96,19 +96,28 @@ def evaluate_sharded(model, get_batch, n_images, batch_size, conf_thresh=0.005, 
     (compact_detections_validation); feed them to voc_eval.mean_ap."""
     lo, hi = shard_range(n_images, rank, world_size)
     model.eval()
-    chunks = []
+    want_cls = bool(validation) and not only_objectness
+    raw = []  # per batch (boxes, keep, keep_counts, cls): everything stays queued on the stream, no host sync per batch
     for b0 in range(lo, hi, batch_size):
         b1 = min(b0 + batch_size, hi)
         x = get_batch(b0, b1)
         head = model(x)
-        want_cls = bool(validation) and not only_objectness
         boxes, counts, cls = decode_device(head, conf_thresh, model.num_classes, model.anchors, model.num_anchors,
                                            only_objectness, want_cls)
         keep, keep_counts = nms_device(boxes, counts, nms_thresh)
-        if want_cls:
-            chunks.append(compact_detections_validation(boxes, keep, keep_counts, cls, conf_thresh, b0))
-        else:
-            chunks.append(compact_detections(boxes, keep, keep_counts, b0))
+        raw.append((boxes, keep, keep_counts, cls))
     dev = next(model.parameters()).device
-    local = torch.cat(chunks, dim=0) if chunks else torch.zeros(0, DET_COLS, dtype=torch.float32, device=dev)
+    if raw:
+        # one compaction for the whole shard (torch.nonzero synchronises: once, not once per batch); images of the shard
+        # are consecutive, so the row index of the concatenation + lo is the global image index
+        boxes = torch.cat([r[0] for r in raw], dim=0)
+        keep = torch.cat([r[1] for r in raw], dim=0)
+        keep_counts = torch.cat([r[2] for r in raw], dim=0)
+        if want_cls:
+            local = compact_detections_validation(boxes, keep, keep_counts, torch.cat([r[3] for r in raw], dim=0),
+                                                  conf_thresh, lo)
+        else:
+            local = compact_detections(boxes, keep, keep_counts, lo)
+    else:
+        local = torch.zeros(0, DET_COLS, dtype=torch.float32, device=dev)
     return gather_detections(local, group) if gather else local
