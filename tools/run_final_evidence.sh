@@ -1,0 +1,7 @@
+set -x
+python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain_bench_short.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_bench_final.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench_short.log 2>&1
+python tools/profile_forward.py 64 > gpurun_out/plain_fwd.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:conv_gemm_tcgen05 -s 18 -c 18 -f -o gpurun_out/prof_conv_r1 python tools/profile_forward.py 64 > gpurun_out/ncu_fwd.log 2>&1
+tail -2 gpurun_out/ncu_fwd.log
