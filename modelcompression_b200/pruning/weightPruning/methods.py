@@ -69,9 +69,10 @@ def _empty_like_all(params):
 
 class _ParamIndex(object):
     """model.parameters() without walking the module tree on every call (the nn.Module generator walk costs ~200 us on
-    the 75-module Darknet, twice the pruning kernel).  The tree is walked once; afterwards the per-module
-    ``_parameters`` / ``_modules`` dicts are re-read at C speed and compared by identity with what the walk saw, so a
-    replaced Parameter, a replaced/added/removed sub-module or a new parameter all invalidate the index."""
+    the 75-module Darknet, twice the pruning kernel).  The tree is walked once.  Afterwards a call (1) checks at C speed
+    that the tree is the one that was walked — every module's ``_modules`` values by identity, every module's number
+    of parameters — and (2) re-reads the parameter objects from their ``_parameters`` dicts, so a replaced Parameter is
+    picked up, and a replaced / added / removed sub-module or a new parameter invalidates the index."""
 
     def __init__(self, model):
         mods, seen = [], set()
@@ -87,56 +88,53 @@ class _ParamIndex(object):
         walk(model)
         self.pdicts = [m._parameters for m in mods]
         self.mdicts = [m._modules for m in mods]
-        flat = self._flat(self.pdicts)
-        self.ids = tuple(map(id, flat)) + tuple(map(id, self._flat(self.mdicts)))
-        uniq, seen_p = [], set()
-        for i, p in enumerate(flat):  # parameters() order: first occurrence of every non-None parameter
-            if p is not None and id(p) not in seen_p:
-                seen_p.add(id(p))
-                uniq.append(i)
-        self.uniq = uniq
+        self.mids = tuple(map(id, _chain.from_iterable(map(dict.values, self.mdicts))))
+        self.plens = list(map(len, self.pdicts))
+        slots, seen_p = [], set()
+        for d in self.pdicts:  # parameters() order: first occurrence of every non-None parameter
+            for name, p in d.items():
+                if p is not None and id(p) not in seen_p:
+                    seen_p.add(id(p))
+                    slots.append((d, name))
+        self.slots = slots
+        self.shared = len(seen_p) != sum(1 for d in self.pdicts for p in d.values() if p is not None)
         self.plans = {}  # conv_only -> _PrunePlan
 
-    @staticmethod
-    def _flat(dicts):
-        return list(_chain.from_iterable(map(dict.values, dicts)))
-
-    def flat_parameters(self):
-        """Current values of every module's _parameters dict (with None / duplicates), or None when the module
-        tree changed since the walk."""
-        flat = self._flat(self.pdicts)
-        if tuple(map(id, _chain(flat, _chain.from_iterable(map(dict.values, self.mdicts))))) != self.ids:
-            return None
-        return flat
+    def valid(self):
+        return tuple(map(id, _chain.from_iterable(map(dict.values, self.mdicts)))) == self.mids and \
+            list(map(len, self.pdicts)) == self.plens
 
     def parameters(self):
-        flat = self.flat_parameters()
-        return None if flat is None else [flat[i] for i in self.uniq]
+        """Current parameter objects in parameters() order (None slots / re-shared parameters force a re-walk)."""
+        out = [d[name] for d, name in self.slots]
+        if any(p is None for p in out) or (len(set(map(id, out))) != len(out)):
+            return None
+        return out
 
 
 def _index(model):
-    """(index, flat parameter slots) for the model, rebuilding the index when the module tree changed."""
+    """(index, current parameter list) for the model, rebuilding the index when the module tree changed."""
     idx = model.__dict__.get('_b200_param_index')
-    flat = idx.flat_parameters() if idx is not None else None
-    if flat is None:
+    params = idx.parameters() if (idx is not None and idx.valid() and not idx.shared) else None
+    if params is None:
         idx = model.__dict__['_b200_param_index'] = _ParamIndex(model)
-        flat = idx.flat_parameters()
-    return idx, flat
+        params = idx.parameters()
+        if params is None:  # cannot happen right after a walk
+            raise RuntimeError("internal: parameter index inconsistent")
+    return idx, params
 
 
 def _all_parameters(model):
-    idx, flat = _index(model)
-    return [flat[i] for i in idx.uniq]
+    return _index(model)[1]
 
 
 class _PrunePlan(object):
     """Everything about the prunable tensors that only depends on their shapes: which parameter slots, the ctypes size
     tables for the C-ABI, the layout of the flat mask buffer."""
 
-    def __init__(self, idx, flat, conv_only):
+    def __init__(self, params, conv_only):
         self.slots, self.shapes = [], []
-        for i in idx.uniq:
-            p = flat[i]
+        for i, p in enumerate(params):
             nd = p.dim()
             if (nd == 4) if conv_only else (nd != 1):
                 self.slots.append(i)
@@ -149,25 +147,31 @@ class _PrunePlan(object):
             self.offs.append(off)
             off += (ne + 3) // 4 * 4
         self.flat_len = off
+        self.padded = [(ne + 3) // 4 * 4 for ne in self.numels]
         if conv_only:
             self.O = [sh[0] for sh in self.shapes]
             self.tables = tuple(_lib.int_array([sh[d] for sh in self.shapes]) for d in range(4))
-        self.ok_ptrs = None  # data pointers of the last call that passed the device/dtype/contiguity checks
+        self.ok_ptrs = None   # data pointers of the last call that passed the device/dtype/contiguity checks
+        self.ptr_array = None  # ... and their ctypes array
+        self.ws_bytes = None
 
 
 def _plan_and_tensors(model, conv_only):
-    """(plan, tensors): the prunable parameter data tensors in parameters() order, validated (CUDA, float32,
-    contiguous).  The per-tensor checks are skipped when the storage pointers are the ones already checked."""
-    idx, flat = _index(model)
+    """(plan, tensors, ctypes pointer array): the prunable parameter tensors in parameters() order, validated (CUDA,
+    float32, contiguous).  The per-tensor checks are skipped when the storage pointers are the ones already checked."""
+    idx, params = _index(model)
     plan = idx.plans.get(conv_only)
     if plan is not None:
-        for i, sh in zip(plan.slots, plan.shapes):
-            if flat[i].shape != sh:  # .data was re-assigned with another shape
-                plan = None
-                break
+        if len(plan.slots) and plan.slots[-1] >= len(params):
+            plan = None
+        else:
+            for i, sh in zip(plan.slots, plan.shapes):
+                if params[i].shape != sh:  # replaced parameter / .data re-assigned with another shape
+                    plan = None
+                    break
     if plan is None:
-        plan = idx.plans[conv_only] = _PrunePlan(idx, flat, conv_only)
-    tensors = [flat[i] for i in plan.slots]
+        plan = idx.plans[conv_only] = _PrunePlan(params, conv_only)
+    tensors = [params[i] for i in plan.slots]
     ptrs = [t.data_ptr() for t in tensors]
     if ptrs != plan.ok_ptrs:
         checked = []
@@ -182,12 +186,41 @@ def _plan_and_tensors(model, conv_only):
                 t = t.data.contiguous()
             checked.append(t)
         tensors = checked
-        plan.ok_ptrs = ptrs if all_contig else None
-    return plan, tensors
+        arr = _lib.ptr_array(tensors)
+        if all_contig:
+            plan.ok_ptrs, plan.ptr_array = ptrs, arr
+        else:
+            plan.ok_ptrs = plan.ptr_array = None
+        return plan, tensors, arr
+    return plan, tensors, plan.ptr_array
 
 
 def _prunable(model, conv_only):
     return [t.data for t in _plan_and_tensors(model, conv_only)[1]]
+
+
+def _mask_views(flat, plan):
+    """Per-parameter views of the flat mask buffer: one split + one view per tensor (created while the kernel runs)."""
+    chunks = flat[:plan.flat_len].split(plan.padded)
+    return [(c if c.numel() == ne else c[:ne]).view(sh) for c, ne, sh in zip(chunks, plan.numels, plan.shapes)]
+
+
+def _on_device(dev):
+    """Context that makes ``dev`` current; free when it already is (torch.cuda.device costs ~8 us per call)."""
+    if torch.cuda.current_device() == (dev.index if dev.index is not None else torch.cuda.current_device()):
+        return _NULLCTX
+    return torch.cuda.device(dev)
+
+
+class _NullCtx(object):
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NULLCTX = _NullCtx()
 
 
 def weight_threshold(params, pruning_perc):
@@ -232,7 +265,7 @@ def weight_prune(model, pruning_perc):
     One cooperative kernel launch (mc_weight_prune_masks): W is read once and the masks are written once.
     '''
     lib = _lib.load()
-    plan, params = _plan_and_tensors(model, conv_only=False)
+    plan, params, parr = _plan_and_tensors(model, conv_only=False)
     if not params:
         return []
     if len(params) > _lib.MC_MAX_SEGMENTS:  # more tensors than one launch takes: threshold first, then mask in groups
@@ -240,20 +273,19 @@ def weight_prune(model, pruning_perc):
     n = plan.n
     k, gamma = _rank_cached(n, pruning_perc, np.float32)
     dev = params[0].device
-    ws_bytes = lib.mc_workspace_bytes_kth_abs_select(n)
+    if plan.ws_bytes is None:
+        plan.ws_bytes = lib.mc_workspace_bytes_kth_abs_select(n)
+    ws_bytes = plan.ws_bytes
     # one allocation: the masks (flat, every mask 16-byte aligned) followed by the 3 result floats
     flat = torch.empty(plan.flat_len + 4, dtype=torch.float32, device=dev)
     base = flat.data_ptr()
     mask_ptrs = (_lib.c_void_p * len(params))(*[base + 4 * o for o in plan.offs])
     ws = _workspace(dev, ws_bytes)
-    with torch.cuda.device(dev):
-        _lib.check(lib.mc_weight_prune_masks(_lib.ptr_array(params), mask_ptrs, plan.sizes64, len(params), k, gamma,
+    with _on_device(dev):
+        _lib.check(lib.mc_weight_prune_masks(parr, mask_ptrs, plan.sizes64, len(params), k, gamma,
                                              base + 4 * plan.flat_len, ws.data_ptr(), ws_bytes, _lib.stream_ptr()),
                    "mc_weight_prune_masks")
-    # the per-parameter views are created while the kernel runs
-    return [v.view(sh) for v, sh in zip(torch.split(flat[:plan.flat_len], [(ne + 3) // 4 * 4 for ne in plan.numels]),
-                                        plan.shapes)] if all(ne % 4 == 0 for ne in plan.numels) else \
-        [flat[o:o + ne].view(sh) for o, ne, sh in zip(plan.offs, plan.numels, plan.shapes)]
+    return _mask_views(flat, plan)
 
 
 def _weight_prune_grouped(lib, params, pruning_perc):
@@ -297,7 +329,7 @@ def quick_filter_prune(model, pruning_perc, return_keep=False):
     With return_keep=True also returns the per-layer surviving-filter index tensors (int64, ascending).
     '''
     lib = _lib.load()
-    plan, params = _plan_and_tensors(model, conv_only=True)
+    plan, params, parr = _plan_and_tensors(model, conv_only=True)
     if not params:
         return ([], []) if return_keep else []
     if len(params) > _lib.MC_MAX_SEGMENTS:
@@ -312,12 +344,12 @@ def quick_filter_prune(model, pruning_perc, return_keep=False):
     mbase = flat.data_ptr()
     vbase = mbase + 4 * plan.flat_len
     mask_ptrs = (_lib.c_void_p * len(params))(*[mbase + 4 * o for o in plan.offs])
-    with torch.cuda.device(dev):
-        _lib.check(lib.mc_filter_prune(_lib.ptr_array(params), plan.tables[0], plan.tables[1], plan.tables[2],
+    with _on_device(dev):
+        _lib.check(lib.mc_filter_prune(parr, plan.tables[0], plan.tables[1], plan.tables[2],
                                        plan.tables[3], len(params), k, gamma, vbase, vbase + 4 * n4, mask_ptrs,
                                        vbase + 4 * n4 + 8 + 256, vbase + 4 * n4 + 8, 256, _lib.stream_ptr()),
                    "mc_filter_prune")
-    masks = [flat[o:o + ne].view(sh) for o, ne, sh in zip(plan.offs, plan.numels, plan.shapes)]  # while the kernels run
+    masks = _mask_views(flat, plan)
     if not return_keep:
         return masks
     keep = flat[plan.flat_len + n4 + 2 + 64:].view(torch.uint8)[:n]
