@@ -121,15 +121,28 @@ __device__ __forceinline__ void epilogue_loop(const ConvKParams& p, uint32_t tme
   const bool vec_ok = ((p.ldc | p.ch_off) & 7) == 0 && (MODE != MC_EPI_REORG2 || (p.N & 7) == 0);
   int as = 0;
   uint32_t aphase = 0;
+  // one N tile: every tile of the launch uses the same scale/shift slice, staged once (a narrow layer's epilogue is
+  // otherwise a chain of global-load latency + barrier per 128 rows)
+  const bool one_n_tile = p.n_tiles == 1;
+  if (one_n_tile) {
+    for (int i = et; i < p.block_n; i += 128) {
+      const bool ok = i < p.Npad;
+      s_ss[i] = ok ? __ldg(p.scale + i) : 0.f;
+      s_ss[256 + i] = ok ? __ldg(p.shift + i) : 0.f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+  }
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
     const int n0 = (tile % p.n_tiles) * p.block_n;
     const int m0 = (tile / p.n_tiles) * BLOCK_M;
-    float* sc = s_ss + as * 512;
+    float* sc = s_ss + (one_n_tile ? 0 : as * 512);
     float* sh = sc + 256;
-    for (int i = et; i < p.block_n; i += 128) {
-      const bool ok = (n0 + i) < p.Npad;
-      sc[i] = ok ? __ldg(p.scale + n0 + i) : 0.f;
-      sh[i] = ok ? __ldg(p.shift + n0 + i) : 0.f;
+    if (!one_n_tile) {
+      for (int i = et; i < p.block_n; i += 128) {
+        const bool ok = (n0 + i) < p.Npad;
+        sc[i] = ok ? __ldg(p.scale + n0 + i) : 0.f;
+        sh[i] = ok ? __ldg(p.shift + n0 + i) : 0.f;
+      }
     }
     const int row = m0 + quarter * 32 + lane;
     const int x = row % p.Wp;
@@ -152,7 +165,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvKParams& p, uint32_t tme
       out_row_base = ((long long)b * p.N * p.H + y) * p.W + x;  // + n*H*W
       do_store = interior;
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // scale/shift of this tile visible to the 4 epilogue warps
+    if (!one_n_tile) asm volatile("bar.sync 1, 128;" ::: "memory");  // scale/shift of this tile visible to the 4 epilogue warps
 
     ptx::mbar_wait(&tmem_full_bar[as], aphase);
     ptx::tc_fence_after();
@@ -183,7 +196,12 @@ __device__ __forceinline__ void epilogue_loop(const ConvKParams& p, uint32_t tme
 
 // Persistent: grid = min(#tiles, #SMs); CTA c works on tiles c, c+grid, ...  The smem ring runs across tiles, and the
 // accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+//
+// MINB (resident CTAs per SM the register budget allows): 1 for the wide compute-bound tiles; 3 for narrow layers
+// (few output channels / short K), whose per-tile chain TMA -> MMA -> commit -> epilogue -> TMEM hand-back is latency
+// bound inside one CTA — several CTAs per SM (each with its own small smem ring and TMEM slice) overlap those chains.
+template <int MINB>
+__global__ void __launch_bounds__(NUM_THREADS, MINB)
 conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_abox, const ConvKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -436,30 +454,84 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   int block_n = d->block_n;
   // (the operand-feed term keeps the un-shared 16 KB A tile: with the shared-box figure the model picks narrower tiles
   //  that measured 4 % slower end to end on B200)
+  {  // experiment switch: MCB200_CONV_BN_BIG=<bn> forces the tile width of the wide 3x3 layers (Npad >= 960)
+    static int bn_big = -1;
+    if (bn_big < 0) {
+      const char* e = getenv("MCB200_CONV_BN_BIG");
+      bn_big = e ? atoi(e) : 0;
+    }
+    if (block_n <= 0 && bn_big >= 16 && bn_big <= 256 && (bn_big % 16) == 0 && d->Npad >= 960 && d->ksize == 3) block_n = bn_big;
+  }
   if (block_n <= 0) block_n = pick_block_n(d->Npad, m_tiles, (ntaps * Kc + 63) / 64, mc_num_sms(), false);  // 64-wide k-block units
   MC_CHECK_ARG(block_n >= 16 && block_n <= 256 && (block_n % 16) == 0, "mc_conv_fwd: block_n %d invalid", block_n);
   const int n_tiles = (d->Npad + block_n - 1) / block_n;
 
   const int stage_bytes = A_TILE_BYTES + block_n * BLOCK_K * 2;
+  const long long total_tiles = (long long)n_tiles * m_tiles;
+  const int acc_stride = ((block_n + 31) / 32) * 32;
+  int tmem_cols = 32;
+  while (tmem_cols < 2 * acc_stride) tmem_cols <<= 1;  // two accumulator stages
+  const int num_kb = ntaps * (Kc / BLOCK_K);
+  constexpr size_t AUX_BYTES = 256 + 4096 + 1024;  // barriers, scale/shift staging, 1024-byte alignment slack
+
+  // smem ring of one CTA when `ctas` CTAs share an SM (each CTA also costs 1 KB of reserved shared memory)
+  auto plan_ring = [&](int ctas, int* st, int* ast, size_t* bytes) -> bool {
+    const long long cap = (ctas == 1 ? 204 * 1024 : (227 * 1024) / ctas - 1024 - (long long)AUX_BYTES);
+    if (share_dx) {
+      const int b_bytes = block_n * 128;
+      int a = ctas == 1 ? MAX_A_STAGES : 2;
+      long long stg = (cap - (long long)a * A_BOX_STRIDE) / b_bytes;
+      if (stg > MAX_STAGES) stg = MAX_STAGES;
+      if (stg < 3) return false;
+      *st = (int)stg; *ast = a;
+      *bytes = (size_t)a * A_BOX_STRIDE + (size_t)stg * b_bytes + AUX_BYTES;
+    } else {
+      long long stg = cap / stage_bytes;
+      if (stg > MAX_STAGES) stg = MAX_STAGES;
+      if (stg > num_kb * 4) stg = num_kb * 4;  // a ring deeper than four tiles' worth of k-blocks buys nothing
+      if (stg < (ctas == 1 ? 1 : 3)) return false;
+      *st = (int)stg; *ast = 0;
+      *bytes = (size_t)stg * stage_bytes + AUX_BYTES;
+    }
+    return true;
+  };
+  // CTAs per SM.  Wide, long-K tiles are tensor-bound: one CTA with the deepest ring.  Narrow layers are bound by the
+  // per-tile latency chain, which only more CTAs (or tiles) in flight hide: up to 3 when the rings and the TMEM
+  // slices fit and every CTA still gets >= 2 tiles.  MCB200_CONV_CTAS=1|2|3 forces the upper limit.
+  static int ctas_env = -1;
+  if (ctas_env < 0) {
+    const char* e = getenv("MCB200_CONV_CTAS");
+    ctas_env = e ? atoi(e) : 0;
+    if (ctas_env < 0 || ctas_env > 3) ctas_env = 0;
+  }
+  int ctas = 1;
+  {
+    const int limit = ctas_env ? ctas_env : 3;
+    const double main_cycles = (double)num_kb * (BLOCK_K / 64.0) * (2.0 * block_n > 128.0 + block_n ? 2.0 * block_n : 128.0 + block_n);
+    const bool narrow = ctas_env ? true : main_cycles < 6000.0;
+    for (int c = limit; c >= 2 && narrow; --c) {
+      int st, ast;
+      size_t bytes;
+      if (c * tmem_cols > 512 || total_tiles < 2ll * c * mc_num_sms() || !plan_ring(c, &st, &ast, &bytes)) continue;
+      ctas = c;
+      break;
+    }
+  }
   int stages = d->stages;
   int a_stages = 0;
   size_t smem_bytes;
-  if (share_dx) {
-    a_stages = MAX_A_STAGES;
-    const int b_bytes = block_n * 128;
-    if (stages <= 0) {
-      stages = (204 * 1024 - a_stages * A_BOX_STRIDE) / b_bytes;
-      if (stages > MAX_STAGES) stages = MAX_STAGES;
-    }
-    MC_CHECK_ARG(stages >= 2 && stages <= MAX_STAGES, "mc_conv_fwd: stages %d invalid", stages);
-    smem_bytes = (size_t)a_stages * A_BOX_STRIDE + (size_t)stages * b_bytes + 256 + 4096 + 1024;
+  if (stages <= 0) {
+    MC_CHECK_ARG(plan_ring(ctas, &stages, &a_stages, &smem_bytes), "mc_conv_fwd: no shared-memory ring fits block_n %d", block_n);
   } else {
-    if (stages <= 0) {
-      stages = (204 * 1024) / stage_bytes;
-      if (stages > MAX_STAGES) stages = MAX_STAGES;
+    ctas = 1;
+    if (share_dx) {
+      a_stages = MAX_A_STAGES;
+      MC_CHECK_ARG(stages >= 2 && stages <= MAX_STAGES, "mc_conv_fwd: stages %d invalid", stages);
+      smem_bytes = (size_t)a_stages * A_BOX_STRIDE + (size_t)stages * block_n * 128 + AUX_BYTES;
+    } else {
+      MC_CHECK_ARG(stages >= 1 && stages <= MAX_STAGES, "mc_conv_fwd: stages %d invalid", stages);
+      smem_bytes = (size_t)stages * stage_bytes + AUX_BYTES;
     }
-    MC_CHECK_ARG(stages >= 1 && stages <= MAX_STAGES, "mc_conv_fwd: stages %d invalid", stages);
-    smem_bytes = (size_t)stages * stage_bytes + 256 + 4096 + 1024;
   }
   MC_CHECK_ARG(smem_bytes <= 227 * 1024, "mc_conv_fwd: smem %zu too large", smem_bytes);
 
@@ -492,10 +564,8 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   p.stages = stages;
   p.share_dx = share_dx;
   p.a_stages = a_stages;
-  p.acc_stride = ((block_n + 31) / 32) * 32;
-  int tc = 32;
-  while (tc < 2 * p.acc_stride) tc <<= 1;
-  p.tmem_cols = tc;  // two accumulator stages
+  p.acc_stride = acc_stride;
+  p.tmem_cols = tmem_cols;
   p.m_tiles = m_tiles;
   p.n_tiles = n_tiles;
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
@@ -509,12 +579,16 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    MC_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MC_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MC_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     attr_set = true;
   }
-  long long total_tiles = (long long)n_tiles * m_tiles;
-  int grid = (int)(total_tiles < mc_num_sms() ? total_tiles : mc_num_sms());
-  conv_gemm_tcgen05_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tm_a, tm_b, tm_abox, p);
+  const long long max_ctas = (long long)mc_num_sms() * ctas;
+  int grid = (int)(total_tiles < max_ctas ? total_tiles : max_ctas);
+  if (ctas >= 3)
+    conv_gemm_tcgen05_kernel<3><<<grid, NUM_THREADS, smem_bytes, stream>>>(tm_a, tm_b, tm_abox, p);
+  else
+    conv_gemm_tcgen05_kernel<1><<<grid, NUM_THREADS, smem_bytes, stream>>>(tm_a, tm_b, tm_abox, p);
   MC_LAUNCH_CHECK("conv_gemm_tcgen05_kernel");
   return 0;
 }
