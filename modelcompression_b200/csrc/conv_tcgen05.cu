@@ -110,14 +110,18 @@ __device__ __forceinline__ void store16(const ConvKParams& p, const float (&v)[1
 
 // Epilogue warps (threads 64..191): per tile, stage the tile's scale/shift in shared memory (double-buffered with
 // the accumulator stage, one named barrier per tile), then drain the accumulator 32 columns at a time.
-template <int MODE, bool LEAKY>
+// PAIR (CTA-pair kernel): `tile` counts (m-tile pair, n-tile) units of the cluster, this CTA owns m-tile 2*pair + rank,
+// and the accumulator stage is handed back on the LEADER CTA's barrier (the MMA issuer waits for both epilogues).
+template <int MODE, bool LEAKY, bool PAIR = false>
 __device__ __forceinline__ void epilogue_loop(const ConvKParams& p, uint32_t tmem_base, uint64_t* tmem_full_bar,
-                                              uint64_t* tmem_empty_bar, float* s_ss) {
+                                              uint64_t* tmem_empty_bar, float* s_ss, int tile0 = -1, int tile_step = 0,
+                                              int total_units = 0, int pair_rank = 0) {
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int et = threadIdx.x - 64;   // 0..127
   const int quarter = warp_idx & 3;  // TMEM lane quarter this warp may access
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int total_tiles = PAIR ? total_units : p.m_tiles * p.n_tiles;
+  if (!PAIR) { tile0 = blockIdx.x; tile_step = gridDim.x; }
   const bool vec_ok = ((p.ldc | p.ch_off) & 7) == 0 && (MODE != MC_EPI_REORG2 || (p.N & 7) == 0);
   int as = 0;
   uint32_t aphase = 0;
@@ -132,9 +136,9 @@ __device__ __forceinline__ void epilogue_loop(const ConvKParams& p, uint32_t tme
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
   }
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+  for (int tile = tile0; tile < total_tiles; tile += tile_step) {
     const int n0 = (tile % p.n_tiles) * p.block_n;
-    const int m0 = (tile / p.n_tiles) * BLOCK_M;
+    const int m0 = (PAIR ? 2 * (tile / p.n_tiles) + pair_rank : tile / p.n_tiles) * BLOCK_M;
     float* sc = s_ss + (one_n_tile ? 0 : as * 512);
     float* sh = sc + 256;
     if (!one_n_tile) {
@@ -189,7 +193,10 @@ __device__ __forceinline__ void epilogue_loop(const ConvKParams& p, uint32_t tme
     // this warp has finished reading the accumulator stage: hand it back to the MMA issuer
     ptx::tc_fence_before();
     __syncwarp();
-    if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+    if (lane == 0) {
+      if (PAIR) ptx::mbar_arrive_leader(&tmem_empty_bar[as]);
+      else ptx::mbar_arrive(&tmem_empty_bar[as]);
+    }
     if (++as == 2) { as = 0; aphase ^= 1u; }
   }
 }
@@ -389,6 +396,145 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp_idx == 1) ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair variant for the wide 3x3 layers (tcgen05 cta_group::2): two CTAs on the two SMs of a TPC compute a
+// 256 x block_n tile together.  Each CTA loads its own 128-row activation boxes but only HALF of every weight tile
+// (block_n/2 rows); the tensor cores of both SMs read both halves.  Why: the single-CTA kernel is bound by the
+// chip-wide L2 -> shared-memory TMA rate (measured ~50 B/clk/SM; a 128x256 tile needs 5.7 KB of A + 32 KB of B per
+// 512 MMA cycles = 74 B/clk) — halving B per SM (5.7 + 16 KB -> 42 B/clk) puts the layer back under the tensor pipe.
+// Barriers: TMA of both CTAs counts bytes on the LEADER's full barriers (only the leader issues MMAs); MMA completion
+// is multicast to the empty / accumulator-full barriers of both CTAs; the epilogues of both CTAs hand the
+// accumulator stage back on the leader's barrier (8 arrivals).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+conv_gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_abox,
+                              const ConvKParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t b_half_bytes = (uint32_t)(p.block_n / 2 * 128);
+  uint8_t* smem = smem_raw;
+  {
+    uint32_t a = ptx::smem_u32(smem);
+    smem += (1024u - (a & 1023u)) & 1023u;
+  }
+  uint8_t* tiles = smem;
+  uint8_t* b_ring = tiles + (size_t)p.a_stages * A_BOX_STRIDE;
+  uint8_t* aux = b_ring + (size_t)p.stages * b_half_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]
+  uint64_t* afull_bar = tmem_empty_bar + 2;           // [MAX_A_STAGES]
+  uint64_t* aempty_bar = afull_bar + MAX_A_STAGES;    // [MAX_A_STAGES]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aempty_bar + MAX_A_STAGES);
+  float* s_ss = reinterpret_cast<float*>(aux + 256);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = (int)ptx::cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int m_pairs = (p.m_tiles + 1) / 2;
+  const int total_units = m_pairs * p.n_tiles;
+
+  if (warp_idx == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_b);
+    ptx::prefetch_tensormap(&tmap_abox);
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);
+      ptx::mbar_init(&tmem_empty_bar[a], 8);  // 4 epilogue warps of each CTA
+    }
+    for (int a = 0; a < MAX_A_STAGES; ++a) {
+      ptx::mbar_init(&afull_bar[a], 1);
+      ptx::mbar_init(&aempty_bar[a], 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp_idx == 1) {
+    ptx::tmem_alloc_pair(tmem_ptr_smem, (uint32_t)p.tmem_cols);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();  // barriers of BOTH CTAs initialised before any remote arrival / complete_tx
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer (one thread per CTA) =====================
+    if (lane == 0) {
+      int s = 0, sa = 0;
+      uint32_t phase = 0, pha = 0;
+      for (int unit = cluster_id; unit < total_units; unit += num_clusters) {
+        const int n0 = (unit % p.n_tiles) * p.block_n + rank * (p.block_n / 2);
+        const int m0 = (2 * (unit / p.n_tiles) + rank) * BLOCK_M;
+        for (int g = 0; g < 3 * p.kb_per_tap; ++g) {
+          const int dy = g / p.kb_per_tap, cb = g - dy * p.kb_per_tap;
+          ptx::mbar_wait(&aempty_bar[sa], pha ^ 1u);
+          if (rank == 0) ptx::mbar_arrive_expect_tx(&afull_bar[sa], 2 * A_BOX_BYTES);
+          ptx::tma_load_2d_pair(tiles + (size_t)sa * A_BOX_STRIDE, &tmap_abox, &afull_bar[sa], cb * 64,
+                                m0 + (dy - 1) * p.Wp - 1);
+          if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
+          for (int dx = 0; dx < 3; ++dx) {
+            const int kb = (dy * 3 + dx) * p.kb_per_tap + cb;
+            ptx::mbar_wait(&empty_bar[s], phase ^ 1u);
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * b_half_bytes);
+            ptx::tma_load_2d_pair(b_ring + (size_t)s * b_half_bytes, &tmap_b, &full_bar[s], kb * 64, n0);
+            if (++s == p.stages) { s = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer (one thread of the leader CTA) =====================
+    if (lane == 0 && rank == 0) {
+      int s = 0, sa = 0, as = 0;
+      uint32_t phase = 0, pha = 0, aphase = 0;
+      for (int unit = cluster_id; unit < total_units; unit += num_clusters) {
+        ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(as * p.acc_stride);
+        for (int g = 0; g < 3 * p.kb_per_tap; ++g) {
+          ptx::mbar_wait(&afull_bar[sa], pha);
+          const uint32_t a_addr = ptx::smem_u32(tiles + (size_t)sa * A_BOX_STRIDE);
+          for (int dx = 0; dx < 3; ++dx) {
+            ptx::mbar_wait(&full_bar[s], phase);
+            ptx::tc_fence_after();
+            const uint64_t adesc = ptx::make_sw128_kmajor_desc(a_addr + (uint32_t)dx * 128u);
+            const uint64_t bdesc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(b_ring + (size_t)s * b_half_bytes));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_bf16_ss_pair(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
+                                     (g > 0 || dx > 0 || k > 0) ? 1u : 0u);
+            ptx::umma_commit_pair(&empty_bar[s]);
+            if (++s == p.stages) { s = 0; phase ^= 1u; }
+          }
+          ptx::umma_commit_pair(&aempty_bar[sa]);
+          if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
+        }
+        ptx::umma_commit_pair(&tmem_full_bar[as]);
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue: warps 2..5 of both CTAs =====================
+    if (p.epi_mode == MC_EPI_PNHWC) {
+      if (p.leaky) epilogue_loop<MC_EPI_PNHWC, true, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, total_units, rank);
+      else epilogue_loop<MC_EPI_PNHWC, false, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, total_units, rank);
+    } else if (p.epi_mode == MC_EPI_REORG2) {
+      if (p.leaky) epilogue_loop<MC_EPI_REORG2, true, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, total_units, rank);
+      else epilogue_loop<MC_EPI_REORG2, false, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, total_units, rank);
+    } else {
+      if (p.leaky) epilogue_loop<MC_EPI_NCHW_F32, true, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, total_units, rank);
+      else epilogue_loop<MC_EPI_NCHW_F32, false, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, total_units, rank);
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();  // the peer may still read this CTA's smem / signal its barriers until both are done
+  if (warp_idx == 1) ptx::tmem_dealloc_pair(tmem_base, (uint32_t)p.tmem_cols);
+}
+
 // Tile-width heuristic.  One 64-wide k-block of a 128 x bn tile costs max(2*bn, 128+bn) SM cycles: 2*bn is the
 // tcgen05 issue floor (128*bn*64 MACs at 4096 MAC/clk), 128+bn is the shared-memory read of the A (16 KB) and
 // B (bn*128 B) tiles at 128 B/clk.  Cost = waves over the SMs x (k-blocks x that + a fixed prologue/epilogue).
@@ -535,6 +681,24 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   }
   MC_CHECK_ARG(smem_bytes <= 227 * 1024, "mc_conv_fwd: smem %zu too large", smem_bytes);
 
+  // CTA pair (cta_group::2) for the wide 3x3 layers: MCB200_CONV_2CTA=0 off, 1 auto (default), 2 wherever legal
+  static int pair_env = -1;
+  if (pair_env < 0) {
+    const char* e = getenv("MCB200_CONV_2CTA");
+    pair_env = e ? atoi(e) : 1;
+    if (pair_env < 0 || pair_env > 2) pair_env = 1;
+  }
+  const bool pair_legal = share_dx && d->stages <= 0 && (block_n % 32) == 0 && block_n >= 64 && m_tiles >= 2;
+  const bool use_pair = pair_legal && (pair_env == 2 || (pair_env == 1 && block_n >= 192 && num_kb >= 36));
+  if (use_pair) {
+    ctas = 1;
+    a_stages = MAX_A_STAGES;
+    const int b_half = block_n / 2 * 128;
+    stages = (204 * 1024 - a_stages * A_BOX_STRIDE) / b_half;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    smem_bytes = (size_t)a_stages * A_BOX_STRIDE + (size_t)stages * b_half + AUX_BYTES;
+  }
+
   CUtensorMap tm_a, tm_b, tm_abox;
   int rc = mc_make_tmap_2d_bf16_k(&tm_a, d->d_in, (uint64_t)M_rows, (uint64_t)d->Cin, (uint64_t)d->Cin_ld, BLOCK_M, BLOCK_K);
   if (rc) return rc;
@@ -545,7 +709,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   }
   // weights: [n_tiles*block_n >= Npad rows (OOB rows zero-filled), ntaps*Kc]
   rc = mc_make_tmap_2d_bf16_k(&tm_b, d->d_wpack, (uint64_t)d->Npad, (uint64_t)ntaps * Kc, (uint64_t)ntaps * Kc,
-                              (uint32_t)block_n, BLOCK_K);
+                              (uint32_t)(use_pair ? block_n / 2 : block_n), BLOCK_K);
   if (rc) return rc;
 
   ConvKParams p;
@@ -576,6 +740,35 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   p.ch_off = d->ch_off;
   p.epi_mode = d->epi_mode;
   p.leaky = d->leaky;
+
+  if (use_pair) {
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(block_n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
+      MC_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * (mc_num_sms() / 2));
+      cfg.blockDim = dim3(NUM_THREADS);
+      cfg.dynamicSmemBytes = 210 * 1024;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, conv_gemm_tcgen05_pair_kernel, &cfg) != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        n = mc_num_sms() / 2;
+      }
+      max_clusters = n;
+    }
+    const int m_pairs = (m_tiles + 1) / 2;
+    const long long units = (long long)m_pairs * n_tiles;
+    const int clusters = (int)(units < max_clusters ? units : max_clusters);
+    conv_gemm_tcgen05_pair_kernel<<<2 * clusters, NUM_THREADS, smem_bytes, stream>>>(tm_b, tm_abox, p);
+    MC_LAUNCH_CHECK("conv_gemm_tcgen05_pair_kernel");
+    return 0;
+  }
 
   static bool attr_set = false;
   if (!attr_set) {
