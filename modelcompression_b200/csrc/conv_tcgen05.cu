@@ -688,7 +688,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
     pair_env = e ? atoi(e) : 1;
     if (pair_env < 0 || pair_env > 2) pair_env = 1;
   }
-  const bool pair_legal = share_dx && d->stages <= 0 && (block_n % 32) == 0 && block_n >= 64 && m_tiles >= 2;
+  const bool pair_legal = share_dx && d->stages <= 0 && (block_n % 16) == 0 && block_n >= 64 && m_tiles >= 2;
   const bool use_pair = pair_legal && (pair_env == 2 || (pair_env == 1 && block_n >= 192 && num_kb >= 36));
   if (use_pair) {
     ctas = 1;
