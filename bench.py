@@ -53,6 +53,19 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, bf16=1590.0, bf16_sustained=1400.0, source='fallback')
 
 
+def nvml_handle(pynvml, index):
+    """NVML handle of CUDA device `index` of this process (NVML numbers physical GPUs, CUDA_VISIBLE_DEVICES renumbers
+    CUDA's): matched by UUID, falling back to the index."""
+    try:
+        import torch
+        uuid = str(torch.cuda.get_device_properties(index).uuid)
+        if not uuid.startswith('GPU-'):
+            uuid = 'GPU-' + uuid
+        return pynvml.nvmlDeviceGetHandleByUUID(uuid)
+    except Exception:
+        return pynvml.nvmlDeviceGetHandleByIndex(index)
+
+
 class ClockSampler(object):
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
@@ -64,7 +77,7 @@ class ClockSampler(object):
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.h = nvml_handle(pynvml, index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
         except Exception:
             self.nv = None
@@ -97,6 +110,27 @@ class ClockSampler(object):
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
         return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def bind_to_gpu_numa(index):
+    """Pin this process to the CPUs NVML reports as local to the GPU (same NUMA node / PCIe root) BEFORE the pinned
+    host buffers are allocated, so they land in memory next to the GPU: on a two-socket host a pinned buffer on the far
+    socket halves the host->device rate of the end-to-end loop.  Returns the number of CPUs bound to (None if NVML or
+    the affinity call is unavailable — the run then proceeds unbound)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = nvml_handle(pynvml, index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return None
 
 
 def build_pruned_model(device):
@@ -296,6 +330,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py (b200 arm) needs a CUDA device; there is no CPU fallback"
     torch.cuda.set_device(local_rank)
     device = torch.device('cuda', local_rank)
+    bound_cpus = bind_to_gpu_numa(local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=device)
@@ -428,7 +463,8 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * IMG * IMG,
                 "d2h_bytes_per_step": int(y.numel() * 4),
-                "input": "uint8 NCHW images in pinned host memory (do_detect's input type), x/255 on the device"},
+                "input": "uint8 NCHW images in pinned host memory (do_detect's input type), x/255 on the device",
+                "host_cpus_bound_to_gpu_numa_node": bound_cpus},
         "gpu_launches": plan.num_launches * args.steps,
         "roofline": {"bound": "tensor", "kernel": "conv_gemm_tcgen05_kernel", "achieved": achieved_tflops,
                      "peak": peaks['bf16_sustained'], "unit": "TFLOP/s",

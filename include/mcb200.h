@@ -175,6 +175,13 @@ typedef struct mc_conv_desc {
 
 int mc_conv_fwd(const mc_conv_desc* desc, void* stream);
 
+/* Which launch configuration the LAST mc_conv_fwd call of this host thread chose (tests / bench reporting):
+ * info[0] = 1 CTA-pair kernel (tcgen05 cta_group::2, 256-row tiles, half of each weight tile per CTA), 0 single CTA
+ * info[1] = tile width block_n      info[2] = resident CTAs per SM requested (1..3)
+ * info[3] = 1 weights resident in shared memory for the whole launch      info[4] = 1 shared activation box (3x3)
+ * info[5] = smem ring stages         info[6] = grid size                   info[7] = k-block (32 or 64)           */
+int mc_conv_last_plan(int info[8]);
+
 /* Small-channel direct convolution on CUDA cores, for layers too thin for a 128xNx64 tensor-core tile: the 3-channel
  * first layer (in_is_nchw_f32=1: d_in is the fp32 NCHW image [B,Cin,H,W]) and the first blocks of a filter-pruned
  * network (d_in PNHWC bf16, pitch Cin_ld).  d_w: fp32 [N,Cin,k,k] (already masked / gathered).  Fused scale/shift,

@@ -22,7 +22,8 @@ namespace {
 
 constexpr int BLOCK_M = 128;  // k-block: 64 bf16 (128-byte swizzle rows) or 32 bf16 (64-byte swizzle rows), per launch
 constexpr int MAX_STAGES = 8;
-constexpr int MAX_A_STAGES = 3;
+constexpr int MAX_A_STAGES = 8;   // activation-box ring: 3 beside a weight ring, up to 8 when the weights are resident
+constexpr int DEF_A_STAGES = 3;
 constexpr int A_BOX_ROWS = BLOCK_M + 8;          // rows m0-1 .. m0+134: the dx = -1, 0, +1 windows of a 128-row tile
 constexpr int A_BOX_BYTES = A_BOX_ROWS * 128;   // 17,408 B landed by TMA
 constexpr int A_BOX_STRIDE = 18 * 1024;         // ring pitch (1024-byte aligned for the 128-byte swizzle)
@@ -38,6 +39,8 @@ struct ConvKParams {
   int ksize;       // 1 or 3
   int Wp, Hp, W, H;  // Wp = W+1, Hp = H+1
   int block_n, stages, tmem_cols, acc_stride;  // acc_stride: TMEM columns between the two accumulator stages
+  int last_ksteps;  // UMMA K steps (16 channels) that hold real channels in the LAST channel block of a tap
+  int b_resident;   // share_dx only: all weight tiles stay in shared memory for the whole launch (one N tile, small K)
   int share_dx, a_stages;  // 3x3 only: one A box (136 rows) serves the three dx taps of a filter row; separate A / B rings
   int m_tiles, n_tiles;
   uint32_t idesc;
@@ -224,7 +227,8 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   uint8_t* tiles = smem;
   // share_dx: [a_stages x A box (18 KB pitch)] [stages x B tile]; else [stages x (A | B)]
   uint8_t* b_ring = tiles + (size_t)p.a_stages * A_BOX_STRIDE;
-  uint8_t* aux = p.share_dx ? b_ring + (size_t)p.stages * b_tile_bytes : tiles + (size_t)p.stages * stage_bytes;
+  uint8_t* aux = p.share_dx ? b_ring + (size_t)(p.b_resident ? p.num_kb : p.stages) * b_tile_bytes
+                            : tiles + (size_t)p.stages * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;   // [2]
@@ -232,7 +236,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   uint64_t* afull_bar = tmem_empty_bar + 2;           // [MAX_A_STAGES]
   uint64_t* aempty_bar = afull_bar + MAX_A_STAGES;    // [MAX_A_STAGES]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aempty_bar + MAX_A_STAGES);
-  float* s_ss = reinterpret_cast<float*>(aux + 256);  // [2 acc stages][scale|shift][256]
+  float* s_ss = reinterpret_cast<float*>(aux + 512);  // [2 acc stages][scale|shift][256]
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -272,6 +276,11 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       // the activations cross L2 -> smem 3 times per tile instead of 9.  B: one tile per tap, its own ring.
       int s = 0, sa = 0;
       uint32_t phase = 0, pha = 0;
+      if (p.b_resident) {  // every weight tile of the layer, once: [num_kb][block_n rows x 128 B]
+        ptx::mbar_arrive_expect_tx(&full_bar[0], (uint32_t)p.num_kb * b_tile_bytes);
+        for (int kb = 0; kb < p.num_kb; ++kb)
+          ptx::tma_load_2d(b_ring + (size_t)kb * b_tile_bytes, &tmap_b, &full_bar[0], kb * 64, 0);
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n0 = (tile % p.n_tiles) * p.block_n;
         const int m0 = (tile / p.n_tiles) * BLOCK_M;
@@ -282,6 +291,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           ptx::tma_load_2d(tiles + (size_t)sa * A_BOX_STRIDE, &tmap_abox, &afull_bar[sa], cb * 64,
                            m0 + (dy - 1) * p.Wp - 1);
           if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
+          if (p.b_resident) continue;
           for (int dx = 0; dx < 3; ++dx) {
             const int kb = (dy * 3 + dx) * p.kb_per_tap + cb;
             ptx::mbar_wait(&empty_bar[s], phase ^ 1u);
@@ -313,40 +323,66 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
     }
   } else if (warp_idx == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0 && p.share_dx) {
+    // ===================== MMA issuer =====================
+    // The WHOLE warp walks the loop (warp-uniform control flow and operands, so descriptors live in uniform
+    // registers) and one elected lane issues the tcgen05 instructions.  With the loop inside `if (lane == 0)` the
+    // compiler wraps every UTCHMMA in a vote/R2UR.BROADCAST loop (~25 instructions), and that single thread's issue
+    // rate — not the tensor pipe — bounds the k-block time.
+    if (p.share_dx) {
       int s = 0, sa = 0, as = 0;
       uint32_t phase = 0, pha = 0, aphase = 0;
+      bool b_loaded = false;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t tmem_acc = tmem_base + (uint32_t)(as * p.acc_stride);
         for (int g = 0; g < 3 * p.kb_per_tap; ++g) {
+          const int dy = g / p.kb_per_tap, cb = g - dy * p.kb_per_tap;
+          // K steps beyond the layer's real channels multiply TMA zero fill by zero weights: not issued
+          const int nk = (cb == p.kb_per_tap - 1) ? p.last_ksteps : 4;
           ptx::mbar_wait(&afull_bar[sa], pha);
           const uint32_t a_addr = ptx::smem_u32(tiles + (size_t)sa * A_BOX_STRIDE);
           for (int dx = 0; dx < 3; ++dx) {
-            ptx::mbar_wait(&full_bar[s], phase);
+            uint32_t b_addr;
+            if (p.b_resident) {
+              if (!b_loaded) { ptx::mbar_wait(&full_bar[0], 0); b_loaded = true; }
+              b_addr = ptx::smem_u32(b_ring + (size_t)((dy * 3 + dx) * p.kb_per_tap + cb) * b_tile_bytes);
+            } else {
+              ptx::mbar_wait(&full_bar[s], phase);
+              b_addr = ptx::smem_u32(b_ring + (size_t)s * b_tile_bytes);
+            }
             ptx::tc_fence_after();
             // the window of tap dx starts dx rows (dx * 128 B) into the box.  The start is then not aligned to the
             // 1024-byte swizzle pattern; measured on B200: the tensor core applies the 128-byte swizzle to the absolute
             // shared-memory address (as TMA did when it wrote the box), so the descriptor's base-offset field must stay
             // 0 — setting it to dx (or 8-dx) reads garbage (tools/debug_share.py)
             const uint64_t adesc = ptx::make_sw128_kmajor_desc(a_addr + (uint32_t)dx * 128u);
-            const uint64_t bdesc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(b_ring + (size_t)s * b_tile_bytes));
+            const uint64_t bdesc = ptx::make_sw128_kmajor_desc(b_addr);
+            if (ptx::elect_one()) {
+              if (nk == 4) {  // (compile-time trip count: this issue loop is on the critical path)
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              ptx::umma_bf16_ss(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
-                                (g > 0 || dx > 0 || k > 0) ? 1u : 0u);
-            ptx::umma_commit(&empty_bar[s]);
-            if (++s == p.stages) { s = 0; phase ^= 1u; }
+                for (int k = 0; k < 4; ++k)
+                  ptx::umma_bf16_ss(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
+                                    (g > 0 || dx > 0 || k > 0) ? 1u : 0u);
+              } else {
+                for (int k = 0; k < nk; ++k)
+                  ptx::umma_bf16_ss(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
+                                    (g > 0 || dx > 0 || k > 0) ? 1u : 0u);
+              }
+              if (!p.b_resident) ptx::umma_commit(&empty_bar[s]);
+              if (dx == 2) ptx::umma_commit(&aempty_bar[sa]);  // the box may be refilled once its three taps retire
+              if (dx == 2 && g == 3 * p.kb_per_tap - 1) ptx::umma_commit(&tmem_full_bar[as]);
+            }
+            __syncwarp();
+            if (!p.b_resident) {
+              if (++s == p.stages) { s = 0; phase ^= 1u; }
+            }
           }
-          ptx::umma_commit(&aempty_bar[sa]);  // the box may be refilled once the MMAs of its three taps retire
           if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
         }
-        ptx::umma_commit(&tmem_full_bar[as]);
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
-    } else if (lane == 0) {
+    } else {
       int s = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -355,6 +391,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1u);  // epilogue has drained this accumulator stage
         ptx::tc_fence_after();
         const uint32_t tmem_acc = tmem_base + (uint32_t)(as * p.acc_stride);
+        int cb_i = 0;  // channel block inside the tap
         for (int kb = 0; kb < p.num_kb; ++kb) {
           ptx::mbar_wait(&full_bar[s], phase);
           ptx::tc_fence_after();
@@ -363,17 +400,21 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const uint64_t adesc = k64 ? ptx::make_sw128_kmajor_desc(a_addr) : ptx::make_sw64_kmajor_desc(a_addr);
           const uint64_t bdesc = k64 ? ptx::make_sw128_kmajor_desc(a_addr + a_tile_bytes)
                                      : ptx::make_sw64_kmajor_desc(a_addr + a_tile_bytes);
-          const int ksteps = p.block_k / 16;
+          const int ksteps = (cb_i == p.kb_per_tap - 1) ? p.last_ksteps : p.block_k / 16;
+          if (++cb_i == p.kb_per_tap) cb_i = 0;
+          if (ptx::elect_one()) {
 #pragma unroll 4
-          for (int k = 0; k < ksteps; ++k) {
-            // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr>>4) field
-            ptx::umma_bf16_ss(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
-                              (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < ksteps; ++k) {
+              // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr>>4) field
+              ptx::umma_bf16_ss(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
+                                (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            ptx::umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+            if (kb == p.num_kb - 1) ptx::umma_commit(&tmem_full_bar[as]);  // accumulator complete
           }
-          ptx::umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+          __syncwarp();
           if (++s == p.stages) { s = 0; phase ^= 1u; }
         }
-        ptx::umma_commit(&tmem_full_bar[as]);  // accumulator complete
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
@@ -425,7 +466,7 @@ conv_gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_b, const 
   uint64_t* afull_bar = tmem_empty_bar + 2;           // [MAX_A_STAGES]
   uint64_t* aempty_bar = afull_bar + MAX_A_STAGES;    // [MAX_A_STAGES]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aempty_bar + MAX_A_STAGES);
-  float* s_ss = reinterpret_cast<float*>(aux + 256);
+  float* s_ss = reinterpret_cast<float*>(aux + 512);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -486,8 +527,8 @@ conv_gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_b, const 
       }
     }
   } else if (warp_idx == 1) {
-    // ===================== MMA issuer (one thread of the leader CTA) =====================
-    if (lane == 0 && rank == 0) {
+    // ===================== MMA issuer (warp 1 of the leader CTA; one elected lane issues) =====================
+    if (rank == 0) {
       int s = 0, sa = 0, as = 0;
       uint32_t phase = 0, pha = 0, aphase = 0;
       for (int unit = cluster_id; unit < total_units; unit += num_clusters) {
@@ -495,6 +536,7 @@ conv_gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_b, const 
         ptx::tc_fence_after();
         const uint32_t tmem_acc = tmem_base + (uint32_t)(as * p.acc_stride);
         for (int g = 0; g < 3 * p.kb_per_tap; ++g) {
+          const int nk = ((g % p.kb_per_tap) == p.kb_per_tap - 1) ? p.last_ksteps : 4;
           ptx::mbar_wait(&afull_bar[sa], pha);
           const uint32_t a_addr = ptx::smem_u32(tiles + (size_t)sa * A_BOX_STRIDE);
           for (int dx = 0; dx < 3; ++dx) {
@@ -502,17 +544,26 @@ conv_gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_b, const 
             ptx::tc_fence_after();
             const uint64_t adesc = ptx::make_sw128_kmajor_desc(a_addr + (uint32_t)dx * 128u);
             const uint64_t bdesc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(b_ring + (size_t)s * b_half_bytes));
+            if (ptx::elect_one()) {
+              if (nk == 4) {  // (compile-time trip count: this issue loop is on the critical path)
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              ptx::umma_bf16_ss_pair(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
-                                     (g > 0 || dx > 0 || k > 0) ? 1u : 0u);
-            ptx::umma_commit_pair(&empty_bar[s]);
+                for (int k = 0; k < 4; ++k)
+                  ptx::umma_bf16_ss_pair(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
+                                         (g > 0 || dx > 0 || k > 0) ? 1u : 0u);
+              } else {
+                for (int k = 0; k < nk; ++k)
+                  ptx::umma_bf16_ss_pair(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
+                                         (g > 0 || dx > 0 || k > 0) ? 1u : 0u);
+              }
+              ptx::umma_commit_pair(&empty_bar[s]);
+              if (dx == 2) ptx::umma_commit_pair(&aempty_bar[sa]);
+              if (dx == 2 && g == 3 * p.kb_per_tap - 1) ptx::umma_commit_pair(&tmem_full_bar[as]);
+            }
+            __syncwarp();
             if (++s == p.stages) { s = 0; phase ^= 1u; }
           }
-          ptx::umma_commit_pair(&aempty_bar[sa]);
           if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
         }
-        ptx::umma_commit_pair(&tmem_full_bar[as]);
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
@@ -567,6 +618,14 @@ int pick_block_n(int Npad, int m_tiles, int num_kb, int num_sms, bool share_dx) 
 
 }  // namespace
 
+static thread_local int g_last_plan[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+extern "C" int mc_conv_last_plan(int info[8]) {
+  MC_CHECK_ARG(info != nullptr, "mc_conv_last_plan: null pointer");
+  for (int i = 0; i < 8; ++i) info[i] = g_last_plan[i];
+  return 0;
+}
+
 extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MC_CHECK_ARG(d != nullptr, "mc_conv_fwd: null descriptor");
@@ -618,14 +677,36 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   int tmem_cols = 32;
   while (tmem_cols < 2 * acc_stride) tmem_cols <<= 1;  // two accumulator stages
   const int num_kb = ntaps * (Kc / BLOCK_K);
-  constexpr size_t AUX_BYTES = 256 + 4096 + 1024;  // barriers, scale/shift staging, 1024-byte alignment slack
+  constexpr size_t AUX_BYTES = 512 + 4096 + 1024;  // barriers, scale/shift staging, 1024-byte alignment slack
 
   // smem ring of one CTA when `ctas` CTAs share an SM (each CTA also costs 1 KB of reserved shared memory)
+  // resident weights: one N tile and all taps' weight tiles fit beside the activation ring -> loaded once per CTA
+  // (narrow 3x3 layers: the per-tile weight re-load is otherwise as much TMA traffic as the activations)
+  const size_t b_res_bytes = (size_t)num_kb * block_n * 128;
+  // OFF by default (MCB200_CONV_RESIDENT=1 enables): measured on B200 it loses to the weight ring on every narrow
+  // 3x3 shape tried (64->64 @52x52: 37 us vs 25 us; 48->32 @104x104: 71 vs 58; 40->80 @52x52: 41 vs 33) because the
+  // resident tiles leave room for ONE CTA per SM, and three small CTAs per SM hide the per-tile latency chain better
+  // than the saved weight traffic.
+  static int res_env = -1;
+  if (res_env < 0) {
+    const char* e = getenv("MCB200_CONV_RESIDENT");
+    res_env = (e && e[0] == '1') ? 1 : 0;
+  }
+  const int b_resident = (res_env && share_dx && n_tiles == 1 && d->stages <= 0 && b_res_bytes <= 112 * 1024) ? 1 : 0;
   auto plan_ring = [&](int ctas, int* st, int* ast, size_t* bytes) -> bool {
     const long long cap = (ctas == 1 ? 204 * 1024 : (227 * 1024) / ctas - 1024 - (long long)AUX_BYTES);
+    if (b_resident) {
+      // the activation ring is the only pipeline left: as deep as the smem beside the weights allows (a tile is 3 boxes)
+      long long a = (cap - (long long)b_res_bytes) / A_BOX_STRIDE;
+      if (a > MAX_A_STAGES) a = MAX_A_STAGES;
+      if (a < (ctas == 1 ? 3 : 2)) return false;
+      *st = 1; *ast = (int)a;
+      *bytes = (size_t)a * A_BOX_STRIDE + b_res_bytes + AUX_BYTES;
+      return true;
+    }
     if (share_dx) {
       const int b_bytes = block_n * 128;
-      int a = ctas == 1 ? MAX_A_STAGES : 2;
+      int a = ctas == 1 ? DEF_A_STAGES : 2;
       long long stg = (cap - (long long)a * A_BOX_STRIDE) / b_bytes;
       if (stg > MAX_STAGES) stg = MAX_STAGES;
       if (stg < 3) return false;
@@ -671,7 +752,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   } else {
     ctas = 1;
     if (share_dx) {
-      a_stages = MAX_A_STAGES;
+      a_stages = DEF_A_STAGES;
       MC_CHECK_ARG(stages >= 2 && stages <= MAX_STAGES, "mc_conv_fwd: stages %d invalid", stages);
       smem_bytes = (size_t)a_stages * A_BOX_STRIDE + (size_t)stages * block_n * 128 + AUX_BYTES;
     } else {
@@ -692,7 +773,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   const bool use_pair = pair_legal && (pair_env == 2 || (pair_env == 1 && block_n >= 192 && num_kb >= 36));
   if (use_pair) {
     ctas = 1;
-    a_stages = MAX_A_STAGES;
+    a_stages = DEF_A_STAGES;
     const int b_half = block_n / 2 * 128;
     stages = (204 * 1024 - a_stages * A_BOX_STRIDE) / b_half;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -727,6 +808,11 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   p.block_n = block_n;
   p.stages = stages;
   p.share_dx = share_dx;
+  p.b_resident = (b_resident && !use_pair) ? 1 : 0;
+  {
+    const int rem = d->Cin - (Kc / BLOCK_K - 1) * BLOCK_K;  // channels in the last channel block of a tap
+    p.last_ksteps = (rem + 15) / 16;
+  }
   p.a_stages = a_stages;
   p.acc_stride = acc_stride;
   p.tmem_cols = tmem_cols;
@@ -765,6 +851,8 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
     const int m_pairs = (m_tiles + 1) / 2;
     const long long units = (long long)m_pairs * n_tiles;
     const int clusters = (int)(units < max_clusters ? units : max_clusters);
+    g_last_plan[0] = 1; g_last_plan[1] = block_n; g_last_plan[2] = 1; g_last_plan[3] = 0; g_last_plan[4] = 1;
+    g_last_plan[5] = stages; g_last_plan[6] = 2 * clusters; g_last_plan[7] = BLOCK_K;
     conv_gemm_tcgen05_pair_kernel<<<2 * clusters, NUM_THREADS, smem_bytes, stream>>>(tm_b, tm_abox, p);
     MC_LAUNCH_CHECK("conv_gemm_tcgen05_pair_kernel");
     return 0;
@@ -778,6 +866,8 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   }
   const long long max_ctas = (long long)mc_num_sms() * ctas;
   int grid = (int)(total_tiles < max_ctas ? total_tiles : max_ctas);
+  g_last_plan[0] = 0; g_last_plan[1] = block_n; g_last_plan[2] = ctas; g_last_plan[3] = p.b_resident;
+  g_last_plan[4] = share_dx; g_last_plan[5] = stages; g_last_plan[6] = grid; g_last_plan[7] = BLOCK_K;
   if (ctas >= 3)
     conv_gemm_tcgen05_kernel<3><<<grid, NUM_THREADS, smem_bytes, stream>>>(tm_a, tm_b, tm_abox, p);
   else

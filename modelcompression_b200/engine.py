@@ -321,8 +321,10 @@ class CompiledDarknet(object):
             self.ops.append(dict(kind='pack_input', dst_buf=bid_in, C=in_ch, H=H, W=W, name='pack_input'))
             src = _TensorRef(bid_in, H, W, in_ch, list(range(in_ch)), torch.zeros(in_ch))
 
-        # k-block of 32 (64-byte swizzle) only where it halves K (<= 32 input channels).  Measured on B200: for 69 -> 96
-        # instead of 128 columns the extra pipeline steps cost more than the 25 % of zero padding they remove.
+        # k-block of 32 (64-byte swizzle) where it halves K (<= 32 input channels).  Measured on B200: TMA cost follows the
+        # box AREA, not the valid channels, so a 64-wide box (shared activation box, resident weights) is slower than
+        # 32-wide boxes for <= 32 channels (dense conv2: 402 us vs 524 us; shrunk conv8: 33 us vs 39 us); and for
+        # 69 -> 96 instead of 128 columns the extra pipeline steps cost more than the zero padding they remove.
         kblk = 32 if c_phys_in <= 32 else 64
         Kc = _round_up(c_phys_in, kblk)
         wpack = torch.empty(Npad, taps * Kc, dtype=torch.bfloat16, device=dev)

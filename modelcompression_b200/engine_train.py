@@ -226,8 +226,9 @@ class TrainPlan(object):
         return got
 
 
-def _kblk(C):
-    """k-block of the tcgen05 conv: 32 (64-byte swizzle) where it halves the K work, i.e. for <= 32 channels."""
+def _kblk(C, k=1):
+    """k-block of the tcgen05 conv: 32 (64-byte swizzle) where it halves the K work, i.e. for <= 32 channels (TMA cost
+    follows the box area: measured faster than a half-empty 64-wide box, see engine.py)."""
     return 32 if C <= 32 else 64
 
 
@@ -292,7 +293,7 @@ def _forward(plan, x, training_stats=True, after_layer=None):
                                               z.data_ptr(), B, L.H, L.W, C, C, O, L.z.ld, 0, 0, s), "conv1 forward")
             sv.keep_alive = (wfull, sc1, sh0)
         else:
-            kb = _kblk(C)
+            kb = _kblk(C, k)
             Kc = _round_up(C, kb)
             wpack = torch.empty(Npad, k * k * Kc, dtype=torch.bfloat16, device=dev)
             _lib.check(lib.mc_pack_conv_weights(w.data_ptr(), mask_ptr, O, C, k, None, O, None, C, wpack.data_ptr(), Npad,
@@ -426,7 +427,7 @@ def _backward(plan, sv, dy, before_bn=None):
             dname = 'd' + src.name
             if dname in written:
                 raise NotImplementedError("two convolutions consume the same activation slice (block %d)" % L.ind)
-            kb = _kblk(O)
+            kb = _kblk(O, k)
             Cpad, Ko = _round_up(C, 16), _round_up(O, kb)
             wpack = torch.empty(Cpad, k * k * Ko, dtype=torch.bfloat16, device=dev)
             _lib.check(lib.mc_pack_conv_weights_dgrad(conv.weight.data_ptr(), mask_ptr, O, C, k, wpack.data_ptr(), Cpad, Ko,

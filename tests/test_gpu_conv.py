@@ -67,6 +67,41 @@ def test_single_conv_layer(B, C, H, W, O, k, bias):
     assert (err2 <= 5e-3 * ref2.abs() + 2e-3 * ref2.abs().max()).all()
 
 
+def _last_plan():
+    import ctypes
+    from modelcompression_b200 import _lib
+    info = (ctypes.c_int * 8)()
+    _lib.check(_lib.load().mc_conv_last_plan(info), "mc_conv_last_plan")
+    return dict(pair=info[0], block_n=info[1], ctas=info[2], resident=info[3], share=info[4], stages=info[5],
+                grid=info[6], block_k=info[7])
+
+
+@pytest.mark.parametrize("B,C,H,W,O,k,want", [
+    (64, 512, 13, 13, 1024, 3, dict(pair=1)),            # wide 3x3 at the bench batch: CTA-pair kernel (cta_group::2)
+    (64, 1006, 13, 13, 1018, 3, dict(pair=1)),           # shrunk-net shape: ragged Cin/N, odd channel-block tail
+    (33, 600, 13, 13, 512, 3, dict(pair=1)),             # odd number of 128-row tiles (51): last pair half-empty
+    (8, 32, 104, 104, 64, 3, dict(share=1, pair=0)),      # narrow 3x3, Cin 32 in a 64-wide k-block: 2 of 4 K steps issued
+    (8, 16, 52, 52, 72, 3, dict(share=1)),
+    (16, 24, 104, 104, 8, 1, dict(pair=0, resident=0)),  # narrow 1x1: several CTAs per SM
+    (32, 80, 52, 52, 16, 1, dict(pair=0)),
+])
+def test_conv_launch_paths(B, C, H, W, O, k, want):
+    """Every launch configuration of mc_conv_fwd (CTA pair, shared activation box with skipped K steps, multi-CTA narrow layers) against fp32
+    conv on bf16-rounded operands, with the chosen configuration read back from the library."""
+    torch.manual_seed(C * 7 + O)
+    conv = mc.MaskedConv2d(C, O, k, 1, (k - 1) // 2, bias=True).to(DEV)
+    x = torch.randn(B, C, H, W, device=DEV)
+    y = conv(x)
+    plan = _last_plan()
+    for key, val in want.items():
+        assert plan[key] == val, (plan, want)
+    if k == 1 and O <= 16:
+        assert plan['ctas'] >= 2, plan
+    ref = F.conv2d(_bf16(x), _bf16(conv.weight.data), conv.bias.data, 1, (k - 1) // 2)
+    err = (y - ref).abs()
+    assert (err <= 5e-3 * ref.abs() + 2e-3 * ref.abs().max()).all(), "max rel %.3g (%s)" % (_rel(y, ref), plan)
+
+
 def _check_blocks(model, x, tag, tol_block=3e-2, tol_head_l2=2e-2):
     with torch.no_grad():
         y = model(x)
