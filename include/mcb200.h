@@ -269,9 +269,13 @@ int mc_conv_wgrad(const void* d_a, int lda, int C, const void* d_dz, int ld_dz, 
                   const float* d_mask, float* d_dw, int accumulate, void* d_ws, size_t ws_bytes, void* stream);
 size_t mc_workspace_bytes_conv_wgrad(int B, int H, int W, int C, int O, int ksize);
 
-/* Weight gradient of the first layer: x is the fp32 NCHW image [B,C<=4,H,W], 3x3, O <= 32 (CUDA cores).           */
+/* Weight gradient of the first layer: x is the fp32 NCHW image [B,C,H,W], 3x3.  With a workspace of
+ * mc_workspace_bytes_conv_wgrad_first() bytes (256-byte aligned; C*9 <= 32): the image is expanded to bf16 im2col rows
+ * [B*(H+1)*(W+1), 32] and dW = the 1x1 tcgen05 weight gradient over them (mc_conv_wgrad).  Without one (d_ws NULL):
+ * CUDA-core kernel, C <= 4, O <= 32 and a multiple of 4.                                                            */
+size_t mc_workspace_bytes_conv_wgrad_first(int B, int H, int W, int C, int O);
 int mc_conv_wgrad_first(const float* d_x, const void* d_dz, int ld_dz, int B, int H, int W, int C, int O,
-                        const float* d_mask, float* d_dw, void* stream);
+                        const float* d_mask, float* d_dw, void* d_ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

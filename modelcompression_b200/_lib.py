@@ -91,7 +91,8 @@ _SIGNATURES = {
                               c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "mc_workspace_bytes_conv_wgrad": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "mc_conv_wgrad_first": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
-                                    c_void_p]),
+                                    c_void_p, c_size_t, c_void_p]),
+    "mc_workspace_bytes_conv_wgrad_first": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
 }
 
 EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))

@@ -818,6 +818,38 @@ __global__ void __launch_bounds__(WF_THREADS) wgrad_first_kernel(const float* __
   }
 }
 
+// First-layer im2col for the tensor-core weight gradient: row = PNHWC pixel row (pad rows are zero), column c*9 + tap
+// = x[b, c, y+dy-1, x+dx-1] rounded to bf16 (zero outside the image), columns >= C*9 zero.  One thread per row writes
+// its 64 bytes with four 16-byte stores; the 9*C image reads of neighbouring pixels overlap in L1.
+__global__ void __launch_bounds__(256) im2col_first_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                           int B, int H, int W, int C) {
+  const long long rows = (long long)B * (H + 1) * (W + 1);
+  for (long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x; row < rows;
+       row += (long long)gridDim.x * blockDim.x) {
+    const int xx = (int)(row % (W + 1));
+    const long long t = row / (W + 1);
+    const int yy = (int)(t % (H + 1));
+    const int b = (int)(t / (H + 1));
+    __align__(16) __nv_bfloat16 v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __float2bfloat16_rn(0.f);
+    if (xx < W && yy < H) {
+      for (int c = 0; c < C; ++c) {
+        const float* xc = x + ((long long)b * C + c) * H * W;
+#pragma unroll
+        for (int tp = 0; tp < 9; ++tp) {
+          const int y2 = yy + tp / 3 - 1, x2 = xx + tp % 3 - 1;
+          const bool ok = y2 >= 0 && y2 < H && x2 >= 0 && x2 < W;
+          v[c * 9 + tp] = __float2bfloat16_rn(ok ? __ldg(xc + (long long)y2 * W + x2) : 0.f);
+        }
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + row * 32);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[q] = reinterpret_cast<const uint4*>(v)[q];
+  }
+}
+
 __global__ void mul_inplace_kernel(float* __restrict__ a, const float* __restrict__ m, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     a[i] *= m[i];
@@ -838,10 +870,34 @@ extern "C" int mc_pack_conv_weights_dgrad(const float* d_w, const float* d_mask,
   return 0;
 }
 
+// im2col rows (bf16, 32 columns) + the split-K workspace of the 1x1 tensor-core weight gradient over them
+extern "C" size_t mc_workspace_bytes_conv_wgrad_first(int B, int H, int W, int C, int O) {
+  if (B <= 0 || H <= 0 || W <= 0 || C < 1 || O < 1 || C * 9 > 32) return 0;
+  const size_t rows = (size_t)B * (H + 1) * (W + 1);
+  const size_t im2col = (rows * 32 * sizeof(__nv_bfloat16) + 255) & ~(size_t)255;
+  return im2col + mc_workspace_bytes_conv_wgrad(B, H, W, C * 9, O, 1);
+}
+
 extern "C" int mc_conv_wgrad_first(const float* d_x, const void* d_dz, int ld_dz, int B, int H, int W, int C, int O,
-                                   const float* d_mask, float* d_dw, void* stream_) {
+                                   const float* d_mask, float* d_dw, void* d_ws, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MC_CHECK_ARG(d_x && d_dz && d_dw && B > 0 && H > 0 && W > 0, "mc_conv_wgrad_first: bad argument");
+  // Tensor-core path (needs the workspace): dW[o, c*9+tap] = sum_rows dZ[row, o] * im2col[row, c*9+tap] is the 1x1
+  // weight gradient over the materialised im2col rows — [O, C*9] is exactly dW[O,C,3,3] in memory.  The im2col
+  // costs one pass over the image + a 64 B/pixel write (712 MB at batch 64), far below the ~1.5 ms the CUDA-core
+  // kernel below needs for the same 9.6 GMAC.
+  const size_t need = mc_workspace_bytes_conv_wgrad_first(B, H, W, C, O);
+  if (d_ws != nullptr && need != 0 && ws_bytes >= need && (ld_dz % 8) == 0 && ((uintptr_t)d_ws & 255) == 0) {
+    const size_t rows = (size_t)B * (H + 1) * (W + 1);
+    const size_t im2col = (rows * 32 * sizeof(__nv_bfloat16) + 255) & ~(size_t)255;
+    __nv_bfloat16* cols = reinterpret_cast<__nv_bfloat16*>(d_ws);
+    long long g = ((long long)rows + 255) / 256;
+    if (g > (long long)mc_num_sms() * 32) g = (long long)mc_num_sms() * 32;
+    im2col_first_kernel<<<(int)g, 256, 0, stream>>>(d_x, cols, B, H, W, C);
+    MC_LAUNCH_CHECK("im2col_first_kernel");
+    return mc_conv_wgrad(cols, 32, C * 9, d_dz, ld_dz, O, B, H, W, 1, d_mask, d_dw, 0,
+                         reinterpret_cast<uint8_t*>(d_ws) + im2col, ws_bytes - im2col, stream_);
+  }
   MC_CHECK_ARG(C >= 1 && C <= 4 && O >= 1 && O <= 32 && (O % 4) == 0 && (ld_dz % 4) == 0 && ld_dz >= O,
                "mc_conv_wgrad_first: needs C <= 4, O <= 32 (multiple of 4), 3x3 (got C=%d O=%d)", C, O);
   MC_CUDA(cudaMemsetAsync(d_dw, 0, sizeof(float) * (size_t)O * C * 9, stream));

@@ -412,7 +412,11 @@ def _backward(plan, sv, dy, before_bn=None):
         # ---- weight gradient
         dw = torch.empty_like(conv.weight.data)
         if L.src is None:
-            _lib.check(lib.mc_conv_wgrad_first(sv.x.data_ptr(), dz_ptr, ld_dz, B, L.H, L.W, C, O, mask_ptr, dw.data_ptr(), s),
+            # image layer: bf16 im2col rows in the workspace + the 1x1 tcgen05 weight gradient over them
+            nbytes = lib.mc_workspace_bytes_conv_wgrad_first(B, L.H, L.W, C, O)
+            ws = _workspace(dev, nbytes) if nbytes else None
+            _lib.check(lib.mc_conv_wgrad_first(sv.x.data_ptr(), dz_ptr, ld_dz, B, L.H, L.W, C, O, mask_ptr, dw.data_ptr(),
+                                               ws.data_ptr() if ws is not None else None, nbytes, s),
                        "mc_conv_wgrad_first")
         else:
             src = L.src

@@ -67,6 +67,33 @@ def test_wgrad_single_layer(B, C, O, H, W, k):
     assert err <= 2e-3 * ref.abs().max().item() + 1e-4, "max err %.3g (ref max %.3g)" % (err, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("B,C,O,H,W,tensor_core", [(2, 3, 32, 64, 64, True), (2, 3, 32, 64, 64, False),
+                                                    (3, 3, 32, 30, 46, True), (1, 1, 16, 32, 32, True)])
+def test_wgrad_first_layer(B, C, O, H, W, tensor_core):
+    """Image-layer weight gradient (fp32 NCHW image x bf16 dZ): the tensor-core path (bf16 im2col rows in the workspace
+    + 1x1 tcgen05 wgrad) and the CUDA-core path (no workspace) against torch's conv2d_weight."""
+    torch.manual_seed(B + H)
+    lib = _lib.load()
+    x = torch.rand(B, C, H, W, device=DEV)
+    dz = _bf(torch.randn(B, O, H, W, device=DEV))
+    mask = (torch.rand(O, C, 3, 3, device=DEV) > 0.3).float()
+    with torch.cuda.device(0):
+        dzp, ldz = _pack(dz)
+        dw = torch.full((O, C, 3, 3), float('nan'), device=DEV)
+        nbytes = lib.mc_workspace_bytes_conv_wgrad_first(B, H, W, C, O) if tensor_core else 0
+        assert (nbytes > 0) == tensor_core
+        ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=DEV)
+        _lib.check(lib.mc_conv_wgrad_first(x.data_ptr(), dzp.data_ptr(), ldz, B, H, W, C, O, mask.data_ptr(), dw.data_ptr(),
+                                           ws.data_ptr() if tensor_core else None, nbytes, _lib.stream_ptr()),
+                   "mc_conv_wgrad_first")
+    # the tensor-core path rounds the image to bf16 (it is a GEMM operand there, as in the forward); the CUDA-core
+    # path multiplies the fp32 image
+    ref = torch.nn.grad.conv2d_weight(_bf(x) if tensor_core else x, (O, C, 3, 3), dz, padding=1) * mask
+    assert float((dw * (1 - mask)).abs().max()) == 0.0
+    err = (dw - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item() + 1e-4, "max err %.3g (ref max %.3g)" % (err, ref.abs().max().item())
+
+
 @pytest.mark.parametrize("B,C,O,H,W,k", [(2, 32, 64, 20, 20, 3), (2, 512, 64, 26, 26, 1), (2, 1280, 1024, 13, 13, 3),
                                          (3, 24, 40, 9, 15, 3)])
 def test_dgrad_single_layer(B, C, O, H, W, k):
