@@ -466,7 +466,7 @@ def main():
                 "input": "uint8 NCHW images in pinned host memory (do_detect's input type), x/255 on the device",
                 "host_cpus_bound_to_gpu_numa_node": bound_cpus},
         "gpu_launches": plan.num_launches * args.steps,
-        "roofline": {"bound": "tensor", "kernel": "conv_gemm_tcgen05_kernel", "achieved": achieved_tflops,
+        "roofline": {"bound": "tensor", "kernel": "conv_gemm_tcgen05_kernel + conv_gemm_tcgen05_pair_kernel (the conv GEMM launches of a forward)", "achieved": achieved_tflops,
                      "peak": peaks['bf16_sustained'], "unit": "TFLOP/s",
                      "frac": achieved_tflops / peaks['bf16_sustained'] if peaks['bf16_sustained'] else None,
                      "traffic": profiled_traffic(), "traffic_unit": "bytes of DRAM traffic per launch (ncu --set full, "
