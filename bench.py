@@ -437,6 +437,18 @@ def main():
                     out.record_stream(out_stream)
             torch.cuda.synchronize()
 
+        # raw host->device rate of this host for the same pinned buffer (the end-to-end loop is bound by it whenever
+        # 33 MB / rate exceeds the forward time): reported next to the end-to-end value
+        with torch.cuda.stream(copy_stream):
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dev_in[0].copy_(host_in[0], non_blocking=True)
+            h0.record(copy_stream)
+            for _ in range(5):
+                dev_in[0].copy_(host_in[0], non_blocking=True)
+            h1.record(copy_stream)
+        torch.cuda.synchronize()
+        h2d_gbs = 5 * host_in[0].numel() / (h0.elapsed_time(h1) * 1e-3) / 1e9
+
         e2e_loop(4)
         if world > 1:
             dist.barrier()
@@ -464,7 +476,10 @@ def main():
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * IMG * IMG,
                 "d2h_bytes_per_step": int(y.numel() * 4),
                 "input": "uint8 NCHW images in pinned host memory (do_detect's input type), x/255 on the device",
-                "host_cpus_bound_to_gpu_numa_node": bound_cpus},
+                "host_cpus_bound_to_gpu_numa_node": bound_cpus, "h2d_gbs_measured": h2d_gbs,
+                "h2d_bound_images_per_s": h2d_gbs * 1e9 / (3 * IMG * IMG),
+                "note": "double-buffered: step time = max(H2D of the next batch, forward, D2H); on this host the H2D "
+                        "of the 33 MB batch is the longest of the three when h2d_bound_images_per_s < value"},
         "gpu_launches": plan.num_launches * args.steps,
         "roofline": {"bound": "tensor", "kernel": "conv_gemm_tcgen05_kernel + conv_gemm_tcgen05_pair_kernel (the conv GEMM launches of a forward)", "achieved": achieved_tflops,
                      "peak": peaks['bf16_sustained'], "unit": "TFLOP/s",

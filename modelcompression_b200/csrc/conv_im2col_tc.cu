@@ -215,6 +215,9 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
       if (FIRST && POOL && p.Cin == 3) {
         // RGB fast path: compile-time offsets from one base pointer.  Row r of the 4x4 window gives chunks 2r
         // (pixels px 0,1) and 2r+1 (pixels px 2,3), each pixel = (c0,c1,c2,0) in bf16.
+        // (tried: the second half-warp walking each column pair in the opposite order to avoid the 2-way bank conflict
+        //  between the two window rows of a warp — the selects and dynamic offsets cost more than the wavefronts saved:
+        //  84 -> 92 us)
         const int base = by * PCF + bx + XS;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
@@ -241,6 +244,7 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
 #pragma unroll
         for (int q = 0; q < NKB * 8; ++q) {  // 16-byte chunk q holds K elements [8q, 8q+8)
           uint4 val = make_uint4(0, 0, 0, 0);
+          int qs = q;  // chunk position in the A row
           if (q * 8 < KELEMS) {
             if constexpr (FIRST != 0) {
               // two pixels per chunk, 4 bf16 each (c0,c1,c2,c3; absent channels 0); patch is [c][PR][PCF]
@@ -260,14 +264,23 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
               val.z = *reinterpret_cast<uint32_t*>(&b0);
               val.w = *reinterpret_cast<uint32_t*>(&b1);
             } else {
+              // Bank conflicts: neighbouring lanes' windows start S = (POOL ? 2 : 1) * CL/8 chunks (16 B) apart, so with
+              // every lane reading "its chunk number q" only 8/S of the 8 bank groups are used (2-4x the wavefronts).
+              // Lane-dependent XOR on the low bits of the chunk offset inside the window row (and on the matching
+              // position in the A row) makes 8 consecutive lanes cover all 8 groups; loads and stores stay a bijection.
               const __nv_bfloat16* patch = reinterpret_cast<const __nv_bfloat16*>(patch_raw);
               constexpr int V = CL / 8;
+              constexpr int NPX = POOL ? 4 : 3;
+              constexpr int S = (POOL ? 2 : 1) * V;
+              const int m = S == 1 ? 0 : (S == 2 ? ((wx >> 2) & 1) : ((wx >> 1) & 3));
               const int pix = q / V, v = q % V;
-              const int r = POOL ? pix / 4 : pix / 3, sx = POOL ? pix % 4 : pix % 3;
-              val = *reinterpret_cast<const uint4*>(patch + ((by + r) * PC + bx + sx) * CL + v * 8);
+              const int r = pix / NPX, sx = pix % NPX;
+              const int rel = (sx * V + v) ^ m;  // chunk inside the window row, permuted per lane
+              val = *reinterpret_cast<const uint4*>(patch + ((by + r) * PC + bx) * CL + rel * 8);
+              qs = r * (NPX * V) + rel;
             }
           }
-          const int kb = q >> 3, j = q & 7;
+          const int kb = qs >> 3, j = qs & 7;
           *reinterpret_cast<uint4*>(arow + (size_t)kb * (128 * 128) + ((uint32_t)(j << 4) ^ swz)) = val;
         }
       }

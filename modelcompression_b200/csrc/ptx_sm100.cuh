@@ -42,6 +42,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   // suspend-time hint (ns): the thread sleeps in hardware until the phase completes or the hint expires, instead of
   // burning issue slots in a polling loop
+#ifdef MC_SPIN_WAIT
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+#else
   asm volatile(
       "{\n\t"
       ".reg .pred P;\n\t"
@@ -51,6 +62,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity), "r"(10000u)
       : "memory");
+#endif
   return ok != 0;
 }
 // Bounded wait: a broken pipeline traps (launch error) instead of hanging the GPU.  With a debug flag the timeout is
