@@ -171,6 +171,10 @@ typedef struct mc_conv_desc {
   int stages;            /* 0 = auto                                                                      */
   int block_k;           /* k-block: 0/64 = 64 bf16 (d_wpack Kc = round_up(Cin,64)); 32 = 32 bf16 with 64-byte   */
                          /* swizzle (Kc = round_up(Cin,32)): less zero padding for Cin like 32, 69, 91             */
+  int in_cols;           /* 0 = Cin.  Else Cin <= in_cols <= Cin_ld: columns of a d_in row TMA may READ.  Columns    */
+                         /* >= Cin meet zero weights and must hold finite values (the engine's pad channels are 0).  */
+                         /* A box that lies wholly inside the tensor takes TMA's fast path: a partly out-of-bounds   */
+                         /* inner box costs 28 us instead of 20 us on a 17-channel 1x1 layer at 104x104, batch 64.   */
 } mc_conv_desc;
 
 int mc_conv_fwd(const mc_conv_desc* desc, void* stream);

@@ -26,7 +26,7 @@ class mc_conv_desc(ctypes.Structure):
         ("N", c_int), ("Npad", c_int),
         ("ksize", c_int), ("leaky", c_int), ("epi_mode", c_int),
         ("ldc", c_int), ("ch_off", c_int),
-        ("block_n", c_int), ("stages", c_int), ("block_k", c_int),
+        ("block_n", c_int), ("stages", c_int), ("block_k", c_int), ("in_cols", c_int),
     ]
 
 

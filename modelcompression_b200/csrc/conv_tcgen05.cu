@@ -27,6 +27,7 @@ constexpr int DEF_A_STAGES = 3;
 constexpr int A_BOX_ROWS = BLOCK_M + 8;          // rows m0-1 .. m0+134: the dx = -1, 0, +1 windows of a 128-row tile
 constexpr int A_BOX_BYTES = A_BOX_ROWS * 128;   // 17,408 B landed by TMA
 constexpr int A_BOX_STRIDE = 18 * 1024;         // ring pitch (1024-byte aligned for the 128-byte swizzle)
+constexpr int MAX_ACC = 8;  // accumulator stages in TMEM (2 for wide tiles; up to 8 for narrow one-N-tile layers)
 constexpr int NUM_THREADS = 192;
 
 struct ConvKParams {
@@ -38,7 +39,8 @@ struct ConvKParams {
   int block_k;     // 64 or 32
   int ksize;       // 1 or 3
   int Wp, Hp, W, H;  // Wp = W+1, Hp = H+1
-  int block_n, stages, tmem_cols, acc_stride;  // acc_stride: TMEM columns between the two accumulator stages
+  int block_n, stages, tmem_cols, acc_stride;  // acc_stride: TMEM columns between accumulator stages
+  int acc_stages;  // accumulator stages: the MMA issuer runs this many tiles ahead of the epilogue
   int last_ksteps;  // UMMA K steps (16 channels) that hold real channels in the LAST channel block of a tap
   int b_resident;   // share_dx only: all weight tiles stay in shared memory for the whole launch (one N tile, small K)
   int share_dx, a_stages;  // 3x3 only: one A box (136 rows) serves the three dx taps of a filter row; separate A / B rings
@@ -200,7 +202,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvKParams& p, uint32_t tme
       if (PAIR) ptx::mbar_arrive_leader(&tmem_empty_bar[as]);
       else ptx::mbar_arrive(&tmem_empty_bar[as]);
     }
-    if (++as == 2) { as = 0; aphase ^= 1u; }
+    if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
   }
 }
 
@@ -231,9 +233,9 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                             : tiles + (size_t)p.stages * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
-  uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;   // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]
-  uint64_t* afull_bar = tmem_empty_bar + 2;           // [MAX_A_STAGES]
+  uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;   // [MAX_ACC]
+  uint64_t* tmem_empty_bar = tmem_full_bar + MAX_ACC; // [MAX_ACC]
+  uint64_t* afull_bar = tmem_empty_bar + MAX_ACC;     // [MAX_A_STAGES]
   uint64_t* aempty_bar = afull_bar + MAX_A_STAGES;    // [MAX_A_STAGES]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aempty_bar + MAX_A_STAGES);
   float* s_ss = reinterpret_cast<float*>(aux + 512);  // [2 acc stages][scale|shift][256]
@@ -249,7 +251,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < p.acc_stages; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
       ptx::mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
     }
@@ -380,7 +382,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
           if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
         }
-        if (++as == 2) { as = 0; aphase ^= 1u; }
+        if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
       }
     } else {
       int s = 0;
@@ -415,7 +417,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           __syncwarp();
           if (++s == p.stages) { s = 0; phase ^= 1u; }
         }
-        if (++as == 2) { as = 0; aphase ^= 1u; }
+        if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
       }
     }
   } else {
@@ -461,9 +463,9 @@ conv_gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_b, const 
   uint8_t* aux = b_ring + (size_t)p.stages * b_half_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
-  uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;   // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]
-  uint64_t* afull_bar = tmem_empty_bar + 2;           // [MAX_A_STAGES]
+  uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;   // [MAX_ACC]
+  uint64_t* tmem_empty_bar = tmem_full_bar + MAX_ACC; // [MAX_ACC]
+  uint64_t* afull_bar = tmem_empty_bar + MAX_ACC;     // [MAX_A_STAGES]
   uint64_t* aempty_bar = afull_bar + MAX_A_STAGES;    // [MAX_A_STAGES]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aempty_bar + MAX_A_STAGES);
   float* s_ss = reinterpret_cast<float*>(aux + 512);
@@ -482,7 +484,7 @@ conv_gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_b, const 
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < p.acc_stages; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
       ptx::mbar_init(&tmem_empty_bar[a], 8);  // 4 epilogue warps of each CTA
     }
@@ -564,7 +566,7 @@ conv_gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_b, const 
           }
           if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
         }
-        if (++as == 2) { as = 0; aphase ^= 1u; }
+        if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
       }
     }
   } else {
@@ -673,9 +675,9 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
 
   const int stage_bytes = A_TILE_BYTES + block_n * BLOCK_K * 2;
   const long long total_tiles = (long long)n_tiles * m_tiles;
-  const int acc_stride = ((block_n + 31) / 32) * 32;
+  const int acc_stride = block_n == 16 ? 16 : ((block_n + 31) / 32) * 32;
   int tmem_cols = 32;
-  while (tmem_cols < 2 * acc_stride) tmem_cols <<= 1;  // two accumulator stages
+  while (tmem_cols < 2 * acc_stride) tmem_cols <<= 1;  // at least two accumulator stages (more below for narrow layers)
   const int num_kb = ntaps * (Kc / BLOCK_K);
   constexpr size_t AUX_BYTES = 512 + 4096 + 1024;  // barriers, scale/shift staging, 1024-byte alignment slack
 
@@ -781,11 +783,13 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   }
 
   CUtensorMap tm_a, tm_b, tm_abox;
-  int rc = mc_make_tmap_2d_bf16_k(&tm_a, d->d_in, (uint64_t)M_rows, (uint64_t)d->Cin, (uint64_t)d->Cin_ld, BLOCK_M, BLOCK_K);
+  MC_CHECK_ARG(d->in_cols == 0 || (d->in_cols >= d->Cin && d->in_cols <= d->Cin_ld), "mc_conv_fwd: in_cols %d outside [Cin, Cin_ld]", d->in_cols);
+  const uint64_t in_cols = d->in_cols ? (uint64_t)d->in_cols : (uint64_t)d->Cin;
+  int rc = mc_make_tmap_2d_bf16_k(&tm_a, d->d_in, (uint64_t)M_rows, in_cols, (uint64_t)d->Cin_ld, BLOCK_M, BLOCK_K);
   if (rc) return rc;
   tm_abox = tm_a;
   if (share_dx) {
-    rc = mc_make_tmap_2d_bf16_k(&tm_abox, d->d_in, (uint64_t)M_rows, (uint64_t)d->Cin, (uint64_t)d->Cin_ld, A_BOX_ROWS, 64);
+    rc = mc_make_tmap_2d_bf16_k(&tm_abox, d->d_in, (uint64_t)M_rows, in_cols, (uint64_t)d->Cin_ld, A_BOX_ROWS, 64);
     if (rc) return rc;
   }
   // weights: [n_tiles*block_n >= Npad rows (OOB rows zero-filled), ntaps*Kc]
@@ -814,6 +818,26 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
     p.last_ksteps = (rem + 15) / 16;
   }
   p.a_stages = a_stages;
+  // Accumulator stages: two.  More (a narrow one-N-tile layer's tiles are small, the CTA's TMEM share holds up to 8) was
+  // measured on B200 and rejected: no gain on the narrow layers themselves (their epilogue warps, not the hand-back
+  // round trip, set the ~1 us per tile and CTA), and the larger TMEM allocations keep the next kernel's CTAs from
+  // co-residing with this kernel's tail (dense step 2.25 -> 2.35 ms).  MCB200_CONV_ACC=<n> (3..8) enables it for A/B.
+  static int acc_env = -1;
+  if (acc_env < 0) {
+    const char* e = getenv("MCB200_CONV_ACC");
+    acc_env = e ? atoi(e) : 0;
+  }
+  int acc_stages = 2;
+  if (n_tiles == 1 && !use_pair && acc_env > 2) {
+    int budget = ctas == 1 ? 512 : (ctas == 2 ? 256 : 128);
+    acc_stages = budget / acc_stride;
+    if (acc_stages > MAX_ACC) acc_stages = MAX_ACC;
+    if (acc_stages > acc_env) acc_stages = acc_env;
+    if (acc_stages < 2) acc_stages = 2;
+    tmem_cols = 32;
+    while (tmem_cols < acc_stages * acc_stride) tmem_cols <<= 1;
+  }
+  p.acc_stages = acc_stages;
   p.acc_stride = acc_stride;
   p.tmem_cols = tmem_cols;
   p.m_tiles = m_tiles;
@@ -829,6 +853,10 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
 
   if (use_pair) {
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(block_n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    p.acc_stages = 2;
+    p.acc_stride = ((block_n + 31) / 32) * 32;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < 2 * p.acc_stride) p.tmem_cols <<= 1;
     static int max_clusters = -1;
     if (max_clusters < 0) {
       MC_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -17,6 +17,7 @@ Activation layout between layers is PNHWC bf16 (include/mcb200.h).  There is no 
 library, a CPU tensor or an unsupported cfg raises.
 """
 import ctypes
+import os
 
 import torch
 import torch.nn as nn
@@ -26,6 +27,21 @@ from . import _lib
 
 def _round_up(x, m):
     return (x + m - 1) // m * m
+
+
+def _pitch(n):
+    """Row pitch (channels) of a PNHWC activation with n physical channels.  TMA takes its fast path only for boxes that
+    lie wholly inside the tensor, and a consumer's k-block is 32 (<= 32 channels) or 64 wide — so the pitch is rounded up
+    to that width where it costs little (<= 32 channels, or <= 25 % growth) and the whole pitch is exposed to the
+    consumer's tensor map (mc_conv_desc.in_cols).  The extra columns are never written: they stay the zeros the buffer was
+    created with.  <= 16 channels keep the 8/16 pitch the im2col kernel expects."""
+    ld = _round_up(n, 8)
+    if n <= 16 or os.environ.get('MCB200_PITCH', '1') == '0':  # (A/B switch)
+        return ld
+    if n <= 32:
+        return 32
+    full = _round_up(n, 64)
+    return full if full * 4 <= ld * 5 else ld
 
 
 class _TensorRef(object):
@@ -146,8 +162,8 @@ class CompiledDarknet(object):
                     raise NotImplementedError("maxpool size=%s stride=%s" % (block['size'], block['stride']))
                 src = cur
                 Ho, Wo = src.H // 2, src.W // 2
-                ld = _round_up(src.c_phys, 8)
-                bid = self._new_buf(Ho, Wo, ld)
+                ld = _pitch(src.c_phys)
+                bid = self._new_buf(Ho, Wo, ld, zero_init=True)
                 self.ops.append(dict(kind='pool', src=src, dst_buf=bid, C=src.c_phys, name='pool@%d' % ind))
                 cur = _TensorRef(bid, Ho, Wo, src.c_orig, list(src.colsrc), src.const)
                 cur_hw = (Ho, Wo)
@@ -295,7 +311,7 @@ class CompiledDarknet(object):
             wfull = torch.zeros(nb_pad, kpad, device=dev)
             wfull[:, :wexp.shape[1]] = wexp
             Ho, Wo = (H // 2, W // 2) if pool else (H, W)
-            ld = _round_up(n_phys, 8)
+            ld = _pitch(n_phys)
             bid = self._new_buf(Ho, Wo, ld, zero_init=True)  # pad line/column stay zero: the kernel never writes them
             n_sc = max(_round_up(npos, 16), 16)
             sc2 = torch.zeros(n_sc, device=dev)
@@ -309,7 +325,7 @@ class CompiledDarknet(object):
         if first and plain_dst and self.lib.mc_conv_direct_supported(c_phys_in, n_phys, k) == 1:
             wd = gathered_fp32().reshape(n_phys, c_phys_in, taps)
             Ho, Wo = (H // 2, W // 2) if pool else (H, W)
-            ld = _round_up(n_phys, 8)
+            ld = _pitch(n_phys)
             bid = self._new_buf(Ho, Wo, ld, zero_init=True)
             self.ops.append(dict(kind='direct', src=src, w=wd.contiguous(), scale=scale_p, shift=shift_p, dst_buf=bid,
                                  N=n_phys, Cin=c_phys_in, H=H, W=W, ld=ld, pool=pool, ksize=k, leaky=int(leaky),
@@ -364,7 +380,7 @@ class CompiledDarknet(object):
             st['parts'][slot] = out
             st['pending'].append((op, slot))
         else:
-            ld = _round_up(n_phys, 8)
+            ld = _pitch(n_phys)
             bid = self._new_buf(H, W, ld)
             op.update(epi=_lib.MC_EPI_PNHWC, dst_buf=bid, ldc=ld, ch_off=0)
             out = _TensorRef(bid, H, W, O, out_colsrc, const_out)
@@ -376,7 +392,7 @@ class CompiledDarknet(object):
                 if (p0.H, p0.W) != (p1.H, p1.W):
                     raise NotImplementedError("concat of different resolutions")
                 off1 = _round_up(p0.c_phys, 8)  # 16-byte aligned slice start -> vector stores in the epilogue
-                ld = _round_up(off1 + p1.c_phys, 8)
+                ld = _pitch(off1 + p1.c_phys)
                 st['buf_id'] = self._new_buf(p0.H, p0.W, ld, zero_init=True)
                 for pop, slot in st['pending']:
                     pop.update(dst_buf=st['buf_id'], ldc=ld, ch_off=0 if slot == 0 else off1)
@@ -503,6 +519,7 @@ class CompiledDarknet(object):
                     d.d_out = bufs[op['dst_buf']].data_ptr()
                     d.B, d.H, d.W = B, op['H'], op['W']
                     d.Cin, d.Cin_ld = op['Cin'], sb.ld
+                    d.in_cols = sb.ld - s.ch_off  # the rest of the row: pad channels (zero) / a neighbouring slice (finite)
                     d.N, d.Npad = op['N'], op['Npad']
                     d.ksize, d.leaky, d.epi_mode = op['ksize'], op['leaky'], op['epi']
                     d.ldc, d.ch_off = op['ldc'], op['ch_off']

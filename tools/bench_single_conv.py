@@ -12,7 +12,8 @@ for i in range(0, len(args), 6):
     B, C, H, W, O, k = args[i:i + 6]
     conv = mc.MaskedConv2d(C, O, k, 1, (k - 1) // 2, bias=False).to(dev)
     lib = _lib.load()
-    ld_in, Kc, Npad, ld_out = (C + 7) // 8 * 8, (C + 63) // 64 * 64, (O + 15) // 16 * 16, (O + 7) // 8 * 8
+    LDM = int(os.environ.get('LD_MULT', '8'))
+    ld_in, Kc, Npad, ld_out = (C + LDM - 1) // LDM * LDM, (C + 63) // 64 * 64, (O + 15) // 16 * 16, (O + 7) // 8 * 8
     rows = B * (H + 1) * (W + 1)
     xin = torch.randn(rows, ld_in, device=dev).to(torch.bfloat16)
     wpack = torch.empty(Npad, k * k * Kc, dtype=torch.bfloat16, device=dev)
@@ -36,5 +37,5 @@ for i in range(0, len(args), 6):
         ts.append(e0.elapsed_time(e1) / 5 * 1e3)
     info = (ctypes.c_int * 8)()
     lib.mc_conv_last_plan(info)
-    out.append(dict(shape=[B, C, H, W, O, k], us=round(statistics.median(ts[2:]), 1), plan=list(info)))
+    out.append(dict(ld_in=ld_in, shape=[B, C, H, W, O, k], us=round(statistics.median(ts[2:]), 1), plan=list(info)))
 print(json.dumps(out))
