@@ -41,6 +41,8 @@ struct ConvKParams {
   int Wp, Hp, W, H;  // Wp = W+1, Hp = H+1
   int block_n, stages, tmem_cols, acc_stride;  // acc_stride: TMEM columns between accumulator stages
   int acc_stages;  // accumulator stages: the MMA issuer runs this many tiles ahead of the epilogue
+  int out_pitch;   // > 0: PNHWC epilogue stages each warp's 32 rows in shared memory (row pitch in bytes) and writes them out coalesced
+  unsigned int wp_mul, wp_shr, hp_mul, hp_shr;  // magic-number division by Wp and Hp (row -> x, y, b)
   int last_ksteps;  // UMMA K steps (16 channels) that hold real channels in the LAST channel block of a tap
   int b_resident;   // share_dx only: all weight tiles stay in shared memory for the whole launch (one N tile, small K)
   int share_dx, a_stages;  // 3x3 only: one A box (136 rows) serves the three dx taps of a filter row; separate A / B rings
@@ -113,14 +115,31 @@ __device__ __forceinline__ void store16(const ConvKParams& p, const float (&v)[1
   }
 }
 
+// 16 fp32 -> 16 bf16 -> two 16-byte shared-memory stores
+__device__ __forceinline__ void pack16_to_smem(const float (&v)[16], uint8_t* dst) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[g * 8 + 0], v[g * 8 + 1]);
+    __nv_bfloat162 h1 = __floats2bfloat162_rn(v[g * 8 + 2], v[g * 8 + 3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[g * 8 + 4], v[g * 8 + 5]);
+    __nv_bfloat162 h3 = __floats2bfloat162_rn(v[g * 8 + 6], v[g * 8 + 7]);
+    uint4 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&h0);
+    pk.y = *reinterpret_cast<uint32_t*>(&h1);
+    pk.z = *reinterpret_cast<uint32_t*>(&h2);
+    pk.w = *reinterpret_cast<uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(dst + g * 16) = pk;
+  }
+}
+
 // Epilogue warps (threads 64..191): per tile, stage the tile's scale/shift in shared memory (double-buffered with
 // the accumulator stage, one named barrier per tile), then drain the accumulator 32 columns at a time.
 // PAIR (CTA-pair kernel): `tile` counts (m-tile pair, n-tile) units of the cluster, this CTA owns m-tile 2*pair + rank,
 // and the accumulator stage is handed back on the LEADER CTA's barrier (the MMA issuer waits for both epilogues).
 template <int MODE, bool LEAKY, bool PAIR = false>
 __device__ __forceinline__ void epilogue_loop(const ConvKParams& p, uint32_t tmem_base, uint64_t* tmem_full_bar,
-                                              uint64_t* tmem_empty_bar, float* s_ss, int tile0 = -1, int tile_step = 0,
-                                              int total_units = 0, int pair_rank = 0) {
+                                              uint64_t* tmem_empty_bar, float* s_ss, uint8_t* s_out = nullptr,
+                                              int tile0 = -1, int tile_step = 0, int total_units = 0, int pair_rank = 0) {
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int et = threadIdx.x - 64;   // 0..127
@@ -154,10 +173,10 @@ __device__ __forceinline__ void epilogue_loop(const ConvKParams& p, uint32_t tme
       }
     }
     const int row = m0 + quarter * 32 + lane;
-    const int x = row % p.Wp;
-    const int t = row / p.Wp;
-    const int y = t % p.Hp;
-    const int b = t / p.Hp;
+    const int t = (int)(__umulhi((unsigned int)row, p.wp_mul) >> p.wp_shr);  // row / Wp (magic-number division)
+    const int x = row - t * p.Wp;
+    const int b = (int)(__umulhi((unsigned int)t, p.hp_mul) >> p.hp_shr);    // t / Hp
+    const int y = t - b * p.Hp;
     const bool in_buf = row < p.M_rows;
     const bool interior = in_buf && (x < p.W) && (y < p.H);
     long long out_row_base = 0;
@@ -179,6 +198,56 @@ __device__ __forceinline__ void epilogue_loop(const ConvKParams& p, uint32_t tme
     ptx::mbar_wait(&tmem_full_bar[as], aphase);
     ptx::tc_fence_after();
     const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.acc_stride);
+
+    if (MODE == MC_EPI_PNHWC && s_out != nullptr) {
+      // Staged store: a thread owns one output ROW, so direct stores are 16-byte pieces one row pitch apart (32 half-
+      // filled sectors per warp instruction: measured ~38 cycles per output column and tile).  Instead the warp parks
+      // its 32 rows x block_n bf16 in shared memory (pitch +16 B: conflict-free), hands the TMEM stage back at once,
+      // and writes the rows out with consecutive lanes on consecutive 16-byte chunks.
+      const int pitch = p.out_pitch;
+      uint8_t* wbuf = s_out + (size_t)quarter * 32 * pitch;
+      uint8_t* mine = wbuf + (size_t)lane * pitch;
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        uint32_t r0[16], r1[16];
+        const bool two = c0 + 16 < p.block_n;
+        ptx::tmem_ld_32x32b_x16(taddr_row + (uint32_t)c0, r0);
+        if (two) ptx::tmem_ld_32x32b_x16(taddr_row + (uint32_t)(c0 + 16), r1);
+        ptx::tmem_ld_wait();
+        float v[16];
+        scale_act16<LEAKY>(r0, sc + c0, sh + c0, interior, v);
+        pack16_to_smem(v, mine + c0 * 2);
+        if (two) {
+          scale_act16<LEAKY>(r1, sc + c0 + 16, sh + c0 + 16, interior, v);
+          pack16_to_smem(v, mine + (c0 + 16) * 2);
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR) ptx::mbar_arrive_leader(&tmem_empty_bar[as]);
+        else ptx::mbar_arrive(&tmem_empty_bar[as]);
+      }
+      if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
+      // columns [n0, n0 + cols_w): whole 8-groups up to the last one that holds a real channel (zeros beyond N)
+      int cols_w = ((p.N - n0 + 7) >> 3) << 3;
+      if (cols_w > p.block_n) cols_w = p.block_n;
+      if (cols_w > 0) {
+        const int cpr = cols_w >> 3;  // 16-byte chunks per row
+        int r = lane / cpr, c = lane - r * cpr;
+        const int dr = 32 / cpr, dc = 32 - dr * cpr;
+        const int row0 = m0 + quarter * 32;
+        __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + p.ch_off + n0;
+        while (r < 32) {
+          if (row0 + r < p.M_rows)
+            *reinterpret_cast<uint4*>(obase + (long long)(row0 + r) * p.ldc + c * 8) =
+                *reinterpret_cast<const uint4*>(wbuf + (size_t)r * pitch + c * 16);
+          r += dr; c += dc;
+          if (c >= cpr) { c -= cpr; ++r; }
+        }
+      }
+      __syncwarp();  // wbuf is rewritten by the next tile
+      continue;
+    }
 
     for (int c0 = 0; c0 < p.block_n; c0 += 32) {
       uint32_t r0[16], r1[16];
@@ -239,6 +308,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   uint64_t* aempty_bar = afull_bar + MAX_A_STAGES;    // [MAX_A_STAGES]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aempty_bar + MAX_A_STAGES);
   float* s_ss = reinterpret_cast<float*>(aux + 512);  // [2 acc stages][scale|shift][256]
+  uint8_t* s_out = aux + 512 + 4096;                  // staged epilogue: [4 warps][32 rows][out_pitch]
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -423,8 +493,8 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   } else {
     // ===================== epilogue: warps 2..5 =====================
     if (p.epi_mode == MC_EPI_PNHWC) {
-      if (p.leaky) epilogue_loop<MC_EPI_PNHWC, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss);
-      else epilogue_loop<MC_EPI_PNHWC, false>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss);
+      if (p.leaky) epilogue_loop<MC_EPI_PNHWC, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, p.out_pitch ? s_out : nullptr);
+      else epilogue_loop<MC_EPI_PNHWC, false>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, p.out_pitch ? s_out : nullptr);
     } else if (p.epi_mode == MC_EPI_REORG2) {
       if (p.leaky) epilogue_loop<MC_EPI_REORG2, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss);
       else epilogue_loop<MC_EPI_REORG2, false>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss);
@@ -572,14 +642,14 @@ conv_gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_b, const 
   } else {
     // ===================== epilogue: warps 2..5 of both CTAs =====================
     if (p.epi_mode == MC_EPI_PNHWC) {
-      if (p.leaky) epilogue_loop<MC_EPI_PNHWC, true, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, total_units, rank);
-      else epilogue_loop<MC_EPI_PNHWC, false, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, total_units, rank);
+      if (p.leaky) epilogue_loop<MC_EPI_PNHWC, true, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, nullptr, cluster_id, num_clusters, total_units, rank);
+      else epilogue_loop<MC_EPI_PNHWC, false, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, nullptr, cluster_id, num_clusters, total_units, rank);
     } else if (p.epi_mode == MC_EPI_REORG2) {
-      if (p.leaky) epilogue_loop<MC_EPI_REORG2, true, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, total_units, rank);
-      else epilogue_loop<MC_EPI_REORG2, false, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, total_units, rank);
+      if (p.leaky) epilogue_loop<MC_EPI_REORG2, true, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, nullptr, cluster_id, num_clusters, total_units, rank);
+      else epilogue_loop<MC_EPI_REORG2, false, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, nullptr, cluster_id, num_clusters, total_units, rank);
     } else {
-      if (p.leaky) epilogue_loop<MC_EPI_NCHW_F32, true, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, total_units, rank);
-      else epilogue_loop<MC_EPI_NCHW_F32, false, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, total_units, rank);
+      if (p.leaky) epilogue_loop<MC_EPI_NCHW_F32, true, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, nullptr, cluster_id, num_clusters, total_units, rank);
+      else epilogue_loop<MC_EPI_NCHW_F32, false, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, nullptr, cluster_id, num_clusters, total_units, rank);
     }
   }
 
@@ -695,15 +765,27 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
     res_env = (e && e[0] == '1') ? 1 : 0;
   }
   const int b_resident = (res_env && share_dx && n_tiles == 1 && d->stages <= 0 && b_res_bytes <= 112 * 1024) ? 1 : 0;
+  // staged epilogue (PNHWC, tiles up to 128 wide): 128 rows x (block_n bf16 + 16 B) of shared memory
+  static int stage_env = -1;  // MCB200_CONV_STAGE_OUT=0 disables (A/B switch)
+  if (stage_env < 0) {
+    const char* e = getenv("MCB200_CONV_STAGE_OUT");
+    stage_env = (e && e[0] == '0') ? 0 : 1;
+  }
+  // (measured: tiles 32..96 wide gain — dense conv2 396 -> 300 us, conv4' 60 -> 54, shrunk conv8 33 -> 29; 128-wide tiles
+  //  lose smem ring depth to the 34 KB staging buffer (133 -> 154 us) and 16-wide rows are two stores either way)
+  const bool stage_out = stage_env && d->epi_mode == MC_EPI_PNHWC && block_n >= 32 && block_n <= 96 &&
+                         ((d->ldc | d->ch_off) & 7) == 0;
+  const int out_pitch = stage_out ? block_n * 2 + 16 : 0;
+  const size_t out_stage_bytes = (size_t)128 * out_pitch;
   auto plan_ring = [&](int ctas, int* st, int* ast, size_t* bytes) -> bool {
-    const long long cap = (ctas == 1 ? 204 * 1024 : (227 * 1024) / ctas - 1024 - (long long)AUX_BYTES);
+    const long long cap = (ctas == 1 ? 204 * 1024 : (227 * 1024) / ctas - 1024 - (long long)AUX_BYTES) - (long long)out_stage_bytes;
     if (b_resident) {
       // the activation ring is the only pipeline left: as deep as the smem beside the weights allows (a tile is 3 boxes)
       long long a = (cap - (long long)b_res_bytes) / A_BOX_STRIDE;
       if (a > MAX_A_STAGES) a = MAX_A_STAGES;
       if (a < (ctas == 1 ? 3 : 2)) return false;
       *st = 1; *ast = (int)a;
-      *bytes = (size_t)a * A_BOX_STRIDE + b_res_bytes + AUX_BYTES;
+      *bytes = (size_t)a * A_BOX_STRIDE + b_res_bytes + AUX_BYTES + out_stage_bytes;
       return true;
     }
     if (share_dx) {
@@ -713,14 +795,14 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
       if (stg > MAX_STAGES) stg = MAX_STAGES;
       if (stg < 3) return false;
       *st = (int)stg; *ast = a;
-      *bytes = (size_t)a * A_BOX_STRIDE + (size_t)stg * b_bytes + AUX_BYTES;
+      *bytes = (size_t)a * A_BOX_STRIDE + (size_t)stg * b_bytes + AUX_BYTES + out_stage_bytes;
     } else {
       long long stg = cap / stage_bytes;
       if (stg > MAX_STAGES) stg = MAX_STAGES;
       if (stg > num_kb * 4) stg = num_kb * 4;  // a ring deeper than four tiles' worth of k-blocks buys nothing
       if (stg < (ctas == 1 ? 1 : 3)) return false;
       *st = (int)stg; *ast = 0;
-      *bytes = (size_t)stg * stage_bytes + AUX_BYTES;
+      *bytes = (size_t)stg * stage_bytes + AUX_BYTES + out_stage_bytes;
     }
     return true;
   };
@@ -756,10 +838,10 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
     if (share_dx) {
       a_stages = DEF_A_STAGES;
       MC_CHECK_ARG(stages >= 2 && stages <= MAX_STAGES, "mc_conv_fwd: stages %d invalid", stages);
-      smem_bytes = (size_t)a_stages * A_BOX_STRIDE + (size_t)stages * block_n * 128 + AUX_BYTES;
+      smem_bytes = (size_t)a_stages * A_BOX_STRIDE + (size_t)stages * block_n * 128 + AUX_BYTES + out_stage_bytes;
     } else {
       MC_CHECK_ARG(stages >= 1 && stages <= MAX_STAGES, "mc_conv_fwd: stages %d invalid", stages);
-      smem_bytes = (size_t)stages * stage_bytes + AUX_BYTES;
+      smem_bytes = (size_t)stages * stage_bytes + AUX_BYTES + out_stage_bytes;
     }
   }
   MC_CHECK_ARG(smem_bytes <= 227 * 1024, "mc_conv_fwd: smem %zu too large", smem_bytes);
@@ -838,6 +920,18 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
     while (tmem_cols < acc_stages * acc_stride) tmem_cols <<= 1;
   }
   p.acc_stages = acc_stages;
+  p.out_pitch = use_pair ? 0 : out_pitch;
+  {
+    auto magic = [](unsigned int dv, unsigned int* mul, unsigned int* shr) {
+      unsigned int l = 0;
+      while ((1u << l) < dv) ++l;
+      const unsigned long long pw = 31ull + l;
+      *mul = (unsigned int)((((unsigned long long)1 << pw) + dv - 1) / dv);
+      *shr = (unsigned int)(pw - 32);
+    };
+    magic((unsigned int)(d->W + 1), &p.wp_mul, &p.wp_shr);
+    magic((unsigned int)(d->H + 1), &p.hp_mul, &p.hp_shr);
+  }
   p.acc_stride = acc_stride;
   p.tmem_cols = tmem_cols;
   p.m_tiles = m_tiles;
