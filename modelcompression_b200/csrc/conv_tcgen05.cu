@@ -297,7 +297,12 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   }
   uint8_t* tiles = smem;
   // share_dx: [a_stages x A box (18 KB pitch)] [stages x B tile]; else [stages x (A | B)]
-  uint8_t* b_ring = tiles + (size_t)p.a_stages * A_BOX_STRIDE;
+  // shared activation box: 136 rows of one k-block row (128 B with 64-wide k-blocks / 128-byte swizzle, 64 B with 32-wide
+  // k-blocks / 64-byte swizzle); ring pitch 18 KB / 9 KB keeps every box 1024-byte aligned
+  const uint32_t a_row_bytes = (uint32_t)p.block_k * 2u;
+  const uint32_t a_box_bytes = (uint32_t)A_BOX_ROWS * a_row_bytes;
+  const uint32_t a_box_stride = p.block_k == 64 ? (uint32_t)A_BOX_STRIDE : (uint32_t)A_BOX_STRIDE / 2u;
+  uint8_t* b_ring = tiles + (size_t)p.a_stages * a_box_stride;
   uint8_t* aux = p.share_dx ? b_ring + (size_t)(p.b_resident ? p.num_kb : p.stages) * b_tile_bytes
                             : tiles + (size_t)p.stages * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
@@ -351,7 +356,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       if (p.b_resident) {  // every weight tile of the layer, once: [num_kb][block_n rows x 128 B]
         ptx::mbar_arrive_expect_tx(&full_bar[0], (uint32_t)p.num_kb * b_tile_bytes);
         for (int kb = 0; kb < p.num_kb; ++kb)
-          ptx::tma_load_2d(b_ring + (size_t)kb * b_tile_bytes, &tmap_b, &full_bar[0], kb * 64, 0);
+          ptx::tma_load_2d(b_ring + (size_t)kb * b_tile_bytes, &tmap_b, &full_bar[0], kb * p.block_k, 0);
       }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n0 = (tile % p.n_tiles) * p.block_n;
@@ -359,8 +364,8 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         for (int g = 0; g < 3 * p.kb_per_tap; ++g) {
           const int dy = g / p.kb_per_tap, cb = g - dy * p.kb_per_tap;
           ptx::mbar_wait(&aempty_bar[sa], pha ^ 1u);
-          ptx::mbar_arrive_expect_tx(&afull_bar[sa], A_BOX_BYTES);
-          ptx::tma_load_2d(tiles + (size_t)sa * A_BOX_STRIDE, &tmap_abox, &afull_bar[sa], cb * 64,
+          ptx::mbar_arrive_expect_tx(&afull_bar[sa], a_box_bytes);
+          ptx::tma_load_2d(tiles + (size_t)sa * a_box_stride, &tmap_abox, &afull_bar[sa], cb * p.block_k,
                            m0 + (dy - 1) * p.Wp - 1);
           if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
           if (p.b_resident) continue;
@@ -368,7 +373,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const int kb = (dy * 3 + dx) * p.kb_per_tap + cb;
             ptx::mbar_wait(&empty_bar[s], phase ^ 1u);
             ptx::mbar_arrive_expect_tx(&full_bar[s], b_tile_bytes);
-            ptx::tma_load_2d(b_ring + (size_t)s * b_tile_bytes, &tmap_b, &full_bar[s], kb * 64, n0);
+            ptx::tma_load_2d(b_ring + (size_t)s * b_tile_bytes, &tmap_b, &full_bar[s], kb * p.block_k, n0);
             if (++s == p.stages) { s = 0; phase ^= 1u; }
           }
         }
@@ -411,9 +416,9 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         for (int g = 0; g < 3 * p.kb_per_tap; ++g) {
           const int dy = g / p.kb_per_tap, cb = g - dy * p.kb_per_tap;
           // K steps beyond the layer's real channels multiply TMA zero fill by zero weights: not issued
-          const int nk = (cb == p.kb_per_tap - 1) ? p.last_ksteps : 4;
+          const int nk = (cb == p.kb_per_tap - 1) ? p.last_ksteps : (int)(a_row_bytes >> 5);
           ptx::mbar_wait(&afull_bar[sa], pha);
-          const uint32_t a_addr = ptx::smem_u32(tiles + (size_t)sa * A_BOX_STRIDE);
+          const uint32_t a_addr = ptx::smem_u32(tiles + (size_t)sa * a_box_stride);
           for (int dx = 0; dx < 3; ++dx) {
             uint32_t b_addr;
             if (p.b_resident) {
@@ -428,8 +433,11 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             // 1024-byte swizzle pattern; measured on B200: the tensor core applies the 128-byte swizzle to the absolute
             // shared-memory address (as TMA did when it wrote the box), so the descriptor's base-offset field must stay
             // 0 — setting it to dx (or 8-dx) reads garbage (tools/debug_share.py)
-            const uint64_t adesc = ptx::make_sw128_kmajor_desc(a_addr + (uint32_t)dx * 128u);
-            const uint64_t bdesc = ptx::make_sw128_kmajor_desc(b_addr);
+            // (32-wide k-blocks: the same holds for the 64-byte swizzle — rows of 64 B, window dx starts dx * 64 B in)
+            const bool k64 = p.block_k == 64;
+            const uint64_t adesc = k64 ? ptx::make_sw128_kmajor_desc(a_addr + (uint32_t)dx * 128u)
+                                       : ptx::make_sw64_kmajor_desc(a_addr + (uint32_t)dx * 64u);
+            const uint64_t bdesc = k64 ? ptx::make_sw128_kmajor_desc(b_addr) : ptx::make_sw64_kmajor_desc(b_addr);
             if (ptx::elect_one()) {
               if (nk == 4) {  // (compile-time trip count: this issue loop is on the critical path)
 #pragma unroll
@@ -722,12 +730,17 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   const int m_tiles = (int)((M_rows + BLOCK_M - 1) / BLOCK_M);
 
   // 3x3 with 64-wide k-blocks: share one activation box among the three dx taps (MCB200_SHARE_DX=0 disables)
-  static int share_env = -1;
+  static int share_env = -1, share_env32 = 1;
   if (share_env < 0) {
     const char* e = getenv("MCB200_SHARE_DX");
     share_env = (e && e[0] == '0') ? 0 : 1;
+    share_env32 = (e && e[0] == '2') ? 0 : 1;
   }
-  const int share_dx = (d->ksize == 3 && BLOCK_K == 64 && share_env) ? 1 : 0;
+  // (MCB200_SHARE_DX=2 restricts the shared box to 64-wide k-blocks, the state before the 64-byte-swizzle variant)
+  // 32-wide k-blocks share the box only on long, feed-bound launches (dense conv2: 21,841 tiles, 306 -> 262 us); short
+  // ones lose a little to the two-ring pipeline (shrunk conv13, 365 tiles: 18 -> 21 us)
+  const int share_dx = (d->ksize == 3 && share_env && (BLOCK_K == 64 || (share_env32 && m_tiles >= 2048))) ? 1 : 0;
+  const int a_box_stride = BLOCK_K == 64 ? A_BOX_STRIDE : A_BOX_STRIDE / 2;
   int block_n = d->block_n;
   // (the operand-feed term keeps the un-shared 16 KB A tile: with the shared-box figure the model picks narrower tiles
   //  that measured 4 % slower end to end on B200)
@@ -754,7 +767,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   // smem ring of one CTA when `ctas` CTAs share an SM (each CTA also costs 1 KB of reserved shared memory)
   // resident weights: one N tile and all taps' weight tiles fit beside the activation ring -> loaded once per CTA
   // (narrow 3x3 layers: the per-tile weight re-load is otherwise as much TMA traffic as the activations)
-  const size_t b_res_bytes = (size_t)num_kb * block_n * 128;
+  const size_t b_res_bytes = (size_t)num_kb * block_n * BLOCK_K * 2;
   // OFF by default (MCB200_CONV_RESIDENT=1 enables): measured on B200 it loses to the weight ring on every narrow
   // 3x3 shape tried (64->64 @52x52: 37 us vs 25 us; 48->32 @104x104: 71 vs 58; 40->80 @52x52: 41 vs 33) because the
   // resident tiles leave room for ONE CTA per SM, and three small CTAs per SM hide the per-tile latency chain better
@@ -781,21 +794,21 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
     const long long cap = (ctas == 1 ? 204 * 1024 : (227 * 1024) / ctas - 1024 - (long long)AUX_BYTES) - (long long)out_stage_bytes;
     if (b_resident) {
       // the activation ring is the only pipeline left: as deep as the smem beside the weights allows (a tile is 3 boxes)
-      long long a = (cap - (long long)b_res_bytes) / A_BOX_STRIDE;
+      long long a = (cap - (long long)b_res_bytes) / a_box_stride;
       if (a > MAX_A_STAGES) a = MAX_A_STAGES;
       if (a < (ctas == 1 ? 3 : 2)) return false;
       *st = 1; *ast = (int)a;
-      *bytes = (size_t)a * A_BOX_STRIDE + b_res_bytes + AUX_BYTES + out_stage_bytes;
+      *bytes = (size_t)a * a_box_stride + b_res_bytes + AUX_BYTES + out_stage_bytes;
       return true;
     }
     if (share_dx) {
-      const int b_bytes = block_n * 128;
+      const int b_bytes = block_n * BLOCK_K * 2;
       int a = ctas == 1 ? DEF_A_STAGES : 2;
-      long long stg = (cap - (long long)a * A_BOX_STRIDE) / b_bytes;
+      long long stg = (cap - (long long)a * a_box_stride) / b_bytes;
       if (stg > MAX_STAGES) stg = MAX_STAGES;
       if (stg < 3) return false;
       *st = (int)stg; *ast = a;
-      *bytes = (size_t)a * A_BOX_STRIDE + (size_t)stg * b_bytes + AUX_BYTES + out_stage_bytes;
+      *bytes = (size_t)a * a_box_stride + (size_t)stg * b_bytes + AUX_BYTES + out_stage_bytes;
     } else {
       long long stg = cap / stage_bytes;
       if (stg > MAX_STAGES) stg = MAX_STAGES;
@@ -838,7 +851,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
     if (share_dx) {
       a_stages = DEF_A_STAGES;
       MC_CHECK_ARG(stages >= 2 && stages <= MAX_STAGES, "mc_conv_fwd: stages %d invalid", stages);
-      smem_bytes = (size_t)a_stages * A_BOX_STRIDE + (size_t)stages * block_n * 128 + AUX_BYTES + out_stage_bytes;
+      smem_bytes = (size_t)a_stages * a_box_stride + (size_t)stages * block_n * BLOCK_K * 2 + AUX_BYTES + out_stage_bytes;
     } else {
       MC_CHECK_ARG(stages >= 1 && stages <= MAX_STAGES, "mc_conv_fwd: stages %d invalid", stages);
       smem_bytes = (size_t)stages * stage_bytes + AUX_BYTES + out_stage_bytes;
@@ -853,7 +866,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
     pair_env = e ? atoi(e) : 1;
     if (pair_env < 0 || pair_env > 2) pair_env = 1;
   }
-  const bool pair_legal = share_dx && d->stages <= 0 && (block_n % 16) == 0 && block_n >= 64 && m_tiles >= 2;
+  const bool pair_legal = share_dx && BLOCK_K == 64 && d->stages <= 0 && (block_n % 16) == 0 && block_n >= 64 && m_tiles >= 2;
   const bool use_pair = pair_legal && (pair_env == 2 || (pair_env == 1 && block_n >= 192 && num_kb >= 36));
   if (use_pair) {
     ctas = 1;
@@ -871,7 +884,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   if (rc) return rc;
   tm_abox = tm_a;
   if (share_dx) {
-    rc = mc_make_tmap_2d_bf16_k(&tm_abox, d->d_in, (uint64_t)M_rows, in_cols, (uint64_t)d->Cin_ld, A_BOX_ROWS, 64);
+    rc = mc_make_tmap_2d_bf16_k(&tm_abox, d->d_in, (uint64_t)M_rows, in_cols, (uint64_t)d->Cin_ld, A_BOX_ROWS, BLOCK_K);
     if (rc) return rc;
   }
   // weights: [n_tiles*block_n >= Npad rows (OOB rows zero-filled), ntaps*Kc]
