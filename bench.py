@@ -415,6 +415,9 @@ def main():
         consumed = [torch.cuda.Event() for _ in range(2)]
         produced = [torch.cuda.Event() for _ in range(2)]
 
+        in_flight = [None, None]
+        d2h_done = [torch.cuda.Event() for _ in range(2)]
+
         def e2e_loop(nsteps):
             with torch.cuda.stream(copy_stream):
                 dev_in[0].copy_(host_in[0], non_blocking=True)
@@ -428,13 +431,20 @@ def main():
                         dev_in[nxt].copy_(host_in[nxt], non_blocking=True)
                         ready[nxt].record(copy_stream)
                 main_stream.wait_event(ready[cur])
+                if in_flight[cur] is not None:
+                    d2h_done[cur].synchronize()  # the copy of two steps ago (finished long since): its block may be reused
+                    in_flight[cur] = None
                 out = model(dev_in[cur])
                 consumed[cur].record(main_stream)
                 produced[cur].record(main_stream)
                 with torch.cuda.stream(out_stream):  # device->host read of the head, off the compute stream
                     out_stream.wait_event(produced[cur])
                     host_out[cur].copy_(out, non_blocking=True)
-                    out.record_stream(out_stream)
+                    d2h_done[cur].record(out_stream)
+                # keep the head alive until the slot is reused two steps later (its copy has long finished by then)
+                # instead of Tensor.record_stream: the allocator's per-malloc event bookkeeping for stream-recorded
+                # blocks cost 0.2-0.9 ms of HOST time per step on some hosts (tools/e2e_probe.py)
+                in_flight[cur] = out
             torch.cuda.synchronize()
 
         # raw host->device rate of this host for the same pinned buffer (the end-to-end loop is bound by it whenever

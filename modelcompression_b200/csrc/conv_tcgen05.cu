@@ -42,6 +42,7 @@ struct ConvKParams {
   int block_n, stages, tmem_cols, acc_stride;  // acc_stride: TMEM columns between accumulator stages
   int acc_stages;  // accumulator stages: the MMA issuer runs this many tiles ahead of the epilogue
   int out_pitch;   // > 0: PNHWC epilogue stages each warp's 32 rows in shared memory (row pitch in bytes) and writes them out coalesced
+  int out_chunk;   // columns staged at a time (<= 64)
   unsigned int wp_mul, wp_shr, hp_mul, hp_shr;  // magic-number division by Wp and Hp (row -> x, y, b)
   int last_ksteps;  // UMMA K steps (16 channels) that hold real channels in the LAST channel block of a tap
   int b_resident;   // share_dx only: all weight tiles stay in shared memory for the whole launch (one N tile, small K)
@@ -204,48 +205,58 @@ __device__ __forceinline__ void epilogue_loop(const ConvKParams& p, uint32_t tme
       // filled sectors per warp instruction: measured ~38 cycles per output column and tile).  Instead the warp parks
       // its 32 rows x block_n bf16 in shared memory (pitch +16 B: conflict-free), hands the TMEM stage back at once,
       // and writes the rows out with consecutive lanes on consecutive 16-byte chunks.
+      // Tiles wider than the staging buffer (64 columns) go through it in 64-column chunks.
       const int pitch = p.out_pitch;
+      const int chunk = p.out_chunk;
       uint8_t* wbuf = s_out + (size_t)quarter * 32 * pitch;
       uint8_t* mine = wbuf + (size_t)lane * pitch;
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-        uint32_t r0[16], r1[16];
-        const bool two = c0 + 16 < p.block_n;
-        ptx::tmem_ld_32x32b_x16(taddr_row + (uint32_t)c0, r0);
-        if (two) ptx::tmem_ld_32x32b_x16(taddr_row + (uint32_t)(c0 + 16), r1);
-        ptx::tmem_ld_wait();
-        float v[16];
-        scale_act16<LEAKY>(r0, sc + c0, sh + c0, interior, v);
-        pack16_to_smem(v, mine + c0 * 2);
-        if (two) {
-          scale_act16<LEAKY>(r1, sc + c0 + 16, sh + c0 + 16, interior, v);
-          pack16_to_smem(v, mine + (c0 + 16) * 2);
+      const int row0 = m0 + quarter * 32;
+      int cols_left = ((p.N - n0 + 7) >> 3) << 3;  // whole 8-groups up to the last one holding a real channel
+      if (cols_left > p.block_n) cols_left = p.block_n;
+      for (int cc = 0; cc < p.block_n; cc += chunk) {
+        const int cw = (p.block_n - cc < chunk) ? p.block_n - cc : chunk;
+        for (int c0 = 0; c0 < cw; c0 += 32) {
+          uint32_t r0[16], r1[16];
+          const bool two = c0 + 16 < cw;
+          ptx::tmem_ld_32x32b_x16(taddr_row + (uint32_t)(cc + c0), r0);
+          if (two) ptx::tmem_ld_32x32b_x16(taddr_row + (uint32_t)(cc + c0 + 16), r1);
+          ptx::tmem_ld_wait();
+          float v[16];
+          scale_act16<LEAKY>(r0, sc + cc + c0, sh + cc + c0, interior, v);
+          pack16_to_smem(v, mine + c0 * 2);
+          if (two) {
+            scale_act16<LEAKY>(r1, sc + cc + c0 + 16, sh + cc + c0 + 16, interior, v);
+            pack16_to_smem(v, mine + (c0 + 16) * 2);
+          }
         }
-      }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (PAIR) ptx::mbar_arrive_leader(&tmem_empty_bar[as]);
-        else ptx::mbar_arrive(&tmem_empty_bar[as]);
+        if (cc + chunk >= p.block_n) {  // last chunk read: hand the TMEM stage back before the copy-out
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR) ptx::mbar_arrive_leader(&tmem_empty_bar[as]);
+            else ptx::mbar_arrive(&tmem_empty_bar[as]);
+          }
+        } else {
+          __syncwarp();
+        }
+        int cols_w = cols_left - cc;
+        if (cols_w > cw) cols_w = cw;
+        if (cols_w > 0) {
+          const int cpr = cols_w >> 3;  // 16-byte chunks per row
+          int r = lane / cpr, c = lane - r * cpr;
+          const int dr = 32 / cpr, dc = 32 - dr * cpr;
+          __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + p.ch_off + n0 + cc;
+          while (r < 32) {
+            if (row0 + r < p.M_rows)
+              *reinterpret_cast<uint4*>(obase + (long long)(row0 + r) * p.ldc + c * 8) =
+                  *reinterpret_cast<const uint4*>(wbuf + (size_t)r * pitch + c * 16);
+            r += dr; c += dc;
+            if (c >= cpr) { c -= cpr; ++r; }
+          }
+        }
+        __syncwarp();  // wbuf is rewritten by the next chunk / tile
       }
       if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
-      // columns [n0, n0 + cols_w): whole 8-groups up to the last one that holds a real channel (zeros beyond N)
-      int cols_w = ((p.N - n0 + 7) >> 3) << 3;
-      if (cols_w > p.block_n) cols_w = p.block_n;
-      if (cols_w > 0) {
-        const int cpr = cols_w >> 3;  // 16-byte chunks per row
-        int r = lane / cpr, c = lane - r * cpr;
-        const int dr = 32 / cpr, dc = 32 - dr * cpr;
-        const int row0 = m0 + quarter * 32;
-        __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + p.ch_off + n0;
-        while (r < 32) {
-          if (row0 + r < p.M_rows)
-            *reinterpret_cast<uint4*>(obase + (long long)(row0 + r) * p.ldc + c * 8) =
-                *reinterpret_cast<const uint4*>(wbuf + (size_t)r * pitch + c * 16);
-          r += dr; c += dc;
-          if (c >= cpr) { c -= cpr; ++r; }
-        }
-      }
-      __syncwarp();  // wbuf is rewritten by the next tile
       continue;
     }
 
@@ -782,13 +793,18 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   static int stage_env = -1;  // MCB200_CONV_STAGE_OUT=0 disables (A/B switch)
   if (stage_env < 0) {
     const char* e = getenv("MCB200_CONV_STAGE_OUT");
-    stage_env = (e && e[0] == '0') ? 0 : 1;
+    stage_env = (e && e[0] == '0') ? 0 : ((e && e[0] == '2') ? 2 : 1);
   }
   // (measured: tiles 32..96 wide gain — dense conv2 396 -> 300 us, conv4' 60 -> 54, shrunk conv8 33 -> 29; 128-wide tiles
   //  lose smem ring depth to the 34 KB staging buffer (133 -> 154 us) and 16-wide rows are two stores either way)
-  const bool stage_out = stage_env && d->epi_mode == MC_EPI_PNHWC && block_n >= 32 && block_n <= 96 &&
+  // Wider tiles go through the buffer in 64-column chunks where it was measured to pay: 3x3 layers at high resolution
+  // (dense conv3/conv5, 128 wide, 5513 tiles: 137 -> 123 us); wide 1x1 layers (conv7: 39 -> 47 us) and the short
+  // launches of the 26x26 / 13x13 stages do not.  MCB200_CONV_STAGE_OUT=2 stages every wide tile (A/B switch).
+  const bool wide_ok = stage_env == 2 || (d->ksize == 3 && m_tiles >= 1024);
+  const bool stage_out = stage_env && d->epi_mode == MC_EPI_PNHWC && block_n >= 32 && (block_n <= 96 || wide_ok) &&
                          ((d->ldc | d->ch_off) & 7) == 0;
-  const int out_pitch = stage_out ? block_n * 2 + 16 : 0;
+  const int out_chunk = block_n <= 96 ? block_n : 64;
+  const int out_pitch = stage_out ? out_chunk * 2 + 16 : 0;
   const size_t out_stage_bytes = (size_t)128 * out_pitch;
   auto plan_ring = [&](int ctas, int* st, int* ast, size_t* bytes) -> bool {
     const long long cap = (ctas == 1 ? 204 * 1024 : (227 * 1024) / ctas - 1024 - (long long)AUX_BYTES) - (long long)out_stage_bytes;
@@ -934,6 +950,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   }
   p.acc_stages = acc_stages;
   p.out_pitch = use_pair ? 0 : out_pitch;
+  p.out_chunk = out_chunk;
   {
     auto magic = [](unsigned int dv, unsigned int* mul, unsigned int* shr) {
       unsigned int l = 0;

@@ -607,7 +607,8 @@ def single_conv_forward(conv, x):
     w = conv.weight.data.float().contiguous()
     mask = conv.mask.to(dev).contiguous() if getattr(conv, 'mask_flag', False) else None
     O = w.shape[0]
-    ld_in, Kc, Npad, ld_out = _round_up(C, 8), _round_up(C, 64), _round_up(O, 16), _round_up(O, 8)
+    kblk = 32 if C <= 32 else 64  # the engine's rule (see _compile_conv)
+    ld_in, Kc, Npad, ld_out = _round_up(C, 8), _round_up(C, kblk), _round_up(O, 16), _round_up(O, 8)
     xin = torch.empty(B * (H + 1) * (W + 1), ld_in, dtype=torch.bfloat16, device=dev)
     wpack = torch.empty(Npad, k * k * Kc, dtype=torch.bfloat16, device=dev)
     scale = torch.zeros(Npad, device=dev)
@@ -627,6 +628,7 @@ def single_conv_forward(conv, x):
                                                             shift.data_ptr(), yb.data_ptr())
         d.B, d.H, d.W, d.Cin, d.Cin_ld, d.N, d.Npad = B, H, W, C, ld_in, O, Npad
         d.ksize, d.leaky, d.epi_mode, d.ldc, d.ch_off, d.block_n, d.stages = k, 0, _lib.MC_EPI_PNHWC, ld_out, 0, 0, 0
+        d.block_k = kblk
         _lib.check(lib.mc_conv_fwd(ctypes.byref(d), s), "mc_conv_fwd")
         _lib.check(lib.mc_unpack_pnhwc(yb.data_ptr(), y.data_ptr(), B, H, W, O, ld_out, 0, s), "mc_unpack_pnhwc")
     return y

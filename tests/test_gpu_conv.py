@@ -80,8 +80,10 @@ def _last_plan():
     (64, 512, 13, 13, 1024, 3, dict(pair=1)),            # wide 3x3 at the bench batch: CTA-pair kernel (cta_group::2)
     (64, 1006, 13, 13, 1018, 3, dict(pair=1)),           # shrunk-net shape: ragged Cin/N, odd channel-block tail
     (33, 600, 13, 13, 512, 3, dict(pair=1)),             # odd number of 128-row tiles (51): last pair half-empty
-    (8, 32, 104, 104, 64, 3, dict(share=1, pair=0)),      # narrow 3x3, Cin 32 in a 64-wide k-block: 2 of 4 K steps issued
-    (8, 16, 52, 52, 72, 3, dict(share=1)),
+    (8, 32, 208, 208, 64, 3, dict(share=1, pair=0, block_k=32)),  # long launch, 32-wide k-blocks: shared box, 64 B swizzle
+    (8, 32, 104, 104, 64, 3, dict(share=0, block_k=32)),  # same layer, short launch: one box per tap
+    (8, 40, 52, 52, 72, 3, dict(share=1, block_k=64)),    # Cin 40 in a 64-wide k-block: 3 of 4 K steps issued
+    (8, 16, 52, 52, 72, 3, dict(block_k=32)),
     (16, 24, 104, 104, 8, 1, dict(pair=0, resident=0)),  # narrow 1x1: several CTAs per SM
     (32, 80, 52, 52, 16, 1, dict(pair=0)),
 ])

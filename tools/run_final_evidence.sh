@@ -1,6 +1,7 @@
 set -x
-# 1. the bench itself (no profiler) -> the numbers; 2. launch list of the same command; 3. ncu --set full of the conv
-# kernels of one eager forward (shrunk net, batch 64): 18 launches (single-CTA + CTA-pair kernels)
+# 0. GPU tests; 1. the bench itself (no profiler) -> the numbers; 2. launch list of the same command; 3. ncu --set full
+# of the conv GEMM kernels of one eager forward (shrunk net, batch 64): 18 launches (single-CTA + CTA-pair kernels)
+python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain_bench_short.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_bench_final.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench_short.log 2>&1
