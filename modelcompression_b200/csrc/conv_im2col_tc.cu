@@ -223,9 +223,29 @@ conv_im2col_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
         for (int r = 0; r < 4; ++r) {
           float v[3][4];
 #pragma unroll
-          for (int c = 0; c < 3; ++c)
+          for (int c = 0; c < 3; ++c) {
+            if constexpr (FIRST == 2) {
+              // uint8 image: the window row's 4 bytes come from two aligned 32-bit loads + a funnel shift (two lanes
+              // share a word: broadcast) instead of 4 byte loads + 4 table look-ups — the LSU data pipe is this
+              // kernel's limiter (ncu), and the byte path made the uint8 kernel slower than the fp32 one.  x/255 is
+              // computed exactly as IEEE division: q0 = a*r, q = fma(fma(-255, q0, a), r, q0) with r = RN(1/255)
+              // (equal to a/255.0f for all 256 byte values — checked exhaustively).
+              const int idx0 = base + (c * PR + r) * PCF;
+              const uint32_t* words = reinterpret_cast<const uint32_t*>(patch_raw);
+              const uint32_t lo = words[idx0 >> 2], hi = words[(idx0 >> 2) + 1];
+              const uint32_t four = __funnelshift_r(lo, hi, (uint32_t)(idx0 & 3) * 8u);
 #pragma unroll
-            for (int sx = 0; sx < 4; ++sx) v[c][sx] = pel(patch_raw, base + (c * PR + r) * PCF + sx);
+              for (int sx = 0; sx < 4; ++sx) {
+                const float a = __uint2float_rn((four >> (8 * sx)) & 0xffu);
+                const float rcp = 0.00392156886f;  // RN(1/255) = 0x3b808081
+                const float q0 = __fmul_rn(a, rcp);
+                v[c][sx] = __fmaf_rn(__fmaf_rn(-255.0f, q0, a), rcp, q0);
+              }
+            } else {
+#pragma unroll
+              for (int sx = 0; sx < 4; ++sx) v[c][sx] = pel(patch_raw, base + (c * PR + r) * PCF + sx);
+            }
+          }
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             __nv_bfloat162 a0 = __floats2bfloat162_rn(v[0][2 * h], v[1][2 * h]);
