@@ -76,4 +76,4 @@ def ncu_summary():
 if __name__ == '__main__':
     launch_summary()
     ncu_summary()
-    shutil.copy(os.path.join(GP, 'bench_final.json'), os.path.join(OUT, 'r1_bench_v7.json'))
+    shutil.copy(os.path.join(GP, 'bench_final.json'), os.path.join(OUT, 'r1_bench_v8.json'))
