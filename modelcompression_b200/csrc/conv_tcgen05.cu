@@ -13,6 +13,7 @@
 // 128-byte swizzle row.  Warp roles: warp0 = TMA producer, warp1 = TMEM owner + MMA issuer (one thread),
 // warps 2..5 = epilogue (TMEM -> regs -> scale/shift/leaky -> bf16/fp32 global stores).
 #include <cuda.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include "common.cuh"
 #include "ptx_sm100.cuh"
@@ -844,6 +845,12 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
     ctas_env = e ? atoi(e) : 0;
     if (ctas_env < 0 || ctas_env > 3) ctas_env = 0;
   }
+  static int min_tiles = -1;  // tiles every CTA must get before another CTA per SM is added (MCB200_CONV_MINTILES, A/B)
+  if (min_tiles < 0) {
+    const char* e = getenv("MCB200_CONV_MINTILES");
+    min_tiles = e ? atoi(e) : 1;  // measured: 1 beats 2 by 0.5 % on the shrunk step (the 365-tile 26x26 layers get 2 CTAs per SM)
+    if (min_tiles < 1) min_tiles = 1;
+  }
   int ctas = 1;
   {
     const int limit = ctas_env ? ctas_env : 3;
@@ -852,7 +859,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
     for (int c = limit; c >= 2 && narrow; --c) {
       int st, ast;
       size_t bytes;
-      if (c * tmem_cols > 512 || total_tiles < 2ll * c * mc_num_sms() || !plan_ring(c, &st, &ast, &bytes)) continue;
+      if (c * tmem_cols > 512 || total_tiles < (long long)min_tiles * c * mc_num_sms() || !plan_ring(c, &st, &ast, &bytes)) continue;
       ctas = c;
       break;
     }
@@ -1018,6 +1025,15 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   }
   const long long max_ctas = (long long)mc_num_sms() * ctas;
   int grid = (int)(total_tiles < max_ctas ? total_tiles : max_ctas);
+  static int trace_env = -1;  // MCB200_CONV_TRACE=1: one line per launch on stderr (tools/bench_layers.py)
+  if (trace_env < 0) {
+    const char* e = getenv("MCB200_CONV_TRACE");
+    trace_env = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (trace_env)
+    fprintf(stderr, "[mc_conv_fwd] %dx%d k%d Cin %d N %d: m_tiles %d block_n %d n_tiles %d kb %d(x%d) ctas %d stages %d/%d share %d stage_out %d grid %d smem %zu\n",
+            d->H, d->W, d->ksize, d->Cin, d->N, m_tiles, block_n, n_tiles, num_kb, BLOCK_K, ctas, stages, a_stages, share_dx,
+            p.out_pitch, grid, smem_bytes);
   g_last_plan[0] = 0; g_last_plan[1] = block_n; g_last_plan[2] = ctas; g_last_plan[3] = p.b_resident;
   g_last_plan[4] = share_dx; g_last_plan[5] = stages; g_last_plan[6] = grid; g_last_plan[7] = BLOCK_K;
   if (ctas >= 3)
