@@ -168,6 +168,11 @@ def run_reference_arm(args, rank):
     import torch
     import modelcompression_b200 as mc
     from oracle import prune_oracle
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 for its workers)
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        pass
     torch.manual_seed(0)
     model = mc.Darknet(mc.write_yolov2_voc_cfg()).eval()
     cw = [p.data.numpy() for p in model.parameters() if p.dim() == 4]
