@@ -199,35 +199,19 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __g
 }
 
 // dW[o][c][tap] = mask[o][c][tap] * sum_split ws[split][tap][o][c]   (PyTorch layout [O, C, kh, kw])
-// Sum the split-K partials ws[split][tap][Opad][Cpad], apply the mask and write dW[O,C,kh,kw].  A thread owns one (o, c):
-// its partial reads are coalesced over c, but its `ntaps` results are consecutive in dW (thread stride = ntaps floats), so
-// they go through a shared-memory tile and are written (and the mask read) with consecutive threads on consecutive floats.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, int nsplit, int ntaps, int Opad,
                                                            int Cpad, int O, int C, const float* __restrict__ mask,
                                                            float* __restrict__ dw, int accumulate) {
-  __shared__ float s_tile[256 * 9];
-  const unsigned int total = (unsigned int)O * (unsigned int)C;  // < 2^31 (host-checked)
-  const size_t tap_stride = (size_t)Opad * Cpad, split_stride = tap_stride * ntaps;
-  for (unsigned int i0 = blockIdx.x * 256u; i0 < total; i0 += gridDim.x * 256u) {
-    const unsigned int i = i0 + threadIdx.x;
-    if (i < total) {
-      const unsigned int o = i / (unsigned int)C, c = i - o * (unsigned int)C;
-      const float* src = ws + (size_t)o * Cpad + c;
-      for (int t = 0; t < ntaps; ++t) {
-        float acc = 0.f;
-        for (int s = 0; s < nsplit; ++s) acc += src[(size_t)s * split_stride + (size_t)t * tap_stride];
-        s_tile[threadIdx.x * ntaps + t] = acc;  // stride ntaps (1 or 9): conflict-free
-      }
+  const long long total = (long long)O * C;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int o = (int)(i / C), c = (int)(i - (long long)o * C);
+    for (int t = 0; t < ntaps; ++t) {
+      float acc = 0.f;
+      for (int s = 0; s < nsplit; ++s) acc += ws[(((size_t)s * ntaps + t) * Opad + o) * Cpad + c];
+      const size_t di = (size_t)i * ntaps + t;
+      if (mask) acc *= mask[di];
+      dw[di] = accumulate ? dw[di] + acc : acc;
     }
-    __syncthreads();
-    const unsigned int n_here = (total - i0 < 256u ? total - i0 : 256u) * (unsigned int)ntaps;
-    const size_t base = (size_t)i0 * ntaps;
-    for (unsigned int k = threadIdx.x; k < n_here; k += 256u) {
-      float v = s_tile[k];
-      if (mask) v *= mask[base + k];
-      dw[base + k] = accumulate ? dw[base + k] + v : v;
-    }
-    __syncthreads();
   }
 }
 

@@ -720,39 +720,18 @@ extern "C" int mc_maxpool2x2_backward(const void* d_a_full, int ld_a, const void
 namespace {
 // one thread = one (input channel c, output channel o), o fastest: the taps are read as one contiguous run, each write
 // is coalesced over o.  Padding is zeroed by a memset before the launch.
-// out[c][taps-1-t][o] = bf16(w[o][c][t] * mask): a transpose of the o axis against the (c, t) axes.  Tile = 32 filters x
-// 288 consecutive (c, t) entries through shared memory, so the fp32 reads (contiguous in (c, t) per filter) and the bf16
-// writes (contiguous in o) are both coalesced.  (The direct version read with a thread stride of C*taps floats.)
-constexpr int PD_SPAN = 288, PD_PITCH = 289;
-__global__ void __launch_bounds__(256) pack_dgrad_weights_kernel(const float* __restrict__ w, const float* __restrict__ mask,
-                                                                 int O, int C, int taps, __nv_bfloat16* __restrict__ out,
-                                                                 int Cpad, int Ko) {
-  __shared__ float s_t[32 * PD_PITCH];
-  const int ct_total = C * taps;
-  const int spans = (ct_total + PD_SPAN - 1) / PD_SPAN;
-  const int o_tiles = (O + 31) / 32;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int tile = blockIdx.x; tile < spans * o_tiles; tile += gridDim.x) {
-    const int o0 = (tile / spans) * 32, ct0 = (tile % spans) * PD_SPAN;
-    const int n_ct = ct_total - ct0 < PD_SPAN ? ct_total - ct0 : PD_SPAN;
-    for (int r = 0; r < 32; ++r) {
-      const int o = o0 + r;
-      if (o >= O) break;
-      const size_t src = (size_t)o * ct_total + ct0;
-      for (int j = threadIdx.x; j < n_ct; j += 256) {
-        float v = w[src + j];
-        if (mask) v *= mask[src + j];
-        s_t[r * PD_PITCH + j] = v;
-      }
+__global__ void pack_dgrad_weights_kernel(const float* __restrict__ w, const float* __restrict__ mask, int O, int C,
+                                          int taps, __nv_bfloat16* __restrict__ out, int Cpad, int Ko) {
+  const unsigned int total = (unsigned int)O * (unsigned int)C;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned int c = i / (unsigned int)O, o = i - c * (unsigned int)O;
+    const size_t src = ((size_t)o * C + c) * taps;
+    __nv_bfloat16* dst = out + (size_t)c * taps * Ko + o;
+    for (int t = 0; t < taps; ++t) {
+      float v = w[src + t];
+      if (mask) v *= mask[src + t];
+      dst[(size_t)(taps - 1 - t) * Ko] = __float2bfloat16_rn(v);
     }
-    __syncthreads();
-    if (o0 + lane < O) {
-      for (int j = warp; j < n_ct; j += 8) {
-        const int ct = ct0 + j, c = ct / taps, t = ct - c * taps;
-        out[((size_t)c * taps + (taps - 1 - t)) * Ko + o0 + lane] = __float2bfloat16_rn(s_t[lane * PD_PITCH + j]);
-      }
-    }
-    __syncthreads();
   }
 }
 
@@ -885,11 +864,8 @@ extern "C" int mc_pack_conv_weights_dgrad(const float* d_w, const float* d_mask,
   const int taps = ksize * ksize;
   MC_CHECK_ARG((long long)O * C < (1ll << 32), "mc_pack_conv_weights_dgrad: tensor too large");
   MC_CUDA(cudaMemsetAsync(d_wpack, 0, (size_t)Cpad * taps * Ko * sizeof(__nv_bfloat16), stream));
-  {
-    const long long tiles = (long long)((C * taps + PD_SPAN - 1) / PD_SPAN) * ((O + 31) / 32);
-    long long g = tiles < (long long)mc_num_sms() * 8 ? tiles : (long long)mc_num_sms() * 8;
-    pack_dgrad_weights_kernel<<<(int)g, 256, 0, stream>>>(d_w, d_mask, O, C, taps, (__nv_bfloat16*)d_wpack, Cpad, Ko);
-  }
+  pack_dgrad_weights_kernel<<<grid_for((long long)O * C, 256), 256, 0, stream>>>(d_w, d_mask, O, C, taps,
+                                                                                (__nv_bfloat16*)d_wpack, Cpad, Ko);
   MC_LAUNCH_CHECK("pack_dgrad_weights_kernel");
   return 0;
 }
