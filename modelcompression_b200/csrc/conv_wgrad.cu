@@ -132,7 +132,7 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __g
       }
     }
   } else if (warp_idx == 1) {
-    if (lane == 0) {  // ===================== MMA issuer =====================
+    {  // ===================== MMA issuer: the whole warp walks the loop, one elected lane issues (see conv_tcgen05.cu)
       int s = 0;
       uint32_t phase = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -140,6 +140,7 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __g
         ptx::tc_fence_after();
         const uint32_t a_addr = ptx::smem_u32(tiles + (size_t)s * stage_bytes);
         const uint64_t adesc = make_sw128_mnmajor_desc(a_addr);
+        if (ptx::elect_one()) {
         if (p.share3) {
           // tap dx = rows dx .. dx+63 of the 72-row box: start dx*128 B into it (the swizzle is applied to the absolute
           // shared-memory address, so an un-aligned start needs no base offset — see conv_tcgen05.cu); 64-column blocks
@@ -162,9 +163,13 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __g
           }
         }
         ptx::umma_commit(&empty_bar[s]);
+        if (kb == kb1 - 1) ptx::umma_commit(tmem_full_bar);
+        }
+        __syncwarp();
         if (++s == p.stages) { s = 0; phase ^= 1u; }
       }
-      ptx::umma_commit(tmem_full_bar);
+      if (kb1 <= kb0 && ptx::elect_one()) ptx::umma_commit(tmem_full_bar);  // empty split: nothing to wait for
+      __syncwarp();
     }
   } else {
     // ===================== epilogue: warps 2..5 -> partial tile to the workspace =====================

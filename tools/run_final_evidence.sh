@@ -8,3 +8,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-fi
 python tools/profile_forward.py 64 > gpurun_out/plain_fwd.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:conv_gemm_tcgen05 -s 18 -c 18 -f -o gpurun_out/prof_conv_r1 python tools/profile_forward.py 64 > gpurun_out/ncu_fwd.log 2>&1
 tail -2 gpurun_out/ncu_fwd.log
+# 4. launch list of the retrain step (BASELINE configs[2])
+python tools/profile_train.py > gpurun_out/plain_train.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_train.csv python tools/profile_train.py > gpurun_out/ncu_train.log 2>&1
+tail -2 gpurun_out/plain_train.log

@@ -73,7 +73,35 @@ def ncu_summary():
     print('ncu full:', n, 'launches,', round(rd + wr, 1), 'MB DRAM traffic')
 
 
+def train_summary(steps=7):
+    """per-kernel totals of one retrain step from the launch list of tools/profile_train.py (7 steps captured)."""
+    src = os.path.join(GP, 'launches_train.csv')
+    if not os.path.exists(src):
+        return
+    rows = list(csv.reader(open(src, errors='ignore')))
+    h = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
+    hdr = rows[h]
+    ki, vi = hdr.index('Kernel Name'), hdr.index('Metric Value')
+    agg = {}
+    for r in rows[h + 2:]:
+        if len(r) <= vi:
+            continue
+        a = agg.setdefault(r[ki].split('(')[0][:70], [0, 0.0])
+        a[0] += 1
+        a[1] += float(r[vi].replace(',', '')) / 1e6
+    tot = sum(a[1] for a in agg.values())
+    with open(os.path.join(OUT, 'r1_launches_train_step_summary.csv'), 'w') as f:
+        w = csv.writer(f)
+        w.writerow(['kernel', 'launches_per_step', 'ms_per_step', 'share'])
+        for name, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            w.writerow([name, round(n / steps, 1), round(ms / steps, 4), round(ms / tot, 4)])
+        w.writerow(['TOTAL (one retrain step, batch 64, ncu gpu__time_duration, cold cache, serialised)', '',
+                    round(tot / steps, 3), 1.0])
+    print('train step:', round(tot / steps, 3), 'ms of kernels per step')
+
+
 if __name__ == '__main__':
+    train_summary()
     launch_summary()
     ncu_summary()
     shutil.copy(os.path.join(GP, 'bench_final.json'), os.path.join(OUT, 'r1_bench_v8.json'))
