@@ -290,7 +290,7 @@ __device__ __forceinline__ const uint4* da_vec(const __nv_bfloat16* da, unsigned
   return reinterpret_cast<const uint4*>(da + orow * ld_da + ch_off + ((y & 1) * 2 + (x & 1)) * C + c0);
 }
 
-__global__ void __launch_bounds__(TB) bn_bwd_reduce_vec_kernel(const __nv_bfloat16* __restrict__ z, int ld_z,
+__global__ void __launch_bounds__(TB, 3) bn_bwd_reduce_vec_kernel(const __nv_bfloat16* __restrict__ z, int ld_z,
                                                                const __nv_bfloat16* __restrict__ da, int ld_da, int ch_off,
                                                                int reorg, int B, int H, int W, int C, int O8,
                                                                const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(TB) bn_bwd_reduce_vec_kernel(const __nv_bfloat
   }
 }
 
-__global__ void __launch_bounds__(TB) bn_bwd_apply_vec_kernel(const __nv_bfloat16* __restrict__ z, int ld_z,
+__global__ void __launch_bounds__(TB, 3) bn_bwd_apply_vec_kernel(const __nv_bfloat16* __restrict__ z, int ld_z,
                                                               const __nv_bfloat16* __restrict__ da, int ld_da, int ch_off,
                                                               int reorg, int B, int H, int W, int C, int O8,
                                                               const float* __restrict__ mean, const float* __restrict__ invstd,
