@@ -104,4 +104,4 @@ if __name__ == '__main__':
     train_summary()
     launch_summary()
     ncu_summary()
-    shutil.copy(os.path.join(GP, 'bench_final.json'), os.path.join(OUT, 'r1_bench_v8.json'))
+    shutil.copy(os.path.join(GP, 'bench_final.json'), os.path.join(OUT, 'r1_bench_v9.json'))
