@@ -451,16 +451,13 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                                        : ptx::make_sw64_kmajor_desc(a_addr + (uint32_t)dx * 64u);
             const uint64_t bdesc = k64 ? ptx::make_sw128_kmajor_desc(b_addr) : ptx::make_sw64_kmajor_desc(b_addr);
             if (ptx::elect_one()) {
-              if (nk == 4) {  // (compile-time trip count: this issue loop is on the critical path)
+              // (compile-time trip count with a per-step predicate: this issue loop is on the critical path, a
+              //  run-time trip count costs the narrow-Cin layers ~4 us each)
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
+              for (int k = 0; k < 4; ++k)
+                if (k < nk)
                   ptx::umma_bf16_ss(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
                                     (g > 0 || dx > 0 || k > 0) ? 1u : 0u);
-              } else {
-                for (int k = 0; k < nk; ++k)
-                  ptx::umma_bf16_ss(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
-                                    (g > 0 || dx > 0 || k > 0) ? 1u : 0u);
-              }
               if (!p.b_resident) ptx::umma_commit(&empty_bar[s]);
               if (dx == 2) ptx::umma_commit(&aempty_bar[sa]);  // the box may be refilled once its three taps retire
               if (dx == 2 && g == 3 * p.kb_per_tap - 1) ptx::umma_commit(&tmem_full_bar[as]);
@@ -495,11 +492,12 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const int ksteps = (cb_i == p.kb_per_tap - 1) ? p.last_ksteps : p.block_k / 16;
           if (++cb_i == p.kb_per_tap) cb_i = 0;
           if (ptx::elect_one()) {
-#pragma unroll 4
-            for (int k = 0; k < ksteps; ++k) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
               // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr>>4) field
-              ptx::umma_bf16_ss(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
-                                (kb > 0 || k > 0) ? 1u : 0u);
+              if (k < ksteps)
+                ptx::umma_bf16_ss(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
+                                  (kb > 0 || k > 0) ? 1u : 0u);
             }
             ptx::umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
             if (kb == p.num_kb - 1) ptx::umma_commit(&tmem_full_bar[as]);  // accumulator complete
@@ -637,16 +635,11 @@ conv_gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_b, const 
             const uint64_t adesc = ptx::make_sw128_kmajor_desc(a_addr + (uint32_t)dx * 128u);
             const uint64_t bdesc = ptx::make_sw128_kmajor_desc(ptx::smem_u32(b_ring + (size_t)s * b_half_bytes));
             if (ptx::elect_one()) {
-              if (nk == 4) {  // (compile-time trip count: this issue loop is on the critical path)
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
+              for (int k = 0; k < 4; ++k)
+                if (k < nk)
                   ptx::umma_bf16_ss_pair(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
                                          (g > 0 || dx > 0 || k > 0) ? 1u : 0u);
-              } else {
-                for (int k = 0; k < nk; ++k)
-                  ptx::umma_bf16_ss_pair(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
-                                         (g > 0 || dx > 0 || k > 0) ? 1u : 0u);
-              }
               ptx::umma_commit_pair(&empty_bar[s]);
               if (dx == 2) ptx::umma_commit_pair(&aempty_bar[sa]);
               if (dx == 2 && g == 3 * p.kb_per_tap - 1) ptx::umma_commit_pair(&tmem_full_bar[as]);
