@@ -756,6 +756,13 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
       bn_big = e ? atoi(e) : 0;
     }
     if (block_n <= 0 && bn_big >= 16 && bn_big <= 256 && (bn_big % 16) == 0 && d->Npad >= 960 && d->ksize == 3) block_n = bn_big;
+    static int bn_mid = -1;  // MCB200_CONV_BN_MID=<bn>: same for 3x3 layers with 512 <= Npad < 960
+    if (bn_mid < 0) {
+      const char* e = getenv("MCB200_CONV_BN_MID");
+      bn_mid = e ? atoi(e) : 0;
+    }
+    if (block_n <= 0 && bn_mid >= 16 && bn_mid <= 256 && (bn_mid % 16) == 0 && d->Npad >= 512 && d->Npad < 960 && d->ksize == 3)
+      block_n = bn_mid;
   }
   if (block_n <= 0) block_n = pick_block_n(d->Npad, m_tiles, (ntaps * Kc + 63) / 64, mc_num_sms(), false);  // 64-wide k-block units
   MC_CHECK_ARG(block_n >= 16 && block_n <= 256 && (block_n % 16) == 0, "mc_conv_fwd: block_n %d invalid", block_n);

@@ -3,7 +3,7 @@
 # inside ONE gpurun call).  Usage:  gpurun -- 'bash tools/ab.sh "MCB200_CONV_2CTA=0" "MCB200_CONV_STAGE_OUT=0" ...'
 # Every argument is one variant (space-separated VAR=value pairs; "" = defaults); each runs twice on the shrunk and once on
 # the dense network.  Result lines: gpurun_out/ab.jsonl (tools/bench_layers.py format).
-# Switches: MCB200_CONV_2CTA (0 off, 2 force), MCB200_CONV_CTAS (1..3), MCB200_CONV_MINTILES, MCB200_CONV_BN_BIG=<bn>,
+# Switches: MCB200_CONV_2CTA (0 off, 2 force), MCB200_CONV_CTAS (1..3), MCB200_CONV_MINTILES, MCB200_CONV_BN_BIG=<bn>, MCB200_CONV_BN_MID=<bn>,
 # MCB200_CONV_STAGE_OUT (0 off, 2 all wide tiles), MCB200_SHARE_DX (0 off, 2 only 64-wide k-blocks), MCB200_CONV_ACC=<n>,
 # MCB200_CONV_RESIDENT=1, MCB200_PITCH=0, MCB200_CONV_TRACE=1.
 mkdir -p gpurun_out
