@@ -170,3 +170,30 @@ def test_train_plan_graph(cfg_path):
     assert Ls[29].C == 1280 and Ls[29].src.name == Ls[24].act.name
     ps = plan.parameters()
     assert sum(p.numel() for p in ps) == 50655389 and len({id(p) for p in ps}) == len(list(model.parameters()))
+
+
+def test_activation_pitch_policy():
+    """engine._pitch: 8-channel granularity up to 16 channels (the im2col kernel's pitch), 32 for 17..32, otherwise the
+    next multiple of 64 when that grows the row by <= 25 %, else the next multiple of 8; always >= n and 16-byte rows."""
+    from modelcompression_b200.engine import _pitch
+    assert [_pitch(n) for n in (1, 4, 8, 9, 16)] == [8, 8, 8, 16, 16]
+    assert [_pitch(n) for n in (17, 22, 32)] == [32, 32, 32]
+    assert _pitch(33) == 40 and _pitch(69) == 72 and _pitch(91) == 96 and _pitch(145) == 152   # > 25 % growth: stay
+    assert _pitch(56) == 64 and _pitch(158) == 192 and _pitch(811) == 832 and _pitch(1006) == 1024 and _pitch(1018) == 1024
+    for n in range(1, 1300):
+        ld = _pitch(n)
+        assert ld >= n and ld % 8 == 0 and (n <= 32 or ld <= max((n + 7) // 8 * 8, int(1.25 * ((n + 7) // 8 * 8))))
+
+
+def test_bench_numa_binding_is_optional():
+    """bench.bind_to_gpu_numa must not raise where NVML / the GPU is missing (it returns None and the run proceeds)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(os.path.dirname(os.path.dirname(__file__)), 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    before = os.sched_getaffinity(0)
+    got = bench.bind_to_gpu_numa(0)
+    assert got is None or (isinstance(got, int) and got >= 1)
+    if got is None:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
