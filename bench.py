@@ -375,7 +375,14 @@ def main():
         torch.cuda.synchronize()
         clocks = sampler.stop()
         elapsed_ms = e0.elapsed_time(e1)
+        per_rank = None
         if world > 1:
+            # every rank's own step time and clocks (diagnostic: which rank sets the max, and whether it was clocked down)
+            mine = {"rank": rank, "ms_per_step": elapsed_ms / args.steps, "sm_mhz": clocks.get("sm_mhz"),
+                    "reasons": clocks.get("reasons")}
+            gathered = [None] * world
+            dist.all_gather_object(gathered, mine)
+            per_rank = gathered
             t = torch.tensor([elapsed_ms], device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             elapsed_ms = float(t.item())
@@ -506,6 +513,8 @@ def main():
                      "kernel_share_of_step": conv_ms / max(conv_ms + other_ms, 1e-9)},
         "whole_net_tflops": flops_img * value / world / 1e12,
     }
+    if per_rank is not None:
+        line["per_rank"] = per_rank
     with torch.no_grad():
         line["eval_pipeline"] = time_eval_pipeline(model, device, B, rank, world)
     if rank == 0:
