@@ -70,3 +70,24 @@ def test_cpu_tensor_fails_loudly(cfg_path):
         model(torch.zeros(1, 3, 416, 416))
     with pytest.raises(RuntimeError, match="no CPU"):
         mc.weight_prune(model, 50.)
+
+
+def test_conv_desc_offsets_match_the_c_compiler(tmp_path):
+    """The ctypes mirror of mc_conv_desc must have the C compiler's layout (size and every field offset): a field added
+    on one side only would silently shift the descriptor the kernels read."""
+    import subprocess
+    fields = [f[0] for f in _lib.mc_conv_desc._fields_]
+    src = tmp_path / "layout.c"
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "mcb200.h"', 'int main(void) {',
+             '  printf("%zu\\n", sizeof(mc_conv_desc));']
+    for f in fields:
+        lines.append('  printf("%%zu\\n", offsetof(mc_conv_desc, %s));' % f)
+    lines += ['  return 0;', '}']
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'include')
+    subprocess.run(['gcc', '-I', inc, str(src), '-o', str(exe)], check=True)
+    out = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert out[0] == ctypes.sizeof(_lib.mc_conv_desc)
+    for f, off in zip(fields, out[1:]):
+        assert getattr(_lib.mc_conv_desc, f).offset == off, f
