@@ -10,8 +10,15 @@
 //     Y[p, n] = sum_{tap} sum_{c} X[p + off(tap), c] * Wt[n, tap*Kc + c]
 // is a plain GEMM whose A-tile row coordinate is shifted per k-block: no im2col buffer, no bounds logic.
 // M tile = 128 rows (UMMA M=128, cta_group::1), N tile = block_n (16..256), K block = 64 bf16 = one
-// 128-byte swizzle row.  Warp roles: warp0 = TMA producer, warp1 = TMEM owner + MMA issuer (one thread),
-// warps 2..5 = epilogue (TMEM -> regs -> scale/shift/leaky -> bf16/fp32 global stores).
+// 128-byte swizzle row (or 32 bf16 / 64-byte swizzle for <= 32 input channels).  Warp roles: warp0 = TMA producer,
+// warp1 = TMEM owner + MMA issuer (warp-uniform loop, one elected lane issues), warps 2..5 = epilogue (TMEM -> regs ->
+// scale/shift/leaky -> bf16/fp32 stores, staged through shared memory for 32..96-wide PNHWC tiles).
+// Two kernels share this file:
+//   conv_gemm_tcgen05_kernel<MINB>   persistent, 1..3 CTAs per SM (MINB = register budget), every layer shape;
+//   conv_gemm_tcgen05_pair_kernel    cluster of 2 CTAs, tcgen05 cta_group::2: 256-row tiles, each CTA loads half of every
+//                                    weight tile — the wide 3x3 layers (block_n >= 192, >= 36 k-blocks).
+// mc_conv_fwd picks kernel, tile width, ring depth and CTAs per SM (mc_conv_last_plan reports the choice;
+// MCB200_CONV_TRACE=1 prints it; the MCB200_* switches listed in tools/ab.sh override single decisions for A/B runs).
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
