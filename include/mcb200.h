@@ -140,6 +140,10 @@ int mc_decode_region(const float* d_head, int B, int H, int W, int A, int nc, co
 int mc_nms_batched(float* d_boxes, const int* d_counts, int B, int cap, float nms_thresh,
                    int* d_keep, int* d_keep_counts, void* stream);
 
+/* Element-wise IoU of two box sets laid out [4, n] (row i = coordinate i of every box) — replaces bbox_ious,
+ * src/nets2_utils.py:100-131 (x1y1x2y2 != 0: corner format; 0: centre format).  d_out[n].  fp32, reference op order. */
+int mc_bbox_ious(const float* d_boxes1, const float* d_boxes2, int64_t n, int x1y1x2y2, float* d_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Darknet-19 forward — replaces the F.conv2d + BatchNorm2d + LeakyReLU + MaxPool2d + Reorg + cat
  * call sites of src/nets.py:720-774 / src/pruning/weightPruning/layers.py:53-64.
@@ -225,6 +229,11 @@ int mc_maxpool2x2(const void* d_in, void* d_out, int B, int H, int W, int C, int
 /* PNHWC bf16 -> NCHW fp32 [B,C,H,W] (debug / per-block parity checks). */
 int mc_unpack_pnhwc(const void* d_in, float* d_out, int B, int H, int W, int C, int ld_in, int ch_off,
                     void* stream);
+
+/* Stand-alone Reorg — replaces Reorg.forward, src/nets.py:648-667, on the reference's layout: fp32 NCHW [B,C,H,W] ->
+ * fp32 NCHW [B, s*s*C, H/s, W/s], out[b,(i*s+j)*C+c,y,x] = in[b,c,s*y+i,s*x+j].  (Inside Darknet.forward the shuffle is
+ * the MC_EPI_REORG2 store addressing of the producing conv.)                                           */
+int mc_reorg_nchw(const float* d_in, float* d_out, int B, int C, int H, int W, int stride, void* stream);
 
 /* NCHW fp32 [B,C,H,W] -> PNHWC bf16 (channels >= C up to ld zeroed; pad rows/cols zeroed). */
 int mc_pack_pnhwc(const float* d_in, void* d_out, int B, int H, int W, int C, int ld_out, void* stream);

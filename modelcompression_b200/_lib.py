@@ -61,6 +61,8 @@ _SIGNATURES = {
     "mc_decode_region": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(c_float), c_float, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p]),
     "mc_nms_batched": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "mc_bbox_ious": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "mc_reorg_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mc_conv_fwd": (c_int, [POINTER(mc_conv_desc), c_void_p]),
     "mc_conv_last_plan": (c_int, [POINTER(c_int)]),
     "mc_conv_direct_supported": (c_int, [c_int, c_int, c_int]),

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include "../../include/mcb200.h"
 
 #define MC_ERR_ARG (-1)
@@ -33,6 +34,18 @@ int mc_set_error(int code, const char* fmt, ...);
       return mc_set_error(-(1000 + (int)e_), "launch of %s failed: %s", name,               \
                           cudaGetErrorString(e_));                                          \
   } while (0)
+
+// A/B switches of the launch planners (MCB200_* environment variables, listed in tools/ab.sh) exist only in a tuning
+// build (make TUNING=1 -> -DMCB200_TUNING).  The product build never reads the environment: every decision is the
+// measured default.
+static inline const char* mc_tune_env(const char* name) {
+#ifdef MCB200_TUNING
+  return getenv(name);
+#else
+  (void)name;
+  return nullptr;
+#endif
+}
 
 static inline int mc_num_sms() {
   static int n = 0;

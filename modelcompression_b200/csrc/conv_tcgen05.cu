@@ -744,7 +744,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   // 3x3 with 64-wide k-blocks: share one activation box among the three dx taps (MCB200_SHARE_DX=0 disables)
   static int share_env = -1, share_env32 = 1;
   if (share_env < 0) {
-    const char* e = getenv("MCB200_SHARE_DX");
+    const char* e = mc_tune_env("MCB200_SHARE_DX");
     share_env = (e && e[0] == '0') ? 0 : 1;
     share_env32 = (e && e[0] == '2') ? 0 : 1;
   }
@@ -759,13 +759,13 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   {  // experiment switch: MCB200_CONV_BN_BIG=<bn> forces the tile width of the wide 3x3 layers (Npad >= 960)
     static int bn_big = -1;
     if (bn_big < 0) {
-      const char* e = getenv("MCB200_CONV_BN_BIG");
+      const char* e = mc_tune_env("MCB200_CONV_BN_BIG");
       bn_big = e ? atoi(e) : 0;
     }
     if (block_n <= 0 && bn_big >= 16 && bn_big <= 256 && (bn_big % 16) == 0 && d->Npad >= 960 && d->ksize == 3) block_n = bn_big;
     static int bn_mid = -1;  // MCB200_CONV_BN_MID=<bn>: same for 3x3 layers with 512 <= Npad < 960
     if (bn_mid < 0) {
-      const char* e = getenv("MCB200_CONV_BN_MID");
+      const char* e = mc_tune_env("MCB200_CONV_BN_MID");
       bn_mid = e ? atoi(e) : 0;
     }
     if (block_n <= 0 && bn_mid >= 16 && bn_mid <= 256 && (bn_mid % 16) == 0 && d->Npad >= 512 && d->Npad < 960 && d->ksize == 3)
@@ -793,14 +793,14 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   // than the saved weight traffic.
   static int res_env = -1;
   if (res_env < 0) {
-    const char* e = getenv("MCB200_CONV_RESIDENT");
+    const char* e = mc_tune_env("MCB200_CONV_RESIDENT");
     res_env = (e && e[0] == '1') ? 1 : 0;
   }
   const int b_resident = (res_env && share_dx && n_tiles == 1 && d->stages <= 0 && b_res_bytes <= 112 * 1024) ? 1 : 0;
   // staged epilogue (PNHWC, tiles up to 128 wide): 128 rows x (block_n bf16 + 16 B) of shared memory
   static int stage_env = -1;  // MCB200_CONV_STAGE_OUT=0 disables (A/B switch)
   if (stage_env < 0) {
-    const char* e = getenv("MCB200_CONV_STAGE_OUT");
+    const char* e = mc_tune_env("MCB200_CONV_STAGE_OUT");
     stage_env = (e && e[0] == '0') ? 0 : ((e && e[0] == '2') ? 2 : 1);
   }
   // (measured: tiles 32..96 wide gain — dense conv2 396 -> 300 us, conv4' 60 -> 54, shrunk conv8 33 -> 29; 128-wide tiles
@@ -848,13 +848,13 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   // slices fit and every CTA still gets >= 2 tiles.  MCB200_CONV_CTAS=1|2|3 forces the upper limit.
   static int ctas_env = -1;
   if (ctas_env < 0) {
-    const char* e = getenv("MCB200_CONV_CTAS");
+    const char* e = mc_tune_env("MCB200_CONV_CTAS");
     ctas_env = e ? atoi(e) : 0;
     if (ctas_env < 0 || ctas_env > 3) ctas_env = 0;
   }
   static int min_tiles = -1;  // tiles every CTA must get before another CTA per SM is added (MCB200_CONV_MINTILES, A/B)
   if (min_tiles < 0) {
-    const char* e = getenv("MCB200_CONV_MINTILES");
+    const char* e = mc_tune_env("MCB200_CONV_MINTILES");
     min_tiles = e ? atoi(e) : 1;  // measured: 1 beats 2 by 0.5 % on the shrunk step (the 365-tile 26x26 layers get 2 CTAs per SM)
     if (min_tiles < 1) min_tiles = 1;
   }
@@ -892,7 +892,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   // CTA pair (cta_group::2) for the wide 3x3 layers: MCB200_CONV_2CTA=0 off, 1 auto (default), 2 wherever legal
   static int pair_env = -1;
   if (pair_env < 0) {
-    const char* e = getenv("MCB200_CONV_2CTA");
+    const char* e = mc_tune_env("MCB200_CONV_2CTA");
     pair_env = e ? atoi(e) : 1;
     if (pair_env < 0 || pair_env > 2) pair_env = 1;
   }
@@ -949,7 +949,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   // co-residing with this kernel's tail (dense step 2.25 -> 2.35 ms).  MCB200_CONV_ACC=<n> (3..8) enables it for A/B.
   static int acc_env = -1;
   if (acc_env < 0) {
-    const char* e = getenv("MCB200_CONV_ACC");
+    const char* e = mc_tune_env("MCB200_CONV_ACC");
     acc_env = e ? atoi(e) : 0;
   }
   int acc_stages = 2;
@@ -1034,7 +1034,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   int grid = (int)(total_tiles < max_ctas ? total_tiles : max_ctas);
   static int trace_env = -1;  // MCB200_CONV_TRACE=1: one line per launch on stderr (tools/bench_layers.py)
   if (trace_env < 0) {
-    const char* e = getenv("MCB200_CONV_TRACE");
+    const char* e = mc_tune_env("MCB200_CONV_TRACE");
     trace_env = (e && e[0] == '1') ? 1 : 0;
   }
   if (trace_env)

@@ -234,7 +234,7 @@ int plan_wgrad(WgradPlan* pl, int B, int H, int W, int C, int O, int ksize) {
   const int c16 = (C + 15) / 16 * 16;
   static int share_env = -1;
   if (share_env < 0) {
-    const char* e = getenv("MCB200_WGRAD_SHARE");
+    const char* e = mc_tune_env("MCB200_WGRAD_SHARE");
     share_env = (e && e[0] == '0') ? 0 : 1;
   }
   pl->share3 = (ksize == 3 && share_env) ? 1 : 0;

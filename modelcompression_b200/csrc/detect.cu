@@ -206,7 +206,47 @@ nms_kernel(float* __restrict__ boxes, const int* __restrict__ counts, int cap, i
   if (threadIdx.x == 0) keep_counts[img] = s_nkeep;
 }
 
+// bbox_ious (src/nets2_utils.py:100-131): element-wise IoU of two [4, n] box sets, every operation a separately rounded
+// fp32 op in the reference's order (torch element-wise kernels do not contract to FMA), `carea[mask] = 0` included.
+__global__ void bbox_ious_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, int corners,
+                                 float* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float a0 = a[i], a1 = a[n + i], a2 = a[2 * n + i], a3 = a[3 * n + i];
+    const float b0 = b[i], b1 = b[n + i], b2 = b[2 * n + i], b3 = b[3 * n + i];
+    float mx, Mx, my, My, w1, h1, w2, h2;
+    if (corners) {
+      mx = fminf(a0, b0); Mx = fmaxf(a2, b2); my = fminf(a1, b1); My = fmaxf(a3, b3);
+      w1 = __fsub_rn(a2, a0); h1 = __fsub_rn(a3, a1); w2 = __fsub_rn(b2, b0); h2 = __fsub_rn(b3, b1);
+    } else {
+      mx = fminf(__fsub_rn(a0, __fdiv_rn(a2, 2.0f)), __fsub_rn(b0, __fdiv_rn(b2, 2.0f)));
+      Mx = fmaxf(__fadd_rn(a0, __fdiv_rn(a2, 2.0f)), __fadd_rn(b0, __fdiv_rn(b2, 2.0f)));
+      my = fminf(__fsub_rn(a1, __fdiv_rn(a3, 2.0f)), __fsub_rn(b1, __fdiv_rn(b3, 2.0f)));
+      My = fmaxf(__fadd_rn(a1, __fdiv_rn(a3, 2.0f)), __fadd_rn(b1, __fdiv_rn(b3, 2.0f)));
+      w1 = a2; h1 = a3; w2 = b2; h2 = b3;
+    }
+    const float uw = __fsub_rn(Mx, mx), uh = __fsub_rn(My, my);
+    const float cw = __fsub_rn(__fadd_rn(w1, w2), uw), ch = __fsub_rn(__fadd_rn(h1, h2), uh);
+    float carea = __fmul_rn(cw, ch);
+    if (cw <= 0.f || ch <= 0.f) carea = 0.f;
+    const float uarea = __fsub_rn(__fadd_rn(__fmul_rn(w1, h1), __fmul_rn(w2, h2)), carea);
+    out[i] = __fdiv_rn(carea, uarea);
+  }
+}
+
 }  // namespace
+
+extern "C" int mc_bbox_ious(const float* d_boxes1, const float* d_boxes2, int64_t n, int x1y1x2y2, float* d_out,
+                            void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MC_CHECK_ARG(d_boxes1 && d_boxes2 && d_out, "mc_bbox_ious: null pointer");
+  MC_CHECK_ARG(n >= 0, "mc_bbox_ious: bad count");
+  if (n == 0) return 0;
+  long long blocks = (n + 255) / 256;
+  if (blocks > (long long)mc_num_sms() * 8) blocks = (long long)mc_num_sms() * 8;
+  bbox_ious_kernel<<<(int)blocks, 256, 0, stream>>>(d_boxes1, d_boxes2, (long long)n, x1y1x2y2 ? 1 : 0, d_out);
+  MC_LAUNCH_CHECK("bbox_ious_kernel");
+  return 0;
+}
 
 extern "C" int mc_decode_region(const float* d_head, int B, int H, int W, int A, int nc, const float* h_anchors,
                                 float conf_thresh, int only_objectness, float* d_boxes, float* d_cls, int* d_counts,

@@ -342,3 +342,43 @@ extern "C" int mc_conv_direct_fwd(const void* d_in, int in_is_nchw_f32, const fl
     return launch_direct<true>(d_in, d_w, d_scale, d_shift, d_out, B, H, W, Cin, Cin_ld, N, ldc, ksize, leaky, pool, stream);
   return launch_direct<false>(d_in, d_w, d_scale, d_shift, d_out, B, H, W, Cin, Cin_ld, N, ldc, ksize, leaky, pool, stream);
 }
+
+
+// ------------------------------------------------------------------------------------------------------------
+// Stand-alone Reorg (src/nets.py:648-667) on the reference's own layout: fp32 NCHW in, fp32 NCHW out,
+//   out[b, (i*s+j)*C + c, y, x] = in[b, c, s*y+i, s*x+j].
+// Inside Darknet.forward the same shuffle is the store addressing of the producing conv's epilogue (MC_EPI_REORG2);
+// this entry point serves a direct Reorg.forward call.
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void reorg_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int C, int H, int W,
+                                  int s) {
+  const int Ho = H / s, Wo = W / s;
+  const long long total = (long long)B * C * H * W;
+  for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < total;
+       o += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(o % Wo);
+    long long t = o / Wo;
+    const int y = (int)(t % Ho);
+    t /= Ho;
+    const int oc = (int)(t % ((long long)C * s * s));
+    const int b = (int)(t / ((long long)C * s * s));
+    const int c = oc % C, q = oc / C;
+    const int i = q / s, j = q - i * s;
+    out[o] = in[(((long long)b * C + c) * H + (s * y + i)) * W + (s * x + j)];
+  }
+}
+}  // namespace
+
+extern "C" int mc_reorg_nchw(const float* d_in, float* d_out, int B, int C, int H, int W, int stride, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MC_CHECK_ARG(d_in && d_out, "mc_reorg_nchw: null pointer");
+  MC_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0 && stride > 0, "mc_reorg_nchw: bad dims");
+  MC_CHECK_ARG((H % stride) == 0 && (W % stride) == 0, "mc_reorg_nchw: H, W must be multiples of the stride");
+  const long long total = (long long)B * C * H * W;
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)mc_num_sms() * 16) blocks = (long long)mc_num_sms() * 16;
+  reorg_nchw_kernel<<<(int)blocks, 256, 0, stream>>>(d_in, d_out, B, C, H, W, stride);
+  MC_LAUNCH_CHECK("reorg_nchw_kernel");
+  return 0;
+}

@@ -725,7 +725,7 @@ int launch_sumsq(const LayerTable& lt, float* d_values, cudaStream_t stream) {
   const int n_generic = lt.toff[lt.nlayers] / SS_THREADS;
   const int first_wave = n_tiled < mc_num_sms() ? n_tiled : mc_num_sms();
   if (n_tiled + n_generic == 0) return 0;
-  const char* dbg = getenv("MCB200_SUMSQ_ONLY");  // timing experiments only (results are incomplete)
+  const char* dbg = mc_tune_env("MCB200_SUMSQ_ONLY");  // timing experiments only (results are incomplete)
   if (dbg && dbg[0] == 't') {
     filter_sumsq_kernel<<<n_tiled, SS_THREADS, SUMSQ_SMEM, stream>>>(lt, d_values, n_tiled, first_wave);
     return 0;

@@ -960,7 +960,7 @@ int launch_weight_prune(const float* const* h_w_ptrs, float* const* h_mask_ptrs,
   unsigned int* cand = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(d_ws) + state_bytes);
 
   // MCB200_SELECT_EXACT=1 forces the exact radix path (used by the tests to cover the fallback on large inputs)
-  const char* force_exact = getenv("MCB200_SELECT_EXACT");
+  const char* force_exact = mc_tune_env("MCB200_SELECT_EXACT");
   // the fast path indexes elements with 32 bits and needs a sample much smaller than the data
   int use_fast = (n >= 8 * SAMPLE && n < (1ll << 32) && !(force_exact && force_exact[0] == '1')) ? 1 : 0;
 

@@ -17,7 +17,6 @@ Activation layout between layers is PNHWC bf16 (include/mcb200.h).  There is no 
 library, a CPU tensor or an unsupported cfg raises.
 """
 import ctypes
-import os
 
 import torch
 import torch.nn as nn
@@ -36,7 +35,7 @@ def _pitch(n):
     consumer's tensor map (mc_conv_desc.in_cols).  The extra columns are never written: they stay the zeros the buffer was
     created with.  <= 16 channels keep the 8/16 pitch the im2col kernel expects."""
     ld = _round_up(n, 8)
-    if n <= 16 or os.environ.get('MCB200_PITCH', '1') == '0':  # (A/B switch)
+    if n <= 16:
         return ld
     if n <= 32:
         return 32

@@ -21,6 +21,7 @@ Masked weights get exactly zero gradient (dW is multiplied by the mask, layers.p
 No CPU / PyTorch fallback: a CPU tensor or an unsupported cfg raises.
 """
 import ctypes
+import weakref
 
 import torch
 
@@ -215,15 +216,27 @@ class TrainPlan(object):
                 ps.append(L.conv.bias)
         return ps
 
-    def buffers(self, B, dev):
+    def buffers(self, B, dev, owner=None):
+        """A buffer set (activations saved for backward + gradient buffers) for batch B.  Sets are cached per (B, device).
+        A set whose forward still has a backward pending (its `owner`, the _Saved object autograd holds through ctx, is
+        alive and not yet consumed) is never handed out again: a second training-mode forward before the backward —
+        gradient accumulation over two micro-batches, loss(model(x1)) + loss(model(x2)), or a train-mode forward under
+        no_grad — gets another set instead of overwriting the saved tensors of the pending graph (the reference's
+        autograd graph keeps every forward's tensors alive in the same way).  owner=None: the caller promises no
+        backward (no_grad / tests); the set is free again immediately."""
         key = (B, str(dev))
-        got = self._bufs.get(key)
-        if got is None:
-            got = {}
+        sets = self._bufs.setdefault(key, [])
+        for st in sets:
+            ref = st['owner']
+            if ref is None or ref() is None or ref().consumed:
+                break
+        else:
+            st = {'owner': None, 't': {}}
             for name, (H, W, ld) in list(self.buf_specs.items()) + list(self.grad_specs.items()):
-                got[name] = torch.zeros(B * (H + 1) * (W + 1), ld, dtype=torch.bfloat16, device=dev)
-            self._bufs[key] = got
-        return got
+                st['t'][name] = torch.zeros(B * (H + 1) * (W + 1), ld, dtype=torch.bfloat16, device=dev)
+            sets.append(st)
+        st['owner'] = weakref.ref(owner) if owner is not None else None
+        return st['t']
 
 
 def _kblk(C, k=1):
@@ -246,10 +259,10 @@ def _masked(conv):
 
 
 class _Saved(object):
-    pass
+    consumed = False  # set once the backward has run (or the caller declared that none will)
 
 
-def _forward(plan, x, training_stats=True, after_layer=None):
+def _forward(plan, x, training_stats=True, after_layer=None, needs_backward=True):
     """Launch the training-mode forward; returns (y, saved).  after_layer(L, bufs) is a test hook called once a hidden
     layer's activation (and pooled activation) is in its buffer."""
     lib = plan.lib
@@ -258,8 +271,8 @@ def _forward(plan, x, training_stats=True, after_layer=None):
     if (H, W) != plan.in_hw:
         raise NotImplementedError("the plan was built for %dx%d inputs (cfg width/height); got %dx%d" %
                                   (plan.in_hw[1], plan.in_hw[0], W, H))
-    bufs = plan.buffers(B, dev)
     sv = _Saved()
+    bufs = plan.buffers(B, dev, sv if needs_backward else None)
     sv.x, sv.B, sv.bufs, sv.stats = x, B, bufs, {}
     s = _lib.stream_ptr()
     y = None
@@ -445,22 +458,26 @@ def _backward(plan, sv, dy, before_bn=None):
     for work, t in pending:  # the current stream waits for NCCL; gradients become the mean over the replicas
         work.wait()
         t.div_(plan.dp_world)
+    sv.consumed = True  # the buffer set may serve the next forward
     return [grads[id(p)] for p in plan.parameters()]
 
 
 class _DarknetTrainFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, plan, *params):
-        y, sv = _forward(plan, x)
+    def forward(ctx, x, plan, needs_backward, *params):
+        y, sv = _forward(plan, x, needs_backward=needs_backward)
         ctx.plan, ctx.sv = plan, sv
         return y
 
     @staticmethod
     def backward(ctx, dy):
         plan, sv = ctx.plan, ctx.sv
+        if sv.consumed:
+            raise RuntimeError("Darknet (training): backward called twice on the same forward (retain_graph is not "
+                               "supported: the saved activations are recycled after the first backward)")
         with torch.cuda.device(dy.device):
             g = _backward(plan, sv, dy.contiguous().float())
-        return (None, None) + tuple(g)
+        return (None, None, None) + tuple(g)
 
 
 def darknet_train_forward(model, x):
@@ -477,5 +494,7 @@ def darknet_train_forward(model, x):
         if p.dtype != torch.float32 or not p.is_contiguous():
             raise TypeError("training path expects contiguous float32 parameters")
     x = x.detach().float().contiguous()
+    # under no_grad (or with every parameter frozen) autograd records nothing: the forward must not claim a buffer set
+    needs_backward = torch.is_grad_enabled() and any(p.requires_grad for p in params)
     with torch.cuda.device(x.device):
-        return _DarknetTrainFn.apply(x, plan, *params)
+        return _DarknetTrainFn.apply(x, plan, needs_backward, *params)

@@ -54,14 +54,26 @@ class MaxPoolStride1(nn.Module):
 
 class Reorg(nn.Module):
     """nets.py:648-667: out[b,(i*s+j)*C+c,y,x] = in[b,c,s*y+i,s*x+j].  Inside ``Darknet`` the engine fuses this into
-    the producing conv's store addressing; the module itself only records the stride."""
+    the producing conv's store addressing (MC_EPI_REORG2); a direct call of the module runs mc_reorg_nchw."""
 
     def __init__(self, stride=2):
         super(Reorg, self).__init__()
         self.stride = stride
 
     def forward(self, x):
-        raise NotImplementedError("Reorg runs fused inside Darknet.forward (engine.py); it has no stand-alone path")
+        """Stand-alone call (float32 NCHW CUDA tensor in and out, the reference's layout): one libmcb200 kernel."""
+        from . import _lib
+        lib = _lib.load()
+        _lib.require_cuda(x, "Reorg.forward")
+        assert x.dim() == 4
+        B, C, H, W = x.shape
+        s = int(self.stride)
+        assert H % s == 0 and W % s == 0
+        xin = x.detach().float().contiguous()
+        out = torch.empty(B, s * s * C, H // s, W // s, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.mc_reorg_nchw(xin.data_ptr(), out.data_ptr(), B, C, H, W, s, _lib.stream_ptr()), "mc_reorg_nchw")
+        return out
 
 
 class GlobalAvgPool2d(nn.Module):
@@ -262,8 +274,11 @@ class Darknet(nn.Module):
                 seen = np.fromfile(f, dtype=np.int64, count=1)
             else:
                 seen = np.fromfile(f, dtype=np.int32, count=1)
-            self.header = torch.IntTensor([int(major), int(minor), int(revision), int(seen[0]) & 0x7fffffff])
-            self.seen = int(seen[0])
+            # The reference reads and DISCARDS the file header (nets.py:899-905): self.header stays [0,0,0,0], so a later
+            # save_weights always writes version 0.0.0 with an int32 `seen` — a 16-byte header both loaders read back.
+            # Copying a v0.2 file's major/minor here would make save_weights emit "0.2" with a 16-byte header, which every
+            # reader then mis-aligns by 4 bytes.  Only the image counter is kept (clamped to what int32 `seen` can hold).
+            self.seen = int(seen[0]) & 0x7fffffff
 
             def read_into(t):
                 buf = np.fromfile(f, dtype=np.float32, count=t.numel())

@@ -44,6 +44,24 @@ def bbox_iou(box1, box2, x1y1x2y2=True):
     return carea / uarea
 
 
+def bbox_ious(boxes1, boxes2, x1y1x2y2=True):
+    """nets2_utils.py:100-131 — element-wise IoU of two box sets given as [4, n] tensors (row i = coordinate i); returns
+    a float32 tensor [n] on the inputs' device.  One libmcb200 kernel with the reference's float32 operation order."""
+    lib = _lib.load()
+    _lib.require_cuda(boxes1, "bbox_ious")
+    _lib.require_cuda(boxes2, "bbox_ious")
+    if boxes1.shape[0] != 4 or boxes2.shape != boxes1.shape:
+        raise ValueError("bbox_ious expects two [4, n] tensors of the same shape")
+    shape = boxes1.shape[1:]
+    b1 = boxes1.detach().float().reshape(4, -1).contiguous()
+    b2 = boxes2.detach().float().reshape(4, -1).contiguous()
+    out = torch.empty(b1.shape[1], dtype=torch.float32, device=b1.device)
+    with torch.cuda.device(b1.device):
+        _lib.check(lib.mc_bbox_ious(b1.data_ptr(), b2.data_ptr(), b1.shape[1], 1 if x1y1x2y2 else 0, out.data_ptr(),
+                                    _lib.stream_ptr()), "mc_bbox_ious")
+    return out.reshape(shape)
+
+
 # ------------------------------------------------------------------------------------------------ device forms
 def decode_device(output, conf_thresh, num_classes, anchors_list, anchors_cell, only_objectness=1, want_cls=False):
     """Region decode on the GPU.  Returns (boxes [B,P,8] float32, counts [B] int32, cls [B,P,nc] or None) where

@@ -28,6 +28,16 @@ def _apply_mask_inplace(weight, mask):
                                       _lib.stream_ptr()), "mc_apply_masks")
 
 
+def _normalised_mask(mask, weight):
+    """Mask as a contiguous float32 tensor of the weight's shape on the weight's device (bool / uint8 / float64 /
+    strided masks are converted; a shape mismatch raises)."""
+    if not torch.is_tensor(mask):
+        mask = torch.as_tensor(mask)
+    if mask.numel() != weight.numel():
+        raise ValueError("mask shape %s does not match weight shape %s" % (tuple(mask.shape), tuple(weight.shape)))
+    return mask.detach().to(device=weight.device, dtype=torch.float32).reshape(weight.shape).contiguous()
+
+
 class MaskedConv2d(nn.Conv2d):
     def __init__(self, in_channels, out_channels, kernel_size, stride=1,
                  padding=0, dilation=1, groups=1, bias=True):
@@ -38,6 +48,9 @@ class MaskedConv2d(nn.Conv2d):
 
     def set_mask(self, mask):
         # layers.py:41-47: register_buffer('mask'), weight.data *= mask, mask_flag = True
+        # The reference's `weight * mask` accepts any dtype / layout; the kernels read the buffer as dense float32 on the
+        # weight's device (engine_train passes mask.data_ptr() to the wgrad / dgrad packers), so it is normalised here.
+        mask = _normalised_mask(mask, self.weight)
         self.register_buffer('mask', mask)
         mask_var = self.get_mask()
         if mask_var.device != self.mask.device:
@@ -65,6 +78,7 @@ class MaskedLinear(nn.Linear):
         self.name = 'MaskedLinear'
 
     def set_mask(self, mask):
+        mask = _normalised_mask(mask, self.weight)
         self.register_buffer('mask', mask)
         mask_var = self.get_mask()
         if mask_var.device != self.mask.device:

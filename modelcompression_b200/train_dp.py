@@ -37,10 +37,19 @@ def disable(model):
     return model
 
 
+def _invalidate_eval_plan(model):
+    """The collectives above write through ``.data``: neither the autograd version counters nor the storage addresses
+    engine._plan_key watches change, so a compiled eval plan (folded BN, packed weights) would go stale silently."""
+    if hasattr(model, '_b200_plan'):
+        model._b200_plan = None
+        model._b200_watch = None
+
+
 def broadcast_parameters(model, src=0, group=None):
     """Every rank starts from rank ``src``'s parameters and buffers (masks included)."""
     for t in list(model.parameters()) + list(model.buffers()):
         dist.broadcast(t.data, src=src, group=group)
+    _invalidate_eval_plan(model)
 
 
 def allreduce_gradients(params, group=None):
@@ -67,3 +76,4 @@ def average_buffers(model, group=None):
         if b.is_floating_point() and b.dim() == 1:
             dist.all_reduce(b.data, group=group)
             b.data.div_(world)
+    _invalidate_eval_plan(model)

@@ -99,6 +99,36 @@ def test_weights_file_roundtrip(cfg_path, tmp_path):
             assert torch.equal(sa[k], sb[k]), k
 
 
+def test_weights_v02_header_load_then_save_is_readable(cfg_path, tmp_path):
+    """A darknet v0.2 file (int64 `seen`, 20-byte header — what the official yolov2-voc.weights is) must survive
+    load -> save -> load.  The reference discards the file's version on load (src/nets.py:899-905) and always writes
+    0.0.0 with an int32 `seen`; copying major/minor into self.header made save_weights write an unreadable file."""
+    torch.manual_seed(6)
+    a = mc.Darknet(cfg_path)
+    p0 = str(tmp_path / 'v0.weights')
+    a.save_weights(p0)
+    raw = open(p0, 'rb').read()
+    p2 = str(tmp_path / 'v2.weights')
+    with open(p2, 'wb') as f:
+        np.array([0, 2, 0], dtype=np.int32).tofile(f)
+        np.array([32013312], dtype=np.int64).tofile(f)
+        f.write(raw[16:])
+    b = mc.Darknet(cfg_path)
+    b.load_weights(p2)
+    assert b.header.tolist()[:3] == [0, 0, 0]  # the reference never touches self.header on load
+    assert b.seen == 32013312
+    p3 = str(tmp_path / 'resaved.weights')
+    b.save_weights(p3)
+    assert os.path.getsize(p3) == len(raw)  # 16-byte header again
+    c = mc.Darknet(cfg_path)
+    c.load_weights(p3)
+    assert c.seen == 32013312
+    sa, sc = a.state_dict(), c.state_dict()
+    for k in sa:
+        if not k.endswith('num_batches_tracked'):
+            assert torch.equal(sa[k], sc[k]), k
+
+
 def test_arg_nonzero_min_reference_quirks():
     assert arg_nonzero_min([0.0, 3.0, 2.0, 5.0]) == (2.0, 2)
     assert arg_nonzero_min([]) is None
