@@ -140,6 +140,26 @@ int mc_decode_region(const float* d_head, int B, int H, int W, int A, int nc, co
 int mc_nms_batched(float* d_boxes, const int* d_counts, int B, int cap, float nms_thresh,
                    int* d_keep, int* d_keep_counts, void* stream);
 
+/* mc_nms_batched plus what the batched evaluator needs from the same pass (src/predict.py:148-173):
+ *   d_counts == NULL: `d_boxes` is a DENSE slot table [B, cap, 8] (one row per (cy*W+cx)*A + a, element 7 = slot index
+ *                     for a candidate, -1 for a non-candidate — the output of the fused decode epilogue MC_EPI_DECODE);
+ *                     `d_keep` then holds slot indices.  Slot order == the reference's list order, so ties break alike.
+ *   d_row_counts [B] (may be NULL): rows image b contributes to the detection table — one per kept box, plus, when
+ *                     d_cls [B, cap, nc] is given (validation mode, nets2_utils.py:223-228), one per other class c
+ *                     with conf*cls[c] > conf_thresh.
+ *   d_cand_counts [B] (may be NULL): number of candidates per image.                                    */
+int mc_nms_detect(float* d_boxes, const int* d_counts, int B, int cap, float nms_thresh, int* d_keep,
+                  int* d_keep_counts, const float* d_cls, int nc, float conf_thresh, int* d_row_counts,
+                  int* d_cand_counts, void* stream);
+
+/* Detection rows [img, x, y, w, h, box_conf, cls_conf, cls_id] of B images written straight from the NMS output —
+ * replaces the per-class row emission of src/predict.py:157-173.  Image b's rows start at d_row_offsets[b] (int64,
+ * exclusive prefix sums of mc_nms_detect's d_row_counts) and are in NMS order; with d_cls (validation mode) the arg-max
+ * class row comes first, then the other passing classes in ascending order.  img = first_image + b.               */
+int mc_compact_detections(const float* d_boxes, const int* d_keep, const int* d_keep_counts, const float* d_cls,
+                          int B, int cap, int nc, float conf_thresh, int first_image,
+                          const int64_t* d_row_offsets, float* d_out, void* stream);
+
 /* Element-wise IoU of two box sets laid out [4, n] (row i = coordinate i of every box) — replaces bbox_ious,
  * src/nets2_utils.py:100-131 (x1y1x2y2 != 0: corner format; 0: centre format).  d_out[n].  fp32, reference op order. */
 int mc_bbox_ious(const float* d_boxes1, const float* d_boxes2, int64_t n, int x1y1x2y2, float* d_out, void* stream);
@@ -156,7 +176,27 @@ int mc_bbox_ious(const float* d_boxes1, const float* d_boxes2, int64_t n, int x1
 enum { MC_EPI_PNHWC = 0,      /* bf16 PNHWC at the same resolution, channel offset ch_off, row pitch ldc   */
        MC_EPI_REORG2 = 1,     /* bf16 PNHWC at (H/2,W/2): channel ((y&1)*2+(x&1))*N + n + ch_off (Reorg)   */
        MC_EPI_NCHW_F32 = 2,   /* fp32 NCHW [B,N,H,W] (network head)                                        */
-       MC_EPI_POOL2 = 3 };    /* bf16 PNHWC at (H/2,W/2) after 2x2/2 max-pool                              */
+       MC_EPI_POOL2 = 3,      /* bf16 PNHWC at (H/2,W/2) after 2x2/2 max-pool                              */
+       MC_EPI_DECODE = 4 };   /* network head + region decode fused: see mc_decode_params                  */
+
+/* MC_EPI_DECODE — get_region_boxes (src/nets2_utils.py:158-205) applied to the head convolution's accumulators in its
+ * epilogue: the thread that owns pixel (b, cy, cx) holds all A*(5+nc) logits of the cell, so sigmoid / exp / softmax /
+ * arg-max / threshold run there and the raw head never makes a round trip through HBM.  Output is the DENSE slot table
+ *   d_boxes [B, H*W*A, 8]: slot (cy*W+cx)*A + a = x/W, y/H, w/W, h/H, conf, cls_max_conf, (float)cls_max_id,
+ *                          (float)slot for a candidate (conf > thresh, or conf*cls_max_conf > thresh) else -1
+ *   d_cls   [B, H*W*A, nc] softmax probabilities of the candidates (may be NULL)
+ *   d_head  fp32 NCHW [B, A*(5+nc), H, W]: the raw head as MC_EPI_NCHW_F32 would store it (may be NULL)
+ * which mc_nms_detect consumes directly (d_counts = NULL).  Slot order is the reference's list order (cy, cx, anchor).
+ * Needs N == A*(5+nc) <= 256 (one N tile).  Arithmetic identical to mc_decode_region on the same fp32 logits.      */
+typedef struct mc_decode_params {
+  float* d_boxes;
+  float* d_cls;
+  float* d_head;
+  int A, nc;
+  float conf_thresh;
+  int only_objectness;
+  float anchors[32];     /* (w, h) pairs, A of them                                                      */
+} mc_decode_params;
 
 typedef struct mc_conv_desc {
   const void* d_in;      /* bf16 PNHWC [B*(H+1)*(W+1), Cin_ld]                                           */
@@ -179,6 +219,7 @@ typedef struct mc_conv_desc {
                          /* >= Cin meet zero weights and must hold finite values (the engine's pad channels are 0).  */
                          /* A box that lies wholly inside the tensor takes TMA's fast path: a partly out-of-bounds   */
                          /* inner box costs 28 us instead of 20 us on a 17-channel 1x1 layer at 104x104, batch 64.   */
+  const mc_decode_params* decode; /* MC_EPI_DECODE only (host pointer, copied at launch); d_out is unused then      */
 } mc_conv_desc;
 
 int mc_conv_fwd(const mc_conv_desc* desc, void* stream);

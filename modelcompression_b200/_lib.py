@@ -11,11 +11,19 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmcb200.so")
 
 MC_MAX_SEGMENTS = 64
-MC_EPI_PNHWC, MC_EPI_REORG2, MC_EPI_NCHW_F32, MC_EPI_POOL2 = 0, 1, 2, 3
+MC_EPI_PNHWC, MC_EPI_REORG2, MC_EPI_NCHW_F32, MC_EPI_POOL2, MC_EPI_DECODE = 0, 1, 2, 3, 4
 
 
 class McError(RuntimeError):
     """A libmcb200 entry point returned a non-zero status."""
+
+
+class mc_decode_params(ctypes.Structure):
+    _fields_ = [
+        ("d_boxes", c_void_p), ("d_cls", c_void_p), ("d_head", c_void_p),
+        ("A", c_int), ("nc", c_int), ("conf_thresh", c_float), ("only_objectness", c_int),
+        ("anchors", c_float * 32),
+    ]
 
 
 class mc_conv_desc(ctypes.Structure):
@@ -27,6 +35,7 @@ class mc_conv_desc(ctypes.Structure):
         ("ksize", c_int), ("leaky", c_int), ("epi_mode", c_int),
         ("ldc", c_int), ("ch_off", c_int),
         ("block_n", c_int), ("stages", c_int), ("block_k", c_int), ("in_cols", c_int),
+        ("decode", POINTER(mc_decode_params)),
     ]
 
 
@@ -61,6 +70,10 @@ _SIGNATURES = {
     "mc_decode_region": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(c_float), c_float, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p]),
     "mc_nms_batched": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "mc_nms_detect": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int, c_float,
+                              c_void_p, c_void_p, c_void_p]),
+    "mc_compact_detections": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int,
+                                      c_void_p, c_void_p, c_void_p]),
     "mc_bbox_ious": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "mc_reorg_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mc_conv_fwd": (c_int, [POINTER(mc_conv_desc), c_void_p]),

@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 #include "tmap.cuh"
+#include "decode_math.cuh"
 
 namespace {
 
@@ -61,6 +62,13 @@ struct ConvKParams {
   const float* shift;
   void* out;
   int ldc, ch_off, epi_mode, leaky;
+  // MC_EPI_DECODE (region decode fused into the head's epilogue)
+  float* dec_boxes;
+  float* dec_cls;
+  float* dec_head;
+  int dec_A, dec_nc, dec_only_obj;
+  float dec_thresh;
+  McAnchors dec_anc;
 };
 
 // 16 accumulator columns of one row: y = acc*scale + shift (-> leaky) ; rows outside the image become 0.
@@ -86,7 +94,7 @@ __device__ __forceinline__ void scale_act16(const uint32_t (&r)[16], const float
 template <int MODE>
 __device__ __forceinline__ void store16(const ConvKParams& p, const float (&v)[16], int nbase, long long out_row_base,
                                         bool vec_ok) {
-  if (MODE == MC_EPI_NCHW_F32) {
+  if (MODE == MC_EPI_NCHW_F32 || MODE == MC_EPI_DECODE) {
     float* out_f = reinterpret_cast<float*>(p.out);
     const long long hw = (long long)p.H * p.W;
 #pragma unroll
@@ -264,6 +272,53 @@ __device__ __forceinline__ void epilogue_loop(const ConvKParams& p, uint32_t tme
         }
         __syncwarp();  // wbuf is rewritten by the next chunk / tile
       }
+      if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
+      continue;
+    }
+
+    if (MODE == MC_EPI_DECODE) {
+      // Region decode in the epilogue (get_region_boxes, src/nets2_utils.py:158-205).  The thread owns pixel (b, y, x):
+      // its A*(5+nc) logits (= acc*scale + shift, the head's bias) are parked in the warp's shared-memory rows (row
+      // pitch block_n+1 floats: lanes hit different banks), the TMEM stage goes back to the MMA issuer at once, and the
+      // thread then decodes its A anchors from shared memory with the arithmetic of decode_math.cuh.
+      const int pitch_f = p.block_n + 1;
+      float* mine = reinterpret_cast<float*>(s_out) + (size_t)(quarter * 32 + lane) * pitch_f;
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        uint32_t r0[16];
+        ptx::tmem_ld_32x32b_x16(taddr_row + (uint32_t)c0, r0);
+        ptx::tmem_ld_wait();
+        float v[16];
+        scale_act16<LEAKY>(r0, sc + c0, sh + c0, true, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) mine[c0 + j] = v[j];
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+      if (interior) {
+        const int A = p.dec_A, nc = p.dec_nc, F = 5 + p.dec_nc;
+        const long long P = (long long)p.H * p.W * A;
+        const long long slot0 = (long long)(y * p.W + x) * A;
+        if (p.dec_head != nullptr) {
+          float* hd = p.dec_head + ((long long)b * p.N * p.H + y) * p.W + x;
+          const long long hw = (long long)p.H * p.W;
+          for (int n = 0; n < p.N; ++n) hd[n * hw] = mine[n];
+        }
+        for (int a = 0; a < A; ++a) {
+          const float* row = mine + a * F;
+          const McDecoded d = mc_decode_anchor([row](int f) { return row[f]; }, nc, x, y, p.W, p.H, p.dec_anc.w[a],
+                                               p.dec_anc.h[a], p.dec_thresh, p.dec_only_obj);
+          float* dst = p.dec_boxes + ((long long)b * P + slot0 + a) * 8;
+          reinterpret_cast<float4*>(dst)[0] = make_float4(d.bx, d.by, d.bw, d.bh);
+          reinterpret_cast<float4*>(dst)[1] =
+              make_float4(d.conf, d.cmax, (float)d.cid, d.cand ? (float)(slot0 + a) : -1.0f);
+          if (d.cand && p.dec_cls != nullptr) {
+            float* cd = p.dec_cls + ((long long)b * P + slot0 + a) * nc;
+            for (int c = 0; c < nc; ++c) cd[c] = __fdiv_rn(expf(__fsub_rn(row[5 + c], d.cls_max_logit)), d.cls_sum);
+          }
+        }
+      }
+      __syncwarp();  // the rows are rewritten by the next tile
       if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
       continue;
     }
@@ -523,6 +578,8 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     } else if (p.epi_mode == MC_EPI_REORG2) {
       if (p.leaky) epilogue_loop<MC_EPI_REORG2, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss);
       else epilogue_loop<MC_EPI_REORG2, false>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss);
+    } else if (p.epi_mode == MC_EPI_DECODE) {
+      epilogue_loop<MC_EPI_DECODE, false>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, s_out);
     } else {
       if (p.leaky) epilogue_loop<MC_EPI_NCHW_F32, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss);
       else epilogue_loop<MC_EPI_NCHW_F32, false>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss);
@@ -721,15 +778,26 @@ extern "C" int mc_conv_last_plan(int info[8]) {
 extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MC_CHECK_ARG(d != nullptr, "mc_conv_fwd: null descriptor");
-  MC_CHECK_ARG(d->d_in && d->d_wpack && d->d_scale && d->d_shift && d->d_out, "mc_conv_fwd: null pointer");
+  MC_CHECK_ARG(d->d_in && d->d_wpack && d->d_scale && d->d_shift && (d->d_out || d->epi_mode == MC_EPI_DECODE),
+               "mc_conv_fwd: null pointer");
   MC_CHECK_ARG(d->ksize == 1 || d->ksize == 3, "mc_conv_fwd: ksize must be 1 or 3 (got %d)", d->ksize);
   MC_CHECK_ARG(d->B > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->N > 0, "mc_conv_fwd: bad dims");
   MC_CHECK_ARG((d->Cin_ld % 8) == 0 && d->Cin <= d->Cin_ld, "mc_conv_fwd: Cin_ld must be a multiple of 8 >= Cin");
   MC_CHECK_ARG((d->Npad % 16) == 0 && d->Npad >= d->N, "mc_conv_fwd: Npad must be a multiple of 16 >= N");
   MC_CHECK_ARG(((uintptr_t)d->d_in & 15) == 0 && ((uintptr_t)d->d_wpack & 15) == 0 && ((uintptr_t)d->d_out & 15) == 0,
                "mc_conv_fwd: pointers must be 16-byte aligned");
-  MC_CHECK_ARG(d->epi_mode == MC_EPI_PNHWC || d->epi_mode == MC_EPI_REORG2 || d->epi_mode == MC_EPI_NCHW_F32,
+  MC_CHECK_ARG(d->epi_mode == MC_EPI_PNHWC || d->epi_mode == MC_EPI_REORG2 || d->epi_mode == MC_EPI_NCHW_F32 ||
+                   d->epi_mode == MC_EPI_DECODE,
                "mc_conv_fwd: unsupported epilogue mode %d", d->epi_mode);
+  const bool decode = d->epi_mode == MC_EPI_DECODE;
+  if (decode) {
+    const mc_decode_params* q = d->decode;
+    MC_CHECK_ARG(q != nullptr && q->d_boxes != nullptr, "mc_conv_fwd: MC_EPI_DECODE needs decode parameters with d_boxes");
+    MC_CHECK_ARG(q->A > 0 && q->A <= MC_MAX_ANCHORS && q->nc > 0 && q->A * (5 + q->nc) == d->N,
+                 "mc_conv_fwd: decode needs N == A*(5+nc) (N %d, A %d, nc %d)", d->N, q->A, q->nc);
+    MC_CHECK_ARG(d->Npad <= 256 && d->leaky == 0, "mc_conv_fwd: decode needs a linear head of <= 256 channels");
+    MC_CHECK_ARG(((uintptr_t)q->d_boxes & 15) == 0, "mc_conv_fwd: d_boxes must be 16-byte aligned");
+  }
   if (d->epi_mode == MC_EPI_REORG2) MC_CHECK_ARG((d->H % 2) == 0 && (d->W % 2) == 0, "mc_conv_fwd: reorg needs even H,W");
 
   const int ntaps = d->ksize * d->ksize;
@@ -771,6 +839,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
     if (block_n <= 0 && bn_mid >= 16 && bn_mid <= 256 && (bn_mid % 16) == 0 && d->Npad >= 512 && d->Npad < 960 && d->ksize == 3)
       block_n = bn_mid;
   }
+  if (decode) block_n = d->Npad;  // every logit of a cell in ONE accumulator row
   if (block_n <= 0) block_n = pick_block_n(d->Npad, m_tiles, (ntaps * Kc + 63) / 64, mc_num_sms(), false);  // 64-wide k-block units
   MC_CHECK_ARG(block_n >= 16 && block_n <= 256 && (block_n % 16) == 0, "mc_conv_fwd: block_n %d invalid", block_n);
   const int n_tiles = (d->Npad + block_n - 1) / block_n;
@@ -813,7 +882,8 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
                          ((d->ldc | d->ch_off) & 7) == 0;
   const int out_chunk = block_n <= 96 ? block_n : 64;
   const int out_pitch = stage_out ? out_chunk * 2 + 16 : 0;
-  const size_t out_stage_bytes = (size_t)128 * out_pitch;
+  // (decode epilogue: 128 rows x (block_n + 1) floats of logits)
+  const size_t out_stage_bytes = decode ? (size_t)128 * (block_n + 1) * 4 : (size_t)128 * out_pitch;
   auto plan_ring = [&](int ctas, int* st, int* ast, size_t* bytes) -> bool {
     const long long cap = (ctas == 1 ? 204 * 1024 : (227 * 1024) / ctas - 1024 - (long long)AUX_BYTES) - (long long)out_stage_bytes;
     if (b_resident) {
@@ -897,7 +967,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
     if (pair_env < 0 || pair_env > 2) pair_env = 1;
   }
   const bool pair_legal = share_dx && BLOCK_K == 64 && d->stages <= 0 && (block_n % 16) == 0 && block_n >= 64 && m_tiles >= 2;
-  const bool use_pair = pair_legal && (pair_env == 2 || (pair_env == 1 && block_n >= 192 && num_kb >= 36));
+  const bool use_pair = !decode && pair_legal && (pair_env == 2 || (pair_env == 1 && block_n >= 192 && num_kb >= 36));
   if (use_pair) {
     ctas = 1;
     a_stages = DEF_A_STAGES;
@@ -988,6 +1058,23 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   p.ch_off = d->ch_off;
   p.epi_mode = d->epi_mode;
   p.leaky = d->leaky;
+  p.dec_boxes = p.dec_cls = p.dec_head = nullptr;
+  p.dec_A = p.dec_nc = p.dec_only_obj = 0;
+  p.dec_thresh = 0.f;
+  if (decode) {
+    const mc_decode_params* q = d->decode;
+    p.dec_boxes = q->d_boxes;
+    p.dec_cls = q->d_cls;
+    p.dec_head = q->d_head;
+    p.dec_A = q->A;
+    p.dec_nc = q->nc;
+    p.dec_only_obj = q->only_objectness;
+    p.dec_thresh = q->conf_thresh;
+    for (int a = 0; a < MC_MAX_ANCHORS; ++a) {
+      p.dec_anc.w[a] = a < q->A ? q->anchors[2 * a] : 0.f;
+      p.dec_anc.h[a] = a < q->A ? q->anchors[2 * a + 1] : 0.f;
+    }
+  }
 
   if (use_pair) {
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(block_n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);

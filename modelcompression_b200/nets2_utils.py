@@ -91,10 +91,15 @@ def decode_device(output, conf_thresh, num_classes, anchors_list, anchors_cell, 
     return boxes, counts, cls
 
 
-def nms_device(boxes, counts, nms_thresh):
-    """Greedy NMS per image on decode_device output.  Returns (keep [B,P] int32, keep_counts [B] int32); keep[b,:kc]
-    are candidate indices in the reference's output order.  ``boxes[...,4]`` of suppressed candidates is zeroed in
-    place, as the reference mutates its input (nets2_utils.py:258)."""
+def nms_device(boxes, counts, nms_thresh, cls=None, conf_thresh=0.0, want_rows=False):
+    """Greedy NMS per image on a box table.  Returns (keep [B,P] int32, keep_counts [B] int32) — keep[b,:kc] are row
+    indices of the table in the reference's output order — and, with ``want_rows``, a third tensor [B] int32 with the
+    number of detection rows each image contributes (one per kept box; with ``cls`` also one per other class passing
+    conf*cls > conf_thresh, nets2_utils.py:223-228).  ``boxes[...,4]`` of suppressed candidates is zeroed in place, as
+    the reference mutates its input (nets2_utils.py:258).
+
+    counts [B] int32: rows [0, counts[b]) are image b's candidates (decode_device output).  counts=None: ``boxes`` is
+    the DENSE slot table of the fused decode epilogue (element 7 = slot index, -1 for a non-candidate)."""
     lib = _lib.load()
     _lib.require_cuda(boxes, "nms")
     B, P, S = boxes.shape
@@ -102,9 +107,19 @@ def nms_device(boxes, counts, nms_thresh):
     dev = boxes.device
     keep = torch.empty(B, P, dtype=torch.int32, device=dev)
     keep_counts = torch.empty(B, dtype=torch.int32, device=dev)
+    rows = torch.empty(B, dtype=torch.int32, device=dev) if want_rows else None
+    nc = 0
+    if cls is not None:
+        assert cls.is_contiguous() and cls.dtype == torch.float32 and cls.shape[:2] == (B, P)
+        nc = cls.shape[2]
     with torch.cuda.device(dev):
-        _lib.check(lib.mc_nms_batched(boxes.data_ptr(), counts.data_ptr(), B, P, float(nms_thresh), keep.data_ptr(),
-                                      keep_counts.data_ptr(), _lib.stream_ptr()), "mc_nms_batched")
+        _lib.check(lib.mc_nms_detect(boxes.data_ptr(), None if counts is None else counts.data_ptr(), B, P,
+                                     float(nms_thresh), keep.data_ptr(), keep_counts.data_ptr(),
+                                     None if cls is None else cls.data_ptr(), nc, float(conf_thresh),
+                                     None if rows is None else rows.data_ptr(), None, _lib.stream_ptr()),
+                   "mc_nms_detect")
+    if want_rows:
+        return keep, keep_counts, rows
     return keep, keep_counts
 
 

@@ -1,5 +1,6 @@
-"""CPU, gloo, world size 2: the host-side logic of the batch-sharded evaluation (shard ranges + the two-collective
-detection gather).  The per-shard compute is CUDA-only and is covered by test_gpu_eval.py."""
+"""CPU, gloo, world size 2: the host-side logic of the batch-sharded evaluation (shard ranges + the detection gather:
+one all_gather of counts, then unpadded rows sent once to the destination rank).  The per-shard compute is CUDA-only
+and is covered by test_gpu_eval.py; the same gather over NCCL on real GPUs by test_gpu_multi.py and bench.py."""
 import os
 import socket
 
@@ -33,10 +34,17 @@ def _worker(rank, world, port, n_images, out_dir):
     try:
         lo, hi = shard_range(n_images, rank, world)
         local = _fake_detections(lo, hi)
-        got = gather_detections(local)
         want = _fake_detections(0, n_images)
-        assert got.shape == want.shape, (got.shape, want.shape)
-        assert torch.equal(got, want), "rank-major gather must equal the single-process result"
+        got = gather_detections(local)  # default: delivered to rank 0 only
+        if rank == 0:
+            assert got.shape == want.shape, (got.shape, want.shape)
+            assert torch.equal(got, want), "rank-major gather must equal the single-process result"
+        else:
+            assert got.shape == (0, DET_COLS)
+        got1 = gather_detections(local, dst=1)
+        assert torch.equal(got1, want) if rank == 1 else got1.shape == (0, DET_COLS)
+        got = gather_detections(local, dst=None)  # every rank
+        assert got.shape == want.shape and torch.equal(got, want)
         torch.save(got, os.path.join(out_dir, 'rank%d.pt' % rank))
     finally:
         dist.destroy_process_group()

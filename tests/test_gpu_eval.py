@@ -41,6 +41,41 @@ def test_sharded_eval_matches_single_pass(cfg_path):
         np.testing.assert_allclose(mine, dec[b]['box'][keep], rtol=2e-5, atol=1e-7)
 
 
+def test_compact_detections_order_and_validation_rows():
+    """mc_compact_detections against a plain-torch statement of the row rules (src/predict.py:160-173 with the boxes of
+    nets2_utils.py:216-228): image-major, NMS order, arg-max class first, then the other passing classes ascending."""
+    from modelcompression_b200.eval import compact_detections, compact_detections_validation
+    boxes = torch.arange(2 * 4 * 8, dtype=torch.float32).view(2, 4, 8).to(DEV)
+    keep = torch.tensor([[2, 0, 0, 0], [3, 1, 2, 0]], dtype=torch.int32, device=DEV)
+    kc = torch.tensor([2, 3], dtype=torch.int32, device=DEV)
+    det = compact_detections(boxes, keep, kc, first_image_index=10).cpu()
+    assert det.shape == (5, 8)
+    assert det[:, 0].tolist() == [10, 10, 11, 11, 11]
+    assert torch.equal(det[0, 1:], boxes[0, 2, :7].cpu()) and torch.equal(det[4, 1:], boxes[1, 2, :7].cpu())
+    # validation rows on random tables (ragged keep lists incl. an image with none and one with > 256 kept boxes)
+    torch.manual_seed(5)
+    B, P, nc, thr = 5, 845, 20, 0.02
+    bx = torch.rand(B, P, 8)
+    bx[:, :, 6] = torch.randint(0, nc, (B, P)).float()
+    cls = torch.softmax(torch.randn(B, P, nc) * 2, dim=2)
+    kcs = [0, 1, 300, 845, 37]
+    keep = torch.stack([torch.randperm(P)[:P] for _ in range(B)]).to(torch.int32)
+    kc = torch.tensor(kcs, dtype=torch.int32)
+    want = []
+    for b in range(B):
+        for k in range(kcs[b]):
+            r = int(keep[b, k])
+            row = bx[b, r]
+            cid = int(row[6])
+            want.append([100.0 + b] + row[:5].tolist() + [float(row[5]), float(cid)])
+            for c in range(nc):
+                if c != cid and bool((row[4] * cls[b, r, c]) > torch.tensor(thr)):  # float32 product, strict
+                    want.append([100.0 + b] + row[:5].tolist() + [float(cls[b, r, c]), float(c)])
+    got = compact_detections_validation(bx.to(DEV), keep.to(DEV), kc.to(DEV), cls.to(DEV), thr, 100).cpu()
+    want = torch.tensor(want, dtype=torch.float32)
+    assert got.shape == want.shape and torch.equal(got, want)
+
+
 def test_do_detect_single_image(cfg_path):
     model = make_darknet(cfg_path, seed=0, kn=True, device=DEV)
     torch.manual_seed(9)

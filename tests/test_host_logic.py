@@ -7,7 +7,7 @@ import pytest
 import torch
 
 import modelcompression_b200 as mc
-from modelcompression_b200.eval import compact_detections, shard_range
+from modelcompression_b200.eval import shard_range
 from modelcompression_b200.pruning.weightPruning.methods import percentile_rank
 from modelcompression_b200.pruning.weightPruning.utils import arg_nonzero_min
 
@@ -150,16 +150,6 @@ def test_shard_range_covers_everything():
             for (a, b), (c, d) in zip(spans, spans[1:]):
                 assert b == c and a <= b and c <= d
     assert shard_range(4952, 7, 8) == (4333, 4952) and shard_range(4952, 0, 8) == (0, 619)
-
-
-def test_compact_detections_order():
-    boxes = torch.arange(2 * 4 * 8, dtype=torch.float32).view(2, 4, 8)
-    keep = torch.tensor([[2, 0, 0, 0], [3, 1, 2, 0]], dtype=torch.int32)
-    kc = torch.tensor([2, 3], dtype=torch.int32)
-    det = compact_detections(boxes, keep, kc, first_image_index=10)
-    assert det.shape == (5, 8)
-    assert det[:, 0].tolist() == [10, 10, 11, 11, 11]
-    assert torch.equal(det[0, 1:], boxes[0, 2, :7]) and torch.equal(det[4, 1:], boxes[1, 2, :7])
 
 
 def test_param_index_tracks_module_tree(cfg_path):
