@@ -254,6 +254,24 @@ int mc_conv_im2col_fwd(const void* d_in, int in_is_nchw_f32, const void* d_wexp,
                        const float* d_shift, void* d_out, int B, int H, int W, int Cin, int Cin_ld, int N, int ldc,
                        int leaky, int pool, void* stream);
 
+/* Thin 3x3 layers on the tensor cores WITHOUT an im2col build (csrc/conv_window.cu): un-swizzled UMMA descriptors read
+ * the overlapping receptive-field windows of a 16x8 output tile straight out of a shared-memory pixel patch.
+ *   in_kind 0: d_in bf16 PNHWC with pitch 8 (Cin <= 8), N <= 128, optional 2x2/2 max-pool taken across lanes in the
+ *              epilogue.  d_w: bf16 [nb][80], row n, column tap*8 + c = w[n,c,tap/3,tap%3] (columns 72..79 zero).
+ *   in_kind 1 / 2: d_in fp32 / uint8 NCHW image [B,3,H,W] (uint8 is scaled by 1/255 like ToTensor), pool = 1 required:
+ *              pool-window GEMM, d_w in mc_conv_im2col_fwd's expanded layout with CL = 4 and 64 columns:
+ *              row pos*npos + n, column (py*4+px)*4 + c = w[n,c,py-dy,px-dx] (pos = dy*2+dx).
+ * mc_conv_window_geometry reports npos, nb (rows of d_w, multiple of 16) and the column count of d_w.
+ * Writes channels [0,N) of the interior rows of a PNHWC bf16 buffer whose pad line/column are already zero.       */
+int mc_conv_window_supported(int Cin, int in_kind, int N, int pool);
+int mc_conv_window_geometry(int Cin, int in_kind, int N, int pool, int* npos, int* nb, int* kcols);
+int mc_conv_window_fwd(const void* d_in, int in_kind, const void* d_w, const float* d_scale, const float* d_shift,
+                       void* d_out, int B, int H, int W, int Cin, int N, int ldc, int leaky, int pool, void* stream);
+
+/* Debug aid (tuning builds, make TUNING=1): later mc_conv_window_fwd launches record clock64 stamps of CTA 0 into
+ * d_buf (128 x uint64); NULL switches it off.  A product build ignores the buffer.                              */
+int mc_debug_window_trace(void* d_buf);
+
 /* Debug aid: code of the first mbarrier wait that timed out inside mc_conv_im2col_fwd kernels (0 = none). */
 int mc_debug_im2col_timeout(void);
 

@@ -78,6 +78,7 @@ class CompiledDarknet(object):
             if self.lib.mc_device_ok() != 1:
                 raise RuntimeError("Darknet.forward: " + self.lib.mc_last_error_string().decode())
         self.shrink = bool(shrink)
+        self.use_window = bool(getattr(model, 'b200_window', True))  # (False: the im2col-build kernels, for A/B runs)
         self.bufs = []       # list[_Buf] (shapes depend on input H, W: compiled for the cfg's width/height lazily)
         self.ops = []        # list of dict
         self.block_out = {}  # models index -> _TensorRef
@@ -286,6 +287,46 @@ class CompiledDarknet(object):
             wd[:, torch.tensor([c < 0 for c in cidx], device=dev)] = 0
             return wd
 
+        # ---- no-build window kernel (csrc/conv_window.cu): the image layer with its pool, and <= 8-channel PNHWC inputs
+        win_kind = None
+        if self.use_window and plain_dst and k == 3 and (not pool or (H % 2 == 0 and W % 2 == 0)):
+            # Measured on B200 (tools/bench_window.py, batch 64): the window kernel wins for the narrow image layer
+            # (3 -> <= 8 filters: 92 -> 68 us) and for un-pooled <= 8-channel layers (37 -> 31 us); with 32 filters its
+            # epilogue (128 accumulator columns per pool window) costs what the im2col build saved (194 vs 192 us), and
+            # pooled pitch-8 layers lose to the pool-window GEMM of conv_im2col_tc.cu (49 vs 39 us).
+            if first and pool and c_phys_in <= 3 and n_phys <= 8:
+                win_kind = 1  # (2 when the caller hands in uint8 pixels: decided per call)
+            elif not first and not pool and src.ch_off == 0 and self.bufs[src.buf_id].ld == 8 and c_phys_in <= 8:
+                win_kind = 0
+        if win_kind is not None and self.lib.mc_conv_window_supported(c_phys_in, win_kind, n_phys, pool) == 1:
+            npos, nb, kcols = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+            _lib.check(self.lib.mc_conv_window_geometry(c_phys_in, win_kind, n_phys, pool, ctypes.byref(npos),
+                                                        ctypes.byref(nb), ctypes.byref(kcols)), "mc_conv_window_geometry")
+            npos, nb, kcols = npos.value, nb.value, kcols.value
+            wd = gathered_fp32().permute(0, 2, 3, 1)  # [n, r, s, c]
+            if win_kind == 0:
+                wk = torch.zeros(nb, 10, 8, device=dev)
+                wk[:n_phys, :9, :c_phys_in] = wd.reshape(n_phys, 9, c_phys_in)
+            else:
+                wk = torch.zeros(nb, 4, 4, 4, device=dev)
+                for dy in range(2):
+                    for dx in range(2):
+                        r0 = (dy * 2 + dx) * npos
+                        wk[r0:r0 + n_phys, dy:dy + 3, dx:dx + 3, :c_phys_in] = wd
+            wk = wk.reshape(nb, kcols).to(torch.bfloat16).contiguous()
+            Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+            ld = _pitch(n_phys)
+            bid = self._new_buf(Ho, Wo, ld, zero_init=True)  # pad line/column stay zero: the kernel never writes them
+            n_sc = max(_round_up(npos, 16), 16)
+            sc2 = torch.zeros(n_sc, device=dev)
+            sh2 = torch.zeros(n_sc, device=dev)
+            sc2[:n_phys] = sc
+            sh2[:n_phys] = sh
+            self.ops.append(dict(kind='window', src=src, w=wk, scale=sc2, shift=sh2, dst_buf=bid, N=n_phys, Cin=c_phys_in,
+                                 H=H, W=W, ld=ld, pool=pool, leaky=int(leaky), in_kind=win_kind,
+                                 name='window%s@%d' % ('+pool' if pool else '', ind), flops_per_image=op_flops))
+            return _TensorRef(bid, Ho, Wo, O, out_colsrc, const_out), ('pool' if pool else None)
+
         src_ok = first or (src.ch_off == 0 and self.bufs[src.buf_id].ld == (8 if c_phys_in <= 8 else 16))
         if plain_dst and k == 3 and src_ok and (H % 2 == 0 and W % 2 == 0 or not pool) and \
                 self.lib.mc_conv_im2col_supported(c_phys_in, 1 if first else 0, n_phys, pool) == 1:
@@ -490,7 +531,8 @@ class CompiledDarknet(object):
         x = x.detach()
         # uint8 images (what PIL / cv2 hand to do_detect, src/nets2_utils.py:346-352) are scaled by 1/255 inside the
         # first-layer kernel: 4x less host->device traffic than shipping the float tensor the reference builds on the CPU
-        u8 = x.dtype == torch.uint8 and self.ops and self.ops[0]['kind'] == 'im2col' and self.ops[0]['src'] is None
+        u8 = x.dtype == torch.uint8 and self.ops and self.ops[0]['kind'] in ('im2col', 'window') and \
+            self.ops[0]['src'] is None
         if x.dtype == torch.uint8 and not u8:
             x = x.float().div_(255.0)
         elif x.dtype not in (torch.float32, torch.uint8):
@@ -517,6 +559,16 @@ class CompiledDarknet(object):
                                                       op['shift'].data_ptr(), bufs[op['dst_buf']].data_ptr(), B,
                                                       op['H'], op['W'], op['Cin'], cin_ld, op['N'], op['ld'],
                                                       op['leaky'], op['pool'], stream), op['name'])
+                elif kind == 'window':
+                    s = op['src']
+                    if s is None:
+                        in_ptr, in_kind = x.data_ptr(), (2 if u8 else 1)
+                    else:
+                        in_ptr, in_kind = bufs[s.buf_id].data_ptr(), 0
+                    _lib.check(lib.mc_conv_window_fwd(in_ptr, in_kind, op['w'].data_ptr(), op['scale'].data_ptr(),
+                                                      op['shift'].data_ptr(), bufs[op['dst_buf']].data_ptr(), B, op['H'],
+                                                      op['W'], op['Cin'], op['N'], op['ld'], op['leaky'], op['pool'],
+                                                      stream), op['name'])
                 elif kind == 'direct':
                     s = op['src']
                     if s is None:

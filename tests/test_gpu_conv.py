@@ -22,6 +22,7 @@ from oracle import forward_oracle
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
+HEAD_REL_L2 = 2e-2
 
 
 def _bf16(t):
@@ -186,7 +187,7 @@ def test_filter_pruned_network_physically_shrunk(cfg_path):
     model.b200_shrink = True
     y_s, y_ref = _check_blocks(model, x1, 'f40-shrunk')
     plan = compile_darknet(model)
-    convs = [op for op in plan.ops if op['kind'] in ('conv', 'direct', 'im2col')]
+    convs = [op for op in plan.ops if op['kind'] in ('conv', 'direct', 'im2col', 'window')]
     kept = [int(k.numel()) for k in keep]
     # every non-head layer lost filters physically (+1 for the ones channel where constants are non-zero)
     assert all(op['N'] <= n + 1 for op, n in zip(convs[:-1], kept[:-1]))
@@ -223,19 +224,31 @@ def test_plan_invalidation_and_batch_sizes(cfg_path):
 
 
 def test_uint8_image_input_matches_float_path(cfg_path):
-    """uint8 NCHW images (do_detect's input, src/nets2_utils.py:346-352) are scaled by 1/255 inside the first-layer
-    kernel: same bf16 operands as feeding img.float().div(255.0), so the head is bit-identical."""
+    """uint8 NCHW images (do_detect's input, src/nets2_utils.py:346-352): the first-layer kernel feeds the exact integers
+    0..255 to the tensor core and folds ToTensor's 1/255 into its fp32 epilogue scale, so the uint8 path has NO input
+    rounding, while feeding img.float().div(255.0) rounds x/255 to bf16 first.  Both must match the fp32 oracle at the
+    first block to the bf16 output-rounding level (measured 1.9e-3 / 2.4e-3 relative L2) and at the head."""
     for shrink in (True, False):
         model = make_darknet(cfg_path, seed=0, kn=True, randbn=True, device=DEV)
         if shrink:
             model.set_masks(mc.quick_filter_prune(model, 40.))
         torch.manual_seed(4)
         xu = torch.randint(0, 256, (3, 3, 416, 416), dtype=torch.uint8, device=DEV)
+        xf = xu.float().div(255.0)
         with torch.no_grad():
-            for _ in range(3):  # eager, then graph capture, then replay
+            for _ in range(4):  # eager, static-buffer graph, ..., per-address graph
                 yu = model(xu)
-            yf = model(xu.float().div(255.0))
-        assert yu.dtype == torch.float32 and torch.equal(yu, yf)
+            plan = compile_darknet(model)
+            plan.run(xu, events=[])
+            a_u = plan.block_activation(1).clone()
+            yf = model(xf)
+            plan.run(xf, events=[])
+            a_f = plan.block_activation(1).clone()
+            ref, outs = forward_oracle.darknet_forward_fp32(model.blocks, model.state_dict(), xf, keep_outputs=True)
+        assert yu.dtype == torch.float32
+        assert _rel_l2(yu, ref) < HEAD_REL_L2 and _rel_l2(yf, ref) < HEAD_REL_L2
+        e_u, e_f = _rel_l2(a_u, outs[1]), _rel_l2(a_f, outs[1])
+        assert e_u < 4e-3 and e_f < 4e-3, (e_u, e_f)
 
 
 @pytest.mark.parametrize("C,O,k", [(32, 64, 3), (69, 145, 3), (17, 40, 1), (96, 32, 3)])
@@ -271,3 +284,110 @@ def test_conv_k_block_32(C, O, k):
     ref = F.leaky_relu(F.conv2d(x.bfloat16().float(), w.bfloat16().float(), padding=(k - 1) // 2), 0.1)
     assert (outs[0] - ref).abs().max() <= 5e-3 * ref.abs().max() + 2e-3
     assert (outs[1] - ref).abs().max() <= 5e-3 * ref.abs().max() + 2e-3
+
+
+# ------------------------------------------------------------------------------------------------ window kernel
+def _window_ref(x_bf, w, scale, shift, leaky, pool):
+    """fp32 reference of conv -> scale/shift -> leaky -> maxpool on bf16-rounded operands."""
+    y = F.conv2d(x_bf, _bf16(w), None, 1, 1)
+    y = y * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    if leaky:
+        y = F.leaky_relu(y, 0.1)
+    if pool:
+        y = F.max_pool2d(y, 2, 2)
+    return y
+
+
+def _run_window(x, in_kind, w, scale, shift, leaky, pool):
+    """x: in_kind 0 -> float NCHW (packed to pitch-8 PNHWC here); 1 -> float image; 2 -> uint8 image."""
+    import ctypes
+    from modelcompression_b200 import _lib
+    lib = _lib.load()
+    B, C, H, W = x.shape
+    N = w.shape[0]
+    assert lib.mc_conv_window_supported(C, in_kind, N, pool) == 1
+    npos, nb, kcols = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    _lib.check(lib.mc_conv_window_geometry(C, in_kind, N, pool, ctypes.byref(npos), ctypes.byref(nb), ctypes.byref(kcols)), "geom")
+    npos, nb, kcols = npos.value, nb.value, kcols.value
+    wd = w.permute(0, 2, 3, 1)
+    if in_kind == 0:
+        wk = torch.zeros(nb, 10, 8, device=DEV)
+        wk[:N, :9, :C] = wd.reshape(N, 9, C)
+    else:
+        wk = torch.zeros(nb, 4, 4, 4, device=DEV)
+        for dy in range(2):
+            for dx in range(2):
+                r0 = (dy * 2 + dx) * npos
+                wk[r0:r0 + N, dy:dy + 3, dx:dx + 3, :C] = wd
+    wk = wk.reshape(nb, kcols).to(torch.bfloat16).contiguous()
+    nsc = max((npos + 15) // 16 * 16, 16)
+    sc = torch.zeros(nsc, device=DEV)
+    sh = torch.zeros(nsc, device=DEV)
+    sc[:N], sh[:N] = scale, shift
+    Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+    ld = (N + 7) // 8 * 8
+    out = torch.zeros(B * (Ho + 1) * (Wo + 1), ld, dtype=torch.bfloat16, device=DEV)
+    s = _lib.stream_ptr()
+    if in_kind == 0:
+        xin = torch.empty(B * (H + 1) * (W + 1), 8, dtype=torch.bfloat16, device=DEV)
+        _lib.check(lib.mc_pack_pnhwc(x.contiguous().data_ptr(), xin.data_ptr(), B, H, W, C, 8, s), "pack")
+    else:
+        xin = x.contiguous()
+    _lib.check(lib.mc_conv_window_fwd(xin.data_ptr(), in_kind, wk.data_ptr(), sc.data_ptr(), sh.data_ptr(), out.data_ptr(),
+                                      B, H, W, C, N, ld, int(leaky), int(pool), s), "mc_conv_window_fwd")
+    y = torch.empty(B, N, Ho, Wo, device=DEV)
+    _lib.check(lib.mc_unpack_pnhwc(out.data_ptr(), y.data_ptr(), B, Ho, Wo, N, ld, 0, s), "unpack")
+    torch.cuda.synchronize()
+    # the kernel must leave the pad line / column of the destination untouched (zero)
+    o4 = out.view(B, Ho + 1, Wo + 1, ld)
+    assert float(o4[:, Ho].abs().max()) == 0.0 and float(o4[:, :, Wo].abs().max()) == 0.0
+    return y
+
+
+@pytest.mark.parametrize("B,C,H,W,N,pool", [
+    (2, 4, 32, 32, 1, True),      # shrunk conv2: 4 -> 1 with pool
+    (3, 1, 24, 40, 17, False),    # shrunk conv3: 1 -> 17, tiles ragged in both directions
+    (2, 4, 104, 104, 11, True),   # shrunk conv5
+    (1, 8, 16, 8, 16, False),     # exactly one tile
+    (2, 7, 52, 52, 80, False),    # five 16-column groups
+    (5, 3, 18, 22, 5, True),      # H, W not multiples of the tile, pooled
+    (64, 4, 208, 208, 1, True),   # the bench shape (21,632 tiles, persistent CTAs wrap many times)
+])
+def test_window_kernel_p8(B, C, H, W, N, pool):
+    torch.manual_seed(C * 100 + N)
+    x = torch.randn(B, C, H, W, device=DEV)
+    w = torch.randn(N, C, 3, 3, device=DEV) * 0.3
+    scale = torch.rand(N, device=DEV) + 0.5
+    scale[::3] *= -1  # negative BN scale: the pool must be taken AFTER scale/shift
+    shift = torch.randn(N, device=DEV) * 0.2
+    for leaky in (1, 0):
+        y = _run_window(x, 0, w, scale, shift, leaky, pool)
+        ref = _window_ref(_bf16(x), w, scale, shift, leaky, pool)
+        err = (y - ref).abs()
+        assert (err <= 5e-3 * ref.abs() + 2e-3 * ref.abs().max()).all(), "max rel %.3g" % _rel(y, ref)
+
+
+@pytest.mark.parametrize("B,H,W,N", [
+    (2, 64, 64, 4),       # shrunk conv1 (npos 4)
+    (1, 32, 16, 8),       # npos 8, exactly one tile
+    (2, 96, 160, 32),     # dense conv1: 4 positions x 32 filters = 128 columns
+    (3, 36, 48, 13),      # ragged tiles, npos 16
+    (64, 416, 416, 4),    # the bench shape
+])
+def test_window_kernel_image(B, H, W, N):
+    torch.manual_seed(N)
+    xu = torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8, device=DEV)
+    xf = xu.float().div(255.0)
+    w = torch.randn(N, 3, 3, 3, device=DEV) * 0.3
+    scale = torch.rand(N, device=DEV) + 0.5
+    scale[::3] *= -1
+    shift = torch.randn(N, device=DEV) * 0.2
+    ref = _window_ref(_bf16(xf), w, scale, shift, 1, True)
+    y1 = _run_window(xf, 1, w, scale, shift, 1, True)
+    err = (y1 - ref).abs()
+    assert (err <= 5e-3 * ref.abs() + 2e-3 * ref.abs().max()).all(), "max rel %.3g" % _rel(y1, ref)
+    # uint8 path: exact integer pixels on the tensor core, 1/255 in the fp32 epilogue -> no input rounding at all
+    y2 = _run_window(xu, 2, w, scale, shift, 1, True)
+    ref2 = _window_ref(xf, w, scale, shift, 1, True)
+    err2 = (y2 - ref2).abs()
+    assert (err2 <= 5e-3 * ref2.abs() + 2e-3 * ref2.abs().max()).all(), "max rel %.3g" % _rel(y2, ref2)
