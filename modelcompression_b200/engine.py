@@ -17,6 +17,7 @@ Activation layout between layers is PNHWC bf16 (include/mcb200.h).  There is no 
 library, a CPU tensor or an unsupported cfg raises.
 """
 import ctypes
+import weakref
 
 import torch
 import torch.nn as nn
@@ -473,19 +474,28 @@ class CompiledDarknet(object):
         if events is not None or not self.use_graph or not x.is_cuda or x.dtype not in (torch.float32, torch.uint8) or \
                 not x.is_contiguous() or x.requires_grad:
             return self._run_eager(x, events, detect)
-        # Graphs are keyed by the input ADDRESS (they read it in place).  An address seen a third time gets its own graph
-        # (zero-copy: a serving loop rotating over a few pinned device buffers); any other address is copied into a
+        # Graphs are keyed by the input ADDRESS (they read it in place).  A tensor OBJECT seen a third time gets its own
+        # graph (zero-copy: a serving loop rotating over a few device buffers it keeps); any other input is copied into a
         # plan-owned static input buffer and replays that buffer's graph (33 MB for a uint8 batch of 64: ~10 us), so
         # callers that hand in a fresh tensor every step never trigger a capture or an eager step.
         base = (tuple(x.shape), torch.cuda.current_stream(x.device).cuda_stream, x.dtype, detect)
         key = base + (x.data_ptr(),)
         entry = self._graphs.get(key)
+        if entry is not None and entry[2] is not x:
+            # same address, another tensor object: the allocator recycled the block of a dead tensor.  Not a pinned buffer.
+            entry = None
+            key = None
         if entry is None:
-            seen = self._graph_seen.get(key, 0) + 1
-            if len(self._graph_seen) > 4096:
-                self._graph_seen.clear()
-            self._graph_seen[key] = seen
-            if seen >= 3 and sum(1 for k in self._graphs if k[:4] == base) < 8:
+            seen = 0
+            if key is not None:
+                ref = self._graph_seen.get(key)
+                # only sightings of the SAME live tensor object count (a serving loop that keeps its input buffers);
+                # a recycled allocation shows up as a new object at an old address and starts over
+                seen = (ref[1] if ref is not None and ref[0]() is x else 0) + 1
+                if len(self._graph_seen) > 4096:
+                    self._graph_seen.clear()
+                self._graph_seen[key] = (weakref.ref(x), seen)
+            if seen >= 3 and sum(1 for k in self._graphs if k[:4] == base and k[4] != 'static') < 8:
                 entry = self._capture(key, x, detect)
             else:
                 skey = base + ('static',)

@@ -315,6 +315,190 @@ class Darknet(nn.Module):
                     t.detach().cpu().numpy().astype(np.float32).tofile(fp)
 
 
+    # ------------------------------------------------------------------ physically shrunk checkpoints
+    def channel_map(self):
+        """Which original channels survive filter pruning, per convolution: a filter whose (masked) weights are all zero
+        is removed from its layer and from the input of every consumer (through maxpool / reorg / route exactly like
+        engine.py).  The head convolution keeps all its outputs (the region layer's channel layout is positional).
+        Returns a list of dicts (one per conv, cfg order): block, keep_out, keep_in, out_full, in_full, nonzero_out
+        (filters with any non-zero weight: equals keep_out except for the head)."""
+        alive = {}          # block index -> list of surviving ORIGINAL channel indices of that block's output
+        full = {}           # block index -> original channel count
+        cur, cur_full = list(range(int(self.blocks[0]['channels']))), int(self.blocks[0]['channels'])
+        convs = [i for i, b in enumerate(self.blocks[1:]) if b['type'] == 'convolutional']
+        out = []
+        ind = -2
+        for block in self.blocks:
+            ind += 1
+            t = block['type']
+            if t == 'net':
+                continue
+            if t == 'convolutional':
+                conv = self.models[ind][0]
+                w = conv.weight.data
+                if getattr(conv, 'mask_flag', False):
+                    w = w * conv.mask.to(w.device)
+                nonzero = torch.nonzero(w.abs().amax(dim=(1, 2, 3)) > 0).flatten().tolist()
+                keep = list(range(w.shape[0])) if ind == convs[-1] else (nonzero or [0])
+                out.append(dict(block=ind, keep_out=keep, keep_in=list(cur), out_full=int(w.shape[0]),
+                                in_full=int(w.shape[1]), nonzero_out=nonzero))
+                cur, cur_full = keep, int(w.shape[0])
+            elif t == 'reorg':
+                s2 = int(block['stride']) ** 2
+                cur = [q * cur_full + c for q in range(s2) for c in cur]
+                cur_full = s2 * cur_full
+            elif t == 'route':
+                ls = [int(i) if int(i) > 0 else int(i) + ind for i in block['layers'].split(',')]
+                if len(ls) == 1:
+                    cur, cur_full = list(alive[ls[0]]), full[ls[0]]
+                else:
+                    cur = list(alive[ls[0]]) + [c + full[ls[0]] for c in alive[ls[1]]]
+                    cur_full = full[ls[0]] + full[ls[1]]
+            alive[ind], full[ind] = list(cur), cur_full
+        return out
+
+    def save_shrunk_weights(self, outfile, mapfile=None):
+        """Write the PHYSICALLY shrunk network as a darknet ``.weights`` file (same record layout as save_weights:
+        [bn.bias, bn.weight, running_mean, running_var, conv.weight] or [conv.bias, conv.weight], only the surviving
+        filters and input channels) plus a JSON side-car: the per-layer channel map, the BatchNorm parameters of the
+        removed filters and a cfg text with the shrunk filter counts.  A removed filter's output is the constant
+        leaky(beta - gamma*mean/sqrt(var+eps)) — zero with default BatchNorm statistics — and the consumers' weights on
+        removed input channels are NOT stored: per consumer the side-car keeps `fold` [kept_out, k, k] = sum over removed
+        input channels of w * constant (what engine.py feeds through its ones channel), or null when it is all zero.
+        Returns the side-car dict.  The reference never shrinks (README "params after pruning" counts zeros)."""
+        import json
+        cmap = self.channel_map()
+        side = dict(format='mcb200-shrunk-1', seen=int(self.seen), layers=[])
+        cfg_lines, conv_i = [], 0
+        prev_const = torch.zeros(int(self.blocks[0]['channels']))  # constant value of every input channel (0 if kept)
+        consts = {}  # block index -> per-channel constants of that block's output
+        ind_of = {id(m): i for i, m in enumerate(self.models)}
+        with open(outfile, 'wb') as fp:
+            np.array([0, 0, 0, int(self.seen) & 0x7fffffff], dtype=np.int32).tofile(fp)
+            for block, model in self._conv_blocks():
+                m = cmap[conv_i]
+                conv_i += 1
+                conv = model[0]
+                ko = torch.tensor(m['keep_out'], dtype=torch.long)
+                ki = torch.tensor(m['keep_in'], dtype=torch.long)
+                w = conv.weight.data.detach().cpu()
+                if getattr(conv, 'mask_flag', False):
+                    w = w * conv.mask.detach().cpu()
+                entry = dict(m)
+                # constants arriving on this conv's input: follow the graph like channel_map does
+                in_const = self._input_constants(m['block'], consts)
+                gone_in = torch.tensor(sorted(set(range(m['in_full'])) - set(m['keep_in'])), dtype=torch.long)
+                fold = torch.einsum('ocrs,c->ors', w[ko][:, gone_in], in_const[gone_in]) if gone_in.numel() else None
+                entry['fold'] = fold.tolist() if fold is not None and bool((fold != 0).any()) else None
+                out_const = torch.zeros(m['out_full'])
+                if int(block['batch_normalize']):
+                    bn = model[1]
+                    ps = [bn.bias.data, bn.weight.data, bn.running_mean, bn.running_var]
+                    ps = [t.detach().cpu() for t in ps]
+                    gone = torch.tensor(sorted(set(range(m['out_full'])) - set(m['keep_out'])), dtype=torch.long)
+                    entry['removed'] = gone.tolist()
+                    entry['removed_bn'] = [t[gone].tolist() for t in ps]
+                    shift = ps[0] - ps[2] * ps[1] / torch.sqrt(ps[3] + bn.eps)
+                    cval = torch.where(shift > 0, shift, 0.1 * shift) if block['activation'] == 'leaky' else shift
+                    out_const[gone] = cval[gone]
+                    for t in ps:
+                        t[ko].numpy().astype(np.float32).tofile(fp)
+                else:
+                    conv.bias.data.detach().cpu()[ko].numpy().astype(np.float32).tofile(fp)
+                w[ko][:, ki].contiguous().numpy().astype(np.float32).tofile(fp)
+                consts[m['block']] = out_const
+                side['layers'].append(entry)
+        conv_i = 0
+        for block in self.blocks:
+            cfg_lines.append('[%s]' % block['type'])
+            for k, v in block.items():
+                if k == 'type':
+                    continue
+                if block['type'] == 'convolutional' and k == 'filters':
+                    v = len(cmap[conv_i]['keep_out'])
+                cfg_lines.append('%s=%s' % ('type' if k == '_type' else k, v))
+            if block['type'] == 'convolutional':
+                conv_i += 1
+            cfg_lines.append('')
+        side['cfg'] = '\n'.join(cfg_lines)
+        if mapfile is not None:
+            with open(mapfile, 'w') as f:
+                json.dump(side, f)
+        return side
+
+    def _input_constants(self, conv_block, consts):
+        """Per-channel constants (values of removed channels) on the input of the conv at models[conv_block], given
+        the constants of every earlier conv's output; walks maxpool / reorg / route like channel_map."""
+        vals = {}
+        cur = torch.zeros(int(self.blocks[0]['channels']))
+        ind = -2
+        for block in self.blocks:
+            ind += 1
+            t = block['type']
+            if t == 'net':
+                continue
+            if ind == conv_block:
+                return cur
+            if t == 'convolutional':
+                cur = consts[ind]
+            elif t == 'reorg':
+                cur = cur.repeat(int(block['stride']) ** 2)
+            elif t == 'route':
+                ls = [int(i) if int(i) > 0 else int(i) + ind for i in block['layers'].split(',')]
+                cur = vals[ls[0]] if len(ls) == 1 else torch.cat([vals[ls[0]], vals[ls[1]]])
+            vals[ind] = cur
+        return cur
+
+    def load_shrunk_weights(self, weightfile, side):
+        """Inverse of save_shrunk_weights on a FULL-size model built from the original cfg: surviving weights go back to
+        their original positions, removed filters get zero weights, a zero mask and their recorded BatchNorm parameters.
+        The restored model equals the masked model the file was written from except for the (dropped) weights on removed
+        input channels, which only matter when a removed filter's constant is non-zero (side-car `fold`).  Returns the
+        masks (quick_filter_prune form: whole filters)."""
+        import json
+        if isinstance(side, str):
+            with open(side) as f:
+                side = json.load(f)
+        if side.get('format') != 'mcb200-shrunk-1':
+            raise ValueError("not a shrunk-weights side-car")
+        masks = []
+        with open(weightfile, 'rb') as f:
+            np.fromfile(f, dtype=np.int32, count=4)
+            self.seen = int(side.get('seen', 0))
+            for (block, model), m in zip(self._conv_blocks(), side['layers']):
+                conv = model[0]
+                ko = torch.tensor(m['keep_out'], dtype=torch.long)
+                ki = torch.tensor(m['keep_in'], dtype=torch.long)
+
+                def read(n):
+                    buf = np.fromfile(f, dtype=np.float32, count=n)
+                    if buf.size != n:
+                        raise IOError("%s: truncated shrunk weights file" % weightfile)
+                    return torch.from_numpy(buf)
+                if int(block['batch_normalize']):
+                    bn = model[1]
+                    gone = torch.tensor(m['removed'], dtype=torch.long)
+                    for t, rem in zip((bn.bias.data, bn.weight.data, bn.running_mean, bn.running_var), m['removed_bn']):
+                        v = torch.empty(m['out_full'])
+                        v[ko] = read(len(m['keep_out']))
+                        v[gone] = torch.tensor(rem, dtype=torch.float32)
+                        t.copy_(v.to(t.device))
+                else:
+                    v = torch.zeros(m['out_full'])
+                    v[ko] = read(len(m['keep_out']))
+                    conv.bias.data.copy_(v.to(conv.bias.device))
+                k = conv.kernel_size[0]
+                ws = read(len(m['keep_out']) * len(m['keep_in']) * k * k).view(len(m['keep_out']), len(m['keep_in']), k, k)
+                w = torch.zeros(m['out_full'], m['in_full'], k, k)
+                w[ko.view(-1, 1), ki.view(1, -1)] = ws
+                conv.weight.data.copy_(w.to(conv.weight.device))
+                mask = torch.zeros(m['out_full'], m['in_full'], k, k)
+                mask[torch.tensor(m['nonzero_out'], dtype=torch.long)] = 1.0  # whole filters (methods.py:75)
+                masks.append(mask)
+        self._b200_plan = None
+        return masks
+
+
 def getYOLOv2(cfgfile, weightfile):
     """nets.py:1069-1074."""
     model = Darknet(cfgfile)

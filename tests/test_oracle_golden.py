@@ -174,3 +174,61 @@ def test_region_loss_matches_reference_golden():
         assert abs(float(loss.detach()) - float(g['loss_' + name])) <= 2e-6 * abs(float(g['loss_' + name]))
         gref = torch.from_numpy(g['grad_' + name])
         assert float((out.grad - gref).abs().max()) <= 2e-6 * float(gref.abs().max())
+
+
+def test_weights_file_written_by_the_reference(tmp_path):
+    """a darknet .weights file written by the UNMODIFIED reference's save_weights
+    (oracle/make_golden_weights.py; src/nets.py:1007-1051) loads here tensor for tensor, this package's save_weights
+    reproduces it byte for byte, a darknet v0.2 copy (int64 `seen`) loads to the same tensors, and the shrunk-model
+    writer round-trips through its side-car."""
+    import torch
+    import modelcompression_b200 as mc
+    g = load_golden('weights_mini.npz')
+    cfg = tmp_path / 'mini.cfg'
+    cfg.write_bytes(g['cfg'].tobytes())
+    raw = g['file_bytes'].tobytes()
+    wfile = tmp_path / 'ref.weights'
+    wfile.write_bytes(raw)
+    model = mc.Darknet(str(cfg))
+    model.load_weights(str(wfile))
+    sd = model.state_dict()
+    keys = [k[3:] for k in g.files if k.startswith('sd.')]
+    assert sorted(keys) == sorted(sd.keys())
+    for k in keys:
+        if not k.endswith('num_batches_tracked'):
+            assert np.array_equal(sd[k].numpy(), g['sd.' + k]), k
+    assert model.seen == int(g['seen'])
+    out = tmp_path / 'mine.weights'
+    model.save_weights(str(out))
+    assert out.read_bytes() == raw
+    # v0.2 header variant of the same payload
+    v2 = tmp_path / 'v2.weights'
+    v2.write_bytes(np.array([0, 2, 0], np.int32).tobytes() + np.array([int(g['seen'])], np.int64).tobytes() + raw[16:])
+    m2 = mc.Darknet(str(cfg))
+    m2.load_weights(str(v2))
+    for k in keys:
+        if not k.endswith('num_batches_tracked'):
+            assert np.array_equal(m2.state_dict()[k].numpy(), g['sd.' + k]), k
+    # shrunk writer: zero three filters of the second conv, write, restore
+    conv = model.masked_convs()[1]
+    mask = torch.ones_like(conv.weight.data)
+    mask[[1, 5, 9]] = 0
+    conv.register_buffer('mask', mask)
+    conv.weight.data *= mask
+    conv.mask_flag = True
+    side = model.save_shrunk_weights(str(tmp_path / 's.weights'), str(tmp_path / 's.json'))
+    assert len(side['layers'][1]['keep_out']) == 13 and len(side['layers'][2]['keep_in']) == 13
+    assert 'filters=13' in side['cfg']
+    m3 = mc.Darknet(str(cfg))
+    masks = m3.load_shrunk_weights(str(tmp_path / 's.weights'), str(tmp_path / 's.json'))
+    assert torch.equal(masks[1], mask)
+    alive = torch.ones(16)
+    alive[[1, 5, 9]] = 0
+    sd3 = m3.state_dict()
+    for ka, a in model.state_dict().items():
+        if ka.endswith('num_batches_tracked') or ka.endswith('.mask'):
+            continue
+        if ka.endswith('conv3.weight'):
+            a = a * alive.view(1, -1, 1, 1)  # weights on removed input channels are dropped (side-car `fold`)
+        assert torch.equal(a, sd3[ka]), ka
+    assert side['layers'][2]['fold'] is not None  # rand BN statistics: the removed filters' constants are non-zero
