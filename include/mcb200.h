@@ -349,6 +349,14 @@ size_t mc_workspace_bytes_conv_wgrad_first(int B, int H, int W, int C, int O);
 int mc_conv_wgrad_first(const float* d_x, const void* d_dz, int ld_dz, int B, int H, int W, int C, int O,
                         const float* d_mask, float* d_dw, void* d_ws, size_t ws_bytes, void* stream);
 
+/* Momentum SGD over `nseg` parameter tensors in one launch — replaces torch.optim.SGD.step() as the reference
+ * configures it (src/train.py:144-147, stepped at :233-235; dampening 0, no nesterov): per element
+ *   d = g + weight_decay*p;  buf = first_step ? d : momentum*buf + d;  p -= lr*buf      (fp32, torch's operation order).
+ * Pruned weights have exactly zero gradients (mc_conv_wgrad multiplies by the mask) and therefore stay exactly zero. */
+int mc_sgd_momentum_step(float* const* h_param_ptrs, const float* const* h_grad_ptrs, float* const* h_buf_ptrs,
+                         const int64_t* h_sizes, int nseg, float lr, float momentum, float weight_decay,
+                         int first_step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

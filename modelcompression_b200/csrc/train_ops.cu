@@ -912,3 +912,92 @@ extern "C" int mc_conv_wgrad_first(const float* d_x, const void* d_dz, int ld_dz
   }
   return 0;
 }
+
+
+// ------------------------------------------------------------------------------------------------------------
+// Fused momentum SGD over all parameters in ONE launch — replaces torch.optim.SGD.step() as configured by the
+// reference (src/train.py:144-147: lr 1e-5, momentum 0.9, weight_decay 5e-4*batch, dampening 0, no nesterov;
+// stepped at src/train.py:233-235), i.e. per element
+//     d = g + wd * p;   buf = first_step ? d : momentum * buf + d;   p = p - lr * buf
+// with the same fp32 operation order (fma(wd, p, g); mul then add; fma(-lr, buf, p)).  Pruned weights carry exactly
+// zero gradients (the weight gradient kernels multiply by the mask), so they stay exactly zero: d = 0 + wd*0.
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr int SGD_MAX_SEG = 96;
+struct SgdTable {
+  float* p[SGD_MAX_SEG];
+  const float* g[SGD_MAX_SEG];
+  float* buf[SGD_MAX_SEG];
+  unsigned int start4[SGD_MAX_SEG + 1];  // prefix sums of ceil(size / 4)
+  unsigned int size[SGD_MAX_SEG];
+  int nseg;
+};
+
+__global__ void __launch_bounds__(256) sgd_momentum_kernel(const __grid_constant__ SgdTable t, float lr, float momentum,
+                                                           float wd, int first_step) {
+  const unsigned int total4 = t.start4[t.nseg];
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+    int lo = 0, hi = t.nseg - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (t.start4[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    const unsigned int e0 = (i - t.start4[lo]) * 4u, n = t.size[lo];
+    float* p = t.p[lo] + e0;
+    const float* g = t.g[lo] + e0;
+    float* b = t.buf[lo] + e0;
+    if (e0 + 4u <= n && ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)b)) & 15) == 0) {
+      float4 pv = *reinterpret_cast<float4*>(p);
+      const float4 gv = ld_stream_f4(reinterpret_cast<const float4*>(g));
+      float4 bv = first_step ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<float4*>(b);
+      float pe[4] = {pv.x, pv.y, pv.z, pv.w}, ge[4] = {gv.x, gv.y, gv.z, gv.w}, be[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float d = __fmaf_rn(wd, pe[j], ge[j]);
+        be[j] = first_step ? d : __fadd_rn(__fmul_rn(be[j], momentum), d);
+        pe[j] = __fmaf_rn(-lr, be[j], pe[j]);
+      }
+      *reinterpret_cast<float4*>(p) = make_float4(pe[0], pe[1], pe[2], pe[3]);
+      *reinterpret_cast<float4*>(b) = make_float4(be[0], be[1], be[2], be[3]);
+    } else {
+      for (unsigned int j = 0; j < 4u && e0 + j < n; ++j) {
+        const float d = __fmaf_rn(wd, p[j], g[j]);
+        const float nb = first_step ? d : __fadd_rn(__fmul_rn(b[j], momentum), d);
+        b[j] = nb;
+        p[j] = __fmaf_rn(-lr, nb, p[j]);
+      }
+    }
+  }
+}
+}  // namespace
+
+extern "C" int mc_sgd_momentum_step(float* const* h_param_ptrs, const float* const* h_grad_ptrs, float* const* h_buf_ptrs,
+                                    const int64_t* h_sizes, int nseg, float lr, float momentum, float weight_decay,
+                                    int first_step, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MC_CHECK_ARG(h_param_ptrs && h_grad_ptrs && h_buf_ptrs && h_sizes && nseg > 0, "mc_sgd_momentum_step: bad argument");
+  for (int s0 = 0; s0 < nseg; s0 += SGD_MAX_SEG) {
+    SgdTable t;
+    t.nseg = nseg - s0 < SGD_MAX_SEG ? nseg - s0 : SGD_MAX_SEG;
+    unsigned long long acc = 0;
+    for (int i = 0; i < t.nseg; ++i) {
+      MC_CHECK_ARG(h_param_ptrs[s0 + i] && h_grad_ptrs[s0 + i] && h_buf_ptrs[s0 + i] && h_sizes[s0 + i] > 0 &&
+                       h_sizes[s0 + i] < (1ll << 32),
+                   "mc_sgd_momentum_step: bad segment %d", s0 + i);
+      t.p[i] = h_param_ptrs[s0 + i];
+      t.g[i] = h_grad_ptrs[s0 + i];
+      t.buf[i] = h_buf_ptrs[s0 + i];
+      t.size[i] = (unsigned int)h_sizes[s0 + i];
+      t.start4[i] = (unsigned int)acc;
+      acc += ((unsigned long long)h_sizes[s0 + i] + 3) / 4;
+    }
+    MC_CHECK_ARG(acc < (1ull << 32), "mc_sgd_momentum_step: too many elements in one launch");
+    t.start4[t.nseg] = (unsigned int)acc;
+    long long blocks = ((long long)acc + 255) / 256;
+    const long long cap = (long long)mc_num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    sgd_momentum_kernel<<<(int)blocks, 256, 0, stream>>>(t, lr, momentum, weight_decay, first_step);
+    MC_LAUNCH_CHECK("sgd_momentum_kernel");
+  }
+  return 0;
+}
