@@ -379,7 +379,13 @@ def time_eval_pipeline(model, device, B, rank, world, tag, conf=0.005, n_images=
                        "NMS (0.45) + detection gather to rank 0" % (n_images, tag, B, conf),
            "images_per_s": n_images / dt, "seconds": dt, "detection_rows": int(dets.shape[0]) if rank == 0 else None,
            "includes": "images produced on the device per batch (uint8); no host->device copies"}
+    ph = {}
+    evaluate_sharded(model, get_batch, n_images, B, conf, 0.45, 0, rank, world, validation=True, phases=ph)
+    res["phases_rank%d" % rank] = {k: round(v, 5) for k, v in ph.items()}
     if world > 1:
+        allp = [None] * world
+        dist.all_gather_object(allp, {k: round(v, 5) for k, v in ph.items()})
+        res["phases_max_over_ranks"] = {k: max(p[k] for p in allp) for k in ph}
         # parity of the multi-GPU path on hardware: gathered detections == the 1-GPU result for the same images
         n_chk = min(n_images, 3 * B * world + 7)
         got = evaluate_sharded(model, get_batch, n_chk, B, conf, 0.45, 0, rank, world, validation=True)
@@ -393,6 +399,54 @@ def time_eval_pipeline(model, device, B, rank, world, tag, conf=0.005, n_images=
             assert ok, "gathered detections differ from the 1-GPU result"
         dist.barrier()
     return res
+
+
+def time_scorer_and_loss(model, device, B):
+    """SURVEY.md §8f N1 / N3, timed (they are tensor code on the device, not hand-written kernels): the VOC07 scorer
+    (voc_eval.mean_ap, src/predict.py:216-437) on the detections of 512 KN-init images against synthetic labels, and
+    RegionLoss forward + backward (src/nets.py:442-636) on a batch-B head."""
+    import numpy as np
+    import torch
+    from modelcompression_b200 import voc_eval
+    from modelcompression_b200.eval import evaluate_sharded
+    n = 512
+    get_batch = eval_image_source(device, B)
+    dets = evaluate_sharded(model, get_batch, n, B, 0.005, 0.45, 0, validation=True)
+    rng = np.random.RandomState(4)
+    rows = []
+    for i in range(n):  # SURVEY.md §8d: 1-5 boxes per image, class U{0..19}, centre U[0.1,0.9], size U[0.05,0.5]
+        for _ in range(rng.randint(1, 6)):
+            c = int(rng.randint(0, 20))
+            cx, cy = rng.uniform(0.1, 0.9, 2)
+            w, h = rng.uniform(0.05, 0.5, 2)
+            rows.append([i, c, max(int((cx - w / 2) * IMG), 1), max(int((cy - h / 2) * IMG), 1),
+                         min(int((cx + w / 2) * IMG), IMG), min(int((cy + h / 2) * IMG), IMG), 0])
+    gts = torch.tensor(rows, device=device)
+    voc_eval.mean_ap(dets, gts, 20, None, 0.5, True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    aps, m = voc_eval.mean_ap(dets, gts, 20, None, 0.5, True)
+    torch.cuda.synchronize()
+    t_map = time.perf_counter() - t0
+    torch.manual_seed(5)
+    head = torch.randn(B, 125, 13, 13, device=device, requires_grad=True)
+    target = torch.zeros(B, 250, device=device)
+    for b in range(B):
+        for j in range(3):
+            target[b, 5 * j:5 * j + 5] = torch.tensor([float((b + j) % 20), 0.2 + 0.2 * j, 0.3 + 0.1 * j, 0.2, 0.3])
+    ts = []
+    for it in range(5):
+        head.grad = None
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        loss = model.loss(head, target)
+        loss.backward()
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    return {"voc_map_scorer": {"seconds": t_map, "images": n, "detection_rows": int(dets.shape[0]), "gt_boxes": len(rows),
+                               "mAP": m, "note": "wall clock of voc_eval.mean_ap (device tensor code, 20-class loop)"},
+            "region_loss": {"ms_forward_backward": statistics.median(ts) * 1e3, "batch": B,
+                            "note": "wall clock of RegionLoss forward + backward (vectorised device tensor code)"}}
 
 
 def time_retrain(device, peaks, B, steps=5):
@@ -848,7 +902,10 @@ def main():
         with torch.no_grad():
             line["eval_pipeline"] = time_eval_pipeline(model, device, B, rank, world, "default-init worst case")
             kn = kn_model(device)
-            line["eval_pipeline_kn"] = time_eval_pipeline(kn, device, B, rank, world, "KN-init")
+            line["eval_pipeline_kn"] = time_eval_pipeline(kn, device, B, rank, world, "KN-init, dense un-pruned network")
+            if world == 1 and rank == 0:
+                with torch.enable_grad():
+                    line["next_rows"] = time_scorer_and_loss(kn, device, B)
             del kn
     if world > 1 and not args.no_retrain:
         torch.cuda.empty_cache()

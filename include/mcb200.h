@@ -220,14 +220,21 @@ typedef struct mc_conv_desc {
                          /* A box that lies wholly inside the tensor takes TMA's fast path: a partly out-of-bounds   */
                          /* inner box costs 28 us instead of 20 us on a 17-channel 1x1 layer at 104x104, batch 64.   */
   const mc_decode_params* decode; /* MC_EPI_DECODE only (host pointer, copied at launch); d_out is unused then      */
+  void* d_ws;            /* optional scratch (256-byte aligned, mc_workspace_bytes_conv_fwd bytes, its first 2 KB ZERO   */
+  size_t ws_bytes;       /* before the first use; launches leave them zero): lets the CTA-pair kernel split the partial  */
+                         /* last wave of tiles along K (stream-K).  NULL: whole tiles only.                             */
 } mc_conv_desc;
 
 int mc_conv_fwd(const mc_conv_desc* desc, void* stream);
+/* Scratch bytes mc_conv_fwd can use for this layer shape (0 = none).  The same buffer may serve every layer of a network
+ * (launches on one stream are ordered); contents are meaningless between calls.                                  */
+size_t mc_workspace_bytes_conv_fwd(const mc_conv_desc* desc);
 
 /* Which launch configuration the LAST mc_conv_fwd call of this host thread chose (tests / bench reporting):
  * info[0] = 1 CTA-pair kernel (tcgen05 cta_group::2, 256-row tiles, half of each weight tile per CTA), 0 single CTA
  * info[1] = tile width block_n      info[2] = resident CTAs per SM requested (1..3)
- * info[3] = 1 weights resident in shared memory for the whole launch      info[4] = 1 shared activation box (3x3)
+ * info[3] = single CTA: 1 weights resident in shared memory; CTA pair: units in the stream-K tail
+ * info[4] = 1 shared activation box (3x3)
  * info[5] = smem ring stages         info[6] = grid size                   info[7] = k-block (32 or 64)           */
 int mc_conv_last_plan(int info[8]);
 

@@ -36,6 +36,7 @@ class mc_conv_desc(ctypes.Structure):
         ("ldc", c_int), ("ch_off", c_int),
         ("block_n", c_int), ("stages", c_int), ("block_k", c_int), ("in_cols", c_int),
         ("decode", POINTER(mc_decode_params)),
+        ("d_ws", c_void_p), ("ws_bytes", c_size_t),
     ]
 
 
@@ -77,6 +78,7 @@ _SIGNATURES = {
     "mc_bbox_ious": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "mc_reorg_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mc_conv_fwd": (c_int, [POINTER(mc_conv_desc), c_void_p]),
+    "mc_workspace_bytes_conv_fwd": (c_size_t, [POINTER(mc_conv_desc)]),
     "mc_conv_last_plan": (c_int, [POINTER(c_int)]),
     "mc_conv_direct_supported": (c_int, [c_int, c_int, c_int]),
     "mc_conv_direct_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,

@@ -62,6 +62,12 @@ struct ConvKParams {
   const float* shift;
   void* out;
   int ldc, ch_off, epi_mode, leaky;
+  // stream-K tail of the CTA-pair kernel (sk_units > 0): the units of the last, partial wave are cut along K into equal
+  // spans, one per cluster; spans that do not end a unit leave their fp32 accumulator in the workspace
+  int sk_first, sk_units;        // first stream-K unit (the units before it run one per cluster and round), their number
+  int sk_gper, sk_total_g;       // K groups (one activation box = 3 taps) per unit; sk_units * sk_gper
+  unsigned int* sk_count;        // [sk_units] arrivals of partial writers (8 epilogue warps each), zeroed per launch
+  float* sk_part;                // [sk_units][2][256 rows][block_n] partial accumulators
   // MC_EPI_DECODE (region decode fused into the head's epilogue)
   float* dec_boxes;
   float* dec_cls;
@@ -591,6 +597,233 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp_idx == 1) ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// Work items of one cluster of the CTA-pair kernel: whole units first (cluster c: units c, c+G, ... < sk_first), then
+// its stream-K span.  Stream-K: the sk_units units of the partial last wave hold sk_total_g K groups; cluster c owns
+// groups [c*T/G, (c+1)*T/G) of the unit-major sequence, i.e. the END of one unit and / or the START of the next (a span
+// is shorter than a unit, so it touches at most two).  The START piece runs first and leaves its accumulator in the
+// workspace; the END piece is the unit's finisher: it adds the (at most two) earlier pieces and runs the epilogue.  The
+// earlier pieces were the FIRST thing their clusters did, so the finisher practically never waits.
+struct PairWork {
+  int unit;    // unit index (m-pair, n-tile)
+  int g0, g1;  // K groups [g0, g1) of the unit
+  int kind;    // 0 whole unit, 1 partial (dump to slot), 2 finisher (add n partials)
+  int aux;     // kind 1: slot; kind 2: number of partial pieces to add
+};
+
+struct PairWorkIter {
+  int next_full, step, sk_first;
+  int sk_state;  // 0: stream-K pieces not started, 1: first piece done, 2: finished
+  int c, G, gper, T, units;
+  __device__ __forceinline__ void init(const ConvKParams& p, int cluster_id, int num_clusters) {
+    next_full = cluster_id;
+    step = num_clusters;
+    sk_first = p.sk_first;
+    sk_state = p.sk_units > 0 ? 0 : 2;
+    c = cluster_id; G = num_clusters; gper = p.sk_gper; T = p.sk_total_g; units = p.sk_units;
+  }
+  __device__ __forceinline__ int span_begin(int cl) const { return (int)(((long long)cl * T) / G); }
+  __device__ __forceinline__ void describe(int u, int a, int b, PairWork& w) const {  // groups [a,b) of stream-K unit u
+    w.unit = sk_first + u;
+    w.g0 = a;
+    w.g1 = b;
+    // first cluster whose span reaches into unit u
+    int cf = c;
+    while (cf > 0 && span_begin(cf) > u * gper) --cf;
+    if (b == gper) {
+      w.kind = (a == 0) ? 0 : 2;
+      w.aux = c - cf;
+    } else {
+      w.kind = 1;
+      w.aux = c - cf;
+    }
+  }
+  __device__ __forceinline__ bool next(PairWork& w) {
+    if (next_full < sk_first) {
+      w.unit = next_full; w.g0 = 0; w.g1 = -1; w.kind = 0; w.aux = 0;  // g1 < 0: the whole K range
+      next_full += step;
+      return true;
+    }
+    if (sk_state == 2) return false;
+    const int r0 = span_begin(c), r1 = span_begin(c + 1);
+    if (r1 <= r0) { sk_state = 2; return false; }
+    const int u0 = r0 / gper, u1 = (r1 - 1) / gper;
+    if (u0 == u1) {
+      sk_state = 2;
+      describe(u0, r0 - u0 * gper, r1 - u0 * gper, w);
+      return true;
+    }
+    if (sk_state == 0) {  // the START piece of the later unit first
+      sk_state = 1;
+      describe(u1, 0, r1 - u1 * gper, w);
+      return true;
+    }
+    sk_state = 2;
+    describe(u0, r0 - u0 * gper, gper, w);
+    return true;
+  }
+};
+
+// Epilogue warps of the CTA-pair kernel: one pass per work item.  Whole units and finishers drain the accumulator
+// through scale/shift/leaky and store (a finisher first adds the partial accumulators of the unit's earlier K spans);
+// partial pieces park their raw fp32 accumulator in the workspace and count themselves in.
+template <int MODE, bool LEAKY>
+__device__ __forceinline__ void epilogue_loop_pair(const ConvKParams& p, uint32_t tmem_base, uint64_t* tmem_full_bar,
+                                                   uint64_t* tmem_empty_bar, float* s_ss, int cluster_id, int num_clusters,
+                                                   int pair_rank) {
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int et = threadIdx.x - 64;   // 0..127
+  const int quarter = warp_idx & 3;  // TMEM lane quarter this warp may access
+  const bool vec_ok = ((p.ldc | p.ch_off) & 7) == 0 && (MODE != MC_EPI_REORG2 || (p.N & 7) == 0);
+  int as = 0;
+  uint32_t aphase = 0;
+  const bool one_n_tile = p.n_tiles == 1;
+  if (one_n_tile) {
+    for (int i = et; i < p.block_n; i += 128) {
+      const bool ok = i < p.Npad;
+      s_ss[i] = ok ? __ldg(p.scale + i) : 0.f;
+      s_ss[256 + i] = ok ? __ldg(p.shift + i) : 0.f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+  }
+  PairWorkIter it;
+  it.init(p, cluster_id, num_clusters);
+  PairWork w;
+  while (it.next(w)) {
+    const int tile = w.unit;
+    const int n0 = (tile % p.n_tiles) * p.block_n;
+    const int m0 = (2 * (tile / p.n_tiles) + pair_rank) * BLOCK_M;
+    float* sc = s_ss + (one_n_tile ? 0 : as * 512);
+    float* sh = sc + 256;
+    if (!one_n_tile) {
+      for (int i = et; i < p.block_n; i += 128) {
+        const bool ok = (n0 + i) < p.Npad;
+        sc[i] = ok ? __ldg(p.scale + n0 + i) : 0.f;
+        sh[i] = ok ? __ldg(p.shift + n0 + i) : 0.f;
+      }
+    }
+    const int row = m0 + quarter * 32 + lane;
+    const int t = (int)(__umulhi((unsigned int)row, p.wp_mul) >> p.wp_shr);  // row / Wp (magic-number division)
+    const int x = row - t * p.Wp;
+    const int b = (int)(__umulhi((unsigned int)t, p.hp_mul) >> p.hp_shr);    // t / Hp
+    const int y = t - b * p.Hp;
+    const bool in_buf = row < p.M_rows;
+    const bool interior = in_buf && (x < p.W) && (y < p.H);
+    long long out_row_base = 0;
+    bool do_store = false;
+    if (MODE == MC_EPI_PNHWC) {
+      out_row_base = (long long)row * p.ldc + p.ch_off;
+      do_store = in_buf;  // pad rows are written as zeros to keep the layout invariant
+    } else if (MODE == MC_EPI_REORG2) {
+      const int Wo = p.W / 2 + 1, Ho = p.H / 2 + 1;
+      const long long orow = ((long long)b * Ho + (y >> 1)) * Wo + (x >> 1);
+      out_row_base = orow * p.ldc + p.ch_off + ((y & 1) * 2 + (x & 1)) * p.N;
+      do_store = interior;
+    } else {  // MC_EPI_NCHW_F32
+      out_row_base = ((long long)b * p.N * p.H + y) * p.W + x;  // + n*H*W
+      do_store = interior;
+    }
+    if (!one_n_tile) asm volatile("bar.sync 1, 128;" ::: "memory");  // scale/shift of this tile visible to the 4 warps
+
+    ptx::mbar_wait(&tmem_full_bar[as], aphase);
+    ptx::tc_fence_after();
+    const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.acc_stride);
+    const int u_sk = tile - p.sk_first;  // (stream-K pieces only)
+    // partial tiles are stored [slot][column / 4][256 rows][4 floats]: a warp instruction (32 rows, one float4 each) is one
+    // contiguous 512-byte segment, for the writers and for the finisher that reads them back with the same mapping
+    const int prow = pair_rank * 128 + quarter * 32 + lane;
+    const size_t slot_stride = (size_t)256 * p.block_n;
+    float* part_unit = p.sk_part + (size_t)(u_sk < 0 ? 0 : u_sk) * 2 * slot_stride;
+    auto part_ptr = [&](int slot, int col) -> float* {  // col multiple of 4
+      return part_unit + (size_t)slot * slot_stride + ((size_t)(col >> 2) * 256 + prow) * 4;
+    };
+    if (w.kind == 1) {
+      // partial piece: raw accumulator -> workspace slot, then count this warp in (release)
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        uint32_t r0[16], r1[16];
+        const bool two = c0 + 16 < p.block_n;
+        ptx::tmem_ld_32x32b_x16(taddr_row + (uint32_t)c0, r0);
+        if (two) ptx::tmem_ld_32x32b_x16(taddr_row + (uint32_t)(c0 + 16), r1);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(part_ptr(w.aux, c0 + 4 * q)) = make_uint4(r0[4 * q], r0[4 * q + 1], r0[4 * q + 2], r0[4 * q + 3]);
+        if (two) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(part_ptr(w.aux, c0 + 16 + 4 * q)) = make_uint4(r1[4 * q], r1[4 * q + 1], r1[4 * q + 2], r1[4 * q + 3]);
+        }
+      }
+      ptx::tc_fence_before();
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        atomicAdd(p.sk_count + u_sk, 1u);
+        ptx::mbar_arrive_leader(&tmem_empty_bar[as]);
+      }
+    } else {
+      const int nparts = w.kind == 2 ? w.aux : 0;
+      if (nparts > 0) {
+        // the earlier K spans of this unit were the first thing their clusters computed: normally long finished
+        if (lane == 0) {
+          const unsigned int want = 8u * (unsigned int)nparts;
+          unsigned int spins = 0;
+          while (*reinterpret_cast<volatile unsigned int*>(p.sk_count + u_sk) < want) {
+            if (++spins > (1u << 24)) __trap();
+          }
+          // every writer has arrived and all 8 finisher warps must see that: the LAST finisher warp to get here puts the
+          // counter back to zero (second counter = finisher warps done), so the workspace needs no per-launch memset
+          if (atomicAdd(p.sk_count + 256 + u_sk, 1u) == 7u) {
+            p.sk_count[256 + u_sk] = 0u;
+            p.sk_count[u_sk] = 0u;
+          }
+        }
+        __syncwarp();
+        __threadfence();
+      }
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        uint32_t r0[16], r1[16];
+        const bool two = c0 + 16 < p.block_n;
+        ptx::tmem_ld_32x32b_x16(taddr_row + (uint32_t)c0, r0);
+        if (two) ptx::tmem_ld_32x32b_x16(taddr_row + (uint32_t)(c0 + 16), r1);
+        ptx::tmem_ld_wait();
+        if (!do_store) continue;
+        for (int s2 = 0; s2 < nparts; ++s2) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 a = __ldcg(reinterpret_cast<const float4*>(part_ptr(s2, c0 + 4 * q)));
+            r0[4 * q] = __float_as_uint(__uint_as_float(r0[4 * q]) + a.x);
+            r0[4 * q + 1] = __float_as_uint(__uint_as_float(r0[4 * q + 1]) + a.y);
+            r0[4 * q + 2] = __float_as_uint(__uint_as_float(r0[4 * q + 2]) + a.z);
+            r0[4 * q + 3] = __float_as_uint(__uint_as_float(r0[4 * q + 3]) + a.w);
+          }
+          if (two) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 a = __ldcg(reinterpret_cast<const float4*>(part_ptr(s2, c0 + 16 + 4 * q)));
+              r1[4 * q] = __float_as_uint(__uint_as_float(r1[4 * q]) + a.x);
+              r1[4 * q + 1] = __float_as_uint(__uint_as_float(r1[4 * q + 1]) + a.y);
+              r1[4 * q + 2] = __float_as_uint(__uint_as_float(r1[4 * q + 2]) + a.z);
+              r1[4 * q + 3] = __float_as_uint(__uint_as_float(r1[4 * q + 3]) + a.w);
+            }
+          }
+        }
+        float v[16];
+        scale_act16<LEAKY>(r0, sc + c0, sh + c0, interior, v);
+        store16<MODE>(p, v, n0 + c0, out_row_base, vec_ok);
+        if (two) {
+          scale_act16<LEAKY>(r1, sc + c0 + 16, sh + c0 + 16, interior, v);
+          store16<MODE>(p, v, n0 + c0 + 16, out_row_base, vec_ok);
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_leader(&tmem_empty_bar[as]);
+    }
+    if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // CTA-pair variant for the wide 3x3 layers (tcgen05 cta_group::2): two CTAs on the two SMs of a TPC compute a
 // 256 x block_n tile together.  Each CTA loads its own 128-row activation boxes but only HALF of every weight tile
@@ -660,10 +893,15 @@ conv_gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_b, const 
     if (lane == 0) {
       int s = 0, sa = 0;
       uint32_t phase = 0, pha = 0;
-      for (int unit = cluster_id; unit < total_units; unit += num_clusters) {
+      PairWorkIter it;
+      it.init(p, cluster_id, num_clusters);
+      PairWork w;
+      while (it.next(w)) {
+        const int unit = w.unit;
         const int n0 = (unit % p.n_tiles) * p.block_n + rank * (p.block_n / 2);
         const int m0 = (2 * (unit / p.n_tiles) + rank) * BLOCK_M;
-        for (int g = 0; g < 3 * p.kb_per_tap; ++g) {
+        const int gb = w.g0, ge = w.g1 < 0 ? 3 * p.kb_per_tap : w.g1;
+        for (int g = gb; g < ge; ++g) {
           const int dy = g / p.kb_per_tap, cb = g - dy * p.kb_per_tap;
           ptx::mbar_wait(&aempty_bar[sa], pha ^ 1u);
           if (rank == 0) ptx::mbar_arrive_expect_tx(&afull_bar[sa], 2 * A_BOX_BYTES);
@@ -685,11 +923,15 @@ conv_gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_b, const 
     if (rank == 0) {
       int s = 0, sa = 0, as = 0;
       uint32_t phase = 0, pha = 0, aphase = 0;
-      for (int unit = cluster_id; unit < total_units; unit += num_clusters) {
+      PairWorkIter it;
+      it.init(p, cluster_id, num_clusters);
+      PairWork w;
+      while (it.next(w)) {
         ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t tmem_acc = tmem_base + (uint32_t)(as * p.acc_stride);
-        for (int g = 0; g < 3 * p.kb_per_tap; ++g) {
+        const int gb = w.g0, ge = w.g1 < 0 ? 3 * p.kb_per_tap : w.g1;
+        for (int g = gb; g < ge; ++g) {
           const int nk = ((g % p.kb_per_tap) == p.kb_per_tap - 1) ? p.last_ksteps : 4;
           ptx::mbar_wait(&afull_bar[sa], pha);
           const uint32_t a_addr = ptx::smem_u32(tiles + (size_t)sa * A_BOX_STRIDE);
@@ -703,10 +945,10 @@ conv_gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_b, const 
               for (int k = 0; k < 4; ++k)
                 if (k < nk)
                   ptx::umma_bf16_ss_pair(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
-                                         (g > 0 || dx > 0 || k > 0) ? 1u : 0u);
+                                         (g > gb || dx > 0 || k > 0) ? 1u : 0u);
               ptx::umma_commit_pair(&empty_bar[s]);
               if (dx == 2) ptx::umma_commit_pair(&aempty_bar[sa]);
-              if (dx == 2 && g == 3 * p.kb_per_tap - 1) ptx::umma_commit_pair(&tmem_full_bar[as]);
+              if (dx == 2 && g == ge - 1) ptx::umma_commit_pair(&tmem_full_bar[as]);
             }
             __syncwarp();
             if (++s == p.stages) { s = 0; phase ^= 1u; }
@@ -719,14 +961,14 @@ conv_gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_b, const 
   } else {
     // ===================== epilogue: warps 2..5 of both CTAs =====================
     if (p.epi_mode == MC_EPI_PNHWC) {
-      if (p.leaky) epilogue_loop<MC_EPI_PNHWC, true, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, nullptr, cluster_id, num_clusters, total_units, rank);
-      else epilogue_loop<MC_EPI_PNHWC, false, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, nullptr, cluster_id, num_clusters, total_units, rank);
+      if (p.leaky) epilogue_loop_pair<MC_EPI_PNHWC, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, rank);
+      else epilogue_loop_pair<MC_EPI_PNHWC, false>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, rank);
     } else if (p.epi_mode == MC_EPI_REORG2) {
-      if (p.leaky) epilogue_loop<MC_EPI_REORG2, true, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, nullptr, cluster_id, num_clusters, total_units, rank);
-      else epilogue_loop<MC_EPI_REORG2, false, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, nullptr, cluster_id, num_clusters, total_units, rank);
+      if (p.leaky) epilogue_loop_pair<MC_EPI_REORG2, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, rank);
+      else epilogue_loop_pair<MC_EPI_REORG2, false>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, rank);
     } else {
-      if (p.leaky) epilogue_loop<MC_EPI_NCHW_F32, true, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, nullptr, cluster_id, num_clusters, total_units, rank);
-      else epilogue_loop<MC_EPI_NCHW_F32, false, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, nullptr, cluster_id, num_clusters, total_units, rank);
+      if (p.leaky) epilogue_loop_pair<MC_EPI_NCHW_F32, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, rank);
+      else epilogue_loop_pair<MC_EPI_NCHW_F32, false>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, rank);
     }
   }
 
@@ -773,6 +1015,15 @@ extern "C" int mc_conv_last_plan(int info[8]) {
   MC_CHECK_ARG(info != nullptr, "mc_conv_last_plan: null pointer");
   for (int i = 0; i < 8; ++i) info[i] = g_last_plan[i];
   return 0;
+}
+
+// Workspace the stream-K tail of the CTA-pair kernel can use for this layer (0: the layer never takes that path).  Upper
+// bound over every tile width the planner may pick: up to 148/2 stream-K units x 2 partial slots x 256 rows x 256 columns
+// of fp32, plus 2 KB of counters.  The counters must be ZERO before the first launch; every launch leaves them zero.
+extern "C" size_t mc_workspace_bytes_conv_fwd(const mc_conv_desc* d) {
+  if (d == nullptr || d->ksize != 3 || d->Cin <= 32 || d->Npad < 192) return 0;
+  const int clusters = mc_num_sms() / 2;
+  return (size_t)2048 + (size_t)clusters * 2 * 256 * 256 * sizeof(float);
 }
 
 extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
@@ -1058,6 +1309,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   p.ch_off = d->ch_off;
   p.epi_mode = d->epi_mode;
   p.leaky = d->leaky;
+  p.sk_first = 0; p.sk_units = 0; p.sk_gper = 0; p.sk_total_g = 0; p.sk_count = nullptr; p.sk_part = nullptr;
   p.dec_boxes = p.dec_cls = p.dec_head = nullptr;
   p.dec_A = p.dec_nc = p.dec_only_obj = 0;
   p.dec_thresh = 0.f;
@@ -1104,7 +1356,33 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
     const int m_pairs = (m_tiles + 1) / 2;
     const long long units = (long long)m_pairs * n_tiles;
     const int clusters = (int)(units < max_clusters ? units : max_clusters);
-    g_last_plan[0] = 1; g_last_plan[1] = block_n; g_last_plan[2] = 1; g_last_plan[3] = 0; g_last_plan[4] = 1;
+    // Stream-K for a SHORT partial last wave (at most half a wave of units left over, e.g. batch 32: 100 units over 74
+    // clusters — without it the 26 left-over units cost a whole second round).  Measured on B200 for the bench shapes
+    // (196 units = 2.65 waves): no gain, 0.8556 vs 0.8584 ms per step — the 48 clusters of a two-thirds-full last wave
+    // run their units faster because the operand feed from L2 is shared by fewer SMs, so whole tiles are kept there.
+    // Needs the caller's workspace; MCB200_CONV_STREAMK=0 disables, =2 forces it for any remainder (tuning builds).
+    p.sk_first = (int)units;
+    p.sk_units = 0;
+    p.sk_gper = 3 * p.kb_per_tap;
+    p.sk_total_g = 0;
+    p.sk_count = nullptr;
+    p.sk_part = nullptr;
+    {
+      const long long full = units / clusters, rem = units % clusters;
+      const char* e = mc_tune_env("MCB200_CONV_STREAMK");
+      const bool on = !(e && e[0] == '0');
+      const bool any_rem = e && e[0] == '2';
+      const size_t need = mc_workspace_bytes_conv_fwd(d);
+      if (on && full >= 1 && rem > 0 && (rem * 2 <= (long long)clusters || any_rem) && d->d_ws != nullptr && need > 0 &&
+          d->ws_bytes >= need && ((uintptr_t)d->d_ws & 255) == 0) {
+        p.sk_first = (int)(full * clusters);
+        p.sk_units = (int)rem;
+        p.sk_total_g = (int)rem * p.sk_gper;
+        p.sk_count = reinterpret_cast<unsigned int*>(d->d_ws);  // [256] writer arrivals, [256] finisher warps done
+        p.sk_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(d->d_ws) + 2048);
+      }
+    }
+    g_last_plan[0] = 1; g_last_plan[1] = block_n; g_last_plan[2] = 1; g_last_plan[3] = p.sk_units; g_last_plan[4] = 1;
     g_last_plan[5] = stages; g_last_plan[6] = 2 * clusters; g_last_plan[7] = BLOCK_K;
     conv_gemm_tcgen05_pair_kernel<<<2 * clusters, NUM_THREADS, smem_bytes, stream>>>(tm_b, tm_abox, p);
     MC_LAUNCH_CHECK("conv_gemm_tcgen05_pair_kernel");

@@ -524,6 +524,16 @@ class CompiledDarknet(object):
         self._graphs[key] = entry
         return entry
 
+    def _conv_workspace(self, nbytes):
+        """One scratch buffer for every conv launch of the plan (stream-K partial tiles of the CTA-pair kernel; launches
+        on a stream are ordered, and a captured graph keeps reading the same address)."""
+        ws = getattr(self, '_ws', None)
+        if ws is None or ws.numel() < nbytes:
+            if ws is not None and self._graphs:
+                raise RuntimeError("internal: conv workspace grew after a CUDA graph captured its address")
+            ws = self._ws = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)  # (counters start at zero)
+        return ws
+
     def supports_detect(self, model):
         """The fused decode epilogue needs the head to be the last op, all A*(5+nc) channels in one tile."""
         if not self.ops or self.ops[-1].get('epi') != _lib.MC_EPI_NCHW_F32:
@@ -642,6 +652,11 @@ class CompiledDarknet(object):
                     d.block_n = op.get('block_n', 0)
                     d.stages = op.get('stages', 0)
                     d.block_k = op.get('block_k', 0)
+                    if op.get('ws_bytes') is None:
+                        op['ws_bytes'] = int(lib.mc_workspace_bytes_conv_fwd(ctypes.byref(d)))
+                    if op['ws_bytes']:
+                        ws = self._conv_workspace(op['ws_bytes'])
+                        d.d_ws, d.ws_bytes = ws.data_ptr(), ws.numel()
                     _lib.check(lib.mc_conv_fwd(ctypes.byref(d), stream), op['name'])
                 else:
                     raise RuntimeError("unknown op " + kind)
@@ -759,6 +774,10 @@ def single_conv_forward(conv, x):
         d.B, d.H, d.W, d.Cin, d.Cin_ld, d.N, d.Npad = B, H, W, C, ld_in, O, Npad
         d.ksize, d.leaky, d.epi_mode, d.ldc, d.ch_off, d.block_n, d.stages = k, 0, _lib.MC_EPI_PNHWC, ld_out, 0, 0, 0
         d.block_k = kblk
+        need = int(lib.mc_workspace_bytes_conv_fwd(ctypes.byref(d)))
+        if need and not getattr(conv, 'b200_no_workspace', False):  # (attribute: tests compare with / without stream-K)
+            ws = torch.zeros(need, dtype=torch.uint8, device=dev)
+            d.d_ws, d.ws_bytes = ws.data_ptr(), need
         _lib.check(lib.mc_conv_fwd(ctypes.byref(d), s), "mc_conv_fwd")
         _lib.check(lib.mc_unpack_pnhwc(yb.data_ptr(), y.data_ptr(), B, H, W, O, ld_out, 0, s), "mc_unpack_pnhwc")
     return y

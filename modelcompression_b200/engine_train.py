@@ -263,12 +263,18 @@ def _kblk(C, k=1):
     return 32 if C <= 32 else 64
 
 
-def _conv_desc(in_ptr, wpack, scale, shift, out_ptr, B, H, W, Cin, Cin_ld, N, Npad, k, leaky, epi, ldc, ch_off, block_k=0):
+def _conv_desc(in_ptr, wpack, scale, shift, out_ptr, B, H, W, Cin, Cin_ld, N, Npad, k, leaky, epi, ldc, ch_off, block_k=0,
+               plan=None, dev=None):
     d = _lib.mc_conv_desc()
     d.block_k = block_k
     d.d_in, d.d_wpack, d.d_scale, d.d_shift, d.d_out = in_ptr, wpack, scale, shift, out_ptr
     d.B, d.H, d.W, d.Cin, d.Cin_ld, d.N, d.Npad = B, H, W, Cin, Cin_ld, N, Npad
     d.ksize, d.leaky, d.epi_mode, d.ldc, d.ch_off, d.block_n, d.stages = k, leaky, epi, ldc, ch_off, 0, 0
+    if plan is not None:
+        need = int(plan.lib.mc_workspace_bytes_conv_fwd(ctypes.byref(d)))
+        if need:
+            ws = plan.scratch(dev, 'conv_ws', (need,), torch.uint8, zero=True)
+            d.d_ws, d.ws_bytes = ws.data_ptr(), need
     return d
 
 
@@ -336,12 +342,12 @@ def _forward(plan, x, training_stats=True, after_layer=None, needs_backward=True
                 shift = plan.scratch(dev, 'head_shift', (Npad,), zero=True)
                 shift[:O].copy_(conv.bias.data)
                 d = _conv_desc(in_ptr, wpack.data_ptr(), ones.data_ptr(), shift.data_ptr(), y.data_ptr(), B, L.H, L.W, C,
-                               src.ld, O, Npad, k, 0, _lib.MC_EPI_NCHW_F32, 0, 0, kb)
+                               src.ld, O, Npad, k, 0, _lib.MC_EPI_NCHW_F32, 0, 0, kb, plan, dev)
                 _lib.check(lib.mc_conv_fwd(ctypes.byref(d), s), "head forward")
                 continue
             z = bufs[L.z.name]
             d = _conv_desc(in_ptr, wpack.data_ptr(), ones.data_ptr(), zeros.data_ptr(), z.data_ptr(), B, L.H, L.W, C,
-                           src.ld, O, Npad, k, 0, _lib.MC_EPI_PNHWC, L.z.ld, 0, kb)
+                           src.ld, O, Npad, k, 0, _lib.MC_EPI_PNHWC, L.z.ld, 0, kb, plan, dev)
             _lib.check(lib.mc_conv_fwd(ctypes.byref(d), s), "conv forward (block %d)" % L.ind)
         # ---- batch statistics + affine + leaky
         bn = L.bn
@@ -470,7 +476,7 @@ def _backward(plan, sv, dy, before_bn=None):
             ones = plan.const(dev, 1.0, Cpad)
             zeros = plan.const(dev, 0.0, Cpad)
             d = _conv_desc(dz_ptr, wpack.data_ptr(), ones.data_ptr(), zeros.data_ptr(), bufs[dname].data_ptr(), B, L.H, L.W,
-                           O, ld_dz, C, Cpad, k, 0, _lib.MC_EPI_PNHWC, src.ld, src.ch_off, kb)
+                           O, ld_dz, C, Cpad, k, 0, _lib.MC_EPI_PNHWC, src.ld, src.ch_off, kb, plan, dev)
             _lib.check(lib.mc_conv_fwd(ctypes.byref(d), s), "dgrad (block %d)" % L.ind)
             written.add(dname)
     for work, t in pending:  # the current stream waits for NCCL; gradients become the mean over the replicas

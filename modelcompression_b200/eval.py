@@ -142,7 +142,7 @@ def _detect_batch_device(model, x, conf_thresh, nms_thresh, only_objectness, wan
 
 @torch.no_grad()
 def evaluate_sharded(model, get_batch, n_images, batch_size, conf_thresh=0.005, nms_thresh=0.45, only_objectness=0,
-                     rank=0, world_size=1, group=None, gather=True, validation=False, fused=True):
+                     rank=0, world_size=1, group=None, gather=True, validation=False, fused=True, phases=None):
     """Run detection over images [0, n_images) split across ranks.
 
     get_batch(lo, hi) -> float32 or uint8 CUDA tensor [hi-lo, 3, H, W] for global image indices [lo, hi).
@@ -150,7 +150,18 @@ def evaluate_sharded(model, get_batch, n_images, batch_size, conf_thresh=0.005, 
     ranks on rank 0 (an empty tensor elsewhere; gather='all' delivers to every rank), else this rank's own.
     validation=True (with only_objectness=0) emits the multi-class rows the reference's scorer consumes
     (compact_detections_validation); feed them to voc_eval.mean_ap.
-    fused=True uses the head convolution's decode epilogue when the model's plan supports it (same results)."""
+    fused=True uses the head convolution's decode epilogue when the model's plan supports it (same results).
+    phases: optional dict; when given, the wall-clock seconds of the three phases (batches / compaction / gather) are
+    stored in it — this adds a device synchronisation after each phase, so it is a diagnostic, not the fast path."""
+    import time as _time
+
+    def _mark(name, t0):
+        if phases is not None:
+            torch.cuda.synchronize()
+            phases[name] = phases.get(name, 0.0) + _time.perf_counter() - t0
+        return _time.perf_counter()
+
+    t0 = _time.perf_counter()
     lo, hi = shard_range(n_images, rank, world_size)
     model.eval()
     want_cls = bool(validation) and not only_objectness
@@ -160,6 +171,7 @@ def evaluate_sharded(model, get_batch, n_images, batch_size, conf_thresh=0.005, 
         raw.append((b0,) + _detect_batch_device(model, get_batch(b0, b1), conf_thresh, nms_thresh, only_objectness,
                                                 want_cls, fused))
     dev = next(model.parameters()).device
+    t0 = _mark('batches_s', t0)
     if raw:
         # ONE synchronisation per shard: the table size.  Offsets stay on the device.
         rows = torch.cat([r[5] for r in raw]).to(torch.int64)
@@ -175,6 +187,9 @@ def evaluate_sharded(model, get_batch, n_images, batch_size, conf_thresh=0.005, 
             pos += nb
     else:
         local = torch.zeros(0, DET_COLS, dtype=torch.float32, device=dev)
+    t0 = _mark('compaction_s', t0)
     if not gather:
         return local
-    return gather_detections(local, group, None if gather == 'all' else 0)
+    out = gather_detections(local, group, None if gather == 'all' else 0)
+    _mark('gather_s', t0)
+    return out

@@ -286,6 +286,41 @@ def test_conv_k_block_32(C, O, k):
     assert (outs[1] - ref).abs().max() <= 5e-3 * ref.abs().max() + 2e-3
 
 
+@pytest.mark.parametrize("B,C,H,W,O,sk", [
+    (64, 512, 13, 13, 1024, False),   # 196 pair-units over 74 clusters = 2.65 waves: whole tiles (stream-K measured: no gain)
+    (32, 1006, 13, 13, 1018, True),   # 25 m-pairs x 4 n-tiles = 100 units: 26 in the stream-K tail, ragged channel tail
+    (40, 256, 13, 13, 768, True),     # 31 m-pairs x 3 n-tiles = 93 units: 19 in the tail, each cut into ~4 spans
+    (8, 256, 26, 26, 1024, True),     # 26x26 stage: 23 m-pairs x 4 n-tiles = 92 units, 18 in the tail
+])
+def test_conv_stream_k_tail(B, C, H, W, O, sk):
+    """CTA-pair kernel with the stream-K tail (workspace given) vs whole-tile scheduling (no workspace) vs fp32 conv on
+    bf16-rounded operands.  Stream-K only changes where the fp32 partial sums of a tile are added, so the two launches
+    agree to fp32 round-off before the bf16 output rounding."""
+    torch.manual_seed(C + O)
+    conv = mc.MaskedConv2d(C, O, 3, 1, 1, bias=True).to(DEV)
+    x = torch.randn(B, C, H, W, device=DEV)
+    y_sk = conv(x)
+    plan = _last_plan()
+    conv.b200_no_workspace = True
+    y_dp = conv(x)
+    assert plan['pair'] == 1 and (plan['resident'] > 0) == sk  # ('resident' slot = stream-K units of the pair kernel)
+    assert _last_plan()['pair'] == 1 and _last_plan()['resident'] == 0
+    ref = F.conv2d(_bf16(x), _bf16(conv.weight.data), conv.bias.data, 1, 1)
+    for y in (y_sk, y_dp):
+        err = (y - ref).abs()
+        assert (err <= 5e-3 * ref.abs() + 2e-3 * ref.abs().max()).all(), "max rel %.3g" % _rel(y, ref)
+    # same values up to one bf16 ulp where the fp32 sums straddle a rounding boundary
+    assert float((y_sk - y_dp).abs().max()) <= 8e-3 * float(ref.abs().max())
+    assert float((y_sk != y_dp).float().mean()) < 0.02
+    if not sk:
+        assert torch.equal(y_sk, y_dp)
+    for _ in range(3):  # repeated launches reuse the counters of the workspace (zeroed per launch)
+        assert torch.equal(conv_again := conv(x), y_dp)
+    conv.b200_no_workspace = False
+    for _ in range(3):
+        assert torch.equal(conv(x), y_sk)
+
+
 # ------------------------------------------------------------------------------------------------ window kernel
 def _window_ref(x_bf, w, scale, shift, leaky, pool):
     """fp32 reference of conv -> scale/shift -> leaky -> maxpool on bf16-rounded operands."""

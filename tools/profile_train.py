@@ -14,7 +14,7 @@ torch.manual_seed(0)
 model = mc.Darknet(mc.write_yolov2_voc_cfg()).to(dev)
 model.set_masks(mc.weight_prune(model, 90.))
 model.train()
-opt = torch.optim.SGD(model.parameters(), lr=1e-5, momentum=0.9, weight_decay=5e-4 * B)
+opt = mc.MaskedSGD(model.parameters(), lr=1e-5, momentum=0.9, weight_decay=5e-4 * B)
 torch.manual_seed(1)
 x = torch.rand(B, 3, 416, 416, device=dev)
 torch.manual_seed(3)
