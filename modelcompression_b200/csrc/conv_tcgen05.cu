@@ -66,8 +66,9 @@ struct ConvKParams {
   // spans, one per cluster; spans that do not end a unit leave their fp32 accumulator in the workspace
   int sk_first, sk_units;        // first stream-K unit (the units before it run one per cluster and round), their number
   int sk_gper, sk_total_g;       // K groups (one activation box = 3 taps) per unit; sk_units * sk_gper
+  int sk_clusters;               // clusters that take a stream-K span (<= 3 * sk_units: a unit has at most 4 pieces)
   unsigned int* sk_count;        // [sk_units] arrivals of partial writers (8 epilogue warps each), zeroed per launch
-  float* sk_part;                // [sk_units][2][256 rows][block_n] partial accumulators
+  float* sk_part;                // [sk_units][3][block_n / 4][256 rows][4] partial accumulators
   // MC_EPI_DECODE (region decode fused into the head's epilogue)
   float* dec_boxes;
   float* dec_cls;
@@ -598,10 +599,11 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 }
 
 // Work items of one cluster of the CTA-pair kernel: whole units first (cluster c: units c, c+G, ... < sk_first), then
-// its stream-K span.  Stream-K: the sk_units units of the partial last wave hold sk_total_g K groups; cluster c owns
-// groups [c*T/G, (c+1)*T/G) of the unit-major sequence, i.e. the END of one unit and / or the START of the next (a span
-// is shorter than a unit, so it touches at most two).  The START piece runs first and leaves its accumulator in the
-// workspace; the END piece is the unit's finisher: it adds the (at most two) earlier pieces and runs the epilogue.  The
+// its stream-K span.  Stream-K: the sk_units units of the partial last wave hold sk_total_g K groups; cluster c (of the
+// first G' = min(G, 3 * sk_units) clusters) owns groups [c*T/G', (c+1)*T/G') of the unit-major sequence, i.e. the END of
+// one unit and / or the START of the next (a span is shorter than a unit, so it touches at most two; a unit is cut into
+// at most four pieces).  The START piece runs first and leaves its accumulator in the workspace; the END piece is the
+// unit's finisher: it adds the (at most three) earlier pieces and runs the epilogue.  The
 // earlier pieces were the FIRST thing their clusters did, so the finisher practically never waits.
 struct PairWork {
   int unit;    // unit index (m-pair, n-tile)
@@ -618,8 +620,8 @@ struct PairWorkIter {
     next_full = cluster_id;
     step = num_clusters;
     sk_first = p.sk_first;
-    sk_state = p.sk_units > 0 ? 0 : 2;
-    c = cluster_id; G = num_clusters; gper = p.sk_gper; T = p.sk_total_g; units = p.sk_units;
+    c = cluster_id; G = p.sk_clusters; gper = p.sk_gper; T = p.sk_total_g; units = p.sk_units;
+    sk_state = (p.sk_units > 0 && c < G) ? 0 : 2;
   }
   __device__ __forceinline__ int span_begin(int cl) const { return (int)(((long long)cl * T) / G); }
   __device__ __forceinline__ void describe(int u, int a, int b, PairWork& w) const {  // groups [a,b) of stream-K unit u
@@ -733,7 +735,7 @@ __device__ __forceinline__ void epilogue_loop_pair(const ConvKParams& p, uint32_
     // contiguous 512-byte segment, for the writers and for the finisher that reads them back with the same mapping
     const int prow = pair_rank * 128 + quarter * 32 + lane;
     const size_t slot_stride = (size_t)256 * p.block_n;
-    float* part_unit = p.sk_part + (size_t)(u_sk < 0 ? 0 : u_sk) * 2 * slot_stride;
+    float* part_unit = p.sk_part + (size_t)(u_sk < 0 ? 0 : u_sk) * 3 * slot_stride;
     auto part_ptr = [&](int slot, int col) -> float* {  // col multiple of 4
       return part_unit + (size_t)slot * slot_stride + ((size_t)(col >> 2) * 256 + prow) * 4;
     };
@@ -1018,12 +1020,12 @@ extern "C" int mc_conv_last_plan(int info[8]) {
 }
 
 // Workspace the stream-K tail of the CTA-pair kernel can use for this layer (0: the layer never takes that path).  Upper
-// bound over every tile width the planner may pick: up to 148/2 stream-K units x 2 partial slots x 256 rows x 256 columns
+// bound over every tile width the planner may pick: up to 148/2 stream-K units x 3 partial slots x 256 rows x 256 columns
 // of fp32, plus 2 KB of counters.  The counters must be ZERO before the first launch; every launch leaves them zero.
 extern "C" size_t mc_workspace_bytes_conv_fwd(const mc_conv_desc* d) {
   if (d == nullptr || d->ksize != 3 || d->Cin <= 32 || d->Npad < 192) return 0;
   const int clusters = mc_num_sms() / 2;
-  return (size_t)2048 + (size_t)clusters * 2 * 256 * 256 * sizeof(float);
+  return (size_t)2048 + (size_t)clusters * 3 * 256 * 256 * sizeof(float);
 }
 
 extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
@@ -1309,7 +1311,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   p.ch_off = d->ch_off;
   p.epi_mode = d->epi_mode;
   p.leaky = d->leaky;
-  p.sk_first = 0; p.sk_units = 0; p.sk_gper = 0; p.sk_total_g = 0; p.sk_count = nullptr; p.sk_part = nullptr;
+  p.sk_first = 0; p.sk_units = 0; p.sk_gper = 0; p.sk_total_g = 0; p.sk_clusters = 0; p.sk_count = nullptr; p.sk_part = nullptr;
   p.dec_boxes = p.dec_cls = p.dec_head = nullptr;
   p.dec_A = p.dec_nc = p.dec_only_obj = 0;
   p.dec_thresh = 0.f;
@@ -1365,6 +1367,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
     p.sk_units = 0;
     p.sk_gper = 3 * p.kb_per_tap;
     p.sk_total_g = 0;
+    p.sk_clusters = 0;
     p.sk_count = nullptr;
     p.sk_part = nullptr;
     {
@@ -1378,6 +1381,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
         p.sk_first = (int)(full * clusters);
         p.sk_units = (int)rem;
         p.sk_total_g = (int)rem * p.sk_gper;
+        p.sk_clusters = (int)(3 * rem < clusters ? 3 * rem : clusters);
         p.sk_count = reinterpret_cast<unsigned int*>(d->d_ws);  // [256] writer arrivals, [256] finisher warps done
         p.sk_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(d->d_ws) + 2048);
       }

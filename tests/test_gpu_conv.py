@@ -288,9 +288,9 @@ def test_conv_k_block_32(C, O, k):
 
 @pytest.mark.parametrize("B,C,H,W,O,sk", [
     (64, 512, 13, 13, 1024, False),   # 196 pair-units over 74 clusters = 2.65 waves: whole tiles (stream-K measured: no gain)
-    (32, 1006, 13, 13, 1018, True),   # 25 m-pairs x 4 n-tiles = 100 units: 26 in the stream-K tail, ragged channel tail
-    (40, 256, 13, 13, 768, True),     # 31 m-pairs x 3 n-tiles = 93 units: 19 in the tail, each cut into ~4 spans
-    (8, 256, 26, 26, 1024, True),     # 26x26 stage: 23 m-pairs x 4 n-tiles = 92 units, 18 in the tail
+    (24, 512, 13, 13, 1024, True),    # 19 m-pairs x 4 n-tiles = 76 units: 2 in the tail, each cut into 3 spans
+    (16, 512, 26, 26, 1024, True),    # 26x26 stage: 46 m-pairs x 4 = 184 units, 36 in the tail (spans of ~half a unit)
+    (16, 1006, 26, 26, 1018, True),   # the same with the shrunk net's ragged channel-block tail inside the K spans
 ])
 def test_conv_stream_k_tail(B, C, H, W, O, sk):
     """CTA-pair kernel with the stream-K tail (workspace given) vs whole-tile scheduling (no workspace) vs fp32 conv on

@@ -12,7 +12,7 @@ from modelcompression_b200.engine import compile_darknet
 
 dense = 'dense' in sys.argv
 tag = sys.argv[-1] if len(sys.argv) > 1 else ''
-B = 64
+B = int(os.environ.get("BENCH_B", "64"))
 dev = torch.device('cuda:0')
 torch.manual_seed(0)
 model = mc.Darknet(mc.write_yolov2_voc_cfg()).to(dev).eval()
