@@ -1,7 +1,7 @@
 """Turn the raw gpurun_out/ captures of tools/run_final_evidence.sh into the tracked summaries under profiles/:
-  r1_launches_bench_final.csv (+ _summary.csv)   per-kernel totals of the launch list of the bench command
-  r1_ncu_full_conv_gemm_summary.csv              one row per conv GEMM launch of a forward (ncu --set full)
-  r1_ncu_full_conv_gemm.json                     DRAM traffic of those launches (bench.py's roofline.traffic)
+  r2_launches_bench_final.csv (+ _summary.csv)   per-kernel totals of the launch list of the bench command
+  r2_ncu_full_conv_gemm_summary.csv              one row per conv GEMM launch of a forward (ncu --set full)
+  r2_ncu_full_conv_gemm.json                     DRAM traffic of those launches (bench.py's roofline.traffic)
 Run here (no GPU needed): python tools/summarize_profiles.py"""
 import csv
 import json
@@ -30,8 +30,8 @@ def launch_summary():
         a[0] += 1
         a[1] += float(r[vi].replace(',', '')) / 1e6  # ns -> ms
     tot = sum(a[1] for a in agg.values())
-    shutil.copy(src, os.path.join(OUT, 'r1_launches_bench_final.csv'))
-    with open(os.path.join(OUT, 'r1_launches_bench_final_summary.csv'), 'w') as f:
+    shutil.copy(src, os.path.join(OUT, 'r2_launches_bench_final.csv'))
+    with open(os.path.join(OUT, 'r2_launches_bench_final_summary.csv'), 'w') as f:
         w = csv.writer(f)
         w.writerow(['kernel', 'launches', 'total_ms', 'share_of_captured'])
         for name, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -50,7 +50,7 @@ def ncu_summary():
             'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'launch__registers_per_thread',
             'launch__cluster_size', 'smsp__cycles_active.avg', 'sm__cycles_elapsed.max']
     idx = [hdr.index(w) for w in want if w in hdr]
-    with open(os.path.join(OUT, 'r1_ncu_full_conv_gemm_summary.csv'), 'w') as f:
+    with open(os.path.join(OUT, 'r2_ncu_full_conv_gemm_summary.csv'), 'w') as f:
         w = csv.writer(f)
         w.writerow([hdr[i] for i in idx])
         w.writerow([units[i] for i in idx])
@@ -69,7 +69,7 @@ def ncu_summary():
                          "64, the %d conv GEMM launches of one forward)" % n,
                "launches": n, "dram_read_mbytes_total": rd, "dram_write_mbytes_total": wr,
                "dram_bytes_per_launch": (rd + wr) * 1e6 / n},
-              open(os.path.join(OUT, 'r1_ncu_full_conv_gemm.json'), 'w'), indent=1)
+              open(os.path.join(OUT, 'r2_ncu_full_conv_gemm.json'), 'w'), indent=1)
     print('ncu full:', n, 'launches,', round(rd + wr, 1), 'MB DRAM traffic')
 
 
@@ -90,7 +90,7 @@ def train_summary(steps=7):
         a[0] += 1
         a[1] += float(r[vi].replace(',', '')) / 1e6
     tot = sum(a[1] for a in agg.values())
-    with open(os.path.join(OUT, 'r1_launches_train_step_summary.csv'), 'w') as f:
+    with open(os.path.join(OUT, 'r2_launches_train_step_summary.csv'), 'w') as f:
         w = csv.writer(f)
         w.writerow(['kernel', 'launches_per_step', 'ms_per_step', 'share'])
         for name, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -104,4 +104,4 @@ if __name__ == '__main__':
     train_summary()
     launch_summary()
     ncu_summary()
-    shutil.copy(os.path.join(GP, 'bench_final.json'), os.path.join(OUT, 'r1_bench_v9.json'))
+    shutil.copy(os.path.join(GP, 'bench_final.json'), os.path.join(OUT, 'r2_bench_final.json'))
