@@ -279,6 +279,11 @@ int mc_conv_window_fwd(const void* d_in, int in_kind, const void* d_w, const flo
  * d_buf (128 x uint64); NULL switches it off.  A product build ignores the buffer.                              */
 int mc_debug_window_trace(void* d_buf);
 
+/* Debug aid: later single-CTA mc_conv_fwd launches record globaltimer stamps (32 x uint64 per CTA: entry, set-up done,
+ * first operands landed, per-tile MMA issue / accumulator ready / epilogue done, exit) into d_buf (32*8*grid bytes);
+ * NULL switches it off.  tools/trace_conv.py prints the timelines.                                              */
+int mc_debug_conv_trace(void* d_buf);
+
 /* Debug aid: code of the first mbarrier wait that timed out inside mc_conv_im2col_fwd kernels (0 = none). */
 int mc_debug_im2col_timeout(void);
 

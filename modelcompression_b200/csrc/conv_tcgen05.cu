@@ -52,6 +52,7 @@ struct ConvKParams {
   int acc_stages;  // accumulator stages: the MMA issuer runs this many tiles ahead of the epilogue
   int out_pitch;   // > 0: PNHWC epilogue stages each warp's 32 rows in shared memory (row pitch in bytes) and writes them out coalesced
   int out_chunk;   // columns staged at a time (<= 64)
+  int tma_bufs;    // > 0: PNHWC epilogue writes whole 64-column chunks with TMA stores from this many 4 KB slabs per warp
   unsigned int wp_mul, wp_shr, hp_mul, hp_shr;  // magic-number division by Wp and Hp (row -> x, y, b)
   int last_ksteps;  // UMMA K steps (16 channels) that hold real channels in the LAST channel block of a tap
   int b_resident;   // share_dx only: all weight tiles stay in shared memory for the whole launch (one N tile, small K)
@@ -76,7 +77,17 @@ struct ConvKParams {
   int dec_A, dec_nc, dec_only_obj;
   float dec_thresh;
   McAnchors dec_anc;
+  unsigned long long* dbg;  // mc_debug_conv_trace: globaltimer stamps, 32 slots per CTA (nullptr: no tracing)
 };
+
+// Timeline stamps of the single-CTA kernel (slot layout in tools/trace_conv.py)
+__device__ __forceinline__ void conv_stamp(const ConvKParams& p, int slot) {
+  if (p.dbg != nullptr && slot < 32) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.dbg[(size_t)blockIdx.x * 32 + slot] = t;
+  }
+}
 
 // 16 accumulator columns of one row: y = acc*scale + shift (-> leaky) ; rows outside the image become 0.
 template <bool LEAKY>
@@ -156,13 +167,119 @@ __device__ __forceinline__ void pack16_to_smem(const float (&v)[16], uint8_t* ds
   }
 }
 
+// 16 fp32 -> 16 bf16 -> the two 16-byte chunks (index chunk, chunk + 1) of this lane's 128-byte row of a TMA store
+// slab.  The slab has the tensor map's 128-byte swizzle: chunk j of row r sits at chunk position j ^ (r & 7).
+__device__ __forceinline__ void pack16_to_slab(const float (&v)[16], uint8_t* row, int chunk, int lane) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[g * 8 + 0], v[g * 8 + 1]);
+    __nv_bfloat162 h1 = __floats2bfloat162_rn(v[g * 8 + 2], v[g * 8 + 3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(v[g * 8 + 4], v[g * 8 + 5]);
+    __nv_bfloat162 h3 = __floats2bfloat162_rn(v[g * 8 + 6], v[g * 8 + 7]);
+    uint4 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&h0);
+    pk.y = *reinterpret_cast<uint32_t*>(&h1);
+    pk.z = *reinterpret_cast<uint32_t*>(&h2);
+    pk.w = *reinterpret_cast<uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(row + (((chunk + g) ^ (lane & 7)) << 4)) = pk;
+  }
+}
+
+// PNHWC epilogue of one accumulator tile through TMA stores.  A warp owns 32 rows; every whole 64-column chunk of the
+// tile is converted into the warp's 4 KB slab (32 rows x 128 B, swizzled like the tensor map of the output) and leaves
+// as ONE bulk tensor store — 128-byte rows, issued by one lane, asynchronous — instead of 16-byte pieces one row pitch
+// apart per thread (measured: ~38 cycles per output column and tile, 4..7.6 us for a 208..256-wide tile, which
+// throttles short-K layers and is exposed after the last tile of every CTA).  With two slabs per warp the conversion of
+// chunk i+1 overlaps the store of chunk i.  The tile's last block_n % 64 columns take direct stores; rows and columns
+// outside the output tensor are clipped by TMA.  add(r, col) lets a stream-K finisher add partial accumulators.
+template <bool LEAKY, bool PAIR, bool WIDE_LD, typename AddFn>
+__device__ __forceinline__ void epilogue_tile_tma(const ConvKParams& p, const CUtensorMap* tm_out, uint32_t taddr_row,
+                                                  const float* sc, const float* sh, bool interior, bool in_buf,
+                                                  int row0, int n0, long long out_row_base, bool vec_ok, uint8_t* slab,
+                                                  int& buf, uint64_t* empty_bar, AddFn add) {
+  const int lane = threadIdx.x & 31;
+  int cols_valid = ((p.N - n0 + 7) >> 3) << 3;  // whole 8-groups up to the last one holding a real channel
+  if (cols_valid > p.block_n) cols_valid = p.block_n;
+  const int full_cols = p.block_n & ~63;
+  for (int cc = 0; cc < full_cols && cc < cols_valid; cc += 64) {
+    uint8_t* sb = slab + (size_t)buf * 4096;
+    if (lane == 0) {  // the store that last read this slab has finished reading it
+      if (p.tma_bufs >= 2) ptx::bulk_wait_group_read<1>();
+      else ptx::bulk_wait_group_read<0>();
+    }
+    __syncwarp();
+    uint8_t* mine = sb + lane * 128;
+    if (WIDE_LD) {
+      // all 64 columns of the chunk in flight before the one wait (register budget of the 1-CTA-per-SM variants)
+      uint32_t r[4][16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ptx::tmem_ld_32x32b_x16(taddr_row + (uint32_t)(cc + 16 * q), r[q]);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        add(r[q], cc + 16 * q);
+        float v[16];
+        scale_act16<LEAKY>(r[q], sc + cc + 16 * q, sh + cc + 16 * q, interior, v);
+        pack16_to_slab(v, mine, 2 * q, lane);
+      }
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t r0[16], r1[16];
+        ptx::tmem_ld_32x32b_x16(taddr_row + (uint32_t)(cc + 32 * h), r0);
+        ptx::tmem_ld_32x32b_x16(taddr_row + (uint32_t)(cc + 32 * h + 16), r1);
+        ptx::tmem_ld_wait();
+        add(r0, cc + 32 * h);
+        add(r1, cc + 32 * h + 16);
+        float v[16];
+        scale_act16<LEAKY>(r0, sc + cc + 32 * h, sh + cc + 32 * h, interior, v);
+        pack16_to_slab(v, mine, 4 * h, lane);
+        scale_act16<LEAKY>(r1, sc + cc + 32 * h + 16, sh + cc + 32 * h + 16, interior, v);
+        pack16_to_slab(v, mine, 4 * h + 2, lane);
+      }
+    }
+    ptx::fence_proxy_async_smem();  // this lane's slab writes -> visible to the TMA (async proxy)
+    __syncwarp();
+    if (lane == 0) {
+      ptx::tma_store_2d(tm_out, sb, n0 + cc, row0);
+      ptx::bulk_commit_group();
+    }
+    if (p.tma_bufs >= 2) buf ^= 1;
+  }
+  for (int c0 = full_cols; c0 < p.block_n; c0 += 32) {
+    uint32_t r0[16], r1[16];
+    const bool two = c0 + 16 < p.block_n;
+    ptx::tmem_ld_32x32b_x16(taddr_row + (uint32_t)c0, r0);
+    if (two) ptx::tmem_ld_32x32b_x16(taddr_row + (uint32_t)(c0 + 16), r1);
+    ptx::tmem_ld_wait();
+    if (!in_buf) continue;
+    add(r0, c0);
+    if (two) add(r1, c0 + 16);
+    float v[16];
+    scale_act16<LEAKY>(r0, sc + c0, sh + c0, interior, v);
+    store16<MC_EPI_PNHWC>(p, v, n0 + c0, out_row_base, vec_ok);
+    if (two) {
+      scale_act16<LEAKY>(r1, sc + c0 + 16, sh + c0 + 16, interior, v);
+      store16<MC_EPI_PNHWC>(p, v, n0 + c0 + 16, out_row_base, vec_ok);
+    }
+  }
+  // this warp has finished reading the accumulator stage: hand it back to the MMA issuer
+  ptx::tc_fence_before();
+  __syncwarp();
+  if (lane == 0) {
+    if (PAIR) ptx::mbar_arrive_leader(empty_bar);
+    else ptx::mbar_arrive(empty_bar);
+  }
+}
+
 // Epilogue warps (threads 64..191): per tile, stage the tile's scale/shift in shared memory (double-buffered with
 // the accumulator stage, one named barrier per tile), then drain the accumulator 32 columns at a time.
 // PAIR (CTA-pair kernel): `tile` counts (m-tile pair, n-tile) units of the cluster, this CTA owns m-tile 2*pair + rank,
 // and the accumulator stage is handed back on the LEADER CTA's barrier (the MMA issuer waits for both epilogues).
-template <int MODE, bool LEAKY, bool PAIR = false>
+template <int MODE, bool LEAKY, bool PAIR = false, bool WIDE_LD = false>
 __device__ __forceinline__ void epilogue_loop(const ConvKParams& p, uint32_t tmem_base, uint64_t* tmem_full_bar,
                                               uint64_t* tmem_empty_bar, float* s_ss, uint8_t* s_out = nullptr,
+                                              const CUtensorMap* tm_out = nullptr,
                                               int tile0 = -1, int tile_step = 0, int total_units = 0, int pair_rank = 0) {
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -173,6 +290,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvKParams& p, uint32_t tme
   const bool vec_ok = ((p.ldc | p.ch_off) & 7) == 0 && (MODE != MC_EPI_REORG2 || (p.N & 7) == 0);
   int as = 0;
   uint32_t aphase = 0;
+  int slab_buf = 0;  // (TMA-store epilogue) slab of this warp the next chunk goes to
   // one N tile: every tile of the launch uses the same scale/shift slice, staged once (a narrow layer's epilogue is
   // otherwise a chain of global-load latency + barrier per 128 rows)
   const bool one_n_tile = p.n_tiles == 1;
@@ -184,7 +302,8 @@ __device__ __forceinline__ void epilogue_loop(const ConvKParams& p, uint32_t tme
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
   }
-  for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+  int ti = 0;  // (tracing) tiles done by this CTA
+  for (int tile = tile0; tile < total_tiles; tile += tile_step, ++ti) {
     const int n0 = (tile % p.n_tiles) * p.block_n;
     const int m0 = (PAIR ? 2 * (tile / p.n_tiles) + pair_rank : tile / p.n_tiles) * BLOCK_M;
     float* sc = s_ss + (one_n_tile ? 0 : as * 512);
@@ -221,7 +340,17 @@ __device__ __forceinline__ void epilogue_loop(const ConvKParams& p, uint32_t tme
 
     ptx::mbar_wait(&tmem_full_bar[as], aphase);
     ptx::tc_fence_after();
+    if (!PAIR && et == 0 && ti < 8) conv_stamp(p, 12 + 2 * ti);
     const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.acc_stride);
+
+    if (MODE == MC_EPI_PNHWC && p.tma_bufs > 0) {
+      epilogue_tile_tma<LEAKY, PAIR, WIDE_LD>(p, tm_out, taddr_row, sc, sh, interior, in_buf, m0 + quarter * 32, n0, out_row_base,
+                                     vec_ok, s_out + (size_t)quarter * p.tma_bufs * 4096, slab_buf, &tmem_empty_bar[as],
+                                     [](uint32_t (&)[16], int) {});
+      if (!PAIR && et == 0 && ti < 8) conv_stamp(p, 13 + 2 * ti);
+      if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
+      continue;
+    }
 
     if (MODE == MC_EPI_PNHWC && s_out != nullptr) {
       // Staged store: a thread owns one output ROW, so direct stores are 16-byte pieces one row pitch apart (32 half-
@@ -279,6 +408,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvKParams& p, uint32_t tme
         }
         __syncwarp();  // wbuf is rewritten by the next chunk / tile
       }
+      if (!PAIR && et == 0 && ti < 8) conv_stamp(p, 13 + 2 * ti);
       if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
       continue;
     }
@@ -352,8 +482,10 @@ __device__ __forceinline__ void epilogue_loop(const ConvKParams& p, uint32_t tme
       if (PAIR) ptx::mbar_arrive_leader(&tmem_empty_bar[as]);
       else ptx::mbar_arrive(&tmem_empty_bar[as]);
     }
+    if (!PAIR && et == 0 && ti < 8) conv_stamp(p, 13 + 2 * ti);
     if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
   }
+  if (MODE == MC_EPI_PNHWC && p.tma_bufs > 0 && lane == 0) ptx::bulk_wait_group_read<0>();  // slabs read before the CTA exits
 }
 
 // Persistent: grid = min(#tiles, #SMs); CTA c works on tiles c, c+grid, ...  The smem ring runs across tiles, and the
@@ -365,7 +497,8 @@ __device__ __forceinline__ void epilogue_loop(const ConvKParams& p, uint32_t tme
 template <int MINB>
 __global__ void __launch_bounds__(NUM_THREADS, MINB)
 conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const __grid_constant__ CUtensorMap tmap_abox, const ConvKParams p) {
+                         const __grid_constant__ CUtensorMap tmap_abox, const __grid_constant__ CUtensorMap tmap_out,
+                         const ConvKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve-up: [stages x (A 16KB | B block_n*128)] | barriers | tmem ptr | scale/shift staging (4 KB)
   const uint32_t a_tile_bytes = (uint32_t)(BLOCK_M * p.block_k * 2);
@@ -394,11 +527,13 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   uint64_t* aempty_bar = afull_bar + MAX_A_STAGES;    // [MAX_A_STAGES]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aempty_bar + MAX_A_STAGES);
   float* s_ss = reinterpret_cast<float*>(aux + 512);  // [2 acc stages][scale|shift][256]
-  uint8_t* s_out = aux + 512 + 4096;                  // staged epilogue: [4 warps][32 rows][out_pitch]
+  uint8_t* s_out = aux + 5120;                        // staged epilogue: [4 warps][32 rows][out_pitch]; TMA-store slabs
+                                                      // [4 warps][tma_bufs][4 KB] (1024-byte aligned: swizzle pattern)
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
+  if (threadIdx.x == 0) conv_stamp(p, 0);
 
   if (warp_idx == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_a);
@@ -416,6 +551,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       ptx::mbar_init(&aempty_bar[a], 1);
     }
     ptx::prefetch_tensormap(&tmap_abox);
+    if (p.tma_bufs > 0) ptx::prefetch_tensormap(&tmap_out);
     ptx::fence_barrier_init();
   }
   if (warp_idx == 1) {
@@ -426,6 +562,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 0) conv_stamp(p, 1);
 
   if (warp_idx == 0) {
     // ===================== TMA producer (one thread) =====================
@@ -459,6 +596,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
         }
       }
+      conv_stamp(p, 3);
     } else if (lane == 0) {
       int s = 0;
       uint32_t phase = 0;
@@ -479,6 +617,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           if (++s == p.stages) { s = 0; phase ^= 1u; }
         }
       }
+      conv_stamp(p, 3);
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
@@ -490,7 +629,8 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       int s = 0, sa = 0, as = 0;
       uint32_t phase = 0, pha = 0, aphase = 0;
       bool b_loaded = false;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int ti = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
         ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t tmem_acc = tmem_base + (uint32_t)(as * p.acc_stride);
@@ -499,6 +639,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           // K steps beyond the layer's real channels multiply TMA zero fill by zero weights: not issued
           const int nk = (cb == p.kb_per_tap - 1) ? p.last_ksteps : (int)(a_row_bytes >> 5);
           ptx::mbar_wait(&afull_bar[sa], pha);
+          if (ti == 0 && g == 0 && lane == 0) conv_stamp(p, 4);
           const uint32_t a_addr = ptx::smem_u32(tiles + (size_t)sa * a_box_stride);
           for (int dx = 0; dx < 3; ++dx) {
             uint32_t b_addr;
@@ -538,6 +679,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
           if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
         }
+        if (lane == 0 && ti < 6) conv_stamp(p, 5 + ti);
         if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
       }
     } else {
@@ -545,7 +687,8 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int ti = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
         ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1u);  // epilogue has drained this accumulator stage
         ptx::tc_fence_after();
         const uint32_t tmem_acc = tmem_base + (uint32_t)(as * p.acc_stride);
@@ -553,6 +696,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         for (int kb = 0; kb < p.num_kb; ++kb) {
           ptx::mbar_wait(&full_bar[s], phase);
           ptx::tc_fence_after();
+          if (ti == 0 && kb == 0 && lane == 0) conv_stamp(p, 4);
           const uint32_t a_addr = ptx::smem_u32(tiles + (size_t)s * stage_bytes);
           const bool k64 = p.block_k == 64;
           const uint64_t adesc = k64 ? ptx::make_sw128_kmajor_desc(a_addr) : ptx::make_sw64_kmajor_desc(a_addr);
@@ -574,14 +718,16 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           __syncwarp();
           if (++s == p.stages) { s = 0; phase ^= 1u; }
         }
+        if (lane == 0 && ti < 6) conv_stamp(p, 5 + ti);
         if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
       }
     }
   } else {
     // ===================== epilogue: warps 2..5 =====================
     if (p.epi_mode == MC_EPI_PNHWC) {
-      if (p.leaky) epilogue_loop<MC_EPI_PNHWC, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, p.out_pitch ? s_out : nullptr);
-      else epilogue_loop<MC_EPI_PNHWC, false>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, p.out_pitch ? s_out : nullptr);
+      uint8_t* so = (p.out_pitch || p.tma_bufs) ? s_out : nullptr;
+      if (p.leaky) epilogue_loop<MC_EPI_PNHWC, true, false, MINB == 1>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, so, &tmap_out);
+      else epilogue_loop<MC_EPI_PNHWC, false, false, MINB == 1>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, so, &tmap_out);
     } else if (p.epi_mode == MC_EPI_REORG2) {
       if (p.leaky) epilogue_loop<MC_EPI_REORG2, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss);
       else epilogue_loop<MC_EPI_REORG2, false>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss);
@@ -595,6 +741,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) conv_stamp(p, 30);
   if (warp_idx == 1) ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
@@ -671,7 +818,7 @@ struct PairWorkIter {
 template <int MODE, bool LEAKY>
 __device__ __forceinline__ void epilogue_loop_pair(const ConvKParams& p, uint32_t tmem_base, uint64_t* tmem_full_bar,
                                                    uint64_t* tmem_empty_bar, float* s_ss, int cluster_id, int num_clusters,
-                                                   int pair_rank) {
+                                                   int pair_rank, uint8_t* s_out, const CUtensorMap* tm_out) {
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int et = threadIdx.x - 64;   // 0..127
@@ -679,6 +826,7 @@ __device__ __forceinline__ void epilogue_loop_pair(const ConvKParams& p, uint32_
   const bool vec_ok = ((p.ldc | p.ch_off) & 7) == 0 && (MODE != MC_EPI_REORG2 || (p.N & 7) == 0);
   int as = 0;
   uint32_t aphase = 0;
+  int slab_buf = 0;
   const bool one_n_tile = p.n_tiles == 1;
   if (one_n_tile) {
     for (int i = et; i < p.block_n; i += 128) {
@@ -691,7 +839,9 @@ __device__ __forceinline__ void epilogue_loop_pair(const ConvKParams& p, uint32_
   PairWorkIter it;
   it.init(p, cluster_id, num_clusters);
   PairWork w;
+  int ti = -1;
   while (it.next(w)) {
+    ++ti;
     const int tile = w.unit;
     const int n0 = (tile % p.n_tiles) * p.block_n;
     const int m0 = (2 * (tile / p.n_tiles) + pair_rank) * BLOCK_M;
@@ -729,6 +879,7 @@ __device__ __forceinline__ void epilogue_loop_pair(const ConvKParams& p, uint32_
 
     ptx::mbar_wait(&tmem_full_bar[as], aphase);
     ptx::tc_fence_after();
+    if (et == 0 && ti < 8) conv_stamp(p, 12 + 2 * ti);
     const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.acc_stride);
     const int u_sk = tile - p.sk_first;  // (stream-K pieces only)
     // partial tiles are stored [slot][column / 4][256 rows][4 floats]: a warp instruction (32 rows, one float4 each) is one
@@ -783,6 +934,25 @@ __device__ __forceinline__ void epilogue_loop_pair(const ConvKParams& p, uint32_
         __syncwarp();
         __threadfence();
       }
+      if (MODE == MC_EPI_PNHWC && p.tma_bufs > 0) {
+        epilogue_tile_tma<LEAKY, true, true>(p, tm_out, taddr_row, sc, sh, interior, in_buf, m0 + quarter * 32, n0, out_row_base,
+                                       vec_ok, s_out + (size_t)quarter * p.tma_bufs * 4096, slab_buf, &tmem_empty_bar[as],
+                                       [&](uint32_t (&r)[16], int col) {
+                                         for (int s2 = 0; s2 < nparts; ++s2) {
+#pragma unroll
+                                           for (int q = 0; q < 4; ++q) {
+                                             const float4 a = __ldcg(reinterpret_cast<const float4*>(part_ptr(s2, col + 4 * q)));
+                                             r[4 * q] = __float_as_uint(__uint_as_float(r[4 * q]) + a.x);
+                                             r[4 * q + 1] = __float_as_uint(__uint_as_float(r[4 * q + 1]) + a.y);
+                                             r[4 * q + 2] = __float_as_uint(__uint_as_float(r[4 * q + 2]) + a.z);
+                                             r[4 * q + 3] = __float_as_uint(__uint_as_float(r[4 * q + 3]) + a.w);
+                                           }
+                                         }
+                                       });
+        if (et == 0 && ti < 8) conv_stamp(p, 13 + 2 * ti);
+        if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
+        continue;
+      }
       for (int c0 = 0; c0 < p.block_n; c0 += 32) {
         uint32_t r0[16], r1[16];
         const bool two = c0 + 16 < p.block_n;
@@ -822,8 +992,10 @@ __device__ __forceinline__ void epilogue_loop_pair(const ConvKParams& p, uint32_
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_leader(&tmem_empty_bar[as]);
     }
+    if (et == 0 && ti < 8) conv_stamp(p, 13 + 2 * ti);
     if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
   }
+  if (MODE == MC_EPI_PNHWC && p.tma_bufs > 0 && lane == 0) ptx::bulk_wait_group_read<0>();  // slabs read before the CTA exits
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -837,7 +1009,7 @@ __device__ __forceinline__ void epilogue_loop_pair(const ConvKParams& p, uint32_
 // accumulator stage back on the leader's barrier (8 arrivals).
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_abox,
-                              const ConvKParams p) {
+                              const __grid_constant__ CUtensorMap tmap_out, const ConvKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t b_half_bytes = (uint32_t)(p.block_n / 2 * 128);
   uint8_t* smem = smem_raw;
@@ -856,17 +1028,18 @@ conv_gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_b, const 
   uint64_t* aempty_bar = afull_bar + MAX_A_STAGES;    // [MAX_A_STAGES]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aempty_bar + MAX_A_STAGES);
   float* s_ss = reinterpret_cast<float*>(aux + 512);
+  uint8_t* s_out = aux + 5120;  // TMA-store slabs [4 warps][tma_bufs][4 KB], 1024-byte aligned
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int rank = (int)ptx::cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-  const int m_pairs = (p.m_tiles + 1) / 2;
-  const int total_units = m_pairs * p.n_tiles;
+  if (threadIdx.x == 0) conv_stamp(p, 0);
 
   if (warp_idx == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_b);
     ptx::prefetch_tensormap(&tmap_abox);
+    if (p.tma_bufs > 0) ptx::prefetch_tensormap(&tmap_out);
     for (int s = 0; s < p.stages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
@@ -889,6 +1062,7 @@ conv_gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_b, const 
   ptx::cluster_sync_all();  // barriers of BOTH CTAs initialised before any remote arrival / complete_tx
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 0) conv_stamp(p, 1);
 
   if (warp_idx == 0) {
     // ===================== TMA producer (one thread per CTA) =====================
@@ -919,6 +1093,7 @@ conv_gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_b, const 
           }
         }
       }
+      conv_stamp(p, 3);
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer (warp 1 of the leader CTA; one elected lane issues) =====================
@@ -928,7 +1103,9 @@ conv_gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_b, const 
       PairWorkIter it;
       it.init(p, cluster_id, num_clusters);
       PairWork w;
+      int ti = -1;
       while (it.next(w)) {
+        ++ti;
         ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t tmem_acc = tmem_base + (uint32_t)(as * p.acc_stride);
@@ -936,6 +1113,7 @@ conv_gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_b, const 
         for (int g = gb; g < ge; ++g) {
           const int nk = ((g % p.kb_per_tap) == p.kb_per_tap - 1) ? p.last_ksteps : 4;
           ptx::mbar_wait(&afull_bar[sa], pha);
+          if (ti == 0 && g == gb && lane == 0) conv_stamp(p, 4);
           const uint32_t a_addr = ptx::smem_u32(tiles + (size_t)sa * A_BOX_STRIDE);
           for (int dx = 0; dx < 3; ++dx) {
             ptx::mbar_wait(&full_bar[s], phase);
@@ -957,20 +1135,21 @@ conv_gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_b, const 
           }
           if (++sa == p.a_stages) { sa = 0; pha ^= 1u; }
         }
+        if (lane == 0 && ti < 6) conv_stamp(p, 5 + ti);
         if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
       }
     }
   } else {
     // ===================== epilogue: warps 2..5 of both CTAs =====================
     if (p.epi_mode == MC_EPI_PNHWC) {
-      if (p.leaky) epilogue_loop_pair<MC_EPI_PNHWC, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, rank);
-      else epilogue_loop_pair<MC_EPI_PNHWC, false>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, rank);
+      if (p.leaky) epilogue_loop_pair<MC_EPI_PNHWC, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, rank, s_out, &tmap_out);
+      else epilogue_loop_pair<MC_EPI_PNHWC, false>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, rank, s_out, &tmap_out);
     } else if (p.epi_mode == MC_EPI_REORG2) {
-      if (p.leaky) epilogue_loop_pair<MC_EPI_REORG2, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, rank);
-      else epilogue_loop_pair<MC_EPI_REORG2, false>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, rank);
+      if (p.leaky) epilogue_loop_pair<MC_EPI_REORG2, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, rank, s_out, &tmap_out);
+      else epilogue_loop_pair<MC_EPI_REORG2, false>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, rank, s_out, &tmap_out);
     } else {
-      if (p.leaky) epilogue_loop_pair<MC_EPI_NCHW_F32, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, rank);
-      else epilogue_loop_pair<MC_EPI_NCHW_F32, false>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, rank);
+      if (p.leaky) epilogue_loop_pair<MC_EPI_NCHW_F32, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, rank, s_out, &tmap_out);
+      else epilogue_loop_pair<MC_EPI_NCHW_F32, false>(p, tmem_base, tmem_full_bar, tmem_empty_bar, s_ss, cluster_id, num_clusters, rank, s_out, &tmap_out);
     }
   }
 
@@ -1012,6 +1191,14 @@ int pick_block_n(int Npad, int m_tiles, int num_kb, int num_sms, bool share_dx) 
 }  // namespace
 
 static thread_local int g_last_plan[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+static unsigned long long* g_conv_dbg = nullptr;
+
+// Debug: timeline stamps of the single-CTA conv GEMM kernel (32 x uint64 per CTA, globaltimer ns) into d_buf, which
+// must hold 32 * 8 * grid bytes; NULL switches tracing off again.  tools/trace_conv.py prints the timelines.
+extern "C" int mc_debug_conv_trace(void* d_buf) {
+  g_conv_dbg = reinterpret_cast<unsigned long long*>(d_buf);
+  return 0;
+}
 
 extern "C" int mc_conv_last_plan(int info[8]) {
   MC_CHECK_ARG(info != nullptr, "mc_conv_last_plan: null pointer");
@@ -1103,7 +1290,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   int tmem_cols = 32;
   while (tmem_cols < 2 * acc_stride) tmem_cols <<= 1;  // at least two accumulator stages (more below for narrow layers)
   const int num_kb = ntaps * (Kc / BLOCK_K);
-  constexpr size_t AUX_BYTES = 512 + 4096 + 1024;  // barriers, scale/shift staging, 1024-byte alignment slack
+  constexpr size_t AUX_BYTES = 5120 + 1024;  // barriers (512), scale/shift staging (4096), pad to 1 KB; 1024-byte alignment slack
 
   // smem ring of one CTA when `ctas` CTAs share an SM (each CTA also costs 1 KB of reserved shared memory)
   // resident weights: one N tile and all taps' weight tiles fit beside the activation ring -> loaded once per CTA
@@ -1131,14 +1318,30 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   // (dense conv3/conv5, 128 wide, 5513 tiles: 137 -> 123 us); wide 1x1 layers (conv7: 39 -> 47 us) and the short
   // launches of the 26x26 / 13x13 stages do not.  MCB200_CONV_STAGE_OUT=2 stages every wide tile (A/B switch).
   const bool wide_ok = stage_env == 2 || (d->ksize == 3 && m_tiles >= 1024);
-  const bool stage_out = stage_env && d->epi_mode == MC_EPI_PNHWC && block_n >= 32 && (block_n <= 96 || wide_ok) &&
+  // TMA-store epilogue (tiles >= 64 wide): whole 64-column chunks leave as bulk tensor stores from 4 KB slabs per
+  // epilogue warp — two slabs per warp when the CTA has the SM to itself, one (16 KB per CTA) when several CTAs share
+  // it (measured: dense conv4/conv6 at 104x104 run 113 us with 2 CTAs per SM + one slab, 158 us with one CTA + two
+  // slabs, 125 us with the staged epilogue).  MCB200_CONV_TMA_OUT=0 disables, =1 / =2 force the slab count.
+  static int tma_env = -1;
+  if (tma_env < 0) {
+    const char* e = mc_tune_env("MCB200_CONV_TMA_OUT");
+    tma_env = e ? atoi(e) : 3;
+    if (tma_env < 0 || tma_env > 3) tma_env = 3;
+  }
+  const bool tma_out = tma_env && d->epi_mode == MC_EPI_PNHWC && block_n >= 64 && ((d->ldc | d->ch_off) & 7) == 0;
+  auto tma_bufs_for = [&](int ctas_) -> int { return !tma_out ? 0 : (tma_env == 3 ? (ctas_ == 1 ? 2 : 1) : tma_env); };
+  const bool stage_out = !tma_out && stage_env && d->epi_mode == MC_EPI_PNHWC && block_n >= 32 && (block_n <= 96 || wide_ok) &&
                          ((d->ldc | d->ch_off) & 7) == 0;
   const int out_chunk = block_n <= 96 ? block_n : 64;
   const int out_pitch = stage_out ? out_chunk * 2 + 16 : 0;
   // (decode epilogue: 128 rows x (block_n + 1) floats of logits)
-  const size_t out_stage_bytes = decode ? (size_t)128 * (block_n + 1) * 4 : (size_t)128 * out_pitch;
+  auto out_stage_for = [&](int ctas_) -> size_t {
+    return decode ? (size_t)128 * (block_n + 1) * 4
+                  : (tma_out ? (size_t)tma_bufs_for(ctas_) * 4 * 4096 : (size_t)128 * out_pitch);
+  };
   auto plan_ring = [&](int ctas, int* st, int* ast, size_t* bytes) -> bool {
-    const long long cap = (ctas == 1 ? 204 * 1024 : (227 * 1024) / ctas - 1024 - (long long)AUX_BYTES) - (long long)out_stage_bytes;
+    const size_t out_stage_bytes = out_stage_for(ctas);
+    const long long cap = (ctas == 1 ? 220 * 1024 - (long long)AUX_BYTES : (227 * 1024) / ctas - 1024 - (long long)AUX_BYTES) - (long long)out_stage_bytes;
     if (b_resident) {
       // the activation ring is the only pipeline left: as deep as the smem beside the weights allows (a tile is 3 boxes)
       long long a = (cap - (long long)b_res_bytes) / a_box_stride;
@@ -1204,10 +1407,10 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
     if (share_dx) {
       a_stages = DEF_A_STAGES;
       MC_CHECK_ARG(stages >= 2 && stages <= MAX_STAGES, "mc_conv_fwd: stages %d invalid", stages);
-      smem_bytes = (size_t)a_stages * a_box_stride + (size_t)stages * block_n * BLOCK_K * 2 + AUX_BYTES + out_stage_bytes;
+      smem_bytes = (size_t)a_stages * a_box_stride + (size_t)stages * block_n * BLOCK_K * 2 + AUX_BYTES + out_stage_for(1);
     } else {
       MC_CHECK_ARG(stages >= 1 && stages <= MAX_STAGES, "mc_conv_fwd: stages %d invalid", stages);
-      smem_bytes = (size_t)stages * stage_bytes + AUX_BYTES + out_stage_bytes;
+      smem_bytes = (size_t)stages * stage_bytes + AUX_BYTES + out_stage_for(1);
     }
   }
   MC_CHECK_ARG(smem_bytes <= 227 * 1024, "mc_conv_fwd: smem %zu too large", smem_bytes);
@@ -1225,9 +1428,10 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
     ctas = 1;
     a_stages = DEF_A_STAGES;
     const int b_half = block_n / 2 * 128;
-    stages = (204 * 1024 - a_stages * A_BOX_STRIDE) / b_half;
+    const int slab_bytes = tma_bufs_for(1) * 4 * 4096;
+    stages = (220 * 1024 - a_stages * A_BOX_STRIDE - slab_bytes) / b_half;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
-    smem_bytes = (size_t)a_stages * A_BOX_STRIDE + (size_t)stages * b_half + AUX_BYTES;
+    smem_bytes = (size_t)a_stages * A_BOX_STRIDE + (size_t)stages * b_half + AUX_BYTES + slab_bytes;
   }
 
   CUtensorMap tm_a, tm_b, tm_abox;
@@ -1244,6 +1448,18 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   rc = mc_make_tmap_2d_bf16_k(&tm_b, d->d_wpack, (uint64_t)d->Npad, (uint64_t)ntaps * Kc, (uint64_t)ntaps * Kc,
                               (uint32_t)(use_pair ? block_n / 2 : block_n), BLOCK_K);
   if (rc) return rc;
+
+  CUtensorMap tm_out = tm_a;
+  const int tma_bufs = tma_bufs_for(use_pair ? 1 : ctas);
+  if (tma_bufs) {
+    // output slice [ch_off, ch_off + N rounded up to 8) of the PNHWC rows: stores are clipped there, so a chunk that
+    // reaches past the layer's channels never touches the neighbouring concat slice; channels N .. 8-multiple get zeros
+    uint64_t ocols = (uint64_t)((d->N + 7) / 8 * 8);
+    if (ocols > (uint64_t)(d->ldc - d->ch_off)) ocols = (uint64_t)(d->ldc - d->ch_off);
+    rc = mc_make_tmap_2d_bf16_k(&tm_out, reinterpret_cast<const __nv_bfloat16*>(d->d_out) + d->ch_off, (uint64_t)M_rows, ocols,
+                                (uint64_t)d->ldc, 32, 64);
+    if (rc) return rc;
+  }
 
   ConvKParams p;
   p.M_rows = (int)M_rows;
@@ -1288,6 +1504,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   p.acc_stages = acc_stages;
   p.out_pitch = use_pair ? 0 : out_pitch;
   p.out_chunk = out_chunk;
+  p.tma_bufs = tma_bufs;
   {
     auto magic = [](unsigned int dv, unsigned int* mul, unsigned int* shr) {
       unsigned int l = 0;
@@ -1312,6 +1529,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   p.epi_mode = d->epi_mode;
   p.leaky = d->leaky;
   p.sk_first = 0; p.sk_units = 0; p.sk_gper = 0; p.sk_total_g = 0; p.sk_clusters = 0; p.sk_count = nullptr; p.sk_part = nullptr;
+  p.dbg = g_conv_dbg;
   p.dec_boxes = p.dec_cls = p.dec_head = nullptr;
   p.dec_A = p.dec_nc = p.dec_only_obj = 0;
   p.dec_thresh = 0.f;
@@ -1342,7 +1560,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(2 * (mc_num_sms() / 2));
       cfg.blockDim = dim3(NUM_THREADS);
-      cfg.dynamicSmemBytes = 210 * 1024;
+      cfg.dynamicSmemBytes = 222 * 1024;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -1388,7 +1606,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
     }
     g_last_plan[0] = 1; g_last_plan[1] = block_n; g_last_plan[2] = 1; g_last_plan[3] = p.sk_units; g_last_plan[4] = 1;
     g_last_plan[5] = stages; g_last_plan[6] = 2 * clusters; g_last_plan[7] = BLOCK_K;
-    conv_gemm_tcgen05_pair_kernel<<<2 * clusters, NUM_THREADS, smem_bytes, stream>>>(tm_b, tm_abox, p);
+    conv_gemm_tcgen05_pair_kernel<<<2 * clusters, NUM_THREADS, smem_bytes, stream>>>(tm_b, tm_abox, tm_out, p);
     MC_LAUNCH_CHECK("conv_gemm_tcgen05_pair_kernel");
     return 0;
   }
@@ -1396,6 +1614,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   static bool attr_set = false;
   if (!attr_set) {
     MC_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MC_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
     MC_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     attr_set = true;
   }
@@ -1413,9 +1632,11 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   g_last_plan[0] = 0; g_last_plan[1] = block_n; g_last_plan[2] = ctas; g_last_plan[3] = p.b_resident;
   g_last_plan[4] = share_dx; g_last_plan[5] = stages; g_last_plan[6] = grid; g_last_plan[7] = BLOCK_K;
   if (ctas >= 3)
-    conv_gemm_tcgen05_kernel<3><<<grid, NUM_THREADS, smem_bytes, stream>>>(tm_a, tm_b, tm_abox, p);
+    conv_gemm_tcgen05_kernel<3><<<grid, NUM_THREADS, smem_bytes, stream>>>(tm_a, tm_b, tm_abox, tm_out, p);
+  else if (ctas == 2)
+    conv_gemm_tcgen05_kernel<2><<<grid, NUM_THREADS, smem_bytes, stream>>>(tm_a, tm_b, tm_abox, tm_out, p);
   else
-    conv_gemm_tcgen05_kernel<1><<<grid, NUM_THREADS, smem_bytes, stream>>>(tm_a, tm_b, tm_abox, p);
+    conv_gemm_tcgen05_kernel<1><<<grid, NUM_THREADS, smem_bytes, stream>>>(tm_a, tm_b, tm_abox, tm_out, p);
   MC_LAUNCH_CHECK("conv_gemm_tcgen05_kernel");
   return 0;
 }
