@@ -13,7 +13,7 @@ for i in range(0, len(args), 6):
     conv = mc.MaskedConv2d(C, O, k, 1, (k - 1) // 2, bias=False).to(dev)
     lib = _lib.load()
     LDM = int(os.environ.get('LD_MULT', '8'))
-    ld_in, Kc, Npad, ld_out = (C + LDM - 1) // LDM * LDM, (C + 63) // 64 * 64, (O + 15) // 16 * 16, (O + 7) // 8 * 8
+    ld_in, Kc, Npad, ld_out = (C + LDM - 1) // LDM * LDM, (C + (31 if C <= 32 else 63)) // (32 if C <= 32 else 64) * (32 if C <= 32 else 64), (O + 15) // 16 * 16, (O + 7) // 8 * 8
     rows = B * (H + 1) * (W + 1)
     xin = torch.randn(rows, ld_in, device=dev).to(torch.bfloat16)
     wpack = torch.empty(Npad, k * k * Kc, dtype=torch.bfloat16, device=dev)
@@ -26,6 +26,11 @@ for i in range(0, len(args), 6):
     d.d_in, d.d_wpack, d.d_scale, d.d_shift, d.d_out = xin.data_ptr(), wpack.data_ptr(), scale.data_ptr(), shift.data_ptr(), yb.data_ptr()
     d.B, d.H, d.W, d.Cin, d.Cin_ld, d.N, d.Npad = B, H, W, C, ld_in, O, Npad
     d.ksize, d.leaky, d.epi_mode, d.ldc, d.ch_off, d.block_n, d.stages = k, 1, _lib.MC_EPI_PNHWC, ld_out, 0, 0, 0
+    d.block_k = 32 if C <= 32 else 64
+    need = int(lib.mc_workspace_bytes_conv_fwd(ctypes.byref(d)))
+    if need and not os.environ.get('NO_WS'):
+        ws = torch.zeros(need, dtype=torch.uint8, device=dev)
+        d.d_ws, d.ws_bytes = ws.data_ptr(), need
     ts = []
     for it in range(12):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

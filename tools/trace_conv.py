@@ -31,6 +31,10 @@ for i in range(0, len(args), 6):
     d.B, d.H, d.W, d.Cin, d.Cin_ld, d.N, d.Npad = B, H, W, C, ld_in, O, Npad
     d.in_cols = ld_in
     d.ksize, d.leaky, d.epi_mode, d.ldc, d.ch_off, d.block_n, d.stages, d.block_k = k, 1, _lib.MC_EPI_PNHWC, ld_out, 0, 0, 0, kb
+    need = int(lib.mc_workspace_bytes_conv_fwd(ctypes.byref(d)))
+    if need and not os.environ.get('NO_WS'):
+        ws = torch.zeros(need, dtype=torch.uint8, device=dev)
+        d.d_ws, d.ws_bytes = ws.data_ptr(), need
     for _ in range(3):
         _lib.check(lib.mc_conv_fwd(ctypes.byref(d), s), "conv")
     torch.cuda.synchronize()
