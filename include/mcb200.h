@@ -109,9 +109,11 @@ int mc_filter_masks(const float* d_values, const double* d_thr, const int* h_O, 
                     int nlayers, float* const* h_mask_ptrs, uint8_t* d_keep, void* stream);
 
 /* The whole of quick_filter_prune (steps 1-4 above) in one call: d_values [sum O] float32, *d_thr float64,
- * d_keep [sum O] (may be NULL), full-shape masks (h_mask_ptrs may be NULL).  Three launches: per-filter sums (3x3
- * layers tiled through shared memory with 128-bit loads), per-layer normalisation + float64 percentile (bitwise
- * binary search on the bit patterns) + keep flags, mask fill.  d_ws: mc_workspace_bytes_filter_prune() bytes.      */
+ * d_keep [sum O] (may be NULL), full-shape masks (h_mask_ptrs may be NULL).  ONE cooperative launch: persistent blocks
+ * take filter groups from an atomic queue (3x3 layers through a cp.async shared-memory ring), the block that completes
+ * a layer normalises it, the block that completes the last layer selects the float64 percentile (bitwise binary
+ * search on the bit patterns) and publishes threshold + keep flags, then every block fills masks.  (More than 28,416
+ * filters: three launches.)  d_ws: mc_workspace_bytes_filter_prune() bytes, any content.                          */
 int mc_filter_prune(const float* const* h_w_ptrs, const int* h_O, const int* h_C, const int* h_kh, const int* h_kw,
                     int nlayers, int64_t k, double gamma, float* d_values, double* d_thr,
                     float* const* h_mask_ptrs, uint8_t* d_keep, void* d_ws, size_t ws_bytes, void* stream);
@@ -342,6 +344,19 @@ int mc_bn_backward(const void* d_z, int ld_z, const void* d_da, int ld_da, int c
 /* d_full[b,y,x,c] (+)= d_pooled[b,y/2,x/2,c] where a_full[b,y,x,c] is the first maximum of its 2x2 window.          */
 int mc_maxpool2x2_backward(const void* d_a_full, int ld_a, const void* d_dpooled, int ld_dp, int B, int H, int W, int C,
                            void* d_dfull, int ld_df, int accumulate, void* stream);
+
+/* BatchNorm(training) + leaky + MaxPool2d(2,2) in one pass each way, for layers whose un-pooled activation only feeds
+ * the pool (nn.BatchNorm2d / nn.LeakyReLU / nn.MaxPool2d of src/nets.py:802-821 and their autograd backward): the
+ * forward writes pooled = maxpool(bf16(act(z*scale + shift))) straight from z; the backward recomputes the window
+ * from z, routes d_pooled to the first maximum and produces dbeta / dgamma / dz like mc_bn_backward — the un-pooled
+ * activation and its gradient never exist.  Needs C = 8 * 2^k (mc_bn_pool_supported), even H and W.                */
+int mc_bn_pool_supported(int C);
+int mc_bn_apply_pool(const void* d_z, int ld_z, int B, int H, int W, int C, const float* d_scale, const float* d_shift,
+                     int leaky, void* d_pooled, int ld_p, void* stream);
+int mc_bn_pool_backward(const void* d_z, int ld_z, const void* d_dpooled, int ld_dp, int B, int H, int W, int C,
+                        const float* d_scale, const float* d_shift, const float* d_mean, const float* d_invstd,
+                        const float* d_gamma, const float* d_beta, int leaky, float* d_dbeta, float* d_dgamma, void* d_dz,
+                        int ld_dz, void* stream);
 
 /* dgrad weights for mc_conv_fwd: bf16 [Cpad, taps*Ko], row c, column tap'*Ko + o = (w*mask)[o, c, taps-1-tap'].      */
 int mc_pack_conv_weights_dgrad(const float* d_w, const float* d_mask, int O, int C, int ksize, void* d_wpack, int Cpad,

@@ -124,9 +124,10 @@ constexpr int ROW_MAX = 2048;     // 1x1 rows up to this many channels are stage
 // NumPy's (h then w) order through shared memory.  taps==1: one WARP per filter runs the lane-parallel pairwise sum.
 constexpr int SS_THREADS = 288;  // multiple of 9 and of 32
 
+template <int NT>
 __device__ void sumsq_generic_block(const LayerTable& lt, int gblk, float* __restrict__ values, float* s_tap,
                                     float (*s_leaf)[MAX_LEAVES]) {
-  const int gt = gblk * SS_THREADS + threadIdx.x;  // global thread slot (blocks never straddle layers)
+  const int gt = gblk * NT + threadIdx.x;  // global thread slot (blocks never straddle layers)
   int l = 0;
   while (l + 1 < lt.nlayers && gt >= lt.toff[l + 1]) ++l;
   const int local = gt - lt.toff[l];
@@ -141,8 +142,8 @@ __device__ void sumsq_generic_block(const LayerTable& lt, int gblk, float* __res
     if (o >= O) return;  // whole warp
     const float* a = w + (long long)o * C;
     float* ls = s_leaf[wib];                                    // [MAX_LEAVES] leaf sums
-    int* linfo = reinterpret_cast<int*>(s_leaf[SS_THREADS / 32]) + wib * 2 * MAX_LEAVES;  // (start, len) per leaf
-    float* srow = reinterpret_cast<float*>(s_leaf[SS_THREADS / 32]) + (SS_THREADS / 32) * 2 * MAX_LEAVES + wib * ROW_MAX;
+    int* linfo = reinterpret_cast<int*>(s_leaf[NT / 32]) + wib * 2 * MAX_LEAVES;  // (start, len) per leaf
+    float* srow = reinterpret_cast<float*>(s_leaf[NT / 32]) + (NT / 32) * 2 * MAX_LEAVES + wib * ROW_MAX;
     if (C <= ROW_MAX) {
       if ((C & 3) == 0) {
         const float4* a4 = reinterpret_cast<const float4*>(a);
@@ -202,8 +203,8 @@ __device__ void sumsq_generic_block(const LayerTable& lt, int gblk, float* __res
     return;
   }
   // blocks hold whole filters: fpb filters x taps threads, the remaining threads of the block idle
-  const int fpb = SS_THREADS / taps;
-  const int blk = local / SS_THREADS, tl = local - blk * SS_THREADS;
+  const int fpb = NT / taps;
+  const int blk = local / NT, tl = local - blk * NT;
   const int fl = tl / taps, j = tl - fl * taps;
   const int o = (fl < fpb) ? blk * fpb + fl : O;  // O = out of range -> idle
   float acc = 0.f;
@@ -259,15 +260,21 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// F filters per block (F * 9 threads run the chains and issue the copies; further threads of the block only take part
+// in the barriers), STAGES ring slots of F x 32 channels.
+template <int F, int STAGES>
 __device__ void sumsq_tiled_block(const LayerTable& lt, int item, float* __restrict__ values,
-                                  float4* s_tile /*[TL_STAGES][TL_TILE4]*/, float* s_tap /*[SS_THREADS]*/) {
+                                  float4* s_tile /*[STAGES][F * TL_ROW4]*/, float* s_tap /*[blockDim.x]*/) {
+  constexpr int WORK = F * 9;          // threads with a (filter, tap) chain
+  constexpr int TILE4 = F * TL_ROW4;
   int ti = 0;
   while (ti + 1 < lt.ntiled && item >= lt.tblk[ti + 1]) ++ti;
   const int l = lt.torder[ti];
   const int C = lt.C[l];
-  const int o0 = (item - lt.tblk[ti]) * TL_F;
+  const int o0 = (item - lt.tblk[ti]) * F;
   const int t = threadIdx.x;
-  const int f = t / 9, j = t - f * 9;
+  const bool worker = t < WORK;
+  const int f = worker ? t / 9 : 0, j = worker ? t - f * 9 : 0;
   const int nchunks = C / TL_C;
   // o0*C*9*4 bytes is a multiple of 16 because C % 32 == 0
   const float4* __restrict__ w4 = reinterpret_cast<const float4*>(lt.w[l] + (long long)o0 * C * 9);
@@ -275,14 +282,14 @@ __device__ void sumsq_tiled_block(const LayerTable& lt, int item, float* __restr
   int grow[8], scol[8];
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
-    const int q = u * SS_THREADS + t;
+    const int q = u * WORK + (worker ? t : 0);
     const int row = q / 72, col4 = q - row * 72;
     grow[u] = row * (C * 9 / 4) + col4;  // float4 index inside the block's filters
     scol[u] = row * TL_ROW4 + col4;
   }
   auto issue = [&](int cc) {
-    if (cc < nchunks) {
-      float4* tile = s_tile + (cc % TL_STAGES) * TL_TILE4;
+    if (cc < nchunks && worker) {
+      float4* tile = s_tile + (cc % STAGES) * TILE4;
       const float4* src = w4 + (long long)cc * (TL_C * 9 / 4);
 #pragma unroll
       for (int u = 0; u < 8; ++u) cp_async16(tile + scol[u], src + grow[u]);
@@ -290,22 +297,23 @@ __device__ void sumsq_tiled_block(const LayerTable& lt, int item, float* __restr
     cp_async_commit();  // an empty group keeps the wait_group arithmetic uniform at the tail
   };
 #pragma unroll
-  for (int p = 0; p < TL_STAGES - 1; ++p) issue(p);
+  for (int p = 0; p < STAGES - 1; ++p) issue(p);
   float acc = 0.f;
   for (int cc = 0; cc < nchunks; ++cc) {
-    cp_async_wait<TL_STAGES - 2>();  // this thread's copies of chunk cc have landed
-    __syncthreads();                 // ... and everyone's; all threads are also done with the stage refilled next
-    issue(cc + TL_STAGES - 1);
-    const float* row = reinterpret_cast<const float*>(s_tile + (cc % TL_STAGES) * TL_TILE4 + f * TL_ROW4) + j;
+    cp_async_wait<STAGES - 2>();  // this thread's copies of chunk cc have landed
+    __syncthreads();              // ... and everyone's; all threads are also done with the stage refilled next
+    issue(cc + STAGES - 1);
+    const float* row = reinterpret_cast<const float*>(s_tile + (cc % STAGES) * TILE4 + f * TL_ROW4) + j;
 #pragma unroll
     for (int c = 0; c < TL_C; ++c) {
       const float x = row[c * 9];
       acc = __fadd_rn(acc, __fmul_rn(x, x));
     }
   }
+  cp_async_wait<0>();
   s_tap[t] = acc;
   __syncthreads();
-  if (j == 0) {
+  if (worker && j == 0) {
     const float* s = &s_tap[t];
     float tot = 0.f;
     for (int ww = 0; ww < 3; ++ww) {
@@ -326,9 +334,9 @@ __global__ void __launch_bounds__(SS_THREADS) filter_sumsq_kernel(const LayerTab
   if ((int)blockIdx.x < n_tiled) {
     int item = blockIdx.x;
     if (item >= first_wave) item = first_wave + (n_tiled - 1 - item);
-    sumsq_tiled_block(lt, item, values, reinterpret_cast<float4*>(dsm), s_tap);
+    sumsq_tiled_block<TL_F, TL_STAGES>(lt, item, values, reinterpret_cast<float4*>(dsm), s_tap);
   } else {
-    sumsq_generic_block(lt, (int)blockIdx.x - n_tiled, values, s_tap, reinterpret_cast<float(*)[MAX_LEAVES]>(dsm));
+    sumsq_generic_block<SS_THREADS>(lt, (int)blockIdx.x - n_tiled, values, s_tap, reinterpret_cast<float(*)[MAX_LEAVES]>(dsm));
   }
 }
 constexpr size_t SUMSQ_SMEM = TL_STAGES * TL_TILE4 * sizeof(float4);  // 113,664 B (the generic path needs 4.6 KB of it)
@@ -655,8 +663,305 @@ __global__ void __launch_bounds__(256) filter_mask_fill_kernel(const LayerTable 
   }
 }
 
+// ---- the whole of quick_filter_prune in ONE cooperative launch ------------------------------------------------------
+// Persistent blocks (2 per SM, all co-resident) take work items from an atomic counter, most expensive first: groups of
+// FU_F filters of the 3x3 layers (descending C), then the blocks of the generic path.  A block that completes a LAYER
+// (per-layer filter counters) normalises it on the spot while the others keep summing; the block that completes the
+// LAST layer selects the float64 percentile over all values, writes threshold + keep flags and raises a flag.  Blocks
+// that run out of work wait for that flag and then fill the masks.  Against the three-launch version this removes two
+// launch boundaries (each a full drain + ramp of the grid) and the single-block finish kernel between the two
+// bandwidth passes; the deeper ring (5 chunks of 18 KB in flight per block) shortens the per-item chain whose length,
+// not the bytes, bounded the big layers' blocks.
+constexpr int FU_THREADS = 160;  // 16 filters x 9 taps = 144 chain threads, rounded up to whole warps
+constexpr int FU_F = 16;
+constexpr int FU_STAGES = 6;
+constexpr size_t FU_SMEM = (size_t)FU_STAGES * FU_F * TL_ROW4 * sizeof(float4);  // 113,664 B: two blocks per SM
+constexpr int FU_KPT = 72;       // keys per thread held in registers by the select (n <= 11,520)
+
+struct FusedState {
+  unsigned int next_item;
+  unsigned int layers_done;
+  unsigned int flag;
+  unsigned int pad;
+  unsigned int layer_cnt[MAX_LAYERS];
+  unsigned long long stamp[8];  // diagnostics (globaltimer ns): block 0 start, last block out of work, select start,
+                                // flag raised, last block done, first block out of tiled items
+  unsigned long long layer_t[MAX_LAYERS];  // diagnostics: when each layer's sums were complete
+};
+__device__ __forceinline__ void fused_stamp(FusedState* st, int i, bool max_over_blocks) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  if (max_over_blocks) atomicMax(&st->stamp[i], t);
+  else st->stamp[i] = t;
+}
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// v /= sqrt(pairwise(v^2)); v /= max(v)   (methods.py:46-51) by one block; v was written by other blocks.
+template <int NT>
+__device__ void fused_normalise_layer(const LayerTable& lt, int l, float* __restrict__ values, float* s_v,
+                                      float* s_leaf /*[MAX_LEAVES]*/, float* s_red /*[NT / 32 + 1]*/) {
+  const int O = lt.O[l];
+  float* v = values + lt.voff[l];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const bool staged = (size_t)O * sizeof(float) <= FU_SMEM;
+  if (staged) {
+    for (int o0 = 0; o0 < O; o0 += 8 * NT) {  // 8 independent L2 loads in flight per thread
+      float x[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) x[u] = (o0 + u * NT + tid < O) ? __ldcg(v + o0 + u * NT + tid) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (o0 + u * NT + tid < O) s_v[o0 + u * NT + tid] = x[u];
+    }
+  }
+  __syncthreads();
+  if (staged && O <= 128 * MAX_LEAVES) {
+    if (tid < 32) {  // lane-parallel replay of NumPy's pairwise recursion (leaves are independent)
+      np_for_each_leaf(O, [&](int leaf, int st, int ln) {
+        if ((leaf & 31) == lane && leaf < MAX_LEAVES) s_leaf[leaf] = np_leaf_sum<true>(s_v + st, ln);
+      });
+      __syncwarp();
+      if (lane == 0) {
+        int next = 0;
+        s_red[NT / 32] = __fsqrt_rn(np_combine_leaves(s_leaf, O, &next));
+      }
+    }
+  } else if (tid == 0) {
+    s_red[NT / 32] = __fsqrt_rn(np_pairwise<true>(staged ? s_v : v, O));
+  }
+  __syncthreads();
+  const float nrm = s_red[NT / 32];
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int o = tid; o < O; o += NT) {
+    const float x = __fdiv_rn(staged ? s_v[o] : v[o], nrm);
+    if (staged) s_v[o] = x; else v[o] = x;
+    mx = fmaxf(mx, x);
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) s_red[wid] = mx;
+  __syncthreads();
+  if (tid == 0) {
+    float m2 = -INFINITY;
+    for (int w2 = 0; w2 < NT / 32; ++w2) m2 = fmaxf(m2, s_red[w2]);
+    s_red[NT / 32] = m2;
+  }
+  __syncthreads();
+  mx = s_red[NT / 32];
+  for (int o = tid; o < O; o += NT) v[o] = __fdiv_rn(staged ? s_v[o] : v[o], mx);
+  __syncthreads();
+}
+
+// np.percentile over all n values (float64 _lerp between the order statistics k and k+1) by one block: bitwise binary
+// search on the fp32 bit patterns (values >= 0), both ranks at once, keys in registers.  Writes *thr and keep[].
+template <int NT>
+__device__ void fused_select(const LayerTable& lt, const float* __restrict__ values, long long k, double gamma,
+                             double* __restrict__ thr, uint8_t* __restrict__ keep, unsigned int* s_k,
+                             unsigned int* s_part /*[2][2][NT / 32]*/, unsigned int* s_flag) {
+  constexpr int WARPS = NT / 32;
+  const int n = lt.voff[lt.nlayers];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) *s_flag = 0u;
+  __syncthreads();
+  unsigned int nan = 0;
+  for (int i0 = 0; i0 < n; i0 += 16 * NT) {  // 16 independent L2 loads in flight per thread (the values are L2-resident)
+    float x[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int i = i0 + u * NT + tid;
+      x[u] = i < n ? __ldcg(values + i) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int i = i0 + u * NT + tid;
+      if (i < n) s_k[i] = __float_as_uint(x[u]);
+      nan |= (x[u] != x[u]);
+    }
+  }
+  if (nan) *s_flag = 1u;
+  __syncthreads();
+  if (*s_flag) {  // np.percentile returns nan if any value is nan (an all-zero layer gives 0/0): nothing is < nan
+    if (tid == 0) *thr = __longlong_as_double(0x7ff8000000000000LL);
+    if (keep)
+      for (int i = tid; i < n; i += NT) keep[i] = 1;
+    return;
+  }
+  const unsigned int r0 = (unsigned int)k, r1 = (unsigned int)((k + 1 < n) ? k + 1 : (long long)n - 1);
+  unsigned int p0 = 0, p1 = 0;
+  const bool in_regs = n <= FU_KPT * NT;
+  unsigned int kreg[FU_KPT];
+#pragma unroll
+  for (int u = 0; u < FU_KPT; ++u) {
+    const int i = u * NT + tid;
+    kreg[u] = (in_regs && i < n) ? s_k[i] : 0xffffffffu;  // padding never counts as "below"
+  }
+  for (int bit = 30, r = 0; bit >= 0; --bit, ++r) {  // keys < 2^31
+    const unsigned int c0 = p0 | (1u << bit), c1 = p1 | (1u << bit);
+    const bool split = p0 != p1;  // block-uniform
+    unsigned int n0 = 0, n1 = 0;
+    if (in_regs) {
+#pragma unroll
+      for (int u = 0; u < FU_KPT; ++u) n0 += kreg[u] < c0;
+      if (split) {
+#pragma unroll
+        for (int u = 0; u < FU_KPT; ++u) n1 += kreg[u] < c1;
+      }
+    } else {
+      for (int i = tid; i < n; i += NT) {
+        const unsigned int key = s_k[i];
+        n0 += key < c0;
+        n1 += key < c1;
+      }
+    }
+    n0 = __reduce_add_sync(0xffffffffu, n0);
+    if (split || !in_regs) n1 = __reduce_add_sync(0xffffffffu, n1);
+    unsigned int* part = s_part + (r & 1) * 2 * WARPS;
+    if (lane == 0) {
+      part[wid] = n0;
+      part[WARPS + wid] = n1;
+    }
+    __syncthreads();  // (slots alternate by round parity: one barrier per round)
+    const unsigned int t0 = __reduce_add_sync(0xffffffffu, lane < WARPS ? part[lane] : 0u);
+    unsigned int t1 = t0;
+    if (split || !in_regs) t1 = __reduce_add_sync(0xffffffffu, lane < WARPS ? part[WARPS + lane] : 0u);
+    if (t0 <= r0) p0 = c0;  // at most r0 keys below the candidate: the r0-th smallest is >= candidate
+    if (t1 <= r1) p1 = c1;
+  }
+  double t;
+  {
+    const double a = (double)__uint_as_float(p0);
+    const double b = (double)__uint_as_float(p1);
+    const double diff = __dsub_rn(b, a);
+    t = __dadd_rn(a, __dmul_rn(diff, gamma));
+    if (gamma >= 0.5) t = __dsub_rn(b, __dmul_rn(diff, __dsub_rn(1.0, gamma)));
+  }
+  if (tid == 0) *thr = t;
+  if (keep)
+    for (int i = tid; i < n; i += NT) keep[i] = ((double)__uint_as_float(s_k[i]) < t) ? 0 : 1;
+}
+
+__global__ void __launch_bounds__(FU_THREADS, 2)
+filter_prune_fused_kernel(const LayerTable lt, float* __restrict__ values, int n_tiled, int n_big, int n_items, long long k,
+                          double gamma, double* __restrict__ thr, uint8_t* __restrict__ keep, FusedState* st, int fill) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  __shared__ float s_tap[FU_THREADS];
+  __shared__ float s_leaf[MAX_LEAVES];
+  __shared__ float s_red[FU_THREADS / 32 + 1];
+  __shared__ unsigned int s_part[2 * 2 * (FU_THREADS / 32)];
+  __shared__ int s_item;
+  __shared__ unsigned int s_bool;
+  const int tid = threadIdx.x;
+  if (tid == 0 && blockIdx.x == 0) fused_stamp(st, 0, false);
+  // ---- phase 1: per-filter sums; layers are normalised as they complete; the last layer triggers the select
+  for (;;) {
+    if (tid == 0) s_item = (int)atomicAdd(&st->next_item, 1u);
+    __syncthreads();
+    const int qpos = s_item;
+    __syncthreads();
+    if (qpos >= n_items) break;
+    // queue order: the long tiled items (C >= 1024, one per block: the bandwidth-bound bulk), then the short generic
+    // blocks (1x1 layers: latency-bound, hidden behind the bulk instead of forming the tail), then the short tiled items
+    const int n_generic = n_items - n_tiled;
+    const int item = qpos < n_big ? qpos : (qpos < n_big + n_generic ? n_tiled + (qpos - n_big) : qpos - n_generic);
+    int l = 0, nf = 0;
+    if (item < n_tiled) {
+      sumsq_tiled_block<FU_F, FU_STAGES>(lt, item, values, reinterpret_cast<float4*>(dsm), s_tap);
+      int ti = 0;
+      while (ti + 1 < lt.ntiled && item >= lt.tblk[ti + 1]) ++ti;
+      l = lt.torder[ti];
+      nf = FU_F;
+    } else {
+      const int gblk = item - n_tiled;
+      sumsq_generic_block<FU_THREADS>(lt, gblk, values, s_tap, reinterpret_cast<float(*)[MAX_LEAVES]>(dsm));
+      const int gt0 = gblk * FU_THREADS;
+      while (l + 1 < lt.nlayers && gt0 >= lt.toff[l + 1]) ++l;
+      const int local0 = gt0 - lt.toff[l];
+      if (lt.taps[l] == 1) {
+        nf = lt.O[l] - (local0 >> 5);
+        if (nf > FU_THREADS / 32) nf = FU_THREADS / 32;
+      } else {
+        const int fpb = FU_THREADS / lt.taps[l];
+        nf = lt.O[l] - (local0 / FU_THREADS) * fpb;
+        if (nf > fpb) nf = fpb;
+      }
+    }
+    __threadfence();  // this block's values are visible device-wide before it counts itself in
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned int old = atomicAdd(&st->layer_cnt[l], (unsigned int)nf);
+      s_bool = (old + (unsigned int)nf == (unsigned int)lt.O[l]) ? 1u : 0u;
+    }
+    __syncthreads();
+    const bool layer_complete = s_bool != 0u;  // block-uniform: this block completed layer l
+    __syncthreads();
+    if (layer_complete) {
+      if (tid == 0) {
+        unsigned long long tt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
+        st->layer_t[l] = tt;
+      }
+      __threadfence();
+      fused_normalise_layer<FU_THREADS>(lt, l, values, reinterpret_cast<float*>(dsm), s_leaf, s_red);
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) s_bool = (atomicAdd(&st->layers_done, 1u) == (unsigned int)lt.nlayers - 1u) ? 1u : 0u;
+      __syncthreads();
+      const bool all_layers = s_bool != 0u;  // ... and it was the last layer
+      __syncthreads();
+      if (all_layers) {
+        __threadfence();
+        if (tid == 0) fused_stamp(st, 2, false);
+        fused_select<FU_THREADS>(lt, values, k, gamma, thr, keep, reinterpret_cast<unsigned int*>(dsm), s_part, &s_bool);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+          fused_stamp(st, 3, false);
+          atomicExch(&st->flag, 1u);
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (tid == 0) fused_stamp(st, 1, true);
+  if (!fill) return;
+  // ---- phase 2: masks, once the threshold is published
+  if (tid == 0) {
+    unsigned int spins = 0;
+    while (ld_acquire_u32(&st->flag) == 0u) {
+      __nanosleep(64);
+      if (++spins > (1u << 26)) __trap();  // (a broken schedule must not hang the GPU)
+    }
+  }
+  __syncthreads();
+  const double t = __ldcg(thr);
+  const int nfilters = lt.voff[lt.nlayers];
+  int l = 0;
+  for (int f = blockIdx.x; f < nfilters; f += gridDim.x) {
+    while (l + 1 < lt.nlayers && f >= lt.voff[l + 1]) ++l;
+    const int o = f - lt.voff[l];
+    const int per = lt.C[l] * lt.taps[l];
+    const float val = ((double)__ldcg(values + f) < t) ? 0.f : 1.f;
+    float* m = lt.mask[l] + (long long)o * per;
+    int head = (int)(((16 - (reinterpret_cast<uintptr_t>(m) & 15)) & 15) >> 2);  // scalar head up to 16-byte alignment
+    if (head > per) head = per;
+    if (tid < head) m[tid] = val;
+    const int body4 = (per - head) >> 2;
+    float4* m4 = reinterpret_cast<float4*>(m + head);
+    const float4 v4 = make_float4(val, val, val, val);
+    for (int i = tid; i < body4; i += FU_THREADS) st_stream_f4(m4 + i, v4);
+    const int tail0 = head + body4 * 4;
+    if (tid < per - tail0) m[tail0 + tid] = val;
+  }
+  if (tid == 0) fused_stamp(st, 4, true);
+}
+
 int build_layers(LayerTable* lt, const float* const* w, float* const* masks, const int* O, const int* C,
-                 const int* taps, int nlayers, const char* who) {
+                 const int* taps, int nlayers, const char* who, int nt = SS_THREADS, int tl_f = TL_F) {
   if (nlayers <= 0 || nlayers > MAX_LAYERS) return mc_set_error(MC_ERR_ARG, "%s: nlayers %d out of range", who, nlayers);
   lt->nlayers = nlayers;
   lt->voff[0] = 0;
@@ -676,18 +981,18 @@ int build_layers(LayerTable* lt, const float* const* w, float* const* masks, con
     const long long thr = (taps[l] == 1) ? O[l] : (long long)O[l] * taps[l];
     // per-layer thread slots rounded up to whole blocks; for taps>1 a block must hold whole filters
     long long slots;
-    if (w && taps[l] == 9 && (C[l] % TL_C) == 0 && (O[l] % TL_F) == 0) slots = 0;  // tiled path
-    else if (taps[l] == 1) slots = ((thr * 32 + SS_THREADS - 1) / SS_THREADS) * SS_THREADS;  // one warp per filter
+    if (w && taps[l] == 9 && (C[l] % TL_C) == 0 && (O[l] % tl_f) == 0) slots = 0;  // tiled path
+    else if (taps[l] == 1) slots = ((thr * 32 + nt - 1) / nt) * nt;  // one warp per filter
     else {
-      const int fpb = SS_THREADS / taps[l];  // filters per block
-      slots = (long long)((O[l] + fpb - 1) / fpb) * SS_THREADS;
+      const int fpb = nt / taps[l];  // filters per block
+      slots = (long long)((O[l] + fpb - 1) / fpb) * nt;
     }
     lt->toff[l + 1] = lt->toff[l] + (int)slots;
   }
   // tiled layers, largest C first (insertion sort; nlayers <= 64)
   lt->ntiled = 0;
   for (int l = 0; l < nlayers; ++l) {
-    if (!(w && taps[l] == 9 && (C[l] % TL_C) == 0 && (O[l] % TL_F) == 0)) continue;
+    if (!(w && taps[l] == 9 && (C[l] % TL_C) == 0 && (O[l] % tl_f) == 0)) continue;
     int pos = lt->ntiled++;
     while (pos > 0 && C[lt->torder[pos - 1]] < C[l]) {
       lt->torder[pos] = lt->torder[pos - 1];
@@ -696,7 +1001,7 @@ int build_layers(LayerTable* lt, const float* const* w, float* const* masks, con
     lt->torder[pos] = l;
   }
   lt->tblk[0] = 0;
-  for (int i = 0; i < lt->ntiled; ++i) lt->tblk[i + 1] = lt->tblk[i] + O[lt->torder[i]] / TL_F;
+  for (int i = 0; i < lt->ntiled; ++i) lt->tblk[i + 1] = lt->tblk[i] + O[lt->torder[i]] / tl_f;
   for (int i = lt->ntiled; i < MAX_LAYERS; ++i) {
     lt->torder[i] = 0;
     lt->tblk[i + 1] = lt->tblk[lt->ntiled];
@@ -807,9 +1112,9 @@ extern "C" int mc_filter_masks(const float* d_values, const double* d_thr, const
   return 0;
 }
 
-/* The whole of quick_filter_prune in one call (3 launches: per-filter sums, normalise + percentile + keep flags, mask
- * fill).  See include/mcb200.h. */
-extern "C" size_t mc_workspace_bytes_filter_prune(void) { return 256; }
+/* The whole of quick_filter_prune in one call: ONE cooperative launch (filter_prune_fused_kernel); models with more
+ * filters than the single-block select holds take the three-launch path.  See include/mcb200.h. */
+extern "C" size_t mc_workspace_bytes_filter_prune(void) { return 1024; }
 
 extern "C" int mc_filter_prune(const float* const* h_w_ptrs, const int* h_O, const int* h_C, const int* h_kh,
                                const int* h_kw, int nlayers, int64_t k, double gamma, float* d_values, double* d_thr,
@@ -834,6 +1139,37 @@ extern "C" int mc_filter_prune(const float* const* h_w_ptrs, const int* h_O, con
   const int n = lt.voff[nlayers];
   MC_CHECK_ARG(k >= 0 && k < n, "mc_filter_prune: rank out of range");
   MC_CHECK_ARG(gamma >= 0.0 && gamma < 1.0, "mc_filter_prune: gamma must be in [0,1)");
+  {
+    const char* e = mc_tune_env("MCB200_FILTER_FUSED");  // =0: the three-launch path (A/B)
+    const bool fused_on = !(e && e[0] == '0');
+    if (fused_on && (size_t)n * sizeof(float) <= FU_SMEM) {
+      LayerTable lf;
+      rc = build_layers(&lf, h_w_ptrs, h_mask_ptrs, h_O, h_C, taps, nlayers, "mc_filter_prune", FU_THREADS, FU_F);
+      if (rc) return rc;
+      static int max_blocks = -1;
+      if (max_blocks < 0) {
+        MC_CUDA(cudaFuncSetAttribute(filter_prune_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM));
+        int per_sm = 0;
+        MC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, filter_prune_fused_kernel, FU_THREADS, FU_SMEM));
+        if (per_sm < 1) return mc_set_error(MC_ERR_SHAPE, "mc_filter_prune: fused kernel does not fit an SM");
+        max_blocks = per_sm * mc_num_sms();
+      }
+      int n_tiled = lf.tblk[lf.ntiled];
+      int n_items = n_tiled + lf.toff[lf.nlayers] / FU_THREADS;
+      int n_big = 0;  // tiled items of the layers with >= 1024 input channels (torder is sorted by descending C)
+      for (int i2 = 0; i2 < lf.ntiled && h_C[lf.torder[i2]] >= 1024; ++i2) n_big = lf.tblk[i2 + 1];
+      int grid = n_items < max_blocks ? n_items : max_blocks;
+      if (grid < 1) grid = 1;
+      MC_CUDA(cudaMemsetAsync(d_ws, 0, sizeof(FusedState), stream));
+      long long kk = (long long)k;
+      FusedState* stp = reinterpret_cast<FusedState*>(d_ws);
+      int fill = h_mask_ptrs ? 1 : 0;
+      void* args[] = {&lf, &d_values, &n_tiled, &n_big, &n_items, &kk, &gamma, &d_thr, &d_keep, &stp, &fill};
+      MC_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(filter_prune_fused_kernel), dim3((unsigned)grid),
+                                          dim3(FU_THREADS), args, FU_SMEM, stream));
+      return 0;
+    }
+  }
   const size_t fin_smem = (size_t)(n > max_o ? n : max_o) * sizeof(float);
   if (fin_smem > 200 * 1024) return mc_set_error(MC_ERR_SHAPE, "mc_filter_prune: %d filters exceed the single-block select", n);
   static size_t fin_attr = 0;

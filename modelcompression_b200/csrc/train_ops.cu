@@ -556,6 +556,150 @@ __global__ void __launch_bounds__(TB) bn_apply_vec_kernel(const __nv_bfloat16* _
   }
 }
 
+// ---- BatchNorm + leaky + 2x2 max-pool as ONE pass each way (layers whose un-pooled activation only feeds the pool) ----
+// The un-pooled activation a = leaky(z*scale + shift) is never stored: the forward writes the pooled tensor straight
+// from z, and the backward recomputes the four window values from z (same fp32 arithmetic, same bf16 rounding as the
+// stored tensor would have had), routes the pooled gradient to the first maximum — nn.MaxPool2d's rule — and feeds the
+// BatchNorm reductions / dz directly.  Per pooled layer this moves 1.25 S (forward) + 3.5 S (backward) bytes instead
+// of 2 S + 1.25 S and 7.25 S (S = bytes of z): the four pooled layers of Darknet-19 hold 63 % of all activation bytes.
+// Work item = (pooled pixel, channel octet); a thread keeps its octet over the grid-stride loop like the kernels above.
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+__device__ __forceinline__ void pool_item(unsigned int pix, const FastDiv& fWo, const FastDiv& fHo, int H, int W,
+                                          long long* r00, long long* prow) {
+  const unsigned int t = fdiv(pix, fWo);
+  const unsigned int wx = pix - t * fWo.d;
+  const unsigned int b = fdiv(t, fHo);
+  const unsigned int wy = t - b * fHo.d;
+  *r00 = ((long long)b * (H + 1) + 2 * wy) * (W + 1) + 2 * wx;
+  *prow = ((long long)b * (fHo.d + 1) + wy) * (fWo.d + 1) + wx;
+}
+
+__global__ void __launch_bounds__(TB) bn_apply_pool_vec_kernel(const __nv_bfloat16* __restrict__ z, int ld_z, int B, int H,
+                                                               int W, int O8, const float* __restrict__ scale,
+                                                               const float* __restrict__ shift, int leaky,
+                                                               __nv_bfloat16* __restrict__ pooled, int ld_p, int o8_shift,
+                                                               FastDiv fWo, FastDiv fHo) {
+  const unsigned int total = (unsigned int)B * fHo.d * fWo.d * (unsigned int)O8;
+  const unsigned int nthreads = gridDim.x * TB;
+  unsigned int i = blockIdx.x * TB + threadIdx.x;
+  const int c0 = (int)(i & (unsigned int)(O8 - 1)) * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; }
+  for (; i < total; i += nthreads) {
+    long long r00, prow;
+    pool_item(i >> o8_shift, fWo, fHo, H, W, &r00, &prow);
+    const long long roff[4] = {r00, r00 + 1, r00 + W + 1, r00 + W + 2};
+    uint4 q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) q[u] = *reinterpret_cast<const uint4*>(z + roff[u] * ld_z + c0);
+    float best[8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8(q[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = fmaf(f[j], sc[j], sh[j]);
+        if (leaky) v = fmaxf(v, 0.1f * v);
+        v = bf16_round(v);
+        best[j] = (u == 0) ? v : fmaxf(best[j], v);
+      }
+    }
+    *reinterpret_cast<uint4*>(pooled + prow * ld_p + c0) = pack8(best);
+  }
+}
+
+// APPLY = false: dbeta += sum g, dgamma += sum g * xhat.  APPLY = true: dz = gamma*invstd * (g - dbeta/N - xhat*dgamma/N).
+// g = d_pooled at the window's first maximum (0 elsewhere), times the leaky slope where the forward pre-activation
+// z*scale + shift is <= 0 (what autograd's LeakyReLU backward tests).  gamma*invstd == scale.
+template <bool APPLY>
+__global__ void __launch_bounds__(TB, 2) bn_pool_bwd_vec_kernel(const __nv_bfloat16* __restrict__ z, int ld_z,
+                                                                const __nv_bfloat16* __restrict__ dp, int ld_dp, int B, int H,
+                                                                int W, int O8, const float* __restrict__ scale,
+                                                                const float* __restrict__ shift, const float* __restrict__ mean,
+                                                                const float* __restrict__ invstd, int leaky,
+                                                                float* __restrict__ dbeta, float* __restrict__ dgamma,
+                                                                float inv_count, __nv_bfloat16* __restrict__ dz, int ld_dz,
+                                                                int o8_shift, FastDiv fWo, FastDiv fHo) {
+  __shared__ float s_a[APPLY ? 1 : TB][9], s_b[APPLY ? 1 : TB][9];
+  const unsigned int total = (unsigned int)B * fHo.d * fWo.d * (unsigned int)O8;
+  const unsigned int nthreads = gridDim.x * TB;  // multiple of O8
+  unsigned int i = blockIdx.x * TB + threadIdx.x;
+  const int c0 = (int)(i & (unsigned int)(O8 - 1)) * 8;
+  float sc[8], sh[8], m[8], is[8], kb[8], kg[8], sa[8], sb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j];
+    m[j] = mean[c0 + j]; is[j] = invstd[c0 + j];
+    sa[j] = sb[j] = 0.f;
+    kb[j] = APPLY ? dbeta[c0 + j] * inv_count : 0.f;
+    kg[j] = APPLY ? dgamma[c0 + j] * inv_count : 0.f;
+  }
+  const float slope = leaky ? 0.1f : 1.0f;
+  for (; i < total; i += nthreads) {
+    long long r00, prow;
+    pool_item(i >> o8_shift, fWo, fHo, H, W, &r00, &prow);
+    const long long roff[4] = {r00, r00 + 1, r00 + W + 1, r00 + W + 2};
+    uint4 q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) q[u] = *reinterpret_cast<const uint4*>(z + roff[u] * ld_z + c0);
+    const uint4 qg = *reinterpret_cast<const uint4*>(dp + prow * ld_dp + c0);
+    float fz[4][8], g[8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) unpack8(q[u], fz[u]);
+    unpack8(qg, g);
+    unsigned int args = 0;  // 2 bits per channel: window position of the first maximum
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int arg = 0;
+      float best = 0.f, zbest = 0.f, pre_best = 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {  // the forward's values, the pool's first-maximum rule
+        const float pre = fmaf(fz[u][j], sc[j], sh[j]);
+        const float v = bf16_round(leaky ? fmaxf(pre, 0.1f * pre) : pre);
+        if (u == 0 || v > best) { best = v; arg = u; zbest = fz[u][j]; pre_best = pre; }
+      }
+      if (!APPLY) {
+        const float xh = (zbest - m[j]) * is[j];
+        const float gg = pre_best <= 0.f ? g[j] * slope : g[j];
+        sa[j] += gg;
+        sb[j] += gg * xh;
+      } else {
+        args |= (unsigned int)arg << (2 * j);
+        if (pre_best <= 0.f) g[j] *= slope;  // (only the maximum's gradient is non-zero)
+      }
+    }
+    if (APPLY) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float out[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (fz[u][j] - m[j]) * is[j];
+          const float gg = (((args >> (2 * j)) & 3u) == (unsigned int)u) ? g[j] : 0.f;
+          out[j] = sc[j] * (gg - kb[j] - xh * kg[j]);
+        }
+        *reinterpret_cast<uint4*>(dz + roff[u] * ld_dz + c0) = pack8(out);
+      }
+    }
+  }
+  if (!APPLY) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s_a[threadIdx.x][j] = sa[j]; s_b[threadIdx.x][j] = sb[j]; }
+    __syncthreads();
+    for (int w = threadIdx.x; w < O8 * 8; w += TB) {
+      const int o2 = w >> 3, j = w & 7;
+      float ta = 0.f, tb = 0.f;
+      const int first = (int)(((unsigned int)O8 + o2 - (blockIdx.x * TB) % (unsigned int)O8) % (unsigned int)O8);
+      for (int t = first; t < TB; t += O8) { ta += s_a[t][j]; tb += s_b[t][j]; }
+      atomicAdd(&dbeta[o2 * 8 + j], ta);
+      atomicAdd(&dgamma[o2 * 8 + j], tb);
+    }
+  }
+}
+
 // thread count that is a multiple of O8 (O8 must divide TB * k): returns blocks, or 0 if the vector path does not apply
 inline int ilog2(int v) {
   int l = 0;
@@ -710,6 +854,58 @@ extern "C" int mc_maxpool2x2_backward(const void* d_a_full, int ld_a, const void
                                                              (const __nv_bfloat16*)d_dpooled, ld_dp, B, H, W, C,
                                                              (__nv_bfloat16*)d_dfull, ld_df, accumulate);
   MC_LAUNCH_CHECK("maxpool_bwd_kernel");
+  return 0;
+}
+
+extern "C" int mc_bn_pool_supported(int C) {
+  const int O8 = C / 8;
+  return ((C % 8) == 0 && O8 > 0 && (O8 & (O8 - 1)) == 0 && (TB % O8) == 0) ? 1 : 0;
+}
+
+extern "C" int mc_bn_apply_pool(const void* d_z, int ld_z, int B, int H, int W, int C, const float* d_scale,
+                                const float* d_shift, int leaky, void* d_pooled, int ld_p, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MC_CHECK_ARG(d_z && d_scale && d_shift && d_pooled && B > 0 && H > 0 && W > 0 && C > 0, "mc_bn_apply_pool: bad argument");
+  MC_CHECK_ARG((H % 2) == 0 && (W % 2) == 0, "mc_bn_apply_pool: H, W must be even");
+  MC_CHECK_ARG(mc_bn_pool_supported(C) == 1 && (ld_z % 8) == 0 && (ld_p % 8) == 0 && ld_z >= C && ld_p >= C &&
+                   (((uintptr_t)d_z | (uintptr_t)d_pooled) & 15) == 0,
+               "mc_bn_apply_pool: needs C = 8 * 2^k <= 2048, pitches multiples of 8, 16-byte aligned buffers");
+  const long long total = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  const int vb = vec_blocks(total, C / 8);
+  MC_CHECK_ARG(vb > 0, "mc_bn_apply_pool: too many work items");
+  bn_apply_pool_vec_kernel<<<vb, TB, 0, stream>>>((const __nv_bfloat16*)d_z, ld_z, B, H, W, C / 8, d_scale, d_shift, leaky,
+                                                  (__nv_bfloat16*)d_pooled, ld_p, ilog2(C / 8), make_fastdiv(W / 2),
+                                                  make_fastdiv(H / 2));
+  MC_LAUNCH_CHECK("bn_apply_pool_vec_kernel");
+  return 0;
+}
+
+extern "C" int mc_bn_pool_backward(const void* d_z, int ld_z, const void* d_dpooled, int ld_dp, int B, int H, int W, int C,
+                                   const float* d_scale, const float* d_shift, const float* d_mean, const float* d_invstd,
+                                   const float* d_gamma, const float* d_beta, int leaky, float* d_dbeta, float* d_dgamma,
+                                   void* d_dz, int ld_dz, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MC_CHECK_ARG(d_z && d_dpooled && d_scale && d_shift && d_mean && d_invstd && d_gamma && d_beta && d_dbeta && d_dgamma && d_dz,
+               "mc_bn_pool_backward: null pointer");
+  MC_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && (H % 2) == 0 && (W % 2) == 0, "mc_bn_pool_backward: bad dims");
+  MC_CHECK_ARG(mc_bn_pool_supported(C) == 1 && (ld_z % 8) == 0 && (ld_dp % 8) == 0 && (ld_dz % 8) == 0 &&
+                   (((uintptr_t)d_z | (uintptr_t)d_dpooled | (uintptr_t)d_dz) & 15) == 0,
+               "mc_bn_pool_backward: needs C = 8 * 2^k <= 2048, pitches multiples of 8, 16-byte aligned buffers");
+  MC_CUDA(cudaMemsetAsync(d_dbeta, 0, sizeof(float) * C, stream));
+  MC_CUDA(cudaMemsetAsync(d_dgamma, 0, sizeof(float) * C, stream));
+  const long long total = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  const int vb = vec_blocks(total, C / 8);
+  MC_CHECK_ARG(vb > 0, "mc_bn_pool_backward: too many work items");
+  const float inv_count = 1.0f / (float)((double)B * H * W);
+  const FastDiv fWo = make_fastdiv(W / 2), fHo = make_fastdiv(H / 2);
+  bn_pool_bwd_vec_kernel<false><<<vb, TB, 0, stream>>>((const __nv_bfloat16*)d_z, ld_z, (const __nv_bfloat16*)d_dpooled, ld_dp,
+                                                       B, H, W, C / 8, d_scale, d_shift, d_mean, d_invstd, leaky, d_dbeta,
+                                                       d_dgamma, inv_count, nullptr, ld_dz, ilog2(C / 8), fWo, fHo);
+  MC_LAUNCH_CHECK("bn_pool_bwd_vec_kernel<reduce>");
+  bn_pool_bwd_vec_kernel<true><<<vb, TB, 0, stream>>>((const __nv_bfloat16*)d_z, ld_z, (const __nv_bfloat16*)d_dpooled, ld_dp, B,
+                                                      H, W, C / 8, d_scale, d_shift, d_mean, d_invstd, leaky, d_dbeta, d_dgamma,
+                                                      inv_count, (__nv_bfloat16*)d_dz, ld_dz, ilog2(C / 8), fWo, fHo);
+  MC_LAUNCH_CHECK("bn_pool_bwd_vec_kernel<apply>");
   return 0;
 }
 

@@ -200,6 +200,20 @@ class TrainPlan(object):
         for L in self.layers:
             if not L.is_head and L.act is None:
                 raise NotImplementedError("unresolved concat producer at block %d" % L.ind)
+        # Pooled layers whose full-resolution activation feeds nothing but the pool: BatchNorm + leaky + pool run as one
+        # pass each way (mc_bn_apply_pool / mc_bn_pool_backward) and the activation / its gradient are never stored
+        # (model.b200_fuse_pool = False keeps the separate passes: A/B runs, tests)
+        fuse = bool(getattr(model, 'b200_fuse_pool', True))
+        for L in self.layers:
+            L.fused_pool = False
+            if not (fuse and L.pool and not L.is_head and L.act is not None and L.act.name == 'a%d' % L.ind):
+                continue
+            if self.lib.mc_bn_pool_supported(L.O) != 1 or any(o.src is L.act for o in self.layers):
+                continue
+            L.fused_pool = True
+            del self.buf_specs[L.act.name]
+            del self.grad_specs['d' + L.act.name]
+            L.act = None
         self._bufs = {}  # (B, device) -> dict name -> tensor
         self._consts = {}  # (device, kind, n) -> constant vectors / reusable staging tensors (no fill kernels per step)
         self.dp_group = None   # set by train_dp.enable(): gradients are all-reduced inside the backward
@@ -364,10 +378,16 @@ def _forward(plan, x, training_stats=True, after_layer=None, needs_backward=True
                    "mc_bn_finalize")
         if upd and bn.num_batches_tracked is not None:
             bn.num_batches_tracked += 1
+        sv.stats[L.ind] = st
+        if L.fused_pool:
+            _lib.check(lib.mc_bn_apply_pool(z.data_ptr(), L.z.ld, B, L.H, L.W, O, st[2].data_ptr(), st[3].data_ptr(),
+                                            L.leaky, bufs[L.pooled.name].data_ptr(), L.pooled.ld, s), "mc_bn_apply_pool")
+            if after_layer is not None:
+                after_layer(L, bufs)
+            continue
         a = L.act
         _lib.check(lib.mc_bn_apply(z.data_ptr(), L.z.ld, B, L.H, L.W, O, st[2].data_ptr(), st[3].data_ptr(), L.leaky,
                                    bufs[a.name].data_ptr(), a.ld, a.ch_off, int(L.reorg), s), "mc_bn_apply")
-        sv.stats[L.ind] = st
         if L.pool:
             _lib.check(lib.mc_maxpool2x2(bufs[a.name].data_ptr(), bufs[L.pooled.name].data_ptr(), B, L.H, L.W, O, a.ld,
                                          L.pooled.ld, s), "mc_maxpool2x2")
@@ -419,6 +439,25 @@ def _backward(plan, sv, dy, before_bn=None):
             dz_ptr, ld_dz = dzh.data_ptr(), ld_h
             # bias gradient = column sums of dY; computed in fp32 from dy itself (tiny)
             grads[id(conv.bias)] = reduce_async(dy.sum(dim=(0, 2, 3)))
+        elif L.fused_pool:
+            st = sv.stats[L.ind]
+            dp_name = 'd' + L.pooled.name
+            if dp_name not in written:
+                raise RuntimeError("internal: pooled gradient of block %d was never produced" % L.ind)
+            if before_bn is not None:
+                before_bn(L, bufs)
+            dz = bufs['dz%d' % L.ind]
+            dgb = torch.empty(2, O, device=dev)
+            bn = L.bn
+            _lib.check(lib.mc_bn_pool_backward(bufs[L.z.name].data_ptr(), L.z.ld, bufs[dp_name].data_ptr(), L.pooled.ld, B,
+                                               L.H, L.W, O, st[2].data_ptr(), st[3].data_ptr(), st[4].data_ptr(),
+                                               st[5].data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr(), L.leaky,
+                                               dgb[0].data_ptr(), dgb[1].data_ptr(), dz.data_ptr(), L.z.ld, s),
+                       "mc_bn_pool_backward")
+            reduce_async(dgb)
+            grads[id(bn.bias)] = dgb[0]
+            grads[id(bn.weight)] = dgb[1]
+            dz_ptr, ld_dz = dz.data_ptr(), L.z.ld
         else:
             st = sv.stats[L.ind]
             a = L.act

@@ -235,7 +235,10 @@ def test_train_forward_teacher_forced(train_setup):
 
     with torch.cuda.device(0), torch.no_grad():
         y, _ = _forward(plan, x, training_stats=False, after_layer=check_and_force)
-    assert len(seen) == 22 + 5
+    # (pooled layers whose activation only feeds the pool run BatchNorm + leaky + pool as one pass: only the pooled
+    #  tensor exists there)
+    n_fused = sum(1 for L in plan.layers if getattr(L, 'fused_pool', False))
+    assert n_fused == 4 and len(seen) == 22 + 5 - n_fused
     assert _rel(y, y_e) < 2e-3
     print("teacher-forced per-layer rel-L2: max %.3g" % max(r for _, _, r in seen))
 
@@ -269,8 +272,10 @@ def test_train_backward_teacher_forced(train_setup):
     seen = []
 
     def check_force_bwd(L, bufs):
-        act = L.act
-        ref = (outs[L.ind + 1] if L.reorg else outs[L.ind]).grad
+        # fused BatchNorm + pool layers: the gradient that exists is the pooled tensor's
+        fused = getattr(L, 'fused_pool', False)
+        act = L.pooled if fused else L.act
+        ref = (outs[L.ind + 1] if (L.reorg or fused) else outs[L.ind]).grad
         reg = region(bufs, 'd' + act.name, act, ref.shape[1])
         rel = _rel(reg.float().permute(0, 3, 1, 2), ref)
         seen.append((L.ind, rel))
@@ -290,6 +295,56 @@ def test_train_backward_teacher_forced(train_setup):
         assert rel < 1e-2, "%s: rel-L2 %.3g with oracle inputs" % (name, rel)
     print("teacher-forced backward: activation-gradient rel-L2 max %.3g, parameter-gradient rel-L2 max %.3g (%s)"
           % (max(r for _, r in seen), worst[0], worst[1]))
+
+
+@pytest.mark.parametrize("B,H,W,C,leaky", [(3, 26, 26, 64, 1), (2, 52, 36, 256, 1), (2, 8, 8, 8, 0)])
+def test_fused_bn_pool_equals_separate_passes(B, H, W, C, leaky):
+    """BatchNorm + leaky + pool as one pass each way (mc_bn_apply_pool / mc_bn_pool_backward: the un-pooled activation
+    and its gradient are never stored) against the separate passes bn_apply -> maxpool and maxpool_bwd -> bn_backward on
+    the same z, statistics and pooled gradient: the pooled tensor is bit-identical (same arithmetic, same bf16
+    rounding, ties included), dz / dgamma / dbeta agree up to the order of the fp32 per-channel reductions."""
+    lib = _lib.load()
+    torch.manual_seed(B * 1000 + C)
+    rows, prow = B * (H + 1) * (W + 1), B * (H // 2 + 1) * (W // 2 + 1)
+    z4 = torch.zeros(B, H + 1, W + 1, C, device=DEV)
+    # few distinct values: many exact ties inside the 2x2 windows (first-maximum rule)
+    z4[:, :H, :W] = torch.randint(-6, 7, (B, H, W, C), device=DEV).float() * 0.25
+    z = z4.view(rows, C).to(torch.bfloat16).contiguous()
+    gamma, beta = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.3
+    mean, invstd = torch.randn(C, device=DEV) * 0.2, torch.rand(C, device=DEV) + 0.5
+    scale = gamma * invstd
+    shift = beta - mean * scale
+    dp4 = torch.zeros(B, H // 2 + 1, W // 2 + 1, C, device=DEV)
+    dp4[:, :H // 2, :W // 2] = torch.randn(B, H // 2, W // 2, C, device=DEV)
+    dp = dp4.view(prow, C).to(torch.bfloat16).contiguous()
+    s = _lib.stream_ptr()
+    with torch.cuda.device(0):
+        a = torch.zeros(rows, C, dtype=torch.bfloat16, device=DEV)
+        p_sep = torch.zeros(prow, C, dtype=torch.bfloat16, device=DEV)
+        p_fus = torch.zeros(prow, C, dtype=torch.bfloat16, device=DEV)
+        _lib.check(lib.mc_bn_apply(z.data_ptr(), C, B, H, W, C, scale.data_ptr(), shift.data_ptr(), leaky, a.data_ptr(), C, 0,
+                                   0, s), "bn_apply")
+        _lib.check(lib.mc_maxpool2x2(a.data_ptr(), p_sep.data_ptr(), B, H, W, C, C, C, s), "maxpool")
+        assert lib.mc_bn_pool_supported(C) == 1
+        _lib.check(lib.mc_bn_apply_pool(z.data_ptr(), C, B, H, W, C, scale.data_ptr(), shift.data_ptr(), leaky,
+                                        p_fus.data_ptr(), C, s), "bn_apply_pool")
+        assert torch.equal(p_sep, p_fus)
+        da = torch.zeros(rows, C, dtype=torch.bfloat16, device=DEV)
+        dz_sep = torch.zeros(rows, C, dtype=torch.bfloat16, device=DEV)
+        dz_fus = torch.zeros(rows, C, dtype=torch.bfloat16, device=DEV)
+        g_sep, g_fus = torch.empty(2, C, device=DEV), torch.empty(2, C, device=DEV)
+        _lib.check(lib.mc_maxpool2x2_backward(a.data_ptr(), C, dp.data_ptr(), C, B, H, W, C, da.data_ptr(), C, 0, s), "pool bwd")
+        _lib.check(lib.mc_bn_backward(z.data_ptr(), C, da.data_ptr(), C, 0, 0, B, H, W, C, mean.data_ptr(), invstd.data_ptr(),
+                                      gamma.data_ptr(), beta.data_ptr(), leaky, g_sep[0].data_ptr(), g_sep[1].data_ptr(),
+                                      dz_sep.data_ptr(), C, s), "bn_backward")
+        _lib.check(lib.mc_bn_pool_backward(z.data_ptr(), C, dp.data_ptr(), C, B, H, W, C, scale.data_ptr(), shift.data_ptr(),
+                                           mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), leaky,
+                                           g_fus[0].data_ptr(), g_fus[1].data_ptr(), dz_fus.data_ptr(), C, s),
+                   "bn_pool_backward")
+        torch.cuda.synchronize()
+    assert _rel(g_fus, g_sep) < 1e-5
+    assert _rel(dz_fus.float(), dz_sep.float()) < 2e-3  # (bf16 storage: a last-bit flip of dgamma/dbeta moves single elements by one ulp)
+    assert (dz_fus.float() - dz_sep.float()).abs().max() <= 0.02 * dz_sep.float().abs().max()
 
 
 def test_train_step_vs_oracle_and_reference(train_setup):

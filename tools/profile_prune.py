@@ -57,3 +57,19 @@ for _ in range(9):
     ts.append(e0.elapsed_time(e1) * 1e3)
 print("quick_filter_prune(40): median %.1f us (min %.1f) -> %.3f of the 8n roofline at 6542 GB/s" %
       (statistics.median(ts), min(ts), 405076736 / (statistics.median(ts) * 1e-6) / 6542.4e9))
+
+# fused filter pruner: phase stamps (the 512-byte state block sits behind values | thr in the call's flat buffer)
+import numpy as np
+plan, params, parr = methods._plan_and_tensors(model, conv_only=True)
+n = sum(plan.O)
+n4 = (n + 1) // 2 * 2
+masks = mc.quick_filter_prune(model, 40.)
+torch.cuda.synchronize()
+flat_bytes = 4 * (plan.flat_len + n4 + 2)
+whole = torch.empty(0, dtype=torch.uint8, device=dev).set_(masks[0].untyped_storage())
+st = whole[flat_bytes + 272:flat_bytes + 272 + 64].view(torch.int64).cpu().tolist()
+lt = whole[flat_bytes + 336:flat_bytes + 336 + 8 * len(plan.O)].view(torch.int64).cpu().tolist()
+print("layer sums complete at (us):", " ".join("%d:%s/%d=%.0f" % (i, tuple(p.shape[1:]), p.shape[0], (v - st[0]) / 1e3) for i, (p, v) in enumerate(zip(params, lt))))
+t = [int(x) for x in st]
+print("fused filter pruner stamps (us since block 0 start): out-of-work(last block) %.1f, select start %.1f, flag %.1f, done(last block) %.1f" %
+      tuple((x - t[0]) / 1e3 for x in t[1:5]))
