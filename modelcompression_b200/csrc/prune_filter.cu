@@ -664,29 +664,32 @@ __global__ void __launch_bounds__(256) filter_mask_fill_kernel(const LayerTable 
 }
 
 // ---- the whole of quick_filter_prune in ONE cooperative launch ------------------------------------------------------
-// Persistent blocks (2 per SM, all co-resident) take work items from an atomic counter, most expensive first: groups of
-// FU_F filters of the 3x3 layers (descending C), then the blocks of the generic path.  A block that completes a LAYER
-// (per-layer filter counters) normalises it on the spot while the others keep summing; the block that completes the
-// LAST layer selects the float64 percentile over all values, writes threshold + keep flags and raises a flag.  Blocks
-// that run out of work wait for that flag and then fill the masks.  Against the three-launch version this removes two
-// launch boundaries (each a full drain + ramp of the grid) and the single-block finish kernel between the two
-// bandwidth passes; the deeper ring (5 chunks of 18 KB in flight per block) shortens the per-item chain whose length,
-// not the bytes, bounded the big layers' blocks.
+// Persistent blocks (2 per SM, all co-resident) take work items from an atomic queue: groups of FU_F filters of the 3x3
+// layers through a 6-stage cp.async ring, and the blocks of the generic path (1x1 layers) slotted in behind the long
+// items so that their latency-bound work does not form the tail.  Raw per-filter sums go to a scratch array.  When the
+// queue is empty EVERY block waits for the last item, pulls all raw sums (42 KB for Darknet-19) from L2 into shared
+// memory and redundantly runs the small serial part itself — per-layer normalisation in NumPy's pairwise order, then a
+// two-rank radix select for np.percentile — so nothing is exchanged between blocks after the sums and no block waits
+// for another one's result; it then writes its slice of the normalised values / keep flags and fills its share of the
+// masks.  Against three launches this removes two full drains + ramps of the grid and the single-block finish kernel
+// (~30 us of pure latency between the two bandwidth passes).
 constexpr int FU_THREADS = 160;  // 16 filters x 9 taps = 144 chain threads, rounded up to whole warps
 constexpr int FU_F = 16;
 constexpr int FU_STAGES = 6;
 constexpr size_t FU_SMEM = (size_t)FU_STAGES * FU_F * TL_ROW4 * sizeof(float4);  // 113,664 B: two blocks per SM
-constexpr int FU_KPT = 72;       // keys per thread held in registers by the select (n <= 11,520)
+constexpr int FU_AUX_BYTES = 8192;                                                // leaf table / histograms
+constexpr int FU_MAX_N = (int)((FU_SMEM - FU_AUX_BYTES) / sizeof(float));         // 26,368 filters
+static_assert((size_t)(FU_THREADS / 32) * MAX_LEAVES * 4 <= (size_t)FU_AUX_BYTES, "leaf sums must fit the aux region");
 
 struct FusedState {
-  unsigned int next_item;
-  unsigned int layers_done;
-  unsigned int flag;
-  unsigned int pad;
-  unsigned int layer_cnt[MAX_LAYERS];
-  unsigned long long stamp[8];  // diagnostics (globaltimer ns): block 0 start, last block out of work, select start,
-                                // flag raised, last block done, first block out of tiled items
-  unsigned long long layer_t[MAX_LAYERS];  // diagnostics: when each layer's sums were complete
+  unsigned int next_item;  // work queue
+  unsigned int pad0[31];
+  unsigned int items_done;
+  unsigned int pad1[31];
+  unsigned int flag;  // polled by idle blocks: its own 128-byte line
+  unsigned int pad2[31];
+  unsigned long long stamp[8];  // diagnostics (globaltimer ns): block 0 start, last block out of work, last block past the
+                                // wait, last block with thr, last block done
 };
 __device__ __forceinline__ void fused_stamp(FusedState* st, int i, bool max_over_blocks) {
   unsigned long long t;
@@ -701,125 +704,127 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   return v;
 }
 
-// v /= sqrt(pairwise(v^2)); v /= max(v)   (methods.py:46-51) by one block; v was written by other blocks.
+// All raw sums -> normalised values in shared memory (methods.py:43-51 for every layer), by one block.
+// s_val [n]; aux: leaf table (start, len) + leaf sums.  Returns true (block-uniform) if any value is NaN.
 template <int NT>
-__device__ void fused_normalise_layer(const LayerTable& lt, int l, float* __restrict__ values, float* s_v,
-                                      float* s_leaf /*[MAX_LEAVES]*/, float* s_red /*[NT / 32 + 1]*/) {
-  const int O = lt.O[l];
-  float* v = values + lt.voff[l];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const bool staged = (size_t)O * sizeof(float) <= FU_SMEM;
-  if (staged) {
-    for (int o0 = 0; o0 < O; o0 += 8 * NT) {  // 8 independent L2 loads in flight per thread
-      float x[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) x[u] = (o0 + u * NT + tid < O) ? __ldcg(v + o0 + u * NT + tid) : 0.f;
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (o0 + u * NT + tid < O) s_v[o0 + u * NT + tid] = x[u];
-    }
-  }
-  __syncthreads();
-  if (staged && O <= 128 * MAX_LEAVES) {
-    if (tid < 32) {  // lane-parallel replay of NumPy's pairwise recursion (leaves are independent)
-      np_for_each_leaf(O, [&](int leaf, int st, int ln) {
-        if ((leaf & 31) == lane && leaf < MAX_LEAVES) s_leaf[leaf] = np_leaf_sum<true>(s_v + st, ln);
-      });
-      __syncwarp();
-      if (lane == 0) {
-        int next = 0;
-        s_red[NT / 32] = __fsqrt_rn(np_combine_leaves(s_leaf, O, &next));
-      }
-    }
-  } else if (tid == 0) {
-    s_red[NT / 32] = __fsqrt_rn(np_pairwise<true>(staged ? s_v : v, O));
-  }
-  __syncthreads();
-  const float nrm = s_red[NT / 32];
-  __syncthreads();
-  float mx = -INFINITY;
-  for (int o = tid; o < O; o += NT) {
-    const float x = __fdiv_rn(staged ? s_v[o] : v[o], nrm);
-    if (staged) s_v[o] = x; else v[o] = x;
-    mx = fmaxf(mx, x);
-  }
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if (lane == 0) s_red[wid] = mx;
-  __syncthreads();
-  if (tid == 0) {
-    float m2 = -INFINITY;
-    for (int w2 = 0; w2 < NT / 32; ++w2) m2 = fmaxf(m2, s_red[w2]);
-    s_red[NT / 32] = m2;
-  }
-  __syncthreads();
-  mx = s_red[NT / 32];
-  for (int o = tid; o < O; o += NT) v[o] = __fdiv_rn(staged ? s_v[o] : v[o], mx);
-  __syncthreads();
-}
-
-// np.percentile over all n values (float64 _lerp between the order statistics k and k+1) by one block: bitwise binary
-// search on the fp32 bit patterns (values >= 0), both ranks at once, keys in registers.  Writes *thr and keep[].
-template <int NT>
-__device__ void fused_select(const LayerTable& lt, const float* __restrict__ values, long long k, double gamma,
-                             double* __restrict__ thr, uint8_t* __restrict__ keep, unsigned int* s_k,
-                             unsigned int* s_part /*[2][2][NT / 32]*/, unsigned int* s_flag) {
-  constexpr int WARPS = NT / 32;
-  const int n = lt.voff[lt.nlayers];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) *s_flag = 0u;
-  __syncthreads();
-  unsigned int nan = 0;
-  for (int i0 = 0; i0 < n; i0 += 16 * NT) {  // 16 independent L2 loads in flight per thread (the values are L2-resident)
+__device__ bool fused_normalise_all(const LayerTable& lt, const float* __restrict__ raw, float* s_val, unsigned char* aux) {
+  const int n = lt.voff[lt.nlayers], nl = lt.nlayers;
+  const int tid = threadIdx.x;
+  float* s_lsum = reinterpret_cast<float*>(aux);  // [NT / 32][MAX_LEAVES] leaf sums, one row per warp
+  for (int i0 = 0; i0 < n; i0 += 16 * NT) {  // 16 independent L2 loads in flight per thread
     float x[16];
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
       const int i = i0 + u * NT + tid;
-      x[u] = i < n ? __ldcg(values + i) : 0.f;
+      x[u] = i < n ? __ldcg(raw + i) : 0.f;
     }
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
       const int i = i0 + u * NT + tid;
-      if (i < n) s_k[i] = __float_as_uint(x[u]);
-      nan |= (x[u] != x[u]);
+      if (i < n) s_val[i] = x[u];
     }
   }
-  if (nan) *s_flag = 1u;
   __syncthreads();
-  if (*s_flag) {  // np.percentile returns nan if any value is nan (an all-zero layer gives 0/0): nothing is < nan
-    if (tid == 0) *thr = __longlong_as_double(0x7ff8000000000000LL);
-    if (keep)
-      for (int i = tid; i < n; i += NT) keep[i] = 1;
-    return;
-  }
-  const unsigned int r0 = (unsigned int)k, r1 = (unsigned int)((k + 1 < n) ? k + 1 : (long long)n - 1);
-  unsigned int p0 = 0, p1 = 0;
-  const bool in_regs = n <= FU_KPT * NT;
-  unsigned int kreg[FU_KPT];
+  // One warp per layer, start to finish (no block barrier inside).  ||v||: O <= 128 is one leaf of NumPy's pairwise
+  // recursion, O = 128 * 2^k splits into 2^k leaves of 128 combined as a balanced tree (the recursion halves exactly);
+  // a leaf is 8 strided accumulator chains combined ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) plus a sequential tail — lane =
+  // (leaf, accumulator), the xor-butterfly performs exactly those additions.  Any other O: lane 0 runs the recursion.
+  // Then x = v / ||v||, max(x) (a NaN wins, as np.max propagates it), v = x / max.
+  unsigned int nan = 0;
+  {
+    const int lane = tid & 31, wid = tid >> 5;
+    float* ls = s_lsum + wid * MAX_LEAVES;
+    for (int l = wid; l < nl; l += NT / 32) {
+      const int O = lt.O[l];
+      float* vv = s_val + lt.voff[l];
+      const int nleaf = O <= 128 ? 1 : O / 128;
+      const bool fast = O <= 128 || ((O % 128) == 0 && (nleaf & (nleaf - 1)) == 0 && nleaf <= MAX_LEAVES);
+      float nrm = 0.f;
+      if (fast) {
+        const int lq = lane >> 3, j = lane & 7;
+        for (int g0 = 0; g0 < nleaf; g0 += 4) {
+          const int leaf = g0 + lq;
+          const bool have = leaf < nleaf;
+          const int st = leaf * 128, ln = have ? (O <= 128 ? O : 128) : 0;
+          float r = 0.f;
+          if (ln >= 8) {
+            float x = vv[st + j];
+            r = __fmul_rn(x, x);
+            const int body = ln - (ln % 8);
+            for (int i = 8; i < body; i += 8) {
+              x = vv[st + i + j];
+              r = __fadd_rn(r, __fmul_rn(x, x));
+            }
+          }
+          float t = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+          t = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, 2));
+          t = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, 4));
+          if (have && j == 0) {
+            float sum;
+            int i;
+            if (ln >= 8) { sum = t; i = ln - (ln % 8); } else { sum = 0.f; i = 0; }
+            for (; i < ln; ++i) {
+              const float x = vv[st + i];
+              sum = __fadd_rn(sum, __fmul_rn(x, x));
+            }
+            ls[leaf] = sum;
+          }
+        }
+        __syncwarp();
+        for (int w2 = 1; w2 < nleaf; w2 <<= 1) {  // balanced tree: (L0+L1), (L2+L3), ... then pairs of those, ...
+          for (int i = lane * 2 * w2; i + w2 < nleaf; i += 64 * w2) ls[i] = __fadd_rn(ls[i], ls[i + w2]);
+          __syncwarp();
+        }
+        nrm = __fsqrt_rn(ls[0]);
+      } else {
+        if (lane == 0) ls[0] = __fsqrt_rn(np_pairwise<true>(vv, O));
+        __syncwarp();
+        nrm = ls[0];
+      }
+      __syncwarp();
+      unsigned int mb = 0u;
+      for (int i = lane; i < O; i += 32) {
+        const float x = __fdiv_rn(vv[i], nrm);
+        vv[i] = x;
+        mb = max(mb, __float_as_uint(x) & 0x7fffffffu);
+      }
 #pragma unroll
-  for (int u = 0; u < FU_KPT; ++u) {
-    const int i = u * NT + tid;
-    kreg[u] = (in_regs && i < n) ? s_k[i] : 0xffffffffu;  // padding never counts as "below"
+      for (int o = 16; o > 0; o >>= 1) mb = max(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+      const float mx = __uint_as_float(mb);
+      for (int i = lane; i < O; i += 32) {
+        const float v = __fdiv_rn(vv[i], mx);
+        vv[i] = v;
+        nan |= (v != v);
+      }
+    }
   }
-  for (int bit = 30, r = 0; bit >= 0; --bit, ++r) {  // keys < 2^31
-    const unsigned int c0 = p0 | (1u << bit), c1 = p1 | (1u << bit);
-    const bool split = p0 != p1;  // block-uniform
+  return __syncthreads_or((int)nan) != 0;
+}
+
+// np.percentile over the n normalised values in shared memory: the order statistics k and k+1 (both at once), then
+// NumPy's float64 _lerp.  The values of a layer crowd into a handful of exponents, so the top byte of the bit patterns
+// is resolved by 7 rounds of counting "keys below prefix|bit" (a shared-memory histogram would serialise 32-way on
+// those few bins: measured 10 us for that pass alone); the three lower bytes, which are well spread, by 8-bit radix
+// passes with shared-memory atomics (one histogram per rank).  Every thread returns the threshold.
+template <int NT>
+__device__ double fused_select(const float* s_val, int n, long long k, double gamma, unsigned int* s_hist /*[2][256]*/,
+                               unsigned int* s_bin /*[4]*/) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int WARPS = NT / 32;
+  const long long k1 = (k + 1 < n) ? k + 1 : (long long)n - 1;
+  unsigned int rank[2] = {(unsigned int)k, (unsigned int)k1};
+  unsigned int prefix[2] = {0, 0};
+  unsigned int* s_part = s_hist;  // [2 parities][2 ranks][WARPS] partial counts of the counting rounds
+  for (int bit = 30, r = 0; bit >= 24; --bit, ++r) {  // keys < 2^31
+    const unsigned int c0 = prefix[0] | (1u << bit), c1 = prefix[1] | (1u << bit);
     unsigned int n0 = 0, n1 = 0;
-    if (in_regs) {
-#pragma unroll
-      for (int u = 0; u < FU_KPT; ++u) n0 += kreg[u] < c0;
-      if (split) {
-#pragma unroll
-        for (int u = 0; u < FU_KPT; ++u) n1 += kreg[u] < c1;
-      }
-    } else {
-      for (int i = tid; i < n; i += NT) {
-        const unsigned int key = s_k[i];
-        n0 += key < c0;
-        n1 += key < c1;
-      }
+    for (int i = tid; i < n; i += NT) {
+      const unsigned int key = __float_as_uint(s_val[i]);
+      n0 += key < c0;
+      n1 += key < c1;
     }
     n0 = __reduce_add_sync(0xffffffffu, n0);
-    if (split || !in_regs) n1 = __reduce_add_sync(0xffffffffu, n1);
+    n1 = __reduce_add_sync(0xffffffffu, n1);
     unsigned int* part = s_part + (r & 1) * 2 * WARPS;
     if (lane == 0) {
       part[wid] = n0;
@@ -827,37 +832,72 @@ __device__ void fused_select(const LayerTable& lt, const float* __restrict__ val
     }
     __syncthreads();  // (slots alternate by round parity: one barrier per round)
     const unsigned int t0 = __reduce_add_sync(0xffffffffu, lane < WARPS ? part[lane] : 0u);
-    unsigned int t1 = t0;
-    if (split || !in_regs) t1 = __reduce_add_sync(0xffffffffu, lane < WARPS ? part[WARPS + lane] : 0u);
-    if (t0 <= r0) p0 = c0;  // at most r0 keys below the candidate: the r0-th smallest is >= candidate
-    if (t1 <= r1) p1 = c1;
+    const unsigned int t1 = __reduce_add_sync(0xffffffffu, lane < WARPS ? part[WARPS + lane] : 0u);
+    if (t0 <= (unsigned int)k) prefix[0] = c0;   // at most k keys below the candidate: the k-th smallest is >= candidate
+    if (t1 <= (unsigned int)k1) prefix[1] = c1;
   }
-  double t;
-  {
-    const double a = (double)__uint_as_float(p0);
-    const double b = (double)__uint_as_float(p1);
-    const double diff = __dsub_rn(b, a);
-    t = __dadd_rn(a, __dmul_rn(diff, gamma));
-    if (gamma >= 0.5) t = __dsub_rn(b, __dmul_rn(diff, __dsub_rn(1.0, gamma)));
+  {  // ranks relative to the keys that share the top byte: subtract the keys below the prefix
+    unsigned int n0 = 0, n1 = 0;
+    for (int i = tid; i < n; i += NT) {
+      const unsigned int key = __float_as_uint(s_val[i]);
+      n0 += key < prefix[0];
+      n1 += key < prefix[1];
+    }
+    n0 = __reduce_add_sync(0xffffffffu, n0);
+    n1 = __reduce_add_sync(0xffffffffu, n1);
+    __syncthreads();
+    if (lane == 0) {
+      s_part[wid] = n0;
+      s_part[WARPS + wid] = n1;
+    }
+    __syncthreads();
+    rank[0] -= __reduce_add_sync(0xffffffffu, lane < WARPS ? s_part[lane] : 0u);
+    rank[1] -= __reduce_add_sync(0xffffffffu, lane < WARPS ? s_part[WARPS + lane] : 0u);
+    __syncthreads();
   }
-  if (tid == 0) *thr = t;
-  if (keep)
-    for (int i = tid; i < n; i += NT) keep[i] = ((double)__uint_as_float(s_k[i]) < t) ? 0 : 1;
+  unsigned int mask = 0xff000000u;
+  for (int shift = 16; shift >= 0; shift -= 8) {
+    for (int i = tid; i < 512; i += NT) s_hist[i] = 0;
+    __syncthreads();
+    const bool same = prefix[0] == prefix[1];  // block-uniform: one histogram serves both ranks while they agree
+    for (int i = tid; i < n; i += NT) {
+      const unsigned int key = __float_as_uint(s_val[i]);
+      const unsigned int d = (key >> shift) & 255u;
+      if ((key & mask) == prefix[0]) atomicAdd(&s_hist[d], 1u);
+      else if (!same && (key & mask) == prefix[1]) atomicAdd(&s_hist[256 + d], 1u);
+    }
+    __syncthreads();
+    if (wid == 0) warp_find_bin(s_hist, rank[0], &s_bin[0], &s_bin[2]);
+    if (wid == 1) warp_find_bin(same ? s_hist : s_hist + 256, rank[1], &s_bin[1], &s_bin[3]);
+    __syncthreads();
+    prefix[0] |= s_bin[0] << shift;
+    prefix[1] |= s_bin[1] << shift;
+    rank[0] = s_bin[2];
+    rank[1] = s_bin[3];
+    mask |= 255u << shift;
+    __syncthreads();
+  }
+  const double a = (double)__uint_as_float(prefix[0]);
+  const double b = (double)__uint_as_float(prefix[1]);
+  const double diff = __dsub_rn(b, a);
+  double r = __dadd_rn(a, __dmul_rn(diff, gamma));
+  if (gamma >= 0.5) r = __dsub_rn(b, __dmul_rn(diff, __dsub_rn(1.0, gamma)));
+  return r;
 }
 
 __global__ void __launch_bounds__(FU_THREADS, 2)
-filter_prune_fused_kernel(const LayerTable lt, float* __restrict__ values, int n_tiled, int n_big, int n_items, long long k,
-                          double gamma, double* __restrict__ thr, uint8_t* __restrict__ keep, FusedState* st, int fill) {
+filter_prune_fused_kernel(const LayerTable lt, float* __restrict__ raw, float* __restrict__ values, int n_tiled, int n_big,
+                          int n_items, long long k, double gamma, double* __restrict__ thr, uint8_t* __restrict__ keep,
+                          FusedState* st, int fill) {
   extern __shared__ __align__(16) unsigned char dsm[];
   __shared__ float s_tap[FU_THREADS];
-  __shared__ float s_leaf[MAX_LEAVES];
-  __shared__ float s_red[FU_THREADS / 32 + 1];
-  __shared__ unsigned int s_part[2 * 2 * (FU_THREADS / 32)];
+  __shared__ unsigned int s_bin[4];
   __shared__ int s_item;
-  __shared__ unsigned int s_bool;
+  __shared__ unsigned int s_last;
   const int tid = threadIdx.x;
+  const int n = lt.voff[lt.nlayers];
   if (tid == 0 && blockIdx.x == 0) fused_stamp(st, 0, false);
-  // ---- phase 1: per-filter sums; layers are normalised as they complete; the last layer triggers the select
+  // ---- phase 1: raw per-filter sums
   for (;;) {
     if (tid == 0) s_item = (int)atomicAdd(&st->next_item, 1u);
     __syncthreads();
@@ -868,80 +908,55 @@ filter_prune_fused_kernel(const LayerTable lt, float* __restrict__ values, int n
     // blocks (1x1 layers: latency-bound, hidden behind the bulk instead of forming the tail), then the short tiled items
     const int n_generic = n_items - n_tiled;
     const int item = qpos < n_big ? qpos : (qpos < n_big + n_generic ? n_tiled + (qpos - n_big) : qpos - n_generic);
-    int l = 0, nf = 0;
-    if (item < n_tiled) {
-      sumsq_tiled_block<FU_F, FU_STAGES>(lt, item, values, reinterpret_cast<float4*>(dsm), s_tap);
-      int ti = 0;
-      while (ti + 1 < lt.ntiled && item >= lt.tblk[ti + 1]) ++ti;
-      l = lt.torder[ti];
-      nf = FU_F;
-    } else {
-      const int gblk = item - n_tiled;
-      sumsq_generic_block<FU_THREADS>(lt, gblk, values, s_tap, reinterpret_cast<float(*)[MAX_LEAVES]>(dsm));
-      const int gt0 = gblk * FU_THREADS;
-      while (l + 1 < lt.nlayers && gt0 >= lt.toff[l + 1]) ++l;
-      const int local0 = gt0 - lt.toff[l];
-      if (lt.taps[l] == 1) {
-        nf = lt.O[l] - (local0 >> 5);
-        if (nf > FU_THREADS / 32) nf = FU_THREADS / 32;
-      } else {
-        const int fpb = FU_THREADS / lt.taps[l];
-        nf = lt.O[l] - (local0 / FU_THREADS) * fpb;
-        if (nf > fpb) nf = fpb;
-      }
+    if (item < n_tiled)
+      sumsq_tiled_block<FU_F, FU_STAGES>(lt, item, raw, reinterpret_cast<float4*>(dsm), s_tap);
+    else
+      sumsq_generic_block<FU_THREADS>(lt, item - n_tiled, raw, s_tap, reinterpret_cast<float(*)[MAX_LEAVES]>(dsm));
+    __threadfence();  // this block's sums are visible device-wide before it counts the item in
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&st->items_done, 1u) == (unsigned int)n_items - 1u) ? 1u : 0u;
+    __syncthreads();
+    const bool finisher = s_last != 0u;  // block-uniform: this block completed the LAST item
+    __syncthreads();
+    if (!finisher) continue;
+    // ---- phase 2 (the finisher alone; every other block is out of work or about to be): all sums -> normalised values
+    //      -> threshold, published for everyone
+    __threadfence();
+    if (tid == 0) fused_stamp(st, 2, false);
+    float* s_val = reinterpret_cast<float*>(dsm);
+    unsigned char* aux = dsm + (FU_SMEM - FU_AUX_BYTES);
+    const bool any_nan = fused_normalise_all<FU_THREADS>(lt, raw, s_val, aux);
+    if (tid == 0) fused_stamp(st, 5, false);
+    double t;
+    if (any_nan) t = __longlong_as_double(0x7ff8000000000000LL);  // np.percentile returns nan: nothing is < nan
+    else t = fused_select<FU_THREADS>(s_val, n, k, gamma, reinterpret_cast<unsigned int*>(aux), s_bin);
+    for (int i = tid; i < n; i += FU_THREADS) {
+      values[i] = s_val[i];
+      if (keep) keep[i] = ((double)s_val[i] < t) ? 0 : 1;
     }
-    __threadfence();  // this block's values are visible device-wide before it counts itself in
+    if (tid == 0) *thr = t;
+    __threadfence();
     __syncthreads();
     if (tid == 0) {
-      const unsigned int old = atomicAdd(&st->layer_cnt[l], (unsigned int)nf);
-      s_bool = (old + (unsigned int)nf == (unsigned int)lt.O[l]) ? 1u : 0u;
+      fused_stamp(st, 3, false);
+      atomicExch(&st->flag, 1u);
     }
     __syncthreads();
-    const bool layer_complete = s_bool != 0u;  // block-uniform: this block completed layer l
-    __syncthreads();
-    if (layer_complete) {
-      if (tid == 0) {
-        unsigned long long tt;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
-        st->layer_t[l] = tt;
-      }
-      __threadfence();
-      fused_normalise_layer<FU_THREADS>(lt, l, values, reinterpret_cast<float*>(dsm), s_leaf, s_red);
-      __threadfence();
-      __syncthreads();
-      if (tid == 0) s_bool = (atomicAdd(&st->layers_done, 1u) == (unsigned int)lt.nlayers - 1u) ? 1u : 0u;
-      __syncthreads();
-      const bool all_layers = s_bool != 0u;  // ... and it was the last layer
-      __syncthreads();
-      if (all_layers) {
-        __threadfence();
-        if (tid == 0) fused_stamp(st, 2, false);
-        fused_select<FU_THREADS>(lt, values, k, gamma, thr, keep, reinterpret_cast<unsigned int*>(dsm), s_part, &s_bool);
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) {
-          fused_stamp(st, 3, false);
-          atomicExch(&st->flag, 1u);
-        }
-      }
-      __syncthreads();
-    }
   }
   if (tid == 0) fused_stamp(st, 1, true);
   if (!fill) return;
-  // ---- phase 2: masks, once the threshold is published
+  // ---- phase 3: masks, once the threshold is published
   if (tid == 0) {
     unsigned int spins = 0;
     while (ld_acquire_u32(&st->flag) == 0u) {
-      __nanosleep(64);
+      __nanosleep(128);
       if (++spins > (1u << 26)) __trap();  // (a broken schedule must not hang the GPU)
     }
   }
   __syncthreads();
   const double t = __ldcg(thr);
-  const int nfilters = lt.voff[lt.nlayers];
   int l = 0;
-  for (int f = blockIdx.x; f < nfilters; f += gridDim.x) {
+  for (int f = blockIdx.x; f < n; f += gridDim.x) {
     while (l + 1 < lt.nlayers && f >= lt.voff[l + 1]) ++l;
     const int o = f - lt.voff[l];
     const int per = lt.C[l] * lt.taps[l];
@@ -1114,7 +1129,8 @@ extern "C" int mc_filter_masks(const float* d_values, const double* d_thr, const
 
 /* The whole of quick_filter_prune in one call: ONE cooperative launch (filter_prune_fused_kernel); models with more
  * filters than the single-block select holds take the three-launch path.  See include/mcb200.h. */
-extern "C" size_t mc_workspace_bytes_filter_prune(void) { return 1024; }
+extern "C" size_t mc_workspace_bytes_filter_prune(void) { return 2048 + (size_t)FU_MAX_N * sizeof(float); }
+static_assert(sizeof(FusedState) <= 2048, "FusedState must fit the head of the filter-prune workspace");
 
 extern "C" int mc_filter_prune(const float* const* h_w_ptrs, const int* h_O, const int* h_C, const int* h_kh,
                                const int* h_kw, int nlayers, int64_t k, double gamma, float* d_values, double* d_thr,
@@ -1142,7 +1158,7 @@ extern "C" int mc_filter_prune(const float* const* h_w_ptrs, const int* h_O, con
   {
     const char* e = mc_tune_env("MCB200_FILTER_FUSED");  // =0: the three-launch path (A/B)
     const bool fused_on = !(e && e[0] == '0');
-    if (fused_on && (size_t)n * sizeof(float) <= FU_SMEM) {
+    if (fused_on && n <= FU_MAX_N) {
       LayerTable lf;
       rc = build_layers(&lf, h_w_ptrs, h_mask_ptrs, h_O, h_C, taps, nlayers, "mc_filter_prune", FU_THREADS, FU_F);
       if (rc) return rc;
@@ -1163,8 +1179,9 @@ extern "C" int mc_filter_prune(const float* const* h_w_ptrs, const int* h_O, con
       MC_CUDA(cudaMemsetAsync(d_ws, 0, sizeof(FusedState), stream));
       long long kk = (long long)k;
       FusedState* stp = reinterpret_cast<FusedState*>(d_ws);
+      float* d_raw = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(d_ws) + 2048);  // raw sums [n]
       int fill = h_mask_ptrs ? 1 : 0;
-      void* args[] = {&lf, &d_values, &n_tiled, &n_big, &n_items, &kk, &gamma, &d_thr, &d_keep, &stp, &fill};
+      void* args[] = {&lf, &d_raw, &d_values, &n_tiled, &n_big, &n_items, &kk, &gamma, &d_thr, &d_keep, &stp, &fill};
       MC_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(filter_prune_fused_kernel), dim3((unsigned)grid),
                                           dim3(FU_THREADS), args, FU_SMEM, stream));
       return 0;

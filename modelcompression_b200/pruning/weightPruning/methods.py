@@ -338,21 +338,22 @@ def quick_filter_prune(model, pruning_perc, return_keep=False):
     O = plan.O
     n = sum(O)
     k, gamma = _rank_cached(n, pruning_perc, np.float64)
-    # one allocation: masks (flat, 16-byte aligned each) | values [n] f32 | thr f64 | 1 KB kernel state | keep [n] u8
+    # one allocation: masks (flat, 16-byte aligned each) | values [n] f32 | thr f64 | kernel workspace | keep [n] u8
     n4 = (n + 1) // 2 * 2
-    flat = torch.empty(plan.flat_len + n4 + 2 + 256 + (n + 3) // 4, dtype=torch.float32, device=dev)
+    wsf = (int(lib.mc_workspace_bytes_filter_prune()) + 15) // 16 * 4  # workspace in floats
+    flat = torch.empty(plan.flat_len + n4 + 2 + wsf + (n + 3) // 4, dtype=torch.float32, device=dev)
     mbase = flat.data_ptr()
     vbase = mbase + 4 * plan.flat_len
     mask_ptrs = (_lib.c_void_p * len(params))(*[mbase + 4 * o for o in plan.offs])
     with _on_device(dev):
         _lib.check(lib.mc_filter_prune(parr, plan.tables[0], plan.tables[1], plan.tables[2],
                                        plan.tables[3], len(params), k, gamma, vbase, vbase + 4 * n4, mask_ptrs,
-                                       vbase + 4 * n4 + 8 + 1024, vbase + 4 * n4 + 8, 1024, _lib.stream_ptr()),
+                                       vbase + 4 * n4 + 8 + 4 * wsf, vbase + 4 * n4 + 8, 4 * wsf, _lib.stream_ptr()),
                    "mc_filter_prune")
     masks = _mask_views(flat, plan)
     if not return_keep:
         return masks
-    keep = flat[plan.flat_len + n4 + 2 + 256:].view(torch.uint8)[:n]
+    keep = flat[plan.flat_len + n4 + 2 + wsf:].view(torch.uint8)[:n]
     keep_idx = [torch.nonzero(kp, as_tuple=False).flatten() for kp in torch.split(keep, O)]
     return masks, keep_idx
 

@@ -67,9 +67,7 @@ masks = mc.quick_filter_prune(model, 40.)
 torch.cuda.synchronize()
 flat_bytes = 4 * (plan.flat_len + n4 + 2)
 whole = torch.empty(0, dtype=torch.uint8, device=dev).set_(masks[0].untyped_storage())
-st = whole[flat_bytes + 272:flat_bytes + 272 + 64].view(torch.int64).cpu().tolist()
-lt = whole[flat_bytes + 336:flat_bytes + 336 + 8 * len(plan.O)].view(torch.int64).cpu().tolist()
-print("layer sums complete at (us):", " ".join("%d:%s/%d=%.0f" % (i, tuple(p.shape[1:]), p.shape[0], (v - st[0]) / 1e3) for i, (p, v) in enumerate(zip(params, lt))))
+st = whole[flat_bytes + 384:flat_bytes + 384 + 64].view(torch.int64).cpu().tolist()
 t = [int(x) for x in st]
-print("fused filter pruner stamps (us since block 0 start): out-of-work(last block) %.1f, select start %.1f, flag %.1f, done(last block) %.1f" %
-      tuple((x - t[0]) / 1e3 for x in t[1:5]))
+print("fused filter pruner stamps (us since block 0 start): last block out of work %.1f, finisher starts %.1f, normalised %.1f, flag %.1f, done %.1f" %
+      tuple((t[i] - t[0]) / 1e3 for i in (1, 2, 5, 3, 4)))
