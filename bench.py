@@ -444,9 +444,9 @@ def time_scorer_and_loss(model, device, B):
         torch.cuda.synchronize()
         ts.append(time.perf_counter() - t0)
     return {"voc_map_scorer": {"seconds": t_map, "images": n, "detection_rows": int(dets.shape[0]), "gt_boxes": len(rows),
-                               "mAP": m, "note": "wall clock of voc_eval.mean_ap (device tensor code, 20-class loop)"},
+                               "mAP": m, "note": "wall clock of voc_eval.mean_ap (libmcb200 mc_voc_table + mc_voc_match over all classes, torch.sort / cumsum, vectorised 11-point AP)"},
             "region_loss": {"ms_forward_backward": statistics.median(ts) * 1e3, "batch": B,
-                            "note": "wall clock of RegionLoss forward + backward (vectorised device tensor code)"}}
+                            "note": "wall clock of RegionLoss forward + backward (libmcb200 mc_region_loss: two kernels)"}}
 
 
 def time_retrain(device, peaks, B, steps=5):

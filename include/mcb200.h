@@ -358,6 +358,32 @@ int mc_bn_pool_backward(const void* d_z, int ld_z, const void* d_dpooled, int ld
                         const float* d_gamma, const float* d_beta, int leaky, float* d_dbeta, float* d_dgamma, void* d_dz,
                         int ld_dz, void* stream);
 
+/* YOLOv2 region loss — replaces RegionLoss.forward + build_targets (src/nets.py:282-440, 468-610) and the backward of
+ * the loss expression: d_output fp32 [nB, nA*(5+nC), nH, nW] (the head), d_target fp32 [nB, 50*5] rows of
+ * (cls, x, y, w, h) normalised and zero padded (dataloader.py:82-96), h_anchors 2*nA HOST doubles (the cfg's floats).
+ * Writes *d_loss (float32 scalar), d_grad = d loss / d output (same shape as the head), d_counts = {nGT, nCorrect}.
+ * The reference's quirks are kept (w/h exp()-ed twice for the IoU boxes, tw = gw/anchor_w, list ends at the first
+ * x == 0, later box overwrites an earlier one on the same (anchor, cell), no positive anchor IoU -> last anchor).   */
+size_t mc_workspace_bytes_region_loss(int nB);
+int mc_region_loss(const float* d_output, const float* d_target, int nB, int nA, int nC, int nH, int nW,
+                   const double* h_anchors, float coord_scale, float noobject_scale, float object_scale,
+                   float class_scale, float thresh, float* d_grad, float* d_loss, int* d_counts, void* d_ws,
+                   size_t ws_bytes, void* stream);
+
+/* PASCAL-VOC scorer pieces — replace the '%f' detection files of the eval loop (src/predict.py:157-173) and the
+ * per-detection matching loop of voc_eval (src/predict.py:305-380).  mc_voc_table: rows (image, x, y, w, h, box_conf,
+ * cls_conf, cls) -> image / class ids, score and corner boxes after the reference's float32 arithmetic and the 6-decimal
+ * text round trip (float64); d_sizes [n_images, 2] (width, height) or NULL (def_w x def_h).  mc_voc_match: detections in
+ * (class, descending score) order with key = class*K + image, ground-truth boxes sorted by the same key (float64
+ * corners, difficult flags) -> tp / fp flags (float64 0/1) by the reference's rule: best-overlap box (first maximum),
+ * > ovthresh, difficult boxes ignored, the first detection in order that reaches a box is its true positive.        */
+int mc_voc_table(const float* d_dets, int64_t n, const float* d_sizes, float def_w, float def_h, int64_t* d_img,
+                 int64_t* d_cls, double* d_conf, double* d_corners, void* stream);
+size_t mc_workspace_bytes_voc_match(int64_t n, int64_t m);
+int mc_voc_match(const int64_t* d_key, const double* d_corners, int64_t n, const int64_t* d_gkey, const double* d_gbox,
+                 const uint8_t* d_gdiff, int64_t m, double ovthresh, double* d_tp, double* d_fp, void* d_ws,
+                 size_t ws_bytes, void* stream);
+
 /* dgrad weights for mc_conv_fwd: bf16 [Cpad, taps*Ko], row c, column tap'*Ko + o = (w*mask)[o, c, taps-1-tap'].      */
 int mc_pack_conv_weights_dgrad(const float* d_w, const float* d_mask, int O, int C, int ksize, void* d_wpack, int Cpad,
                                int Ko, void* stream);

@@ -109,6 +109,13 @@ _SIGNATURES = {
                                c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "mc_maxpool2x2_backward": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                        c_int, c_void_p]),
+    "mc_workspace_bytes_region_loss": (c_size_t, [c_int]),
+    "mc_region_loss": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(c_double), c_float, c_float,
+                               c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mc_voc_table": (c_int, [c_void_p, c_int64, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mc_workspace_bytes_voc_match": (c_size_t, [c_int64, c_int64]),
+    "mc_voc_match": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_void_p,
+                             c_void_p, c_void_p, c_size_t, c_void_p]),
     "mc_bn_pool_supported": (c_int, [c_int]),
     "mc_bn_apply_pool": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
                                  c_void_p]),

@@ -90,9 +90,9 @@ class EmptyModule(nn.Module):
 
 class RegionLoss(nn.Module):
     """nets.py:442-636.  Hyper-parameters as in the reference (filled by create_network :873-889).  ``forward`` is the
-    device-resident, vectorised restatement in region_loss.py: no copy to the CPU, no Python loop
-    over images / boxes / anchors; loss and gradient equal the reference's to float32 round-off
-    (oracle/make_golden_region.py)."""
+    libmcb200 call of region_loss.py (csrc/region_loss.cu): no copy to the CPU, no Python loop over
+    images / boxes / anchors; loss and gradient equal the reference's to float32 round-off (tests/golden/region_loss.npz,
+    written by oracle/make_golden_region.py from the unmodified reference)."""
 
     def __init__(self, num_classes=20, anchor_list=None, anchors_cell=5):
         super(RegionLoss, self).__init__()

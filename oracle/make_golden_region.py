@@ -1,4 +1,4 @@
-"""Pins the vectorised region loss (modelcompression_b200/region_loss.py) against the UNMODIFIED reference
+"""Pins the vectorised region loss (oracle/region_oracle.py) against the UNMODIFIED reference
 RegionLoss + build_targets (src/nets.py:282-636), CPU only.  The reference allocates torch.cuda tensors
 unconditionally; the shim maps torch.cuda.FloatTensor/LongTensor to the CPU types (Tensor.cuda is already the
 identity, oracle/ref_shim.py).  Asserts loss and d loss / d output agree to float32 round-off for several scale settings,
@@ -13,7 +13,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import ref_shim  # noqa: E402
-from modelcompression_b200.region_loss import region_loss  # noqa: E402
+from oracle.region_oracle import region_loss  # noqa: E402
 
 ANCHORS = [1.3221, 1.73145, 3.19275, 4.00944, 5.05587, 8.09892, 9.47112, 4.84053, 11.2364, 10.0071]
 

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 import modelcompression_b200 as mc
-from conftest import make_darknet
+from conftest import load_golden, make_darknet
 from modelcompression_b200.eval import evaluate_sharded, shard_range
 from oracle import detect_oracle
 
@@ -205,3 +205,21 @@ def test_end_to_end_map_bf16_forward_vs_fp32_oracle(cfg_path):
     assert abs(map_ref - map_got) <= 0.03
     assert max(abs(a - b) for a, b in zip(aps, aps_ref)) <= 0.2
     assert frac >= 0.85
+
+
+def test_voc_scorer_kernels_match_reference_golden():
+    """N1 on the GPU: mc_voc_table + mc_voc_match + the vectorised AP (modelcompression_b200/voc_eval.py) reproduce the
+    reference's voc_eval APs exactly (tests/golden/voc_map.npz, written by oracle/make_golden_map.py from the unmodified
+    src/predict.py): 20 classes, VOC07 11-point and area metrics, confidence ties and 'difficult' boxes included; CPU
+    tensors are refused."""
+    from modelcompression_b200 import voc_eval
+    g = load_golden('voc_map.npz')
+    dets, gts = torch.from_numpy(g['dets']).to(DEV), torch.from_numpy(g['gts']).to(DEV)
+    for m07, key in ((True, 'ap07'), (False, 'ap_area')):
+        aps, m = voc_eval.mean_ap(dets, gts, 20, None, 0.5, m07)
+        assert aps == g[key].tolist()
+        assert m == float(np.mean(g[key]))
+    aps0, m0 = voc_eval.mean_ap(dets[:0], gts, 20, None, 0.5, True)
+    assert aps0 == [0.0] * 20 and m0 == 0.0
+    with pytest.raises(Exception):
+        voc_eval.mean_ap(dets.cpu(), gts.cpu(), 20, None, 0.5, True)

@@ -490,6 +490,42 @@ def test_region_loss_on_device_and_full_retrain_step(cfg_path):
     assert mc.are_masks_consistent(model, [c.mask for c in model.masked_convs()]) is True
 
 
+def test_region_loss_kernel_vs_oracle_random():
+    """mc_region_loss against the pinned oracle (oracle/region_oracle.py) on random heads and label lists that exercise
+    the quirks: lists ending at the first x == 0, two boxes landing on the same (anchor, cell), boxes with no positive
+    anchor IoU (zero width), every scale combination."""
+    from modelcompression_b200.region_loss import region_loss
+    from oracle import region_oracle
+    anchors = [1.3221, 1.73145, 3.19275, 4.00944, 5.05587, 8.09892, 9.47112, 4.84053, 11.2364, 10.0071]
+    torch.manual_seed(5)
+    nB = 6
+    out0 = torch.randn(nB, 125, 13, 13, device=DEV) * 0.7
+    target = torch.zeros(nB, 250, device=DEV)
+    gen = torch.Generator().manual_seed(7)
+    for b in range(nB):
+        nbox = [0, 1, 3, 7, 20, 50][b]
+        for j in range(nbox):
+            cls = float(torch.randint(0, 20, (1,), generator=gen))
+            x, y = (torch.rand(2, generator=gen) * 0.9 + 0.05).tolist()
+            w, h = (torch.rand(2, generator=gen) * 0.5 + 0.02).tolist()
+            target[b, 5 * j:5 * j + 5] = torch.tensor([cls, x, y, w, h])
+    target[3, 5:10] = target[3, 0:5]                      # two boxes on the same (anchor, cell): the later one wins
+    target[3, 5] = float((int(target[3, 0]) + 3) % 20)    # ... with another class
+    target[4, 5 * 4 + 3] = 0.0                            # zero width: no anchor has a positive IoU -> last anchor
+    target[4, 5 * 9 + 1] = 0.0                            # x == 0 ends the list: boxes 9..19 of image 4 are ignored
+    for cs, ns, os_, cl in ((1, 1, 1, 1), (1, 1, 5, 1), (2.5, 0.5, 5, 3)):
+        o_k = out0.clone().requires_grad_(True)
+        o_o = out0.clone().requires_grad_(True)
+        l_k = region_loss(o_k, target, anchors, 5, 20, cs, ns, os_, cl, 0.6)
+        l_o = region_oracle.region_loss(o_o, target, anchors, 5, 20, cs, ns, os_, cl, 0.6)
+        (l_k * 1.7).backward()
+        (l_o * 1.7).backward()
+        assert abs(float(l_k.detach()) - float(l_o.detach())) <= 1e-5 * abs(float(l_o.detach()))
+        assert float((o_k.grad - o_o.grad).abs().max()) <= 1e-5 * float(o_o.grad.abs().max())
+    with pytest.raises(Exception):
+        region_loss(out0.cpu(), target.cpu(), anchors, 5, 20)
+
+
 def test_masked_sgd_equals_torch_sgd():
     """MaskedSGD (one libmcb200 launch over all parameters) vs torch.optim.SGD with the reference's hyper-parameters
     (src/train.py:144-147): same parameters and momentum buffers after several steps, ragged sizes included."""

@@ -135,18 +135,11 @@ def test_forward_oracle_against_reference_vectors(cfg_path):
 
 
 def test_voc_scorer_matches_reference_golden():
-    """N1: the tensor scorer (modelcompression_b200/voc_eval.py, device-agnostic torch code, here on CPU tensors) and
-    the NumPy oracle both reproduce the reference's voc_eval APs (tests/golden/voc_map.npz, pinned by
-    oracle/make_golden_map.py): 20 classes, VOC07 11-point and area metrics, ties and 'difficult' boxes included."""
-    import torch
-    from modelcompression_b200 import voc_eval
+    """N1: the NumPy oracle reproduces the reference's voc_eval APs (tests/golden/voc_map.npz, pinned by
+    oracle/make_golden_map.py): 20 classes, ties and 'difficult' boxes included.  (The product's scorer — kernels in
+    csrc/voc_eval.cu — is checked against the same vectors on the GPU: tests/test_gpu_eval.py.)"""
     from oracle import map_oracle
     g = load_golden('voc_map.npz')
-    dets, gts = torch.from_numpy(g['dets']), torch.from_numpy(g['gts'])
-    for m07, key in ((True, 'ap07'), (False, 'ap_area')):
-        aps, m = voc_eval.mean_ap(dets, gts, 20, None, 0.5, m07)
-        assert aps == g[key].tolist()
-        assert m == float(np.mean(g[key]))
     # the oracle from the flat rows (one (cls_conf, cls_id) pair per row)
     kept = [[] for _ in range(int(g['n_images']))]
     for r in g['dets']:
@@ -160,10 +153,10 @@ def test_voc_scorer_matches_reference_golden():
 
 
 def test_region_loss_matches_reference_golden():
-    """N3: the vectorised region loss equals the reference's RegionLoss + build_targets (loss and gradient stored by
-    oracle/make_golden_region.py) — run here on CPU tensors; the GPU test runs the same check on cuda."""
+    """N3: the region-loss oracle equals the reference's RegionLoss + build_targets (loss and gradient stored by
+    oracle/make_golden_region.py); the GPU test checks the product's kernels against the same vectors and the oracle."""
     import torch
-    from modelcompression_b200.region_loss import region_loss
+    from oracle.region_oracle import region_loss
     g = load_golden('region_loss.npz')
     anchors = [1.3221, 1.73145, 3.19275, 4.00944, 5.05587, 8.09892, 9.47112, 4.84053, 11.2364, 10.0071]
     for name in ('ones', 'cfg', 'mixed'):
