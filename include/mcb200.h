@@ -225,6 +225,9 @@ typedef struct mc_conv_desc {
   void* d_ws;            /* optional scratch (256-byte aligned, mc_workspace_bytes_conv_fwd bytes, its first 2 KB ZERO   */
   size_t ws_bytes;       /* before the first use; launches leave them zero): lets the CTA-pair kernel split the partial  */
                          /* last wave of tiles along K (stream-K).  NULL: whole tiles only.                             */
+  float* d_stat_sum;     /* optional, MC_EPI_PNHWC with N > 32 only (training forward): per-output-channel sum and sum of */
+  float* d_stat_sumsq;   /* squares of the STORED bf16 values over all rows are ADDED here (atomics; the caller zeroes    */
+                         /* them) — nn.BatchNorm2d's batch statistics (src/nets.py:802) without a pass over the output.   */
 } mc_conv_desc;
 
 int mc_conv_fwd(const mc_conv_desc* desc, void* stream);

@@ -37,6 +37,7 @@ class mc_conv_desc(ctypes.Structure):
         ("block_n", c_int), ("stages", c_int), ("block_k", c_int), ("in_cols", c_int),
         ("decode", POINTER(mc_decode_params)),
         ("d_ws", c_void_p), ("ws_bytes", c_size_t),
+        ("d_stat_sum", c_void_p), ("d_stat_sumsq", c_void_p),
     ]
 
 

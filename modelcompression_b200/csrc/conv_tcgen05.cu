@@ -53,6 +53,8 @@ struct ConvKParams {
   int out_pitch;   // > 0: PNHWC epilogue stages each warp's 32 rows in shared memory (row pitch in bytes) and writes them out coalesced
   int out_chunk;   // columns staged at a time (<= 64)
   int tma_bufs;    // > 0: PNHWC epilogue writes whole 64-column chunks with TMA stores from this many 4 KB slabs per warp
+  float* stat_sum;    // training forward: per-channel sum / sum of squares of the STORED (bf16-rounded) outputs are
+  float* stat_sumsq;  // accumulated from the TMA-store slabs (the batch statistics of BatchNorm); nullptr: off
   unsigned int wp_mul, wp_shr, hp_mul, hp_shr;  // magic-number division by Wp and Hp (row -> x, y, b)
   int last_ksteps;  // UMMA K steps (16 channels) that hold real channels in the LAST channel block of a tap
   int b_resident;   // share_dx only: all weight tiles stay in shared memory for the whole launch (one N tile, small K)
@@ -185,6 +187,37 @@ __device__ __forceinline__ void pack16_to_slab(const float (&v)[16], uint8_t* ro
   }
 }
 
+// Batch statistics from a finished 32-row x 64-column slab: lane L owns columns 2L, 2L+1 (one 4-byte word per row: the
+// 32 lanes read 32 different words of a 128-byte row, conflict-free) and adds the 32 rows into this warp's private
+// shared-memory accumulators acc[0][col] (sum) / acc[1][col] (sum of squares); pad rows hold zeros.
+__device__ __forceinline__ void slab_stats(const uint8_t* sb, float* acc /*[2][256]*/, int col0, int lane) {
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  const int j = lane >> 2, w = lane & 3;
+#pragma unroll 8
+  for (int r = 0; r < 32; ++r) {
+    const uint32_t u = *reinterpret_cast<const uint32_t*>(sb + r * 128 + ((j ^ (r & 7)) << 4) + w * 4);
+    const float a = __uint_as_float(u << 16), b = __uint_as_float(u & 0xffff0000u);
+    s0 += a; s1 += b;
+    q0 = fmaf(a, a, q0); q1 = fmaf(b, b, q1);
+  }
+  acc[col0 + 2 * lane] += s0;
+  acc[col0 + 2 * lane + 1] += s1;
+  acc[256 + col0 + 2 * lane] += q0;
+  acc[256 + col0 + 2 * lane + 1] += q1;
+}
+// the warp's accumulated statistics of N tile n0 -> global (one atomic per column, statistic and warp), then zero
+__device__ __forceinline__ void flush_stats(const ConvKParams& p, float* acc, int n0, int lane) {
+  for (int c = lane; c < p.block_n; c += 32) {
+    if (n0 + c < p.N) {
+      atomicAdd(p.stat_sum + n0 + c, acc[c]);
+      atomicAdd(p.stat_sumsq + n0 + c, acc[256 + c]);
+    }
+    acc[c] = 0.f;
+    acc[256 + c] = 0.f;
+  }
+  __syncwarp();
+}
+
 // PNHWC epilogue of one accumulator tile through TMA stores.  A warp owns 32 rows; every whole 64-column chunk of the
 // tile is converted into the warp's 4 KB slab (32 rows x 128 B, swizzled like the tensor map of the output) and leaves
 // as ONE bulk tensor store — 128-byte rows, issued by one lane, asynchronous — instead of 16-byte pieces one row pitch
@@ -196,7 +229,7 @@ template <bool LEAKY, bool PAIR, bool WIDE_LD, typename AddFn>
 __device__ __forceinline__ void epilogue_tile_tma(const ConvKParams& p, const CUtensorMap* tm_out, uint32_t taddr_row,
                                                   const float* sc, const float* sh, bool interior, bool in_buf,
                                                   int row0, int n0, long long out_row_base, bool vec_ok, uint8_t* slab,
-                                                  int& buf, uint64_t* empty_bar, AddFn add) {
+                                                  int& buf, uint64_t* empty_bar, AddFn add, float* stat_acc = nullptr) {
   const int lane = threadIdx.x & 31;
   int cols_valid = ((p.N - n0 + 7) >> 3) << 3;  // whole 8-groups up to the last one holding a real channel
   if (cols_valid > p.block_n) cols_valid = p.block_n;
@@ -244,6 +277,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const ConvKParams& p, const CU
       ptx::tma_store_2d(tm_out, sb, n0 + cc, row0);
       ptx::bulk_commit_group();
     }
+    if (stat_acc != nullptr) slab_stats(sb, stat_acc, cc, lane);
     if (p.tma_bufs >= 2) buf ^= 1;
   }
   for (int c0 = full_cols; c0 < p.block_n; c0 += 32) {
@@ -291,6 +325,14 @@ __device__ __forceinline__ void epilogue_loop(const ConvKParams& p, uint32_t tme
   int as = 0;
   uint32_t aphase = 0;
   int slab_buf = 0;  // (TMA-store epilogue) slab of this warp the next chunk goes to
+  // (batch statistics) this warp's accumulators behind the slabs; flushed whenever the N tile changes and at the end
+  float* stat_acc = nullptr;
+  int stat_n0 = -1;
+  if (MODE == MC_EPI_PNHWC && p.tma_bufs > 0 && p.stat_sum != nullptr) {
+    stat_acc = reinterpret_cast<float*>(s_out + (size_t)4 * p.tma_bufs * 4096) + quarter * 512;
+    for (int c = lane; c < 512; c += 32) stat_acc[c] = 0.f;
+    __syncwarp();
+  }
   // one N tile: every tile of the launch uses the same scale/shift slice, staged once (a narrow layer's epilogue is
   // otherwise a chain of global-load latency + barrier per 128 rows)
   const bool one_n_tile = p.n_tiles == 1;
@@ -344,9 +386,13 @@ __device__ __forceinline__ void epilogue_loop(const ConvKParams& p, uint32_t tme
     const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.acc_stride);
 
     if (MODE == MC_EPI_PNHWC && p.tma_bufs > 0) {
+      if (stat_acc != nullptr && n0 != stat_n0) {
+        if (stat_n0 >= 0) flush_stats(p, stat_acc, stat_n0, lane);
+        stat_n0 = n0;
+      }
       epilogue_tile_tma<LEAKY, PAIR, WIDE_LD>(p, tm_out, taddr_row, sc, sh, interior, in_buf, m0 + quarter * 32, n0, out_row_base,
                                      vec_ok, s_out + (size_t)quarter * p.tma_bufs * 4096, slab_buf, &tmem_empty_bar[as],
-                                     [](uint32_t (&)[16], int) {});
+                                     [](uint32_t (&)[16], int) {}, stat_acc);
       if (!PAIR && et == 0 && ti < 8) conv_stamp(p, 13 + 2 * ti);
       if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
       continue;
@@ -485,6 +531,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvKParams& p, uint32_t tme
     if (!PAIR && et == 0 && ti < 8) conv_stamp(p, 13 + 2 * ti);
     if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
   }
+  if (stat_acc != nullptr && stat_n0 >= 0) flush_stats(p, stat_acc, stat_n0, lane);
   if (MODE == MC_EPI_PNHWC && p.tma_bufs > 0 && lane == 0) ptx::bulk_wait_group_read<0>();  // slabs read before the CTA exits
 }
 
@@ -827,6 +874,13 @@ __device__ __forceinline__ void epilogue_loop_pair(const ConvKParams& p, uint32_
   int as = 0;
   uint32_t aphase = 0;
   int slab_buf = 0;
+  float* stat_acc = nullptr;
+  int stat_n0 = -1;
+  if (MODE == MC_EPI_PNHWC && p.tma_bufs > 0 && p.stat_sum != nullptr) {
+    stat_acc = reinterpret_cast<float*>(s_out + (size_t)4 * p.tma_bufs * 4096) + quarter * 512;
+    for (int c = lane; c < 512; c += 32) stat_acc[c] = 0.f;
+    __syncwarp();
+  }
   const bool one_n_tile = p.n_tiles == 1;
   if (one_n_tile) {
     for (int i = et; i < p.block_n; i += 128) {
@@ -935,6 +989,10 @@ __device__ __forceinline__ void epilogue_loop_pair(const ConvKParams& p, uint32_
         __threadfence();
       }
       if (MODE == MC_EPI_PNHWC && p.tma_bufs > 0) {
+        if (stat_acc != nullptr && n0 != stat_n0) {
+          if (stat_n0 >= 0) flush_stats(p, stat_acc, stat_n0, lane);
+          stat_n0 = n0;
+        }
         epilogue_tile_tma<LEAKY, true, true>(p, tm_out, taddr_row, sc, sh, interior, in_buf, m0 + quarter * 32, n0, out_row_base,
                                        vec_ok, s_out + (size_t)quarter * p.tma_bufs * 4096, slab_buf, &tmem_empty_bar[as],
                                        [&](uint32_t (&r)[16], int col) {
@@ -948,7 +1006,7 @@ __device__ __forceinline__ void epilogue_loop_pair(const ConvKParams& p, uint32_
                                              r[4 * q + 3] = __float_as_uint(__uint_as_float(r[4 * q + 3]) + a.w);
                                            }
                                          }
-                                       });
+                                       }, stat_acc);
         if (et == 0 && ti < 8) conv_stamp(p, 13 + 2 * ti);
         if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
         continue;
@@ -995,6 +1053,7 @@ __device__ __forceinline__ void epilogue_loop_pair(const ConvKParams& p, uint32_
     if (et == 0 && ti < 8) conv_stamp(p, 13 + 2 * ti);
     if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
   }
+  if (stat_acc != nullptr && stat_n0 >= 0) flush_stats(p, stat_acc, stat_n0, lane);
   if (MODE == MC_EPI_PNHWC && p.tma_bufs > 0 && lane == 0) ptx::bulk_wait_group_read<0>();  // slabs read before the CTA exits
 }
 
@@ -1281,6 +1340,15 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   }
   if (decode) block_n = d->Npad;  // every logit of a cell in ONE accumulator row
   if (block_n <= 0) block_n = pick_block_n(d->Npad, m_tiles, (ntaps * Kc + 63) / 64, mc_num_sms(), false);  // 64-wide k-block units
+  const bool want_stats = d->d_stat_sum != nullptr || d->d_stat_sumsq != nullptr;
+  if (want_stats) {
+    // batch statistics come from the TMA-store slabs: every column of a tile must leave in a whole 64-column chunk
+    MC_CHECK_ARG(d->d_stat_sum != nullptr && d->d_stat_sumsq != nullptr, "mc_conv_fwd: d_stat_sum and d_stat_sumsq go together");
+    MC_CHECK_ARG(d->epi_mode == MC_EPI_PNHWC && ((d->ldc | d->ch_off) & 7) == 0 && d->N >= 33,
+                 "mc_conv_fwd: statistics need the PNHWC epilogue, 8-aligned pitch / offset and more than 32 channels");
+    block_n = (block_n + 63) / 64 * 64;
+    if (block_n > 256) block_n = 256;
+  }
   MC_CHECK_ARG(block_n >= 16 && block_n <= 256 && (block_n % 16) == 0, "mc_conv_fwd: block_n %d invalid", block_n);
   const int n_tiles = (d->Npad + block_n - 1) / block_n;
 
@@ -1337,7 +1405,8 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   // (decode epilogue: 128 rows x (block_n + 1) floats of logits)
   auto out_stage_for = [&](int ctas_) -> size_t {
     return decode ? (size_t)128 * (block_n + 1) * 4
-                  : (tma_out ? (size_t)tma_bufs_for(ctas_) * 4 * 4096 : (size_t)128 * out_pitch);
+                  : (tma_out ? (size_t)tma_bufs_for(ctas_) * 4 * 4096 + (want_stats ? 4 * 512 * sizeof(float) : 0)
+                             : (size_t)128 * out_pitch);
   };
   auto plan_ring = [&](int ctas, int* st, int* ast, size_t* bytes) -> bool {
     const size_t out_stage_bytes = out_stage_for(ctas);
@@ -1428,7 +1497,7 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
     ctas = 1;
     a_stages = DEF_A_STAGES;
     const int b_half = block_n / 2 * 128;
-    const int slab_bytes = tma_bufs_for(1) * 4 * 4096;
+    const int slab_bytes = tma_bufs_for(1) * 4 * 4096 + (want_stats ? 4 * 512 * (int)sizeof(float) : 0);
     stages = (220 * 1024 - a_stages * A_BOX_STRIDE - slab_bytes) / b_half;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     smem_bytes = (size_t)a_stages * A_BOX_STRIDE + (size_t)stages * b_half + AUX_BYTES + slab_bytes;
@@ -1505,6 +1574,9 @@ extern "C" int mc_conv_fwd(const mc_conv_desc* d, void* stream_) {
   p.out_pitch = use_pair ? 0 : out_pitch;
   p.out_chunk = out_chunk;
   p.tma_bufs = tma_bufs;
+  p.stat_sum = d->d_stat_sum;
+  p.stat_sumsq = d->d_stat_sumsq;
+  MC_CHECK_ARG(!want_stats || tma_bufs > 0, "mc_conv_fwd: statistics need the TMA-store epilogue (tuning switch disabled it)");
   {
     auto magic = [](unsigned int dv, unsigned int* mul, unsigned int* shr) {
       unsigned int l = 0;

@@ -314,7 +314,10 @@ def _forward(plan, x, training_stats=True, after_layer=None, needs_backward=True
     sv.x, sv.B, sv.bufs, sv.stats = x, B, bufs, {}
     s = _lib.stream_ptr()
     y = None
+    fuse_stats = bool(getattr(plan, 'fuse_stats', True))
     for L in plan.layers:
+        stats_done = False
+        st = None
         conv = L.conv
         w = conv.weight.data
         mask_ptr = _masked(conv)
@@ -362,12 +365,19 @@ def _forward(plan, x, training_stats=True, after_layer=None, needs_backward=True
             z = bufs[L.z.name]
             d = _conv_desc(in_ptr, wpack.data_ptr(), ones.data_ptr(), zeros.data_ptr(), z.data_ptr(), B, L.H, L.W, C,
                            src.ld, O, Npad, k, 0, _lib.MC_EPI_PNHWC, L.z.ld, 0, kb, plan, dev)
+            if fuse_stats and O > 32 and (L.z.ld % 8) == 0:
+                # batch statistics straight from the conv epilogue (sums of the stored bf16 z): no mc_col_stats pass
+                st = torch.zeros(6, O, device=dev)
+                d.d_stat_sum, d.d_stat_sumsq = st[0].data_ptr(), st[1].data_ptr()
+                stats_done = True
             _lib.check(lib.mc_conv_fwd(ctypes.byref(d), s), "conv forward (block %d)" % L.ind)
         # ---- batch statistics + affine + leaky
         bn = L.bn
         rows = B * (L.H + 1) * (L.W + 1)
-        st = torch.empty(6, O, device=dev)  # sum, sumsq, scale, shift, mean, invstd
-        _lib.check(lib.mc_col_stats(z.data_ptr(), rows, O, L.z.ld, 0, st[0].data_ptr(), st[1].data_ptr(), s), "mc_col_stats")
+        if not stats_done:
+            st = torch.empty(6, O, device=dev)  # sum, sumsq, scale, shift, mean, invstd
+            _lib.check(lib.mc_col_stats(z.data_ptr(), rows, O, L.z.ld, 0, st[0].data_ptr(), st[1].data_ptr(), s),
+                       "mc_col_stats")
         upd = training_stats and bn.track_running_stats and bn.running_mean is not None
         mom = bn.momentum if bn.momentum is not None else 0.1
         _lib.check(lib.mc_bn_finalize(st[0].data_ptr(), st[1].data_ptr(), O, float(B * L.H * L.W), bn.weight.data_ptr(),

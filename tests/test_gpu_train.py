@@ -490,6 +490,43 @@ def test_region_loss_on_device_and_full_retrain_step(cfg_path):
     assert mc.are_masks_consistent(model, [c.mask for c in model.masked_convs()]) is True
 
 
+@pytest.mark.parametrize("B,C,O,H,W,k", [(4, 32, 64, 40, 40, 3), (3, 256, 512, 26, 26, 3), (8, 512, 1024, 13, 13, 3),
+                                         (2, 512, 256, 26, 26, 1), (3, 40, 80, 20, 12, 3)])
+def test_conv_epilogue_batch_statistics(B, C, O, H, W, k):
+    """Batch statistics from the conv epilogue (mc_conv_desc.d_stat_sum / d_stat_sumsq: sums of the stored bf16 outputs,
+    accumulated from the TMA-store slabs) against the sums of the output buffer itself (what mc_col_stats reads): narrow
+    one-tile layers, several N tiles per CTA, the CTA-pair kernel, a ragged channel count."""
+    from modelcompression_b200.engine_train import _conv_desc, _kblk, _round_up
+    lib = _lib.load()
+    torch.manual_seed(O + C)
+    rows = B * (H + 1) * (W + 1)
+    ld_in, ldz = _round_up(C, 8), _round_up(O, 8)
+    x4 = torch.zeros(B, H + 1, W + 1, ld_in, device=DEV)
+    x4[:, :H, :W, :C] = torch.randn(B, H, W, C, device=DEV)
+    xin = x4.view(rows, ld_in).to(torch.bfloat16).contiguous()
+    w = torch.randn(O, C, k, k, device=DEV) * (C * k * k) ** -0.5
+    kb = _kblk(C, k)
+    Kc, Npad = _round_up(C, kb), _round_up(O, 16)
+    wpack = torch.empty(Npad, k * k * Kc, dtype=torch.bfloat16, device=DEV)
+    ones, zeros = torch.ones(Npad, device=DEV), torch.zeros(Npad, device=DEV)
+    z = torch.zeros(rows, ldz, dtype=torch.bfloat16, device=DEV)
+    st = torch.zeros(2, O, device=DEV)
+    with torch.cuda.device(0):
+        s = _lib.stream_ptr()
+        _lib.check(lib.mc_pack_conv_weights(w.data_ptr(), None, O, C, k, None, O, None, C, wpack.data_ptr(), Npad, Kc, s), "pack")
+        d = _conv_desc(xin.data_ptr(), wpack.data_ptr(), ones.data_ptr(), zeros.data_ptr(), z.data_ptr(), B, H, W, C, ld_in, O,
+                       Npad, k, 0, _lib.MC_EPI_PNHWC, ldz, 0, kb)
+        d.d_stat_sum, d.d_stat_sumsq = st[0].data_ptr(), st[1].data_ptr()
+        _lib.check(lib.mc_conv_fwd(ctypes.byref(d), s), "conv")
+        torch.cuda.synchronize()
+    zf = z[:, :O].double()
+    ref_sum, ref_sq = zf.sum(0), (zf * zf).sum(0)
+    assert float((st[0].double() - ref_sum).abs().max()) <= 1e-4 * float(ref_sum.abs().max()) + 1e-3
+    assert float((st[1].double() - ref_sq).abs().max()) <= 1e-4 * float(ref_sq.abs().max())
+    if ldz > O:
+        assert float(z[:, O:].abs().max()) == 0.0
+
+
 def test_region_loss_kernel_vs_oracle_random():
     """mc_region_loss against the pinned oracle (oracle/region_oracle.py) on random heads and label lists that exercise
     the quirks: lists ending at the first x == 0, two boxes landing on the same (anchor, cell), boxes with no positive
