@@ -36,6 +36,7 @@ IMG = 416
 PRUNE_PERC = 40.0
 METRIC = "yolov2_416_pruned_fwd_images_per_sec"
 CPU_SAMPLE_BATCH = 4
+PER_OP_REPS = 6  # launches per event pair in the per-kernel timing (amortises the events' own cost)
 N_INPUT_BUFFERS = 6  # 6 x 33 MB uint8 batches = 199 MB > 126 MB L2
 DENSE_GFLOP_PER_IMAGE = 29.360
 
@@ -363,7 +364,9 @@ def time_eval_pipeline(model, device, B, rank, world, tag, conf=0.005, n_images=
     from modelcompression_b200.eval import evaluate_sharded
 
     get_batch = eval_image_source(device, B)
-    evaluate_sharded(model, get_batch, 4 * B * world, B, conf, 0.45, 0, rank, world, validation=True)  # warm-up
+    # warm-up at FULL size: the first pass also pays the caching allocator's cudaMalloc of the ~1 GB detection tensors
+    # (0.1-0.2 s, once per process), which is not the pipeline
+    evaluate_sharded(model, get_batch, n_images, B, conf, 0.45, 0, rank, world, validation=True)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -402,9 +405,9 @@ def time_eval_pipeline(model, device, B, rank, world, tag, conf=0.005, n_images=
 
 
 def time_scorer_and_loss(model, device, B):
-    """SURVEY.md §8f N1 / N3, timed (they are tensor code on the device, not hand-written kernels): the VOC07 scorer
-    (voc_eval.mean_ap, src/predict.py:216-437) on the detections of 512 KN-init images against synthetic labels, and
-    RegionLoss forward + backward (src/nets.py:442-636) on a batch-B head."""
+    """SURVEY.md §8f N1 / N3, timed: the VOC07 scorer (voc_eval.mean_ap, src/predict.py:216-437; csrc/voc_eval.cu) on the
+    detections of 512 KN-init images against synthetic labels, and RegionLoss forward + backward (src/nets.py:442-636;
+    csrc/region_loss.cu) on a batch-B head."""
     import numpy as np
     import torch
     from modelcompression_b200 import voc_eval
@@ -718,11 +721,18 @@ def main():
         # The launch queue is primed: a ~1.5 ms spin kernel holds the stream while the host enqueues the timed steps, so
         # the interval between the first and the last event is device time of exactly K steps (no idle gap before the
         # first launch, no host jitter inside a window that is only milliseconds long).
-        torch.cuda._sleep(3000000)
+        # The spin covers the host's enqueue time of all K steps (~60 us each: plan check, graph replay, output clone), and
+        # the garbage collector is off meanwhile: a host stall inside the loop (one 45 ms pause was seen in a 100-step
+        # run) would otherwise be billed to the device.
+        import gc
+        gc.collect()
+        gc.disable()
+        torch.cuda._sleep(max(3000000, 130000 * K))
         ev[0].record()
         for i in range(K):
             y = step(i)
             ev[i + 1].record()
+        gc.enable()
         while not ev[K].query():  # clocks / throttle reasons sampled DURING the timed region, off the launch path
             probe.sample()
             time.sleep(0.0005)
@@ -751,10 +761,13 @@ def main():
         ksteps = min(K, 20)
         for i in range(ksteps):
             events = []
-            plan.run(xs[i % len(xs)], events=events)
+            # queue primed: the eager launches (ctypes calls, ~20 us of host time each) are enqueued while the GPU spins, so
+            # an event interval is the kernel's duration on the device, not the host's latency between record and launch
+            torch.cuda._sleep(8000000)
+            plan.run(xs[i % len(xs)], events=events, repeat=PER_OP_REPS)
             torch.cuda.synchronize()
             for op, a, b in events:
-                ms = a.elapsed_time(b)
+                ms = a.elapsed_time(b) / PER_OP_REPS
                 if op['kind'] == 'conv':
                     conv_ms += ms
                 else:
@@ -889,6 +902,10 @@ def main():
                          peaks['source'], elapsed_ms),
                      "traffic": traffic, "traffic_unit": "bytes of DRAM traffic per launch (ncu --set full, %s)" % traffic_src,
                      "avg_launch_ms": conv_ms_per_launch, "launches_per_step": conv_launches,
+                     "how": "eager forwards on the launching stream with the launch queue primed by a spin kernel; every "
+                            "launch is issued %d times back to back between its two CUDA events and the interval divided "
+                            "by %d (an event pair costs a few microseconds, comparable to the short kernels); the timed "
+                            "steps themselves replay a CUDA graph" % (PER_OP_REPS, PER_OP_REPS),
                      "algorithmic_gflop_per_step": conv_flops_step / 1e9,
                      "kernel_share_of_step": conv_ms / max(conv_ms + other_ms, 1e-9),
                      "whole_net_tflops": whole_tflops, "whole_net_frac": whole_tflops / peaks['bf16'],
@@ -935,10 +952,11 @@ def main():
                     dper = {}
                     for i in range(5):
                         evs = []
-                        dplan.run(xs[i % len(xs)], events=evs)
+                        torch.cuda._sleep(8000000)
+                        dplan.run(xs[i % len(xs)], events=evs, repeat=PER_OP_REPS)
                         torch.cuda.synchronize()
                         for op, e0_, e1_ in evs:
-                            dper.setdefault(op['name'], []).append(e0_.elapsed_time(e1_))
+                            dper.setdefault(op['name'], []).append(e0_.elapsed_time(e1_) / PER_OP_REPS)
                 tfl = DENSE_GFLOP_PER_IMAGE * B / ms
                 line["dense"] = {"images_per_s": B / (ms * 1e-3), "tflops": tfl, "frac_of_bf16_burst": tfl / peaks['bf16'],
                                  "frac_of_bf16_sustained": tfl / peaks['bf16_sustained'], "ms_per_step": ms,

@@ -463,17 +463,19 @@ class CompiledDarknet(object):
         self._alloc[key] = tensors
         return tensors
 
-    def run(self, x, events=None, detect=None):
+    def run(self, x, events=None, detect=None, repeat=1):
         """Forward.  The launch sequence is captured into a CUDA graph the second time an input buffer (same
         device address and shape) is seen and replayed afterwards: ~25 launches per step otherwise cost more host time
         than the GPU needs for the small layers.  events: optional list; when given the eager path is used and
-        (op, start_event, end_event) is appended per op (bench/profiling).
+        (op, start_event, end_event) is appended per op (bench/profiling); with repeat > 1 every op is launched that many
+        times between its two events (same inputs, same outputs), so the events' own cost — a few microseconds per pair,
+        comparable to the short kernels — is amortised: interval / repeat is the kernel's device time.
         detect=(conf_thresh, only_objectness, want_cls): the head convolution runs with the region decode fused into
         its epilogue (MC_EPI_DECODE) and the call returns (boxes [B,P,8] dense slot table, cls [B,P,nc] or None)
         instead of the raw head."""
         if events is not None or not self.use_graph or not x.is_cuda or x.dtype not in (torch.float32, torch.uint8) or \
                 not x.is_contiguous() or x.requires_grad:
-            return self._run_eager(x, events, detect)
+            return self._run_eager(x, events, detect, repeat)
         # Graphs are keyed by the input ADDRESS (they read it in place).  A tensor OBJECT seen a third time gets its own
         # graph (zero-copy: a serving loop rotating over a few device buffers it keeps); any other input is copied into a
         # plan-owned static input buffer and replays that buffer's graph (33 MB for a uint8 batch of 64: ~10 us), so
@@ -542,7 +544,7 @@ class CompiledDarknet(object):
         return n == model.num_anchors * (5 + model.num_classes) and self.ops[-1]['Npad'] <= 256 and \
             len(model.anchors) == 2 * model.num_anchors and model.num_anchors <= 16
 
-    def _run_eager(self, x, events=None, detect=None):
+    def _run_eager(self, x, events=None, detect=None, repeat=1):
         if x.dim() != 4:
             raise ValueError("expected [B,3,H,W] input")
         _lib.require_cuda(x, "Darknet.forward")
@@ -564,11 +566,15 @@ class CompiledDarknet(object):
             bufs = list(self._buffers(B, H, W))
             stream = _lib.stream_ptr()
             out = None
-            for op in self.ops:
+            self._prev_op = None
+            for op in (o for o in self.ops for _ in range(repeat if events is not None else 1)):
                 kind = op['kind']
-                if events is not None:
+                first_rep = op is not getattr(self, '_prev_op', None)
+                self._prev_op = op
+                if events is not None and first_rep:
                     ev0 = torch.cuda.Event(enable_timing=True)
                     ev0.record()
+                    reps_left = repeat
                 if kind == 'im2col':
                     s = op['src']
                     if s is None:
@@ -661,9 +667,12 @@ class CompiledDarknet(object):
                 else:
                     raise RuntimeError("unknown op " + kind)
                 if events is not None:
-                    ev1 = torch.cuda.Event(enable_timing=True)
-                    ev1.record()
-                    events.append((op, ev0, ev1))
+                    reps_left -= 1
+                    if reps_left == 0:
+                        ev1 = torch.cuda.Event(enable_timing=True)
+                        ev1.record()
+                        events.append((op, ev0, ev1))
+            self._prev_op = None
             self._last_bufs = bufs
         return out
 
