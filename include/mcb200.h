@@ -253,6 +253,21 @@ int mc_conv_direct_fwd(const void* d_in, int in_is_nchw_f32, const float* d_w, c
                        const float* d_shift, void* d_out, int B, int H, int W, int Cin, int Cin_ld, int N, int ldc,
                        int ksize, int leaky, int pool, void* stream);
 
+/* Degenerate layers of a filter-pruned network on CUDA cores (csrc/conv_thin.cu): MaskedConv2d + folded BatchNorm +
+ * leaky [+ 2x2/2 max-pool] (src/nets.py:779-821) for a 3x3 layer with <= 8 input channels or a 1x1 layer with <= 32
+ * input channels and <= 8 outputs, a few hundred multiply-adds per pixel at most.  One thread per output pixel (or pool
+ * window); the weights are passed as KERNEL PARAMETERS, so h_w / h_scale / h_shift (and the *2 arrays) are HOST pointers:
+ *   h_w   fp32 [(tap*ct + c)*nt + n] = w[n,c,tap/k,tap%k] (bf16-rounded by the caller, zero padded), h_scale/h_shift [nt]
+ *   N2 > 0: the 1x1 layer behind a 3x3 layer is applied in the same thread to the bf16-rounded activations:
+ *   h_w2  fp32 [n*n2t + o] = w2[o,n], h_scale2/h_shift2 [n2t]; the output then has N2 channels.
+ * mc_conv_thin_geometry returns 1 and the padded sizes (ct channels read per input pixel, nt, n2t) when the shape is
+ * taken, 0 otherwise.  d_in: bf16 PNHWC with pitch Cin_ld >= ct; d_out: interior rows of a bf16 PNHWC buffer at (H,W) or
+ * (H/2,W/2) whose pad line/column are already zero; channels up to the next multiple of 8 are written (zeros).      */
+int mc_conv_thin_geometry(int ksize, int Cin, int N, int pool, int N2, int* ct, int* nt, int* n2t);
+int mc_conv_thin_fwd(const void* d_in, const float* h_w, const float* h_scale, const float* h_shift, const float* h_w2,
+                     const float* h_scale2, const float* h_shift2, void* d_out, int B, int H, int W, int Cin, int Cin_ld,
+                     int N, int ldc, int ksize, int leaky, int pool, int N2, int leaky2, void* stream);
+
 /* Thin 3x3 layers on the tensor cores with the im2col tile built in shared memory (csrc/conv_im2col_tc.cu): the
  * 3-channel first layer (in_is_nchw_f32=1, Cin<=4) or a PNHWC bf16 input with pitch == CL (8 for Cin<=8, 16 for
  * Cin<=16).  pool=1 fuses the 2x2/2 max-pool ("pool-window GEMM").  d_wexp is the expanded bf16 weight matrix

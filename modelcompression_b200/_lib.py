@@ -84,6 +84,9 @@ _SIGNATURES = {
     "mc_conv_direct_supported": (c_int, [c_int, c_int, c_int]),
     "mc_conv_direct_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                    c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mc_conv_thin_geometry": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "mc_conv_thin_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                 c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mc_conv_im2col_supported": (c_int, [c_int, c_int, c_int, c_int]),
     "mc_conv_im2col_geometry": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int),
                                         POINTER(c_int)]),

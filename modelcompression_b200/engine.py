@@ -44,6 +44,25 @@ def _pitch(n):
     return full if full * 4 <= ld * 5 else ld
 
 
+def _c_floats(t):
+    """host float array handed to libmcb200 by pointer (kernel-parameter weights of csrc/conv_thin.cu)."""
+    vals = t.flatten().tolist()
+    return (ctypes.c_float * len(vals))(*vals)
+
+
+def _thin_host_weights(wd, sc, sh, ct, nt):
+    """mc_conv_thin_fwd's weight layout [(tap*ct + c)*nt + n] from the gathered fp32 [n, c, k, k] weights, rounded to bf16
+    (the operand precision of the tensor-core layers), zero padded; scale/shift padded to nt."""
+    n, c, k, _ = wd.shape
+    wt = torch.zeros(k * k, ct, nt)
+    wt[:, :c, :n] = wd.to(torch.bfloat16).float().permute(2, 3, 1, 0).reshape(k * k, c, n).cpu()
+    sct = torch.zeros(nt)
+    sht = torch.zeros(nt)
+    sct[:n] = sc.float().cpu()
+    sht[:n] = sh.float().cpu()
+    return _c_floats(wt), _c_floats(sct), _c_floats(sht)
+
+
 class _TensorRef(object):
     """A logical activation: where it lives and how its physical channels map to the original channel space."""
 
@@ -64,6 +83,7 @@ class _Buf(object):
     def __init__(self, H, W, ld, zero_init=False, fp32_nchw_channels=0):
         self.H, self.W, self.ld = H, W, ld
         self.zero_init = zero_init
+        self.dead = False  # True: its producer was fused into the consumer (never allocated)
         self.fp32_nchw_channels = fp32_nchw_channels  # >0: this is the fp32 NCHW network output
 
 
@@ -80,6 +100,9 @@ class CompiledDarknet(object):
                 raise RuntimeError("Darknet.forward: " + self.lib.mc_last_error_string().decode())
         self.shrink = bool(shrink)
         self.use_window = bool(getattr(model, 'b200_window', True))  # (False: the im2col-build kernels, for A/B runs)
+        # CUDA-core kernel for the degenerate layers of a shrunk net (csrc/conv_thin.cu): 0 off, 1 on, 2 on + the 1x1 layer
+        # behind a thin 3x3 layer applied in the same kernel
+        self.use_thin = int(getattr(model, 'b200_thin', 2))
         self.bufs = []       # list[_Buf] (shapes depend on input H, W: compiled for the cfg's width/height lazily)
         self.ops = []        # list of dict
         self.block_out = {}  # models index -> _TensorRef
@@ -204,6 +227,73 @@ class CompiledDarknet(object):
                 raise NotImplementedError("cfg block type '%s'" % btype)
         self.out_ref = cur
         del n_models
+        if self.use_thin >= 2:
+            routed = set()
+            ind = -2
+            for block in blocks:
+                ind += 1
+                if block['type'] == 'route':
+                    routed.update(int(i) if int(i) > 0 else int(i) + ind for i in block['layers'].split(','))
+            self._fuse_thin_pairs(routed)
+
+    def _fuse_thin_pairs(self, routed):
+        """thin 3x3 layer -> 1x1 layer with <= 8 outputs: the second layer is applied by the same thread to the bf16-rounded
+        activations (csrc/conv_thin.cu, N2T > 0); the intermediate tensor is never stored and its block output is no
+        longer available to block_activation()."""
+        i = 0
+        while i + 1 < len(self.ops):
+            a, b = self.ops[i], self.ops[i + 1]
+            i += 1
+            if a['kind'] != 'thin' or a['pool'] or a['ksize'] != 3 or a['N2'] or a['ind'] in routed:
+                continue
+            if b['kind'] == 'conv':
+                if b['ksize'] != 1 or not b.get('plain') or b['epi'] != _lib.MC_EPI_PNHWC or b['ch_off'] != 0:
+                    continue
+                b_ld = b['ldc']
+            elif b['kind'] == 'thin':
+                if b['ksize'] != 1 or b['N2']:
+                    continue
+                b_ld = b['ld']
+            else:
+                continue
+            if b['src'].buf_id != a['dst_buf'] or b['src'].ch_off != 0 or b['Cin'] != a['N']:
+                continue
+            ct, nt, n2t = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+            if self.lib.mc_conv_thin_geometry(3, a['Cin'], a['N'], 0, b['N'], ctypes.byref(ct), ctypes.byref(nt),
+                                              ctypes.byref(n2t)) != 1:
+                continue
+            ct, nt, n2t = ct.value, nt.value, n2t.value
+            if self.bufs[a['src'].buf_id].ld < ct or b_ld < _round_up(n2t, 8):
+                continue
+            # first layer's weights re-padded to the fused instance's NT; second layer's from its packed bf16 matrix
+            taps, ct0, nt0 = 9, a['hw_shape'][1], a['hw_shape'][2]
+            w1 = torch.tensor(list(a['hw'])).view(taps, ct0, nt0)
+            w1p = torch.zeros(taps, ct, nt)
+            w1p[:, :min(ct, ct0), :min(nt, nt0)] = w1[:, :min(ct, ct0), :min(nt, nt0)]
+            sc1 = torch.zeros(nt)
+            sh1 = torch.zeros(nt)
+            sc1[:a['N']] = torch.tensor(list(a['hsc']))[:a['N']]
+            sh1[:a['N']] = torch.tensor(list(a['hsh']))[:a['N']]
+            w2 = torch.zeros(nt, n2t)
+            sc2 = torch.zeros(n2t)
+            sh2 = torch.zeros(n2t)
+            if b['kind'] == 'conv':
+                w2[:a['N'], :b['N']] = b['wpack'][:b['N'], :a['N']].float().t().cpu()
+                sc2[:b['N']] = b['scale'][:b['N']].cpu()
+                sh2[:b['N']] = b['shift'][:b['N']].cpu()
+            else:
+                wb = torch.tensor(list(b['hw'])).view(b['hw_shape'])[0]  # [ct_b, nt_b] = w2[o, c] at [c, o]
+                w2[:a['N'], :b['N']] = wb[:a['N'], :b['N']]
+                sc2[:b['N']] = torch.tensor(list(b['hsc']))[:b['N']]
+                sh2[:b['N']] = torch.tensor(list(b['hsh']))[:b['N']]
+            fused = dict(a)
+            fused.update(hw=_c_floats(w1p), hsc=_c_floats(sc1), hsh=_c_floats(sh1), hw_shape=(taps, ct, nt),
+                         hw2=_c_floats(w2), hsc2=_c_floats(sc2), hsh2=_c_floats(sh2), N2=b['N'], leaky2=b['leaky'],
+                         dst_buf=b['dst_buf'], ld=b_ld, name='thin@%d+%d' % (a['ind'], b['ind']),
+                         flops_per_image=a['flops_per_image'] + b['flops_per_image'], fused_n1=a['N'])
+            self.bufs[a['dst_buf']].dead = True  # the intermediate activation no longer exists
+            self.block_out.pop(a['ind'], None)
+            self.ops[i - 1:i + 1] = [fused]
 
     def _compile_conv(self, conv, bn, leaky, src, src_hw, in_ch, is_head, ind, cat_of, cat_state, nxt_is_pool,
                       nxt_is_reorg):
@@ -287,6 +377,25 @@ class CompiledDarknet(object):
             wd[torch.tensor([o < 0 for o in o_list], device=dev)] = 0
             wd[:, torch.tensor([c < 0 for c in cidx], device=dev)] = 0
             return wd
+
+        # ---- degenerate layers (a few hundred multiply-adds per pixel): CUDA-core kernel with the weights as kernel
+        #      parameters (csrc/conv_thin.cu).  Measured on B200 at batch 64 (tools/bench_layers.py): 4 -> 1 + pool at 208^2,
+        #      1 -> 17 at 104^2, 17 -> 4 (1x1) and 4 -> 11 + pool at 104^2 took 37 / 28 / 31 / 25 us on the tensor-core thin
+        #      kernels (per-tile latency chain), bound by reading the input once here.
+        if self.use_thin and plain_dst and not first and src.ch_off == 0 and (not pool or (H % 2 == 0 and W % 2 == 0)):
+            ct, nt = ctypes.c_int(), ctypes.c_int()
+            src_ld = self.bufs[src.buf_id].ld
+            if self.lib.mc_conv_thin_geometry(k, c_phys_in, n_phys, pool, 0, ctypes.byref(ct), ctypes.byref(nt), None) == 1 \
+                    and src_ld >= ct.value and _pitch(n_phys) >= _round_up(nt.value, 8):
+                ct, nt = ct.value, nt.value
+                Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+                ld = _pitch(n_phys)
+                bid = self._new_buf(Ho, Wo, ld, zero_init=True)  # pad line/column stay zero: the kernel never writes them
+                hw, hsc, hsh = _thin_host_weights(gathered_fp32(), sc, sh, ct, nt)
+                self.ops.append(dict(kind='thin', src=src, hw=hw, hsc=hsc, hsh=hsh, hw_shape=(taps, ct, nt), dst_buf=bid, N=n_phys, Cin=c_phys_in,
+                                     H=H, W=W, ld=ld, pool=pool, ksize=k, leaky=int(leaky), N2=0, leaky2=0, ind=ind,
+                                     name='thin%s@%d' % ('+pool' if pool else '', ind), flops_per_image=op_flops))
+                return _TensorRef(bid, Ho, Wo, O, out_colsrc, const_out), ('pool' if pool else None)
 
         # ---- no-build window kernel (csrc/conv_window.cu): the image layer with its pool, and <= 8-channel PNHWC inputs
         win_kind = None
@@ -394,7 +503,8 @@ class CompiledDarknet(object):
                                                      wpack.data_ptr(), Npad, Kc, _lib.stream_ptr()),
                        "mc_pack_conv_weights")
         op = dict(kind='conv', src=src, wpack=wpack, scale=scale_p, shift=shift_p, N=n_phys, Npad=Npad, ksize=k,
-                  leaky=int(leaky), Cin=c_phys_in, name='conv@%d' % ind, H=H, W=W, flops_per_image=op_flops, block_k=kblk)
+                  leaky=int(leaky), Cin=c_phys_in, name='conv@%d' % ind, H=H, W=W, flops_per_image=op_flops, block_k=kblk,
+                  ind=ind, plain=bool(plain_dst))
         fused = None
         if is_head:
             bid = self._new_buf(H, W, 0, fp32_nchw_channels=n_phys)
@@ -452,8 +562,8 @@ class CompiledDarknet(object):
                                       (self.in_hw[1], self.in_hw[0], W, H))
         tensors = []
         for b in self.bufs:
-            if b.fp32_nchw_channels:
-                tensors.append(None)  # allocated per call (returned to the caller)
+            if b.fp32_nchw_channels or b.dead:
+                tensors.append(None)  # allocated per call (returned to the caller) / fused away
             else:
                 # zero-initialised: pad rows/columns that no kernel writes, and the channels between a layer's physical
                 # channel count and the 8-aligned pitch, must be finite zeros (0-weight x NaN garbage would poison
@@ -595,6 +705,13 @@ class CompiledDarknet(object):
                                                       op['shift'].data_ptr(), bufs[op['dst_buf']].data_ptr(), B, op['H'],
                                                       op['W'], op['Cin'], op['N'], op['ld'], op['leaky'], op['pool'],
                                                       stream), op['name'])
+                elif kind == 'thin':
+                    s = op['src']
+                    _lib.check(lib.mc_conv_thin_fwd(bufs[s.buf_id].data_ptr(), op['hw'], op['hsc'], op['hsh'],
+                                                    op.get('hw2'), op.get('hsc2'), op.get('hsh2'),
+                                                    bufs[op['dst_buf']].data_ptr(), B, op['H'], op['W'], op['Cin'],
+                                                    self.bufs[s.buf_id].ld, op['N'], op['ld'], op['ksize'], op['leaky'],
+                                                    op['pool'], op['N2'], op['leaky2'], stream), op['name'])
                 elif kind == 'direct':
                     s = op['src']
                     if s is None:

@@ -187,10 +187,14 @@ def test_filter_pruned_network_physically_shrunk(cfg_path):
     model.b200_shrink = True
     y_s, y_ref = _check_blocks(model, x1, 'f40-shrunk')
     plan = compile_darknet(model)
-    convs = [op for op in plan.ops if op['kind'] in ('conv', 'direct', 'im2col', 'window')]
+    convs = [op for op in plan.ops if op['kind'] in ('conv', 'direct', 'im2col', 'window', 'thin')]
+    widths = []  # physical output channels per conv layer (a fused thin pair is two layers in one launch)
+    for op in convs:
+        widths += [op['fused_n1'], op['N2']] if op.get('N2') else [op['N']]
     kept = [int(k.numel()) for k in keep]
+    assert len(widths) == len(kept)
     # every non-head layer lost filters physically (+1 for the ones channel where constants are non-zero)
-    assert all(op['N'] <= n + 1 for op, n in zip(convs[:-1], kept[:-1]))
+    assert all(n_phys <= n + 1 for n_phys, n in zip(widths[:-1], kept[:-1]))
     assert convs[-1]['N'] == 125  # the head keeps all outputs: pruned ones are bias-only (SURVEY.md §7 hard part 4)
     assert plan.flops_per_image < 0.6 * 29.36e9
     # un-shrunk (masked, dense shapes) gives the same logits
@@ -426,3 +430,88 @@ def test_window_kernel_image(B, H, W, N):
     ref2 = _window_ref(xf, w, scale, shift, 1, True)
     err2 = (y2 - ref2).abs()
     assert (err2 <= 5e-3 * ref2.abs() + 2e-3 * ref2.abs().max()).all(), "max rel %.3g" % _rel(y2, ref2)
+
+
+@pytest.mark.parametrize("k,C,N,pool,N2,H,W", [
+    (3, 4, 1, 1, 0, 20, 24),    # conv2 of the 40 % filter-pruned net: 4 -> 1 + pool
+    (3, 1, 17, 0, 0, 12, 20),   # conv3: 1 -> 17
+    (1, 17, 4, 0, 0, 12, 20),   # conv4: 17 -> 4, 1x1
+    (3, 4, 11, 1, 0, 16, 16),   # conv5: 4 -> 11 + pool
+    (3, 1, 17, 0, 4, 12, 20),   # conv3 with conv4 applied in the same thread
+    (3, 8, 8, 0, 8, 10, 14),    # widest fused instance
+    (3, 2, 3, 0, 0, 9, 7),      # odd image, no pool
+    (1, 32, 8, 0, 0, 6, 10),    # widest 1x1
+    (3, 5, 4, 1, 0, 8, 12),     # 5 channels -> 8 read per pixel, pooled
+    (3, 2, 24, 0, 0, 8, 8),     # 24 outputs -> three 16-byte pieces per pixel
+])
+def test_thin_conv_kernel(k, C, N, pool, N2, H, W):
+    """csrc/conv_thin.cu (CUDA-core kernel for the degenerate layers of a shrunk net) vs fp32 PyTorch on bf16-rounded
+    operands; borders come from the PNHWC pad line/column, which the kernel must leave zero in its output."""
+    import ctypes
+    from modelcompression_b200 import _lib
+    from modelcompression_b200.engine import _pitch, _thin_host_weights, _c_floats
+    lib = _lib.load()
+    torch.manual_seed(100 * C + N)
+    B = 3
+    ct, nt, n2t = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    assert lib.mc_conv_thin_geometry(k, C, N, pool, N2, ctypes.byref(ct), ctypes.byref(nt), ctypes.byref(n2t)) == 1
+    ct, nt, n2t = ct.value, nt.value, n2t.value
+    x = torch.randn(B, C, H, W, device=DEV)
+    w = torch.randn(N, C, k, k, device=DEV) / (C * k * k) ** 0.5
+    sc, sh = torch.rand(N, device=DEV) + 0.5, torch.randn(N, device=DEV) * 0.2
+    ld_in = max(_pitch(C), ct)
+    xin = torch.zeros(B * (H + 1) * (W + 1), ld_in, dtype=torch.bfloat16, device=DEV)
+    s = _lib.stream_ptr()
+    _lib.check(lib.mc_pack_pnhwc(x.data_ptr(), xin.data_ptr(), B, H, W, C, ld_in, s), "pack")
+    hw, hsc, hsh = _thin_host_weights(w, sc, sh, ct, nt)
+    ref = F.conv2d(_bf16(x), _bf16(w), None, 1, (k - 1) // 2) * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)
+    ref = F.leaky_relu(ref, 0.1)
+    if pool:
+        ref = F.max_pool2d(ref, 2, 2)
+    Ho, Wo = ref.shape[2:]
+    hw2 = hsc2 = hsh2 = None
+    n_out = N
+    if N2:
+        w2 = torch.randn(N2, N, device=DEV) / N ** 0.5
+        sc2, sh2 = torch.rand(N2, device=DEV) + 0.5, torch.randn(N2, device=DEV) * 0.2
+        w2p = torch.zeros(nt, n2t)
+        w2p[:N, :N2] = _bf16(w2).t().cpu()
+        s2p, h2p = torch.zeros(n2t), torch.zeros(n2t)
+        s2p[:N2], h2p[:N2] = sc2.cpu(), sh2.cpu()
+        hw2, hsc2, hsh2 = _c_floats(w2p), _c_floats(s2p), _c_floats(h2p)
+        ref = F.conv2d(_bf16(ref), _bf16(w2).view(N2, N, 1, 1)) * sc2.view(1, -1, 1, 1) + sh2.view(1, -1, 1, 1)
+        ref = F.leaky_relu(ref, 0.1)
+        n_out = N2
+    ld_out = _pitch(n_out)
+    yb = torch.zeros(B * (Ho + 1) * (Wo + 1), ld_out, dtype=torch.bfloat16, device=DEV)
+    _lib.check(lib.mc_conv_thin_fwd(xin.data_ptr(), hw, hsc, hsh, hw2, hsc2, hsh2, yb.data_ptr(), B, H, W, C, ld_in, N,
+                                    ld_out, k, 1, pool, N2, 1, s), "mc_conv_thin_fwd")
+    y = torch.empty(B, n_out, Ho, Wo, device=DEV)
+    _lib.check(lib.mc_unpack_pnhwc(yb.data_ptr(), y.data_ptr(), B, Ho, Wo, n_out, ld_out, 0, s), "unpack")
+    torch.cuda.synchronize()
+    err = (y - ref).abs()
+    assert (err <= 5e-3 * ref.abs() + 2e-3 * ref.abs().max()).all(), "max rel %.3g" % _rel(y, ref)
+    # pad column, pad line and the channels beyond n_out stay zero
+    grid = yb.view(B, Ho + 1, Wo + 1, ld_out)
+    assert grid[:, Ho].abs().max().item() == 0 and grid[:, :, Wo].abs().max().item() == 0
+    if ld_out > n_out:
+        assert grid[..., n_out:].abs().max().item() == 0
+
+
+def test_thin_layers_and_fusion_in_the_shrunk_network(cfg_path):
+    """The compiled plan of the 40 % filter-pruned seed-0 network (the bench workload's shapes: conv2 4 -> 1, conv3 1 -> 17,
+    conv4 17 -> 4, conv5 4 -> 11; rand-BN adds the ones channel) takes the thin CUDA-core kernel for its degenerate layers
+    and fuses the 3x3 -> 1x1 pair; every materialised block matches the fp32 oracle with and without them."""
+    model = make_darknet(cfg_path, seed=0, randbn=True, device=DEV)
+    model.set_masks(mc.quick_filter_prune(model, 40.))
+    torch.manual_seed(3)
+    x = torch.rand(2, 3, 416, 416, device=DEV)
+    for mode in (0, 1, 2):
+        model.b200_thin = mode
+        plan = compile_darknet(model, force=True)
+        kinds = [op['kind'] for op in plan.ops]
+        assert ('thin' in kinds) == (mode > 0), kinds
+        assert any(op.get('N2') for op in plan.ops) == (mode == 2), [op['name'] for op in plan.ops]
+        _check_blocks(model, x, 'f40-thin%d' % mode)
+    model.b200_thin = 2
+    compile_darknet(model, force=True)

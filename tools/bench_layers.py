@@ -16,6 +16,8 @@ B = int(os.environ.get("BENCH_B", "64"))
 dev = torch.device('cuda:0')
 torch.manual_seed(0)
 model = mc.Darknet(mc.write_yolov2_voc_cfg()).to(dev).eval()
+if os.environ.get("BENCH_THIN"):
+    model.b200_thin = int(os.environ["BENCH_THIN"])
 if not dense:
     model.set_masks(mc.quick_filter_prune(model, 40.))
     model.b200_shrink = True
