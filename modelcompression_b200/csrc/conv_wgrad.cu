@@ -220,6 +220,59 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   }
 }
 
+// Same sum for SMALL filter banks (the stem: 2 K .. 32 K (o, c) pairs summed over up to 99 splits).  One thread per
+// (o, c) left 4-32 blocks walking 9 x nsplit dependent loads each (93 us for conv2's 18 K outputs); here a warp owns 32
+// consecutive c of one (tap, o), G warps share the splits of that item (split s goes to group s % G, partial sums are
+// combined in group order through shared memory: the result does not depend on scheduling) and a block holds 8 / G
+// items, so the grid is ntaps * O * ceil(C / 32) / (8 / G) blocks.
+template <int G>
+__global__ void __launch_bounds__(256) wgrad_reduce_small_kernel(const float* __restrict__ ws, int nsplit, int ntaps,
+                                                                 int Opad, int Cpad, int O, int C,
+                                                                 const float* __restrict__ mask, float* __restrict__ dw,
+                                                                 int accumulate) {
+  constexpr int R = 8 / G;
+  __shared__ float part[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = warp % G, r = warp / G;
+  const int cchunks = (C + 31) / 32;
+  const long long items = (long long)ntaps * O * cchunks;
+  const long long item = (long long)blockIdx.x * R + r;
+  // item -> (o, chunk, tap) with the tap fastest: the 9 taps of a weight are 36 contiguous bytes of dW
+  const int t = (int)(item % ntaps);
+  const long long oc = item / ntaps;
+  const int cc = (int)(oc % cchunks), o = (int)(oc / cchunks);
+  const int c = cc * 32 + lane;
+  const bool valid = item < items && c < C;
+  float acc = 0.f;
+  if (valid) {
+    const float* src = ws + ((size_t)t * Opad + o) * Cpad + c;
+    const size_t sstride = (size_t)ntaps * Opad * Cpad;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int s = g;
+    for (; s + 3 * G < nsplit; s += 4 * G) {
+      a0 += src[(size_t)s * sstride];
+      a1 += src[(size_t)(s + G) * sstride];
+      a2 += src[(size_t)(s + 2 * G) * sstride];
+      a3 += src[(size_t)(s + 3 * G) * sstride];
+    }
+    for (; s < nsplit; s += G) a0 += src[(size_t)s * sstride];
+    acc = (a0 + a1) + (a2 + a3);
+  }
+  if (G > 1) {
+    part[warp][lane] = acc;
+    __syncthreads();
+    if (g != 0) return;
+    acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < G; ++k) acc += part[r * G + k][lane];
+  }
+  if (valid) {
+    const size_t di = ((size_t)o * C + c) * ntaps + t;
+    if (mask) acc *= mask[di];
+    dw[di] = accumulate ? dw[di] + acc : acc;
+  }
+}
+
 struct WgradPlan {
   int block_n, nb64, n_tiles, m_tiles, ntaps, num_kb, nsplit, stages, tmem_cols, Opad, Cpad, share3;
   size_t smem_bytes, ws_bytes;
@@ -325,6 +378,22 @@ extern "C" int mc_conv_wgrad(const void* d_a, int lda, int C, const void* d_dz, 
   conv_wgrad_tcgen05_kernel<<<grid, NUM_THREADS, pl.smem_bytes, stream>>>(tm_dz, tm_a, p);
   MC_LAUNCH_CHECK("conv_wgrad_tcgen05_kernel");
   long long tot = (long long)O * C;
+  if (tot < 65536 && pl.nsplit > 1) {
+    // few outputs, many splits: parallel over taps and split groups
+    const long long items = (long long)pl.ntaps * O * ((C + 31) / 32);
+    if (pl.nsplit >= 32) {
+      wgrad_reduce_small_kernel<8><<<(unsigned)items, 256, 0, stream>>>(p.ws, pl.nsplit, pl.ntaps, pl.Opad, pl.Cpad, O, C,
+                                                                        d_mask, d_dw, accumulate);
+    } else if (pl.nsplit >= 8) {
+      wgrad_reduce_small_kernel<4><<<(unsigned)((items + 1) / 2), 256, 0, stream>>>(p.ws, pl.nsplit, pl.ntaps, pl.Opad,
+                                                                                    pl.Cpad, O, C, d_mask, d_dw, accumulate);
+    } else {
+      wgrad_reduce_small_kernel<1><<<(unsigned)((items + 7) / 8), 256, 0, stream>>>(p.ws, pl.nsplit, pl.ntaps, pl.Opad,
+                                                                                    pl.Cpad, O, C, d_mask, d_dw, accumulate);
+    }
+    MC_LAUNCH_CHECK("wgrad_reduce_small_kernel");
+    return 0;
+  }
   int rgrid = (int)((tot + 255) / 256);
   if (rgrid > mc_num_sms() * 8) rgrid = mc_num_sms() * 8;
   wgrad_reduce_kernel<<<rgrid, 256, 0, stream>>>(p.ws, pl.nsplit, pl.ntaps, pl.Opad, pl.Cpad, O, C, d_mask, d_dw,
