@@ -41,7 +41,10 @@ struct WgradParams {
   int stages, tmem_cols;
   int Wp, ksize;
   int share3;       // 3x3: one CTA = one filter row (dy), three accumulators, the activation box shared by its 3 taps
+  int merge3;       // share3 with <= 64 input channels: the three dx taps are ONE instruction of N = 192 (see the issuer)
+  uint32_t idesc3;  // instruction descriptor of that N = 192 instruction
   int Opad, Cpad;   // workspace tile pitch: m_tiles*128, n_tiles*block_n
+  int O;            // real output channels
   uint32_t idesc;
   float* ws;        // [nsplit][ntaps][Opad][Cpad]
 };
@@ -58,6 +61,8 @@ __device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr) 
   return d;
 }
 
+__device__ __forceinline__ int m_tile_of(int block, const WgradParams& p) { return (block / p.n_tiles) % p.m_tiles; }
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_constant__ CUtensorMap tmap_a,
                           const WgradParams p) {
@@ -69,7 +74,12 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __g
   }
   const uint32_t b_blk = p.share3 ? (uint32_t)BBOX_STRIDE : (uint32_t)BOX_BYTES;  // pitch of a 64-column block of B
   const uint32_t stage_bytes = 2u * BOX_BYTES + (uint32_t)p.nb64 * b_blk;
-  const uint32_t tx_bytes = 2u * BOX_BYTES + (uint32_t)p.nb64 * (p.share3 ? (uint32_t)BBOX_BYTES : (uint32_t)BOX_BYTES);
+  // <= 64 output channels left in this M tile: the second 64-column dZ box would be pure zero fill, and TMA time follows
+  // the box area.  It is not loaded; accumulator rows 64..127 then hold products of stale shared memory, which land in
+  // workspace rows >= O that the reduction never reads.
+  const bool a_half = (m_tile_of(blockIdx.x, p) * BLOCK_M + 64 >= p.O);
+  const uint32_t tx_bytes = (a_half ? 1u : 2u) * BOX_BYTES +
+                            (uint32_t)p.nb64 * (p.share3 ? (uint32_t)BBOX_BYTES : (uint32_t)BOX_BYTES);
   uint8_t* tiles = smem;
   uint8_t* aux = tiles + (size_t)p.stages * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
@@ -125,7 +135,7 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __g
         uint8_t* b_dst = a_dst + 2 * BOX_BYTES;
         ptx::mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
         ptx::tma_load_2d(a_dst, &tmap_dz, &full_bar[s], m0, kb * BLOCK_K);
-        ptx::tma_load_2d(a_dst + BOX_BYTES, &tmap_dz, &full_bar[s], m0 + 64, kb * BLOCK_K);
+        if (!a_half) ptx::tma_load_2d(a_dst + BOX_BYTES, &tmap_dz, &full_bar[s], m0 + 64, kb * BLOCK_K);
         for (int j = 0; j < p.nb64; ++j)
           ptx::tma_load_2d(b_dst + (size_t)j * b_blk, &tmap_a, &full_bar[s], n0 + j * 64, kb * BLOCK_K + row_off);
         if (++s == p.stages) { s = 0; phase ^= 1u; }
@@ -141,7 +151,18 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __g
         const uint32_t a_addr = ptx::smem_u32(tiles + (size_t)s * stage_bytes);
         const uint64_t adesc = make_sw128_mnmajor_desc(a_addr);
         if (ptx::elect_one()) {
-        if (p.share3) {
+        if (p.merge3) {
+          // <= 64 input channels: the B tile of a tap is ONE 64-column block, and tap dx is the same block one pixel row
+          // (128 B) further down.  An MN-major descriptor reaches the next 64-column block through its leading byte
+          // offset, so LBO = 128 B makes the three taps the three column blocks of a single N = 192 operand: 4 instead
+          // of 12 instructions per 64 pixel rows (the narrow layers were bound by the COUNT of narrow MMAs).
+          uint64_t bdesc = make_sw128_mnmajor_desc(a_addr + 2 * BOX_BYTES);
+          bdesc = (bdesc & ~((uint64_t)0x3FFF << 16)) | ((uint64_t)(128 >> 4) << 16);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k)
+            ptx::umma_bf16_ss(tmem_base, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), p.idesc3,
+                              (kb > kb0 || k > 0) ? 1u : 0u);
+        } else if (p.share3) {
           // tap dx = rows dx .. dx+63 of the 72-row box: start dx*128 B into it (the swizzle is applied to the absolute
           // shared-memory address, so an un-aligned start needs no base offset — see conv_tcgen05.cu); 64-column blocks
           // are BBOX_STRIDE apart (LBO)
@@ -184,7 +205,7 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __g
       float* dst = p.ws + ((((size_t)split * p.ntaps + tap_out) * p.Opad + o) * p.Cpad + n0);
       for (int c0 = 0; c0 < p.block_n; c0 += 16) {
         uint32_t r[16];
-        ptx::tmem_ld_32x32b_x16(taddr_row + (uint32_t)(acc * p.block_n + c0), r);
+        ptx::tmem_ld_32x32b_x16(taddr_row + (uint32_t)(acc * (p.merge3 ? 64 : p.block_n) + c0), r);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -274,7 +295,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_small_kernel(const float* __
 }
 
 struct WgradPlan {
-  int block_n, nb64, n_tiles, m_tiles, ntaps, num_kb, nsplit, stages, tmem_cols, Opad, Cpad, share3;
+  int block_n, nb64, n_tiles, m_tiles, ntaps, num_kb, nsplit, stages, tmem_cols, Opad, Cpad, share3, merge3;
   size_t smem_bytes, ws_bytes;
 };
 
@@ -298,19 +319,39 @@ int plan_wgrad(WgradPlan* pl, int B, int H, int W, int C, int O, int ksize) {
   pl->Opad = pl->m_tiles * BLOCK_M;
   pl->Cpad = pl->n_tiles * pl->block_n;
   const int tiles = pl->m_tiles * pl->n_tiles * (pl->share3 ? 3 : pl->ntaps);
-  // enough CTAs for ~2 per SM, but at least 8 pipeline steps each
-  int nsplit = (2 * mc_num_sms() + tiles - 1) / tiles;
+  // Split count.  The ring takes ~200 KB of shared memory, so ONE CTA is resident per SM and the grid runs in waves of
+  // num_sms CTAs: "about two CTAs per SM" used to give grids like 297 or 300 (two waves plus a third one of 1-4 CTAs,
+  // i.e. 1.5x the time).  Pick the split that minimises   waves * (k-blocks per CTA + fixed) + reduction traffic
+  // (a k-block costs its TMA bytes at ~46 B/ns per SM — measured 0.30 us for the 17 KB stages of a 32 -> 64 layer and
+  // 0.75 us for the 34 KB stages of 1024 -> 1024 —, ~3 us of set-up / partial-tile store per CTA, partial tiles written
+  // and re-read at ~3 TB/s); at least 8 pipeline steps per CTA.
+  const int sms = mc_num_sms();
   const int max_split = pl->num_kb / 8 > 0 ? pl->num_kb / 8 : 1;
-  if (nsplit > max_split) nsplit = max_split;
-  if (nsplit < 1) nsplit = 1;
+  const double tile_bytes = 128.0 * pl->block_n * (pl->share3 ? 3 : 1) * 4.0;
+  const int nb64_ = (pl->block_n + 63) / 64;
+  const double kb_us = ((O <= 64 ? 1 : 2) * (double)BOX_BYTES + nb64_ * (double)(pl->share3 ? BBOX_BYTES : BOX_BYTES)) *
+                       2.18e-5;
+  int nsplit = 1;
+  double best = 1e30;
+  for (int sp = 1; sp <= max_split && (long long)sp * tiles <= 6ll * sms; ++sp) {
+    const int waves = (sp * tiles + sms - 1) / sms;
+    const double t = waves * ((double)pl->num_kb / sp * kb_us + 3.0) + (sp > 1 ? 2.0 * sp * tiles * tile_bytes / 3.0e6 : 0.0);
+    if (t < best) { best = t; nsplit = sp; }
+  }
   pl->nsplit = nsplit;
   const int stage_bytes = 2 * BOX_BYTES + pl->nb64 * (pl->share3 ? BBOX_STRIDE : BOX_BYTES);
   int stages = (200 * 1024) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   pl->stages = stages;
   pl->smem_bytes = (size_t)stages * stage_bytes + 256 + 1024;
+  static int merge_env = -1;
+  if (merge_env < 0) {
+    const char* e = mc_tune_env("MCB200_WGRAD_MERGE");
+    merge_env = (e && e[0] == '0') ? 0 : 1;
+  }
+  pl->merge3 = (pl->share3 && pl->nb64 == 1 && pl->n_tiles == 1 && merge_env) ? 1 : 0;
   int tc = 32;
-  while (tc < (pl->share3 ? 3 : 1) * pl->block_n) tc <<= 1;
+  while (tc < (pl->merge3 ? 192 : (pl->share3 ? 3 : 1) * pl->block_n)) tc <<= 1;
   pl->tmem_cols = tc;
   pl->ws_bytes = (size_t)nsplit * pl->ntaps * pl->Opad * pl->Cpad * sizeof(float);
   return 0;
@@ -362,11 +403,15 @@ extern "C" int mc_conv_wgrad(const void* d_a, int lda, int C, const void* d_dz, 
   p.Wp = W + 1;
   p.ksize = ksize;
   p.share3 = pl.share3;
+  p.merge3 = pl.merge3;
   p.Opad = pl.Opad;
   p.Cpad = pl.Cpad;
+  p.O = O;
   // c=f32, a=b=bf16, both operands MN-major (bits 15/16), N>>3 at [17,23), M>>4 at [24,29)
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(pl.block_n >> 3) << 17) |
             ((uint32_t)(BLOCK_M >> 4) << 24);
+  p.idesc3 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(192 >> 3) << 17) |
+             ((uint32_t)(BLOCK_M >> 4) << 24);
   p.ws = reinterpret_cast<float*>(d_ws);
 
   static bool attr_set = false;

@@ -47,7 +47,8 @@ def _rel(a, b):
 
 @pytest.mark.parametrize("B,C,O,H,W,k", [(2, 32, 64, 20, 20, 3), (3, 128, 256, 13, 13, 3), (2, 512, 64, 26, 26, 1),
                                          (2, 1280, 1024, 13, 13, 3), (4, 24, 40, 9, 15, 3), (1, 1024, 125, 13, 13, 1),
-                                         (3, 40, 160, 12, 18, 3)])  # (<= 48 channels: nine-tap work units, 2 M tiles)
+                                         (3, 40, 160, 12, 18, 3),  # (<= 64 channels: the three dx taps in one N = 192 MMA)
+                                         (2, 64, 128, 16, 16, 3), (2, 8, 16, 30, 22, 3)])
 def test_wgrad_single_layer(B, C, O, H, W, k):
     torch.manual_seed(C + O)
     lib = _lib.load()
