@@ -914,6 +914,60 @@ extern "C" int mc_bn_pool_backward(const void* d_z, int ld_z, const void* d_dpoo
 // So dgrad reuses the forward tcgen05 kernel (mc_conv_fwd) on this packing: bf16 [Cpad, taps*Ko] K-major, row c,
 // column tap'*Ko + o  (Ko = round_up(O, 64)), masked like the forward weights (layers.py:59).
 namespace {
+// Large filter banks: a block transposes a tile of 32 output x 32 input channels through shared memory.  Reading, a warp
+// walks the 32*taps contiguous floats that one output channel holds for the tile's input channels (coalesced 128-byte
+// requests; the direct kernel below reads 36-byte runs 36 KB apart); writing, two input channels x 16 output-channel
+// pairs per warp store 64-byte runs of the K-major dgrad matrix.  All loads of a thread (4 output channels x taps) are
+// issued before the one barrier.  (A first tiled version that looped 32 dependent load steps around two barriers was
+// slower than the direct kernel: DESIGN.md §9.)
+template <int TAPS>
+__global__ void __launch_bounds__(256) pack_dgrad_weights_tiled_kernel(const float* __restrict__ w,
+                                                                       const float* __restrict__ mask, int O, int C,
+                                                                       __nv_bfloat16* __restrict__ out, int Ko) {
+  __shared__ float tile[32][32 * TAPS + 1];  // [o][c*TAPS + t]
+  const int o0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cw = min(32, C - c0);  // input channels of this tile
+  const int run = cw * TAPS;       // contiguous floats per output channel
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int ol = warp * 4 + q;
+    const int o = o0 + ol;
+    if (o < O) {
+      const size_t src = ((size_t)o * C + c0) * TAPS;
+#pragma unroll
+      for (int j = 0; j < TAPS; ++j) {
+        const int e = j * 32 + lane;
+        if (e < run) {
+          float v = w[src + e];
+          if (mask) v *= mask[src + e];
+          tile[ol][e] = v;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // warp: 2 input channels per pass (half-warps), lane & 15 = pair of output channels
+  const int half = lane >> 4, op = (lane & 15) * 2;
+  for (int cl = warp * 2 + half; cl < cw; cl += 16) {
+    const int c = c0 + cl;
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) {
+      const int o = o0 + op;
+      if (o < O) {
+        const float a = tile[op][cl * TAPS + t];
+        const float b = (o + 1 < O) ? tile[op + 1][cl * TAPS + t] : 0.f;
+        __nv_bfloat16* dst = out + ((size_t)c * TAPS + (TAPS - 1 - t)) * Ko + o;
+        if (o + 1 < O) {
+          *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(a, b);
+        } else {
+          *dst = __float2bfloat16_rn(a);
+        }
+      }
+    }
+  }
+}
+
 // one thread = one (input channel c, output channel o), o fastest: the taps are read as one contiguous run, each write
 // is coalesced over o.  Padding is zeroed by a memset before the launch.
 __global__ void pack_dgrad_weights_kernel(const float* __restrict__ w, const float* __restrict__ mask, int O, int C,
@@ -1060,6 +1114,15 @@ extern "C" int mc_pack_conv_weights_dgrad(const float* d_w, const float* d_mask,
   const int taps = ksize * ksize;
   MC_CHECK_ARG((long long)O * C < (1ll << 32), "mc_pack_conv_weights_dgrad: tensor too large");
   MC_CUDA(cudaMemsetAsync(d_wpack, 0, (size_t)Cpad * taps * Ko * sizeof(__nv_bfloat16), stream));
+  if ((long long)O * C >= 65536 && (Ko % 2) == 0) {
+    const dim3 grid((O + 31) / 32, (C + 31) / 32);
+    if (taps == 9)
+      pack_dgrad_weights_tiled_kernel<9><<<grid, 256, 0, stream>>>(d_w, d_mask, O, C, (__nv_bfloat16*)d_wpack, Ko);
+    else
+      pack_dgrad_weights_tiled_kernel<1><<<grid, 256, 0, stream>>>(d_w, d_mask, O, C, (__nv_bfloat16*)d_wpack, Ko);
+    MC_LAUNCH_CHECK("pack_dgrad_weights_tiled_kernel");
+    return 0;
+  }
   pack_dgrad_weights_kernel<<<grid_for((long long)O * C, 256), 256, 0, stream>>>(d_w, d_mask, O, C, taps,
                                                                                 (__nv_bfloat16*)d_wpack, Cpad, Ko);
   MC_LAUNCH_CHECK("pack_dgrad_weights_kernel");

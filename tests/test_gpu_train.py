@@ -97,7 +97,8 @@ def test_wgrad_first_layer(B, C, O, H, W, tensor_core):
 
 
 @pytest.mark.parametrize("B,C,O,H,W,k", [(2, 32, 64, 20, 20, 3), (2, 512, 64, 26, 26, 1), (2, 1280, 1024, 13, 13, 3),
-                                         (3, 24, 40, 9, 15, 3)])
+                                         (3, 24, 40, 9, 15, 3),
+                                         (2, 1024, 500, 13, 13, 1), (2, 300, 250, 13, 13, 3)])  # (tiled weight packing, ragged)
 def test_dgrad_single_layer(B, C, O, H, W, k):
     torch.manual_seed(C * 3 + O)
     lib = _lib.load()
