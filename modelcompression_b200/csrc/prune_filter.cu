@@ -897,6 +897,8 @@ filter_prune_fused_kernel(const LayerTable lt, float* __restrict__ raw, float* _
   const int tid = threadIdx.x;
   const int n = lt.voff[lt.nlayers];
   if (tid == 0 && blockIdx.x == 0) fused_stamp(st, 0, false);
+  if (tid == 0) s_last = 0u;  // (a block that never gets an item is not the finisher)
+  __syncthreads();
   // ---- phase 1: raw per-filter sums
   for (;;) {
     if (tid == 0) s_item = (int)atomicAdd(&st->next_item, 1u);
@@ -945,7 +947,38 @@ filter_prune_fused_kernel(const LayerTable lt, float* __restrict__ raw, float* _
   }
   if (tid == 0) fused_stamp(st, 1, true);
   if (!fill) return;
-  // ---- phase 3: masks, once the threshold is published
+  // ---- phase 3: masks.  A block owns the filters blockIdx.x, blockIdx.x + gridDim.x, ... in both passes below.
+  // While the finisher runs the serial part (normalise + percentile: ~38 us during which HBM would sit idle), every other
+  // block already fills ITS filters with the PROVISIONAL value — the majority outcome, known from the rank alone: 1 when
+  // fewer than half of the filters will be pruned, else 0 — and once the threshold is published only the filters whose
+  // flag differs are rewritten (same thread, same addresses: ordered).  The finisher itself writes its filters once.
+  const float prov = (2 * k < (long long)n) ? 1.f : 0.f;
+  const bool i_finished = (s_last != 0u);  // block-uniform (s_last is only rewritten inside the queue loop)
+  auto fill_filters = [&](int pass) {
+    const double t = pass ? __ldcg(thr) : 0.0;
+    int l = 0;
+    for (int f = blockIdx.x; f < n; f += gridDim.x) {
+      while (l + 1 < lt.nlayers && f >= lt.voff[l + 1]) ++l;
+      float val = prov;
+      if (pass) {
+        val = ((double)__ldcg(values + f) < t) ? 0.f : 1.f;
+        if (!i_finished && val == prov) continue;  // already written by the provisional pass
+      }
+      const int o = f - lt.voff[l];
+      const int per = lt.C[l] * lt.taps[l];
+      float* m = lt.mask[l] + (long long)o * per;
+      int head = (int)(((16 - (reinterpret_cast<uintptr_t>(m) & 15)) & 15) >> 2);  // scalar head up to 16-byte alignment
+      if (head > per) head = per;
+      if (tid < head) m[tid] = val;
+      const int body4 = (per - head) >> 2;
+      float4* m4 = reinterpret_cast<float4*>(m + head);
+      const float4 v4 = make_float4(val, val, val, val);
+      for (int i = tid; i < body4; i += FU_THREADS) st_stream_f4(m4 + i, v4);
+      const int tail0 = head + body4 * 4;
+      if (tid < per - tail0) m[tail0 + tid] = val;
+    }
+  };
+  if (!i_finished) fill_filters(0);
   if (tid == 0) {
     unsigned int spins = 0;
     while (ld_acquire_u32(&st->flag) == 0u) {
@@ -954,24 +987,7 @@ filter_prune_fused_kernel(const LayerTable lt, float* __restrict__ raw, float* _
     }
   }
   __syncthreads();
-  const double t = __ldcg(thr);
-  int l = 0;
-  for (int f = blockIdx.x; f < n; f += gridDim.x) {
-    while (l + 1 < lt.nlayers && f >= lt.voff[l + 1]) ++l;
-    const int o = f - lt.voff[l];
-    const int per = lt.C[l] * lt.taps[l];
-    const float val = ((double)__ldcg(values + f) < t) ? 0.f : 1.f;
-    float* m = lt.mask[l] + (long long)o * per;
-    int head = (int)(((16 - (reinterpret_cast<uintptr_t>(m) & 15)) & 15) >> 2);  // scalar head up to 16-byte alignment
-    if (head > per) head = per;
-    if (tid < head) m[tid] = val;
-    const int body4 = (per - head) >> 2;
-    float4* m4 = reinterpret_cast<float4*>(m + head);
-    const float4 v4 = make_float4(val, val, val, val);
-    for (int i = tid; i < body4; i += FU_THREADS) st_stream_f4(m4 + i, v4);
-    const int tail0 = head + body4 * 4;
-    if (tid < per - tail0) m[tail0 + tid] = val;
-  }
+  fill_filters(1);
   if (tid == 0) fused_stamp(st, 4, true);
 }
 
