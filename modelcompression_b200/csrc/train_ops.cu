@@ -1100,6 +1100,18 @@ __global__ void __launch_bounds__(256) im2col_first_kernel(const float* __restri
   }
 }
 
+// dW[o][j] = mask * (t[o][j] + t[32 + o][32 + j]): the two diagonal blocks of the doubled-row product (see
+// mc_conv_wgrad_first)
+__global__ void wgrad_fold2_kernel(const float* __restrict__ t, const float* __restrict__ mask, float* __restrict__ dw,
+                                   int O, int J) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= O * J) return;
+  const int o = i / J, j = i - o * J;
+  float v = t[o * 64 + j] + t[(32 + o) * 64 + 32 + j];
+  if (mask) v *= mask[i];
+  dw[i] = v;
+}
+
 __global__ void mul_inplace_kernel(float* __restrict__ a, const float* __restrict__ m, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     a[i] *= m[i];
@@ -1134,7 +1146,12 @@ extern "C" size_t mc_workspace_bytes_conv_wgrad_first(int B, int H, int W, int C
   if (B <= 0 || H <= 0 || W <= 0 || C < 1 || O < 1 || C * 9 > 32) return 0;
   const size_t rows = (size_t)B * (H + 1) * (W + 1);
   const size_t im2col = (rows * 32 * sizeof(__nv_bfloat16) + 255) & ~(size_t)255;
-  return im2col + mc_workspace_bytes_conv_wgrad(B, H, W, C * 9, O, 1);
+  size_t w1 = mc_workspace_bytes_conv_wgrad(B, H, W, C * 9, O, 1);
+  if ((B % 2) == 0 && O == 32) {  // doubled-row view (see mc_conv_wgrad_first) + its 64x64 product
+    const size_t w2 = mc_workspace_bytes_conv_wgrad(B / 2, H, W, 64, 64, 1) + 64 * 64 * sizeof(float) + 256;
+    if (w2 > w1) w1 = w2;
+  }
+  return im2col + w1;
 }
 
 extern "C" int mc_conv_wgrad_first(const float* d_x, const void* d_dz, int ld_dz, int B, int H, int W, int C, int O,
@@ -1154,6 +1171,24 @@ extern "C" int mc_conv_wgrad_first(const float* d_x, const void* d_dz, int ld_dz
     if (g > (long long)mc_num_sms() * 32) g = (long long)mc_num_sms() * 32;
     im2col_first_kernel<<<(int)g, 256, 0, stream>>>(d_x, cols, B, H, W, C);
     MC_LAUNCH_CHECK("im2col_first_kernel");
+    if ((B % 2) == 0 && O == 32 && ld_dz == 32) {
+      // Both operands are 32 columns wide, i.e. half of the 64-column (128-byte) rows the MN-major TMA boxes move: every
+      // box would be half zero fill, and the kernel is bound by TMA bytes per k-block.  View both matrices as
+      // [rows/2, 64] instead — row r holds pixel rows 2r and 2r+1 side by side.  The product of the doubled operands is
+      // 64x64 with  D[p*32+o][q*32+j] = sum_r dZ[2r+p][o] * cols[2r+q][j];  the wanted gradient is the sum of its two
+      // diagonal blocks (p == q), the off-diagonal blocks are discarded.  Half the k-blocks, no zero fill
+      // (B even <=> the row count is even; the batch split B/2 only tells the callee the row count).
+      uint8_t* w2 = reinterpret_cast<uint8_t*>(d_ws) + im2col;
+      float* prod = reinterpret_cast<float*>(w2);
+      uint8_t* ws2 = w2 + ((64 * 64 * sizeof(float) + 255) & ~(size_t)255);
+      const size_t ws2_bytes = ws_bytes - im2col - ((64 * 64 * sizeof(float) + 255) & ~(size_t)255);
+      int rc = mc_conv_wgrad(cols, 64, 64, d_dz, 64, 64, B / 2, H, W, 1, nullptr, prod, 0, ws2, ws2_bytes, stream_);
+      if (rc) return rc;
+      const int J = C * 9;
+      wgrad_fold2_kernel<<<(O * J + 255) / 256, 256, 0, stream>>>(prod, d_mask, d_dw, O, J);
+      MC_LAUNCH_CHECK("wgrad_fold2_kernel");
+      return 0;
+    }
     return mc_conv_wgrad(cols, 32, C * 9, d_dz, ld_dz, O, B, H, W, 1, d_mask, d_dw, 0,
                          reinterpret_cast<uint8_t*>(d_ws) + im2col, ws_bytes - im2col, stream_);
   }
