@@ -178,7 +178,9 @@ int mc_bbox_ious(const float* d_boxes1, const float* d_boxes2, int64_t n, int x1
 enum { MC_EPI_PNHWC = 0,      /* bf16 PNHWC at the same resolution, channel offset ch_off, row pitch ldc   */
        MC_EPI_REORG2 = 1,     /* bf16 PNHWC at (H/2,W/2): channel ((y&1)*2+(x&1))*N + n + ch_off (Reorg)   */
        MC_EPI_NCHW_F32 = 2,   /* fp32 NCHW [B,N,H,W] (network head)                                        */
-       MC_EPI_POOL2 = 3,      /* bf16 PNHWC at (H/2,W/2) after 2x2/2 max-pool                              */
+       /* (3 is unused: a 2x2/2 max-pool is fused by the thin-layer kernels below, whose GEMM row is a pool window — */
+       /* mc_conv_im2col_fwd / mc_conv_window_fwd / mc_conv_thin_fwd with pool=1 —, not by this row-tiled kernel:  */
+       /* DESIGN.md §9)                                                                                            */
        MC_EPI_DECODE = 4 };   /* network head + region decode fused: see mc_decode_params                  */
 
 /* MC_EPI_DECODE — get_region_boxes (src/nets2_utils.py:158-205) applied to the head convolution's accumulators in its

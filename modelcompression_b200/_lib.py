@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmcb200.so")
 
 MC_MAX_SEGMENTS = 64
-MC_EPI_PNHWC, MC_EPI_REORG2, MC_EPI_NCHW_F32, MC_EPI_POOL2, MC_EPI_DECODE = 0, 1, 2, 3, 4
+MC_EPI_PNHWC, MC_EPI_REORG2, MC_EPI_NCHW_F32, MC_EPI_DECODE = 0, 1, 2, 4
 
 
 class McError(RuntimeError):
