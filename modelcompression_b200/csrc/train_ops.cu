@@ -707,10 +707,16 @@ inline int ilog2(int v) {
   return l;
 }
 
-inline int vec_blocks(long long total, int O8) {
+// items_per_thread > 1: kernels that end in per-block atomics (one per channel and block) want fewer, longer blocks on the
+// small layers — at 13x13x1024 the cap of 8 blocks per SM gave every thread 5 items and the grid 2.4 M atomics
+inline int vec_blocks(long long total, int O8, int items_per_thread = 1) {
   if (O8 <= 0 || (TB % O8) != 0 || (O8 & (O8 - 1)) != 0 || total >= (1ll << 31)) return 0;
-  long long blocks = (total + TB - 1) / TB;
+  long long blocks = (total + (long long)TB * items_per_thread - 1) / ((long long)TB * items_per_thread);
   const long long cap = (long long)mc_num_sms() * 8;
+  if (items_per_thread > 1 && blocks < 2ll * mc_num_sms()) {
+    blocks = (total + TB - 1) / TB;
+    if (blocks > 2ll * mc_num_sms()) blocks = 2ll * mc_num_sms();
+  }
   if (blocks > cap) blocks = cap;
   return (int)(blocks < 1 ? 1 : blocks);
 }
@@ -806,7 +812,8 @@ extern "C" int mc_bn_backward(const void* d_z, int ld_z, const void* d_da, int l
                       (((uintptr_t)d_z | (uintptr_t)d_da | (uintptr_t)d_dz) & 15) == 0;
   const int vb = vec_ok ? vec_blocks(rows * (C / 8), C / 8) : 0;
   if (vb > 0) {
-    bn_bwd_reduce_vec_kernel<<<vb, TB, 0, stream>>>((const __nv_bfloat16*)d_z, ld_z, (const __nv_bfloat16*)d_da, ld_da,
+    const int vbr = vec_blocks(rows * (C / 8), C / 8, 16);
+    bn_bwd_reduce_vec_kernel<<<vbr, TB, 0, stream>>>((const __nv_bfloat16*)d_z, ld_z, (const __nv_bfloat16*)d_da, ld_da,
                                                     ch_off, reorg, B, H, W, C, C / 8, d_mean, d_invstd, d_gamma, d_beta,
                                                     leaky, d_dbeta, d_dgamma, ilog2(C / 8), make_fastdiv(W + 1),
                                                     make_fastdiv(H + 1));
