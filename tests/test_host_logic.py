@@ -217,3 +217,45 @@ def test_bench_numa_binding_is_optional():
     if got is None:
         assert os.sched_getaffinity(0) == before
     os.sched_setaffinity(0, before)
+
+
+def test_thin_kernel_geometry_and_weight_layout():
+    """csrc/conv_thin.cu takes the degenerate layers of a filter-pruned net; which shapes it takes (a host-side rule of
+    the library: no GPU involved) and the kernel-parameter weight layout the engine builds for it."""
+    import ctypes
+    from modelcompression_b200 import _lib
+    from modelcompression_b200.engine import _thin_host_weights
+    lib = _lib.load()
+
+    def geom(k, cin, n, pool, n2):
+        ct, nt, n2t = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        ok = lib.mc_conv_thin_geometry(k, cin, n, pool, n2, ctypes.byref(ct), ctypes.byref(nt), ctypes.byref(n2t))
+        return (ct.value, nt.value, n2t.value) if ok == 1 else None
+
+    # the bench network's stem after 40 % filter pruning
+    assert geom(3, 4, 1, 1, 0) == (4, 1, 0)      # conv2 4 -> 1 + pool
+    assert geom(3, 1, 17, 0, 0) == (2, 20, 0)    # conv3 1 -> 17
+    assert geom(3, 1, 17, 0, 4) == (2, 20, 4)    # conv3 with conv4 behind it
+    assert geom(1, 17, 4, 0, 0) == (24, 4, 0)    # conv4 17 -> 4 (1x1)
+    assert geom(3, 4, 11, 1, 0) == (4, 12, 0)    # conv5 4 -> 11 + pool
+    # real contractions stay on the tensor cores
+    assert geom(3, 11, 78, 0, 0) is None         # conv6
+    assert geom(3, 8, 16, 0, 0) is None          # 9 * 8 * 16 multiply-adds per pixel: above the budget
+    assert geom(1, 78, 16, 0, 0) is None         # 1x1 with more than 32 inputs
+    assert geom(3, 5, 12, 1, 0) is None          # pooled: four positions per thread, budget 4x tighter
+    assert geom(1, 17, 4, 1, 0) is None          # no pooled 1x1
+    assert geom(3, 4, 30, 0, 0) is None          # more than 24 outputs
+
+    # weight layout [(tap*ct + c)*nt + n], bf16-rounded, zero padded; scale / shift padded to nt
+    torch.manual_seed(0)
+    wd = torch.randn(3, 2, 3, 3)
+    sc, sh = torch.rand(3) + 0.5, torch.randn(3)
+    hw, hsc, hsh = _thin_host_weights(wd, sc, sh, 4, 8)
+    w = np.array(list(hw), dtype=np.float32).reshape(9, 4, 8)
+    want = wd.to(torch.bfloat16).float().numpy()
+    for n in range(3):
+        for c in range(2):
+            assert np.array_equal(w[:, c, n], want[n, c].reshape(9))
+    assert not w[:, 2:, :].any() and not w[:, :, 3:].any()
+    assert np.allclose(np.array(list(hsc))[:3], sc.numpy()) and not np.array(list(hsc))[3:].any()
+    assert np.allclose(np.array(list(hsh))[:3], sh.numpy()) and not np.array(list(hsh))[3:].any()
